@@ -1,0 +1,321 @@
+"""Host side of the contrastive (InfoNCE) + teacher/student logit-KL path.
+
+Two entry levels, both backed only by the CUDA library (no eager fallback):
+
+* `clip_contrastive(...)` -- the fused path used by `LossCalculator.cal_tow_tower_loss`: losses and gradients
+  straight from the embeddings (`last_representation`), the B x B logits never exist in HBM.  It replaces
+  `CLIPModel.forward`'s normalise + matmul (reference model/component/clip_model.py:36-44), `HardLabel`
+  (model/loss_component/hard_label.py:10-12), `SoftLabel` (soft_label.py:11-16) and the 0.5*(i2t+t2i) sums of
+  model/_loss.py:130-137.  With a process group it is row-sharded: every rank owns B/R rows of each embedding
+  matrix, all-gathers the opposite side, and computes its row slice of the global logits (labels are the global
+  row indices) and the gradients of its own rows; see DESIGN.md section "multi-GPU".
+
+* `hard_label_from_logits / soft_label_from_logits` -- the per-module API on materialised logits (including the
+  `.T` view), for callers that use `HardLabel` / `SoftLabel` directly.
+
+The sharding / collective logic is written against a small "engine" interface so that it can be exercised on CPU
+(gloo, world_size 2) with a test double; the product engine is `CudaEngine` below.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional, Sequence
+
+import torch
+
+from . import _lib, ops
+
+MIN_FUSED_TEMPERATURE = 0.025       # exp((S-1)/T) with S in [-1, 1] stays a normal fp32 number above this
+_HALF = (torch.bfloat16, torch.float16)
+
+
+def _vp(t: Optional[torch.Tensor]):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+# ==============================================================================================
+# engine: one call per kernel family of the C ABI
+# ==============================================================================================
+class CudaEngine:
+    """Thin, stateless wrapper over the C ABI (include/distillclip_b200.h)."""
+
+    def inv_norms(self, mats: Sequence[torch.Tensor]):
+        outs = [torch.empty(m.shape[0], dtype=torch.float32, device=m.device) for m in mats]
+        _lib.call("dcb_row_inv_norm", len(mats), _lib.ptr_array([m.data_ptr() for m in mats]),
+                  _lib.ptr_array([o.data_ptr() for o in outs]), _lib.i64_array([m.shape[0] for m in mats]),
+                  mats[0].shape[1], ops.dtype_code(mats[0]), ops._stream_ptr())
+        return outs
+
+    def row_stats(self, a_s, b_s, a_t, b_t, a_s_inv, b_s_inv, a_t_inv, b_t_inv, row_offset, temperature,
+                  dump=None):
+        rows, dim = a_s.shape
+        cols = b_s.shape[0]
+        stats = torch.empty(5, rows, dtype=torch.float32, device=a_s.device)
+        ws = torch.empty(max(1, _lib.load().dcb_clip_workspace_bytes(rows, cols)), dtype=torch.uint8, device=a_s.device)
+        _lib.call("dcb_clip_row_stats", _vp(a_s), _vp(b_s), _vp(a_t), _vp(b_t), _vp(a_s_inv), _vp(b_s_inv),
+                  _vp(a_t_inv), _vp(b_t_inv), rows, int(row_offset), cols, dim, ops.dtype_code(a_s),
+                  float(temperature or 1.0), _vp(stats), _vp(ws), _vp(dump[0]) if dump else None,
+                  _vp(dump[1]) if dump and a_t is not None else None, ops._stream_ptr())
+        return stats
+
+    def losses(self, stats_i2t, stats_t2i, global_batch, temperature, has_teacher):
+        dev = stats_i2t.device
+        sums = torch.empty(4, dtype=torch.float64, device=dev)
+        out = torch.empty(2, dtype=torch.float32, device=dev)
+        _lib.call("dcb_clip_losses", _vp(stats_i2t), _vp(stats_t2i), stats_i2t.shape[1], stats_t2i.shape[1],
+                  int(global_batch), float(temperature or 1.0), int(has_teacher), _vp(sums), _vp(out), ops._stream_ptr())
+        return sums, out
+
+    def coef(self, stats, global_batch, temperature, has_teacher, upstream):
+        rows = stats.shape[1]
+        coef = torch.empty(3, rows, dtype=torch.float32, device=stats.device)
+        _lib.call("dcb_clip_grad_coef", _vp(stats), rows, int(global_batch), float(temperature or 1.0),
+                  int(has_teacher), _vp(upstream), _vp(coef), ops._stream_ptr())
+        return coef
+
+    def transpose_bf16(self, b):
+        rows, dim = b.shape
+        pitch = (rows + 7) // 8 * 8
+        out = torch.empty(dim, pitch, dtype=torch.bfloat16, device=b.device)
+        _lib.call("dcb_transpose_to_bf16", _vp(b), _vp(out), rows, dim, pitch, ops.dtype_code(b), ops._stream_ptr())
+        return out
+
+    def row_grads(self, a_s, b_s, a_t, b_t, b_s_t, a_s_inv, b_s_inv, a_t_inv, b_t_inv, coef_row, coef_col,
+                  row_offset, global_batch, temperature, upstream, grad_dtype):
+        rows, dim = a_s.shape
+        cols = b_s.shape[0]
+        lib = _lib.load()
+        n_split = lib.dcb_clip_grad_splits(rows, cols, dim)
+        acc = torch.empty(n_split, rows, dim, dtype=torch.float32, device=a_s.device)
+        _lib.call("dcb_clip_row_grads", _vp(a_s), _vp(b_s), _vp(a_t), _vp(b_t), _vp(b_s_t), b_s_t.shape[1],
+                  _vp(a_s_inv), _vp(b_s_inv), _vp(a_t_inv), _vp(b_t_inv), _vp(coef_row), _vp(coef_col),
+                  rows, cols, dim, ops.dtype_code(a_s), float(temperature or 1.0), _vp(acc), ops._stream_ptr())
+        grad = torch.empty(rows, dim, dtype=grad_dtype, device=a_s.device)
+        _lib.call("dcb_clip_grad_finish", _vp(acc), n_split, _vp(a_s), _vp(a_s_inv), _vp(b_s), _vp(b_s_inv), rows, cols,
+                  dim, int(row_offset), int(global_batch), _vp(upstream), ops.dtype_code(a_s), _vp(grad),
+                  ops._DT[grad_dtype], ops._stream_ptr())
+        return grad
+
+
+# ==============================================================================================
+# sharding logic (engine-agnostic; collectives through torch.distributed)
+# ==============================================================================================
+def _shard_info(group):
+    """-> (rank, world). group=None means "not sharded" even if torch.distributed is initialised."""
+    if group is None:
+        return 0, 1
+    import torch.distributed as dist
+    return dist.get_rank(group), dist.get_world_size(group)
+
+
+def _all_gather_rows(x: torch.Tensor, group, world: int) -> torch.Tensor:
+    """[n, ...] per rank -> [world * n, ...] in rank order (equal n on every rank)."""
+    if world == 1:
+        return x
+    import torch.distributed as dist
+    out = torch.empty((world * x.shape[0],) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+    dist.all_gather_into_tensor(out, x.contiguous(), group=group)
+    return out
+
+
+def _all_gather_cols(x: torch.Tensor, group, world: int) -> torch.Tensor:
+    """[k, n] per rank -> [k, world * n]."""
+    if world == 1:
+        return x
+    g = _all_gather_rows(x.t().contiguous(), group, world)
+    return g.t().contiguous()
+
+
+def contrastive_forward(engine, si, st, ti, tt, temperature, group=None):
+    """Row statistics + loss values.  si/st/ti/tt: this rank's rows [B_local, D] (tt/ti None = hard label only).
+    Returns (out[2] = {hard, soft} for the GLOBAL batch, saved state for the backward)."""
+    rank, world = _shard_info(group)
+    has_teacher = ti is not None
+    b_local = si.shape[0]
+    b_global = b_local * world
+    offset = rank * b_local
+    # exchange step: every rank needs all rows of the opposite modality (student and teacher)
+    si_all, st_all = _all_gather_rows(si, group, world), _all_gather_rows(st, group, world)
+    ti_all = _all_gather_rows(ti, group, world) if has_teacher else None
+    tt_all = _all_gather_rows(tt, group, world) if has_teacher else None
+    mats = [si_all, st_all] + ([ti_all, tt_all] if has_teacher else [])
+    inv = engine.inv_norms(mats)
+    si_inv_all, st_inv_all = inv[0], inv[1]
+    ti_inv_all, tt_inv_all = (inv[2], inv[3]) if has_teacher else (None, None)
+    loc = slice(offset, offset + b_local)
+
+    def local(x):
+        return None if x is None else x[loc]
+    # i2t rows: a = image, b = text ; t2i rows: a = text, b = image
+    stats_i2t = engine.row_stats(si, st_all, ti, tt_all, local(si_inv_all), st_inv_all, local(ti_inv_all), tt_inv_all,
+                                 offset, temperature)
+    stats_t2i = engine.row_stats(st, si_all, tt, ti_all, local(st_inv_all), si_inv_all, local(tt_inv_all), ti_inv_all,
+                                 offset, temperature)
+    sums, out = engine.losses(stats_i2t, stats_t2i, b_global, temperature, has_teacher)
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(sums, group=group)
+        out = torch.stack([0.5 * (sums[0] + sums[1]) / b_global, 0.5 * (sums[2] + sums[3])]).to(torch.float32)
+    saved = dict(si=si, st=st, ti=ti, tt=tt, si_all=si_all, st_all=st_all, ti_all=ti_all, tt_all=tt_all,
+                 si_inv_all=si_inv_all, st_inv_all=st_inv_all, ti_inv_all=ti_inv_all, tt_inv_all=tt_inv_all,
+                 stats_i2t=stats_i2t, stats_t2i=stats_t2i, offset=offset, b_global=b_global, world=world,
+                 group=group, temperature=temperature, has_teacher=has_teacher)
+    return out, saved
+
+
+def contrastive_backward(engine, saved, upstream, want_img=True, want_txt=True, grad_dtype=None):
+    """upstream: device float32[2] = {d total/d hard, d total/d soft}.  Returns (grad_si, grad_st) for the local rows."""
+    s = saved
+    world, group = s["world"], s["group"]
+    b_global, T, has_teacher, offset = s["b_global"], s["temperature"], s["has_teacher"], s["offset"]
+    b_local = s["si"].shape[0]
+    loc = slice(offset, offset + b_local)
+    # column softmax statistics of a direction = row statistics of the opposite direction, for ALL rows
+    stats_i2t_all = _all_gather_cols(s["stats_i2t"], group, world)
+    stats_t2i_all = _all_gather_cols(s["stats_t2i"], group, world)
+    coef_i2t_all = engine.coef(stats_i2t_all, b_global, T, has_teacher, upstream)
+    coef_t2i_all = engine.coef(stats_t2i_all, b_global, T, has_teacher, upstream)
+    coef_i2t = coef_i2t_all[:, loc].contiguous() if world > 1 else coef_i2t_all
+    coef_t2i = coef_t2i_all[:, loc].contiguous() if world > 1 else coef_t2i_all
+
+    def local(x):
+        return None if x is None else x[loc]
+    g_img = g_txt = None
+    if want_img:
+        g_img = engine.row_grads(s["si"], s["st_all"], s["ti"], s["tt_all"], engine.transpose_bf16(s["st_all"]),
+                                 local(s["si_inv_all"]), s["st_inv_all"], local(s["ti_inv_all"]), s["tt_inv_all"],
+                                 coef_i2t, coef_t2i_all, offset, b_global, T, upstream, grad_dtype or s["si"].dtype)
+    if want_txt:
+        g_txt = engine.row_grads(s["st"], s["si_all"], s["tt"], s["ti_all"], engine.transpose_bf16(s["si_all"]),
+                                 local(s["st_inv_all"]), s["si_inv_all"], local(s["tt_inv_all"]), s["ti_inv_all"],
+                                 coef_t2i, coef_i2t_all, offset, b_global, T, upstream, grad_dtype or s["st"].dtype)
+    return g_img, g_txt
+
+
+# ==============================================================================================
+# autograd
+# ==============================================================================================
+_ENGINE = CudaEngine()
+
+
+class ClipContrastiveFn(torch.autograd.Function):
+    """(stu_img, stu_txt, tea_img, tea_txt) -> (hard, soft): 0.5*(i2t + t2i) of CrossEntropy(mean) and of
+    T^2 KL(sum) (reference _loss.py:130-137), global batch when `group` is given."""
+
+    @staticmethod
+    def forward(ctx, si, st, ti, tt, temperature, group):
+        out, saved = contrastive_forward(_ENGINE, si, st, ti, tt, temperature, group)
+        ctx.saved = saved
+        ctx.set_materialize_grads(False)
+        return out[0], out[1]
+
+    @staticmethod
+    def backward(ctx, g_hard, g_soft):
+        dev = ctx.saved["si"].device
+        zero = torch.zeros((), dtype=torch.float32, device=dev)
+        up = torch.stack([(g_hard if g_hard is not None else zero).to(torch.float32).reshape(()),
+                          (g_soft if g_soft is not None else zero).to(torch.float32).reshape(())]).contiguous()
+        g_img, g_txt = contrastive_backward(_ENGINE, ctx.saved, up, ctx.needs_input_grad[0], ctx.needs_input_grad[1])
+        return g_img, g_txt, None, None, None, None
+
+
+def fused_supported(stu_img: torch.Tensor, stu_txt: torch.Tensor, temperature=None) -> bool:
+    """The tcgen05 path takes bf16/fp16 [B, D] embeddings with D % 8 == 0 and T >= MIN_FUSED_TEMPERATURE."""
+    ok = (stu_img.is_cuda and stu_img.dim() == 2 and stu_img.shape == stu_txt.shape and stu_img.dtype in _HALF
+          and stu_txt.dtype == stu_img.dtype and stu_img.shape[1] % 8 == 0)
+    if temperature is not None:
+        ok = ok and float(temperature) >= MIN_FUSED_TEMPERATURE
+    return bool(ok)
+
+
+def _prep(x: Optional[torch.Tensor], dtype, what: str):
+    if x is None:
+        return None
+    ops._require_cuda(x, what)
+    if x.dtype != dtype:
+        x = x.to(dtype)
+    return x if x.is_contiguous() else x.contiguous()
+
+
+def clip_contrastive(stu_img, stu_txt, tea_img=None, tea_txt=None, temperature=None, want_hard=True,
+                     want_soft=False, group=None) -> Dict[str, torch.Tensor]:
+    """Fused hard-label / soft-label losses from embeddings.  Returns {'hard_label': ..., 'soft_label': ...}
+    (only the requested keys); values are 0-dim fp32 tensors on the autograd graph of the student embeddings."""
+    if not fused_supported(stu_img, stu_txt, temperature if want_soft else None):
+        raise _lib.DistillClipB200Error(
+            "fused contrastive path needs CUDA bf16/fp16 [B, D] embeddings with D % 8 == 0 and "
+            f"temperature >= {MIN_FUSED_TEMPERATURE}; use HardLabel / SoftLabel on logits otherwise")
+    dt = stu_img.dtype
+    si, st = _prep(stu_img, dt, "student image embedding"), _prep(stu_txt, dt, "student text embedding")
+    ti = tt = None
+    if want_soft:
+        if tea_img is None or tea_txt is None:
+            raise ValueError("soft_label needs the teacher embeddings")
+        ti, tt = _prep(tea_img.detach(), dt, "teacher image embedding"), _prep(tea_txt.detach(), dt, "teacher text embedding")
+        if ti.shape != si.shape or tt.shape != st.shape:
+            raise ValueError("teacher and student embeddings must have the same [B, D] shape on the fused path "
+                             f"(student {tuple(si.shape)}, teacher {tuple(ti.shape)})")
+    hard, soft = ClipContrastiveFn.apply(si, st, ti, tt, float(temperature) if want_soft else None, group)
+    res = {}
+    if want_hard:
+        res["hard_label"] = hard
+    if want_soft:
+        res["soft_label"] = soft
+    return res
+
+
+# ==============================================================================================
+# per-module API on materialised logits
+# ==============================================================================================
+class LogitsLossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, stu, tea, temperature, mode):
+        n = stu.shape[0]
+        dev = stu.device
+        saved = torch.empty(n, 4, dtype=torch.float32, device=dev)
+        rowloss = torch.empty(n, dtype=torch.float64, device=dev)
+        _lib.call("dcb_logits_row_stats", _vp(stu), stu.stride(0), stu.stride(1), _vp(tea),
+                  tea.stride(0) if tea is not None else 0, tea.stride(1) if tea is not None else 0, n,
+                  ops.dtype_code(stu), float(temperature or 1.0), mode, _vp(saved), _vp(rowloss), ops._stream_ptr())
+        scale = float(temperature) ** 2 if mode == 1 else 1.0 / n
+        out = ops.finalize([(rowloss, n)], [scale], [1.0])
+        ctx.save_for_backward(stu, tea if tea is not None else stu, saved)
+        ctx.meta = (temperature, mode, tea is not None)
+        return out[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        stu, tea, saved = ctx.saved_tensors
+        temperature, mode, has_tea = ctx.meta
+        n = stu.shape[0]
+        up = g.to(torch.float32).reshape(1).contiguous()
+        grad = torch.empty(n, n, dtype=stu.dtype, device=stu.device)
+        _lib.call("dcb_logits_row_grads", _vp(stu), stu.stride(0), stu.stride(1), _vp(tea) if has_tea else None,
+                  tea.stride(0) if has_tea else 0, tea.stride(1) if has_tea else 0, n, ops.dtype_code(stu),
+                  float(temperature or 1.0), mode, _vp(saved), _vp(up), _vp(grad), ops._DT[grad.dtype],
+                  ops._stream_ptr())
+        return grad, None, None, None
+
+
+def _check_logits(x: torch.Tensor, what: str):
+    ops._require_cuda(x, what)
+    ops.dtype_code(x)
+    if x.dim() != 2 or x.shape[0] != x.shape[1]:
+        raise ValueError(f"{what} must be a square [B, B] matrix, got {tuple(x.shape)}")
+
+
+def hard_label_from_logits(stu_logits: torch.Tensor) -> torch.Tensor:
+    """CrossEntropy(mean)(logits, arange(B)) -- reference hard_label.py:10-12.  Strided views are read in place."""
+    _check_logits(stu_logits, "stu_logits")
+    return LogitsLossFn.apply(stu_logits, None, None, 0)
+
+
+def soft_label_from_logits(stu_logits: torch.Tensor, tea_logits: torch.Tensor, temperature) -> torch.Tensor:
+    """KLDiv(sum)(softmax(stu/T).log(), softmax(tea/T)) * T^2 -- reference soft_label.py:11-16."""
+    _check_logits(stu_logits, "stu_logits")
+    _check_logits(tea_logits, "tea_logits")
+    if tea_logits.shape != stu_logits.shape:
+        raise ValueError("student and teacher logits must have the same shape")
+    if tea_logits.dtype != stu_logits.dtype:
+        tea_logits = tea_logits.to(stu_logits.dtype)
+    return LogitsLossFn.apply(stu_logits, tea_logits.detach(), float(temperature), 1)

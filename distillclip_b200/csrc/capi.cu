@@ -1,0 +1,125 @@
+// C-ABI glue that is not tied to one loss family: error buffer, version, deterministic finalize,
+// and the backward-time gradient rescale.
+#include "common.cuh"
+
+namespace dcb {
+
+char* error_buffer() {
+    static thread_local char buf[512] = {0};
+    return buf;
+}
+
+// ---------------------------------------------------------------------------------------------
+// finalize: out[k] = scale[k] * sum(partials[k]) ; out[n] = sum_k percent[k] * out[k]
+// (reference model/_loss.py:195-200 -- `cal_res[n] * scale` then `loss += cal_res[n] * percent[n]`)
+// One CTA; partials are summed in index order with a fixed tree, so the result is run-to-run identical.
+// ---------------------------------------------------------------------------------------------
+struct FinalizeParams {
+    int n_terms;
+    const double* partials[DCB_MAX_TERMS];
+    int counts[DCB_MAX_TERMS];
+    float scale[DCB_MAX_TERMS];
+    float percent[DCB_MAX_TERMS];
+};
+
+__global__ void __launch_bounds__(256) finalize_kernel(const __grid_constant__ FinalizeParams p,
+                                                       float* __restrict__ out) {
+    __shared__ double term_sum[DCB_MAX_TERMS];
+    for (int k = 0; k < p.n_terms; ++k) {
+        double v = 0.0;
+        for (int i = threadIdx.x; i < p.counts[k]; i += blockDim.x) v += p.partials[k][i];
+        v = block_sum(v);
+        if (threadIdx.x == 0) term_sum[k] = v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        float total = 0.f;
+        for (int k = 0; k < p.n_terms; ++k) {
+            // same rounding points as the reference: fp32 value, * scale, * percent, += in fp32
+            const float res = (float)term_sum[k] * p.scale[k];
+            out[k] = res;
+            total += res * p.percent[k];
+        }
+        out[p.n_terms] = total;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// rescale: grads[k] *= (*upstream[k]) / expected[k], skipped entirely when equal.
+// ---------------------------------------------------------------------------------------------
+struct RescaleSeg {
+    void* g;
+    long long n;
+    const float* upstream;
+    float expected;
+};
+struct RescaleParams {
+    int n_seg;
+    RescaleSeg seg[2 * DCB_MAX_LAYERS];
+};
+
+template <typename G>
+__global__ void __launch_bounds__(256) rescale_kernel(const __grid_constant__ RescaleParams p) {
+    const int k = blockIdx.y;
+    if (k >= p.n_seg) return;
+    const float up = __ldg(p.seg[k].upstream);
+    const float expected = p.seg[k].expected;
+    if (up == expected) return;                       // common case: nothing to do, no HBM traffic
+    const float f = up / expected;
+    G* __restrict__ g = static_cast<G*>(p.seg[k].g);
+    const long long n = p.seg[k].n;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        g[i] = Elem<G>::from_f(Elem<G>::to_f(g[i]) * f);
+}
+
+}  // namespace dcb
+
+extern "C" {
+
+int dcb_version(void) { return 100; }
+int dcb_compiled_arch(void) { return 100; }
+const char* dcb_last_error(void) { return dcb::error_buffer(); }
+
+int dcb_finalize(int n_terms, const double* const* partials, const int32_t* counts, const float* scale,
+                 const float* percent, float* out, void* stream) {
+    using namespace dcb;
+    DCB_REQUIRE(n_terms >= 1 && n_terms <= DCB_MAX_TERMS, "n_terms=%d out of range [1,%d]", n_terms, DCB_MAX_TERMS);
+    DCB_REQUIRE(out, "out must not be NULL");
+    FinalizeParams p{};
+    p.n_terms = n_terms;
+    for (int k = 0; k < n_terms; ++k) {
+        DCB_REQUIRE(partials[k] && counts[k] >= 0, "term %d: bad partials", k);
+        p.partials[k] = partials[k];
+        p.counts[k] = counts[k];
+        p.scale[k] = scale ? scale[k] : 1.f;
+        p.percent[k] = percent ? percent[k] : 0.f;
+    }
+    finalize_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(p, out);
+    DCB_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int dcb_rescale_grads(int n_seg, void* const* grads, const int64_t* numel, int dtype,
+                      const float* const* upstream, const float* expected, void* stream) {
+    using namespace dcb;
+    DCB_REQUIRE(n_seg >= 1 && n_seg <= 2 * DCB_MAX_LAYERS, "n_seg=%d out of range", n_seg);
+    RescaleParams p{};
+    p.n_seg = n_seg;
+    for (int k = 0; k < n_seg; ++k) {
+        DCB_REQUIRE(grads[k] && upstream[k], "segment %d: NULL pointer", k);
+        DCB_REQUIRE(expected[k] != 0.f, "segment %d: expected upstream gradient must be non-zero", k);
+        p.seg[k] = RescaleSeg{grads[k], (long long)numel[k], upstream[k], expected[k]};
+    }
+    dim3 grid(kNumSMs * 4, n_seg);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    switch (dtype) {
+        case DCB_BF16: rescale_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(p); break;
+        case DCB_F16: rescale_kernel<__half><<<grid, 256, 0, st>>>(p); break;
+        case DCB_F32: rescale_kernel<float><<<grid, 256, 0, st>>>(p); break;
+        default: return fail("unknown dtype %d", dtype);
+    }
+    DCB_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+}  // extern "C"

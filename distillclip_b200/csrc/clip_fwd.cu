@@ -1,0 +1,338 @@
+// Fused similarity GEMM + softmax statistics for one direction of the CLIP contrastive / logit-KL losses.
+//
+// Replaces, without ever writing the B x B logits to HBM:
+//   CLIPModel.forward's L2-normalise + `image_feature @ text_feature.t()`   (reference model/component/clip_model.py:36-44)
+//   HardLabel.forward   CrossEntropy(mean) vs arange(B)                      (reference model/loss_component/hard_label.py:10-12)
+//   SoftLabel.forward   softmax(./T), .log(), KLDiv(sum) * T^2               (reference model/loss_component/soft_label.py:11-16)
+//
+// One CTA owns a block of 128 "a-side" rows and walks a range of 128-wide "b-side" column tiles.  Per tile the
+// raw bf16/fp16 embeddings stream through a TMA -> shared-memory ring (64-wide K chunks, 128 B swizzle) into
+// tcgen05.mma (M=128, N=128, K=16) with the student and the teacher similarity accumulators side by side in
+// TMEM, double-buffered (2 x (128 + 128) = 512 columns) so the MMAs of tile n+1 overlap the epilogue of tile n.
+// The epilogue warps read the accumulators with tcgen05.ld (one row per thread), apply the fp32 inverse norms
+// (logit = acc * r_i * c_j, so normalised embeddings are never rounded to bf16) and accumulate per row
+//   A  = sum_j exp(S_ij - 1)            Zs = sum_j exp((S_ij - 1)/T)
+//   Zt = sum_j exp((T_ij - 1)/T)        W  = sum_j exp((T_ij - 1)/T) (T_ij - S_ij)        and S_ii.
+// Cosine logits are bounded by 1, so 1 is a valid softmax shift for every row: the sums of different column
+// ranges simply add (no running max, no rescaling), which is what lets a row be split over CTAs and ranks.
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2-5 = epilogue.
+#include "tc_common.cuh"
+
+namespace dcb {
+
+namespace fwd {
+constexpr int kBM = 128, kBN = 128, kBK = 64, kUmmaK = 16;
+constexpr int kStages = 3;
+constexpr int kTileBytes = kBM * kBK * 2;                 // 16 KiB: one [128 x 64] 16-bit operand tile
+constexpr int kStageBytes = 4 * kTileBytes;               // a_stu, b_stu, a_tea, b_tea
+constexpr int kThreads = 192;
+constexpr int kTmemCols = 512;
+constexpr int kSmemBytes = 1024 /*align slack*/ + kStages * kStageBytes + 2 * 2 * kBN * 4 + 256;
+}  // namespace fwd
+
+struct ClipFwdParams {
+    const float* a_inv_stu;   // [rows]   1/||a_i||  student
+    const float* b_inv_stu;   // [cols]
+    const float* a_inv_tea;
+    const float* b_inv_tea;
+    float* ws;                // [n_split][4][rows] partial sums
+    float* diag;              // [rows] S_ii
+    float* dump_s;            // optional [rows, cols] raw logits (tests only), else nullptr
+    float* dump_t;
+    int rows, cols, dim;
+    int row_offset;           // global index of local row 0 (labels = arange(B): the diagonal is global)
+    int n_split, col_tiles;
+    float inv_temp;           // 1/T
+};
+
+__device__ __forceinline__ float ex2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+template <bool kTeacher>
+__global__ void __launch_bounds__(fwd::kThreads, 1)
+clip_fwd_kernel(const __grid_constant__ CUtensorMap map_a_stu, const __grid_constant__ CUtensorMap map_b_stu,
+                const __grid_constant__ CUtensorMap map_a_tea, const __grid_constant__ CUtensorMap map_b_tea,
+                const __grid_constant__ ClipFwdParams p, const uint32_t idesc) {
+    using namespace fwd;
+    using namespace tc;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+    const uint32_t ring = smem_base;
+    float* scale_buf = reinterpret_cast<float*>(smem_gen + kStages * kStageBytes);   // [2 buf][2 stu/tea][128]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_gen + kStages * kStageBytes + 2 * 2 * kBN * 4);
+    const uint32_t bar_full = smem_u32(bars);                   // [kStages]
+    const uint32_t bar_empty = bar_full + 8 * kStages;          // [kStages]
+    const uint32_t bar_tfull = bar_empty + 8 * kStages;         // [2]
+    const uint32_t bar_tempty = bar_tfull + 16;                 // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int rb = blockIdx.x / p.n_split, sp = blockIdx.x % p.n_split;
+    const int tile_begin = (int)(((long long)sp * p.col_tiles) / p.n_split);
+    const int tile_end = (int)(((long long)(sp + 1) * p.col_tiles) / p.n_split);
+    const int n_tiles = tile_end - tile_begin;
+    const int n_kc = (p.dim + kBK - 1) / kBK;
+    const int row0 = rb * kBM;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(bar_full + 8 * s, 1);
+            mbar_init(bar_empty + 8 * s, 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(bar_tfull + 8 * s, 1);
+            mbar_init(bar_tempty + 8 * s, 4);     // one arrive per epilogue warp
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(smem_u32(tmem_slot), kTmemCols);
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ---------------------------------------------------------------- TMA producer
+        if (lane == 0) {
+            tma_prefetch_desc(&map_a_stu);
+            tma_prefetch_desc(&map_b_stu);
+            if (kTeacher) {
+                tma_prefetch_desc(&map_a_tea);
+                tma_prefetch_desc(&map_b_tea);
+            }
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int t = 0; t < n_tiles; ++t) {
+                const int col0 = (tile_begin + t) * kBN;
+                for (int kc = 0; kc < n_kc; ++kc) {
+                    mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+                    const uint32_t dst = ring + stage * kStageBytes;
+                    const uint32_t full = bar_full + 8 * stage;
+                    mbar_arrive_expect_tx(full, (kTeacher ? 4 : 2) * kTileBytes);
+                    tma_load_2d(dst, &map_a_stu, full, kc * kBK, row0);
+                    tma_load_2d(dst + kTileBytes, &map_b_stu, full, kc * kBK, col0);
+                    if (kTeacher) {
+                        tma_load_2d(dst + 2 * kTileBytes, &map_a_tea, full, kc * kBK, row0);
+                        tma_load_2d(dst + 3 * kTileBytes, &map_b_tea, full, kc * kBK, col0);
+                    }
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ---------------------------------------------------------------- MMA issuer (one thread)
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int t = 0; t < n_tiles; ++t) {
+                const int as = t & 1;                       // accumulator stage
+                const uint32_t aphase = (t >> 1) & 1;
+                mbar_wait(bar_tempty + 8 * as, aphase ^ 1);
+                tc_fence_after_sync();
+                const uint32_t acc_s = tmem_base + as * 256;
+                const uint32_t acc_t = acc_s + 128;
+                for (int kc = 0; kc < n_kc; ++kc) {
+                    mbar_wait(bar_full + 8 * stage, phase);
+                    tc_fence_after_sync();
+                    const uint32_t src = ring + stage * kStageBytes;
+                    const uint64_t da_s = umma_desc_k_sw128(src), db_s = umma_desc_k_sw128(src + kTileBytes);
+                    const uint64_t da_t = umma_desc_k_sw128(src + 2 * kTileBytes), db_t = umma_desc_k_sw128(src + 3 * kTileBytes);
+#pragma unroll
+                    for (int k = 0; k < kBK / kUmmaK; ++k) {
+                        const uint32_t accum = (kc > 0 || k > 0) ? 1u : 0u;
+                        umma_f16(acc_s, da_s + 2 * k, db_s + 2 * k, idesc, accum);     // +32 B per K=16 step
+                        if (kTeacher) umma_f16(acc_t, da_t + 2 * k, db_t + 2 * k, idesc, accum);
+                    }
+                    umma_commit(bar_empty + 8 * stage);     // frees the smem slot once these MMAs retire
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(bar_tfull + 8 * as);            // accumulators of this tile are complete
+            }
+        }
+    } else {
+        // ---------------------------------------------------------------- epilogue: 4 warps, one row per thread
+        const int q = warp & 3;                             // TMEM lane quadrant this warp may read
+        const int r = q * 32 + lane;                        // row inside the block
+        const int ep_tid = r;                               // 0..127, also used to stage column scales
+        const int grow = row0 + r;                          // local row
+        const bool row_ok = grow < p.rows;
+        const float LOG2E = 1.4426950408889634f;
+        const float r_s = row_ok ? __ldg(p.a_inv_stu + grow) : 0.f;
+        const float r_t = (kTeacher && row_ok) ? __ldg(p.a_inv_tea + grow) : 0.f;
+        const float k1 = r_s * LOG2E, k1t = r_s * LOG2E * p.inv_temp, k2t = r_t * LOG2E * p.inv_temp;
+        const float n1 = -LOG2E, n1t = -LOG2E * p.inv_temp;
+        const int diag_col = p.row_offset + grow;           // global column holding this row's label
+        float A = 0.f, Zs = 0.f, Zt = 0.f, W = 0.f, diag = 0.f;
+        bool have_diag = false;
+        for (int t = 0; t < n_tiles; ++t) {
+            const int as = t & 1;
+            const uint32_t aphase = (t >> 1) & 1;
+            const int col0 = (tile_begin + t) * kBN;
+            float* sc = scale_buf + as * 2 * kBN;           // [stu 128][tea 128]
+            {
+                const int c = col0 + ep_tid;
+                sc[ep_tid] = c < p.cols ? __ldg(p.b_inv_stu + c) : 0.f;
+                if (kTeacher) sc[kBN + ep_tid] = c < p.cols ? __ldg(p.b_inv_tea + c) : 0.f;
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            mbar_wait(bar_tfull + 8 * as, aphase);
+            tc_fence_after_sync();
+            const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * 256;
+            const bool edge = (col0 + kBN > p.cols) || (diag_col >= col0 && diag_col < col0 + kBN) ||
+                              (p.dump_s != nullptr);
+#pragma unroll 1
+            for (int ch = 0; ch < kBN / 32; ++ch) {
+                float sv[32], tv[32];
+                tmem_ld_32x32(lane_addr + ch * 32, sv);
+                if (kTeacher) tmem_ld_32x32(lane_addr + 128 + ch * 32, tv);
+                tmem_ld_wait();
+                const float* scs = sc + ch * 32;
+                const float* sct = sc + kBN + ch * 32;
+                if (!edge) {
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) {
+                        const float u = sv[c] * scs[c];
+                        A += ex2(fmaf(u, k1, n1));
+                        if (kTeacher) {
+                            const float v = tv[c] * sct[c];
+                            const float et = ex2(fmaf(v, k2t, n1t));
+                            Zs += ex2(fmaf(u, k1t, n1t));
+                            Zt += et;
+                            W = fmaf(et, fmaf(v, r_t, -(u * r_s)), W);
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) {
+                        const int gc = col0 + ch * 32 + c;
+                        const bool ok = gc < p.cols;
+                        const float u = sv[c] * scs[c];
+                        const float s = u * r_s;
+                        if (gc == diag_col) { diag = s; have_diag = true; }
+                        A += ok ? ex2(fmaf(u, k1, n1)) : 0.f;
+                        if (p.dump_s && row_ok && ok) p.dump_s[(size_t)grow * p.cols + gc] = s;
+                        if (kTeacher) {
+                            const float v = tv[c] * sct[c];
+                            const float tt = v * r_t;
+                            const float et = ok ? ex2(fmaf(v, k2t, n1t)) : 0.f;
+                            Zs += ok ? ex2(fmaf(u, k1t, n1t)) : 0.f;
+                            Zt += et;
+                            W = fmaf(et, tt - s, W);
+                            if (p.dump_t && row_ok && ok) p.dump_t[(size_t)grow * p.cols + gc] = tt;
+                        }
+                    }
+                }
+            }
+            tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_tempty + 8 * as);
+        }
+        if (row_ok) {
+            float* w = p.ws + (size_t)sp * 4 * p.rows + grow;
+            w[0] = A;
+            w[(size_t)p.rows] = Zs;
+            w[(size_t)2 * p.rows] = Zt;
+            w[(size_t)3 * p.rows] = W;
+            if (have_diag) p.diag[grow] = diag;
+        }
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after_sync();
+        tc::tmem_dealloc(tmem_base, kTmemCols);
+    }
+}
+
+// stats[k][r] = sum over splits (fixed order -> deterministic), stats[4][r] = S_rr
+__global__ void __launch_bounds__(256) clip_combine_kernel(const float* __restrict__ ws, const float* __restrict__ diag,
+                                                           float* __restrict__ stats, int rows, int n_split) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 4 * rows) return;
+    float v = 0.f;
+    for (int s = 0; s < n_split; ++s) v += ws[(size_t)s * 4 * rows + i];
+    stats[i] = v;
+    if (i < rows) stats[(size_t)4 * rows + i] = diag[i];
+}
+
+static int clip_fwd_splits(int64_t rows, int64_t cols) {
+    const int64_t row_blocks = (rows + fwd::kBM - 1) / fwd::kBM;
+    const int64_t col_tiles = (cols + fwd::kBN - 1) / fwd::kBN;
+    int64_t n = (2 * kNumSMs + row_blocks - 1) / row_blocks;     // aim for >= 2 CTAs per SM worth of work items
+    if (n > col_tiles) n = col_tiles;
+    if (n < 1) n = 1;
+    return (int)n;
+}
+
+}  // namespace dcb
+
+extern "C" int64_t dcb_clip_workspace_bytes(int64_t rows_local, int64_t cols) {
+    if (rows_local < 1 || cols < 1) return 0;
+    return ((int64_t)dcb::clip_fwd_splits(rows_local, cols) * 4 + 1) * rows_local * (int64_t)sizeof(float);
+}
+
+extern "C" int dcb_clip_row_stats(const void* stu_a, const void* stu_b, const void* tea_a, const void* tea_b,
+                                  const float* stu_a_inv, const float* stu_b_inv, const float* tea_a_inv,
+                                  const float* tea_b_inv, int64_t rows_local, int64_t row_offset, int64_t cols,
+                                  int64_t dim, int dtype, float temperature, float* stats, void* workspace,
+                                  float* dump_s, float* dump_t, void* stream) {
+    using namespace dcb;
+    DCB_REQUIRE(stu_a && stu_b && stu_a_inv && stu_b_inv && stats && workspace, "NULL pointer argument");
+    DCB_REQUIRE(dtype == DCB_BF16 || dtype == DCB_F16, "the fused contrastive kernel takes bf16 or fp16 embeddings");
+    DCB_REQUIRE(rows_local >= 1 && cols >= 1 && dim >= 8 && dim % 8 == 0, "bad shape rows=%lld cols=%lld dim=%lld (dim %% 8 == 0)",
+                (long long)rows_local, (long long)cols, (long long)dim);
+    DCB_REQUIRE(rows_local < (1ll << 30) && cols < (1ll << 30), "batch too large");
+    const bool teacher = tea_a != nullptr;
+    if (teacher) {
+        DCB_REQUIRE(tea_b && tea_a_inv && tea_b_inv, "teacher pointers must be all set or all NULL");
+        DCB_REQUIRE(temperature > 0.f, "temperature must be positive");
+    }
+    CUtensorMap ma_s, mb_s, ma_t, mb_t;
+    const uint64_t pitch = (uint64_t)dim * 2;
+    if (tc::encode_tile_map_16bit(&ma_s, stu_a, rows_local, dim, pitch, fwd::kBM)) return 1;
+    if (tc::encode_tile_map_16bit(&mb_s, stu_b, cols, dim, pitch, fwd::kBN)) return 1;
+    if (teacher) {
+        if (tc::encode_tile_map_16bit(&ma_t, tea_a, rows_local, dim, pitch, fwd::kBM)) return 1;
+        if (tc::encode_tile_map_16bit(&mb_t, tea_b, cols, dim, pitch, fwd::kBN)) return 1;
+    } else {
+        ma_t = ma_s;
+        mb_t = mb_s;
+    }
+    ClipFwdParams p{};
+    p.a_inv_stu = stu_a_inv;
+    p.b_inv_stu = stu_b_inv;
+    p.a_inv_tea = tea_a_inv;
+    p.b_inv_tea = tea_b_inv;
+    p.rows = (int)rows_local;
+    p.cols = (int)cols;
+    p.dim = (int)dim;
+    p.row_offset = (int)row_offset;
+    p.n_split = clip_fwd_splits(rows_local, cols);
+    p.col_tiles = (int)((cols + fwd::kBN - 1) / fwd::kBN);
+    p.ws = static_cast<float*>(workspace);
+    p.diag = p.ws + (size_t)p.n_split * 4 * rows_local;
+    p.dump_s = dump_s;
+    p.dump_t = dump_t;
+    p.inv_temp = teacher ? 1.0f / temperature : 1.0f;
+    const int row_blocks = (int)((rows_local + fwd::kBM - 1) / fwd::kBM);
+    const uint32_t idesc = tc::umma_idesc_f16(fwd::kBM, fwd::kBN, dtype == DCB_BF16 ? 1 : 0);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    dim3 grid((unsigned)(row_blocks * p.n_split));
+    if (teacher) {
+        DCB_CUDA_OK(cudaFuncSetAttribute(clip_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd::kSmemBytes));
+        clip_fwd_kernel<true><<<grid, fwd::kThreads, fwd::kSmemBytes, st>>>(ma_s, mb_s, ma_t, mb_t, p, idesc);
+    } else {
+        DCB_CUDA_OK(cudaFuncSetAttribute(clip_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd::kSmemBytes));
+        clip_fwd_kernel<false><<<grid, fwd::kThreads, fwd::kSmemBytes, st>>>(ma_s, mb_s, ma_t, mb_t, p, idesc);
+    }
+    DCB_CUDA_OK(cudaGetLastError());
+    const int n = 4 * (int)rows_local;
+    clip_combine_kernel<<<(n + 255) / 256, 256, 0, st>>>(p.ws, p.diag, stats, (int)rows_local, p.n_split);
+    DCB_CUDA_OK(cudaGetLastError());
+    return 0;
+}

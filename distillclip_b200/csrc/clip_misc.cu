@@ -1,0 +1,218 @@
+// Small kernels around the fused contrastive path: inverse L2 norms, the one-off b-side transpose,
+// loss values from the row statistics, gradient coefficients, and the normalisation Jacobian.
+#include "common.cuh"
+
+namespace dcb {
+
+// ---------------------------------------------------------------------------------------------
+// r_i = 1 / ||x_i||_2   (reference model/component/clip_model.py:37-38 divides by x.norm(dim=1))
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) inv_norm_kernel(const T* __restrict__ x, float* __restrict__ out, long long rows,
+                                                       int dim) {
+    const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const int lane = threadIdx.x & 31;
+    const T* __restrict__ p = x + row * dim;
+    float acc = 0.f;
+    for (int d = lane; d < dim; d += 32) {
+        const float v = Elem<T>::to_f(p[d]);
+        acc = fmaf(v, v, acc);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) out[row] = 1.0f / sqrtf(acc);
+}
+
+// ---------------------------------------------------------------------------------------------
+// out[d][j] = bf16(in[j][d])     in: [rows, dim] row-major, out: [dim, pitch] row-major (pitch >= rows)
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) transpose_to_bf16_kernel(const T* __restrict__ in, __nv_bfloat16* __restrict__ out,
+                                                                int rows, int dim, long long pitch) {
+    __shared__ float tile[32][33];
+    const int j0 = blockIdx.x * 32, d0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;      // 32 x 8
+    for (int k = ty; k < 32; k += 8) {
+        const int j = j0 + k, d = d0 + tx;
+        tile[k][tx] = (j < rows && d < dim) ? Elem<T>::to_f(in[(long long)j * dim + d]) : 0.f;
+    }
+    __syncthreads();
+    for (int k = ty; k < 32; k += 8) {
+        const int d = d0 + k, j = j0 + tx;
+        if (d < dim && j < pitch) out[(long long)d * pitch + j] = __float2bfloat16_rn(j < rows ? tile[tx][k] : 0.f);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Loss values of both directions from the row statistics ([5][rows]: A, Zs, Zt, W, S_ii):
+//   CE row  = lse_i - S_ii = 1 + log A_i - S_ii                      (hard_label.py:12, shift 1)
+//   KL row  = T^2 [ W_i / (T Zt_i) - log Zt_i + log Zs_i ]           (soft_label.py:12-15, 'sum')
+// sums[0..3] (double) = {sum CE i2t, sum CE t2i, sum KL i2t, sum KL t2i} over this rank's rows;
+// out[0] = 0.5 (sums0 + sums1) / global_batch, out[1] = 0.5 (sums2 + sums3)   (_loss.py:131,135-136)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) clip_loss_kernel(const float* __restrict__ st_i2t, const float* __restrict__ st_t2i,
+                                                         int rows_i2t, int rows_t2i, float temperature, int has_teacher,
+                                                         double inv_batch, double* __restrict__ sums, float* __restrict__ out) {
+    __shared__ double res[4];
+    for (int dir = 0; dir < 2; ++dir) {
+        const float* st = dir == 0 ? st_i2t : st_t2i;
+        const int rows = dir == 0 ? rows_i2t : rows_t2i;
+        double ce = 0.0, kl = 0.0;
+        for (int i = threadIdx.x; i < rows; i += blockDim.x) {
+            const float A = st[i], diag = st[(size_t)4 * rows + i];
+            ce += (double)(1.0f + logf(A) - diag);
+            if (has_teacher) {
+                const float Zs = st[(size_t)rows + i], Zt = st[(size_t)2 * rows + i], W = st[(size_t)3 * rows + i];
+                kl += (double)(W / (temperature * Zt) - logf(Zt) + logf(Zs));
+            }
+        }
+        ce = block_sum(ce);
+        __syncthreads();
+        kl = block_sum(kl);
+        if (threadIdx.x == 0) {
+            res[dir] = ce;
+            res[2 + dir] = kl * (double)temperature * (double)temperature;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        for (int k = 0; k < 4; ++k) sums[k] = res[k];
+        out[0] = (float)(0.5 * (res[0] + res[1]) * inv_batch);
+        out[1] = (float)(0.5 * (res[2] + res[3]));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// coef[0][i] = gh / (2 B A_i)   coef[1][i] = gs T / (2 Zs_i)   coef[2][i] = gs T / (2 Zt_i)
+// upstream = {gh, gs} on the device (no host sync in backward)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) clip_coef_kernel(const float* __restrict__ stats, int rows, float temperature,
+                                                        int has_teacher, float inv_batch, const float* __restrict__ upstream,
+                                                        float* __restrict__ coef) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows) return;
+    const float gh = upstream[0], gs = upstream[1];
+    coef[i] = 0.5f * gh * inv_batch / stats[i];
+    coef[(size_t)rows + i] = has_teacher ? 0.5f * gs * temperature / stats[(size_t)rows + i] : 0.f;
+    coef[(size_t)2 * rows + i] = has_teacher ? 0.5f * gs * temperature / stats[(size_t)2 * rows + i] : 0.f;
+}
+
+// ---------------------------------------------------------------------------------------------
+// grad_a[i,:] = r_i (acc_i - a_hat_i (a_hat_i . acc_i)),  acc_i = sum_splits acc_parts - (gh/B) b_hat_{offset+i}
+// (Jacobian of x / ||x||, reference clip_model.py:37-38, plus the -delta_ij label term of cross entropy)
+// ---------------------------------------------------------------------------------------------
+template <typename T, typename G>
+__global__ void __launch_bounds__(256) clip_grad_finish_kernel(const float* __restrict__ acc_parts, int n_split,
+                                                               const T* __restrict__ a, const float* __restrict__ a_inv,
+                                                               const T* __restrict__ b, const float* __restrict__ b_inv,
+                                                               long long rows, long long cols, int dim, long long row_offset,
+                                                               float inv_batch, const float* __restrict__ upstream,
+                                                               G* __restrict__ grad) {
+    const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const int lane = threadIdx.x & 31;
+    const float r = a_inv[row];
+    const long long gi = row_offset + row;
+    const bool has_label = gi < cols;
+    const float lab = has_label ? upstream[0] * inv_batch * b_inv[gi] : 0.f;
+    const T* __restrict__ ap = a + row * dim;
+    const T* __restrict__ bp = b + (has_label ? gi : 0) * dim;
+    float dot = 0.f;
+    for (int d = lane; d < dim; d += 32) {
+        float v = 0.f;
+        for (int s = 0; s < n_split; ++s) v += acc_parts[((size_t)s * rows + row) * dim + d];
+        v -= lab * Elem<T>::to_f(bp[d]);
+        dot = fmaf(Elem<T>::to_f(ap[d]) * r, v, dot);
+    }
+    dot = warp_sum(dot);
+    G* __restrict__ gp = grad + row * dim;
+    for (int d = lane; d < dim; d += 32) {
+        float v = 0.f;
+        for (int s = 0; s < n_split; ++s) v += acc_parts[((size_t)s * rows + row) * dim + d];
+        v -= lab * Elem<T>::to_f(bp[d]);
+        gp[d] = Elem<G>::from_f(r * (v - Elem<T>::to_f(ap[d]) * r * dot));
+    }
+}
+
+}  // namespace dcb
+
+extern "C" {
+
+int dcb_row_inv_norm(int n_mats, const void* const* mats, float* const* inv_norm, const int64_t* rows, int64_t dim,
+                     int dtype, void* stream) {
+    using namespace dcb;
+    DCB_REQUIRE(n_mats >= 1 && n_mats <= 8 && dim >= 1, "bad arguments");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    for (int k = 0; k < n_mats; ++k) {
+        DCB_REQUIRE(mats[k] && inv_norm[k] && rows[k] >= 1, "matrix %d: bad arguments", k);
+        const unsigned grid = (unsigned)((rows[k] + 7) / 8);
+        switch (dtype) {
+            case DCB_BF16: inv_norm_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(mats[k]), inv_norm[k], rows[k], (int)dim); break;
+            case DCB_F16: inv_norm_kernel<__half><<<grid, 256, 0, st>>>(static_cast<const __half*>(mats[k]), inv_norm[k], rows[k], (int)dim); break;
+            case DCB_F32: inv_norm_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(mats[k]), inv_norm[k], rows[k], (int)dim); break;
+            default: return fail("unknown dtype %d", dtype);
+        }
+    }
+    DCB_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int dcb_transpose_to_bf16(const void* in, void* out, int64_t rows, int64_t dim, int64_t out_pitch_elems, int dtype,
+                          void* stream) {
+    using namespace dcb;
+    DCB_REQUIRE(in && out && rows >= 1 && dim >= 1 && out_pitch_elems >= rows, "bad arguments");
+    dim3 grid((unsigned)((out_pitch_elems + 31) / 32), (unsigned)((dim + 31) / 32));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    __nv_bfloat16* o = static_cast<__nv_bfloat16*>(out);
+    switch (dtype) {
+        case DCB_BF16: transpose_to_bf16_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(in), o, (int)rows, (int)dim, out_pitch_elems); break;
+        case DCB_F16: transpose_to_bf16_kernel<__half><<<grid, 256, 0, st>>>(static_cast<const __half*>(in), o, (int)rows, (int)dim, out_pitch_elems); break;
+        default: return fail("transpose: bf16 or fp16 input only");
+    }
+    DCB_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int dcb_clip_losses(const float* stats_i2t, const float* stats_t2i, int64_t rows_i2t, int64_t rows_t2i,
+                    int64_t global_batch, float temperature, int has_teacher, double* sums, float* out, void* stream) {
+    using namespace dcb;
+    DCB_REQUIRE(stats_i2t && stats_t2i && sums && out && global_batch >= 1, "bad arguments");
+    clip_loss_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(stats_i2t, stats_t2i, (int)rows_i2t, (int)rows_t2i,
+                                                                        temperature, has_teacher, 1.0 / (double)global_batch,
+                                                                        sums, out);
+    DCB_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int dcb_clip_grad_coef(const float* stats, int64_t rows, int64_t global_batch, float temperature, int has_teacher,
+                       const float* upstream, float* coef, void* stream) {
+    using namespace dcb;
+    DCB_REQUIRE(stats && upstream && coef && rows >= 1 && global_batch >= 1, "bad arguments");
+    clip_coef_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        stats, (int)rows, temperature, has_teacher, 1.0f / (float)global_batch, upstream, coef);
+    DCB_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int dcb_clip_grad_finish(const float* acc_parts, int n_split, const void* stu_a, const float* stu_a_inv,
+                         const void* stu_b, const float* stu_b_inv, int64_t rows, int64_t cols, int64_t dim,
+                         int64_t row_offset, int64_t global_batch, const float* upstream, int in_dtype, void* grad_a,
+                         int grad_dtype, void* stream) {
+    using namespace dcb;
+    DCB_REQUIRE(acc_parts && stu_a && stu_a_inv && stu_b && stu_b_inv && upstream && grad_a, "NULL pointer argument");
+    DCB_REQUIRE(n_split >= 1 && rows >= 1 && dim >= 1 && global_batch >= 1, "bad arguments");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const unsigned grid = (unsigned)((rows + 7) / 8);
+    const float inv_b = 1.0f / (float)global_batch;
+    return dispatch_in_grad(in_dtype, grad_dtype, [&](auto tt, auto gg) -> int {
+        using T = decltype(tt);
+        using G = decltype(gg);
+        clip_grad_finish_kernel<T, G><<<grid, 256, 0, st>>>(acc_parts, n_split, static_cast<const T*>(stu_a), stu_a_inv,
+                                                           static_cast<const T*>(stu_b), stu_b_inv, rows, cols, (int)dim,
+                                                           row_offset, inv_b, upstream, static_cast<G*>(grad_a));
+        DCB_CUDA_OK(cudaGetLastError());
+        return 0;
+    });
+}
+
+}  // extern "C"

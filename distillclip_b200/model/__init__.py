@@ -1,0 +1,8 @@
+"""Mirror of the reference's `model` package for the loss hot path (same import paths below `model`)."""
+from ._loss import IMAGE_TEXT_LOSS, LOSSNAME, LossCalculator
+from .component.output import CLIPOutput, ControlOutput, TextTransformerOutput, VisionTransformerOutput
+from .loss_component import AttentionProbsKL, EmbedMSELoss, HardLabel, HiddenMSE, SoftLabel
+
+__all__ = ["LossCalculator", "LOSSNAME", "IMAGE_TEXT_LOSS", "CLIPOutput", "ControlOutput",
+           "TextTransformerOutput", "VisionTransformerOutput", "AttentionProbsKL", "EmbedMSELoss", "HardLabel",
+           "HiddenMSE", "SoftLabel"]

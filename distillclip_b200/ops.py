@@ -1,0 +1,242 @@
+"""Host side of the streaming losses: launches through the C ABI + custom autograd.
+
+The one-pass kernels write the student gradients during the forward pass, pre-multiplied by the
+upstream gradient the caller expects (`percent * scale` when called from LossCalculator, else 1).
+`backward` only has to check that expectation on the device (`dcb_rescale_grads`, which exits without
+touching HBM when it holds), so fwd+bwd costs read s + read t + write ds and nothing more.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+
+_DT = {torch.bfloat16: _lib.BF16, torch.float16: _lib.F16, torch.float32: _lib.F32}
+
+
+def dtype_code(t: torch.Tensor) -> int:
+    try:
+        return _DT[t.dtype]
+    except KeyError:
+        raise TypeError(f"distillclip_b200: unsupported dtype {t.dtype} (bf16 / fp16 / fp32 only)") from None
+
+
+def _stream_ptr() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _require_cuda(t: torch.Tensor, what: str):
+    if not t.is_cuda:
+        raise _lib.DistillClipB200Error(
+            f"{what} is on {t.device}: distillclip_b200 runs on CUDA (sm_100a) only and has no CPU fallback")
+
+
+def _prep_pair(stu: Sequence[torch.Tensor], tea: Sequence[torch.Tensor]):
+    """zip()-truncate like the reference loops do, make contiguous, unify dtypes."""
+    n = min(len(stu), len(tea))
+    s_out, t_out = [], []
+    for s, t in zip(stu[:n], tea[:n]):
+        _require_cuda(s, "student tensor")
+        _require_cuda(t, "teacher tensor")
+        dtype_code(s)
+        if t.dtype != s.dtype:
+            t = t.to(s.dtype)
+        s_out.append(s if s.is_contiguous() else s.contiguous())
+        t_out.append(t.detach() if t.is_contiguous() else t.detach().contiguous())
+    if n and any(s.dtype != s_out[0].dtype for s in s_out):
+        raise TypeError("distillclip_b200: all student layers of one loss must share a dtype")
+    return s_out, t_out
+
+
+# ----------------------------------------------------------------------------------------------
+# raw launches (no autograd)
+# ----------------------------------------------------------------------------------------------
+def launch_mse(stu: List[torch.Tensor], tea: List[torch.Tensor], divisor: int, grad_scale: float,
+               need_grad: Sequence[bool], grad_dtype: Optional[torch.dtype] = None):
+    """-> (partials, count, grads). Shapes must match pairwise (same rule as nn.MSELoss without broadcasting)."""
+    dev = stu[0].device
+    grads: List[Optional[torch.Tensor]] = []
+    for s, t, ng in zip(stu, tea, need_grad):
+        if s.shape != t.shape:
+            raise ValueError(f"MSE: student {tuple(s.shape)} and teacher {tuple(t.shape)} shapes differ")
+        grads.append(torch.empty_like(s, dtype=grad_dtype or s.dtype) if ng else None)
+    gd = _DT[grad_dtype] if grad_dtype is not None else dtype_code(stu[0])
+    nchunk = (len(stu) + _lib.MAX_LAYERS - 1) // _lib.MAX_LAYERS
+    if nchunk == 1:
+        partials = torch.empty(_lib.MAX_PARTIALS, dtype=torch.float64, device=dev)
+    else:
+        partials = torch.zeros(nchunk * _lib.MAX_PARTIALS, dtype=torch.float64, device=dev)
+    count = C.c_int(0)
+    for c in range(nchunk):
+        sl = slice(c * _lib.MAX_LAYERS, (c + 1) * _lib.MAX_LAYERS)
+        ss, tt, gg = stu[sl], tea[sl], grads[sl]
+        _lib.call("dcb_mse_fwd_bwd", len(ss), _lib.ptr_array([x.data_ptr() for x in ss]),
+                  _lib.ptr_array([x.data_ptr() for x in tt]),
+                  _lib.ptr_array([g.data_ptr() if g is not None else 0 for g in gg]),
+                  _lib.i64_array([x.numel() for x in ss]), dtype_code(ss[0]), gd, int(divisor), float(grad_scale),
+                  C.c_void_p(partials.data_ptr() + 8 * c * _lib.MAX_PARTIALS), C.byref(count), _stream_ptr())
+    n_part = count.value if nchunk == 1 else nchunk * _lib.MAX_PARTIALS
+    return partials, n_part, grads
+
+
+def launch_attn_kl(stu: List[torch.Tensor], tea: List[torch.Tensor], divisor: int, grad_scale: float,
+                   need_grad: Sequence[bool], grad_dtype: Optional[torch.dtype] = None):
+    dev = stu[0].device
+    grads: List[Optional[torch.Tensor]] = []
+    batch, hs, ht, pos = [], [], [], []
+    for s, t, ng in zip(stu, tea, need_grad):
+        if s.dim() < 3 or t.dim() != s.dim() or s.shape[0] != t.shape[0] or s.shape[2:] != t.shape[2:]:
+            raise ValueError(f"attention maps must be [B, H, ...] with equal B and map size: "
+                             f"student {tuple(s.shape)} vs teacher {tuple(t.shape)}")
+        batch.append(s.shape[0])
+        hs.append(s.shape[1])
+        ht.append(t.shape[1])
+        pos.append(s[0, 0].numel())
+        grads.append(torch.empty_like(s, dtype=grad_dtype or s.dtype) if ng else None)
+    gd = _DT[grad_dtype] if grad_dtype is not None else dtype_code(stu[0])
+    nchunk = (len(stu) + _lib.MAX_LAYERS - 1) // _lib.MAX_LAYERS
+    if nchunk == 1:
+        partials = torch.empty(_lib.MAX_PARTIALS, dtype=torch.float64, device=dev)
+    else:
+        partials = torch.zeros(nchunk * _lib.MAX_PARTIALS, dtype=torch.float64, device=dev)
+    count = C.c_int(0)
+    for c in range(nchunk):
+        sl = slice(c * _lib.MAX_LAYERS, (c + 1) * _lib.MAX_LAYERS)
+        ss, tt, gg = stu[sl], tea[sl], grads[sl]
+        _lib.call("dcb_attn_kl_fwd_bwd", len(ss), _lib.ptr_array([x.data_ptr() for x in ss]),
+                  _lib.ptr_array([x.data_ptr() for x in tt]),
+                  _lib.ptr_array([g.data_ptr() if g is not None else 0 for g in gg]),
+                  _lib.i64_array(batch[sl]), _lib.i32_array(hs[sl]), _lib.i32_array(ht[sl]), _lib.i64_array(pos[sl]),
+                  dtype_code(ss[0]), gd, int(divisor), float(grad_scale),
+                  C.c_void_p(partials.data_ptr() + 8 * c * _lib.MAX_PARTIALS), C.byref(count), _stream_ptr())
+    n_part = count.value if nchunk == 1 else nchunk * _lib.MAX_PARTIALS
+    return partials, n_part, grads
+
+
+def finalize(terms: Sequence[Tuple[torch.Tensor, int]], scale: Sequence[float], percent: Sequence[float]):
+    """out[k] = scale[k]*sum(partials_k) ; out[-1] = sum_k percent[k]*out[k]   (fp32, device)."""
+    out = torch.empty(len(terms) + 1, dtype=torch.float32, device=terms[0][0].device)
+    _lib.call("dcb_finalize", len(terms), _lib.ptr_array([p.data_ptr() for p, _ in terms]),
+              _lib.i32_array([c for _, c in terms]), _lib.f32_array(scale), _lib.f32_array(percent),
+              C.c_void_p(out.data_ptr()), _stream_ptr())
+    return out
+
+
+def rescale(groups: Sequence[Tuple[Sequence[Optional[torch.Tensor]], torch.Tensor, float]]):
+    """groups: (grads, upstream 0-dim fp32 device tensor, expected value). In-place, early-exit when equal."""
+    by_dtype = {}
+    for grads, up, expected in groups:
+        for g in grads:
+            if g is not None:
+                by_dtype.setdefault(g.dtype, []).append((g, up, expected))
+    for dt, segs in by_dtype.items():
+        for i in range(0, len(segs), 2 * _lib.MAX_LAYERS):
+            part = segs[i:i + 2 * _lib.MAX_LAYERS]
+            _lib.call("dcb_rescale_grads", len(part), _lib.ptr_array([g.data_ptr() for g, _, _ in part]),
+                      _lib.i64_array([g.numel() for g, _, _ in part]), _DT[dt],
+                      _lib.ptr_array([u.data_ptr() for _, u, _ in part]), _lib.f32_array([e for _, _, e in part]),
+                      _stream_ptr())
+
+
+def _as_upstream(g: Optional[torch.Tensor], like: torch.Tensor) -> torch.Tensor:
+    if g is None:
+        return torch.zeros((), dtype=torch.float32, device=like.device)
+    if g.dtype != torch.float32 or not g.is_contiguous():
+        g = g.to(torch.float32).contiguous()
+    return g
+
+
+# ----------------------------------------------------------------------------------------------
+# autograd: one loss family (used by the per-module classes)
+# ----------------------------------------------------------------------------------------------
+KIND_MSE, KIND_ATTN_KL = "mse", "attn_kl"
+_LAUNCH = {KIND_MSE: launch_mse, KIND_ATTN_KL: launch_attn_kl}
+
+
+class StreamLossFn(torch.autograd.Function):
+    """loss = kernel(stu_0..n-1, tea_0..n-1); gradients for the students come out of the same pass."""
+
+    @staticmethod
+    def forward(ctx, kind: str, divisor: int, n: int, *tensors):
+        stu, tea = list(tensors[:n]), list(tensors[n:])
+        need = [bool(ng) for ng in ctx.needs_input_grad[3:3 + n]]
+        partials, count, grads = _LAUNCH[kind](stu, tea, divisor, 1.0, need)
+        out = finalize([(partials, count)], [1.0], [1.0])
+        ctx.grads = grads
+        ctx.n = n
+        return out[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        grads = ctx.grads
+        if any(x is not None for x in grads):
+            rescale([(grads, _as_upstream(g, next(x for x in grads if x is not None)), 1.0)])
+        return (None, None, None, *grads, *([None] * ctx.n))
+
+
+def stream_loss(kind: str, stu: Sequence[torch.Tensor], tea: Sequence[torch.Tensor]):
+    """Reference list semantics: zip-truncation, divisor len(stu), ZeroDivisionError on empty (F8)."""
+    divisor = len(stu)
+    if divisor == 0:
+        raise ZeroDivisionError("division by zero")
+    s, t = _prep_pair(stu, tea)
+    if not s:
+        return 0.0          # reference: `res_loss = 0; res_loss /= len(stu)` -> python float
+    return StreamLossFn.apply(kind, divisor, len(s), *s, *t)
+
+
+# ----------------------------------------------------------------------------------------------
+# autograd: a whole tower (LossCalculator.cal_one_tower_loss) -> one finalize, one rescale
+# ----------------------------------------------------------------------------------------------
+class TowerLossFn(torch.autograd.Function):
+    """spec: list of (kind, divisor, n_layers, scale, percent); tensors: for each entry stu_0.., tea_0..
+    Returns (total, res_0, ..., res_{k-1}) with res_k = raw_k * scale_k and total = sum res_k * percent_k
+    (reference model/_loss.py:195-200)."""
+
+    @staticmethod
+    def forward(ctx, spec, *tensors):
+        ctx.set_materialize_grads(False)
+        terms, scales, percents, all_grads, pres, layout = [], [], [], [], [], []
+        off = 0
+        for kind, divisor, n, scale, percent in spec:
+            stu, tea = list(tensors[off:off + n]), list(tensors[off + n:off + 2 * n])
+            need = [bool(x) for x in ctx.needs_input_grad[1 + off:1 + off + n]]
+            w = float(np.float32(percent) * np.float32(scale))
+            pre = w if w != 0.0 else 1.0
+            partials, count, grads = _LAUNCH[kind](stu, tea, divisor, pre, need)
+            terms.append((partials, count))
+            scales.append(scale)
+            percents.append(percent)
+            all_grads.append(grads)
+            pres.append((pre, w))
+            layout.append((off, n))
+            off += 2 * n
+        out = finalize(terms, scales, percents)
+        ctx.all_grads, ctx.pres, ctx.layout, ctx.spec, ctx.n_in = all_grads, pres, layout, spec, len(tensors)
+        k = len(spec)
+        return (out[k], *out[:k].unbind(0))
+
+    @staticmethod
+    def backward(ctx, g_total, *g_res):
+        ret: List[Optional[torch.Tensor]] = [None] * ctx.n_in
+        groups = []
+        for i, (grads, (pre, w), (off, n)) in enumerate(zip(ctx.all_grads, ctx.pres, ctx.layout)):
+            live = [x for x in grads if x is not None]
+            if not live:
+                continue
+            scale = float(ctx.spec[i][3])
+            if g_res[i] is None and pre == w and g_total is not None:
+                groups.append((grads, _as_upstream(g_total, live[0]), 1.0))      # common path: no torch kernels
+            else:
+                up = _as_upstream(g_total, live[0]) * w
+                if g_res[i] is not None:
+                    up = up + _as_upstream(g_res[i], live[0]) * scale
+                groups.append((grads, up.contiguous(), pre))
+            ret[off:off + n] = grads
+        if groups:
+            rescale(groups)
+        return (None, *ret)

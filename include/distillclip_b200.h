@@ -1,0 +1,177 @@
+/*
+ * distillclip_b200 -- C ABI of the B200-native distillation-loss hot path.
+ *
+ * The reference (ForJadeForest/DistillCLIP) is pure Python: its "operator interface" for this
+ * path is the nn.Module API of model/_loss.py and model/loss_component/ (SURVEY.md section 8b).
+ * Every entry point below is what a ctypes/cffi binding inside those modules' forward()/backward()
+ * would call; each cites the reference code it replaces (paths relative to the reference root).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all buffers are caller-allocated DEVICE memory unless the
+ *     parameter says "host"; pointer *arrays* (`const void* const*`) are HOST arrays of device pointers;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); every call only
+ *     enqueues work on it, never synchronises and never allocates, so calls are CUDA-graph capturable;
+ *   - return 0 on success, non-zero on error; `dcb_last_error()` returns a thread-local message;
+ *   - dtypes: DCB_BF16 / DCB_F16 / DCB_F32 for student+teacher inputs (both the same), and for
+ *     gradient outputs either the input dtype or DCB_F32;
+ *   - loss values are produced in two steps so that results are deterministic (no float atomics):
+ *     a kernel writes per-CTA partial sums (double) and `dcb_finalize` reduces them in a fixed order.
+ */
+#ifndef DISTILLCLIP_B200_H_
+#define DISTILLCLIP_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum { DCB_BF16 = 0, DCB_F16 = 1, DCB_F32 = 2 };
+enum { DCB_MAX_LAYERS = 16, DCB_MAX_PARTIALS = 4096, DCB_MAX_TERMS = 16 };
+
+/* library / build identification */
+int dcb_version(void);
+const char* dcb_last_error(void);
+/* compute capability the kernels were compiled for (100 = sm_100a) */
+int dcb_compiled_arch(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Hidden-state / embedding MSE, forward and backward in ONE pass.
+ * Replaces HiddenMSE.forward (model/loss_component/hidden_mse.py:9-17), EmbedMSELoss.forward
+ * (model/loss_component/embed_mse.py:9-10) and the autograd backward of nn.MSELoss under them.
+ *   value  = (1/divisor) * sum_l mean((stu_l - tea_l)^2)          (divisor = len(stu_hidden), :16)
+ *   grad_l = grad_scale * 2 (stu_l - tea_l) / (numel_l * divisor)  (written when grad_stu[l] != NULL)
+ * partials: >= DCB_MAX_PARTIALS doubles; *n_partials (host) receives how many were written.
+ * --------------------------------------------------------------------------------------------- */
+int dcb_mse_fwd_bwd(int n_layers, const void* const* stu, const void* const* tea, void* const* grad_stu,
+                    const int64_t* numel, int in_dtype, int grad_dtype, int divisor, float grad_scale,
+                    double* partials, int* n_partials, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Attention-map KL, forward and backward in ONE pass.
+ * Replaces AttentionProbsKL.forward (model/loss_component/attention_probs_kl.py:10-22).
+ * Layer l: stu_l is [batch, stu_heads, positions], tea_l is [batch, tea_heads, positions]
+ * (positions = N*N, contiguous).  s = head-mean(stu), t = head-mean(tea):
+ *   value    = (1/divisor) * sum_l sum_{b,p} [xlogy(t,t) - t log s]          (KLDivLoss 'sum', :8)
+ *   grad_l   = -grad_scale * t / (s * stu_heads * divisor), the same for every head
+ * NaN/Inf propagate exactly as in the reference (both maps zero at one position -> NaN).
+ * --------------------------------------------------------------------------------------------- */
+int dcb_attn_kl_fwd_bwd(int n_layers, const void* const* stu, const void* const* tea, void* const* grad_stu,
+                        const int64_t* batch, const int32_t* stu_heads, const int32_t* tea_heads,
+                        const int64_t* positions, int in_dtype, int grad_dtype, int divisor, float grad_scale,
+                        double* partials, int* n_partials, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Deterministic reduction + weighting (model/_loss.py:195-200 and :148-152).
+ *   out[k]        = scale[k] * sum(partials[k][0 .. counts[k]))            k < n_terms
+ *   out[n_terms]  = sum_k percent[k] * out[k]
+ * partials: host array of device pointers; counts/scale/percent: host arrays; out: device floats.
+ * --------------------------------------------------------------------------------------------- */
+int dcb_finalize(int n_terms, const double* const* partials, const int32_t* counts, const float* scale,
+                 const float* percent, float* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Backward helper: the one-pass kernels above write gradients pre-multiplied by the upstream
+ * gradient the caller EXPECTS (grad_scale).  At backward time the true upstream scalar lives on
+ * the device; this kernel multiplies segment k in place by (*upstream[k] / expected[k]) and exits
+ * immediately when they are equal (the common case), so no host sync and no extra HBM pass.
+ * --------------------------------------------------------------------------------------------- */
+int dcb_rescale_grads(int n_seg, void* const* grads, const int64_t* numel, int dtype,
+                      const float* const* upstream, const float* expected, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Fused global-batch contrastive (InfoNCE) + teacher/student logit KL from EMBEDDINGS.
+ * Replaces, without ever writing the B x B logits:
+ *   CLIPModel.forward's normalise + `image_feature @ text_feature.t()` (model/component/clip_model.py:36-44),
+ *   HardLabel.forward (model/loss_component/hard_label.py:10-12) on i2t and t2i,
+ *   SoftLabel.forward (model/loss_component/soft_label.py:11-16) on i2t and t2i,
+ *   the 0.5*(i2t + t2i) combination of model/_loss.py:130-137, and autograd through all of them.
+ *
+ * Row-sharded: this process owns `rows_local` rows [row_offset, row_offset+rows_local) of the global
+ * batch on the "a" side and sees all `cols` rows of the "b" side (after an all-gather, or the local
+ * batch when not sharded).  A "direction" is (a=image,b=text) for i2t rows or (a=text,b=image) for t2i.
+ * Embeddings are bf16 or fp16 (`dtype`), row-major [rows, dim] with dim % 8 == 0, 16-byte aligned.
+ * Cosine logits are bounded by 1, so softmax uses the fixed shift 1 and partial sums over column
+ * ranges / ranks simply add.  temperature must be >= 0.025 on this path (exp((S-1)/T) stays normal).
+ * --------------------------------------------------------------------------------------------- */
+
+/* inv_norm[k][i] = 1 / ||mats[k][i,:]||_2  (clip_model.py:37-38).  dtype: DCB_BF16 / DCB_F16 / DCB_F32. */
+int dcb_row_inv_norm(int n_mats, const void* const* mats, float* const* inv_norm, const int64_t* rows,
+                     int64_t dim, int dtype, void* stream);
+
+/* out[d][j] = bf16(in[j][d]); out is [dim, out_pitch_elems] (pitch >= rows, % 8 == 0, pad columns zeroed).
+ * The gradient GEMM wants the student b-side K-major, so it is transposed once per backward. */
+int dcb_transpose_to_bf16(const void* in, void* out, int64_t rows, int64_t dim, int64_t out_pitch_elems, int dtype,
+                          void* stream);
+
+/* dcb_clip_row_stats: ONE fused tcgen05 kernel for one direction.  For each local row i:
+ *   stats[0][i] = sum_j exp(S_ij - 1)                 (hard label; S = student cosine logits)
+ *   stats[1][i] = sum_j exp((S_ij - 1)/T)             stats[2][i] = sum_j exp((T_ij - 1)/T)
+ *   stats[3][i] = sum_j exp((T_ij - 1)/T) (T_ij - S_ij)      stats[4][i] = S_ii (global diagonal)
+ * tea_* may all be NULL (hard label only; stats[1..3] are then 0).  stats: [5, rows_local] floats.
+ * workspace: dcb_clip_workspace_bytes(rows_local, cols) bytes of device scratch.
+ * dump_s / dump_t: optional [rows_local, cols] fp32 buffers that receive the logits (tests only; NULL in production). */
+int64_t dcb_clip_workspace_bytes(int64_t rows_local, int64_t cols);
+int dcb_clip_row_stats(const void* stu_a, const void* stu_b, const void* tea_a, const void* tea_b,
+                       const float* stu_a_inv, const float* stu_b_inv, const float* tea_a_inv, const float* tea_b_inv,
+                       int64_t rows_local, int64_t row_offset, int64_t cols, int64_t dim, int dtype, float temperature,
+                       float* stats, void* workspace, float* dump_s, float* dump_t, void* stream);
+
+/* Loss values of both directions from this rank's row statistics:
+ *   sums[0..3] (double) = {sum_i CE_i (i2t), sum_i CE_i (t2i), T^2 sum_i KL_i (i2t), T^2 sum_i KL_i (t2i)}
+ *   out[0] = 0.5 (sums[0] + sums[1]) / global_batch   (hard_label.py:12 'mean', _loss.py:131)
+ *   out[1] = 0.5 (sums[2] + sums[3])                  (soft_label.py:8 'sum', _loss.py:135-136)
+ * When sharded, all-reduce `sums` over ranks and rescale instead of using `out`. */
+int dcb_clip_losses(const float* stats_i2t, const float* stats_t2i, int64_t rows_i2t, int64_t rows_t2i,
+                    int64_t global_batch, float temperature, int has_teacher, double* sums, float* out, void* stream);
+
+/* coef[0][i] = gh/(2 B A_i), coef[1][i] = gs T/(2 Zs_i), coef[2][i] = gs T/(2 Zt_i) from stats [5, rows];
+ * upstream: device float[2] = {gh = d total / d hard, gs = d total / d soft}. */
+int dcb_clip_grad_coef(const float* stats, int64_t rows, int64_t global_batch, float temperature, int has_teacher,
+                       const float* upstream, float* coef, void* stream);
+
+/* dcb_clip_row_grads: backward for one direction, recomputing the logits tile by tile:
+ *   G_ij = e1_ij (coef_row[0][i] + coef_col[0][j]) + es_ij (coef_row[1][i] + coef_col[1][j])
+ *        - et_ij (coef_row[2][i] + coef_col[2][j])
+ *   acc_parts[s][i,:] = partial sums over column range s of  sum_j G_ij b_hat_j      (fp32)
+ * coef_col are the coefficients of the OPPOSITE direction for all `cols` rows (the column softmax of the same logits).
+ * stu_b_t: dcb_transpose_to_bf16(stu_b).  acc_parts: dcb_clip_grad_workspace_bytes(...) bytes,
+ * dcb_clip_grad_splits(...) partial buffers of [rows_local, dim]. */
+int64_t dcb_clip_grad_workspace_bytes(int64_t rows_local, int64_t cols, int64_t dim);
+int dcb_clip_grad_splits(int64_t rows_local, int64_t cols, int64_t dim);
+int dcb_clip_row_grads(const void* stu_a, const void* stu_b, const void* tea_a, const void* tea_b,
+                       const void* stu_b_t, int64_t bt_pitch_elems,
+                       const float* stu_a_inv, const float* stu_b_inv, const float* tea_a_inv, const float* tea_b_inv,
+                       const float* coef_row, const float* coef_col,
+                       int64_t rows_local, int64_t cols, int64_t dim, int dtype, float temperature,
+                       float* acc_parts, void* stream);
+
+/* grad_a[i,:] = r_i (acc_i - a_hat_i (a_hat_i . acc_i)),  acc_i = sum_s acc_parts[s][i,:] - (gh/B) b_hat_{row_offset+i}
+ * (the -[i==j] label term of the cross entropy, added here in fp32, then the x/||x|| Jacobian of clip_model.py:37-38). */
+int dcb_clip_grad_finish(const float* acc_parts, int n_split, const void* stu_a, const float* stu_a_inv,
+                         const void* stu_b, const float* stu_b_inv, int64_t rows, int64_t cols, int64_t dim,
+                         int64_t row_offset, int64_t global_batch, const float* upstream, int in_dtype, void* grad_a,
+                         int grad_dtype, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Per-module API on MATERIALISED logits (HardLabel / SoftLabel keep their logits signature).
+ * logits: [n, n] with element strides (row_stride, col_stride) so that `logits.T` views work.
+ * mode 0 = HardLabel (hard_label.py:10-12), mode 1 = SoftLabel (soft_label.py:11-16).
+ *   saved[i]   = {max_s, Z_s, max_t, Z_t} (float4 per row, for the backward)
+ *   rowloss[i] = CE_i (mode 0) or KL_i without the T^2 factor (mode 1), double; reduce with dcb_finalize
+ *                (scale 1/n resp. T^2).
+ *   grad_logits: contiguous [n, n], dtype `grad_dtype`; upstream: device float[1].
+ * --------------------------------------------------------------------------------------------- */
+int dcb_logits_row_stats(const void* stu_logits, int64_t stu_rs, int64_t stu_cs,
+                         const void* tea_logits, int64_t tea_rs, int64_t tea_cs,
+                         int64_t n, int dtype, float temperature, int mode, float* saved, double* rowloss, void* stream);
+int dcb_logits_row_grads(const void* stu_logits, int64_t stu_rs, int64_t stu_cs,
+                         const void* tea_logits, int64_t tea_rs, int64_t tea_cs,
+                         int64_t n, int dtype, float temperature, int mode, const float* saved,
+                         const float* upstream, void* grad_logits, int grad_dtype, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DISTILLCLIP_B200_H_ */

@@ -1,0 +1,67 @@
+"""CPU test double of `distillclip_b200.contrastive.CudaEngine` (TEST INFRASTRUCTURE ONLY).
+
+It restates, in float64 torch on the CPU, exactly the decomposition the CUDA kernels implement (shift-1 softmax
+statistics, loss from statistics, gradient coefficients, G tile, label term, normalisation Jacobian), so that
+(a) the formulas can be checked against the oracle without a GPU and (b) the sharding / collective logic of
+`contrastive.contrastive_forward/backward` can run under gloo with world_size 2.  The product never imports it."""
+import torch
+
+
+class DoubleEngine:
+    def inv_norms(self, mats):
+        return [1.0 / m.double().norm(dim=1) for m in mats]
+
+    def _logits(self, a, b, a_inv, b_inv):
+        return (a.double() @ b.double().t()) * a_inv[:, None] * b_inv[None, :]
+
+    def row_stats(self, a_s, b_s, a_t, b_t, a_s_inv, b_s_inv, a_t_inv, b_t_inv, row_offset, temperature, dump=None):
+        S = self._logits(a_s, b_s, a_s_inv, b_s_inv)
+        rows = S.shape[0]
+        idx = torch.arange(rows)
+        st = torch.zeros(5, rows, dtype=torch.float64)
+        st[0] = torch.exp(S - 1).sum(1)
+        st[4] = S[idx, row_offset + idx]
+        if a_t is not None:
+            T = self._logits(a_t, b_t, a_t_inv, b_t_inv)
+            et = torch.exp((T - 1) / temperature)
+            st[1] = torch.exp((S - 1) / temperature).sum(1)
+            st[2] = et.sum(1)
+            st[3] = (et * (T - S)).sum(1)
+        return st
+
+    def losses(self, stats_i2t, stats_t2i, global_batch, temperature, has_teacher):
+        sums = torch.zeros(4, dtype=torch.float64)
+        for d, st in enumerate((stats_i2t, stats_t2i)):
+            sums[d] = (1 + torch.log(st[0]) - st[4]).sum()
+            if has_teacher:
+                sums[2 + d] = temperature ** 2 * (st[3] / (temperature * st[2]) - torch.log(st[2]) + torch.log(st[1])).sum()
+        out = torch.stack([0.5 * (sums[0] + sums[1]) / global_batch, 0.5 * (sums[2] + sums[3])])
+        return sums, out
+
+    def coef(self, stats, global_batch, temperature, has_teacher, upstream):
+        gh, gs = upstream.double()
+        c = torch.zeros(3, stats.shape[1], dtype=torch.float64)
+        c[0] = 0.5 * gh / (global_batch * stats[0])
+        if has_teacher:
+            c[1] = 0.5 * gs * temperature / stats[1]
+            c[2] = 0.5 * gs * temperature / stats[2]
+        return c
+
+    def transpose_bf16(self, b):
+        return b.double().t().contiguous()
+
+    def row_grads(self, a_s, b_s, a_t, b_t, b_s_t, a_s_inv, b_s_inv, a_t_inv, b_t_inv, coef_row, coef_col,
+                  row_offset, global_batch, temperature, upstream, grad_dtype):
+        S = self._logits(a_s, b_s, a_s_inv, b_s_inv)
+        G = torch.exp(S - 1) * (coef_row[0][:, None] + coef_col[0][None, :])
+        if a_t is not None:
+            T = self._logits(a_t, b_t, a_t_inv, b_t_inv)
+            G = G + torch.exp((S - 1) / temperature) * (coef_row[1][:, None] + coef_col[1][None, :])
+            G = G - torch.exp((T - 1) / temperature) * (coef_row[2][:, None] + coef_col[2][None, :])
+        acc = (G * b_s_inv[None, :]) @ b_s_t.t()                       # sum_j G_ij c_j b_j
+        rows = a_s.shape[0]
+        gi = row_offset + torch.arange(rows)
+        acc = acc - (upstream[0].double() / global_batch) * b_s_inv[gi][:, None] * b_s.double()[gi]
+        a_hat = a_s.double() * a_s_inv[:, None]
+        grad = a_s_inv[:, None] * (acc - a_hat * (a_hat * acc).sum(1, keepdim=True))
+        return grad
