@@ -146,12 +146,40 @@ def make_clip(cfg, device, gen, rows, offset):
 # timing helpers
 # ------------------------------------------------------------------------------------------------
 class Timer:
+    """Times exactly `steps` executions of `fn` with one CUDA-event pair per step (summed), after `warmup` untimed
+    executions, barrier + synchronize on both sides, max over ranks.  With graph=True the step is captured once into
+    a CUDA graph (the C ABI only enqueues on the current stream and never allocates or synchronises) and each timed
+    step is one replay, so the number is device throughput rather than Python launch overhead; if capture fails the
+    step runs eagerly and `mode` says so."""
+
     def __init__(self, device, flush: bool):
         self.flush_buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=device) if flush else None
+        self.mode = "eager"
 
-    def run(self, fn, steps, warmup, dist=None):
-        for _ in range(warmup):
+    def _capture(self, fn):
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                fn()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
             fn()
+        return g
+
+    def run(self, fn, steps, warmup, dist=None, graph=True):
+        run_step = fn
+        if graph:
+            try:
+                g = self._capture(fn)
+                run_step, self.mode = g.replay, "cuda-graph replay"
+            except Exception as e:                                  # noqa: BLE001 -- report and fall back to eager
+                torch.cuda.synchronize()
+                self.mode = f"eager (graph capture failed: {type(e).__name__})"
+        for _ in range(warmup):
+            run_step()
         torch.cuda.synchronize()
         if dist is not None:
             dist.barrier()
@@ -162,7 +190,7 @@ class Timer:
                 self.flush_buf.zero_()
             s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             s.record()
-            fn()
+            run_step()
             e.record()
             pairs.append((s, e))
         torch.cuda.synchronize()
@@ -177,21 +205,27 @@ class Timer:
         return total_ms
 
 
-def time_kernel(fn, iters, flush_buf=None):
-    """Average duration of one launch sequence `fn` (CUDA events on the current stream)."""
+def time_kernel(fn, iters, device):
+    """Average duration of the launch(es) in `fn`, measured on the launching stream with one event pair per launch.
+    `fn` is captured into a CUDA graph and replays alternate with a 256 MiB L2 flush, all enqueued ahead of the GPU,
+    so each pair brackets exactly one cold-L2 execution and no host time."""
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=device)
     fn()
     torch.cuda.synchronize()
-    tot = 0.0
-    for _ in range(iters):
-        if flush_buf is not None:
-            flush_buf.zero_()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        fn()
+    pairs = []
+    for _ in range(iters + 2):
+        flush.zero_()
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
-        fn()
+        g.replay()
         e.record()
-        torch.cuda.synchronize()
-        tot += s.elapsed_time(e)
-    return tot / iters
+        pairs.append((s, e))
+    torch.cuda.synchronize()
+    times = [s.elapsed_time(e) for s, e in pairs[2:]]
+    return sum(times) / len(times)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -235,24 +269,28 @@ def bench_tower(cfg, name, args, device, dist, world, pk, with_cpu):
     algo_bytes = 6 * total_el                                   # read s, read t, write ds; bf16
     in_bytes = 4 * total_el
     timer = Timer(device, flush=in_bytes < L2_BYTES)
+    step()
     _lib.LAUNCHES = 0
+    step()
+    launches = _lib.LAUNCHES * args.steps                         # our kernels per step x timed steps
     with ClockSampler(torch.cuda.current_device()) as clk:
         total_ms = timer.run(step, args.steps, args.warmup, dist)
-    launches = _lib.LAUNCHES // (args.steps + args.warmup) * args.steps
     ms = total_ms / args.steps
     value = world * cfg["batch"] / (ms * 1e-3)
 
-    # dominant kernel, timed alone through the raw C-ABI launch (same inputs, same stream)
+    # dominant kernel, timed alone through the raw C-ABI launch (same inputs, same stream, preallocated outputs)
     kernels = {}
     s_h, t_h = [x.detach() for x in stu["representations"]], tea["representations"]
-    kernels["hidden_rep_mse"] = (lambda: ops.launch_mse(s_h, t_h, len(s_h), 1.0, [True] * len(s_h)),
+    p_h, _, g_h = ops.launch_mse(s_h, t_h, len(s_h), 1.0, [True] * len(s_h))
+    kernels["hidden_rep_mse"] = (lambda: ops.launch_mse(s_h, t_h, len(s_h), 1.0, [True] * len(s_h), out=(p_h, g_h)),
                                  6 * elements["hidden_rep_mse"])
     s_a, t_a = [x.detach() for x in stu["attention_probs"]], tea["attention_probs"]
-    kernels["attention_probs_kl"] = (lambda: ops.launch_attn_kl(s_a, t_a, len(s_a), 1.0, [True] * len(s_a)),
+    p_a, _, g_a = ops.launch_attn_kl(s_a, t_a, len(s_a), 1.0, [True] * len(s_a))
+    kernels["attention_probs_kl"] = (lambda: ops.launch_attn_kl(s_a, t_a, len(s_a), 1.0, [True] * len(s_a), out=(p_a, g_a)),
                                      6 * elements["attention_probs_kl"])
     kres = {}
     for kname, (fn, nbytes) in kernels.items():
-        k_ms = time_kernel(fn, 20, timer.flush_buf)
+        k_ms = time_kernel(fn, 20, device)
         kres[kname] = {"ms": round(k_ms, 5), "algorithmic_bytes": nbytes, "gbs": round(nbytes / k_ms / 1e6, 1),
                        "frac": round(nbytes / k_ms / 1e6 / pk["hbm"], 4)}
     dom = max(kres, key=lambda k: kres[k]["algorithmic_bytes"])
@@ -278,7 +316,7 @@ def bench_tower(cfg, name, args, device, dist, world, pk, with_cpu):
         loss.backward()
         loss_host.copy_(loss.detach(), non_blocking=True)
         torch.cuda.current_stream().synchronize()
-    e2e_ms = Timer(device, flush=False).run(e2e_step, max(3, args.steps // 4), 2, dist) / max(3, args.steps // 4)
+    e2e_ms = Timer(device, flush=False).run(e2e_step, max(3, args.steps // 4), 2, dist, graph=False) / max(3, args.steps // 4)
     e2e = {"value": round(world * cfg["batch"] / (e2e_ms * 1e-3), 1), "unit": "samples/s", "ms_per_step": round(e2e_ms, 4),
            "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4}
 
@@ -286,7 +324,7 @@ def bench_tower(cfg, name, args, device, dist, world, pk, with_cpu):
     if with_cpu:
         cpu = cpu_tower(cfg, stu, tea, budget_s=20.0)
     return dict(value=value, ms=ms, launches=launches, roofline=roofline, e2e=e2e, clocks=clk.summary(), cpu=cpu,
-                flush=timer.flush_buf is not None, algo_bytes=algo_bytes)
+                flush=timer.flush_buf is not None, algo_bytes=algo_bytes, mode=timer.mode)
 
 
 def cpu_tower(cfg, stu, tea, budget_s):
@@ -330,15 +368,17 @@ def bench_clip(cfg, args, device, dist, rank, world, pk, steps, warmup):
         res = clip_contrastive(si, st, ti, tt, T, want_hard=True, want_soft=True, group=group)
         (0.5 * res["hard_label"] + 0.5 * res["soft_label"]).backward()
     timer = Timer(device, flush=4 * b * d * 2 < L2_BYTES)
+    step()
     _lib.LAUNCHES = 0
-    total_ms = timer.run(step, steps, warmup, dist)
-    launches = _lib.LAUNCHES // (steps + warmup) * steps
+    step()
+    launches = _lib.LAUNCHES * steps
+    total_ms = timer.run(step, steps, warmup, dist, graph=(world == 1))
     ms = total_ms / steps
     flops = 12.0 * b * b * d                                     # credited, whole job
     tf = flops / (ms * 1e-3) / 1e12
     return {"workload": cfg["desc"], "global_batch": b, "dim": d, "temperature": T, "n_gpus": world,
             "value": round(b / (ms * 1e-3), 1), "unit": "samples/s", "ms_per_step": round(ms, 4), "steps": steps,
-            "scaling": "strong", "gpu_launches": launches, "l2_flush": timer.flush_buf is not None,
+            "scaling": "strong", "gpu_launches": launches, "l2_flush": timer.flush_buf is not None, "timing": timer.mode,
             "roofline": {"bound": "tensor", "kernel": "clip_fwd_kernel + clip_bwd_kernel (fused tcgen05, both directions)",
                          "achieved": round(tf, 2), "peak": pk["tf_burst"] * world, "unit": "TFLOP/s",
                          "frac": round(tf / (pk["tf_burst"] * world), 4),
@@ -373,7 +413,7 @@ def run_ours(args):
                 "data": "synthetic (seed 2022)",
                 "config": {"workload": cfg["desc"], "parallelism": f"{world} independent replica(s); this path has no exchange step",
                            "l2": "flushed before every timed step" if r["flush"] else "inputs (student+teacher) larger than the 126 MB L2",
-                           "algorithmic_bytes_per_step": r["algo_bytes"]},
+                           "algorithmic_bytes_per_step": r["algo_bytes"], "timing": r["mode"]},
                 "roofline": r["roofline"], "e2e": r["e2e"], "gpu_launches": r["launches"], "clocks": r["clocks"]}
         if r["cpu"]:
             line["cpu_baseline"] = r["cpu"]
@@ -389,7 +429,7 @@ def run_ours(args):
                 t = bench_tower(WORKLOADS["text_stage"], "text_stage", args, device, dist, world, pk, with_cpu=False)
                 line["text_stage"] = {"workload": WORKLOADS["text_stage"]["desc"], "value": round(t["value"], 1),
                                       "unit": "samples/s", "ms_per_step": round(t["ms"], 5), "roofline": t["roofline"],
-                                      "e2e": t["e2e"], "gpu_launches": t["launches"]}
+                                      "e2e": t["e2e"], "gpu_launches": t["launches"], "timing": t["mode"]}
         line["contrastive"] = extras
     else:
         with ClockSampler(torch.cuda.current_device()) as clk:

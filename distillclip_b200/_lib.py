@@ -26,15 +26,15 @@ SIGNATURES = {
     "dcb_finalize": [C.c_int, _vpp, _i32p, _f32p, _f32p, _vp, _vp],
     "dcb_rescale_grads": [C.c_int, _vpp, _i64p, C.c_int, _vpp, _f32p, _vp],
     "dcb_row_inv_norm": [C.c_int, _vpp, _vpp, _i64p, C.c_int64, C.c_int, _vp],
-    "dcb_transpose_to_bf16": [_vp, _vp, C.c_int64, C.c_int64, C.c_int64, C.c_int, _vp],
+    "dcb_transpose_norm_f16": [_vp, _vp, _vp, C.c_int64, C.c_int64, C.c_int64, C.c_int, _vp],
     "dcb_clip_row_stats": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int64, C.c_int64, C.c_int64, C.c_int64,
                            C.c_int, C.c_float, _vp, _vp, _vp, _vp, _vp],
     "dcb_clip_losses": [_vp, _vp, C.c_int64, C.c_int64, C.c_int64, C.c_float, C.c_int, _vp, _vp, _vp],
-    "dcb_clip_grad_coef": [_vp, C.c_int64, C.c_int64, C.c_float, C.c_int, _vp, _vp, _vp],
-    "dcb_clip_row_grads": [_vp, _vp, _vp, _vp, _vp, C.c_int64, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int64, C.c_int64,
-                           C.c_int64, C.c_int, C.c_float, _vp, _vp],
+    "dcb_clip_grad_coef": [_vp, C.c_int64, C.c_int64, C.c_float, C.c_int, _vp, _vp, _vp, _vp],
+    "dcb_clip_row_grads": [_vp, _vp, _vp, _vp, _vp, C.c_int64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int64,
+                           C.c_int64, C.c_int64, C.c_int, C.c_float, _vp, _vp],
     "dcb_clip_grad_finish": [_vp, C.c_int, _vp, _vp, _vp, _vp, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int64,
-                             _vp, C.c_int, _vp, C.c_int, _vp],
+                             _vp, _vp, _vp, C.c_int, _vp, C.c_int, _vp],
     "dcb_logits_row_stats": [_vp, C.c_int64, C.c_int64, _vp, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_float,
                              C.c_int, _vp, _vp, _vp],
     "dcb_logits_row_grads": [_vp, C.c_int64, C.c_int64, _vp, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_float,

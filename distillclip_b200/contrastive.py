@@ -67,21 +67,25 @@ class CudaEngine:
         return sums, out
 
     def coef(self, stats, global_batch, temperature, has_teacher, upstream):
+        """-> (coef [3, rows], gmax [1]): gradient coefficients and the bound max_i sum_k |coef_k,i|."""
         rows = stats.shape[1]
         coef = torch.empty(3, rows, dtype=torch.float32, device=stats.device)
+        gmax = torch.empty(1, dtype=torch.float32, device=stats.device)
         _lib.call("dcb_clip_grad_coef", _vp(stats), rows, int(global_batch), float(temperature or 1.0),
-                  int(has_teacher), _vp(upstream), _vp(coef), ops._stream_ptr())
-        return coef
+                  int(has_teacher), _vp(upstream), _vp(coef), _vp(gmax), ops._stream_ptr())
+        return coef, gmax
 
-    def transpose_bf16(self, b):
+    def transpose_norm(self, b, b_inv):
+        """fp16 [D, pitch] = (b * b_inv[:, None]).T, the K-major b-side operand of the gradient GEMM."""
         rows, dim = b.shape
         pitch = (rows + 7) // 8 * 8
-        out = torch.empty(dim, pitch, dtype=torch.bfloat16, device=b.device)
-        _lib.call("dcb_transpose_to_bf16", _vp(b), _vp(out), rows, dim, pitch, ops.dtype_code(b), ops._stream_ptr())
+        out = torch.empty(dim, pitch, dtype=torch.float16, device=b.device)
+        _lib.call("dcb_transpose_norm_f16", _vp(b), _vp(b_inv), _vp(out), rows, dim, pitch, ops.dtype_code(b),
+                  ops._stream_ptr())
         return out
 
     def row_grads(self, a_s, b_s, a_t, b_t, b_s_t, a_s_inv, b_s_inv, a_t_inv, b_t_inv, coef_row, coef_col,
-                  row_offset, global_batch, temperature, upstream, grad_dtype):
+                  gmax_row, gmax_col, row_offset, global_batch, temperature, upstream, grad_dtype):
         rows, dim = a_s.shape
         cols = b_s.shape[0]
         lib = _lib.load()
@@ -89,11 +93,12 @@ class CudaEngine:
         acc = torch.empty(n_split, rows, dim, dtype=torch.float32, device=a_s.device)
         _lib.call("dcb_clip_row_grads", _vp(a_s), _vp(b_s), _vp(a_t), _vp(b_t), _vp(b_s_t), b_s_t.shape[1],
                   _vp(a_s_inv), _vp(b_s_inv), _vp(a_t_inv), _vp(b_t_inv), _vp(coef_row), _vp(coef_col),
-                  rows, cols, dim, ops.dtype_code(a_s), float(temperature or 1.0), _vp(acc), ops._stream_ptr())
+                  _vp(gmax_row), _vp(gmax_col), rows, cols, dim, ops.dtype_code(a_s), float(temperature or 1.0),
+                  _vp(acc), ops._stream_ptr())
         grad = torch.empty(rows, dim, dtype=grad_dtype, device=a_s.device)
         _lib.call("dcb_clip_grad_finish", _vp(acc), n_split, _vp(a_s), _vp(a_s_inv), _vp(b_s), _vp(b_s_inv), rows, cols,
-                  dim, int(row_offset), int(global_batch), _vp(upstream), ops.dtype_code(a_s), _vp(grad),
-                  ops._DT[grad_dtype], ops._stream_ptr())
+                  dim, int(row_offset), int(global_batch), _vp(upstream), _vp(gmax_row), _vp(gmax_col),
+                  ops.dtype_code(a_s), _vp(grad), ops._DT[grad_dtype], ops._stream_ptr())
         return grad
 
 
@@ -173,8 +178,8 @@ def contrastive_backward(engine, saved, upstream, want_img=True, want_txt=True, 
     # column softmax statistics of a direction = row statistics of the opposite direction, for ALL rows
     stats_i2t_all = _all_gather_cols(s["stats_i2t"], group, world)
     stats_t2i_all = _all_gather_cols(s["stats_t2i"], group, world)
-    coef_i2t_all = engine.coef(stats_i2t_all, b_global, T, has_teacher, upstream)
-    coef_t2i_all = engine.coef(stats_t2i_all, b_global, T, has_teacher, upstream)
+    coef_i2t_all, gmax_i2t = engine.coef(stats_i2t_all, b_global, T, has_teacher, upstream)
+    coef_t2i_all, gmax_t2i = engine.coef(stats_t2i_all, b_global, T, has_teacher, upstream)
     coef_i2t = coef_i2t_all[:, loc].contiguous() if world > 1 else coef_i2t_all
     coef_t2i = coef_t2i_all[:, loc].contiguous() if world > 1 else coef_t2i_all
 
@@ -182,13 +187,15 @@ def contrastive_backward(engine, saved, upstream, want_img=True, want_txt=True, 
         return None if x is None else x[loc]
     g_img = g_txt = None
     if want_img:
-        g_img = engine.row_grads(s["si"], s["st_all"], s["ti"], s["tt_all"], engine.transpose_bf16(s["st_all"]),
+        g_img = engine.row_grads(s["si"], s["st_all"], s["ti"], s["tt_all"],
+                                 engine.transpose_norm(s["st_all"], s["st_inv_all"]),
                                  local(s["si_inv_all"]), s["st_inv_all"], local(s["ti_inv_all"]), s["tt_inv_all"],
-                                 coef_i2t, coef_t2i_all, offset, b_global, T, upstream, grad_dtype or s["si"].dtype)
+                                 coef_i2t, coef_t2i_all, gmax_i2t, gmax_t2i, offset, b_global, T, upstream, grad_dtype or s["si"].dtype)
     if want_txt:
-        g_txt = engine.row_grads(s["st"], s["si_all"], s["tt"], s["ti_all"], engine.transpose_bf16(s["si_all"]),
+        g_txt = engine.row_grads(s["st"], s["si_all"], s["tt"], s["ti_all"],
+                                 engine.transpose_norm(s["si_all"], s["si_inv_all"]),
                                  local(s["st_inv_all"]), s["si_inv_all"], local(s["tt_inv_all"]), s["ti_inv_all"],
-                                 coef_t2i, coef_i2t_all, offset, b_global, T, upstream, grad_dtype or s["st"].dtype)
+                                 coef_t2i, coef_i2t_all, gmax_t2i, gmax_i2t, offset, b_global, T, upstream, grad_dtype or s["st"].dtype)
     return g_img, g_txt
 
 

@@ -12,7 +12,7 @@ char* error_buffer() {
 // ---------------------------------------------------------------------------------------------
 // finalize: out[k] = scale[k] * sum(partials[k]) ; out[n] = sum_k percent[k] * out[k]
 // (reference model/_loss.py:195-200 -- `cal_res[n] * scale` then `loss += cal_res[n] * percent[n]`)
-// One CTA; partials are summed in index order with a fixed tree, so the result is run-to-run identical.
+// One CTA; partials are summed with a fixed assignment and a fixed tree, so the result is run-to-run identical.
 // ---------------------------------------------------------------------------------------------
 struct FinalizeParams {
     int n_terms;
@@ -22,23 +22,34 @@ struct FinalizeParams {
     float percent[DCB_MAX_TERMS];
 };
 
-__global__ void __launch_bounds__(256) finalize_kernel(const __grid_constant__ FinalizeParams p,
-                                                       float* __restrict__ out) {
+// One warp per term (<= 16 terms -> 512 threads): lane-strided loads in index order, fixed shuffle tree.
+__global__ void __launch_bounds__(32 * DCB_MAX_TERMS) finalize_kernel(const __grid_constant__ FinalizeParams p,
+                                                                      float* __restrict__ out) {
     __shared__ double term_sum[DCB_MAX_TERMS];
-    for (int k = 0; k < p.n_terms; ++k) {
-        double v = 0.0;
-        for (int i = threadIdx.x; i < p.counts[k]; i += blockDim.x) v += p.partials[k][i];
-        v = block_sum(v);
-        if (threadIdx.x == 0) term_sum[k] = v;
-        __syncthreads();
+    const int k = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (k < p.n_terms) {
+        const double* __restrict__ src = p.partials[k];
+        const int n = p.counts[k];
+        double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;
+        int i = lane;
+        for (; i + 96 < n; i += 128) {
+            v0 += src[i];
+            v1 += src[i + 32];
+            v2 += src[i + 64];
+            v3 += src[i + 96];
+        }
+        for (; i < n; i += 32) v0 += src[i];
+        const double v = warp_sum((v0 + v1) + (v2 + v3));
+        if (lane == 0) term_sum[k] = v;
     }
+    __syncthreads();
     if (threadIdx.x == 0) {
         float total = 0.f;
-        for (int k = 0; k < p.n_terms; ++k) {
+        for (int t = 0; t < p.n_terms; ++t) {
             // same rounding points as the reference: fp32 value, * scale, * percent, += in fp32
-            const float res = (float)term_sum[k] * p.scale[k];
-            out[k] = res;
-            total += res * p.percent[k];
+            const float res = (float)term_sum[t] * p.scale[t];
+            out[t] = res;
+            total += res * p.percent[t];
         }
         out[p.n_terms] = total;
     }
@@ -94,7 +105,7 @@ int dcb_finalize(int n_terms, const double* const* partials, const int32_t* coun
         p.scale[k] = scale ? scale[k] : 1.f;
         p.percent[k] = percent ? percent[k] : 0.f;
     }
-    finalize_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(p, out);
+    finalize_kernel<<<1, 32 * DCB_MAX_TERMS, 0, static_cast<cudaStream_t>(stream)>>>(p, out);
     DCB_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -110,7 +121,7 @@ int dcb_rescale_grads(int n_seg, void* const* grads, const int64_t* numel, int d
         DCB_REQUIRE(expected[k] != 0.f, "segment %d: expected upstream gradient must be non-zero", k);
         p.seg[k] = RescaleSeg{grads[k], (long long)numel[k], upstream[k], expected[k]};
     }
-    dim3 grid(kNumSMs * 4, n_seg);
+    dim3 grid(kNumSMs * 2, n_seg);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     switch (dtype) {
         case DCB_BF16: rescale_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(p); break;

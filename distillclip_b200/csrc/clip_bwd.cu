@@ -10,10 +10,12 @@
 // and d total / d a_hat_i = sum_j G_ij b_hat_j.  The delta term is added in fp32 by dcb_clip_grad_finish.
 //
 // Per CTA: a block of 128 a-side rows and one chunk (<= 256 columns) of the embedding dimension.  Loop over
-// 64-wide column tiles:  tcgen05.mma S,T (M=128,N=64) -> epilogue warps turn the accumulators into the bf16 tile
-// G_ij * c_j, written to shared memory in the K-major 128B-swizzle layout -> tcgen05.mma acc[128 x Dc] += G * bT
-// (bT = student b-side transposed once per call, so both operands are K-major).  S/T accumulators are double
-// buffered in TMEM (2 x 128 columns) next to the gradient accumulator (<= 256 columns).
+// 64-wide column tiles:  tcgen05.mma S,T (M=128,N=64) -> epilogue warps turn the accumulators into the fp16 tile
+// G_ij * 2^k, written to shared memory in the K-major 128B-swizzle layout -> tcgen05.mma acc[128 x Dc] += G * b_hatT
+// (b_hatT = normalised student b-side, transposed to fp16 once per call, so both operands are K-major).  fp16 keeps
+// 11 significant bits of G (bf16: 8 -> ~1.3e-3 gradient error, measured); the power-of-two scale 2^k, derived on the
+// device from the largest possible |G| (max row coefficient + max column coefficient), keeps G in fp16's normal range.
+// S/T accumulators are double buffered in TMEM (2 x 128 columns) next to the gradient accumulator (<= 256 columns).
 //
 // Warp roles (256 threads): warp 0 = TMA ring producer, warp 1 = TMEM alloc + MMA issuer, warp 2 = bT producer,
 // warp 3 idle, warps 4-7 = epilogue.
@@ -43,12 +45,22 @@ struct ClipBwdParams {
     const float* b_inv_tea;
     const float* coef_row;    // [3][rows]  alpha, beta, gamma of this direction's rows
     const float* coef_col;    // [3][cols]  alpha', beta', gamma' (opposite direction, all columns)
+    const float* gmax_row;    // [1] max_i (|alpha_i| + |beta_i| + |gamma_i|) over this direction's rows (all ranks)
+    const float* gmax_col;    // [1] same for the opposite direction
     float* acc;               // [n_split][rows][dim] fp32 partial gradients w.r.t. a_hat
     int rows, cols, dim;
     int dc;                   // columns of the embedding dimension per CTA (multiple of 16, <= 256)
     int n_split, col_tiles;
     float inv_temp;
 };
+
+// 2^k with 2^k * gmax <= 2^14: G * 2^k stays inside fp16's normal range with headroom for the accumulate
+__device__ __forceinline__ float grad_tile_scale(float gmax) {
+    if (!(gmax > 0.f) || !isfinite(gmax)) return 1.f;
+    int e;
+    frexpf(gmax, &e);                 // gmax = m * 2^e, m in [0.5, 1)
+    return ldexpf(1.f, 14 - e);
+}
 
 __device__ __forceinline__ float ex2b(float x) {
     float y;
@@ -203,6 +215,7 @@ clip_bwd_kernel(const __grid_constant__ CUtensorMap map_a_stu, const __grid_cons
         const float ra = row_ok ? __ldg(p.coef_row + grow) : 0.f;
         const float rbeta = (kTeacher && row_ok) ? __ldg(p.coef_row + p.rows + grow) : 0.f;
         const float rg = (kTeacher && row_ok) ? __ldg(p.coef_row + 2 * (size_t)p.rows + grow) : 0.f;
+        const float gscale = grad_tile_scale(__ldg(p.gmax_row) + __ldg(p.gmax_col));
         for (int t = 0; t < n_tiles; ++t) {
             const int as = t & 1;
             const int col0 = (tile_begin + t) * kBN;
@@ -243,9 +256,9 @@ clip_bwd_kernel(const __grid_constant__ CUtensorMap map_a_stu, const __grid_cons
                             g = fmaf(ex2b(fmaf(u, k1t, n1t)), rbeta + sc[3 * kBN + cc], g);
                             g = fmaf(-ex2b(fmaf(v, k2t, n1t)), rg + sc[4 * kBN + cc], g);
                         }
-                        g2[e] = g * cs;          // fold c_j: acc_i = sum_j (G_ij c_j) b_j ; cs == 0 masks columns >= cols
+                        g2[e] = g * gscale;      // columns >= cols meet all-zero rows of b_hatT, so they need no mask
                     }
-                    packed[(ch * 32 + c) >> 1] = pack2<__nv_bfloat16>(g2[0], g2[1]);
+                    packed[(ch * 32 + c) >> 1] = pack2<__half>(g2[0], g2[1]);
                 }
             }
             // S/T accumulators of this stage are in registers now
@@ -325,10 +338,11 @@ extern "C" int dcb_clip_row_grads(const void* stu_a, const void* stu_b, const vo
                                   const void* stu_b_t, int64_t bt_pitch_elems,
                                   const float* stu_a_inv, const float* stu_b_inv, const float* tea_a_inv,
                                   const float* tea_b_inv, const float* coef_row, const float* coef_col,
-                                  int64_t rows_local, int64_t cols, int64_t dim, int dtype, float temperature,
+                                  const float* gmax_row, const float* gmax_col, int64_t rows_local, int64_t cols, int64_t dim, int dtype, float temperature,
                                   float* acc_parts, void* stream) {
     using namespace dcb;
-    DCB_REQUIRE(stu_a && stu_b && stu_b_t && stu_a_inv && stu_b_inv && coef_row && coef_col && acc_parts, "NULL pointer argument");
+    DCB_REQUIRE(stu_a && stu_b && stu_b_t && stu_a_inv && stu_b_inv && coef_row && coef_col && gmax_row && gmax_col && acc_parts,
+                "NULL pointer argument");
     DCB_REQUIRE(dtype == DCB_BF16 || dtype == DCB_F16, "the fused contrastive kernel takes bf16 or fp16 embeddings");
     DCB_REQUIRE(rows_local >= 1 && cols >= 1 && dim >= 8 && dim % 8 == 0, "bad shape");
     DCB_REQUIRE(bt_pitch_elems >= cols && bt_pitch_elems % 8 == 0, "bT pitch must be >= cols and a multiple of 8 elements");
@@ -354,6 +368,8 @@ extern "C" int dcb_clip_row_grads(const void* stu_a, const void* stu_b, const vo
     p.b_inv_tea = tea_b_inv;
     p.coef_row = coef_row;
     p.coef_col = coef_col;
+    p.gmax_row = gmax_row;
+    p.gmax_col = gmax_col;
     p.acc = acc_parts;
     p.rows = (int)rows_local;
     p.cols = (int)cols;
@@ -365,14 +381,16 @@ extern "C" int dcb_clip_row_grads(const void* stu_a, const void* stu_b, const vo
     const int row_blocks = (int)((rows_local + bwd::kBM - 1) / bwd::kBM);
     const int chunks = (int)((dim + dc - 1) / dc);
     const uint32_t idesc_st = tc::umma_idesc_f16(bwd::kBM, bwd::kBN, dtype == DCB_BF16 ? 1 : 0);
-    const uint32_t idesc_grad = tc::umma_idesc_f16(bwd::kBM, dc, 1);     // G and bT are always bf16
+    const uint32_t idesc_grad = tc::umma_idesc_f16(bwd::kBM, dc, 0);     // G and b_hatT are always fp16
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     dim3 grid((unsigned)(row_blocks * p.n_split), (unsigned)chunks);
     if (teacher) {
-        DCB_CUDA_OK(cudaFuncSetAttribute(clip_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd::kSmemBytes));
+        static const cudaError_t attr_true = cudaFuncSetAttribute(clip_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd::kSmemBytes);
+        DCB_CUDA_OK(attr_true);     // set once per process (not a stream operation; kept out of graph captures)
         clip_bwd_kernel<true><<<grid, bwd::kThreads, bwd::kSmemBytes, st>>>(ma_s, mb_s, ma_t, mb_t, mbt, p, idesc_st, idesc_grad);
     } else {
-        DCB_CUDA_OK(cudaFuncSetAttribute(clip_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd::kSmemBytes));
+        static const cudaError_t attr_false = cudaFuncSetAttribute(clip_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd::kSmemBytes);
+        DCB_CUDA_OK(attr_false);     // set once per process (not a stream operation; kept out of graph captures)
         clip_bwd_kernel<false><<<grid, bwd::kThreads, bwd::kSmemBytes, st>>>(ma_s, mb_s, ma_t, mb_t, mbt, p, idesc_st, idesc_grad);
     }
     DCB_CUDA_OK(cudaGetLastError());

@@ -167,8 +167,18 @@ clip_fwd_kernel(const __grid_constant__ CUtensorMap map_a_stu, const __grid_cons
         const float k1 = r_s * LOG2E, k1t = r_s * LOG2E * p.inv_temp, k2t = r_t * LOG2E * p.inv_temp;
         const float n1 = -LOG2E, n1t = -LOG2E * p.inv_temp;
         const int diag_col = p.row_offset + grow;           // global column holding this row's label
+        // Row totals with Kahan compensation: sums of each 32-column chunk start from zero (small magnitudes) and are
+        // folded into the running totals with an error term, so Zs/Zt keep ~1e-7 relative accuracy even for B = 32768
+        // (KL_i is a small difference of log Zs and log Zt; plain fp32 accumulation costs ~1e-4 on the loss, measured).
         float A = 0.f, Zs = 0.f, Zt = 0.f, W = 0.f, diag = 0.f;
+        float cA = 0.f, cZs = 0.f, cZt = 0.f, cW = 0.f;
         bool have_diag = false;
+        auto kahan = [](float& sum, float& comp, float x) {
+            const float y = x - comp;
+            const float t = sum + y;
+            comp = (t - sum) - y;
+            sum = t;
+        };
         for (int t = 0; t < n_tiles; ++t) {
             const int as = t & 1;
             const uint32_t aphase = (t >> 1) & 1;
@@ -193,17 +203,22 @@ clip_fwd_kernel(const __grid_constant__ CUtensorMap map_a_stu, const __grid_cons
                 tmem_ld_wait();
                 const float* scs = sc + ch * 32;
                 const float* sct = sc + kBN + ch * 32;
+                float a0 = 0.f, a1 = 0.f, zs0 = 0.f, zs1 = 0.f, zt0 = 0.f, zt1 = 0.f, w0 = 0.f, w1 = 0.f;
                 if (!edge) {
 #pragma unroll
-                    for (int c = 0; c < 32; ++c) {
-                        const float u = sv[c] * scs[c];
-                        A += ex2(fmaf(u, k1, n1));
+                    for (int c = 0; c < 32; c += 2) {
+                        const float u0 = sv[c] * scs[c], u1 = sv[c + 1] * scs[c + 1];
+                        a0 += ex2(fmaf(u0, k1, n1));
+                        a1 += ex2(fmaf(u1, k1, n1));
                         if (kTeacher) {
-                            const float v = tv[c] * sct[c];
-                            const float et = ex2(fmaf(v, k2t, n1t));
-                            Zs += ex2(fmaf(u, k1t, n1t));
-                            Zt += et;
-                            W = fmaf(et, fmaf(v, r_t, -(u * r_s)), W);
+                            const float v0 = tv[c] * sct[c], v1 = tv[c + 1] * sct[c + 1];
+                            const float et0 = ex2(fmaf(v0, k2t, n1t)), et1 = ex2(fmaf(v1, k2t, n1t));
+                            zs0 += ex2(fmaf(u0, k1t, n1t));
+                            zs1 += ex2(fmaf(u1, k1t, n1t));
+                            zt0 += et0;
+                            zt1 += et1;
+                            w0 = fmaf(et0, fmaf(v0, r_t, -(u0 * r_s)), w0);
+                            w1 = fmaf(et1, fmaf(v1, r_t, -(u1 * r_s)), w1);
                         }
                     }
                 } else {
@@ -214,18 +229,24 @@ clip_fwd_kernel(const __grid_constant__ CUtensorMap map_a_stu, const __grid_cons
                         const float u = sv[c] * scs[c];
                         const float s = u * r_s;
                         if (gc == diag_col) { diag = s; have_diag = true; }
-                        A += ok ? ex2(fmaf(u, k1, n1)) : 0.f;
+                        a0 += ok ? ex2(fmaf(u, k1, n1)) : 0.f;
                         if (p.dump_s && row_ok && ok) p.dump_s[(size_t)grow * p.cols + gc] = s;
                         if (kTeacher) {
                             const float v = tv[c] * sct[c];
                             const float tt = v * r_t;
                             const float et = ok ? ex2(fmaf(v, k2t, n1t)) : 0.f;
-                            Zs += ok ? ex2(fmaf(u, k1t, n1t)) : 0.f;
-                            Zt += et;
-                            W = fmaf(et, tt - s, W);
+                            zs0 += ok ? ex2(fmaf(u, k1t, n1t)) : 0.f;
+                            zt0 += et;
+                            w0 = fmaf(et, tt - s, w0);
                             if (p.dump_t && row_ok && ok) p.dump_t[(size_t)grow * p.cols + gc] = tt;
                         }
                     }
+                }
+                kahan(A, cA, a0 + a1);
+                if (kTeacher) {
+                    kahan(Zs, cZs, zs0 + zs1);
+                    kahan(Zt, cZt, zt0 + zt1);
+                    kahan(W, cW, w0 + w1);
                 }
             }
             tc_fence_before_sync();
@@ -324,10 +345,12 @@ extern "C" int dcb_clip_row_stats(const void* stu_a, const void* stu_b, const vo
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     dim3 grid((unsigned)(row_blocks * p.n_split));
     if (teacher) {
-        DCB_CUDA_OK(cudaFuncSetAttribute(clip_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd::kSmemBytes));
+        static const cudaError_t attr_true = cudaFuncSetAttribute(clip_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd::kSmemBytes);
+        DCB_CUDA_OK(attr_true);     // set once per process (not a stream operation; kept out of graph captures)
         clip_fwd_kernel<true><<<grid, fwd::kThreads, fwd::kSmemBytes, st>>>(ma_s, mb_s, ma_t, mb_t, p, idesc);
     } else {
-        DCB_CUDA_OK(cudaFuncSetAttribute(clip_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd::kSmemBytes));
+        static const cudaError_t attr_false = cudaFuncSetAttribute(clip_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd::kSmemBytes);
+        DCB_CUDA_OK(attr_false);     // set once per process (not a stream operation; kept out of graph captures)
         clip_fwd_kernel<false><<<grid, fwd::kThreads, fwd::kSmemBytes, st>>>(ma_s, mb_s, ma_t, mb_t, p, idesc);
     }
     DCB_CUDA_OK(cudaGetLastError());

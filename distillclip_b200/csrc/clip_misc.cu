@@ -1,4 +1,4 @@
-// Small kernels around the fused contrastive path: inverse L2 norms, the one-off b-side transpose,
+// Small kernels around the fused contrastive path: inverse L2 norms, the one-off normalised b-side transpose,
 // loss values from the row statistics, gradient coefficients, and the normalisation Jacobian.
 #include "common.cuh"
 
@@ -24,22 +24,23 @@ __global__ void __launch_bounds__(256) inv_norm_kernel(const T* __restrict__ x, 
 }
 
 // ---------------------------------------------------------------------------------------------
-// out[d][j] = bf16(in[j][d])     in: [rows, dim] row-major, out: [dim, pitch] row-major (pitch >= rows)
+// out[d][j] = fp16(in[j][d] * inv_norm[j])   in: [rows, dim] row-major, out: [dim, pitch] row-major (pitch >= rows)
+// (normalised entries are bounded by 1, so fp16 cannot overflow and keeps 11 significant bits)
 // ---------------------------------------------------------------------------------------------
 template <typename T>
-__global__ void __launch_bounds__(256) transpose_to_bf16_kernel(const T* __restrict__ in, __nv_bfloat16* __restrict__ out,
-                                                                int rows, int dim, long long pitch) {
+__global__ void __launch_bounds__(256) transpose_norm_f16_kernel(const T* __restrict__ in, const float* __restrict__ inv_norm,
+                                                                 __half* __restrict__ out, int rows, int dim, long long pitch) {
     __shared__ float tile[32][33];
     const int j0 = blockIdx.x * 32, d0 = blockIdx.y * 32;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;      // 32 x 8
     for (int k = ty; k < 32; k += 8) {
         const int j = j0 + k, d = d0 + tx;
-        tile[k][tx] = (j < rows && d < dim) ? Elem<T>::to_f(in[(long long)j * dim + d]) : 0.f;
+        tile[k][tx] = (j < rows && d < dim) ? Elem<T>::to_f(in[(long long)j * dim + d]) * inv_norm[j] : 0.f;
     }
     __syncthreads();
     for (int k = ty; k < 32; k += 8) {
         const int d = d0 + k, j = j0 + tx;
-        if (d < dim && j < pitch) out[(long long)d * pitch + j] = __float2bfloat16_rn(j < rows ? tile[tx][k] : 0.f);
+        if (d < dim && j < pitch) out[(long long)d * pitch + j] = __float2half_rn(j < rows ? tile[tx][k] : 0.f);
     }
 }
 
@@ -59,11 +60,12 @@ __global__ void __launch_bounds__(1024) clip_loss_kernel(const float* __restrict
         const int rows = dir == 0 ? rows_i2t : rows_t2i;
         double ce = 0.0, kl = 0.0;
         for (int i = threadIdx.x; i < rows; i += blockDim.x) {
-            const float A = st[i], diag = st[(size_t)4 * rows + i];
-            ce += (double)(1.0f + logf(A) - diag);
+            // double: KL_i is a small difference of O(1) terms (W/(T Zt) against log Zs - log Zt)
+            const double A = st[i], diag = st[(size_t)4 * rows + i];
+            ce += 1.0 + log(A) - diag;
             if (has_teacher) {
-                const float Zs = st[(size_t)rows + i], Zt = st[(size_t)2 * rows + i], W = st[(size_t)3 * rows + i];
-                kl += (double)(W / (temperature * Zt) - logf(Zt) + logf(Zs));
+                const double Zs = st[(size_t)rows + i], Zt = st[(size_t)2 * rows + i], W = st[(size_t)3 * rows + i];
+                kl += W / ((double)temperature * Zt) + log(Zs / Zt);
             }
         }
         ce = block_sum(ce);
@@ -86,19 +88,36 @@ __global__ void __launch_bounds__(1024) clip_loss_kernel(const float* __restrict
 // coef[0][i] = gh / (2 B A_i)   coef[1][i] = gs T / (2 Zs_i)   coef[2][i] = gs T / (2 Zt_i)
 // upstream = {gh, gs} on the device (no host sync in backward)
 // ---------------------------------------------------------------------------------------------
+// gmax[0] = max_i (|coef0| + |coef1| + |coef2|): bounds |G_ij| <= gmax(rows) + gmax(cols) since every exp term is <= 1
 __global__ void __launch_bounds__(256) clip_coef_kernel(const float* __restrict__ stats, int rows, float temperature,
                                                         int has_teacher, float inv_batch, const float* __restrict__ upstream,
-                                                        float* __restrict__ coef) {
+                                                        float* __restrict__ coef, unsigned int* __restrict__ gmax) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= rows) return;
-    const float gh = upstream[0], gs = upstream[1];
-    coef[i] = 0.5f * gh * inv_batch / stats[i];
-    coef[(size_t)rows + i] = has_teacher ? 0.5f * gs * temperature / stats[(size_t)rows + i] : 0.f;
-    coef[(size_t)2 * rows + i] = has_teacher ? 0.5f * gs * temperature / stats[(size_t)2 * rows + i] : 0.f;
+    float m = 0.f;
+    if (i < rows) {
+        const float gh = upstream[0], gs = upstream[1];
+        const float a = 0.5f * gh * inv_batch / stats[i];
+        const float b = has_teacher ? 0.5f * gs * temperature / stats[(size_t)rows + i] : 0.f;
+        const float c = has_teacher ? 0.5f * gs * temperature / stats[(size_t)2 * rows + i] : 0.f;
+        coef[i] = a;
+        coef[(size_t)rows + i] = b;
+        coef[(size_t)2 * rows + i] = c;
+        m = fabsf(a) + fabsf(b) + fabsf(c);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(gmax, __float_as_uint(m));     // non-negative floats order like uints
 }
 
 // ---------------------------------------------------------------------------------------------
-// grad_a[i,:] = r_i (acc_i - a_hat_i (a_hat_i . acc_i)),  acc_i = sum_splits acc_parts - (gh/B) b_hat_{offset+i}
+__device__ __forceinline__ float clip_grad_tile_scale(float gmax) {     // must match grad_tile_scale in clip_bwd.cu
+    if (!(gmax > 0.f) || !isfinite(gmax)) return 1.f;
+    int e;
+    frexpf(gmax, &e);
+    return ldexpf(1.f, 14 - e);
+}
+
+// grad_a[i,:] = r_i (acc_i - a_hat_i (a_hat_i . acc_i)),  acc_i = sum_splits acc_parts / 2^k - (gh/B) b_hat_{offset+i}
 // (Jacobian of x / ||x||, reference clip_model.py:37-38, plus the -delta_ij label term of cross entropy)
 // ---------------------------------------------------------------------------------------------
 template <typename T, typename G>
@@ -107,11 +126,13 @@ __global__ void __launch_bounds__(256) clip_grad_finish_kernel(const float* __re
                                                                const T* __restrict__ b, const float* __restrict__ b_inv,
                                                                long long rows, long long cols, int dim, long long row_offset,
                                                                float inv_batch, const float* __restrict__ upstream,
+                                                               const float* __restrict__ gmax_row, const float* __restrict__ gmax_col,
                                                                G* __restrict__ grad) {
     const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= rows) return;
     const int lane = threadIdx.x & 31;
     const float r = a_inv[row];
+    const float unscale = 1.0f / clip_grad_tile_scale(gmax_row[0] + gmax_col[0]);   // the MMA accumulated G * 2^k
     const long long gi = row_offset + row;
     const bool has_label = gi < cols;
     const float lab = has_label ? upstream[0] * inv_batch * b_inv[gi] : 0.f;
@@ -121,7 +142,7 @@ __global__ void __launch_bounds__(256) clip_grad_finish_kernel(const float* __re
     for (int d = lane; d < dim; d += 32) {
         float v = 0.f;
         for (int s = 0; s < n_split; ++s) v += acc_parts[((size_t)s * rows + row) * dim + d];
-        v -= lab * Elem<T>::to_f(bp[d]);
+        v = v * unscale - lab * Elem<T>::to_f(bp[d]);
         dot = fmaf(Elem<T>::to_f(ap[d]) * r, v, dot);
     }
     dot = warp_sum(dot);
@@ -129,7 +150,7 @@ __global__ void __launch_bounds__(256) clip_grad_finish_kernel(const float* __re
     for (int d = lane; d < dim; d += 32) {
         float v = 0.f;
         for (int s = 0; s < n_split; ++s) v += acc_parts[((size_t)s * rows + row) * dim + d];
-        v -= lab * Elem<T>::to_f(bp[d]);
+        v = v * unscale - lab * Elem<T>::to_f(bp[d]);
         gp[d] = Elem<G>::from_f(r * (v - Elem<T>::to_f(ap[d]) * r * dot));
     }
 }
@@ -157,16 +178,16 @@ int dcb_row_inv_norm(int n_mats, const void* const* mats, float* const* inv_norm
     return 0;
 }
 
-int dcb_transpose_to_bf16(const void* in, void* out, int64_t rows, int64_t dim, int64_t out_pitch_elems, int dtype,
-                          void* stream) {
+int dcb_transpose_norm_f16(const void* in, const float* inv_norm, void* out, int64_t rows, int64_t dim,
+                           int64_t out_pitch_elems, int dtype, void* stream) {
     using namespace dcb;
-    DCB_REQUIRE(in && out && rows >= 1 && dim >= 1 && out_pitch_elems >= rows, "bad arguments");
+    DCB_REQUIRE(in && inv_norm && out && rows >= 1 && dim >= 1 && out_pitch_elems >= rows, "bad arguments");
     dim3 grid((unsigned)((out_pitch_elems + 31) / 32), (unsigned)((dim + 31) / 32));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    __nv_bfloat16* o = static_cast<__nv_bfloat16*>(out);
+    __half* o = static_cast<__half*>(out);
     switch (dtype) {
-        case DCB_BF16: transpose_to_bf16_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(in), o, (int)rows, (int)dim, out_pitch_elems); break;
-        case DCB_F16: transpose_to_bf16_kernel<__half><<<grid, 256, 0, st>>>(static_cast<const __half*>(in), o, (int)rows, (int)dim, out_pitch_elems); break;
+        case DCB_BF16: transpose_norm_f16_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(in), inv_norm, o, (int)rows, (int)dim, out_pitch_elems); break;
+        case DCB_F16: transpose_norm_f16_kernel<__half><<<grid, 256, 0, st>>>(static_cast<const __half*>(in), inv_norm, o, (int)rows, (int)dim, out_pitch_elems); break;
         default: return fail("transpose: bf16 or fp16 input only");
     }
     DCB_CUDA_OK(cudaGetLastError());
@@ -185,21 +206,24 @@ int dcb_clip_losses(const float* stats_i2t, const float* stats_t2i, int64_t rows
 }
 
 int dcb_clip_grad_coef(const float* stats, int64_t rows, int64_t global_batch, float temperature, int has_teacher,
-                       const float* upstream, float* coef, void* stream) {
+                       const float* upstream, float* coef, float* gmax, void* stream) {
     using namespace dcb;
-    DCB_REQUIRE(stats && upstream && coef && rows >= 1 && global_batch >= 1, "bad arguments");
+    DCB_REQUIRE(stats && upstream && coef && gmax && rows >= 1 && global_batch >= 1, "bad arguments");
+    DCB_CUDA_OK(cudaMemsetAsync(gmax, 0, sizeof(float), static_cast<cudaStream_t>(stream)));
     clip_coef_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        stats, (int)rows, temperature, has_teacher, 1.0f / (float)global_batch, upstream, coef);
+        stats, (int)rows, temperature, has_teacher, 1.0f / (float)global_batch, upstream, coef,
+        reinterpret_cast<unsigned int*>(gmax));
     DCB_CUDA_OK(cudaGetLastError());
     return 0;
 }
 
 int dcb_clip_grad_finish(const float* acc_parts, int n_split, const void* stu_a, const float* stu_a_inv,
                          const void* stu_b, const float* stu_b_inv, int64_t rows, int64_t cols, int64_t dim,
-                         int64_t row_offset, int64_t global_batch, const float* upstream, int in_dtype, void* grad_a,
-                         int grad_dtype, void* stream) {
+                         int64_t row_offset, int64_t global_batch, const float* upstream, const float* gmax_row,
+                         const float* gmax_col, int in_dtype, void* grad_a, int grad_dtype, void* stream) {
     using namespace dcb;
-    DCB_REQUIRE(acc_parts && stu_a && stu_a_inv && stu_b && stu_b_inv && upstream && grad_a, "NULL pointer argument");
+    DCB_REQUIRE(acc_parts && stu_a && stu_a_inv && stu_b && stu_b_inv && upstream && gmax_row && gmax_col && grad_a,
+                "NULL pointer argument");
     DCB_REQUIRE(n_split >= 1 && rows >= 1 && dim >= 1 && global_batch >= 1, "bad arguments");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const unsigned grid = (unsigned)((rows + 7) / 8);
@@ -209,7 +233,7 @@ int dcb_clip_grad_finish(const float* acc_parts, int n_split, const void* stu_a,
         using G = decltype(gg);
         clip_grad_finish_kernel<T, G><<<grid, 256, 0, st>>>(acc_parts, n_split, static_cast<const T*>(stu_a), stu_a_inv,
                                                            static_cast<const T*>(stu_b), stu_b_inv, rows, cols, (int)dim,
-                                                           row_offset, inv_b, upstream, static_cast<G*>(grad_a));
+                                                           row_offset, inv_b, upstream, gmax_row, gmax_col, static_cast<G*>(grad_a));
         DCB_CUDA_OK(cudaGetLastError());
         return 0;
     });

@@ -75,10 +75,11 @@ __global__ void __launch_bounds__(kLogitThreads) logits_stats_kernel(const T* __
     if (threadIdx.x == 0) {
         saved[i] = make_float4(ms, zs, mt, zt);
         if (kSoft) {
-            const float lse_s = ms * inv_temp + logf(zs), lse_t = mt * inv_temp + logf(zt);
-            rowloss[i] = (double)(w * inv_temp / zt - lse_t + lse_s);
+            // double: KL_i is a small difference of O(1) terms
+            rowloss[i] = (double)w * (double)inv_temp / (double)zt + ((double)ms - (double)mt) * (double)inv_temp +
+                         log((double)zs / (double)zt);
         } else {
-            rowloss[i] = (double)(ms + logf(zs) - ld_logit(s, srs, scs, i, i));
+            rowloss[i] = (double)ms + log((double)zs) - (double)ld_logit(s, srs, scs, i, i);
         }
     }
 }

@@ -41,6 +41,9 @@ _TOWER_KERNELS = {
 class LossCalculator(nn.Module):
     #: use the fused embeddings->loss kernel for hard/soft label in two-tower mode (else the logits modules)
     fused_contrastive = True
+    #: upstream gradient assumed by the one-pass streaming kernels (set to GradScaler.get_scale() under fp16 AMP);
+    #: None = use distillclip_b200.ops.EXPECTED_GRAD_SCALE
+    expected_grad_scale = None
     #: torch.distributed process group for GLOBAL-batch contrastive losses (embeddings all-gathered, each rank
     #: computes its row slice; SURVEY.md F5: the reference itself is local-batch, so the default is None)
     contrastive_group = None
@@ -137,12 +140,13 @@ class LossCalculator(nn.Module):
             full_spec = [(kind, div, n, float(self.loss_scale[name]), float(self.percent[name]))
                          for kind, div, n, name in spec]
             flat = [x for s, t in tensors for x in (*s, *t)]
-            outs = ops.TowerLossFn.apply(full_spec, *flat)
+            expected = float(self.expected_grad_scale if self.expected_grad_scale is not None else ops.EXPECTED_GRAD_SCALE)
+            outs = ops.TowerLossFn.apply(full_spec, expected, *flat)
             fused_total, fused = outs[0], dict(zip(order, outs[1:]))
         else:
             fused_total, fused = None, {}
             for (kind, div, n, name), (s, t) in zip(spec, tensors):
-                cal_res[name] = ops.StreamLossFn.apply(kind, div, n, *s, *t)
+                cal_res[name] = ops.StreamLossFn.apply(kind, div, n, float(ops.EXPECTED_GRAD_SCALE), *s, *t)
         for name in self.loss:                      # dict order of the reference: order of self.loss
             if name in fused:
                 cal_res[name] = fused[name]

@@ -55,21 +55,28 @@ def _prep_pair(stu: Sequence[torch.Tensor], tea: Sequence[torch.Tensor]):
 # ----------------------------------------------------------------------------------------------
 # raw launches (no autograd)
 # ----------------------------------------------------------------------------------------------
-def launch_mse(stu: List[torch.Tensor], tea: List[torch.Tensor], divisor: int, grad_scale: float,
-               need_grad: Sequence[bool], grad_dtype: Optional[torch.dtype] = None):
-    """-> (partials, count, grads). Shapes must match pairwise (same rule as nn.MSELoss without broadcasting)."""
-    dev = stu[0].device
-    grads: List[Optional[torch.Tensor]] = []
-    for s, t, ng in zip(stu, tea, need_grad):
-        if s.shape != t.shape:
-            raise ValueError(f"MSE: student {tuple(s.shape)} and teacher {tuple(t.shape)} shapes differ")
-        grads.append(torch.empty_like(s, dtype=grad_dtype or s.dtype) if ng else None)
-    gd = _DT[grad_dtype] if grad_dtype is not None else dtype_code(stu[0])
-    nchunk = (len(stu) + _lib.MAX_LAYERS - 1) // _lib.MAX_LAYERS
+def _alloc_partials(nchunk: int, dev):
     if nchunk == 1:
-        partials = torch.empty(_lib.MAX_PARTIALS, dtype=torch.float64, device=dev)
+        return torch.empty(_lib.MAX_PARTIALS, dtype=torch.float64, device=dev)
+    return torch.zeros(nchunk * _lib.MAX_PARTIALS, dtype=torch.float64, device=dev)
+
+
+def launch_mse(stu: List[torch.Tensor], tea: List[torch.Tensor], divisor: int, grad_scale: float,
+               need_grad: Sequence[bool], grad_dtype: Optional[torch.dtype] = None, out=None):
+    """-> (partials, count, grads). Shapes must match pairwise (same rule as nn.MSELoss without broadcasting).
+    `out=(partials, grads)` reuses buffers from an earlier call (no allocation: used for kernel-only timing)."""
+    dev = stu[0].device
+    nchunk = (len(stu) + _lib.MAX_LAYERS - 1) // _lib.MAX_LAYERS
+    if out is not None:
+        partials, grads = out
     else:
-        partials = torch.zeros(nchunk * _lib.MAX_PARTIALS, dtype=torch.float64, device=dev)
+        grads = []
+        for s, t, ng in zip(stu, tea, need_grad):
+            if s.shape != t.shape:
+                raise ValueError(f"MSE: student {tuple(s.shape)} and teacher {tuple(t.shape)} shapes differ")
+            grads.append(torch.empty_like(s, dtype=grad_dtype or s.dtype) if ng else None)
+        partials = _alloc_partials(nchunk, dev)
+    gd = _DT[grad_dtype] if grad_dtype is not None else dtype_code(stu[0])
     count = C.c_int(0)
     for c in range(nchunk):
         sl = slice(c * _lib.MAX_LAYERS, (c + 1) * _lib.MAX_LAYERS)
@@ -84,7 +91,7 @@ def launch_mse(stu: List[torch.Tensor], tea: List[torch.Tensor], divisor: int, g
 
 
 def launch_attn_kl(stu: List[torch.Tensor], tea: List[torch.Tensor], divisor: int, grad_scale: float,
-                   need_grad: Sequence[bool], grad_dtype: Optional[torch.dtype] = None):
+                   need_grad: Sequence[bool], grad_dtype: Optional[torch.dtype] = None, out=None):
     dev = stu[0].device
     grads: List[Optional[torch.Tensor]] = []
     batch, hs, ht, pos = [], [], [], []
@@ -95,14 +102,15 @@ def launch_attn_kl(stu: List[torch.Tensor], tea: List[torch.Tensor], divisor: in
         batch.append(s.shape[0])
         hs.append(s.shape[1])
         ht.append(t.shape[1])
-        pos.append(s[0, 0].numel())
-        grads.append(torch.empty_like(s, dtype=grad_dtype or s.dtype) if ng else None)
+        pos.append(s.numel() // (s.shape[0] * s.shape[1]))
+        if out is None:
+            grads.append(torch.empty_like(s, dtype=grad_dtype or s.dtype) if ng else None)
     gd = _DT[grad_dtype] if grad_dtype is not None else dtype_code(stu[0])
     nchunk = (len(stu) + _lib.MAX_LAYERS - 1) // _lib.MAX_LAYERS
-    if nchunk == 1:
-        partials = torch.empty(_lib.MAX_PARTIALS, dtype=torch.float64, device=dev)
+    if out is not None:
+        partials, grads = out
     else:
-        partials = torch.zeros(nchunk * _lib.MAX_PARTIALS, dtype=torch.float64, device=dev)
+        partials = _alloc_partials(nchunk, dev)
     count = C.c_int(0)
     for c in range(nchunk):
         sl = slice(c * _lib.MAX_LAYERS, (c + 1) * _lib.MAX_LAYERS)
@@ -153,6 +161,12 @@ def _as_upstream(g: Optional[torch.Tensor], like: torch.Tensor) -> torch.Tensor:
 # ----------------------------------------------------------------------------------------------
 # autograd: one loss family (used by the per-module classes)
 # ----------------------------------------------------------------------------------------------
+#: Upstream gradient the one-pass kernels assume when they write the student gradients during the forward pass.
+#: 1.0 is right for plain `loss.backward()`.  Under fp16 AMP set it (or `LossCalculator.expected_grad_scale`) to
+#: `GradScaler.get_scale()`: a different upstream value is still honoured exactly (device-side rescale in backward),
+#: but fp16-stored gradients were then already rounded at the unscaled magnitude.
+EXPECTED_GRAD_SCALE = 1.0
+
 KIND_MSE, KIND_ATTN_KL = "mse", "attn_kl"
 _LAUNCH = {KIND_MSE: launch_mse, KIND_ATTN_KL: launch_attn_kl}
 
@@ -161,21 +175,22 @@ class StreamLossFn(torch.autograd.Function):
     """loss = kernel(stu_0..n-1, tea_0..n-1); gradients for the students come out of the same pass."""
 
     @staticmethod
-    def forward(ctx, kind: str, divisor: int, n: int, *tensors):
+    def forward(ctx, kind: str, divisor: int, n: int, expected: float, *tensors):
         stu, tea = list(tensors[:n]), list(tensors[n:])
-        need = [bool(ng) for ng in ctx.needs_input_grad[3:3 + n]]
-        partials, count, grads = _LAUNCH[kind](stu, tea, divisor, 1.0, need)
+        need = [bool(ng) for ng in ctx.needs_input_grad[4:4 + n]]
+        partials, count, grads = _LAUNCH[kind](stu, tea, divisor, expected, need)
         out = finalize([(partials, count)], [1.0], [1.0])
         ctx.grads = grads
         ctx.n = n
+        ctx.expected = expected
         return out[0]
 
     @staticmethod
     def backward(ctx, g):
         grads = ctx.grads
         if any(x is not None for x in grads):
-            rescale([(grads, _as_upstream(g, next(x for x in grads if x is not None)), 1.0)])
-        return (None, None, None, *grads, *([None] * ctx.n))
+            rescale([(grads, _as_upstream(g, next(x for x in grads if x is not None)), ctx.expected)])
+        return (None, None, None, None, *grads, *([None] * ctx.n))
 
 
 def stream_loss(kind: str, stu: Sequence[torch.Tensor], tea: Sequence[torch.Tensor]):
@@ -186,7 +201,7 @@ def stream_loss(kind: str, stu: Sequence[torch.Tensor], tea: Sequence[torch.Tens
     s, t = _prep_pair(stu, tea)
     if not s:
         return 0.0          # reference: `res_loss = 0; res_loss /= len(stu)` -> python float
-    return StreamLossFn.apply(kind, divisor, len(s), *s, *t)
+    return StreamLossFn.apply(kind, divisor, len(s), float(EXPECTED_GRAD_SCALE), *s, *t)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -195,18 +210,18 @@ def stream_loss(kind: str, stu: Sequence[torch.Tensor], tea: Sequence[torch.Tens
 class TowerLossFn(torch.autograd.Function):
     """spec: list of (kind, divisor, n_layers, scale, percent); tensors: for each entry stu_0.., tea_0..
     Returns (total, res_0, ..., res_{k-1}) with res_k = raw_k * scale_k and total = sum res_k * percent_k
-    (reference model/_loss.py:195-200)."""
+    (reference model/_loss.py:195-200).  `expected` = upstream gradient of `total` assumed in the forward pass."""
 
     @staticmethod
-    def forward(ctx, spec, *tensors):
+    def forward(ctx, spec, expected, *tensors):
         ctx.set_materialize_grads(False)
         terms, scales, percents, all_grads, pres, layout = [], [], [], [], [], []
         off = 0
         for kind, divisor, n, scale, percent in spec:
             stu, tea = list(tensors[off:off + n]), list(tensors[off + n:off + 2 * n])
-            need = [bool(x) for x in ctx.needs_input_grad[1 + off:1 + off + n]]
+            need = [bool(x) for x in ctx.needs_input_grad[2 + off:2 + off + n]]
             w = float(np.float32(percent) * np.float32(scale))
-            pre = w if w != 0.0 else 1.0
+            pre = w * expected if w != 0.0 else 1.0
             partials, count, grads = _LAUNCH[kind](stu, tea, divisor, pre, need)
             terms.append((partials, count))
             scales.append(scale)
@@ -217,6 +232,7 @@ class TowerLossFn(torch.autograd.Function):
             off += 2 * n
         out = finalize(terms, scales, percents)
         ctx.all_grads, ctx.pres, ctx.layout, ctx.spec, ctx.n_in = all_grads, pres, layout, spec, len(tensors)
+        ctx.expected = expected
         k = len(spec)
         return (out[k], *out[:k].unbind(0))
 
@@ -229,8 +245,8 @@ class TowerLossFn(torch.autograd.Function):
             if not live:
                 continue
             scale = float(ctx.spec[i][3])
-            if g_res[i] is None and pre == w and g_total is not None:
-                groups.append((grads, _as_upstream(g_total, live[0]), 1.0))      # common path: no torch kernels
+            if g_res[i] is None and pre == w * ctx.expected and g_total is not None:
+                groups.append((grads, _as_upstream(g_total, live[0]), ctx.expected))   # common path: no torch kernels
             else:
                 up = _as_upstream(g_total, live[0]) * w
                 if g_res[i] is not None:
@@ -239,4 +255,4 @@ class TowerLossFn(torch.autograd.Function):
             ret[off:off + n] = grads
         if groups:
             rescale(groups)
-        return (None, *ret)
+        return (None, None, *ret)

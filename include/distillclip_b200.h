@@ -100,10 +100,10 @@ int dcb_rescale_grads(int n_seg, void* const* grads, const int64_t* numel, int d
 int dcb_row_inv_norm(int n_mats, const void* const* mats, float* const* inv_norm, const int64_t* rows,
                      int64_t dim, int dtype, void* stream);
 
-/* out[d][j] = bf16(in[j][d]); out is [dim, out_pitch_elems] (pitch >= rows, % 8 == 0, pad columns zeroed).
- * The gradient GEMM wants the student b-side K-major, so it is transposed once per backward. */
-int dcb_transpose_to_bf16(const void* in, void* out, int64_t rows, int64_t dim, int64_t out_pitch_elems, int dtype,
-                          void* stream);
+/* out[d][j] = fp16(in[j][d] * inv_norm[j]); out is [dim, out_pitch_elems] (pitch >= rows, % 8 == 0, pad columns zeroed).
+ * The gradient GEMM wants the normalised student b-side K-major, so it is transposed once per backward. */
+int dcb_transpose_norm_f16(const void* in, const float* inv_norm, void* out, int64_t rows, int64_t dim,
+                           int64_t out_pitch_elems, int dtype, void* stream);
 
 /* dcb_clip_row_stats: ONE fused tcgen05 kernel for one direction.  For each local row i:
  *   stats[0][i] = sum_j exp(S_ij - 1)                 (hard label; S = student cosine logits)
@@ -127,32 +127,35 @@ int dcb_clip_losses(const float* stats_i2t, const float* stats_t2i, int64_t rows
                     int64_t global_batch, float temperature, int has_teacher, double* sums, float* out, void* stream);
 
 /* coef[0][i] = gh/(2 B A_i), coef[1][i] = gs T/(2 Zs_i), coef[2][i] = gs T/(2 Zt_i) from stats [5, rows];
- * upstream: device float[2] = {gh = d total / d hard, gs = d total / d soft}. */
+ * upstream: device float[2] = {gh = d total / d hard, gs = d total / d soft}.
+ * gmax: device float[1], receives max_i (|coef0| + |coef1| + |coef2|) -- the bound that fixes the fp16 scale of G. */
 int dcb_clip_grad_coef(const float* stats, int64_t rows, int64_t global_batch, float temperature, int has_teacher,
-                       const float* upstream, float* coef, void* stream);
+                       const float* upstream, float* coef, float* gmax, void* stream);
 
 /* dcb_clip_row_grads: backward for one direction, recomputing the logits tile by tile:
  *   G_ij = e1_ij (coef_row[0][i] + coef_col[0][j]) + es_ij (coef_row[1][i] + coef_col[1][j])
  *        - et_ij (coef_row[2][i] + coef_col[2][j])
- *   acc_parts[s][i,:] = partial sums over column range s of  sum_j G_ij b_hat_j      (fp32)
- * coef_col are the coefficients of the OPPOSITE direction for all `cols` rows (the column softmax of the same logits).
- * stu_b_t: dcb_transpose_to_bf16(stu_b).  acc_parts: dcb_clip_grad_workspace_bytes(...) bytes,
+ *   acc_parts[s][i,:] = partial sums over column range s of  2^k sum_j G_ij b_hat_j      (fp32)
+ * coef_col are the coefficients of the OPPOSITE direction for all `cols` rows (the column softmax of the same logits);
+ * gmax_row / gmax_col the matching outputs of dcb_clip_grad_coef (2^k = largest power of two with
+ * 2^k (gmax_row + gmax_col) <= 2^14: G goes through the tensor cores as fp16).
+ * stu_b_t: dcb_transpose_norm_f16(stu_b).  acc_parts: dcb_clip_grad_workspace_bytes(...) bytes,
  * dcb_clip_grad_splits(...) partial buffers of [rows_local, dim]. */
 int64_t dcb_clip_grad_workspace_bytes(int64_t rows_local, int64_t cols, int64_t dim);
 int dcb_clip_grad_splits(int64_t rows_local, int64_t cols, int64_t dim);
 int dcb_clip_row_grads(const void* stu_a, const void* stu_b, const void* tea_a, const void* tea_b,
                        const void* stu_b_t, int64_t bt_pitch_elems,
                        const float* stu_a_inv, const float* stu_b_inv, const float* tea_a_inv, const float* tea_b_inv,
-                       const float* coef_row, const float* coef_col,
+                       const float* coef_row, const float* coef_col, const float* gmax_row, const float* gmax_col,
                        int64_t rows_local, int64_t cols, int64_t dim, int dtype, float temperature,
                        float* acc_parts, void* stream);
 
-/* grad_a[i,:] = r_i (acc_i - a_hat_i (a_hat_i . acc_i)),  acc_i = sum_s acc_parts[s][i,:] - (gh/B) b_hat_{row_offset+i}
+/* grad_a[i,:] = r_i (acc_i - a_hat_i (a_hat_i . acc_i)),  acc_i = 2^-k sum_s acc_parts[s][i,:] - (gh/B) b_hat_{row_offset+i}
  * (the -[i==j] label term of the cross entropy, added here in fp32, then the x/||x|| Jacobian of clip_model.py:37-38). */
 int dcb_clip_grad_finish(const float* acc_parts, int n_split, const void* stu_a, const float* stu_a_inv,
                          const void* stu_b, const float* stu_b_inv, int64_t rows, int64_t cols, int64_t dim,
-                         int64_t row_offset, int64_t global_batch, const float* upstream, int in_dtype, void* grad_a,
-                         int grad_dtype, void* stream);
+                         int64_t row_offset, int64_t global_batch, const float* upstream, const float* gmax_row,
+                         const float* gmax_col, int in_dtype, void* grad_a, int grad_dtype, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Per-module API on MATERIALISED logits (HardLabel / SoftLabel keep their logits signature).

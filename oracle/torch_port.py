@@ -155,4 +155,4 @@ def stage_step_cpu(names, stu: Dict, tea: Dict, temperature=None, two=False, thr
     fn = two_tower if two else one_tower
     loss, _ = fn(names, scale, percent, temperature, stu, tea)
     loss.backward()
-    return float(loss)
+    return float(loss.detach())

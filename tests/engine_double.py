@@ -45,20 +45,22 @@ class DoubleEngine:
         if has_teacher:
             c[1] = 0.5 * gs * temperature / stats[1]
             c[2] = 0.5 * gs * temperature / stats[2]
-        return c
+        return c, c.abs().sum(0).max().reshape(1)
 
-    def transpose_bf16(self, b):
-        return b.double().t().contiguous()
+    def transpose_norm(self, b, b_inv):
+        return (b.double() * b_inv[:, None]).t().contiguous()
 
     def row_grads(self, a_s, b_s, a_t, b_t, b_s_t, a_s_inv, b_s_inv, a_t_inv, b_t_inv, coef_row, coef_col,
-                  row_offset, global_batch, temperature, upstream, grad_dtype):
+                  gmax_row, gmax_col, row_offset, global_batch, temperature, upstream, grad_dtype):
         S = self._logits(a_s, b_s, a_s_inv, b_s_inv)
         G = torch.exp(S - 1) * (coef_row[0][:, None] + coef_col[0][None, :])
         if a_t is not None:
             T = self._logits(a_t, b_t, a_t_inv, b_t_inv)
             G = G + torch.exp((S - 1) / temperature) * (coef_row[1][:, None] + coef_col[1][None, :])
             G = G - torch.exp((T - 1) / temperature) * (coef_row[2][:, None] + coef_col[2][None, :])
-        acc = (G * b_s_inv[None, :]) @ b_s_t.t()                       # sum_j G_ij c_j b_j
+        scale = 2.0 ** (14 - torch.frexp(gmax_row + gmax_col)[1].item())     # the fp16 tile scale of the kernel
+        assert float((G.abs() * scale).max()) <= 2.0 ** 14
+        acc = ((G * scale) @ b_s_t.t()) / scale                        # sum_j G_ij b_hat_j
         rows = a_s.shape[0]
         gi = row_offset + torch.arange(rows)
         acc = acc - (upstream[0].double() / global_batch) * b_s_inv[gi][:, None] * b_s.double()[gi]

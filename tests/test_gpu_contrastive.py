@@ -126,16 +126,16 @@ def test_row_sharded_virtual_ranks(cuda_device):
     assert float(0.5 * (sums[0] + sums[1]) / b) == pytest.approx(ref["hard"], rel=LOSS_RTOL)
     assert float(0.5 * (sums[2] + sums[3])) == pytest.approx(ref["soft"], rel=LOSS_RTOL)
     up = torch.tensor([1.0, 1.0], device="cuda")
-    ci_all = eng.coef(torch.cat(stats_i, 1).contiguous(), b, T, True, up)
-    ct_all = eng.coef(torch.cat(stats_t, 1).contiguous(), b, T, True, up)
-    st_t, si_t = eng.transpose_bf16(st), eng.transpose_bf16(si)
+    ci_all, gm_i = eng.coef(torch.cat(stats_i, 1).contiguous(), b, T, True, up)
+    ct_all, gm_t = eng.coef(torch.cat(stats_t, 1).contiguous(), b, T, True, up)
+    st_t, si_t = eng.transpose_norm(st, inv[1]), eng.transpose_norm(si, inv[0])
     gi, gt = [], []
     for r in range(R):
         loc = slice(r * bl, (r + 1) * bl)
         gi.append(eng.row_grads(si[loc], st, ti[loc], tt, st_t, inv[0][loc], inv[1], inv[2][loc], inv[3],
-                                ci_all[:, loc].contiguous(), ct_all, r * bl, b, T, up, torch.float32))
+                                ci_all[:, loc].contiguous(), ct_all, gm_i, gm_t, r * bl, b, T, up, torch.float32))
         gt.append(eng.row_grads(st[loc], si, tt[loc], ti, si_t, inv[1][loc], inv[0], inv[3][loc], inv[2],
-                                ct_all[:, loc].contiguous(), ci_all, r * bl, b, T, up, torch.float32))
+                                ct_all[:, loc].contiguous(), ci_all, gm_t, gm_i, r * bl, b, T, up, torch.float32))
     assert rel_l2(torch.cat(gi).cpu().numpy(), ref["d_img"]) <= GRAD_RTOL
     assert rel_l2(torch.cat(gt).cpu().numpy(), ref["d_txt"]) <= GRAD_RTOL
 

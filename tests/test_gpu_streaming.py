@@ -22,7 +22,7 @@ def dev(x, dtype=torch.bfloat16, grad=False):
 
 
 def _check(loss, grads, ref_loss, ref_grads, storage_rounded):
-    assert float(loss) == pytest.approx(float(ref_loss), rel=LOSS_RTOL)
+    assert float(loss.detach()) == pytest.approx(float(ref_loss), rel=LOSS_RTOL)
     tol = GRAD_BF16_STORAGE_RTOL if storage_rounded else GRAD_RTOL
     for g, r in zip(grads, ref_grads):
         if np.all(np.asarray(r) == 0):
@@ -98,11 +98,19 @@ def test_hidden_mse_random_vs_oracle(cuda_device, dtype, shape, layers):
     gen = torch.Generator().manual_seed(7)
     stu = [torch.randn(*shape, generator=gen).to(dtype) for _ in range(layers)]
     tea = [torch.randn(*shape, generator=gen).to(dtype) for _ in range(layers)]
+    from distillclip_b200 import ops
     ref_loss, ref_grads = cf.hidden_mse([s.float().numpy() for s in stu], [t.float().numpy() for t in tea])
     ds = [s.cuda().requires_grad_(True) for s in stu]
-    loss = HiddenMSE()(ds, [t.cuda() for t in tea])
-    loss.backward()
-    _check(loss, [s.grad for s in ds], ref_loss, ref_grads, dtype != torch.float32)
+    # fp16 gradients of this size (~1e-6) are subnormal: like fp16 AMP, scale the loss (GradScaler) and tell the
+    # one-pass kernel which upstream gradient to expect so the single rounding happens at the scaled magnitude
+    k = 4096.0 if dtype == torch.float16 else 1.0
+    ops.EXPECTED_GRAD_SCALE = k
+    try:
+        loss = HiddenMSE()(ds, [t.cuda() for t in tea])
+        (loss * k).backward()
+    finally:
+        ops.EXPECTED_GRAD_SCALE = 1.0
+    _check(loss.detach(), [s.grad.float() / k for s in ds], ref_loss, ref_grads, dtype != torch.float32)
 
 
 def test_mse_unaligned_views(cuda_device):
@@ -129,7 +137,24 @@ def test_attn_kl_random_vs_oracle(cuda_device, dtype, b, hs, ht, n, layers):
     ds = [s.cuda().requires_grad_(True) for s in stu]
     loss = AttentionProbsKL()(ds, [t.cuda() for t in tea])
     loss.backward()
-    _check(loss, [s.grad for s in ds], ref_loss, ref_grads, dtype != torch.float32)
+    _check(loss.detach(), [s.grad for s in ds], ref_loss, ref_grads, dtype != torch.float32)
+
+
+def test_unexpected_upstream_after_fp16_scaling(cuda_device):
+    """If the upstream gradient differs from the expected one, backward rescales on the device: still exact in fp32."""
+    from distillclip_b200 import ops
+    from distillclip_b200.model import AttentionProbsKL
+    gen = torch.Generator().manual_seed(17)
+    s = torch.softmax(torch.randn(2, 4, 9, 9, generator=gen), -1).cuda().requires_grad_(True)
+    t = torch.softmax(torch.randn(2, 4, 9, 9, generator=gen), -1).cuda()
+    ref_loss, ref_grads = cf.attention_probs_kl([s.detach().cpu().numpy()], [t.cpu().numpy()])
+    ops.EXPECTED_GRAD_SCALE = 128.0
+    try:
+        loss = AttentionProbsKL()([s], [t])
+        (loss * 0.5).backward()
+    finally:
+        ops.EXPECTED_GRAD_SCALE = 1.0
+    assert rel_l2(s.grad.cpu().numpy(), 0.5 * ref_grads[0]) <= 1e-5
 
 
 def test_upstream_gradient_is_applied(cuda_device):
