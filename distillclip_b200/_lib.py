@@ -13,6 +13,7 @@ LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "lib
 
 BF16, F16, F32 = 0, 1, 2
 MAX_LAYERS, MAX_PARTIALS, MAX_TERMS = 16, 4096, 16
+TOWER_MAX_SEG, TOWER_MAX_TERMS = 40, 4
 
 _vp, _i64p, _i32p, _f32p = C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int32), C.POINTER(C.c_float)
 _vpp = C.POINTER(C.c_void_p)
@@ -24,6 +25,8 @@ SIGNATURES = {
     "dcb_attn_kl_fwd_bwd": [C.c_int, _vpp, _vpp, _vpp, _i64p, _i32p, _i32p, _i64p, C.c_int, C.c_int, C.c_int,
                             C.c_float, _vp, C.POINTER(C.c_int), _vp],
     "dcb_finalize": [C.c_int, _vpp, _i32p, _f32p, _f32p, _vp, _vp],
+    "dcb_tower_fwd_bwd": [C.c_int, _i32p, _i32p, _vpp, _vpp, _vpp, _i64p, _i64p, _i32p, _i32p, _i64p, _i32p, _f32p,
+                          C.c_int, _f32p, _f32p, C.c_int, C.c_int, _vp, _vp, _vp, _vp],
     "dcb_rescale_grads": [C.c_int, _vpp, _i64p, C.c_int, _vpp, _f32p, _vp],
     "dcb_row_inv_norm": [C.c_int, _vpp, _vpp, _i64p, C.c_int64, C.c_int, _vp],
     "dcb_transpose_norm_f16": [_vp, _vp, _vp, C.c_int64, C.c_int64, C.c_int64, C.c_int, _vp],
@@ -44,6 +47,7 @@ _SPECIAL = {
     "dcb_clip_workspace_bytes": (C.c_int64, [C.c_int64, C.c_int64]),
     "dcb_clip_grad_workspace_bytes": (C.c_int64, [C.c_int64, C.c_int64, C.c_int64]),
     "dcb_clip_grad_splits": (C.c_int, [C.c_int64, C.c_int64, C.c_int64]),
+    "dcb_tower_grid": (C.c_int, []),
     "dcb_version": (C.c_int, []),
     "dcb_compiled_arch": (C.c_int, []),
     "dcb_last_error": (C.c_char_p, []),

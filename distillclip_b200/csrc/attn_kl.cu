@@ -10,7 +10,7 @@
 // positions of one sample, walks the heads with independent vector loads (the head stride P*sizeof(T)
 // keeps VEC*sizeof(T) alignment because P % VEC == 0), then writes the same gradient vector to every
 // student head.  All layers go through one launch; per-CTA double partials are reduced by dcb_finalize.
-#include "common.cuh"
+#include "stream_tiles.cuh"
 
 namespace dcb {
 
@@ -33,30 +33,7 @@ struct AttnParams {
     AttnSeg seg[DCB_MAX_LAYERS];
 };
 
-constexpr int kAttnThreads = 256;
-
-template <typename T, int VEC, int H>
-__device__ __forceinline__ void head_sum(const T* __restrict__ p, long long stride, int h_rt, float (&acc)[VEC]) {
-#pragma unroll
-    for (int e = 0; e < VEC; ++e) acc[e] = 0.f;
-    if constexpr (H > 0) {
-        float v[H][VEC];
-#pragma unroll
-        for (int h = 0; h < H; ++h) load_vec<T, VEC>(p + h * stride, v[h]);
-#pragma unroll
-        for (int h = 0; h < H; ++h)
-#pragma unroll
-            for (int e = 0; e < VEC; ++e) acc[e] += v[h][e];
-    } else {
-#pragma unroll 4
-        for (int h = 0; h < h_rt; ++h) {
-            float v[VEC];
-            load_vec<T, VEC>(p + h * stride, v);
-#pragma unroll
-            for (int e = 0; e < VEC; ++e) acc[e] += v[e];
-        }
-    }
-}
+constexpr int kAttnThreads = kStreamThreads;
 
 // H = compile-time head count for both maps (0 = runtime head counts)
 template <typename T, typename G, int VEC, int H>
@@ -68,39 +45,11 @@ __global__ void __launch_bounds__(kAttnThreads) attn_kl_kernel(const __grid_cons
         int k = 0;
 #pragma unroll 1
         while (k + 1 < p.n_seg && tile >= p.seg[k + 1].tile_begin) ++k;
-        const long long gi = (tile - p.seg[k].tile_begin) * kAttnThreads + tid;
-        float acc = 0.f;
-        if (gi < p.seg[k].groups) {
-            const long long P = p.seg[k].positions;
-            const long long b = gi / p.seg[k].groups_per_b;
-            const long long pos = (gi - b * p.seg[k].groups_per_b) * VEC;
-            const int hs = p.seg[k].hs, ht = p.seg[k].ht;
-            const T* __restrict__ s = static_cast<const T*>(p.seg[k].s) + (b * hs) * P + pos;
-            const T* __restrict__ t = static_cast<const T*>(p.seg[k].t) + (b * ht) * P + pos;
-            float ssum[VEC], tsum[VEC], gv[VEC];
-            head_sum<T, VEC, H>(s, P, hs, ssum);
-            head_sum<T, VEC, H>(t, P, ht, tsum);
-            const float ihs = p.seg[k].inv_hs, iht = p.seg[k].inv_ht, gc = p.seg[k].grad_coef;
-#pragma unroll
-            for (int e = 0; e < VEC; ++e) {
-                const float sm = ssum[e] * ihs;
-                const float tm = tsum[e] * iht;
-                const float tl = (tm == 0.f) ? 0.f : tm * logf(tm);     // xlogy(t, t)
-                acc += tl - tm * logf(sm);                               // 0 * -inf -> NaN like the reference
-                gv[e] = -gc * (tm / sm);
-            }
-            if (p.seg[k].g) {
-                G* __restrict__ g = static_cast<G*>(p.seg[k].g) + (b * hs) * P + pos;
-                if constexpr (H > 0) {
-#pragma unroll
-                    for (int h = 0; h < H; ++h) store_vec<G, VEC>(g + h * P, gv);
-                } else {
-#pragma unroll 4
-                    for (int h = 0; h < hs; ++h) store_vec<G, VEC>(g + h * P, gv);
-                }
-            }
-        }
-        dacc += (double)acc * (double)p.seg[k].val_coef;
+        const AttnSeg& sg = p.seg[k];
+        AttnShape sh{sg.groups, sg.groups_per_b, sg.positions, sg.hs, sg.ht, sg.inv_hs, sg.inv_ht};
+        const float acc = attn_tile<T, G, VEC, H>(static_cast<const T*>(sg.s), static_cast<const T*>(sg.t), static_cast<G*>(sg.g),
+                                                  sh, (tile - sg.tile_begin) * kAttnThreads + tid, sg.grad_coef);
+        dacc += (double)acc * (double)sg.val_coef;
     }
     const double total = block_sum(dacc);
     if (tid == 0) partials[blockIdx.x] = total;

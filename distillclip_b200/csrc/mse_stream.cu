@@ -8,7 +8,7 @@
 // fully coalesced tiles (8 x 128-bit loads in flight per thread), accumulates (s-t)^2 in fp32 per
 // tile / double per CTA, and writes its partial sum; dcb_finalize reduces the partials in a fixed
 // order, so the value is deterministic (no float atomics).
-#include "common.cuh"
+#include "stream_tiles.cuh"
 
 namespace dcb {
 
@@ -27,11 +27,12 @@ struct MseParams {
     MseSeg seg[DCB_MAX_LAYERS];
 };
 
-constexpr int kMseThreads = 256;
+constexpr int kMseThreads = kStreamThreads;
 
 template <typename T, typename G, int VEC, int UNROLL>
 __global__ void __launch_bounds__(kMseThreads) mse_stream_kernel(const __grid_constant__ MseParams p,
                                                                    double* __restrict__ partials) {
+    static_assert(UNROLL == kMseUnroll, "tile body is written for kMseUnroll");
     constexpr int kTile = kMseThreads * UNROLL * VEC;
     const int tid = threadIdx.x;
     double dacc = 0.0;
@@ -40,53 +41,9 @@ __global__ void __launch_bounds__(kMseThreads) mse_stream_kernel(const __grid_co
 #pragma unroll 1
         while (k + 1 < p.n_seg && tile >= p.seg[k + 1].tile_begin) ++k;
         const long long base = (tile - p.seg[k].tile_begin) * kTile;
-        const long long rem = p.seg[k].n - base;
-        const T* __restrict__ s = static_cast<const T*>(p.seg[k].s) + base;
-        const T* __restrict__ t = static_cast<const T*>(p.seg[k].t) + base;
-        G* __restrict__ g = p.seg[k].g ? static_cast<G*>(p.seg[k].g) + base : nullptr;
-        const float gc = p.seg[k].grad_coef;
-        float acc = 0.f;
-        if (rem >= kTile) {
-            float sv[UNROLL][VEC], tv[UNROLL][VEC];
-#pragma unroll
-            for (int u = 0; u < UNROLL; ++u) load_vec<T, VEC>(s + (u * kMseThreads + tid) * VEC, sv[u]);
-#pragma unroll
-            for (int u = 0; u < UNROLL; ++u) load_vec<T, VEC>(t + (u * kMseThreads + tid) * VEC, tv[u]);
-#pragma unroll
-            for (int u = 0; u < UNROLL; ++u) {
-                float gv[VEC];
-#pragma unroll
-                for (int e = 0; e < VEC; ++e) {
-                    const float d = sv[u][e] - tv[u][e];
-                    acc = fmaf(d, d, acc);
-                    gv[e] = d * gc;
-                }
-                if (g) store_vec<G, VEC>(g + (u * kMseThreads + tid) * VEC, gv);
-            }
-        } else {
-#pragma unroll 1
-            for (int u = 0; u < UNROLL; ++u) {
-                const long long i0 = (long long)(u * kMseThreads + tid) * VEC;
-                if (i0 + VEC <= rem) {
-                    float sv[VEC], tv[VEC], gv[VEC];
-                    load_vec<T, VEC>(s + i0, sv);
-                    load_vec<T, VEC>(t + i0, tv);
-#pragma unroll
-                    for (int e = 0; e < VEC; ++e) {
-                        const float d = sv[e] - tv[e];
-                        acc = fmaf(d, d, acc);
-                        gv[e] = d * gc;
-                    }
-                    if (g) store_vec<G, VEC>(g + i0, gv);
-                } else {
-                    for (long long i = i0; i < rem; ++i) {
-                        const float d = Elem<T>::to_f(s[i]) - Elem<T>::to_f(t[i]);
-                        acc = fmaf(d, d, acc);
-                        if (g) g[i] = Elem<G>::from_f(d * gc);
-                    }
-                }
-            }
-        }
+        G* g = p.seg[k].g ? static_cast<G*>(p.seg[k].g) + base : nullptr;
+        const float acc = mse_tile<T, G, VEC>(static_cast<const T*>(p.seg[k].s) + base, static_cast<const T*>(p.seg[k].t) + base,
+                                              g, p.seg[k].n - base, p.seg[k].grad_coef, tid);
         dacc += (double)acc * (double)p.seg[k].val_coef;
     }
     const double total = block_sum(dacc);

@@ -1,0 +1,219 @@
+// All streaming losses of one tower in ONE launch: hidden-state / embedding MSE and attention-map KL over every layer,
+// values and student gradients in a single pass over HBM, plus the weighting of model/_loss.py:195-200.
+//
+// Replaces LossCalculator.cal_one_tower_loss's python loops over layers and loss names (reference model/_loss.py:155-202,
+// loss_component/attention_probs_kl.py:10-22, hidden_mse.py:9-17, embed_mse.py:9-10) and their autograd backward.
+//
+// A persistent grid (4 CTAs per SM) walks a unified tile list (MSE tiles, then attention tiles).  Every CTA keeps one
+// double accumulator per loss term and writes it to partials[term][cta]; the last CTA to finish (atomic ticket) reduces
+// the partials in a fixed order -- so values are run-to-run identical -- applies `scale` and `percent`, and resets the
+// ticket for the next launch.  No separate finalize launch, no float atomics.
+#include "stream_tiles.cuh"
+
+namespace dcb {
+
+constexpr int kTowerMaxSeg = 40;
+constexpr int kTowerMaxTerms = 4;
+
+struct TowerSeg {
+    const void* s;
+    const void* t;
+    void* g;
+    long long n;           // MSE: elements; ATTN: groups (batch * positions / VEC)
+    long long tile_begin;
+    long long positions;   // ATTN
+    long long groups_per_b;
+    int kind;              // 0 = MSE, 1 = attention KL
+    int term;
+    int hs, ht;
+    int aligned;           // MSE: 16-byte aligned pointers -> vector path
+    float inv_hs, inv_ht;
+    float val_coef;
+    float grad_coef;
+};
+struct TowerParams {
+    int n_seg, n_terms;
+    long long total_tiles;
+    float scale[kTowerMaxTerms], percent[kTowerMaxTerms];
+    double* partials;      // [n_terms][gridDim.x]
+    unsigned int* ticket;
+    float* out;            // [n_terms + 1]
+    TowerSeg seg[kTowerMaxSeg];
+};
+
+template <typename T, typename G, int AVEC, int AH>
+__global__ void __launch_bounds__(kStreamThreads, 4) tower_stream_kernel(const __grid_constant__ TowerParams p) {
+    constexpr int MVEC = Elem<T>::kPer16B;
+    constexpr long long kMseTile = (long long)kStreamThreads * kMseUnroll * MVEC;
+    constexpr long long kMseTileScalar = (long long)kStreamThreads * kMseUnroll;
+    const int tid = threadIdx.x;
+    double dacc[kTowerMaxTerms];
+#pragma unroll
+    for (int k = 0; k < kTowerMaxTerms; ++k) dacc[k] = 0.0;
+    int k = 0;
+    for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        while (k + 1 < p.n_seg && tile >= p.seg[k + 1].tile_begin) ++k;
+        const TowerSeg& sg = p.seg[k];
+        const long long lt = tile - sg.tile_begin;
+        float acc;
+        if (sg.kind == 0) {
+            G* g = static_cast<G*>(sg.g);
+            if (sg.aligned) {
+                const long long base = lt * kMseTile;
+                acc = mse_tile<T, G, MVEC>(static_cast<const T*>(sg.s) + base, static_cast<const T*>(sg.t) + base,
+                                           g ? g + base : nullptr, sg.n - base, sg.grad_coef, tid);
+            } else {
+                const long long base = lt * kMseTileScalar;
+                acc = mse_tile<T, G, 1>(static_cast<const T*>(sg.s) + base, static_cast<const T*>(sg.t) + base,
+                                        g ? g + base : nullptr, sg.n - base, sg.grad_coef, tid);
+            }
+        } else {
+            AttnShape sh{sg.n, sg.groups_per_b, sg.positions, sg.hs, sg.ht, sg.inv_hs, sg.inv_ht};
+            acc = attn_tile<T, G, AVEC, AH>(static_cast<const T*>(sg.s), static_cast<const T*>(sg.t), static_cast<G*>(sg.g),
+                                            sh, lt * kStreamThreads + tid, sg.grad_coef);
+        }
+        const double v = (double)acc * (double)sg.val_coef;
+#pragma unroll
+        for (int q = 0; q < kTowerMaxTerms; ++q)
+            if (q == sg.term) dacc[q] += v;
+    }
+    __shared__ bool is_last;
+    for (int q = 0; q < p.n_terms; ++q) {
+        const double total = block_sum(dacc[q]);
+        if (tid == 0) p.partials[(size_t)q * gridDim.x + blockIdx.x] = total;
+        __syncthreads();
+    }
+    if (tid == 0) {
+        __threadfence();
+        const unsigned int ticket = atomicAdd(p.ticket, 1u);
+        is_last = ticket == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    __shared__ double term_sum[kTowerMaxTerms];
+    for (int q = 0; q < p.n_terms; ++q) {
+        const volatile double* src = p.partials + (size_t)q * gridDim.x;
+        double v = 0.0;
+        for (unsigned int i = tid; i < gridDim.x; i += kStreamThreads) v += src[i];     // fixed assignment, fixed tree
+        v = block_sum(v);
+        if (tid == 0) term_sum[q] = v;
+        __syncthreads();
+    }
+    if (tid == 0) {
+        float total = 0.f;
+        for (int q = 0; q < p.n_terms; ++q) {
+            // same rounding points as the reference: fp32 value, * scale, * percent, += in fp32 (_loss.py:199-200)
+            const float res = (float)term_sum[q] * p.scale[q];
+            p.out[q] = res;
+            total += res * p.percent[q];
+        }
+        p.out[p.n_terms] = total;
+        *p.ticket = 0u;          // ready for the next launch (stream order / graph replay)
+    }
+}
+
+template <typename T, typename G, int AVEC>
+static int launch_tower_h(const TowerParams& p, int common_h, unsigned grid, cudaStream_t st) {
+    if (common_h == 12 && AVEC <= 4)
+        tower_stream_kernel<T, G, AVEC, 12><<<grid, kStreamThreads, 0, st>>>(p);
+    else if (common_h == 8 && AVEC <= 4)
+        tower_stream_kernel<T, G, AVEC, 8><<<grid, kStreamThreads, 0, st>>>(p);
+    else
+        tower_stream_kernel<T, G, AVEC, 0><<<grid, kStreamThreads, 0, st>>>(p);
+    DCB_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace dcb
+
+extern "C" int dcb_tower_grid(void) { return dcb::kNumSMs * 4; }
+
+extern "C" int dcb_tower_fwd_bwd(int n_seg, const int32_t* kind, const int32_t* term, const void* const* stu,
+                                 const void* const* tea, void* const* grad_stu, const int64_t* numel,
+                                 const int64_t* batch, const int32_t* stu_heads, const int32_t* tea_heads,
+                                 const int64_t* positions, const int32_t* divisor, const float* grad_scale, int n_terms,
+                                 const float* scale, const float* percent, int in_dtype, int grad_dtype,
+                                 double* partials, uint32_t* ticket, float* out, void* stream) {
+    using namespace dcb;
+    DCB_REQUIRE(n_seg >= 1 && n_seg <= kTowerMaxSeg, "n_seg=%d out of range [1,%d]", n_seg, kTowerMaxSeg);
+    DCB_REQUIRE(n_terms >= 1 && n_terms <= kTowerMaxTerms, "n_terms=%d out of range [1,%d]", n_terms, kTowerMaxTerms);
+    DCB_REQUIRE(partials && ticket && out, "partials / ticket / out must not be NULL");
+    TowerParams p{};
+    p.n_seg = n_seg;
+    p.n_terms = n_terms;
+    p.partials = partials;
+    p.ticket = ticket;
+    p.out = out;
+    for (int q = 0; q < n_terms; ++q) {
+        p.scale[q] = scale ? scale[q] : 1.f;
+        p.percent[q] = percent ? percent[q] : 0.f;
+    }
+    const int isz = dtype_size(in_dtype), gsz = dtype_size(grad_dtype);
+    int avec = 16 / isz, common_h = -1;
+    for (int k = 0; k < n_seg; ++k) {
+        DCB_REQUIRE(stu[k] && tea[k], "segment %d: NULL input", k);
+        DCB_REQUIRE(term[k] >= 0 && term[k] < n_terms && divisor[k] >= 1, "segment %d: bad term / divisor", k);
+        TowerSeg& sg = p.seg[k];
+        sg.s = stu[k];
+        sg.t = tea[k];
+        sg.g = grad_stu ? grad_stu[k] : nullptr;
+        sg.kind = kind[k];
+        sg.term = term[k];
+        if (kind[k] == 0) {
+            DCB_REQUIRE(numel[k] >= 1, "segment %d: numel must be >= 1", k);
+            sg.n = numel[k];
+            const double denom = (double)numel[k] * (double)divisor[k];
+            sg.val_coef = (float)(1.0 / denom);
+            sg.grad_coef = (float)(2.0 * (double)grad_scale[k] / denom);
+            sg.aligned = (((uintptr_t)stu[k] | (uintptr_t)tea[k] | (uintptr_t)sg.g) % 16 == 0) ? 1 : 0;
+        } else if (kind[k] == 1) {
+            DCB_REQUIRE(batch[k] >= 1 && positions[k] >= 1 && stu_heads[k] >= 1 && tea_heads[k] >= 1, "segment %d: bad shape", k);
+            sg.n = batch[k];
+            sg.positions = positions[k];
+            sg.hs = stu_heads[k];
+            sg.ht = tea_heads[k];
+            sg.inv_hs = 1.0f / (float)stu_heads[k];
+            sg.inv_ht = 1.0f / (float)tea_heads[k];
+            sg.val_coef = (float)(1.0 / (double)divisor[k]);
+            sg.grad_coef = (float)((double)grad_scale[k] / ((double)stu_heads[k] * (double)divisor[k]));
+            while (avec > 1 && (positions[k] % avec != 0 || ((uintptr_t)stu[k] | (uintptr_t)tea[k]) % (avec * isz) != 0 ||
+                                (sg.g && (uintptr_t)sg.g % (avec * gsz < 16 ? avec * gsz : 16) != 0)))
+                avec >>= 1;
+            if (common_h == -1) common_h = stu_heads[k];
+            if (stu_heads[k] != common_h || tea_heads[k] != common_h) common_h = 0;
+        } else {
+            return fail("segment %d: unknown kind %d", k, kind[k]);
+        }
+    }
+    long long tiles = 0;
+    const long long mse_tile_vec = (long long)kStreamThreads * kMseUnroll * (16 / isz);
+    const long long mse_tile_scalar = (long long)kStreamThreads * kMseUnroll;
+    for (int k = 0; k < n_seg; ++k) {
+        TowerSeg& sg = p.seg[k];
+        sg.tile_begin = tiles;
+        if (sg.kind == 0) {
+            const long long tl = sg.aligned ? mse_tile_vec : mse_tile_scalar;
+            tiles += (sg.n + tl - 1) / tl;
+        } else {
+            sg.groups_per_b = sg.positions / avec;
+            sg.n *= sg.groups_per_b;
+            tiles += (sg.n + kStreamThreads - 1) / kStreamThreads;
+        }
+    }
+    p.total_tiles = tiles;
+    long long grid = tiles < (long long)dcb_tower_grid() ? tiles : (long long)dcb_tower_grid();
+    if (grid < 1) grid = 1;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    return dispatch_in_grad(in_dtype, grad_dtype, [&](auto tt, auto gg) -> int {
+        using T = decltype(tt);
+        using G = decltype(gg);
+        constexpr int kMax = Elem<T>::kPer16B;
+        if (avec >= kMax) return launch_tower_h<T, G, kMax>(p, common_h, (unsigned)grid, st);
+        if (avec == 4) {
+            if constexpr (kMax > 4) return launch_tower_h<T, G, 4>(p, common_h, (unsigned)grid, st);
+        }
+        if (avec == 2) return launch_tower_h<T, G, 2>(p, common_h, (unsigned)grid, st);
+        return launch_tower_h<T, G, 1>(p, common_h, (unsigned)grid, st);
+    });
+}

@@ -160,7 +160,7 @@ class LossCalculator(nn.Module):
                 continue
             if loss_name in fused:
                 if pending_fused:                   # all fused names were weighted inside the kernel
-                    loss = loss + fused_total
+                    loss = fused_total if (isinstance(loss, int) and loss == 0) else loss + fused_total
                     pending_fused = False
                 continue
             cal_res[loss_name] = cal_res[loss_name] * scale

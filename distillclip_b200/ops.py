@@ -125,6 +125,66 @@ def launch_attn_kl(stu: List[torch.Tensor], tea: List[torch.Tensor], divisor: in
     return partials, n_part, grads
 
 
+_TICKETS = {}
+
+
+def _ticket(dev: torch.device) -> torch.Tensor:
+    """Zero-initialised uint32 the tower kernel uses to find its last CTA; the kernel resets it, so one per
+    (device, stream) serves every launch on that stream."""
+    key = (dev.index, torch.cuda.current_stream(dev).cuda_stream)
+    t = _TICKETS.get(key)
+    if t is None:
+        t = _TICKETS[key] = torch.zeros(1, dtype=torch.int32, device=dev)
+    return t
+
+
+def launch_tower(entries, scale: Sequence[float], percent: Sequence[float], grad_dtype: Optional[torch.dtype] = None,
+                 out=None):
+    """All streaming losses of one tower in one launch (csrc/tower_stream.cu).
+    entries: [(kind, divisor, stu list, tea list, need_grad list, grad_scale)], one per loss term.
+    -> (out[n_terms + 1] = scaled term values + weighted total, grads per entry).  `out=(out, grads, partials)`
+    reuses buffers (kernel-only timing)."""
+    dev = entries[0][2][0].device
+    kinds, terms, stu_p, tea_p, grad_p, numel, batch, hs, ht, pos, div, gsc = ([] for _ in range(12))
+    all_grads = [] if out is None else out[1]
+    for ti, (kind, divisor, stu, tea, need, pre) in enumerate(entries):
+        grads = [] if out is None else all_grads[ti]
+        for li, (s, t, ng) in enumerate(zip(stu, tea, need)):
+            if kind == KIND_MSE:
+                if s.shape != t.shape:
+                    raise ValueError(f"MSE: student {tuple(s.shape)} and teacher {tuple(t.shape)} shapes differ")
+                batch.append(1), hs.append(1), ht.append(1), pos.append(1)
+            else:
+                if s.dim() < 3 or t.dim() != s.dim() or s.shape[0] != t.shape[0] or s.shape[2:] != t.shape[2:]:
+                    raise ValueError(f"attention maps must be [B, H, ...] with equal B and map size: "
+                                     f"student {tuple(s.shape)} vs teacher {tuple(t.shape)}")
+                batch.append(s.shape[0]), hs.append(s.shape[1]), ht.append(t.shape[1])
+                pos.append(s.numel() // (s.shape[0] * s.shape[1]))
+            if out is None:
+                grads.append(torch.empty_like(s, dtype=grad_dtype or s.dtype) if ng else None)
+            g = grads[li]
+            kinds.append(0 if kind == KIND_MSE else 1), terms.append(ti)
+            stu_p.append(s.data_ptr()), tea_p.append(t.data_ptr()), grad_p.append(g.data_ptr() if g is not None else 0)
+            numel.append(s.numel()), div.append(int(divisor)), gsc.append(float(pre))
+        if out is None:
+            all_grads.append(grads)
+    n_terms = len(entries)
+    if out is None:
+        res = torch.empty(n_terms + 1, dtype=torch.float32, device=dev)
+        partials = torch.empty(n_terms * _lib.load().dcb_tower_grid(), dtype=torch.float64, device=dev)
+    else:
+        res, partials = out[0], out[2]
+    in_dt = dtype_code(entries[0][2][0])
+    gd = _DT[grad_dtype] if grad_dtype is not None else in_dt
+    _lib.call("dcb_tower_fwd_bwd", len(kinds), _lib.i32_array(kinds), _lib.i32_array(terms), _lib.ptr_array(stu_p),
+              _lib.ptr_array(tea_p), _lib.ptr_array(grad_p), _lib.i64_array(numel), _lib.i64_array(batch),
+              _lib.i32_array(hs), _lib.i32_array(ht), _lib.i64_array(pos), _lib.i32_array(div), _lib.f32_array(gsc),
+              n_terms, _lib.f32_array(scale), _lib.f32_array(percent), in_dt, gd, C.c_void_p(partials.data_ptr()),
+              C.c_void_p(_ticket(dev).data_ptr()), C.c_void_p(res.data_ptr()), _stream_ptr())
+    launch_tower.last_buffers = (res, all_grads, partials)
+    return res, all_grads
+
+
 def finalize(terms: Sequence[Tuple[torch.Tensor, int]], scale: Sequence[float], percent: Sequence[float]):
     """out[k] = scale[k]*sum(partials_k) ; out[-1] = sum_k percent[k]*out[k]   (fp32, device)."""
     out = torch.empty(len(terms) + 1, dtype=torch.float32, device=terms[0][0].device)
@@ -215,22 +275,29 @@ class TowerLossFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, spec, expected, *tensors):
         ctx.set_materialize_grads(False)
-        terms, scales, percents, all_grads, pres, layout = [], [], [], [], [], []
+        entries, all_grads, pres, layout = [], [], [], []
         off = 0
         for kind, divisor, n, scale, percent in spec:
             stu, tea = list(tensors[off:off + n]), list(tensors[off + n:off + 2 * n])
             need = [bool(x) for x in ctx.needs_input_grad[2 + off:2 + off + n]]
             w = float(np.float32(percent) * np.float32(scale))
             pre = w * expected if w != 0.0 else 1.0
-            partials, count, grads = _LAUNCH[kind](stu, tea, divisor, pre, need)
-            terms.append((partials, count))
-            scales.append(scale)
-            percents.append(percent)
-            all_grads.append(grads)
+            entries.append((kind, divisor, stu, tea, need, pre))
             pres.append((pre, w))
             layout.append((off, n))
             off += 2 * n
-        out = finalize(terms, scales, percents)
+        scales, percents = [sp[3] for sp in spec], [sp[4] for sp in spec]
+        n_seg = sum(len(e[2]) for e in entries)
+        dtypes = {t.dtype for e in entries for t in e[2]}
+        if len(spec) <= _lib.TOWER_MAX_TERMS and n_seg <= _lib.TOWER_MAX_SEG and len(dtypes) == 1:
+            out, all_grads = launch_tower(entries, scales, percents)          # ONE launch incl. the weighting
+        else:
+            terms = []
+            for kind, divisor, stu, tea, need, pre in entries:
+                partials, count, grads = _LAUNCH[kind](stu, tea, divisor, pre, need)
+                terms.append((partials, count))
+                all_grads.append(grads)
+            out = finalize(terms, scales, percents)
         ctx.all_grads, ctx.pres, ctx.layout, ctx.spec, ctx.n_in = all_grads, pres, layout, spec, len(tensors)
         ctx.expected = expected
         k = len(spec)

@@ -63,6 +63,24 @@ int dcb_attn_kl_fwd_bwd(int n_layers, const void* const* stu, const void* const*
                         double* partials, int* n_partials, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * ALL streaming losses of one tower in ONE launch, including the weighting below.
+ * Replaces LossCalculator.cal_one_tower_loss's loops (model/_loss.py:155-202) over embedding_mse, hidden_rep_mse and
+ * attention_probs_kl and their autograd backward.  Segment k (one layer of one loss term) has
+ *   kind[k]  0 = MSE (numel[k]),  1 = attention KL (batch[k], stu_heads[k], tea_heads[k], positions[k]);
+ *   term[k]  index of the loss term it adds to (< n_terms <= 4); divisor[k], grad_scale[k] as in the calls above.
+ * out[q] = scale[q] * value_q (q < n_terms), out[n_terms] = sum_q percent[q] * out[q]  (_loss.py:199-200).
+ * partials: n_terms * dcb_tower_grid() doubles of scratch; ticket: one uint32, zero before the first launch (the kernel
+ * resets it).  Values are reduced in a fixed order by the last CTA to finish: deterministic, no extra launch.
+ * --------------------------------------------------------------------------------------------- */
+int dcb_tower_grid(void);
+int dcb_tower_fwd_bwd(int n_seg, const int32_t* kind, const int32_t* term, const void* const* stu,
+                      const void* const* tea, void* const* grad_stu, const int64_t* numel,
+                      const int64_t* batch, const int32_t* stu_heads, const int32_t* tea_heads,
+                      const int64_t* positions, const int32_t* divisor, const float* grad_scale, int n_terms,
+                      const float* scale, const float* percent, int in_dtype, int grad_dtype,
+                      double* partials, uint32_t* ticket, float* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Deterministic reduction + weighting (model/_loss.py:195-200 and :148-152).
  *   out[k]        = scale[k] * sum(partials[k][0 .. counts[k]))            k < n_terms
  *   out[n_terms]  = sum_k percent[k] * out[k]

@@ -17,11 +17,11 @@ timeout 900 python bench.py --steps 20 --warmup 3 > $OUT/bench_$TAG.json 2> $OUT
 echo "bench exit $?" | tee -a $OUT/summary_$TAG.txt
 tail -c 3000 $OUT/bench_$TAG.json
 if [ "${NCU:-1}" = "1" ]; then
-  CMD="python bench.py --steps 2 --warmup 3 --no-extras --no-cpu"
+  CMD="python bench.py --steps 2 --warmup 3 --no-cpu"
   timeout 600 $CMD > $OUT/ncu_plain_$TAG.log 2>&1 &&
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches_$TAG.csv $CMD > $OUT/ncu_launches_$TAG.log 2>&1
   echo "ncu launches exit $?" | tee -a $OUT/summary_$TAG.txt
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:mse_stream -s 4 -c 2 -o $OUT/prof_mse_$TAG -f $CMD > $OUT/ncu_full_$TAG.log 2>&1
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:"mse_stream|attn_kl|clip_fwd|clip_bwd" -s 10 -c 12 -o $OUT/prof_mse_$TAG -f $CMD > $OUT/ncu_full_$TAG.log 2>&1
   echo "ncu full exit $?" | tee -a $OUT/summary_$TAG.txt
 fi
 for f in $OUT/pytest_*_$TAG.log; do echo "== $f"; tail -n 25 $f; done
