@@ -36,6 +36,8 @@ SIGNATURES = {
     "dcb_clip_grad_coef": [_vp, C.c_int64, C.c_int64, C.c_float, C.c_int, _vp, _vp, _vp, _vp],
     "dcb_clip_row_grads": [_vp, _vp, _vp, _vp, _vp, C.c_int64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int64,
                            C.c_int64, C.c_int64, C.c_int, C.c_float, _vp, _vp],
+    "dcb_clip_row_grads_pair": [_vp, _vp, _vp, _vp, _vp, C.c_int64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int64,
+                                C.c_int64, C.c_int64, C.c_int, C.c_float, _vp, _vp, _vp],
     "dcb_clip_grad_finish": [_vp, C.c_int, _vp, _vp, _vp, _vp, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int64,
                              _vp, _vp, _vp, C.c_int, _vp, C.c_int, _vp],
     "dcb_logits_row_stats": [_vp, C.c_int64, C.c_int64, _vp, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_float,
@@ -47,6 +49,8 @@ _SPECIAL = {
     "dcb_clip_workspace_bytes": (C.c_int64, [C.c_int64, C.c_int64]),
     "dcb_clip_grad_workspace_bytes": (C.c_int64, [C.c_int64, C.c_int64, C.c_int64]),
     "dcb_clip_grad_splits": (C.c_int, [C.c_int64, C.c_int64, C.c_int64]),
+    "dcb_clip_pair_splits": (C.c_int, [C.c_int64, C.c_int64, C.c_int64]),
+    "dcb_clip_pair_supported": (C.c_int, [C.c_int64]),
     "dcb_tower_grid": (C.c_int, []),
     "dcb_version": (C.c_int, []),
     "dcb_compiled_arch": (C.c_int, []),

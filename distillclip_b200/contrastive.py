@@ -19,6 +19,7 @@ The sharding / collective logic is written against a small "engine" interface so
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Dict, Optional, Sequence
 
 import torch
@@ -37,7 +38,11 @@ def _vp(t: Optional[torch.Tensor]):
 # engine: one call per kernel family of the C ABI
 # ==============================================================================================
 class CudaEngine:
-    """Thin, stateless wrapper over the C ABI (include/distillclip_b200.h)."""
+    """Thin wrapper over the C ABI (include/distillclip_b200.h)."""
+    #: backward kernel choice: CTA-pair kernel for D <= 768 (default) or the single-CTA D-chunked kernel
+    use_pair_kernel = os.environ.get("DCB_BWD_KERNEL", "pair") != "chunk"
+    #: tests only: [rows, cols] fp32 buffer that receives the logits the pair kernel's epilogue sees
+    dump_pair_logits = None
 
     def inv_norms(self, mats: Sequence[torch.Tensor]):
         outs = [torch.empty(m.shape[0], dtype=torch.float32, device=m.device) for m in mats]
@@ -89,12 +94,21 @@ class CudaEngine:
         rows, dim = a_s.shape
         cols = b_s.shape[0]
         lib = _lib.load()
-        n_split = lib.dcb_clip_grad_splits(rows, cols, dim)
-        acc = torch.empty(n_split, rows, dim, dtype=torch.float32, device=a_s.device)
-        _lib.call("dcb_clip_row_grads", _vp(a_s), _vp(b_s), _vp(a_t), _vp(b_t), _vp(b_s_t), b_s_t.shape[1],
-                  _vp(a_s_inv), _vp(b_s_inv), _vp(a_t_inv), _vp(b_t_inv), _vp(coef_row), _vp(coef_col),
-                  _vp(gmax_row), _vp(gmax_col), rows, cols, dim, ops.dtype_code(a_s), float(temperature or 1.0),
-                  _vp(acc), ops._stream_ptr())
+        if self.use_pair_kernel and lib.dcb_clip_pair_supported(dim):
+            # CTA-pair kernel (cta_group::2): whole embedding dimension in one pass, logits recomputed once
+            n_split = lib.dcb_clip_pair_splits(rows, cols, dim)
+            acc = torch.empty(n_split, rows, dim, dtype=torch.float32, device=a_s.device)
+            _lib.call("dcb_clip_row_grads_pair", _vp(a_s), _vp(b_s), _vp(a_t), _vp(b_t), _vp(b_s_t), b_s_t.shape[1],
+                      _vp(a_s_inv), _vp(b_s_inv), _vp(a_t_inv), _vp(b_t_inv), _vp(coef_row), _vp(coef_col),
+                      _vp(gmax_row), _vp(gmax_col), rows, cols, dim, ops.dtype_code(a_s), float(temperature or 1.0),
+                      _vp(acc), _vp(self.dump_pair_logits), ops._stream_ptr())
+        else:
+            n_split = lib.dcb_clip_grad_splits(rows, cols, dim)
+            acc = torch.empty(n_split, rows, dim, dtype=torch.float32, device=a_s.device)
+            _lib.call("dcb_clip_row_grads", _vp(a_s), _vp(b_s), _vp(a_t), _vp(b_t), _vp(b_s_t), b_s_t.shape[1],
+                      _vp(a_s_inv), _vp(b_s_inv), _vp(a_t_inv), _vp(b_t_inv), _vp(coef_row), _vp(coef_col),
+                      _vp(gmax_row), _vp(gmax_col), rows, cols, dim, ops.dtype_code(a_s), float(temperature or 1.0),
+                      _vp(acc), ops._stream_ptr())
         grad = torch.empty(rows, dim, dtype=grad_dtype, device=a_s.device)
         _lib.call("dcb_clip_grad_finish", _vp(acc), n_split, _vp(a_s), _vp(a_s_inv), _vp(b_s), _vp(b_s_inv), rows, cols,
                   dim, int(row_offset), int(global_batch), _vp(upstream), _vp(gmax_row), _vp(gmax_col),

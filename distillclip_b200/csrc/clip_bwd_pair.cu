@@ -1,0 +1,451 @@
+// Backward of the fused contrastive / logit-KL losses for one direction, CTA-pair version (cta_group::2).
+//
+// Same math as clip_bwd.cu (see there for the reference lines and the definition of G_ij), different mapping:
+// a cluster of two CTAs on one TPC owns a block of 128 a-side rows, 64 per CTA, and the WHOLE embedding dimension.
+// With tcgen05.mma.cta_group::2 and M = 128 each CTA keeps 64 accumulator rows spread over all 128 TMEM lanes
+// (lanes 0-63 hold the first half of the N columns, lanes 64-127 the second half), so an accumulator of N columns
+// costs N/2 TMEM columns: the [64 x D] gradient accumulator of each CTA fits next to double-buffered S/T tiles for
+// D <= 768 (D/2 + 2 x NT <= 512 columns), and the logits are recomputed exactly once per direction instead of once
+// per 256-column chunk of D.  Each CTA stages its own half of every operand: 64 rows of a, NT/2 rows of b, and 128 of
+// the 256 rows of each b_hatT slice; the leader CTA (cluster rank 0) issues all MMAs; completion is multicast to the
+// barriers of both CTAs; both CTAs run the epilogue on their own 64 rows.
+//
+// Warp roles per CTA (256 threads): warp 0 = operand-ring producer, warp 1 = TMEM alloc (+ MMA issuer in the leader),
+// warp 2 = b_hatT producer, warp 3 idle, warps 4-7 = epilogue (warp w reads TMEM lanes 32 (w-4) ..).
+#include "tc_common.cuh"
+
+namespace dcb {
+
+namespace bwdp {
+constexpr int kRowsPerCta = 64, kBK = 64, kUmmaK = 16;
+constexpr int kThreads = 256;
+constexpr int kTmemCols = 512;
+constexpr int kATile = kRowsPerCta * kBK * 2;             // 8 KiB  [64 x 64] 16-bit
+constexpr int kSliceRows = 128;                           // rows of one 256-row b_hatT slice held by one CTA
+constexpr int kMaxSlices = 3;                             // D <= 768
+template <int NT> struct Cfg {
+    static constexpr int kBHalf = NT / 2;                                 // b rows staged per CTA
+    static constexpr int kBTile = kBHalf * kBK * 2;                       // bytes
+    static constexpr int kStageBytes = 2 * kATile + 2 * kBTile;           // a_stu, a_tea, b_stu, b_tea
+    static constexpr int kStages = NT == 128 ? 3 : 4;
+    static constexpr int kGBytes = kRowsPerCta * NT * 2;                  // fp16 G tile of this CTA
+    static constexpr int kBtSliceBytes = kSliceRows * NT * 2;             // one slice, all K sub-tiles
+    static constexpr int kStCols = NT;                                    // TMEM columns of one S/T stage (S NT/2 + T NT/2)
+    static constexpr int kAccCol = 2 * kStCols;
+    static constexpr int smem_bytes(int slices) {
+        return 1024 + kStages * kStageBytes + kGBytes + slices * kBtSliceBytes + 2 * 5 * NT * 4 + 256;
+    }
+};
+}  // namespace bwdp
+
+struct ClipBwdPairParams {
+    const float* a_inv_stu;
+    const float* b_inv_stu;
+    const float* a_inv_tea;
+    const float* b_inv_tea;
+    const float* coef_row;
+    const float* coef_col;
+    const float* gmax_row;
+    const float* gmax_col;
+    float* acc;               // [n_split][rows][dim] fp32
+    float* dump_s;            // tests only: [rows, cols] student logits as seen by the epilogue
+    int rows, cols, dim;
+    int slices;               // ceil(dim / 256)
+    int n_split, col_tiles;
+    float inv_temp;
+};
+
+__device__ __forceinline__ float pair_tile_scale(float gmax) {      // must match clip_grad_tile_scale in clip_misc.cu
+    if (!(gmax > 0.f) || !isfinite(gmax)) return 1.f;
+    int e;
+    frexpf(gmax, &e);
+    return ldexpf(1.f, 14 - e);
+}
+__device__ __forceinline__ float ex2p(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+template <bool kTeacher, int NT>
+__global__ void __launch_bounds__(bwdp::kThreads, 1)
+clip_bwd_pair_kernel(const __grid_constant__ CUtensorMap map_a_stu, const __grid_constant__ CUtensorMap map_b_stu,
+                     const __grid_constant__ CUtensorMap map_a_tea, const __grid_constant__ CUtensorMap map_b_tea,
+                     const __grid_constant__ CUtensorMap map_bt, const __grid_constant__ ClipBwdPairParams p,
+                     const uint32_t idesc_st, const uint32_t idesc_grad) {
+    using namespace bwdp;
+    using namespace tc;
+    using C = Cfg<NT>;
+    constexpr int kSub = NT / kBK;                       // K sub-tiles of the gradient GEMM (K = NT)
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+    const uint32_t ring = smem_base;
+    const uint32_t g_smem = ring + C::kStages * C::kStageBytes;
+    uint8_t* g_gen = smem_gen + C::kStages * C::kStageBytes;
+    const uint32_t bt_smem = g_smem + C::kGBytes;
+    const int bt_bytes = p.slices * C::kBtSliceBytes;
+    float* scale_buf = reinterpret_cast<float*>(smem_gen + C::kStages * C::kStageBytes + C::kGBytes + bt_bytes);   // [2][5][NT]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(scale_buf) + 2 * 5 * NT * 4);
+    const uint32_t bar_full = smem_u32(bars);                    // [kStages]  leader: TMA bytes of both CTAs
+    const uint32_t bar_empty = bar_full + 8 * C::kStages;        // [kStages]  each CTA: slot free (multicast commit)
+    const uint32_t bar_stfull = bar_empty + 8 * C::kStages;      // [2] each CTA: S/T accumulators ready (multicast commit)
+    const uint32_t bar_stempty = bar_stfull + 16;                // [2] leader: 8 epilogue warps of both CTAs drained them
+    const uint32_t bar_gfull = bar_stempty + 16;                 // leader: 8 epilogue warps wrote their G halves
+    const uint32_t bar_gempty = bar_gfull + 8;                   // each CTA: gradient MMAs done with G / b_hatT smem
+    const uint32_t bar_btfull = bar_gempty + 8;                  // leader: b_hatT bytes of both CTAs
+    const uint32_t bar_accfull = bar_btfull + 8;                 // each CTA: gradient accumulator final
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::kStages + 8);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int cluster_id = blockIdx.x >> 1;
+    const int rb = cluster_id / p.n_split, sp = cluster_id % p.n_split;
+    const int tile_begin = (int)(((long long)sp * p.col_tiles) / p.n_split);
+    const int tile_end = (int)(((long long)(sp + 1) * p.col_tiles) / p.n_split);
+    const int n_tiles = tile_end - tile_begin;
+    const int n_kc = (p.dim + kBK - 1) / kBK;
+    const int row0 = rb * 128 + (int)rank * kRowsPerCta;          // first a-side row of this CTA
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < C::kStages; ++s) {
+            mbar_init(bar_full + 8 * s, 1);
+            mbar_init(bar_empty + 8 * s, 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(bar_stfull + 8 * s, 1);
+            mbar_init(bar_stempty + 8 * s, 8);
+        }
+        mbar_init(bar_gfull, 8);
+        mbar_init(bar_gempty, 1);
+        mbar_init(bar_btfull, 1);
+        mbar_init(bar_accfull, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc_pair(smem_u32(tmem_slot), kTmemCols);
+    tc_fence_before_sync();
+    __syncthreads();
+    cluster_sync_all();                                           // peer barriers initialised, both TMEM allocations done
+    tc_fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+    // leader-side barrier addresses as seen from this CTA
+    const uint32_t l_full = map_to_cta(bar_full, 0), l_stempty = map_to_cta(bar_stempty, 0);
+    const uint32_t l_gfull = map_to_cta(bar_gfull, 0), l_btfull = map_to_cta(bar_btfull, 0);
+
+    if (warp == 0) {
+        // ---------------------------------------------------------------- operand ring (own halves)
+        if (lane == 0) {
+            tma_prefetch_desc(&map_a_stu);
+            tma_prefetch_desc(&map_b_stu);
+            int stage = 0;
+            uint32_t phase = 0;
+            constexpr uint32_t kBytesPerCta = (kTeacher ? 2 : 1) * (kATile + C::kBTile);
+            for (int t = 0; t < n_tiles; ++t) {
+                const int col0 = (tile_begin + t) * NT + (int)rank * C::kBHalf;
+                for (int kc = 0; kc < n_kc; ++kc) {
+                    mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+                    const uint32_t dst = ring + stage * C::kStageBytes;
+                    if (leader) mbar_arrive_expect_tx(bar_full + 8 * stage, 2 * kBytesPerCta);
+                    const uint32_t full = l_full + 8 * stage;
+                    tma_load_2d_pair(dst, &map_a_stu, full, kc * kBK, row0);
+                    tma_load_2d_pair(dst + 2 * kATile, &map_b_stu, full, kc * kBK, col0);
+                    if (kTeacher) {
+                        tma_load_2d_pair(dst + kATile, &map_a_tea, full, kc * kBK, row0);
+                        tma_load_2d_pair(dst + 2 * kATile + C::kBTile, &map_b_tea, full, kc * kBK, col0);
+                    }
+                    if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 2) {
+        // ---------------------------------------------------------------- b_hatT: this CTA's 128 rows of every 256-row slice
+        if (lane == 0) {
+            tma_prefetch_desc(&map_bt);
+            for (int t = 0; t < n_tiles; ++t) {
+                mbar_wait(bar_gempty, (t & 1) ^ 1);
+                if (leader) mbar_arrive_expect_tx(bar_btfull, 2 * bt_bytes);
+                const int j0 = (tile_begin + t) * NT;
+                for (int sl = 0; sl < p.slices; ++sl)
+                    for (int ks = 0; ks < kSub; ++ks)
+                        tma_load_2d_pair(bt_smem + sl * C::kBtSliceBytes + ks * (kSliceRows * kBK * 2), &map_bt, l_btfull,
+                                         j0 + ks * kBK, sl * 256 + (int)rank * kSliceRows);
+            }
+        }
+    } else if (warp == 1) {
+        // ---------------------------------------------------------------- MMA issuer (leader CTA, one thread)
+        if (leader && lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            auto issue_st = [&](int t) {
+                const int as = t & 1;
+                mbar_wait(bar_stempty + 8 * as, ((t >> 1) & 1) ^ 1);
+                tc_fence_after_sync();
+                const uint32_t acc_s = tmem_base + as * C::kStCols, acc_t = acc_s + NT / 2;
+                for (int kc = 0; kc < n_kc; ++kc) {
+                    mbar_wait(bar_full + 8 * stage, phase);
+                    tc_fence_after_sync();
+                    const uint32_t src = ring + stage * C::kStageBytes;
+                    const uint64_t da_s = umma_desc_k_sw128(src), da_t = umma_desc_k_sw128(src + kATile);
+                    const uint64_t db_s = umma_desc_k_sw128(src + 2 * kATile);
+                    const uint64_t db_t = umma_desc_k_sw128(src + 2 * kATile + C::kBTile);
+#pragma unroll
+                    for (int k = 0; k < kBK / kUmmaK; ++k) {
+                        const uint32_t accum = (kc > 0 || k > 0) ? 1u : 0u;
+                        umma_f16_pair(acc_s, da_s + 2 * k, db_s + 2 * k, idesc_st, accum);
+                        if (kTeacher) umma_f16_pair(acc_t, da_t + 2 * k, db_t + 2 * k, idesc_st, accum);
+                    }
+                    umma_commit_pair(bar_empty + 8 * stage, 3);
+                    if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+                }
+                umma_commit_pair(bar_stfull + 8 * as, 3);
+            };
+            issue_st(0);
+            for (int t = 0; t < n_tiles; ++t) {
+                if (t + 1 < n_tiles) issue_st(t + 1);
+                mbar_wait(bar_gfull, t & 1);
+                mbar_wait(bar_btfull, t & 1);
+                tc_fence_after_sync();
+                for (int sl = 0; sl < p.slices; ++sl) {
+#pragma unroll
+                    for (int ks = 0; ks < kSub; ++ks) {
+                        const uint64_t dg = umma_desc_k_sw128(g_smem + ks * (kRowsPerCta * kBK * 2));
+                        const uint64_t dbt = umma_desc_k_sw128(bt_smem + sl * C::kBtSliceBytes + ks * (kSliceRows * kBK * 2));
+#pragma unroll
+                        for (int k = 0; k < kBK / kUmmaK; ++k)
+                            umma_f16_pair(tmem_base + C::kAccCol + sl * 128, dg + 2 * k, dbt + 2 * k, idesc_grad,
+                                          (t > 0 || ks > 0 || k > 0) ? 1u : 0u);
+                    }
+                }
+                umma_commit_pair(bar_gempty, 3);
+            }
+            umma_commit_pair(bar_accfull, 3);
+        }
+    } else if (warp >= 4) {
+        // ---------------------------------------------------------------- epilogue (both CTAs, own 64 rows)
+        const int q = warp & 3;                        // TMEM lane quadrant
+        const int r = (q & 1) * 32 + lane;             // row inside this CTA's 64
+        const int half = q >> 1;                       // lanes 0-63: columns [0, N/2), lanes 64-127: columns [N/2, N)
+        constexpr int kColsPerThread = NT / 2;
+        const int ep_tid = (warp - 4) * 32 + lane;     // 0..127
+        const int grow = row0 + r;
+        const bool row_ok = grow < p.rows;
+        const float LOG2E = 1.4426950408889634f;
+        const float r_s = row_ok ? __ldg(p.a_inv_stu + grow) : 0.f;
+        const float r_t = (kTeacher && row_ok) ? __ldg(p.a_inv_tea + grow) : 0.f;
+        const float k1 = r_s * LOG2E, k1t = r_s * LOG2E * p.inv_temp, k2t = r_t * LOG2E * p.inv_temp;
+        const float n1 = -LOG2E, n1t = -LOG2E * p.inv_temp;
+        const float ra = row_ok ? __ldg(p.coef_row + grow) : 0.f;
+        const float rbeta = (kTeacher && row_ok) ? __ldg(p.coef_row + p.rows + grow) : 0.f;
+        const float rg = (kTeacher && row_ok) ? __ldg(p.coef_row + 2 * (size_t)p.rows + grow) : 0.f;
+        const float gscale = pair_tile_scale(__ldg(p.gmax_row) + __ldg(p.gmax_col));
+        for (int t = 0; t < n_tiles; ++t) {
+            const int as = t & 1;
+            const int col0 = (tile_begin + t) * NT;
+            float* sc = scale_buf + as * 5 * NT;           // [c_stu][c_tea][alpha'][beta'][gamma'] x NT
+            for (int c = ep_tid; c < NT; c += 128) {
+                const int gc = col0 + c;
+                const bool ok = gc < p.cols;
+                sc[c] = ok ? __ldg(p.b_inv_stu + gc) : 0.f;
+                sc[2 * NT + c] = ok ? __ldg(p.coef_col + gc) : 0.f;
+                if (kTeacher) {
+                    sc[NT + c] = ok ? __ldg(p.b_inv_tea + gc) : 0.f;
+                    sc[3 * NT + c] = ok ? __ldg(p.coef_col + p.cols + gc) : 0.f;
+                    sc[4 * NT + c] = ok ? __ldg(p.coef_col + 2 * (size_t)p.cols + gc) : 0.f;
+                }
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            mbar_wait(bar_stfull + 8 * as, (t >> 1) & 1);
+            tc_fence_after_sync();
+            const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * C::kStCols;
+            uint32_t packed[kColsPerThread / 2];
+#pragma unroll
+            for (int ch = 0; ch < kColsPerThread / 32; ++ch) {
+                float sv[32], tv[32];
+                tmem_ld_32x32(lane_addr + ch * 32, sv);
+                if (kTeacher) tmem_ld_32x32(lane_addr + NT / 2 + ch * 32, tv);
+                tmem_ld_wait();
+#pragma unroll
+                for (int c = 0; c < 32; c += 2) {
+                    float g2[2];
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int cc = half * kColsPerThread + ch * 32 + c + e;      // column inside the tile
+                        const float u = sv[c + e] * sc[cc];
+                        if (p.dump_s && row_ok && col0 + cc < p.cols) p.dump_s[(size_t)grow * p.cols + col0 + cc] = u * r_s;
+                        float g = ex2p(fmaf(u, k1, n1)) * (ra + sc[2 * NT + cc]);
+                        if (kTeacher) {
+                            const float v = tv[c + e] * sc[NT + cc];
+                            g = fmaf(ex2p(fmaf(u, k1t, n1t)), rbeta + sc[3 * NT + cc], g);
+                            g = fmaf(-ex2p(fmaf(v, k2t, n1t)), rg + sc[4 * NT + cc], g);
+                        }
+                        g2[e] = g * gscale;
+                    }
+                    packed[(ch * 32 + c) >> 1] = pack2<__half>(g2[0], g2[1]);
+                }
+            }
+            tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(l_stempty + 8 * as);
+            mbar_wait(bar_gempty, (t & 1) ^ 1);
+            // this thread's columns [half*NT/2, half*NT/2 + NT/2) of row r -> K-major SW128 sub-tiles of 64 columns
+#pragma unroll
+            for (int c8 = 0; c8 < kColsPerThread / 8; ++c8) {
+                const int col = half * kColsPerThread + c8 * 8;
+                const int ks = col >> 6, chunk = (col & 63) >> 3;
+                uint4 w = make_uint4(packed[4 * c8], packed[4 * c8 + 1], packed[4 * c8 + 2], packed[4 * c8 + 3]);
+                *reinterpret_cast<uint4*>(g_gen + ks * (kRowsPerCta * kBK * 2) + sw128_chunk_offset(r, chunk)) = w;
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(l_gfull);
+        }
+        // gradient accumulator -> global partial buffer.  Slice sl: lanes 0-63 hold d in [256 sl, 256 sl + 128),
+        // lanes 64-127 hold d in [256 sl + 128, 256 sl + 256); 128 TMEM columns per slice.
+        mbar_wait(bar_accfull, 0);
+        tc_fence_after_sync();
+        const uint32_t acc_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + C::kAccCol;
+        float* out = p.acc + ((size_t)sp * p.rows + (row_ok ? grow : 0)) * p.dim;
+        for (int sl = 0; sl < p.slices; ++sl) {
+#pragma unroll 1
+            for (int ch = 0; ch < 4; ++ch) {
+                const int d0 = sl * 256 + half * 128 + ch * 32;
+                if (d0 >= p.dim) break;                                  // warp-uniform
+                float v[32];
+                tmem_ld_32x32(acc_addr + sl * 128 + ch * 32, v);
+                tmem_ld_wait();
+                if (row_ok) {
+#pragma unroll
+                    for (int c = 0; c < 32; c += 4) {
+                        const int d = d0 + c;
+                        if (d + 3 < p.dim) {
+                            *reinterpret_cast<float4*>(out + d) = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
+                        } else {
+                            for (int e = 0; e < 4; ++e)
+                                if (d + e < p.dim) out[d + e] = v[c + e];
+                        }
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    cluster_sync_all();                  // the peer may still be reading operands this CTA's MMAs depend on / arriving remotely
+    if (warp == 1) {
+        __syncwarp();
+        tc_fence_after_sync();
+        tmem_dealloc_pair(tmem_base, kTmemCols);
+    }
+}
+
+static int clip_bwd_pair_nt(int64_t dim) { return dim <= 512 ? 128 : 64; }
+
+static int clip_bwd_pair_splits(int64_t rows, int64_t cols, int64_t dim) {
+    const int64_t row_blocks = (rows + 127) / 128;
+    const int64_t col_tiles = (cols + clip_bwd_pair_nt(dim) - 1) / clip_bwd_pair_nt(dim);
+    const int64_t slots = kNumSMs / 2;                   // clusters resident at once
+    int64_t best = 1;
+    double best_cost = 1e30;
+    for (int64_t n = 1; n <= 32 && n <= col_tiles; ++n) {
+        const int64_t waves = (row_blocks * n + slots - 1) / slots;
+        const int64_t tiles = (col_tiles + n - 1) / n;
+        const double cost = (double)waves * ((double)tiles + 1.5) + 0.02 * (double)n;     // 1.5 tiles of prologue/epilogue per CTA
+        if (cost < best_cost) { best_cost = cost; best = n; }
+    }
+    return (int)best;
+}
+
+template <bool kTeacher, int NT>
+static int launch_pair(dim3 grid, int smem, cudaStream_t st, const CUtensorMap& ma_s, const CUtensorMap& mb_s,
+                       const CUtensorMap& ma_t, const CUtensorMap& mb_t, const CUtensorMap& mbt,
+                       const ClipBwdPairParams& p, uint32_t idesc_st, uint32_t idesc_grad) {
+    static int max_set = 0;
+    if (smem > max_set) {
+        DCB_CUDA_OK(cudaFuncSetAttribute(clip_bwd_pair_kernel<kTeacher, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        max_set = smem;
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(bwdp::kThreads);
+    cfg.dynamicSmemBytes = (size_t)smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    DCB_CUDA_OK(cudaLaunchKernelEx(&cfg, clip_bwd_pair_kernel<kTeacher, NT>, ma_s, mb_s, ma_t, mb_t, mbt, p, idesc_st, idesc_grad));
+    return 0;
+}
+
+}  // namespace dcb
+
+extern "C" int dcb_clip_pair_supported(int64_t dim) { return dim >= 8 && dim <= 768 && dim % 8 == 0; }
+extern "C" int dcb_clip_pair_splits(int64_t rows_local, int64_t cols, int64_t dim) {
+    return dcb::clip_bwd_pair_splits(rows_local, cols, dim);
+}
+
+extern "C" int dcb_clip_row_grads_pair(const void* stu_a, const void* stu_b, const void* tea_a, const void* tea_b,
+                                       const void* stu_b_t, int64_t bt_pitch_elems,
+                                       const float* stu_a_inv, const float* stu_b_inv, const float* tea_a_inv,
+                                       const float* tea_b_inv, const float* coef_row, const float* coef_col,
+                                       const float* gmax_row, const float* gmax_col, int64_t rows_local, int64_t cols,
+                                       int64_t dim, int dtype, float temperature, float* acc_parts, float* dump_s,
+                                       void* stream) {
+    using namespace dcb;
+    DCB_REQUIRE(stu_a && stu_b && stu_b_t && stu_a_inv && stu_b_inv && coef_row && coef_col && gmax_row && gmax_col && acc_parts,
+                "NULL pointer argument");
+    DCB_REQUIRE(dtype == DCB_BF16 || dtype == DCB_F16, "the fused contrastive kernel takes bf16 or fp16 embeddings");
+    DCB_REQUIRE(dcb_clip_pair_supported(dim), "pair kernel supports 8 <= dim <= 768, dim %% 8 == 0 (got %lld)", (long long)dim);
+    DCB_REQUIRE(rows_local >= 1 && cols >= 1, "bad shape");
+    DCB_REQUIRE(bt_pitch_elems >= cols && bt_pitch_elems % 8 == 0, "bT pitch must be >= cols and a multiple of 8 elements");
+    const bool teacher = tea_a != nullptr;
+    if (teacher) DCB_REQUIRE(tea_b && tea_a_inv && tea_b_inv && temperature > 0.f, "teacher arguments incomplete");
+    const int nt = clip_bwd_pair_nt(dim);
+    CUtensorMap ma_s, mb_s, ma_t, mb_t, mbt;
+    const uint64_t pitch = (uint64_t)dim * 2;
+    if (tc::encode_tile_map_16bit(&ma_s, stu_a, rows_local, dim, pitch, bwdp::kRowsPerCta)) return 1;
+    if (tc::encode_tile_map_16bit(&mb_s, stu_b, cols, dim, pitch, nt / 2)) return 1;
+    if (teacher) {
+        if (tc::encode_tile_map_16bit(&ma_t, tea_a, rows_local, dim, pitch, bwdp::kRowsPerCta)) return 1;
+        if (tc::encode_tile_map_16bit(&mb_t, tea_b, cols, dim, pitch, nt / 2)) return 1;
+    } else {
+        ma_t = ma_s;
+        mb_t = mb_s;
+    }
+    if (tc::encode_tile_map_16bit(&mbt, stu_b_t, dim, cols, (uint64_t)bt_pitch_elems * 2, bwdp::kSliceRows)) return 1;
+    ClipBwdPairParams p{};
+    p.a_inv_stu = stu_a_inv;
+    p.b_inv_stu = stu_b_inv;
+    p.a_inv_tea = tea_a_inv;
+    p.b_inv_tea = tea_b_inv;
+    p.coef_row = coef_row;
+    p.coef_col = coef_col;
+    p.gmax_row = gmax_row;
+    p.gmax_col = gmax_col;
+    p.acc = acc_parts;
+    p.dump_s = dump_s;
+    p.rows = (int)rows_local;
+    p.cols = (int)cols;
+    p.dim = (int)dim;
+    p.slices = (int)((dim + 255) / 256);
+    p.n_split = clip_bwd_pair_splits(rows_local, cols, dim);
+    p.col_tiles = (int)((cols + nt - 1) / nt);
+    p.inv_temp = teacher ? 1.0f / temperature : 1.0f;
+    const int row_blocks = (int)((rows_local + 127) / 128);
+    const uint32_t idesc_st = tc::umma_idesc_f16(128, nt, dtype == DCB_BF16 ? 1 : 0);
+    const uint32_t idesc_grad = tc::umma_idesc_f16(128, 256, 0);          // fp16 G x fp16 b_hatT, 256-row slices
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    dim3 grid((unsigned)(2 * row_blocks * p.n_split));
+    if (nt == 128) {
+        const int smem = bwdp::Cfg<128>::smem_bytes(p.slices);
+        return teacher ? launch_pair<true, 128>(grid, smem, st, ma_s, mb_s, ma_t, mb_t, mbt, p, idesc_st, idesc_grad)
+                       : launch_pair<false, 128>(grid, smem, st, ma_s, mb_s, ma_t, mb_t, mbt, p, idesc_st, idesc_grad);
+    }
+    const int smem = bwdp::Cfg<64>::smem_bytes(p.slices);
+    return teacher ? launch_pair<true, 64>(grid, smem, st, ma_s, mb_s, ma_t, mb_t, mbt, p, idesc_st, idesc_grad)
+                   : launch_pair<false, 64>(grid, smem, st, ma_s, mb_s, ma_t, mb_t, mbt, p, idesc_st, idesc_grad);
+}

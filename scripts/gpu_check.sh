@@ -9,7 +9,9 @@ timeout 600 python -m pytest tests/test_gpu_streaming.py -m gpu -q --timeout 300
 echo "streaming exit $?" | tee -a $OUT/summary_$TAG.txt
 timeout 300 python -m pytest tests/test_gpu_contrastive.py -m gpu -q --timeout 120 -k "similarity" > $OUT/pytest_similarity_$TAG.log 2>&1
 echo "similarity exit $?" | tee -a $OUT/summary_$TAG.txt
-timeout 900 python -m pytest tests/test_gpu_contrastive.py -m gpu -q --timeout 300 -k "not similarity" > $OUT/pytest_contrastive_$TAG.log 2>&1
+timeout 300 python -m pytest tests/test_gpu_contrastive.py -m gpu -q --timeout 120 -k "pair_kernel_sees" > $OUT/pytest_pair_$TAG.log 2>&1
+echo "pair exit $?" | tee -a $OUT/summary_$TAG.txt
+timeout 900 python -m pytest tests/test_gpu_contrastive.py -m gpu -q --timeout 300 -k "not similarity and not pair_kernel_sees" > $OUT/pytest_contrastive_$TAG.log 2>&1
 echo "contrastive exit $?" | tee -a $OUT/summary_$TAG.txt
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/smoke_$TAG.log 2>&1
 echo "smoke exit $?" | tee -a $OUT/summary_$TAG.txt

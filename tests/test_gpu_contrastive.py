@@ -50,6 +50,33 @@ def test_similarity_tiles_match_matmul(cuda_device, b, d):
     assert rel_l2(stats[2].cpu().numpy(), np.exp((t_ref - 1) / 2.0).sum(1)) <= 1e-5
 
 
+@pytest.fixture(params=["pair", "chunk"])
+def bwd_kernel(request):
+    """Both backward kernels: the CTA-pair kernel (default, D <= 768) and the single-CTA D-chunked kernel."""
+    from distillclip_b200 import contrastive as ct
+    old = ct.CudaEngine.use_pair_kernel
+    ct.CudaEngine.use_pair_kernel = request.param == "pair"
+    yield request.param
+    ct.CudaEngine.use_pair_kernel = old
+
+
+@pytest.mark.parametrize("b,d", [(130, 72), (256, 512), (300, 200), (384, 768)])
+def test_pair_kernel_sees_the_right_logits(cuda_device, b, d):
+    """cta_group::2 plumbing (cluster launch, per-CTA operand halves, the 2x2 TMEM accumulator layout): the logits the
+    pair kernel's epilogue reconstructs must equal the normalised matmul."""
+    from distillclip_b200 import contrastive as ct
+    si, st, ti, tt = [x.cuda() for x in synth(b, d, 5)]
+    eng = ct.CudaEngine()
+    eng.use_pair_kernel = True
+    eng.dump_pair_logits = torch.zeros(b, b, device="cuda")
+    out, saved = ct.contrastive_forward(eng, si, st, ti, tt, 2.0, None)
+    up = torch.tensor([1.0, 1.0], device="cuda")
+    ct.contrastive_backward(eng, saved, up, want_img=True, want_txt=False)
+    torch.cuda.synchronize()
+    s_ref, _ = cf.clip_logits(si.float().cpu().numpy(), st.float().cpu().numpy())
+    assert np.abs(eng.dump_pair_logits.cpu().numpy() - s_ref).max() <= 2e-6
+
+
 def _fused(si, st, ti, tt, T, w_hard, w_soft, grad_dtype=None):
     from distillclip_b200 import contrastive as ct
     eng = ct.CudaEngine()
@@ -60,7 +87,7 @@ def _fused(si, st, ti, tt, T, w_hard, w_soft, grad_dtype=None):
 
 
 @pytest.mark.parametrize("name", CLIP)
-def test_fused_contrastive_golden(cuda_device, name):
+def test_fused_contrastive_golden(cuda_device, bwd_kernel, name):
     g = golden(name)
     T = float(g["temperature"])
     si, st, ti, tt = dev(g["stu_img"]), dev(g["stu_txt"]), dev(g["tea_img"]), dev(g["tea_txt"])
@@ -77,7 +104,7 @@ def test_fused_contrastive_golden(cuda_device, name):
 @pytest.mark.parametrize("b,d,T,dtype", [(256, 512, 2.0, torch.bfloat16), (512, 512, 1.0, torch.bfloat16),
                                          (384, 768, 4.0, torch.bfloat16), (200, 136, 0.5, torch.bfloat16),
                                          (256, 512, 2.0, torch.float16)])
-def test_fused_contrastive_random_vs_oracle(cuda_device, b, d, T, dtype):
+def test_fused_contrastive_random_vs_oracle(cuda_device, bwd_kernel, b, d, T, dtype):
     si, st, ti, tt = synth(b, d, b + d, dtype)
     ref = cf.contrastive_from_embeddings(*[x.float().numpy() for x in (si, st, ti, tt)], T, w_hard=0.6, w_soft=0.4)
     out, gi, gt = _fused(si.cuda(), st.cuda(), ti.cuda(), tt.cuda(), T, 0.6, 0.4, torch.float32)
@@ -87,7 +114,7 @@ def test_fused_contrastive_random_vs_oracle(cuda_device, b, d, T, dtype):
     assert rel_l2(gt.cpu().numpy(), ref["d_txt"]) <= GRAD_RTOL
 
 
-def test_hard_label_only_autograd(cuda_device):
+def test_hard_label_only_autograd(cuda_device, bwd_kernel):
     from distillclip_b200.contrastive import clip_contrastive
     si, st, _, _ = synth(320, 256, 9)
     ref = cf.contrastive_from_embeddings(si.float().numpy(), st.float().numpy(), w_hard=1.0)
@@ -101,7 +128,7 @@ def test_hard_label_only_autograd(cuda_device):
     assert rel_l2(b.grad.float().cpu().numpy(), ref["d_txt"]) <= GRAD_BF16_STORAGE_RTOL
 
 
-def test_row_sharded_virtual_ranks(cuda_device):
+def test_row_sharded_virtual_ranks(cuda_device, bwd_kernel):
     """R virtual ranks on one GPU.  Each rank's kernel call sees its row slice (row_offset = r*B/R)
     against all columns; per-rank sums add up to the single-process global-batch oracle and the per-rank gradients
     concatenate to the oracle gradient.  Labels for local row i are r*B/R + i (checked through stats[4])."""
