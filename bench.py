@@ -290,8 +290,7 @@ def bench_tower(cfg, name, args, device, dist, world, pk, with_cpu):
         entries.append((kind, len(sv), [x.detach() for x in sv], tv, [True] * len(sv), 1.0 / len(cfg["names"])))
     w = [1.0] * len(entries)
     pct = [1.0 / len(entries)] * len(entries)
-    res0, grads0 = ops.launch_tower(entries, w, pct)
-    bufs = ops.launch_tower.last_buffers
+    bufs = ops.launch_tower(entries, w, pct)
     kernels = {"tower_stream_kernel": (lambda: ops.launch_tower(entries, w, pct, out=bufs), algo_bytes)}
     s_h, t_h = [x.detach() for x in stu["representations"]], tea["representations"]
     p_h, _, g_h = ops.launch_mse(s_h, t_h, len(s_h), 1.0, [True] * len(s_h))

@@ -31,7 +31,7 @@ SIGNATURES = {
     "dcb_row_inv_norm": [C.c_int, _vpp, _vpp, _i64p, C.c_int64, C.c_int, _vp],
     "dcb_transpose_norm_f16": [_vp, _vp, _vp, C.c_int64, C.c_int64, C.c_int64, C.c_int, _vp],
     "dcb_clip_row_stats": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int64, C.c_int64, C.c_int64, C.c_int64,
-                           C.c_int, C.c_float, _vp, _vp, _vp, _vp, _vp],
+                           C.c_int, C.c_float, _vp, _vp, _vp, _vp, _vp, _vp],
     "dcb_clip_losses": [_vp, _vp, C.c_int64, C.c_int64, C.c_int64, C.c_float, C.c_int, _vp, _vp, _vp],
     "dcb_clip_grad_coef": [_vp, C.c_int64, C.c_int64, C.c_float, C.c_int, _vp, _vp, _vp, _vp],
     "dcb_clip_row_grads": [_vp, _vp, _vp, _vp, _vp, C.c_int64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int64,

@@ -56,18 +56,19 @@ class CudaEngine:
         rows, dim = a_s.shape
         cols = b_s.shape[0]
         stats = torch.empty(5, rows, dtype=torch.float32, device=a_s.device)
+        rowloss = torch.empty(2, rows, dtype=torch.float64, device=a_s.device)
         ws = torch.empty(max(1, _lib.load().dcb_clip_workspace_bytes(rows, cols)), dtype=torch.uint8, device=a_s.device)
         _lib.call("dcb_clip_row_stats", _vp(a_s), _vp(b_s), _vp(a_t), _vp(b_t), _vp(a_s_inv), _vp(b_s_inv),
                   _vp(a_t_inv), _vp(b_t_inv), rows, int(row_offset), cols, dim, ops.dtype_code(a_s),
-                  float(temperature or 1.0), _vp(stats), _vp(ws), _vp(dump[0]) if dump else None,
+                  float(temperature or 1.0), _vp(stats), _vp(rowloss), _vp(ws), _vp(dump[0]) if dump else None,
                   _vp(dump[1]) if dump and a_t is not None else None, ops._stream_ptr())
-        return stats
+        return stats, rowloss
 
-    def losses(self, stats_i2t, stats_t2i, global_batch, temperature, has_teacher):
-        dev = stats_i2t.device
+    def losses(self, rowloss_i2t, rowloss_t2i, global_batch, temperature, has_teacher):
+        dev = rowloss_i2t.device
         sums = torch.empty(4, dtype=torch.float64, device=dev)
         out = torch.empty(2, dtype=torch.float32, device=dev)
-        _lib.call("dcb_clip_losses", _vp(stats_i2t), _vp(stats_t2i), stats_i2t.shape[1], stats_t2i.shape[1],
+        _lib.call("dcb_clip_losses", _vp(rowloss_i2t), _vp(rowloss_t2i), rowloss_i2t.shape[1], rowloss_t2i.shape[1],
                   int(global_batch), float(temperature or 1.0), int(has_teacher), _vp(sums), _vp(out), ops._stream_ptr())
         return sums, out
 
@@ -166,11 +167,11 @@ def contrastive_forward(engine, si, st, ti, tt, temperature, group=None):
     def local(x):
         return None if x is None else x[loc]
     # i2t rows: a = image, b = text ; t2i rows: a = text, b = image
-    stats_i2t = engine.row_stats(si, st_all, ti, tt_all, local(si_inv_all), st_inv_all, local(ti_inv_all), tt_inv_all,
-                                 offset, temperature)
-    stats_t2i = engine.row_stats(st, si_all, tt, ti_all, local(st_inv_all), si_inv_all, local(tt_inv_all), ti_inv_all,
-                                 offset, temperature)
-    sums, out = engine.losses(stats_i2t, stats_t2i, b_global, temperature, has_teacher)
+    stats_i2t, rl_i2t = engine.row_stats(si, st_all, ti, tt_all, local(si_inv_all), st_inv_all, local(ti_inv_all),
+                                         tt_inv_all, offset, temperature)
+    stats_t2i, rl_t2i = engine.row_stats(st, si_all, tt, ti_all, local(st_inv_all), si_inv_all, local(tt_inv_all),
+                                         ti_inv_all, offset, temperature)
+    sums, out = engine.losses(rl_i2t, rl_t2i, b_global, temperature, has_teacher)
     if world > 1:
         import torch.distributed as dist
         dist.all_reduce(sums, group=group)

@@ -270,24 +270,41 @@ clip_fwd_kernel(const __grid_constant__ CUtensorMap map_a_stu, const __grid_cons
     }
 }
 
-// stats[k][r] = sum over splits (fixed order -> deterministic), stats[4][r] = S_rr
-__global__ void __launch_bounds__(256) clip_combine_kernel(const float* __restrict__ ws, const float* __restrict__ diag,
-                                                           float* __restrict__ stats, int rows, int n_split) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= 4 * rows) return;
-    float v = 0.f;
-    for (int s = 0; s < n_split; ++s) v += ws[(size_t)s * 4 * rows + i];
-    stats[i] = v;
-    if (i < rows) stats[(size_t)4 * rows + i] = diag[i];
+// stats[k][r] = sum over splits (fixed order -> deterministic), stats[4][r] = S_rr, and the row's loss terms in double
+// (KL_i is a small difference of O(1) terms: W/(T Zt) against log Zs - log Zt):
+//   rowloss[0][r] = CE_r = 1 + log A_r - S_rr       rowloss[1][r] = KL_r / T^2 = W_r/(T Zt_r) + log(Zs_r / Zt_r)
+__global__ void __launch_bounds__(128) clip_combine_kernel(const float* __restrict__ ws, const float* __restrict__ diag,
+                                                           float* __restrict__ stats, double* __restrict__ rowloss,
+                                                           int rows, int n_split, float temperature, int has_teacher) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    float v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        float acc = 0.f;
+        for (int s = 0; s < n_split; ++s) acc += ws[((size_t)s * 4 + k) * rows + r];
+        v[k] = acc;
+        stats[(size_t)k * rows + r] = acc;
+    }
+    const float dg = diag[r];
+    stats[(size_t)4 * rows + r] = dg;
+    rowloss[r] = 1.0 + log((double)v[0]) - (double)dg;
+    rowloss[(size_t)rows + r] = has_teacher ? (double)v[3] / ((double)temperature * (double)v[2]) + log((double)v[1] / (double)v[2]) : 0.0;
 }
 
+// Column ranges per row block: minimise (waves of 148 CTAs) x (tiles per CTA + fixed per-CTA cost)
 static int clip_fwd_splits(int64_t rows, int64_t cols) {
     const int64_t row_blocks = (rows + fwd::kBM - 1) / fwd::kBM;
     const int64_t col_tiles = (cols + fwd::kBN - 1) / fwd::kBN;
-    int64_t n = (2 * kNumSMs + row_blocks - 1) / row_blocks;     // aim for >= 2 CTAs per SM worth of work items
-    if (n > col_tiles) n = col_tiles;
-    if (n < 1) n = 1;
-    return (int)n;
+    int64_t best = 1;
+    double best_cost = 1e30;
+    for (int64_t n = 1; n <= 64 && n <= col_tiles; ++n) {
+        const int64_t waves = (row_blocks * n + kNumSMs - 1) / kNumSMs;
+        const int64_t tiles = (col_tiles + n - 1) / n;
+        const double cost = (double)waves * ((double)tiles + 1.0) + 0.01 * (double)n;
+        if (cost < best_cost) { best_cost = cost; best = n; }
+    }
+    return (int)best;
 }
 
 }  // namespace dcb
@@ -300,10 +317,10 @@ extern "C" int64_t dcb_clip_workspace_bytes(int64_t rows_local, int64_t cols) {
 extern "C" int dcb_clip_row_stats(const void* stu_a, const void* stu_b, const void* tea_a, const void* tea_b,
                                   const float* stu_a_inv, const float* stu_b_inv, const float* tea_a_inv,
                                   const float* tea_b_inv, int64_t rows_local, int64_t row_offset, int64_t cols,
-                                  int64_t dim, int dtype, float temperature, float* stats, void* workspace,
-                                  float* dump_s, float* dump_t, void* stream) {
+                                  int64_t dim, int dtype, float temperature, float* stats, double* rowloss,
+                                  void* workspace, float* dump_s, float* dump_t, void* stream) {
     using namespace dcb;
-    DCB_REQUIRE(stu_a && stu_b && stu_a_inv && stu_b_inv && stats && workspace, "NULL pointer argument");
+    DCB_REQUIRE(stu_a && stu_b && stu_a_inv && stu_b_inv && stats && rowloss && workspace, "NULL pointer argument");
     DCB_REQUIRE(dtype == DCB_BF16 || dtype == DCB_F16, "the fused contrastive kernel takes bf16 or fp16 embeddings");
     DCB_REQUIRE(rows_local >= 1 && cols >= 1 && dim >= 8 && dim % 8 == 0, "bad shape rows=%lld cols=%lld dim=%lld (dim %% 8 == 0)",
                 (long long)rows_local, (long long)cols, (long long)dim);
@@ -354,8 +371,8 @@ extern "C" int dcb_clip_row_stats(const void* stu_a, const void* stu_b, const vo
         clip_fwd_kernel<false><<<grid, fwd::kThreads, fwd::kSmemBytes, st>>>(ma_s, mb_s, ma_t, mb_t, p, idesc);
     }
     DCB_CUDA_OK(cudaGetLastError());
-    const int n = 4 * (int)rows_local;
-    clip_combine_kernel<<<(n + 255) / 256, 256, 0, st>>>(p.ws, p.diag, stats, (int)rows_local, p.n_split);
+    clip_combine_kernel<<<(unsigned)((rows_local + 127) / 128), 128, 0, st>>>(p.ws, p.diag, stats, rowloss, (int)rows_local,
+                                                                               p.n_split, temperature, teacher ? 1 : 0);
     DCB_CUDA_OK(cudaGetLastError());
     return 0;
 }

@@ -45,28 +45,22 @@ __global__ void __launch_bounds__(256) transpose_norm_f16_kernel(const T* __rest
 }
 
 // ---------------------------------------------------------------------------------------------
-// Loss values of both directions from the row statistics ([5][rows]: A, Zs, Zt, W, S_ii):
-//   CE row  = lse_i - S_ii = 1 + log A_i - S_ii                      (hard_label.py:12, shift 1)
-//   KL row  = T^2 [ W_i / (T Zt_i) - log Zt_i + log Zs_i ]           (soft_label.py:12-15, 'sum')
-// sums[0..3] (double) = {sum CE i2t, sum CE t2i, sum KL i2t, sum KL t2i} over this rank's rows;
+// Loss values of both directions from the per-row losses written by the forward kernel's combine step
+// (rowloss[0][i] = CE_i = 1 + log A_i - S_ii, rowloss[1][i] = KL_i / T^2 = W_i/(T Zt_i) + log(Zs_i/Zt_i), double):
+// sums[0..3] (double) = {sum CE i2t, sum CE t2i, T^2 sum KL i2t, T^2 sum KL t2i} over this rank's rows;
 // out[0] = 0.5 (sums0 + sums1) / global_batch, out[1] = 0.5 (sums2 + sums3)   (_loss.py:131,135-136)
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) clip_loss_kernel(const float* __restrict__ st_i2t, const float* __restrict__ st_t2i,
+__global__ void __launch_bounds__(1024) clip_loss_kernel(const double* __restrict__ rl_i2t, const double* __restrict__ rl_t2i,
                                                          int rows_i2t, int rows_t2i, float temperature, int has_teacher,
                                                          double inv_batch, double* __restrict__ sums, float* __restrict__ out) {
     __shared__ double res[4];
     for (int dir = 0; dir < 2; ++dir) {
-        const float* st = dir == 0 ? st_i2t : st_t2i;
+        const double* rl = dir == 0 ? rl_i2t : rl_t2i;
         const int rows = dir == 0 ? rows_i2t : rows_t2i;
         double ce = 0.0, kl = 0.0;
         for (int i = threadIdx.x; i < rows; i += blockDim.x) {
-            // double: KL_i is a small difference of O(1) terms (W/(T Zt) against log Zs - log Zt)
-            const double A = st[i], diag = st[(size_t)4 * rows + i];
-            ce += 1.0 + log(A) - diag;
-            if (has_teacher) {
-                const double Zs = st[(size_t)rows + i], Zt = st[(size_t)2 * rows + i], W = st[(size_t)3 * rows + i];
-                kl += W / ((double)temperature * Zt) + log(Zs / Zt);
-            }
+            ce += rl[i];
+            if (has_teacher) kl += rl[(size_t)rows + i];
         }
         ce = block_sum(ce);
         __syncthreads();
@@ -120,6 +114,8 @@ __device__ __forceinline__ float clip_grad_tile_scale(float gmax) {     // must 
 // grad_a[i,:] = r_i (acc_i - a_hat_i (a_hat_i . acc_i)),  acc_i = sum_splits acc_parts / 2^k - (gh/B) b_hat_{offset+i}
 // (Jacobian of x / ||x||, reference clip_model.py:37-38, plus the -delta_ij label term of cross entropy)
 // ---------------------------------------------------------------------------------------------
+constexpr int kFinishMaxPerLane = 24;     // rows up to 768 wide stay in registers (one pass over acc_parts)
+
 template <typename T, typename G>
 __global__ void __launch_bounds__(256) clip_grad_finish_kernel(const float* __restrict__ acc_parts, int n_split,
                                                                const T* __restrict__ a, const float* __restrict__ a_inv,
@@ -138,18 +134,44 @@ __global__ void __launch_bounds__(256) clip_grad_finish_kernel(const float* __re
     const float lab = has_label ? upstream[0] * inv_batch * b_inv[gi] : 0.f;
     const T* __restrict__ ap = a + row * dim;
     const T* __restrict__ bp = b + (has_label ? gi : 0) * dim;
+    G* __restrict__ gp = grad + row * dim;
+    const size_t split_stride = (size_t)rows * dim;
+    const float* __restrict__ accp = acc_parts + (size_t)row * dim;
+    if (dim <= 32 * kFinishMaxPerLane) {
+        float v[kFinishMaxPerLane], av[kFinishMaxPerLane];
+        float dot = 0.f;
+#pragma unroll
+        for (int k = 0; k < kFinishMaxPerLane; ++k) {
+            const int d = lane + 32 * k;
+            v[k] = 0.f;
+            av[k] = 0.f;
+            if (d < dim) {
+                float acc = 0.f;
+                for (int s = 0; s < n_split; ++s) acc += accp[(size_t)s * split_stride + d];
+                av[k] = Elem<T>::to_f(ap[d]) * r;
+                v[k] = acc * unscale - lab * Elem<T>::to_f(bp[d]);
+                dot = fmaf(av[k], v[k], dot);
+            }
+        }
+        dot = warp_sum(dot);
+#pragma unroll
+        for (int k = 0; k < kFinishMaxPerLane; ++k) {
+            const int d = lane + 32 * k;
+            if (d < dim) gp[d] = Elem<G>::from_f(r * (v[k] - av[k] * dot));
+        }
+        return;
+    }
     float dot = 0.f;
     for (int d = lane; d < dim; d += 32) {
         float v = 0.f;
-        for (int s = 0; s < n_split; ++s) v += acc_parts[((size_t)s * rows + row) * dim + d];
+        for (int s = 0; s < n_split; ++s) v += accp[(size_t)s * split_stride + d];
         v = v * unscale - lab * Elem<T>::to_f(bp[d]);
         dot = fmaf(Elem<T>::to_f(ap[d]) * r, v, dot);
     }
     dot = warp_sum(dot);
-    G* __restrict__ gp = grad + row * dim;
     for (int d = lane; d < dim; d += 32) {
         float v = 0.f;
-        for (int s = 0; s < n_split; ++s) v += acc_parts[((size_t)s * rows + row) * dim + d];
+        for (int s = 0; s < n_split; ++s) v += accp[(size_t)s * split_stride + d];
         v = v * unscale - lab * Elem<T>::to_f(bp[d]);
         gp[d] = Elem<G>::from_f(r * (v - Elem<T>::to_f(ap[d]) * r * dot));
     }
@@ -194,11 +216,11 @@ int dcb_transpose_norm_f16(const void* in, const float* inv_norm, void* out, int
     return 0;
 }
 
-int dcb_clip_losses(const float* stats_i2t, const float* stats_t2i, int64_t rows_i2t, int64_t rows_t2i,
+int dcb_clip_losses(const double* rowloss_i2t, const double* rowloss_t2i, int64_t rows_i2t, int64_t rows_t2i,
                     int64_t global_batch, float temperature, int has_teacher, double* sums, float* out, void* stream) {
     using namespace dcb;
-    DCB_REQUIRE(stats_i2t && stats_t2i && sums && out && global_batch >= 1, "bad arguments");
-    clip_loss_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(stats_i2t, stats_t2i, (int)rows_i2t, (int)rows_t2i,
+    DCB_REQUIRE(rowloss_i2t && rowloss_t2i && sums && out && global_batch >= 1, "bad arguments");
+    clip_loss_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(rowloss_i2t, rowloss_t2i, (int)rows_i2t, (int)rows_t2i,
                                                                         temperature, has_teacher, 1.0 / (double)global_batch,
                                                                         sums, out);
     DCB_CUDA_OK(cudaGetLastError());

@@ -181,8 +181,7 @@ def launch_tower(entries, scale: Sequence[float], percent: Sequence[float], grad
               _lib.i32_array(hs), _lib.i32_array(ht), _lib.i64_array(pos), _lib.i32_array(div), _lib.f32_array(gsc),
               n_terms, _lib.f32_array(scale), _lib.f32_array(percent), in_dt, gd, C.c_void_p(partials.data_ptr()),
               C.c_void_p(_ticket(dev).data_ptr()), C.c_void_p(res.data_ptr()), _stream_ptr())
-    launch_tower.last_buffers = (res, all_grads, partials)
-    return res, all_grads
+    return res, all_grads, partials
 
 
 def finalize(terms: Sequence[Tuple[torch.Tensor, int]], scale: Sequence[float], percent: Sequence[float]):
@@ -247,7 +246,9 @@ class StreamLossFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g):
-        grads = ctx.grads
+        # hand the gradient buffers over without keeping a reference: autograd's AccumulateGrad then adopts them
+        # as `.grad` instead of cloning (a clone would re-read and re-write every gradient byte)
+        grads, ctx.grads = ctx.grads, None
         if any(x is not None for x in grads):
             rescale([(grads, _as_upstream(g, next(x for x in grads if x is not None)), ctx.expected)])
         return (None, None, None, None, *grads, *([None] * ctx.n))
@@ -290,7 +291,7 @@ class TowerLossFn(torch.autograd.Function):
         n_seg = sum(len(e[2]) for e in entries)
         dtypes = {t.dtype for e in entries for t in e[2]}
         if len(spec) <= _lib.TOWER_MAX_TERMS and n_seg <= _lib.TOWER_MAX_SEG and len(dtypes) == 1:
-            out, all_grads = launch_tower(entries, scales, percents)          # ONE launch incl. the weighting
+            out, all_grads, _ = launch_tower(entries, scales, percents)       # ONE launch incl. the weighting
         else:
             terms = []
             for kind, divisor, stu, tea, need, pre in entries:
@@ -307,7 +308,10 @@ class TowerLossFn(torch.autograd.Function):
     def backward(ctx, g_total, *g_res):
         ret: List[Optional[torch.Tensor]] = [None] * ctx.n_in
         groups = []
-        for i, (grads, (pre, w), (off, n)) in enumerate(zip(ctx.all_grads, ctx.pres, ctx.layout)):
+        # drop ctx's references so AccumulateGrad can adopt the buffers as `.grad` (no clone, no extra HBM pass)
+        all_grads, ctx.all_grads = ctx.all_grads, None
+        grads = live = None
+        for i, (grads, (pre, w), (off, n)) in enumerate(zip(all_grads, ctx.pres, ctx.layout)):
             live = [x for x in grads if x is not None]
             if not live:
                 continue
@@ -322,4 +326,5 @@ class TowerLossFn(torch.autograd.Function):
             ret[off:off + n] = grads
         if groups:
             rescale(groups)
+        del groups, all_grads, grads, live
         return (None, None, *ret)

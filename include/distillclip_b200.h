@@ -128,20 +128,21 @@ int dcb_transpose_norm_f16(const void* in, const float* inv_norm, void* out, int
  *   stats[1][i] = sum_j exp((S_ij - 1)/T)             stats[2][i] = sum_j exp((T_ij - 1)/T)
  *   stats[3][i] = sum_j exp((T_ij - 1)/T) (T_ij - S_ij)      stats[4][i] = S_ii (global diagonal)
  * tea_* may all be NULL (hard label only; stats[1..3] are then 0).  stats: [5, rows_local] floats.
+ * rowloss: [2, rows_local] doubles = {CE_i = 1 + log stats0 - stats4,  KL_i / T^2 = stats3/(T stats2) + log(stats1/stats2)}.
  * workspace: dcb_clip_workspace_bytes(rows_local, cols) bytes of device scratch.
  * dump_s / dump_t: optional [rows_local, cols] fp32 buffers that receive the logits (tests only; NULL in production). */
 int64_t dcb_clip_workspace_bytes(int64_t rows_local, int64_t cols);
 int dcb_clip_row_stats(const void* stu_a, const void* stu_b, const void* tea_a, const void* tea_b,
                        const float* stu_a_inv, const float* stu_b_inv, const float* tea_a_inv, const float* tea_b_inv,
                        int64_t rows_local, int64_t row_offset, int64_t cols, int64_t dim, int dtype, float temperature,
-                       float* stats, void* workspace, float* dump_s, float* dump_t, void* stream);
+                       float* stats, double* rowloss, void* workspace, float* dump_s, float* dump_t, void* stream);
 
-/* Loss values of both directions from this rank's row statistics:
+/* Loss values of both directions from this rank's per-row losses (the `rowloss` outputs of dcb_clip_row_stats):
  *   sums[0..3] (double) = {sum_i CE_i (i2t), sum_i CE_i (t2i), T^2 sum_i KL_i (i2t), T^2 sum_i KL_i (t2i)}
  *   out[0] = 0.5 (sums[0] + sums[1]) / global_batch   (hard_label.py:12 'mean', _loss.py:131)
  *   out[1] = 0.5 (sums[2] + sums[3])                  (soft_label.py:8 'sum', _loss.py:135-136)
  * When sharded, all-reduce `sums` over ranks and rescale instead of using `out`. */
-int dcb_clip_losses(const float* stats_i2t, const float* stats_t2i, int64_t rows_i2t, int64_t rows_t2i,
+int dcb_clip_losses(const double* rowloss_i2t, const double* rowloss_t2i, int64_t rows_i2t, int64_t rows_t2i,
                     int64_t global_batch, float temperature, int has_teacher, double* sums, float* out, void* stream);
 
 /* coef[0][i] = gh/(2 B A_i), coef[1][i] = gs T/(2 Zs_i), coef[2][i] = gs T/(2 Zt_i) from stats [5, rows];

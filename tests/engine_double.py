@@ -27,14 +27,18 @@ class DoubleEngine:
             st[1] = torch.exp((S - 1) / temperature).sum(1)
             st[2] = et.sum(1)
             st[3] = (et * (T - S)).sum(1)
-        return st
+        rl = torch.zeros(2, rows, dtype=torch.float64)
+        rl[0] = 1 + torch.log(st[0]) - st[4]
+        if a_t is not None:
+            rl[1] = st[3] / (temperature * st[2]) + torch.log(st[1] / st[2])
+        return st, rl
 
-    def losses(self, stats_i2t, stats_t2i, global_batch, temperature, has_teacher):
+    def losses(self, rl_i2t, rl_t2i, global_batch, temperature, has_teacher):
         sums = torch.zeros(4, dtype=torch.float64)
-        for d, st in enumerate((stats_i2t, stats_t2i)):
-            sums[d] = (1 + torch.log(st[0]) - st[4]).sum()
+        for d, rl in enumerate((rl_i2t, rl_t2i)):
+            sums[d] = rl[0].sum()
             if has_teacher:
-                sums[2 + d] = temperature ** 2 * (st[3] / (temperature * st[2]) - torch.log(st[2]) + torch.log(st[1])).sum()
+                sums[2 + d] = temperature ** 2 * rl[1].sum()
         out = torch.stack([0.5 * (sums[0] + sums[1]) / global_batch, 0.5 * (sums[2] + sums[3])])
         return sums, out
 

@@ -39,7 +39,7 @@ def test_similarity_tiles_match_matmul(cuda_device, b, d):
     eng = CudaEngine()
     inv = eng.inv_norms([si, st, ti, tt])
     dump = (torch.zeros(b, b, device="cuda"), torch.zeros(b, b, device="cuda"))
-    stats = eng.row_stats(si, st, ti, tt, inv[0], inv[1], inv[2], inv[3], 0, 2.0, dump=dump)
+    stats, _ = eng.row_stats(si, st, ti, tt, inv[0], inv[1], inv[2], inv[3], 0, 2.0, dump=dump)
     torch.cuda.synchronize()
     s_ref, _ = cf.clip_logits(si.float().cpu().numpy(), st.float().cpu().numpy())
     t_ref, _ = cf.clip_logits(ti.float().cpu().numpy(), tt.float().cpu().numpy())
@@ -144,10 +144,10 @@ def test_row_sharded_virtual_ranks(cuda_device, bwd_kernel):
     stats_i, stats_t = [], []
     for r in range(R):
         loc = slice(r * bl, (r + 1) * bl)
-        s1 = eng.row_stats(si[loc], st, ti[loc], tt, inv[0][loc], inv[1], inv[2][loc], inv[3], r * bl, T)
-        s2 = eng.row_stats(st[loc], si, tt[loc], ti, inv[1][loc], inv[0], inv[3][loc], inv[2], r * bl, T)
+        s1, l1 = eng.row_stats(si[loc], st, ti[loc], tt, inv[0][loc], inv[1], inv[2][loc], inv[3], r * bl, T)
+        s2, l2 = eng.row_stats(st[loc], si, tt[loc], ti, inv[1][loc], inv[0], inv[3][loc], inv[2], r * bl, T)
         assert np.abs(s1[4].cpu().numpy() - np.diag(s_ref)[loc]).max() <= 2e-6       # global labels, exact position
-        sums += eng.losses(s1, s2, b, T, True)[0]
+        sums += eng.losses(l1, l2, b, T, True)[0]
         stats_i.append(s1)
         stats_t.append(s2)
     assert float(0.5 * (sums[0] + sums[1]) / b) == pytest.approx(ref["hard"], rel=LOSS_RTOL)
