@@ -4,9 +4,9 @@
 // a cluster of two CTAs on one TPC owns a block of 128 a-side rows, 64 per CTA, and the WHOLE embedding dimension.
 // With tcgen05.mma.cta_group::2 and M = 128 each CTA keeps 64 accumulator rows spread over all 128 TMEM lanes
 // (lanes 0-63 hold the first half of the N columns, lanes 64-127 the second half), so an accumulator of N columns
-// costs N/2 TMEM columns: the [64 x D] gradient accumulator of each CTA fits next to double-buffered S/T tiles for
-// D <= 768 (D/2 + 2 x NT <= 512 columns), and the logits are recomputed exactly once per direction instead of once
-// per 256-column chunk of D.  Each CTA stages its own half of every operand: 64 rows of a, NT/2 rows of b, and 128 of
+// costs N/2 TMEM columns: the [64 x D] gradient accumulator of each CTA (D/2 columns) fits next to the 128-wide S/T
+// tiles -- double buffered for D <= 512 (2 x 128 + 256), single buffered for D <= 768 (128 + 384) -- and the logits
+// are recomputed exactly once per direction instead of once per 256-column chunk of D.  Each CTA stages its own half of every operand: 64 rows of a, NT/2 rows of b, and 128 of
 // the 256 rows of each b_hatT slice; the leader CTA (cluster rank 0) issues all MMAs; completion is multicast to the
 // barriers of both CTAs; both CTAs run the epilogue on their own 64 rows.
 //
@@ -23,15 +23,17 @@ constexpr int kTmemCols = 512;
 constexpr int kATile = kRowsPerCta * kBK * 2;             // 8 KiB  [64 x 64] 16-bit
 constexpr int kSliceRows = 128;                           // rows of one 256-row b_hatT slice held by one CTA
 constexpr int kMaxSlices = 3;                             // D <= 768
-template <int NT> struct Cfg {
+// NT = logit-tile width (columns per tile), ST = number of S/T accumulator stages in TMEM (2 = double buffered).
+// TMEM columns: ST * NT for S/T + D/2 for the gradient accumulator <= 512:  D <= 512 -> (128, 2), D <= 768 -> (128, 1).
+template <int NT, int ST> struct Cfg {
     static constexpr int kBHalf = NT / 2;                                 // b rows staged per CTA
     static constexpr int kBTile = kBHalf * kBK * 2;                       // bytes
     static constexpr int kStageBytes = 2 * kATile + 2 * kBTile;           // a_stu, a_tea, b_stu, b_tea
-    static constexpr int kStages = NT == 128 ? 3 : 4;
+    static constexpr int kStages = 3;
     static constexpr int kGBytes = kRowsPerCta * NT * 2;                  // fp16 G tile of this CTA
     static constexpr int kBtSliceBytes = kSliceRows * NT * 2;             // one slice, all K sub-tiles
     static constexpr int kStCols = NT;                                    // TMEM columns of one S/T stage (S NT/2 + T NT/2)
-    static constexpr int kAccCol = 2 * kStCols;
+    static constexpr int kAccCol = ST * kStCols;
     static constexpr int smem_bytes(int slices) {
         return 1024 + kStages * kStageBytes + kGBytes + slices * kBtSliceBytes + 2 * 5 * NT * 4 + 256;
     }
@@ -67,7 +69,7 @@ __device__ __forceinline__ float ex2p(float x) {
     return y;
 }
 
-template <bool kTeacher, int NT>
+template <bool kTeacher, int NT, int ST>
 __global__ void __launch_bounds__(bwdp::kThreads, 1)
 clip_bwd_pair_kernel(const __grid_constant__ CUtensorMap map_a_stu, const __grid_constant__ CUtensorMap map_b_stu,
                      const __grid_constant__ CUtensorMap map_a_tea, const __grid_constant__ CUtensorMap map_b_tea,
@@ -75,7 +77,7 @@ clip_bwd_pair_kernel(const __grid_constant__ CUtensorMap map_a_stu, const __grid
                      const uint32_t idesc_st, const uint32_t idesc_grad) {
     using namespace bwdp;
     using namespace tc;
-    using C = Cfg<NT>;
+    using C = Cfg<NT, ST>;
     constexpr int kSub = NT / kBK;                       // K sub-tiles of the gradient GEMM (K = NT)
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -178,8 +180,8 @@ clip_bwd_pair_kernel(const __grid_constant__ CUtensorMap map_a_stu, const __grid
             int stage = 0;
             uint32_t phase = 0;
             auto issue_st = [&](int t) {
-                const int as = t & 1;
-                mbar_wait(bar_stempty + 8 * as, ((t >> 1) & 1) ^ 1);
+                const int as = t % ST;
+                mbar_wait(bar_stempty + 8 * as, ((t / ST) & 1) ^ 1);
                 tc_fence_after_sync();
                 const uint32_t acc_s = tmem_base + as * C::kStCols, acc_t = acc_s + NT / 2;
                 for (int kc = 0; kc < n_kc; ++kc) {
@@ -200,9 +202,12 @@ clip_bwd_pair_kernel(const __grid_constant__ CUtensorMap map_a_stu, const __grid
                 }
                 umma_commit_pair(bar_stfull + 8 * as, 3);
             };
-            issue_st(0);
-            for (int t = 0; t < n_tiles; ++t) {
-                if (t + 1 < n_tiles) issue_st(t + 1);
+            // order on the (in-order) MMA pipe: S/T(t), grad(t-1), S/T(t+1), ...  -- the gradient GEMM of tile t-1 runs
+            // while the epilogue warps work on tile t; with ST == 2 the S/T GEMM of tile t+1 overlaps them as well
+            for (int tt = 0; tt <= n_tiles; ++tt) {
+                if (tt < n_tiles) issue_st(tt);
+                if (tt == 0) continue;
+                const int t = tt - 1;
                 mbar_wait(bar_gfull, t & 1);
                 mbar_wait(bar_btfull, t & 1);
                 tc_fence_after_sync();
@@ -240,9 +245,9 @@ clip_bwd_pair_kernel(const __grid_constant__ CUtensorMap map_a_stu, const __grid
         const float rg = (kTeacher && row_ok) ? __ldg(p.coef_row + 2 * (size_t)p.rows + grow) : 0.f;
         const float gscale = pair_tile_scale(__ldg(p.gmax_row) + __ldg(p.gmax_col));
         for (int t = 0; t < n_tiles; ++t) {
-            const int as = t & 1;
+            const int as = t % ST;
             const int col0 = (tile_begin + t) * NT;
-            float* sc = scale_buf + as * 5 * NT;           // [c_stu][c_tea][alpha'][beta'][gamma'] x NT
+            float* sc = scale_buf + (t & 1) * 5 * NT;      // [c_stu][c_tea][alpha'][beta'][gamma'] x NT
             for (int c = ep_tid; c < NT; c += 128) {
                 const int gc = col0 + c;
                 const bool ok = gc < p.cols;
@@ -255,7 +260,7 @@ clip_bwd_pair_kernel(const __grid_constant__ CUtensorMap map_a_stu, const __grid
                 }
             }
             asm volatile("bar.sync 1, 128;" ::: "memory");
-            mbar_wait(bar_stfull + 8 * as, (t >> 1) & 1);
+            mbar_wait(bar_stfull + 8 * as, (t / ST) & 1);
             tc_fence_after_sync();
             const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * C::kStCols;
             uint32_t packed[kColsPerThread / 2];
@@ -339,7 +344,7 @@ clip_bwd_pair_kernel(const __grid_constant__ CUtensorMap map_a_stu, const __grid
     }
 }
 
-static int clip_bwd_pair_nt(int64_t dim) { return dim <= 512 ? 128 : 64; }
+static int clip_bwd_pair_nt(int64_t) { return 128; }
 
 static int clip_bwd_pair_splits(int64_t rows, int64_t cols, int64_t dim) {
     const int64_t row_blocks = (rows + 127) / 128;
@@ -356,13 +361,13 @@ static int clip_bwd_pair_splits(int64_t rows, int64_t cols, int64_t dim) {
     return (int)best;
 }
 
-template <bool kTeacher, int NT>
+template <bool kTeacher, int NT, int ST>
 static int launch_pair(dim3 grid, int smem, cudaStream_t st, const CUtensorMap& ma_s, const CUtensorMap& mb_s,
                        const CUtensorMap& ma_t, const CUtensorMap& mb_t, const CUtensorMap& mbt,
                        const ClipBwdPairParams& p, uint32_t idesc_st, uint32_t idesc_grad) {
     static int max_set = 0;
     if (smem > max_set) {
-        DCB_CUDA_OK(cudaFuncSetAttribute(clip_bwd_pair_kernel<kTeacher, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        DCB_CUDA_OK(cudaFuncSetAttribute(clip_bwd_pair_kernel<kTeacher, NT, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         max_set = smem;
     }
     cudaLaunchConfig_t cfg{};
@@ -377,7 +382,7 @@ static int launch_pair(dim3 grid, int smem, cudaStream_t st, const CUtensorMap& 
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    DCB_CUDA_OK(cudaLaunchKernelEx(&cfg, clip_bwd_pair_kernel<kTeacher, NT>, ma_s, mb_s, ma_t, mb_t, mbt, p, idesc_st, idesc_grad));
+    DCB_CUDA_OK(cudaLaunchKernelEx(&cfg, clip_bwd_pair_kernel<kTeacher, NT, ST>, ma_s, mb_s, ma_t, mb_t, mbt, p, idesc_st, idesc_grad));
     return 0;
 }
 
@@ -440,12 +445,12 @@ extern "C" int dcb_clip_row_grads_pair(const void* stu_a, const void* stu_b, con
     const uint32_t idesc_grad = tc::umma_idesc_f16(128, 256, 0);          // fp16 G x fp16 b_hatT, 256-row slices
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     dim3 grid((unsigned)(2 * row_blocks * p.n_split));
-    if (nt == 128) {
-        const int smem = bwdp::Cfg<128>::smem_bytes(p.slices);
-        return teacher ? launch_pair<true, 128>(grid, smem, st, ma_s, mb_s, ma_t, mb_t, mbt, p, idesc_st, idesc_grad)
-                       : launch_pair<false, 128>(grid, smem, st, ma_s, mb_s, ma_t, mb_t, mbt, p, idesc_st, idesc_grad);
+    if (dim <= 512) {       // S/T double buffered: 2 x 128 + D/2 <= 512 TMEM columns
+        const int smem = bwdp::Cfg<128, 2>::smem_bytes(p.slices);
+        return teacher ? launch_pair<true, 128, 2>(grid, smem, st, ma_s, mb_s, ma_t, mb_t, mbt, p, idesc_st, idesc_grad)
+                       : launch_pair<false, 128, 2>(grid, smem, st, ma_s, mb_s, ma_t, mb_t, mbt, p, idesc_st, idesc_grad);
     }
-    const int smem = bwdp::Cfg<64>::smem_bytes(p.slices);
-    return teacher ? launch_pair<true, 64>(grid, smem, st, ma_s, mb_s, ma_t, mb_t, mbt, p, idesc_st, idesc_grad)
-                   : launch_pair<false, 64>(grid, smem, st, ma_s, mb_s, ma_t, mb_t, mbt, p, idesc_st, idesc_grad);
+    const int smem = bwdp::Cfg<128, 1>::smem_bytes(p.slices);   // D <= 768: 128 + 384 TMEM columns, S/T single buffered
+    return teacher ? launch_pair<true, 128, 1>(grid, smem, st, ma_s, mb_s, ma_t, mb_t, mbt, p, idesc_st, idesc_grad)
+                   : launch_pair<false, 128, 1>(grid, smem, st, ma_s, mb_s, ma_t, mb_t, mbt, p, idesc_st, idesc_grad);
 }

@@ -141,15 +141,22 @@ __global__ void __launch_bounds__(256) clip_grad_finish_kernel(const float* __re
         float v[kFinishMaxPerLane], av[kFinishMaxPerLane];
         float dot = 0.f;
 #pragma unroll
+        for (int k = 0; k < kFinishMaxPerLane; ++k) v[k] = 0.f;
+        for (int s = 0; s < n_split; ++s) {               // all loads of one split in flight together
+            const float* __restrict__ src = accp + (size_t)s * split_stride;
+#pragma unroll
+            for (int k = 0; k < kFinishMaxPerLane; ++k) {
+                const int d = lane + 32 * k;
+                if (d < dim) v[k] += src[d];
+            }
+        }
+#pragma unroll
         for (int k = 0; k < kFinishMaxPerLane; ++k) {
             const int d = lane + 32 * k;
-            v[k] = 0.f;
             av[k] = 0.f;
             if (d < dim) {
-                float acc = 0.f;
-                for (int s = 0; s < n_split; ++s) acc += accp[(size_t)s * split_stride + d];
                 av[k] = Elem<T>::to_f(ap[d]) * r;
-                v[k] = acc * unscale - lab * Elem<T>::to_f(bp[d]);
+                v[k] = v[k] * unscale - lab * Elem<T>::to_f(bp[d]);
                 dot = fmaf(av[k], v[k], dot);
             }
         }
