@@ -10,15 +10,17 @@
 // the 256 rows of each b_hatT slice; the leader CTA (cluster rank 0) issues all MMAs; completion is multicast to the
 // barriers of both CTAs; both CTAs run the epilogue on their own 64 rows.
 //
-// Warp roles per CTA (256 threads): warp 0 = operand-ring producer, warp 1 = TMEM alloc (+ MMA issuer in the leader),
-// warp 2 = b_hatT producer, warp 3 idle, warps 4-7 = epilogue (warp w reads TMEM lanes 32 (w-4) ..).
+// Warp roles per CTA (384 threads): warp 0 = operand-ring producer, warp 1 = TMEM alloc (+ MMA issuer in the leader),
+// warp 2 = b_hatT producer, warp 3 idle, warps 4-11 = epilogue: warp w reads TMEM lanes 32 (w % 4) .. and the
+// (w - 4) / 4-th 32-column chunk of its rows, so every scheduler has two epilogue warps to hide MUFU / FMA latency
+// (one warp per scheduler issued only every ~4 cycles, ncu r01d).
 #include "tc_common.cuh"
 
 namespace dcb {
 
 namespace bwdp {
 constexpr int kRowsPerCta = 64, kBK = 64, kUmmaK = 16;
-constexpr int kThreads = 256;
+constexpr int kThreads = 384;                              // 4 control warps + 8 epilogue warps (2 per scheduler)
 constexpr int kTmemCols = 512;
 constexpr int kATile = kRowsPerCta * kBK * 2;             // 8 KiB  [64 x 64] 16-bit
 constexpr int kSliceRows = 128;                           // rows of one 256-row b_hatT slice held by one CTA
@@ -117,9 +119,9 @@ clip_bwd_pair_kernel(const __grid_constant__ CUtensorMap map_a_stu, const __grid
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(bar_stfull + 8 * s, 1);
-            mbar_init(bar_stempty + 8 * s, 8);
+            mbar_init(bar_stempty + 8 * s, 16);
         }
-        mbar_init(bar_gfull, 8);
+        mbar_init(bar_gfull, 16);
         mbar_init(bar_gempty, 1);
         mbar_init(bar_btfull, 1);
         mbar_init(bar_accfull, 1);
@@ -228,11 +230,14 @@ clip_bwd_pair_kernel(const __grid_constant__ CUtensorMap map_a_stu, const __grid
         }
     } else if (warp >= 4) {
         // ---------------------------------------------------------------- epilogue (both CTAs, own 64 rows)
-        const int q = warp & 3;                        // TMEM lane quadrant
+        static_assert(NT == 128, "epilogue mapping below assumes 128-wide tiles: 64 columns per lane, 32 per warp");
+        const int ew = warp - 4;                       // 0..7
+        const int q = ew & 3;                          // TMEM lane quadrant (== warp % 4)
+        const int sub = ew >> 2;                       // which 32-column chunk of this lane's 64 columns
         const int r = (q & 1) * 32 + lane;             // row inside this CTA's 64
-        const int half = q >> 1;                       // lanes 0-63: columns [0, N/2), lanes 64-127: columns [N/2, N)
-        constexpr int kColsPerThread = NT / 2;
-        const int ep_tid = (warp - 4) * 32 + lane;     // 0..127
+        const int half = q >> 1;                       // lanes 0-63: columns [0, 64), lanes 64-127: columns [64, 128)
+        const int cbase = half * 64 + sub * 32;        // first tile column of this thread
+        const int ep_tid = ew * 32 + lane;             // 0..255
         const int grow = row0 + r;
         const bool row_ok = grow < p.rows;
         const float LOG2E = 1.4426950408889634f;
@@ -248,72 +253,79 @@ clip_bwd_pair_kernel(const __grid_constant__ CUtensorMap map_a_stu, const __grid
             const int as = t % ST;
             const int col0 = (tile_begin + t) * NT;
             float* sc = scale_buf + (t & 1) * 5 * NT;      // [c_stu][c_tea][alpha'][beta'][gamma'] x NT
-            for (int c = ep_tid; c < NT; c += 128) {
+            if (ep_tid < NT) {
+                const int gc = col0 + ep_tid;
+                const bool ok = gc < p.cols;
+                sc[ep_tid] = ok ? __ldg(p.b_inv_stu + gc) : 0.f;
+                sc[2 * NT + ep_tid] = ok ? __ldg(p.coef_col + gc) : 0.f;
+            } else if (kTeacher) {
+                const int c = ep_tid - NT;
                 const int gc = col0 + c;
                 const bool ok = gc < p.cols;
-                sc[c] = ok ? __ldg(p.b_inv_stu + gc) : 0.f;
-                sc[2 * NT + c] = ok ? __ldg(p.coef_col + gc) : 0.f;
-                if (kTeacher) {
-                    sc[NT + c] = ok ? __ldg(p.b_inv_tea + gc) : 0.f;
-                    sc[3 * NT + c] = ok ? __ldg(p.coef_col + p.cols + gc) : 0.f;
-                    sc[4 * NT + c] = ok ? __ldg(p.coef_col + 2 * (size_t)p.cols + gc) : 0.f;
-                }
+                sc[NT + c] = ok ? __ldg(p.b_inv_tea + gc) : 0.f;
+                sc[3 * NT + c] = ok ? __ldg(p.coef_col + p.cols + gc) : 0.f;
+                sc[4 * NT + c] = ok ? __ldg(p.coef_col + 2 * (size_t)p.cols + gc) : 0.f;
             }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            asm volatile("bar.sync 1, 256;" ::: "memory");
             mbar_wait(bar_stfull + 8 * as, (t / ST) & 1);
             tc_fence_after_sync();
-            const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * C::kStCols;
-            uint32_t packed[kColsPerThread / 2];
-#pragma unroll
-            for (int ch = 0; ch < kColsPerThread / 32; ++ch) {
-                float sv[32], tv[32];
-                tmem_ld_32x32(lane_addr + ch * 32, sv);
-                if (kTeacher) tmem_ld_32x32(lane_addr + NT / 2 + ch * 32, tv);
-                tmem_ld_wait();
-#pragma unroll
-                for (int c = 0; c < 32; c += 2) {
-                    float g2[2];
-#pragma unroll
-                    for (int e = 0; e < 2; ++e) {
-                        const int cc = half * kColsPerThread + ch * 32 + c + e;      // column inside the tile
-                        const float u = sv[c + e] * sc[cc];
-                        if (p.dump_s && row_ok && col0 + cc < p.cols) p.dump_s[(size_t)grow * p.cols + col0 + cc] = u * r_s;
-                        float g = ex2p(fmaf(u, k1, n1)) * (ra + sc[2 * NT + cc]);
-                        if (kTeacher) {
-                            const float v = tv[c + e] * sc[NT + cc];
-                            g = fmaf(ex2p(fmaf(u, k1t, n1t)), rbeta + sc[3 * NT + cc], g);
-                            g = fmaf(-ex2p(fmaf(v, k2t, n1t)), rg + sc[4 * NT + cc], g);
-                        }
-                        g2[e] = g * gscale;
-                    }
-                    packed[(ch * 32 + c) >> 1] = pack2<__half>(g2[0], g2[1]);
-                }
-            }
+            const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * C::kStCols + sub * 32;
+            uint32_t packed[16];
+            float sv[32], tv[32];
+            tmem_ld_32x32(lane_addr, sv);
+            if (kTeacher) tmem_ld_32x32(lane_addr + NT / 2, tv);
+            tmem_ld_wait();
+            // S/T columns of this warp are in registers: release the accumulator stage as early as possible
             tc_fence_before_sync();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(l_stempty + 8 * as);
-            mbar_wait(bar_gempty, (t & 1) ^ 1);
-            // this thread's columns [half*NT/2, half*NT/2 + NT/2) of row r -> K-major SW128 sub-tiles of 64 columns
+            if (p.dump_s) {                                     // tests only; kept out of the hot loop
+                for (int c = 0; c < 32; ++c)
+                    if (row_ok && col0 + cbase + c < p.cols)
+                        p.dump_s[(size_t)grow * p.cols + col0 + cbase + c] = sv[c] * sc[cbase + c] * r_s;
+            }
+            const float* s_cs = sc + cbase;
+            const float* s_ct = sc + NT + cbase;
+            const float* s_a = sc + 2 * NT + cbase;
+            const float* s_b = sc + 3 * NT + cbase;
+            const float* s_g = sc + 4 * NT + cbase;
 #pragma unroll
-            for (int c8 = 0; c8 < kColsPerThread / 8; ++c8) {
-                const int col = half * kColsPerThread + c8 * 8;
-                const int ks = col >> 6, chunk = (col & 63) >> 3;
+            for (int c = 0; c < 32; c += 2) {
+                float g2[2];
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const float u = sv[c + e] * s_cs[c + e];
+                    float g = ex2p(fmaf(u, k1, n1)) * (ra + s_a[c + e]);
+                    if (kTeacher) {
+                        const float v = tv[c + e] * s_ct[c + e];
+                        g = fmaf(ex2p(fmaf(u, k1t, n1t)), rbeta + s_b[c + e], g);
+                        g = fmaf(-ex2p(fmaf(v, k2t, n1t)), rg + s_g[c + e], g);
+                    }
+                    g2[e] = g * gscale;
+                }
+                packed[c >> 1] = pack2<__half>(g2[0], g2[1]);
+            }
+            mbar_wait(bar_gempty, (t & 1) ^ 1);
+            // columns [cbase, cbase + 32) of row r -> K-major SW128 sub-tile `half`, 16-byte chunks sub*4 .. sub*4+3
+#pragma unroll
+            for (int c8 = 0; c8 < 4; ++c8) {
                 uint4 w = make_uint4(packed[4 * c8], packed[4 * c8 + 1], packed[4 * c8 + 2], packed[4 * c8 + 3]);
-                *reinterpret_cast<uint4*>(g_gen + ks * (kRowsPerCta * kBK * 2) + sw128_chunk_offset(r, chunk)) = w;
+                *reinterpret_cast<uint4*>(g_gen + half * (kRowsPerCta * kBK * 2) + sw128_chunk_offset(r, sub * 4 + c8)) = w;
             }
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(l_gfull);
         }
         // gradient accumulator -> global partial buffer.  Slice sl: lanes 0-63 hold d in [256 sl, 256 sl + 128),
-        // lanes 64-127 hold d in [256 sl + 128, 256 sl + 256); 128 TMEM columns per slice.
+        // lanes 64-127 hold d in [256 sl + 128, 256 sl + 256); 128 TMEM columns per slice, split between the two warps
+        // of a quadrant.
         mbar_wait(bar_accfull, 0);
         tc_fence_after_sync();
         const uint32_t acc_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + C::kAccCol;
         float* out = p.acc + ((size_t)sp * p.rows + (row_ok ? grow : 0)) * p.dim;
         for (int sl = 0; sl < p.slices; ++sl) {
 #pragma unroll 1
-            for (int ch = 0; ch < 4; ++ch) {
+            for (int ch = 2 * sub; ch < 2 * sub + 2; ++ch) {
                 const int d0 = sl * 256 + half * 128 + ch * 32;
                 if (d0 >= p.dim) break;                                  // warp-uniform
                 float v[32];

@@ -16,7 +16,10 @@
 // Cosine logits are bounded by 1, so 1 is a valid softmax shift for every row: the sums of different column
 // ranges simply add (no running max, no rescaling), which is what lets a row be split over CTAs and ranks.
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2-5 = epilogue.
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2-9 = epilogue.
+// Epilogue warp w reads TMEM lanes 32 (w % 4) .. and the columns [64 sub, 64 sub + 64) of the tile, sub = (w - 2) / 4:
+// two warps per scheduler hide the MUFU / FMA latency (a single warp per scheduler issued every ~3 cycles, ncu r01d).
+// The two column halves of a row are accumulated separately and added by the combine kernel.
 #include "tc_common.cuh"
 
 namespace dcb {
@@ -26,7 +29,7 @@ constexpr int kBM = 128, kBN = 128, kBK = 64, kUmmaK = 16;
 constexpr int kStages = 3;
 constexpr int kTileBytes = kBM * kBK * 2;                 // 16 KiB: one [128 x 64] 16-bit operand tile
 constexpr int kStageBytes = 4 * kTileBytes;               // a_stu, b_stu, a_tea, b_tea
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;                            // 2 control warps + 8 epilogue warps (2 per scheduler)
 constexpr int kTmemCols = 512;
 constexpr int kSmemBytes = 1024 /*align slack*/ + kStages * kStageBytes + 2 * 2 * kBN * 4 + 256;
 }  // namespace fwd
@@ -36,7 +39,7 @@ struct ClipFwdParams {
     const float* b_inv_stu;   // [cols]
     const float* a_inv_tea;
     const float* b_inv_tea;
-    float* ws;                // [n_split][4][rows] partial sums
+    float* ws;                // [2 * n_split][4][rows] partial sums (x2: the two epilogue warps of a row)
     float* diag;              // [rows] S_ii
     float* dump_s;            // optional [rows, cols] raw logits (tests only), else nullptr
     float* dump_t;
@@ -86,7 +89,7 @@ clip_fwd_kernel(const __grid_constant__ CUtensorMap map_a_stu, const __grid_cons
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(bar_tfull + 8 * s, 1);
-            mbar_init(bar_tempty + 8 * s, 4);     // one arrive per epilogue warp
+            mbar_init(bar_tempty + 8 * s, 8);     // one arrive per epilogue warp
         }
         fence_barrier_init();
     }
@@ -157,8 +160,9 @@ clip_fwd_kernel(const __grid_constant__ CUtensorMap map_a_stu, const __grid_cons
     } else {
         // ---------------------------------------------------------------- epilogue: 4 warps, one row per thread
         const int q = warp & 3;                             // TMEM lane quadrant this warp may read
+        const int sub = (warp - 2) >> 2;                    // column half of the tile handled by this warp
         const int r = q * 32 + lane;                        // row inside the block
-        const int ep_tid = r;                               // 0..127, also used to stage column scales
+        const int ep_tid = (warp - 2) * 32 + lane;          // 0..255, used to stage column scales
         const int grow = row0 + r;                          // local row
         const bool row_ok = grow < p.rows;
         const float LOG2E = 1.4426950408889634f;
@@ -184,23 +188,30 @@ clip_fwd_kernel(const __grid_constant__ CUtensorMap map_a_stu, const __grid_cons
             const uint32_t aphase = (t >> 1) & 1;
             const int col0 = (tile_begin + t) * kBN;
             float* sc = scale_buf + as * 2 * kBN;           // [stu 128][tea 128]
-            {
+            if (ep_tid < kBN) {
                 const int c = col0 + ep_tid;
                 sc[ep_tid] = c < p.cols ? __ldg(p.b_inv_stu + c) : 0.f;
-                if (kTeacher) sc[kBN + ep_tid] = c < p.cols ? __ldg(p.b_inv_tea + c) : 0.f;
+            } else if (kTeacher) {
+                const int c = col0 + ep_tid - kBN;
+                sc[ep_tid] = c < p.cols ? __ldg(p.b_inv_tea + c) : 0.f;
             }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            asm volatile("bar.sync 1, 256;" ::: "memory");
             mbar_wait(bar_tfull + 8 * as, aphase);
             tc_fence_after_sync();
             const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * 256;
             const bool edge = (col0 + kBN > p.cols) || (diag_col >= col0 && diag_col < col0 + kBN) ||
                               (p.dump_s != nullptr);
 #pragma unroll 1
-            for (int ch = 0; ch < kBN / 32; ++ch) {
+            for (int ch = 2 * sub; ch < 2 * sub + 2; ++ch) {
                 float sv[32], tv[32];
                 tmem_ld_32x32(lane_addr + ch * 32, sv);
                 if (kTeacher) tmem_ld_32x32(lane_addr + 128 + ch * 32, tv);
                 tmem_ld_wait();
+                if (ch == 2 * sub + 1) {                    // last TMEM read of this tile: release the accumulator stage
+                    tc_fence_before_sync();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_tempty + 8 * as);
+                }
                 const float* scs = sc + ch * 32;
                 const float* sct = sc + kBN + ch * 32;
                 float a0 = 0.f, a1 = 0.f, zs0 = 0.f, zs1 = 0.f, zt0 = 0.f, zt1 = 0.f, w0 = 0.f, w1 = 0.f;
@@ -249,12 +260,9 @@ clip_fwd_kernel(const __grid_constant__ CUtensorMap map_a_stu, const __grid_cons
                     kahan(W, cW, w0 + w1);
                 }
             }
-            tc_fence_before_sync();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_tempty + 8 * as);
         }
         if (row_ok) {
-            float* w = p.ws + (size_t)sp * 4 * p.rows + grow;
+            float* w = p.ws + (size_t)(sp * 2 + sub) * 4 * p.rows + grow;
             w[0] = A;
             w[(size_t)p.rows] = Zs;
             w[(size_t)2 * p.rows] = Zt;
@@ -311,7 +319,7 @@ static int clip_fwd_splits(int64_t rows, int64_t cols) {
 
 extern "C" int64_t dcb_clip_workspace_bytes(int64_t rows_local, int64_t cols) {
     if (rows_local < 1 || cols < 1) return 0;
-    return ((int64_t)dcb::clip_fwd_splits(rows_local, cols) * 4 + 1) * rows_local * (int64_t)sizeof(float);
+    return ((int64_t)dcb::clip_fwd_splits(rows_local, cols) * 2 * 4 + 1) * rows_local * (int64_t)sizeof(float);
 }
 
 extern "C" int dcb_clip_row_stats(const void* stu_a, const void* stu_b, const void* tea_a, const void* tea_b,
@@ -353,7 +361,7 @@ extern "C" int dcb_clip_row_stats(const void* stu_a, const void* stu_b, const vo
     p.n_split = clip_fwd_splits(rows_local, cols);
     p.col_tiles = (int)((cols + fwd::kBN - 1) / fwd::kBN);
     p.ws = static_cast<float*>(workspace);
-    p.diag = p.ws + (size_t)p.n_split * 4 * rows_local;
+    p.diag = p.ws + (size_t)p.n_split * 2 * 4 * rows_local;
     p.dump_s = dump_s;
     p.dump_t = dump_t;
     p.inv_temp = teacher ? 1.0f / temperature : 1.0f;
@@ -372,7 +380,7 @@ extern "C" int dcb_clip_row_stats(const void* stu_a, const void* stu_b, const vo
     }
     DCB_CUDA_OK(cudaGetLastError());
     clip_combine_kernel<<<(unsigned)((rows_local + 127) / 128), 128, 0, st>>>(p.ws, p.diag, stats, rowloss, (int)rows_local,
-                                                                               p.n_split, temperature, teacher ? 1 : 0);
+                                                                               2 * p.n_split, temperature, teacher ? 1 : 0);
     DCB_CUDA_OK(cudaGetLastError());
     return 0;
 }
