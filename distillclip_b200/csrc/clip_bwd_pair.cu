@@ -11,7 +11,7 @@
 // barriers of both CTAs; both CTAs run the epilogue on their own 64 rows.
 //
 // Warp roles per CTA (384 threads): warp 0 = operand-ring producer, warp 1 = TMEM alloc (+ MMA issuer in the leader),
-// warp 2 = b_hatT producer, warp 3 idle, warps 4-11 = epilogue: warp w reads TMEM lanes 32 (w % 4) .. and the
+// warps 2-3 idle, warps 4-11 = epilogue: warp w reads TMEM lanes 32 (w % 4) .. and the
 // (w - 4) / 4-th 32-column chunk of its rows, so every scheduler has two epilogue warps to hide MUFU / FMA latency
 // (one warp per scheduler issued only every ~4 cycles, ncu r01d).
 #include "tc_common.cuh"
@@ -28,17 +28,22 @@ constexpr int kMaxSlices = 3;                             // D <= 768
 // NT = logit-tile width (columns per tile), ST = number of S/T accumulator stages in TMEM (2 = double buffered).
 // TMEM columns: ST * NT for S/T + D/2 for the gradient accumulator <= 512:  D <= 512 -> (128, 2), D <= 768 -> (128, 1).
 template <int NT, int ST> struct Cfg {
+    static_assert(NT == 128, "ring entries are sized for 128-wide tiles");
     static constexpr int kBHalf = NT / 2;                                 // b rows staged per CTA
     static constexpr int kBTile = kBHalf * kBK * 2;                       // bytes
-    static constexpr int kStageBytes = 2 * kATile + 2 * kBTile;           // a_stu, a_tea, b_stu, b_tea
-    static constexpr int kStages = 3;
+    // ONE ring for every operand byte, entries consumed in MMA issue order.  Entry kinds (32 KiB each):
+    //   S/T k-chunk:   a_stu [64 x 64], a_tea, b_stu [64 x 64], b_tea
+    //   b_hatT slice:  this CTA's [128 d-rows x 128 j] of one 256-row slice (two K sub-tiles of 16 KiB)
+    // so the bytes in flight from L2 stay at kStages x 32 KiB in both phases of a tile (the S/T recompute was limited
+    // by a 96 KiB ring: 48 B/clk/SM, r01e).
+    static constexpr int kStageBytes = 2 * kATile + 2 * kBTile;
+    static constexpr int kBtSliceBytes = kSliceRows * NT * 2;
+    static_assert(kStageBytes == 32768 && kBtSliceBytes == 32768, "uniform ring entries");
+    static constexpr int kStages = 6;
     static constexpr int kGBytes = kRowsPerCta * NT * 2;                  // fp16 G tile of this CTA
-    static constexpr int kBtSliceBytes = kSliceRows * NT * 2;             // one slice, all K sub-tiles
     static constexpr int kStCols = NT;                                    // TMEM columns of one S/T stage (S NT/2 + T NT/2)
     static constexpr int kAccCol = ST * kStCols;
-    static constexpr int smem_bytes(int slices) {
-        return 1024 + kStages * kStageBytes + kGBytes + slices * kBtSliceBytes + 2 * 5 * NT * 4 + 256;
-    }
+    static constexpr int smem_bytes() { return 1024 + kStages * kStageBytes + kGBytes + 2 * 5 * NT * 4 + 256; }
 };
 }  // namespace bwdp
 
@@ -87,18 +92,15 @@ clip_bwd_pair_kernel(const __grid_constant__ CUtensorMap map_a_stu, const __grid
     const uint32_t ring = smem_base;
     const uint32_t g_smem = ring + C::kStages * C::kStageBytes;
     uint8_t* g_gen = smem_gen + C::kStages * C::kStageBytes;
-    const uint32_t bt_smem = g_smem + C::kGBytes;
-    const int bt_bytes = p.slices * C::kBtSliceBytes;
-    float* scale_buf = reinterpret_cast<float*>(smem_gen + C::kStages * C::kStageBytes + C::kGBytes + bt_bytes);   // [2][5][NT]
+    float* scale_buf = reinterpret_cast<float*>(smem_gen + C::kStages * C::kStageBytes + C::kGBytes);   // [2][5][NT]
     uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(scale_buf) + 2 * 5 * NT * 4);
     const uint32_t bar_full = smem_u32(bars);                    // [kStages]  leader: TMA bytes of both CTAs
     const uint32_t bar_empty = bar_full + 8 * C::kStages;        // [kStages]  each CTA: slot free (multicast commit)
     const uint32_t bar_stfull = bar_empty + 8 * C::kStages;      // [2] each CTA: S/T accumulators ready (multicast commit)
     const uint32_t bar_stempty = bar_stfull + 16;                // [2] leader: 8 epilogue warps of both CTAs drained them
     const uint32_t bar_gfull = bar_stempty + 16;                 // leader: 8 epilogue warps wrote their G halves
-    const uint32_t bar_gempty = bar_gfull + 8;                   // each CTA: gradient MMAs done with G / b_hatT smem
-    const uint32_t bar_btfull = bar_gempty + 8;                  // leader: b_hatT bytes of both CTAs
-    const uint32_t bar_accfull = bar_btfull + 8;                 // each CTA: gradient accumulator final
+    const uint32_t bar_gempty = bar_gfull + 8;                   // each CTA: gradient MMAs done with the G tile
+    const uint32_t bar_accfull = bar_gempty + 8;                 // each CTA: gradient accumulator final
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::kStages + 8);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -123,7 +125,6 @@ clip_bwd_pair_kernel(const __grid_constant__ CUtensorMap map_a_stu, const __grid
         }
         mbar_init(bar_gfull, 16);
         mbar_init(bar_gempty, 1);
-        mbar_init(bar_btfull, 1);
         mbar_init(bar_accfull, 1);
         fence_barrier_init();
     }
@@ -135,45 +136,47 @@ clip_bwd_pair_kernel(const __grid_constant__ CUtensorMap map_a_stu, const __grid
     const uint32_t tmem_base = *tmem_slot;
     // leader-side barrier addresses as seen from this CTA
     const uint32_t l_full = map_to_cta(bar_full, 0), l_stempty = map_to_cta(bar_stempty, 0);
-    const uint32_t l_gfull = map_to_cta(bar_gfull, 0), l_btfull = map_to_cta(bar_btfull, 0);
+    const uint32_t l_gfull = map_to_cta(bar_gfull, 0);
 
     if (warp == 0) {
-        // ---------------------------------------------------------------- operand ring (own halves)
+        // ---------------------------------------------------------------- operand ring (own halves), MMA issue order
         if (lane == 0) {
             tma_prefetch_desc(&map_a_stu);
             tma_prefetch_desc(&map_b_stu);
+            tma_prefetch_desc(&map_bt);
             int stage = 0;
             uint32_t phase = 0;
-            constexpr uint32_t kBytesPerCta = (kTeacher ? 2 : 1) * (kATile + C::kBTile);
-            for (int t = 0; t < n_tiles; ++t) {
-                const int col0 = (tile_begin + t) * NT + (int)rank * C::kBHalf;
-                for (int kc = 0; kc < n_kc; ++kc) {
-                    mbar_wait(bar_empty + 8 * stage, phase ^ 1);
-                    const uint32_t dst = ring + stage * C::kStageBytes;
-                    if (leader) mbar_arrive_expect_tx(bar_full + 8 * stage, 2 * kBytesPerCta);
-                    const uint32_t full = l_full + 8 * stage;
-                    tma_load_2d_pair(dst, &map_a_stu, full, kc * kBK, row0);
-                    tma_load_2d_pair(dst + 2 * kATile, &map_b_stu, full, kc * kBK, col0);
-                    if (kTeacher) {
-                        tma_load_2d_pair(dst + kATile, &map_a_tea, full, kc * kBK, row0);
-                        tma_load_2d_pair(dst + 2 * kATile + C::kBTile, &map_b_tea, full, kc * kBK, col0);
+            constexpr uint32_t kStBytesPerCta = (kTeacher ? 2 : 1) * (kATile + C::kBTile);
+            for (int tt = 0; tt <= n_tiles; ++tt) {
+                if (tt < n_tiles) {                                    // S/T k-chunks of tile tt
+                    const int col0 = (tile_begin + tt) * NT + (int)rank * C::kBHalf;
+                    for (int kc = 0; kc < n_kc; ++kc) {
+                        mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+                        const uint32_t dst = ring + stage * C::kStageBytes;
+                        if (leader) mbar_arrive_expect_tx(bar_full + 8 * stage, 2 * kStBytesPerCta);
+                        const uint32_t full = l_full + 8 * stage;
+                        tma_load_2d_pair(dst, &map_a_stu, full, kc * kBK, row0);
+                        tma_load_2d_pair(dst + 2 * kATile, &map_b_stu, full, kc * kBK, col0);
+                        if (kTeacher) {
+                            tma_load_2d_pair(dst + kATile, &map_a_tea, full, kc * kBK, row0);
+                            tma_load_2d_pair(dst + 2 * kATile + C::kBTile, &map_b_tea, full, kc * kBK, col0);
+                        }
+                        if (++stage == C::kStages) { stage = 0; phase ^= 1; }
                     }
-                    if (++stage == C::kStages) { stage = 0; phase ^= 1; }
                 }
-            }
-        }
-    } else if (warp == 2) {
-        // ---------------------------------------------------------------- b_hatT: this CTA's 128 rows of every 256-row slice
-        if (lane == 0) {
-            tma_prefetch_desc(&map_bt);
-            for (int t = 0; t < n_tiles; ++t) {
-                mbar_wait(bar_gempty, (t & 1) ^ 1);
-                if (leader) mbar_arrive_expect_tx(bar_btfull, 2 * bt_bytes);
-                const int j0 = (tile_begin + t) * NT;
-                for (int sl = 0; sl < p.slices; ++sl)
-                    for (int ks = 0; ks < kSub; ++ks)
-                        tma_load_2d_pair(bt_smem + sl * C::kBtSliceBytes + ks * (kSliceRows * kBK * 2), &map_bt, l_btfull,
-                                         j0 + ks * kBK, sl * 256 + (int)rank * kSliceRows);
+                if (tt > 0) {                                          // b_hatT slices for the gradient GEMM of tile tt-1
+                    const int j0 = (tile_begin + tt - 1) * NT;
+                    for (int sl = 0; sl < p.slices; ++sl) {
+                        mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+                        const uint32_t dst = ring + stage * C::kStageBytes;
+                        if (leader) mbar_arrive_expect_tx(bar_full + 8 * stage, 2 * C::kBtSliceBytes);
+                        const uint32_t full = l_full + 8 * stage;
+                        for (int ks = 0; ks < kSub; ++ks)
+                            tma_load_2d_pair(dst + ks * (kSliceRows * kBK * 2), &map_bt, full, j0 + ks * kBK,
+                                             sl * 256 + (int)rank * kSliceRows);
+                        if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+                    }
+                }
             }
         }
     } else if (warp == 1) {
@@ -211,18 +214,22 @@ clip_bwd_pair_kernel(const __grid_constant__ CUtensorMap map_a_stu, const __grid
                 if (tt == 0) continue;
                 const int t = tt - 1;
                 mbar_wait(bar_gfull, t & 1);
-                mbar_wait(bar_btfull, t & 1);
                 tc_fence_after_sync();
                 for (int sl = 0; sl < p.slices; ++sl) {
+                    mbar_wait(bar_full + 8 * stage, phase);
+                    tc_fence_after_sync();
+                    const uint32_t src = ring + stage * C::kStageBytes;
 #pragma unroll
                     for (int ks = 0; ks < kSub; ++ks) {
                         const uint64_t dg = umma_desc_k_sw128(g_smem + ks * (kRowsPerCta * kBK * 2));
-                        const uint64_t dbt = umma_desc_k_sw128(bt_smem + sl * C::kBtSliceBytes + ks * (kSliceRows * kBK * 2));
+                        const uint64_t dbt = umma_desc_k_sw128(src + ks * (kSliceRows * kBK * 2));
 #pragma unroll
                         for (int k = 0; k < kBK / kUmmaK; ++k)
                             umma_f16_pair(tmem_base + C::kAccCol + sl * 128, dg + 2 * k, dbt + 2 * k, idesc_grad,
                                           (t > 0 || ks > 0 || k > 0) ? 1u : 0u);
                     }
+                    umma_commit_pair(bar_empty + 8 * stage, 3);
+                    if (++stage == C::kStages) { stage = 0; phase ^= 1; }
                 }
                 umma_commit_pair(bar_gempty, 3);
             }
@@ -458,11 +465,11 @@ extern "C" int dcb_clip_row_grads_pair(const void* stu_a, const void* stu_b, con
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     dim3 grid((unsigned)(2 * row_blocks * p.n_split));
     if (dim <= 512) {       // S/T double buffered: 2 x 128 + D/2 <= 512 TMEM columns
-        const int smem = bwdp::Cfg<128, 2>::smem_bytes(p.slices);
+        const int smem = bwdp::Cfg<128, 2>::smem_bytes();
         return teacher ? launch_pair<true, 128, 2>(grid, smem, st, ma_s, mb_s, ma_t, mb_t, mbt, p, idesc_st, idesc_grad)
                        : launch_pair<false, 128, 2>(grid, smem, st, ma_s, mb_s, ma_t, mb_t, mbt, p, idesc_st, idesc_grad);
     }
-    const int smem = bwdp::Cfg<128, 1>::smem_bytes(p.slices);   // D <= 768: 128 + 384 TMEM columns, S/T single buffered
+    const int smem = bwdp::Cfg<128, 1>::smem_bytes();   // D <= 768: 128 + 384 TMEM columns, S/T single buffered
     return teacher ? launch_pair<true, 128, 1>(grid, smem, st, ma_s, mb_s, ma_t, mb_t, mbt, p, idesc_st, idesc_grad)
                    : launch_pair<false, 128, 1>(grid, smem, st, ma_s, mb_s, ma_t, mb_t, mbt, p, idesc_st, idesc_grad);
 }
