@@ -37,7 +37,7 @@ SIGNATURES = {
     "dcb_clip_row_grads": [_vp, _vp, _vp, _vp, _vp, C.c_int64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int64,
                            C.c_int64, C.c_int64, C.c_int, C.c_float, _vp, _vp],
     "dcb_clip_row_grads_pair": [_vp, _vp, _vp, _vp, _vp, C.c_int64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int64,
-                                C.c_int64, C.c_int64, C.c_int, C.c_float, _vp, _vp, _vp],
+                                C.c_int64, C.c_int64, C.c_int, C.c_float, _vp, _vp, _vp, _vp],
     "dcb_clip_grad_finish": [_vp, C.c_int, _vp, _vp, _vp, _vp, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int64,
                              _vp, _vp, _vp, C.c_int, _vp, C.c_int, _vp],
     "dcb_logits_row_stats": [_vp, C.c_int64, C.c_int64, _vp, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_float,

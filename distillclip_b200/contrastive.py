@@ -43,6 +43,8 @@ class CudaEngine:
     use_pair_kernel = os.environ.get("DCB_BWD_KERNEL", "pair") != "chunk"
     #: tests only: [rows, cols] fp32 buffer that receives the logits the pair kernel's epilogue sees
     dump_pair_logits = None
+    #: profiling only: int64 [2, 64, 16] buffer for clock64() stamps of the pair kernel's first cluster
+    trace_pair = None
 
     def inv_norms(self, mats: Sequence[torch.Tensor]):
         outs = [torch.empty(m.shape[0], dtype=torch.float32, device=m.device) for m in mats]
@@ -102,7 +104,7 @@ class CudaEngine:
             _lib.call("dcb_clip_row_grads_pair", _vp(a_s), _vp(b_s), _vp(a_t), _vp(b_t), _vp(b_s_t), b_s_t.shape[1],
                       _vp(a_s_inv), _vp(b_s_inv), _vp(a_t_inv), _vp(b_t_inv), _vp(coef_row), _vp(coef_col),
                       _vp(gmax_row), _vp(gmax_col), rows, cols, dim, ops.dtype_code(a_s), float(temperature or 1.0),
-                      _vp(acc), _vp(self.dump_pair_logits), ops._stream_ptr())
+                      _vp(acc), _vp(self.dump_pair_logits), _vp(self.trace_pair), ops._stream_ptr())
         else:
             n_split = lib.dcb_clip_grad_splits(rows, cols, dim)
             acc = torch.empty(n_split, rows, dim, dtype=torch.float32, device=a_s.device)

@@ -127,7 +127,7 @@ clip_bwd_kernel(const __grid_constant__ CUtensorMap map_a_stu, const __grid_cons
 
     if (warp == 0) {
         // ---------------------------------------------------------------- operand ring for the S / T recompute
-        if (lane == 0) {
+        if (elect_one()) {
             tma_prefetch_desc(&map_a_stu);
             tma_prefetch_desc(&map_b_stu);
             int stage = 0;
@@ -151,7 +151,7 @@ clip_bwd_kernel(const __grid_constant__ CUtensorMap map_a_stu, const __grid_cons
         }
     } else if (warp == 2) {
         // ---------------------------------------------------------------- bT tiles for the gradient GEMM
-        if (lane == 0) {
+        if (elect_one()) {
             tma_prefetch_desc(&map_bt);
             for (int t = 0; t < n_tiles; ++t) {
                 mbar_wait(bar_gempty, (t & 1) ^ 1);           // previous gradient MMAs have consumed the buffer
@@ -160,19 +160,19 @@ clip_bwd_kernel(const __grid_constant__ CUtensorMap map_a_stu, const __grid_cons
             }
         }
     } else if (warp == 1) {
-        // ---------------------------------------------------------------- MMA issuer
-        if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
-            auto issue_st = [&](int t) {
-                const int as = t & 1;
-                mbar_wait(bar_stempty + 8 * as, ((t >> 1) & 1) ^ 1);
+        // ---------------------------------------------------------------- MMA issuer: warp-uniform waits, one elected lane issues
+        int stage = 0;
+        uint32_t phase = 0;
+        auto issue_st = [&](int t) {
+            const int as = t & 1;
+            mbar_wait(bar_stempty + 8 * as, ((t >> 1) & 1) ^ 1);
+            tc_fence_after_sync();
+            const uint32_t acc_s = tmem_base + as * 128, acc_t = acc_s + 64;
+            for (int kc = 0; kc < n_kc; ++kc) {
+                mbar_wait(bar_full + 8 * stage, phase);
                 tc_fence_after_sync();
-                const uint32_t acc_s = tmem_base + as * 128, acc_t = acc_s + 64;
-                for (int kc = 0; kc < n_kc; ++kc) {
-                    mbar_wait(bar_full + 8 * stage, phase);
-                    tc_fence_after_sync();
-                    const uint32_t src = ring + stage * kStageBytes;
+                const uint32_t src = ring + stage * kStageBytes;
+                if (elect_one()) {
                     const uint64_t da_s = umma_desc_k_sw128(src), db_s = umma_desc_k_sw128(src + kATile);
                     const uint64_t da_t = umma_desc_k_sw128(src + kATile + kBTile);
                     const uint64_t db_t = umma_desc_k_sw128(src + 2 * kATile + kBTile);
@@ -183,23 +183,27 @@ clip_bwd_kernel(const __grid_constant__ CUtensorMap map_a_stu, const __grid_cons
                         if (kTeacher) umma_f16(acc_t, da_t + 2 * k, db_t + 2 * k, idesc_st, accum);
                     }
                     umma_commit(bar_empty + 8 * stage);
-                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                    if (kc == n_kc - 1) umma_commit(bar_stfull + 8 * as);
                 }
-                umma_commit(bar_stfull + 8 * as);
-            };
-            issue_st(0);
-            for (int t = 0; t < n_tiles; ++t) {
-                if (t + 1 < n_tiles) issue_st(t + 1);          // overlaps the epilogue of tile t
-                mbar_wait(bar_gfull, t & 1);
-                mbar_wait(bar_btfull, t & 1);
-                tc_fence_after_sync();
+                __syncwarp();
+                if (++stage == kStages) { stage = 0; phase ^= 1; }
+            }
+        };
+        issue_st(0);
+        for (int t = 0; t < n_tiles; ++t) {
+            if (t + 1 < n_tiles) issue_st(t + 1);          // overlaps the epilogue of tile t
+            mbar_wait(bar_gfull, t & 1);
+            mbar_wait(bar_btfull, t & 1);
+            tc_fence_after_sync();
+            if (elect_one()) {
                 const uint64_t dg = umma_desc_k_sw128(g_smem), dbt = umma_desc_k_sw128(bt_smem);
 #pragma unroll
                 for (int k = 0; k < kBN / kUmmaK; ++k)
                     umma_f16(tmem_base + kAccCol, dg + 2 * k, dbt + 2 * k, idesc_grad, (t > 0 || k > 0) ? 1u : 0u);
                 umma_commit(bar_gempty);
+                if (t == n_tiles - 1) umma_commit(bar_accfull);
             }
-            umma_commit(bar_accfull);
+            __syncwarp();
         }
     } else if (warp >= 4) {
         // ---------------------------------------------------------------- epilogue

@@ -58,11 +58,21 @@ struct ClipBwdPairParams {
     const float* gmax_col;
     float* acc;               // [n_split][rows][dim] fp32
     float* dump_s;            // tests only: [rows, cols] student logits as seen by the epilogue
+    long long* trace;         // profiling only: clock64 timestamps of cluster 0 (see kTraceSlots), else nullptr
     int rows, cols, dim;
     int slices;               // ceil(dim / 256)
     int n_split, col_tiles;
     float inv_temp;
 };
+
+// trace layout: [tile][16] : 0-4 MMA thread (st wait done, st issued, gfull wait done, grad issued, -)
+//                            8-14 epilogue warp 4 lane 0 (tile start, scales staged, stfull, tmem loaded, computed, gempty, done)
+constexpr int kTraceSlots = 16, kTraceTiles = 64;
+#define DCB_TRACE(tile, slot)                                                                        \
+    do {                                                                                             \
+        if (p.trace && blockIdx.x < 2 && (tile) < kTraceTiles)                                       \
+            p.trace[((size_t)(blockIdx.x & 1) * kTraceTiles + (tile)) * kTraceSlots + (slot)] = clock64(); \
+    } while (0)
 
 __device__ __forceinline__ float pair_tile_scale(float gmax) {      // must match clip_grad_tile_scale in clip_misc.cu
     if (!(gmax > 0.f) || !isfinite(gmax)) return 1.f;
@@ -140,7 +150,7 @@ clip_bwd_pair_kernel(const __grid_constant__ CUtensorMap map_a_stu, const __grid
 
     if (warp == 0) {
         // ---------------------------------------------------------------- operand ring (own halves), MMA issue order
-        if (lane == 0) {
+        if (elect_one()) {
             tma_prefetch_desc(&map_a_stu);
             tma_prefetch_desc(&map_b_stu);
             tma_prefetch_desc(&map_bt);
@@ -180,32 +190,44 @@ clip_bwd_pair_kernel(const __grid_constant__ CUtensorMap map_a_stu, const __grid
             }
         }
     } else if (warp == 1) {
-        // ---------------------------------------------------------------- MMA issuer (leader CTA, one thread)
-        if (leader && lane == 0) {
+        // ---------------------------------------------------------------- MMA issuer (leader CTA): the whole warp walks
+        // the pipeline (waits are warp-uniform), one elected lane issues
+        if (leader) {
             int stage = 0;
             uint32_t phase = 0;
             auto issue_st = [&](int t) {
                 const int as = t % ST;
                 mbar_wait(bar_stempty + 8 * as, ((t / ST) & 1) ^ 1);
+                if (lane == 0) DCB_TRACE(t, 0);
                 tc_fence_after_sync();
                 const uint32_t acc_s = tmem_base + as * C::kStCols, acc_t = acc_s + NT / 2;
+                long long t_wait = 0, t_mark = p.trace ? clock64() : 0;
                 for (int kc = 0; kc < n_kc; ++kc) {
                     mbar_wait(bar_full + 8 * stage, phase);
+                    if (p.trace) { const long long now = clock64(); t_wait += now - t_mark; }
                     tc_fence_after_sync();
                     const uint32_t src = ring + stage * C::kStageBytes;
-                    const uint64_t da_s = umma_desc_k_sw128(src), da_t = umma_desc_k_sw128(src + kATile);
-                    const uint64_t db_s = umma_desc_k_sw128(src + 2 * kATile);
-                    const uint64_t db_t = umma_desc_k_sw128(src + 2 * kATile + C::kBTile);
+                    if (elect_one()) {
+                        const uint64_t da_s = umma_desc_k_sw128(src), da_t = umma_desc_k_sw128(src + kATile);
+                        const uint64_t db_s = umma_desc_k_sw128(src + 2 * kATile);
+                        const uint64_t db_t = umma_desc_k_sw128(src + 2 * kATile + C::kBTile);
 #pragma unroll
-                    for (int k = 0; k < kBK / kUmmaK; ++k) {
-                        const uint32_t accum = (kc > 0 || k > 0) ? 1u : 0u;
-                        umma_f16_pair(acc_s, da_s + 2 * k, db_s + 2 * k, idesc_st, accum);
-                        if (kTeacher) umma_f16_pair(acc_t, da_t + 2 * k, db_t + 2 * k, idesc_st, accum);
+                        for (int k = 0; k < kBK / kUmmaK; ++k) {
+                            const uint32_t accum = (kc > 0 || k > 0) ? 1u : 0u;
+                            umma_f16_pair(acc_s, da_s + 2 * k, db_s + 2 * k, idesc_st, accum);
+                            if (kTeacher) umma_f16_pair(acc_t, da_t + 2 * k, db_t + 2 * k, idesc_st, accum);
+                        }
+                        umma_commit_pair(bar_empty + 8 * stage, 3);
+                        if (kc == n_kc - 1) umma_commit_pair(bar_stfull + 8 * as, 3);
                     }
-                    umma_commit_pair(bar_empty + 8 * stage, 3);
+                    __syncwarp();
                     if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+                    if (p.trace) t_mark = clock64();
                 }
-                umma_commit_pair(bar_stfull + 8 * as, 3);
+                if (lane == 0) {
+                    DCB_TRACE(t, 1);
+                    if (p.trace && blockIdx.x < 2 && t < kTraceTiles) p.trace[((size_t)(blockIdx.x & 1) * kTraceTiles + t) * kTraceSlots + 4] = t_wait;
+                }
             };
             // order on the (in-order) MMA pipe: S/T(t), grad(t-1), S/T(t+1), ...  -- the gradient GEMM of tile t-1 runs
             // while the epilogue warps work on tile t; with ST == 2 the S/T GEMM of tile t+1 overlaps them as well
@@ -214,26 +236,33 @@ clip_bwd_pair_kernel(const __grid_constant__ CUtensorMap map_a_stu, const __grid
                 if (tt == 0) continue;
                 const int t = tt - 1;
                 mbar_wait(bar_gfull, t & 1);
+                if (lane == 0) DCB_TRACE(t, 2);
                 tc_fence_after_sync();
                 for (int sl = 0; sl < p.slices; ++sl) {
                     mbar_wait(bar_full + 8 * stage, phase);
                     tc_fence_after_sync();
                     const uint32_t src = ring + stage * C::kStageBytes;
+                    if (elect_one()) {
 #pragma unroll
-                    for (int ks = 0; ks < kSub; ++ks) {
-                        const uint64_t dg = umma_desc_k_sw128(g_smem + ks * (kRowsPerCta * kBK * 2));
-                        const uint64_t dbt = umma_desc_k_sw128(src + ks * (kSliceRows * kBK * 2));
+                        for (int ks = 0; ks < kSub; ++ks) {
+                            const uint64_t dg = umma_desc_k_sw128(g_smem + ks * (kRowsPerCta * kBK * 2));
+                            const uint64_t dbt = umma_desc_k_sw128(src + ks * (kSliceRows * kBK * 2));
 #pragma unroll
-                        for (int k = 0; k < kBK / kUmmaK; ++k)
-                            umma_f16_pair(tmem_base + C::kAccCol + sl * 128, dg + 2 * k, dbt + 2 * k, idesc_grad,
-                                          (t > 0 || ks > 0 || k > 0) ? 1u : 0u);
+                            for (int k = 0; k < kBK / kUmmaK; ++k)
+                                umma_f16_pair(tmem_base + C::kAccCol + sl * 128, dg + 2 * k, dbt + 2 * k, idesc_grad,
+                                              (t > 0 || ks > 0 || k > 0) ? 1u : 0u);
+                        }
+                        umma_commit_pair(bar_empty + 8 * stage, 3);
+                        if (sl == p.slices - 1) {
+                            umma_commit_pair(bar_gempty, 3);
+                            if (t == n_tiles - 1) umma_commit_pair(bar_accfull, 3);
+                        }
                     }
-                    umma_commit_pair(bar_empty + 8 * stage, 3);
+                    __syncwarp();
                     if (++stage == C::kStages) { stage = 0; phase ^= 1; }
                 }
-                umma_commit_pair(bar_gempty, 3);
+                if (lane == 0) DCB_TRACE(t, 3);
             }
-            umma_commit_pair(bar_accfull, 3);
         }
     } else if (warp >= 4) {
         // ---------------------------------------------------------------- epilogue (both CTAs, own 64 rows)
@@ -260,6 +289,8 @@ clip_bwd_pair_kernel(const __grid_constant__ CUtensorMap map_a_stu, const __grid
             const int as = t % ST;
             const int col0 = (tile_begin + t) * NT;
             float* sc = scale_buf + (t & 1) * 5 * NT;      // [c_stu][c_tea][alpha'][beta'][gamma'] x NT
+            const bool tr = ep_tid == 0;
+            if (tr) DCB_TRACE(t, 8);
             if (ep_tid < NT) {
                 const int gc = col0 + ep_tid;
                 const bool ok = gc < p.cols;
@@ -274,7 +305,9 @@ clip_bwd_pair_kernel(const __grid_constant__ CUtensorMap map_a_stu, const __grid
                 sc[4 * NT + c] = ok ? __ldg(p.coef_col + 2 * (size_t)p.cols + gc) : 0.f;
             }
             asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (tr) DCB_TRACE(t, 9);
             mbar_wait(bar_stfull + 8 * as, (t / ST) & 1);
+            if (tr) DCB_TRACE(t, 10);
             tc_fence_after_sync();
             const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * C::kStCols + sub * 32;
             uint32_t packed[16];
@@ -286,6 +319,7 @@ clip_bwd_pair_kernel(const __grid_constant__ CUtensorMap map_a_stu, const __grid
             tc_fence_before_sync();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(l_stempty + 8 * as);
+            if (tr) DCB_TRACE(t, 11);
             if (p.dump_s) {                                     // tests only; kept out of the hot loop
                 for (int c = 0; c < 32; ++c)
                     if (row_ok && col0 + cbase + c < p.cols)
@@ -312,7 +346,9 @@ clip_bwd_pair_kernel(const __grid_constant__ CUtensorMap map_a_stu, const __grid
                 }
                 packed[c >> 1] = pack2<__half>(g2[0], g2[1]);
             }
+            if (tr) DCB_TRACE(t, 12);
             mbar_wait(bar_gempty, (t & 1) ^ 1);
+            if (tr) DCB_TRACE(t, 13);
             // columns [cbase, cbase + 32) of row r -> K-major SW128 sub-tile `half`, 16-byte chunks sub*4 .. sub*4+3
 #pragma unroll
             for (int c8 = 0; c8 < 4; ++c8) {
@@ -322,6 +358,7 @@ clip_bwd_pair_kernel(const __grid_constant__ CUtensorMap map_a_stu, const __grid
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(l_gfull);
+            if (tr) DCB_TRACE(t, 14);
         }
         // gradient accumulator -> global partial buffer.  Slice sl: lanes 0-63 hold d in [256 sl, 256 sl + 128),
         // lanes 64-127 hold d in [256 sl + 128, 256 sl + 256); 128 TMEM columns per slice, split between the two warps
@@ -418,7 +455,7 @@ extern "C" int dcb_clip_row_grads_pair(const void* stu_a, const void* stu_b, con
                                        const float* tea_b_inv, const float* coef_row, const float* coef_col,
                                        const float* gmax_row, const float* gmax_col, int64_t rows_local, int64_t cols,
                                        int64_t dim, int dtype, float temperature, float* acc_parts, float* dump_s,
-                                       void* stream) {
+                                       long long* trace, void* stream) {
     using namespace dcb;
     DCB_REQUIRE(stu_a && stu_b && stu_b_t && stu_a_inv && stu_b_inv && coef_row && coef_col && gmax_row && gmax_col && acc_parts,
                 "NULL pointer argument");
@@ -452,6 +489,7 @@ extern "C" int dcb_clip_row_grads_pair(const void* stu_a, const void* stu_b, con
     p.gmax_col = gmax_col;
     p.acc = acc_parts;
     p.dump_s = dump_s;
+    p.trace = trace;
     p.rows = (int)rows_local;
     p.cols = (int)cols;
     p.dim = (int)dim;

@@ -101,7 +101,7 @@ clip_fwd_kernel(const __grid_constant__ CUtensorMap map_a_stu, const __grid_cons
 
     if (warp == 0) {
         // ---------------------------------------------------------------- TMA producer
-        if (lane == 0) {
+        if (elect_one()) {
             tma_prefetch_desc(&map_a_stu);
             tma_prefetch_desc(&map_b_stu);
             if (kTeacher) {
@@ -128,21 +128,21 @@ clip_fwd_kernel(const __grid_constant__ CUtensorMap map_a_stu, const __grid_cons
             }
         }
     } else if (warp == 1) {
-        // ---------------------------------------------------------------- MMA issuer (one thread)
-        if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int t = 0; t < n_tiles; ++t) {
-                const int as = t & 1;                       // accumulator stage
-                const uint32_t aphase = (t >> 1) & 1;
-                mbar_wait(bar_tempty + 8 * as, aphase ^ 1);
+        // ---------------------------------------------------------------- MMA issuer: warp-uniform waits, one elected lane issues
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int t = 0; t < n_tiles; ++t) {
+            const int as = t & 1;                       // accumulator stage
+            const uint32_t aphase = (t >> 1) & 1;
+            mbar_wait(bar_tempty + 8 * as, aphase ^ 1);
+            tc_fence_after_sync();
+            const uint32_t acc_s = tmem_base + as * 256;
+            const uint32_t acc_t = acc_s + 128;
+            for (int kc = 0; kc < n_kc; ++kc) {
+                mbar_wait(bar_full + 8 * stage, phase);
                 tc_fence_after_sync();
-                const uint32_t acc_s = tmem_base + as * 256;
-                const uint32_t acc_t = acc_s + 128;
-                for (int kc = 0; kc < n_kc; ++kc) {
-                    mbar_wait(bar_full + 8 * stage, phase);
-                    tc_fence_after_sync();
-                    const uint32_t src = ring + stage * kStageBytes;
+                const uint32_t src = ring + stage * kStageBytes;
+                if (elect_one()) {
                     const uint64_t da_s = umma_desc_k_sw128(src), db_s = umma_desc_k_sw128(src + kTileBytes);
                     const uint64_t da_t = umma_desc_k_sw128(src + 2 * kTileBytes), db_t = umma_desc_k_sw128(src + 3 * kTileBytes);
 #pragma unroll
@@ -152,9 +152,10 @@ clip_fwd_kernel(const __grid_constant__ CUtensorMap map_a_stu, const __grid_cons
                         if (kTeacher) umma_f16(acc_t, da_t + 2 * k, db_t + 2 * k, idesc, accum);
                     }
                     umma_commit(bar_empty + 8 * stage);     // frees the smem slot once these MMAs retire
-                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                    if (kc == n_kc - 1) umma_commit(bar_tfull + 8 * as);     // accumulators of this tile are complete
                 }
-                umma_commit(bar_tfull + 8 * as);            // accumulators of this tile are complete
+                __syncwarp();
+                if (++stage == kStages) { stage = 0; phase ^= 1; }
             }
         }
     } else {

@@ -16,6 +16,21 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
+// One lane of a fully converged warp.  tcgen05.mma / commit / TMA are warp-level ("uniform datapath") instructions:
+// issued under `if (lane == 0)` the compiler cannot prove that a single lane is active and wraps EVERY such
+// instruction in an ELECT / BRA.U.ANY serialisation loop (~36 clk per MMA, measured r01g); under elect.sync it does not.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "elect.sync _|P1, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, P1;\n\t"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
+
 // ------------------------------------------------------------------------------------------
 // mbarrier
 // ------------------------------------------------------------------------------------------

@@ -171,7 +171,8 @@ int dcb_clip_row_grads(const void* stu_a, const void* stu_b, const void* tea_a, 
 
 /* Same contract as dcb_clip_row_grads, CTA-pair implementation (tcgen05 cta_group::2, clusters of 2): the whole
  * embedding dimension is accumulated in one pass, so the logits are recomputed once per direction.  dim <= 768.
- * acc_parts: dcb_clip_pair_splits(...) buffers of [rows_local, dim].  dump_s: tests only (NULL in production). */
+ * acc_parts: dcb_clip_pair_splits(...) buffers of [rows_local, dim].  dump_s: tests only (NULL in production).
+ * trace: profiling only, 2 x 64 x 16 int64 clock64() stamps of the first cluster's pipeline events (NULL in production). */
 int dcb_clip_pair_supported(int64_t dim);
 int dcb_clip_pair_splits(int64_t rows_local, int64_t cols, int64_t dim);
 int dcb_clip_row_grads_pair(const void* stu_a, const void* stu_b, const void* tea_a, const void* tea_b,
@@ -179,7 +180,7 @@ int dcb_clip_row_grads_pair(const void* stu_a, const void* stu_b, const void* te
                             const float* stu_a_inv, const float* stu_b_inv, const float* tea_a_inv, const float* tea_b_inv,
                             const float* coef_row, const float* coef_col, const float* gmax_row, const float* gmax_col,
                             int64_t rows_local, int64_t cols, int64_t dim, int dtype, float temperature,
-                            float* acc_parts, float* dump_s, void* stream);
+                            float* acc_parts, float* dump_s, long long* trace, void* stream);
 
 /* grad_a[i,:] = r_i (acc_i - a_hat_i (a_hat_i . acc_i)),  acc_i = 2^-k sum_s acc_parts[s][i,:] - (gh/B) b_hat_{row_offset+i}
  * (the -[i==j] label term of the cross entropy, added here in fp32, then the x/||x|| Jacobian of clip_model.py:37-38). */
