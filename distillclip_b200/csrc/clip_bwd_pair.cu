@@ -67,7 +67,7 @@ struct ClipBwdPairParams {
 
 // trace layout: [tile][16] : 0-4 MMA thread (st wait done, st issued, gfull wait done, grad issued, -)
 //                            8-14 epilogue warp 4 lane 0 (tile start, scales staged, stfull, tmem loaded, computed, gempty, done)
-constexpr int kTraceSlots = 16, kTraceTiles = 64;
+constexpr int kTraceSlots = 24, kTraceTiles = 64;
 #define DCB_TRACE(tile, slot)                                                                        \
     do {                                                                                             \
         if (p.trace && blockIdx.x < 2 && (tile) < kTraceTiles)                                       \
@@ -312,9 +312,11 @@ clip_bwd_pair_kernel(const __grid_constant__ CUtensorMap map_a_stu, const __grid
             const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * C::kStCols + sub * 32;
             uint32_t packed[16];
             float sv[32], tv[32];
+            if (tr) DCB_TRACE(t, 16);
             tmem_ld_32x32(lane_addr, sv);
             if (kTeacher) tmem_ld_32x32(lane_addr + NT / 2, tv);
             tmem_ld_wait();
+            if (tr) DCB_TRACE(t, 17);
             // S/T columns of this warp are in registers: release the accumulator stage as early as possible
             tc_fence_before_sync();
             __syncwarp();
@@ -355,7 +357,9 @@ clip_bwd_pair_kernel(const __grid_constant__ CUtensorMap map_a_stu, const __grid
                 uint4 w = make_uint4(packed[4 * c8], packed[4 * c8 + 1], packed[4 * c8 + 2], packed[4 * c8 + 3]);
                 *reinterpret_cast<uint4*>(g_gen + half * (kRowsPerCta * kBK * 2) + sw128_chunk_offset(r, sub * 4 + c8)) = w;
             }
+            if (tr) DCB_TRACE(t, 18);
             fence_proxy_async_smem();
+            if (tr) DCB_TRACE(t, 19);
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(l_gfull);
             if (tr) DCB_TRACE(t, 14);

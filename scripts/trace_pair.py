@@ -13,7 +13,7 @@ eng = ct.CudaEngine()
 out, saved = ct.contrastive_forward(eng, si, st, ti, tt, 2.0, None)
 up = torch.tensor([0.5, 0.5], device="cuda")
 for it in range(3):
-    eng.trace_pair = torch.zeros(2, 64, 16, dtype=torch.int64, device="cuda")
+    eng.trace_pair = torch.zeros(2, 64, 24, dtype=torch.int64, device="cuda")
     ct.contrastive_backward(eng, saved, up, want_img=True, want_txt=False)
     torch.cuda.synchronize()
 tr = eng.trace_pair.cpu()
@@ -35,3 +35,6 @@ for cta in range(2):
           " wait stfull:", sum(int(t[i, 10] - t[i, 9]) for i in range(4, 30)) / 26, " tmem ld:", sum(int(t[i, 11] - t[i, 10]) for i in range(4, 30)) / 26,
           " compute:", sum(int(t[i, 12] - t[i, 11]) for i in range(4, 30)) / 26, " wait gempty:", sum(int(t[i, 13] - t[i, 12]) for i in range(4, 30)) / 26,
           " write+arrive:", sum(int(t[i, 14] - t[i, 13]) for i in range(4, 30)) / 26)
+    print("   fine: after_sync fence:", sum(int(t[i, 16] - t[i, 10]) for i in range(4, 30)) / 26, " ld+wait:", sum(int(t[i, 17] - t[i, 16]) for i in range(4, 30)) / 26,
+          " before_sync+arrive:", sum(int(t[i, 11] - t[i, 17]) for i in range(4, 30)) / 26, " smem stores:", sum(int(t[i, 18] - t[i, 13]) for i in range(4, 30)) / 26,
+          " proxy fence:", sum(int(t[i, 19] - t[i, 18]) for i in range(4, 30)) / 26, " syncwarp+arrive:", sum(int(t[i, 14] - t[i, 19]) for i in range(4, 30)) / 26)
