@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "lib
 
 BF16, F16, F32 = 0, 1, 2
 MAX_LAYERS, MAX_PARTIALS, MAX_TERMS = 16, 4096, 16
-TOWER_MAX_SEG, TOWER_MAX_TERMS = 40, 4
+TOWER_MAX_SEG, TOWER_MAX_TERMS = 40, 8
 
 _vp, _i64p, _i32p, _f32p = C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int32), C.POINTER(C.c_float)
 _vpp = C.POINTER(C.c_void_p)

@@ -301,7 +301,7 @@ class LogitsLossFn(torch.autograd.Function):
         _lib.call("dcb_logits_row_stats", _vp(stu), stu.stride(0), stu.stride(1), _vp(tea),
                   tea.stride(0) if tea is not None else 0, tea.stride(1) if tea is not None else 0, n,
                   ops.dtype_code(stu), float(temperature or 1.0), mode, _vp(saved), _vp(rowloss), ops._stream_ptr())
-        scale = float(temperature) ** 2 if mode == 1 else 1.0 / n
+        scale = float(temperature) ** 2 if mode == 1 else (1.0 / n if mode == 0 else 1.0)
         out = ops.finalize([(rowloss, n)], [scale], [1.0])
         ctx.save_for_backward(stu, tea if tea is not None else stu, saved)
         ctx.meta = (temperature, mode, tea is not None)
@@ -343,3 +343,14 @@ def soft_label_from_logits(stu_logits: torch.Tensor, tea_logits: torch.Tensor, t
     if tea_logits.dtype != stu_logits.dtype:
         tea_logits = tea_logits.to(stu_logits.dtype)
     return LogitsLossFn.apply(stu_logits, tea_logits.detach(), float(temperature), 1)
+
+
+def cos_diff_from_logits(stu_logits: torch.Tensor, tea_logits: torch.Tensor) -> torch.Tensor:
+    """mean relu(tea_ii - stu_ii) + mean_{i != j} relu(stu_ij - tea_ij) -- reference clip_cos_diff.py:12-23."""
+    _check_logits(stu_logits, "stu_logits")
+    _check_logits(tea_logits, "tea_logits")
+    if tea_logits.shape != stu_logits.shape:
+        raise ValueError("student and teacher logits must have the same shape")
+    if tea_logits.dtype != stu_logits.dtype:
+        tea_logits = tea_logits.to(stu_logits.dtype)
+    return LogitsLossFn.apply(stu_logits, tea_logits.detach(), None, 2)

@@ -70,12 +70,17 @@ static int launch_attn(AttnParams& p, double* partials, int* n_partials, cudaStr
     long long grid = tiles < (long long)kNumSMs * 16 ? tiles : (long long)kNumSMs * 16;
     if (grid < 1) grid = 1;
     const unsigned g = (unsigned)grid;
-    if (common_h == 12 && VEC <= 4)
-        attn_kl_kernel<T, G, VEC, 12><<<g, kAttnThreads, 0, stream>>>(p, partials);
-    else if (common_h == 8 && VEC <= 4)
-        attn_kl_kernel<T, G, VEC, 8><<<g, kAttnThreads, 0, stream>>>(p, partials);
-    else
-        attn_kl_kernel<T, G, VEC, 0><<<g, kAttnThreads, 0, stream>>>(p, partials);
+    bool done = false;
+    if constexpr (VEC <= 4) {
+        if (common_h == 12) {
+            attn_kl_kernel<T, G, VEC, 12><<<g, kAttnThreads, 0, stream>>>(p, partials);
+            done = true;
+        } else if (common_h == 8) {
+            attn_kl_kernel<T, G, VEC, 8><<<g, kAttnThreads, 0, stream>>>(p, partials);
+            done = true;
+        }
+    }
+    if (!done) attn_kl_kernel<T, G, VEC, 0><<<g, kAttnThreads, 0, stream>>>(p, partials);
     DCB_CUDA_OK(cudaGetLastError());
     *n_partials = (int)grid;
     return 0;

@@ -105,6 +105,38 @@ __global__ void __launch_bounds__(kLogitThreads) logits_grads_kernel(const T* __
     }
 }
 
+// CLIPCosDiff (reference model/loss_component/clip_cos_diff.py:5-23):
+//   value = mean_i relu(t_ii - s_ii) + mean_{i != j} relu(s_ij - t_ij)      (get_neg_element = all off-diagonal entries)
+// rowloss[i] = relu(t_ii - s_ii) / n + sum_{j != i} relu(s_ij - t_ij) / (n (n-1));  relu'(0) = 0.
+template <typename T>
+__global__ void __launch_bounds__(kLogitThreads) cos_diff_stats_kernel(const T* __restrict__ s, long long srs, long long scs,
+                                                                       const T* __restrict__ t, long long trs, long long tcs,
+                                                                       int n, double* __restrict__ rowloss) {
+    const long long i = blockIdx.x;
+    float neg = 0.f;
+    for (int j = threadIdx.x; j < n; j += kLogitThreads)
+        if (j != i) neg += fmaxf(ld_logit(s, srs, scs, i, j) - ld_logit(t, trs, tcs, i, j), 0.f);
+    neg = block_sum_all(neg);
+    if (threadIdx.x == 0) {
+        const float pos = fmaxf(ld_logit(t, trs, tcs, i, i) - ld_logit(s, srs, scs, i, i), 0.f);
+        rowloss[i] = (double)pos / (double)n + (n > 1 ? (double)neg / ((double)n * (double)(n - 1)) : 0.0);
+    }
+}
+template <typename T, typename G>
+__global__ void __launch_bounds__(kLogitThreads) cos_diff_grads_kernel(const T* __restrict__ s, long long srs, long long scs,
+                                                                       const T* __restrict__ t, long long trs, long long tcs,
+                                                                       int n, const float* __restrict__ upstream, G* __restrict__ grad) {
+    const long long i = blockIdx.x;
+    const float up = upstream[0];
+    const float gpos = -up / (float)n, gneg = n > 1 ? up / ((float)n * (float)(n - 1)) : 0.f;
+    G* __restrict__ g = grad + i * n;
+    for (int j = threadIdx.x; j < n; j += kLogitThreads) {
+        const float sv = ld_logit(s, srs, scs, i, j), tv = ld_logit(t, trs, tcs, i, j);
+        const float v = (j == i) ? (tv > sv ? gpos : 0.f) : (sv > tv ? gneg : 0.f);
+        g[j] = Elem<G>::from_f(v);
+    }
+}
+
 }  // namespace dcb
 
 extern "C" {
@@ -114,8 +146,19 @@ int dcb_logits_row_stats(const void* stu_logits, int64_t stu_rs, int64_t stu_cs,
                          void* stream) {
     using namespace dcb;
     DCB_REQUIRE(stu_logits && saved && rowloss && n >= 1 && n < (1ll << 31), "bad arguments");
-    DCB_REQUIRE(mode == 0 || (mode == 1 && tea_logits && temperature > 0.f), "soft label needs teacher logits and a positive temperature");
+    DCB_REQUIRE(mode == 0 || (mode == 1 && tea_logits && temperature > 0.f) || (mode == 2 && tea_logits),
+                "soft label needs teacher logits and a positive temperature; cos_diff needs teacher logits");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (mode == 2) {
+        switch (dtype) {
+            case DCB_BF16: cos_diff_stats_kernel<__nv_bfloat16><<<(unsigned)n, kLogitThreads, 0, st>>>(static_cast<const __nv_bfloat16*>(stu_logits), stu_rs, stu_cs, static_cast<const __nv_bfloat16*>(tea_logits), tea_rs, tea_cs, (int)n, rowloss); break;
+            case DCB_F16: cos_diff_stats_kernel<__half><<<(unsigned)n, kLogitThreads, 0, st>>>(static_cast<const __half*>(stu_logits), stu_rs, stu_cs, static_cast<const __half*>(tea_logits), tea_rs, tea_cs, (int)n, rowloss); break;
+            case DCB_F32: cos_diff_stats_kernel<float><<<(unsigned)n, kLogitThreads, 0, st>>>(static_cast<const float*>(stu_logits), stu_rs, stu_cs, static_cast<const float*>(tea_logits), tea_rs, tea_cs, (int)n, rowloss); break;
+            default: return fail("unknown dtype %d", dtype);
+        }
+        DCB_CUDA_OK(cudaGetLastError());
+        return 0;
+    }
     const float inv_temp = mode == 1 ? 1.0f / temperature : 1.0f;
     float4* sv = reinterpret_cast<float4*>(saved);
 #define DCB_LAUNCH_STATS(T)                                                                                            \
@@ -141,14 +184,19 @@ int dcb_logits_row_grads(const void* stu_logits, int64_t stu_rs, int64_t stu_cs,
                          const float* upstream, void* grad_logits, int grad_dtype, void* stream) {
     using namespace dcb;
     DCB_REQUIRE(stu_logits && saved && upstream && grad_logits && n >= 1, "bad arguments");
-    DCB_REQUIRE(mode == 0 || (mode == 1 && tea_logits && temperature > 0.f), "soft label needs teacher logits and a positive temperature");
+    DCB_REQUIRE(mode == 0 || (mode == 1 && tea_logits && temperature > 0.f) || (mode == 2 && tea_logits),
+                "soft label needs teacher logits and a positive temperature; cos_diff needs teacher logits");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const float inv_temp = mode == 1 ? 1.0f / temperature : 1.0f;
     const float4* sv = reinterpret_cast<const float4*>(saved);
     return dispatch_in_grad(dtype, grad_dtype, [&](auto tt, auto gg) -> int {
         using T = decltype(tt);
         using G = decltype(gg);
-        if (mode == 1)
+        if (mode == 2)
+            cos_diff_grads_kernel<T, G><<<(unsigned)n, kLogitThreads, 0, st>>>(
+                static_cast<const T*>(stu_logits), stu_rs, stu_cs, static_cast<const T*>(tea_logits), tea_rs, tea_cs, (int)n,
+                upstream, static_cast<G*>(grad_logits));
+        else if (mode == 1)
             logits_grads_kernel<T, G, true><<<(unsigned)n, kLogitThreads, 0, st>>>(
                 static_cast<const T*>(stu_logits), stu_rs, stu_cs, static_cast<const T*>(tea_logits), tea_rs, tea_cs, (int)n,
                 inv_temp, sv, upstream, static_cast<G*>(grad_logits));

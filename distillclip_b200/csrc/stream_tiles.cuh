@@ -9,10 +9,21 @@ constexpr int kStreamThreads = 256;
 constexpr int kMseUnroll = 4;
 
 // ---------------------------------------------------------------------------------------------
-// MSE tile: kStreamThreads * kMseUnroll * VEC consecutive elements.
-// Returns sum (s-t)^2 over this thread's elements (fp32); writes g = (s-t) * grad_coef when g != nullptr.
+// Elementwise-difference tile: kStreamThreads * kMseUnroll * VEC consecutive elements.
+//   L1 == false (nn.MSELoss):  returns sum (s-t)^2,  writes g = (s-t) * grad_coef
+//   L1 == true  (nn.L1Loss):   returns sum |s-t|,    writes g = sign(s-t) * grad_coef   (sign(0) = 0, as ATen)
 // ---------------------------------------------------------------------------------------------
-template <typename T, typename G, int VEC>
+template <bool L1> __device__ __forceinline__ void diff_op(float d, float gc, float& acc, float& g) {
+    if constexpr (L1) {
+        acc += fabsf(d);
+        g = d > 0.f ? gc : (d < 0.f ? -gc : (d == 0.f ? 0.f : d));     // NaN propagates
+    } else {
+        acc = fmaf(d, d, acc);
+        g = d * gc;
+    }
+}
+
+template <typename T, typename G, int VEC, bool L1 = false>
 __device__ __forceinline__ float mse_tile(const T* __restrict__ s, const T* __restrict__ t, G* __restrict__ g,
                                           long long rem, float gc, int tid) {
     constexpr int kTile = kStreamThreads * kMseUnroll * VEC;
@@ -27,11 +38,7 @@ __device__ __forceinline__ float mse_tile(const T* __restrict__ s, const T* __re
         for (int u = 0; u < kMseUnroll; ++u) {
             float gv[VEC];
 #pragma unroll
-            for (int e = 0; e < VEC; ++e) {
-                const float d = sv[u][e] - tv[u][e];
-                acc = fmaf(d, d, acc);
-                gv[e] = d * gc;
-            }
+            for (int e = 0; e < VEC; ++e) diff_op<L1>(sv[u][e] - tv[u][e], gc, acc, gv[e]);
             if (g) store_vec<G, VEC>(g + (u * kStreamThreads + tid) * VEC, gv);
         }
     } else {
@@ -43,17 +50,13 @@ __device__ __forceinline__ float mse_tile(const T* __restrict__ s, const T* __re
                 load_vec<T, VEC>(s + i0, sv);
                 load_vec<T, VEC>(t + i0, tv);
 #pragma unroll
-                for (int e = 0; e < VEC; ++e) {
-                    const float d = sv[e] - tv[e];
-                    acc = fmaf(d, d, acc);
-                    gv[e] = d * gc;
-                }
+                for (int e = 0; e < VEC; ++e) diff_op<L1>(sv[e] - tv[e], gc, acc, gv[e]);
                 if (g) store_vec<G, VEC>(g + i0, gv);
             } else {
                 for (long long i = i0; i < rem; ++i) {
-                    const float d = Elem<T>::to_f(s[i]) - Elem<T>::to_f(t[i]);
-                    acc = fmaf(d, d, acc);
-                    if (g) g[i] = Elem<G>::from_f(d * gc);
+                    float gv1;
+                    diff_op<L1>(Elem<T>::to_f(s[i]) - Elem<T>::to_f(t[i]), gc, acc, gv1);
+                    if (g) g[i] = Elem<G>::from_f(gv1);
                 }
             }
         }
@@ -96,7 +99,10 @@ struct AttnShape {
 };
 
 // H = compile-time head count of both maps (0 = runtime head counts).  gi = group index handled by this thread.
-template <typename T, typename G, int VEC, int H>
+//   MSE == false: KL(sum) of the head means (attention_probs_kl.py:15-20)
+//   MSE == true : squared error of the head means (attention_probs_mse.py:13-20, attention_score_mse.py:13-20);
+//                 value = sum (s_mean - t_mean)^2, gradient = (s_mean - t_mean) * gc for every student head
+template <typename T, typename G, int VEC, int H, bool MSE = false>
 __device__ __forceinline__ float attn_tile(const T* __restrict__ s_base, const T* __restrict__ t_base, G* __restrict__ g_base,
                                            const AttnShape& sh, long long gi, float gc) {
     if (gi >= sh.groups) return 0.f;
@@ -113,9 +119,15 @@ __device__ __forceinline__ float attn_tile(const T* __restrict__ s_base, const T
     for (int e = 0; e < VEC; ++e) {
         const float sm = ssum[e] * sh.inv_hs;
         const float tm = tsum[e] * sh.inv_ht;
-        const float tl = (tm == 0.f) ? 0.f : tm * logf(tm);     // xlogy(t, t)
-        acc += tl - tm * logf(sm);                               // 0 * -inf -> NaN like the reference
-        gv[e] = -gc * (tm / sm);
+        if constexpr (MSE) {
+            const float d = sm - tm;
+            acc = fmaf(d, d, acc);
+            gv[e] = d * gc;
+        } else {
+            const float tl = (tm == 0.f) ? 0.f : tm * logf(tm);     // xlogy(t, t)
+            acc += tl - tm * logf(sm);                               // 0 * -inf -> NaN like the reference
+            gv[e] = -gc * (tm / sm);
+        }
     }
     if (g_base) {
         G* __restrict__ g = g_base + (b * sh.hs) * P + pos;
@@ -128,6 +140,39 @@ __device__ __forceinline__ float attn_tile(const T* __restrict__ s_base, const T
         }
     }
     return acc;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Cosine rows tile (nn.CosineEmbeddingLoss with target 1, out_cos.py:10-11): one warp per row of [rows, dim].
+//   cos = <s,t> / sqrt((<s,s> + eps)(<t,t> + eps)), eps = 1e-12 (ATen EPSILON);  value = sum_rows (1 - cos)
+//   d value / d s = -( t / sqrt(..) - cos * s / (<s,s> + eps) )      (times gc)
+// Returns the row's (1 - cos) in lane 0 (0 elsewhere).
+// ---------------------------------------------------------------------------------------------
+template <typename T, typename G>
+__device__ __forceinline__ float cos_row_tile(const T* __restrict__ s_base, const T* __restrict__ t_base, G* __restrict__ g_base,
+                                              long long rows, int dim, long long row, float gc, int lane) {
+    if (row >= rows) return 0.f;
+    const T* __restrict__ s = s_base + row * dim;
+    const T* __restrict__ t = t_base + row * dim;
+    float st = 0.f, ss = 0.f, tt = 0.f;
+    for (int d = lane; d < dim; d += 32) {
+        const float a = Elem<T>::to_f(s[d]), b = Elem<T>::to_f(t[d]);
+        st = fmaf(a, b, st);
+        ss = fmaf(a, a, ss);
+        tt = fmaf(b, b, tt);
+    }
+    st = warp_sum(st);
+    ss = warp_sum(ss) + 1e-12f;
+    tt = warp_sum(tt) + 1e-12f;
+    const float inv = rsqrtf(ss) * rsqrtf(tt);
+    const float c = st * inv;
+    if (g_base) {
+        G* __restrict__ g = g_base + row * dim;
+        const float k = c / ss;
+        for (int d = lane; d < dim; d += 32)
+            g[d] = Elem<G>::from_f(-gc * (Elem<T>::to_f(t[d]) * inv - k * Elem<T>::to_f(s[d])));
+    }
+    return lane == 0 ? 1.f - c : 0.f;
 }
 
 }  // namespace dcb

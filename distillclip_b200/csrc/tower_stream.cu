@@ -1,8 +1,10 @@
-// All streaming losses of one tower in ONE launch: hidden-state / embedding MSE and attention-map KL over every layer,
-// values and student gradients in a single pass over HBM, plus the weighting of model/_loss.py:195-200.
+// All streaming losses of one tower in ONE launch: hidden-state / embedding MSE, attention-map KL, attention-map /
+// attention-score MSE, output L1 and output cosine, over every layer; values and student gradients in a single pass
+// over HBM, plus the weighting of model/_loss.py:195-200.
 //
 // Replaces LossCalculator.cal_one_tower_loss's python loops over layers and loss names (reference model/_loss.py:155-202,
-// loss_component/attention_probs_kl.py:10-22, hidden_mse.py:9-17, embed_mse.py:9-10) and their autograd backward.
+// loss_component/attention_probs_kl.py:10-22, attention_probs_mse.py:10-22, attention_score_mse.py:10-22,
+// hidden_mse.py:9-17, embed_mse.py:9-10, out_l1.py:9-10, out_cos.py:10-11) and their autograd backward.
 //
 // A persistent grid (4 CTAs per SM) walks a unified tile list (MSE tiles, then attention tiles).  Every CTA keeps one
 // double accumulator per loss term and writes it to partials[term][cta]; the last CTA to finish (atomic ticket) reduces
@@ -13,7 +15,7 @@
 namespace dcb {
 
 constexpr int kTowerMaxSeg = 40;
-constexpr int kTowerMaxTerms = 4;
+constexpr int kTowerMaxTerms = 8;
 
 struct TowerSeg {
     const void* s;
@@ -23,7 +25,7 @@ struct TowerSeg {
     long long tile_begin;
     long long positions;   // ATTN
     long long groups_per_b;
-    int kind;              // 0 = MSE, 1 = attention KL
+    int kind;              // 0 = MSE, 1 = attention KL, 2 = L1, 3 = cosine rows, 4 = attention (head-mean) MSE
     int term;
     int hs, ht;
     int aligned;           // MSE: 16-byte aligned pointers -> vector path
@@ -47,42 +49,61 @@ __global__ void __launch_bounds__(kStreamThreads, 4) tower_stream_kernel(const _
     constexpr long long kMseTile = (long long)kStreamThreads * kMseUnroll * MVEC;
     constexpr long long kMseTileScalar = (long long)kStreamThreads * kMseUnroll;
     const int tid = threadIdx.x;
-    double dacc[kTowerMaxTerms];
-#pragma unroll
-    for (int k = 0; k < kTowerMaxTerms; ++k) dacc[k] = 0.0;
+    // Tiles are ordered by segment and segments by term, so a CTA meets the terms in non-decreasing order: one running
+    // accumulator, flushed (block reduce -> partials[term][cta]) whenever the term changes.
+    double cur = 0.0;
+    int cur_term = -1;
+    unsigned int written = 0;          // thread 0: bit q set once partials[q][cta] has been written
+    auto flush = [&]() {
+        const double total = block_sum(cur);
+        if (tid == 0) {
+            p.partials[(size_t)cur_term * gridDim.x + blockIdx.x] = total;
+            written |= 1u << cur_term;
+        }
+        __syncthreads();
+        cur = 0.0;
+    };
     int k = 0;
     for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         while (k + 1 < p.n_seg && tile >= p.seg[k + 1].tile_begin) ++k;
         const TowerSeg& sg = p.seg[k];
+        if (sg.term != cur_term) {                     // block-uniform
+            if (cur_term >= 0) flush();
+            cur_term = sg.term;
+        }
         const long long lt = tile - sg.tile_begin;
         float acc;
-        if (sg.kind == 0) {
+        if (sg.kind == 0 || sg.kind == 2) {
             G* g = static_cast<G*>(sg.g);
-            if (sg.aligned) {
-                const long long base = lt * kMseTile;
-                acc = mse_tile<T, G, MVEC>(static_cast<const T*>(sg.s) + base, static_cast<const T*>(sg.t) + base,
-                                           g ? g + base : nullptr, sg.n - base, sg.grad_coef, tid);
-            } else {
-                const long long base = lt * kMseTileScalar;
-                acc = mse_tile<T, G, 1>(static_cast<const T*>(sg.s) + base, static_cast<const T*>(sg.t) + base,
-                                        g ? g + base : nullptr, sg.n - base, sg.grad_coef, tid);
-            }
+            const long long base = lt * (sg.aligned ? kMseTile : kMseTileScalar);
+            const T* sp = static_cast<const T*>(sg.s) + base;
+            const T* tp = static_cast<const T*>(sg.t) + base;
+            G* gp = g ? g + base : nullptr;
+            if (sg.kind == 0)
+                acc = sg.aligned ? mse_tile<T, G, MVEC, false>(sp, tp, gp, sg.n - base, sg.grad_coef, tid)
+                                 : mse_tile<T, G, 1, false>(sp, tp, gp, sg.n - base, sg.grad_coef, tid);
+            else
+                acc = sg.aligned ? mse_tile<T, G, MVEC, true>(sp, tp, gp, sg.n - base, sg.grad_coef, tid)
+                                 : mse_tile<T, G, 1, true>(sp, tp, gp, sg.n - base, sg.grad_coef, tid);
+        } else if (sg.kind == 3) {
+            acc = cos_row_tile<T, G>(static_cast<const T*>(sg.s), static_cast<const T*>(sg.t), static_cast<G*>(sg.g), sg.n,
+                                     (int)sg.positions, lt * (kStreamThreads / 32) + (tid >> 5), sg.grad_coef, tid & 31);
         } else {
             AttnShape sh{sg.n, sg.groups_per_b, sg.positions, sg.hs, sg.ht, sg.inv_hs, sg.inv_ht};
-            acc = attn_tile<T, G, AVEC, AH>(static_cast<const T*>(sg.s), static_cast<const T*>(sg.t), static_cast<G*>(sg.g),
-                                            sh, lt * kStreamThreads + tid, sg.grad_coef);
+            if (sg.kind == 1)
+                acc = attn_tile<T, G, AVEC, AH, false>(static_cast<const T*>(sg.s), static_cast<const T*>(sg.t),
+                                                       static_cast<G*>(sg.g), sh, lt * kStreamThreads + tid, sg.grad_coef);
+            else
+                acc = attn_tile<T, G, AVEC, AH, true>(static_cast<const T*>(sg.s), static_cast<const T*>(sg.t),
+                                                      static_cast<G*>(sg.g), sh, lt * kStreamThreads + tid, sg.grad_coef);
         }
-        const double v = (double)acc * (double)sg.val_coef;
-#pragma unroll
-        for (int q = 0; q < kTowerMaxTerms; ++q)
-            if (q == sg.term) dacc[q] += v;
+        cur += (double)acc * (double)sg.val_coef;
     }
+    if (cur_term >= 0) flush();
     __shared__ bool is_last;
-    for (int q = 0; q < p.n_terms; ++q) {
-        const double total = block_sum(dacc[q]);
-        if (tid == 0) p.partials[(size_t)q * gridDim.x + blockIdx.x] = total;
-        __syncthreads();
-    }
+    if (tid == 0)
+        for (int q = 0; q < p.n_terms; ++q)
+            if (!(written & (1u << q))) p.partials[(size_t)q * gridDim.x + blockIdx.x] = 0.0;
     if (tid == 0) {
         __threadfence();
         const unsigned int ticket = atomicAdd(p.ticket, 1u);
@@ -115,12 +136,17 @@ __global__ void __launch_bounds__(kStreamThreads, 4) tower_stream_kernel(const _
 
 template <typename T, typename G, int AVEC>
 static int launch_tower_h(const TowerParams& p, int common_h, unsigned grid, cudaStream_t st) {
-    if (common_h == 12 && AVEC <= 4)
-        tower_stream_kernel<T, G, AVEC, 12><<<grid, kStreamThreads, 0, st>>>(p);
-    else if (common_h == 8 && AVEC <= 4)
-        tower_stream_kernel<T, G, AVEC, 8><<<grid, kStreamThreads, 0, st>>>(p);
-    else
-        tower_stream_kernel<T, G, AVEC, 0><<<grid, kStreamThreads, 0, st>>>(p);
+    bool done = false;
+    if constexpr (AVEC <= 4) {          // head loops fully unrolled for the two head counts of the BASELINE configs
+        if (common_h == 12) {
+            tower_stream_kernel<T, G, AVEC, 12><<<grid, kStreamThreads, 0, st>>>(p);
+            done = true;
+        } else if (common_h == 8) {
+            tower_stream_kernel<T, G, AVEC, 8><<<grid, kStreamThreads, 0, st>>>(p);
+            done = true;
+        }
+    }
+    if (!done) tower_stream_kernel<T, G, AVEC, 0><<<grid, kStreamThreads, 0, st>>>(p);
     DCB_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -160,14 +186,22 @@ extern "C" int dcb_tower_fwd_bwd(int n_seg, const int32_t* kind, const int32_t* 
         sg.g = grad_stu ? grad_stu[k] : nullptr;
         sg.kind = kind[k];
         sg.term = term[k];
-        if (kind[k] == 0) {
+        if (kind[k] == 0 || kind[k] == 2) {
             DCB_REQUIRE(numel[k] >= 1, "segment %d: numel must be >= 1", k);
             sg.n = numel[k];
             const double denom = (double)numel[k] * (double)divisor[k];
             sg.val_coef = (float)(1.0 / denom);
-            sg.grad_coef = (float)(2.0 * (double)grad_scale[k] / denom);
+            sg.grad_coef = (float)((kind[k] == 0 ? 2.0 : 1.0) * (double)grad_scale[k] / denom);
             sg.aligned = (((uintptr_t)stu[k] | (uintptr_t)tea[k] | (uintptr_t)sg.g) % 16 == 0) ? 1 : 0;
-        } else if (kind[k] == 1) {
+        } else if (kind[k] == 3) {
+            // cosine rows: batch[k] rows of positions[k] elements; value = mean over rows of (1 - cos)
+            DCB_REQUIRE(batch[k] >= 1 && positions[k] >= 1 && positions[k] < (1ll << 31), "segment %d: bad shape", k);
+            sg.n = batch[k];
+            sg.positions = positions[k];
+            const double denom = (double)batch[k] * (double)divisor[k];
+            sg.val_coef = (float)(1.0 / denom);
+            sg.grad_coef = (float)((double)grad_scale[k] / denom);
+        } else if (kind[k] == 1 || kind[k] == 4) {
             DCB_REQUIRE(batch[k] >= 1 && positions[k] >= 1 && stu_heads[k] >= 1 && tea_heads[k] >= 1, "segment %d: bad shape", k);
             sg.n = batch[k];
             sg.positions = positions[k];
@@ -175,8 +209,14 @@ extern "C" int dcb_tower_fwd_bwd(int n_seg, const int32_t* kind, const int32_t* 
             sg.ht = tea_heads[k];
             sg.inv_hs = 1.0f / (float)stu_heads[k];
             sg.inv_ht = 1.0f / (float)tea_heads[k];
-            sg.val_coef = (float)(1.0 / (double)divisor[k]);
-            sg.grad_coef = (float)((double)grad_scale[k] / ((double)stu_heads[k] * (double)divisor[k]));
+            if (kind[k] == 1) {
+                sg.val_coef = (float)(1.0 / (double)divisor[k]);
+                sg.grad_coef = (float)((double)grad_scale[k] / ((double)stu_heads[k] * (double)divisor[k]));
+            } else {      // MSE(mean) of the head means: mean over batch * positions elements
+                const double denom = (double)batch[k] * (double)positions[k] * (double)divisor[k];
+                sg.val_coef = (float)(1.0 / denom);
+                sg.grad_coef = (float)(2.0 * (double)grad_scale[k] / (denom * (double)stu_heads[k]));
+            }
             while (avec > 1 && (positions[k] % avec != 0 || ((uintptr_t)stu[k] | (uintptr_t)tea[k]) % (avec * isz) != 0 ||
                                 (sg.g && (uintptr_t)sg.g % (avec * gsz < 16 ? avec * gsz : 16) != 0)))
                 avec >>= 1;
@@ -192,9 +232,11 @@ extern "C" int dcb_tower_fwd_bwd(int n_seg, const int32_t* kind, const int32_t* 
     for (int k = 0; k < n_seg; ++k) {
         TowerSeg& sg = p.seg[k];
         sg.tile_begin = tiles;
-        if (sg.kind == 0) {
+        if (sg.kind == 0 || sg.kind == 2) {
             const long long tl = sg.aligned ? mse_tile_vec : mse_tile_scalar;
             tiles += (sg.n + tl - 1) / tl;
+        } else if (sg.kind == 3) {
+            tiles += (sg.n + kStreamThreads / 32 - 1) / (kStreamThreads / 32);       // one warp per row
         } else {
             sg.groups_per_b = sg.positions / avec;
             sg.n *= sg.groups_per_b;

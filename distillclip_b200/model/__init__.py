@@ -1,8 +1,9 @@
 """Mirror of the reference's `model` package for the loss hot path (same import paths below `model`)."""
 from ._loss import IMAGE_TEXT_LOSS, LOSSNAME, LossCalculator
 from .component.output import CLIPOutput, ControlOutput, TextTransformerOutput, VisionTransformerOutput
-from .loss_component import AttentionProbsKL, EmbedMSELoss, HardLabel, HiddenMSE, SoftLabel
+from .loss_component import (AttentionProbsKL, AttentionProbsMSE, AttentionScoreMSE, CLIPCosDiff, EmbedMSELoss, HardLabel,
+                             HiddenMSE, OutCosLoss, OutL1Loss, SoftLabel)
 
 __all__ = ["LossCalculator", "LOSSNAME", "IMAGE_TEXT_LOSS", "CLIPOutput", "ControlOutput",
-           "TextTransformerOutput", "VisionTransformerOutput", "AttentionProbsKL", "EmbedMSELoss", "HardLabel",
-           "HiddenMSE", "SoftLabel"]
+           "TextTransformerOutput", "VisionTransformerOutput", "AttentionProbsKL", "AttentionProbsMSE", "AttentionScoreMSE",
+           "CLIPCosDiff", "EmbedMSELoss", "HardLabel", "HiddenMSE", "OutCosLoss", "OutL1Loss", "SoftLabel"]

@@ -8,8 +8,9 @@ Underneath, each tower's losses run as one-pass CUDA kernels with a single deter
 two-tower hard/soft-label terms run as the fused tcgen05 contrastive kernel straight from the embeddings
 (`last_representation`), never touching the materialised B x B logits.
 
-In scope: hard_label, soft_label, attention_probs_kl, hidden_rep_mse, embedding_mse.
-The reference's other loss names are recognised but raise NotImplementedError here.
+In scope: hard_label, soft_label, attention_probs_kl, hidden_rep_mse, embedding_mse; widened
+(section 8f) to the losses of the three shipped configs and their siblings: out_l1, out_cos, cos_diff,
+attention_probs_mse, attention_score_mse.  The reference's remaining names are recognised but raise NotImplementedError.
 """
 from typing import Dict, List, Union
 
@@ -18,7 +19,8 @@ from torch import nn
 
 from .. import contrastive, ops
 from .component.output import CLIPOutput, ControlOutput, TextTransformerOutput, VisionTransformerOutput
-from .loss_component import AttentionProbsKL, EmbedMSELoss, HardLabel, HiddenMSE, SoftLabel
+from .loss_component import (AttentionProbsKL, AttentionProbsMSE, AttentionScoreMSE, CLIPCosDiff, EmbedMSELoss,
+                             HardLabel, HiddenMSE, OutCosLoss, OutL1Loss, SoftLabel)
 
 # reference _loss.py:9-12 -- including the missing comma that fuses 'smd' and 'hard_label' 
 LOSSNAME = ['out_l1', 'out_ce', 'out_kl', 'out_cos', 'embedding_mse', 'attention_score_mse',
@@ -27,12 +29,15 @@ LOSSNAME = ['out_l1', 'out_ce', 'out_kl', 'out_cos', 'embedding_mse', 'attention
 IMAGE_TEXT_LOSS = ['hard_label', 'soft_label', 'logits_mse', 'fine_grain', 'cos_diff']
 
 # names the reference accepts (_loss.py:60-94) that are outside this build's hot-path scope
-_REFERENCE_ONLY = ('out_l1', 'out_ce', 'out_kl', 'out_cos', 'attention_score_mse', 'attention_probs_mse',
-                   'last_value_map_kl', 'vit_kd', 'logits_mse', 'fine_grain', 'smd', 'cos_diff')
+_REFERENCE_ONLY = ('out_ce', 'out_kl', 'last_value_map_kl', 'vit_kd', 'logits_mse', 'fine_grain', 'smd')
 
 # one-tower losses: name -> (kernel family, student field, is a list of layers)
 _TOWER_KERNELS = {
+    'out_l1': (ops.KIND_L1, 'last_representation', False),
+    'out_cos': (ops.KIND_COS, 'last_representation', False),
     'embedding_mse': (ops.KIND_MSE, 'embedding', False),
+    'attention_score_mse': (ops.KIND_ATTN_MSE, 'attention_scores', True),
+    'attention_probs_mse': (ops.KIND_ATTN_MSE, 'attention_probs', True),
     'hidden_rep_mse': (ops.KIND_MSE, 'representations', True),
     'attention_probs_kl': (ops.KIND_ATTN_KL, 'attention_probs', True),
 }
@@ -81,8 +86,10 @@ class LossCalculator(nn.Module):
 
     def _init_loss(self):
         table = {
-            'embedding_mse': EmbedMSELoss, 'hidden_rep_mse': HiddenMSE, 'attention_probs_kl': AttentionProbsKL,
-            'hard_label': HardLabel, 'soft_label': lambda: SoftLabel(self.temperature),
+            'out_l1': OutL1Loss, 'out_cos': OutCosLoss, 'embedding_mse': EmbedMSELoss,
+            'attention_score_mse': AttentionScoreMSE, 'attention_probs_mse': AttentionProbsMSE,
+            'hidden_rep_mse': HiddenMSE, 'attention_probs_kl': AttentionProbsKL,
+            'hard_label': HardLabel, 'soft_label': lambda: SoftLabel(self.temperature), 'cos_diff': CLIPCosDiff,
         }
         losses = nn.ModuleDict()
         for n in self.loss_name:
@@ -190,6 +197,11 @@ class LossCalculator(nn.Module):
                 tea_out.text_output.last_representation if want_soft else None,
                 self.temperature if want_soft else None, want_hard, want_soft, group=self.contrastive_group)
         for loss_name in self.loss_name:
+            if loss_name == 'cos_diff':         # reference _loss.py:143-145, on the caller's materialised logits
+                loss = self.loss[loss_name]
+                cal_res[loss_name] = 0.5 * (loss(stu_out.i2t_logits, tea_out.i2t_logits)
+                                            + loss(stu_out.t2i_logits, tea_out.t2i_logits))
+                continue
             if loss_name not in ('hard_label', 'soft_label'):
                 continue
             if loss_name in fused:

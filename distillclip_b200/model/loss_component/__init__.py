@@ -1,7 +1,13 @@
 from .attention_probs_kl import AttentionProbsKL
+from .attention_probs_mse import AttentionProbsMSE
+from .attention_score_mse import AttentionScoreMSE
+from .clip_cos_diff import CLIPCosDiff
 from .embed_mse import EmbedMSELoss
 from .hard_label import HardLabel
 from .hidden_mse import HiddenMSE
+from .out_cos import OutCosLoss
+from .out_l1 import OutL1Loss
 from .soft_label import SoftLabel
 
-__all__ = ["AttentionProbsKL", "EmbedMSELoss", "HardLabel", "HiddenMSE", "SoftLabel"]
+__all__ = ["AttentionProbsKL", "AttentionProbsMSE", "AttentionScoreMSE", "CLIPCosDiff", "EmbedMSELoss", "HardLabel",
+           "HiddenMSE", "OutCosLoss", "OutL1Loss", "SoftLabel"]

@@ -150,10 +150,14 @@ def launch_tower(entries, scale: Sequence[float], percent: Sequence[float], grad
     for ti, (kind, divisor, stu, tea, need, pre) in enumerate(entries):
         grads = [] if out is None else all_grads[ti]
         for li, (s, t, ng) in enumerate(zip(stu, tea, need)):
-            if kind == KIND_MSE:
+            if kind in (KIND_MSE, KIND_L1):
                 if s.shape != t.shape:
-                    raise ValueError(f"MSE: student {tuple(s.shape)} and teacher {tuple(t.shape)} shapes differ")
+                    raise ValueError(f"{kind}: student {tuple(s.shape)} and teacher {tuple(t.shape)} shapes differ")
                 batch.append(1), hs.append(1), ht.append(1), pos.append(1)
+            elif kind == KIND_COS:
+                if s.shape != t.shape or s.dim() != 2:
+                    raise ValueError(f"cosine loss takes equal [B, D] tensors: student {tuple(s.shape)}, teacher {tuple(t.shape)}")
+                batch.append(s.shape[0]), hs.append(1), ht.append(1), pos.append(s.shape[1])
             else:
                 if s.dim() < 3 or t.dim() != s.dim() or s.shape[0] != t.shape[0] or s.shape[2:] != t.shape[2:]:
                     raise ValueError(f"attention maps must be [B, H, ...] with equal B and map size: "
@@ -163,7 +167,7 @@ def launch_tower(entries, scale: Sequence[float], percent: Sequence[float], grad
             if out is None:
                 grads.append(torch.empty_like(s, dtype=grad_dtype or s.dtype) if ng else None)
             g = grads[li]
-            kinds.append(0 if kind == KIND_MSE else 1), terms.append(ti)
+            kinds.append(_KIND_CODE[kind]), terms.append(ti)
             stu_p.append(s.data_ptr()), tea_p.append(t.data_ptr()), grad_p.append(g.data_ptr() if g is not None else 0)
             numel.append(s.numel()), div.append(int(divisor)), gsc.append(float(pre))
         if out is None:
@@ -226,8 +230,9 @@ def _as_upstream(g: Optional[torch.Tensor], like: torch.Tensor) -> torch.Tensor:
 #: but fp16-stored gradients were then already rounded at the unscaled magnitude.
 EXPECTED_GRAD_SCALE = 1.0
 
-KIND_MSE, KIND_ATTN_KL = "mse", "attn_kl"
-_LAUNCH = {KIND_MSE: launch_mse, KIND_ATTN_KL: launch_attn_kl}
+KIND_MSE, KIND_ATTN_KL, KIND_L1, KIND_COS, KIND_ATTN_MSE = "mse", "attn_kl", "l1", "cos", "attn_mse"
+_LAUNCH = {KIND_MSE: launch_mse, KIND_ATTN_KL: launch_attn_kl}        # per-family kernels (the others are tower-only)
+_KIND_CODE = {KIND_MSE: 0, KIND_ATTN_KL: 1, KIND_L1: 2, KIND_COS: 3, KIND_ATTN_MSE: 4}
 
 
 class StreamLossFn(torch.autograd.Function):
@@ -262,6 +267,8 @@ def stream_loss(kind: str, stu: Sequence[torch.Tensor], tea: Sequence[torch.Tens
     s, t = _prep_pair(stu, tea)
     if not s:
         return 0.0          # reference: `res_loss = 0; res_loss /= len(stu)` -> python float
+    if kind not in _LAUNCH:
+        return TowerLossFn.apply([(kind, divisor, len(s), 1.0, 1.0)], float(EXPECTED_GRAD_SCALE), *s, *t)[0]
     return StreamLossFn.apply(kind, divisor, len(s), float(EXPECTED_GRAD_SCALE), *s, *t)
 
 
@@ -290,6 +297,9 @@ class TowerLossFn(torch.autograd.Function):
         scales, percents = [sp[3] for sp in spec], [sp[4] for sp in spec]
         n_seg = sum(len(e[2]) for e in entries)
         dtypes = {t.dtype for e in entries for t in e[2]}
+        tower_only = any(e[0] not in _LAUNCH for e in entries)
+        if tower_only and not (len(spec) <= _lib.TOWER_MAX_TERMS and n_seg <= _lib.TOWER_MAX_SEG and len(dtypes) == 1):
+            raise _lib.DistillClipB200Error("these losses need one dtype per tower, <= 8 terms and <= 40 layer pairs")
         if len(spec) <= _lib.TOWER_MAX_TERMS and n_seg <= _lib.TOWER_MAX_SEG and len(dtypes) == 1:
             out, all_grads, _ = launch_tower(entries, scales, percents)       # ONE launch incl. the weighting
         else:

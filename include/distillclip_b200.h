@@ -66,8 +66,11 @@ int dcb_attn_kl_fwd_bwd(int n_layers, const void* const* stu, const void* const*
  * ALL streaming losses of one tower in ONE launch, including the weighting below.
  * Replaces LossCalculator.cal_one_tower_loss's loops (model/_loss.py:155-202) over embedding_mse, hidden_rep_mse and
  * attention_probs_kl and their autograd backward.  Segment k (one layer of one loss term) has
- *   kind[k]  0 = MSE (numel[k]),  1 = attention KL (batch[k], stu_heads[k], tea_heads[k], positions[k]);
- *   term[k]  index of the loss term it adds to (< n_terms <= 4); divisor[k], grad_scale[k] as in the calls above.
+ *   kind[k]  0 = MSE (numel[k]),  1 = attention KL (batch[k], stu_heads[k], tea_heads[k], positions[k]),
+ *            2 = L1 (out_l1.py, numel[k]),  3 = cosine rows (out_cos.py; batch[k] rows of positions[k] elements),
+ *            4 = MSE of head-mean maps (attention_probs_mse.py / attention_score_mse.py; shapes as kind 1);
+ *   term[k]  index of the loss term it adds to (< n_terms <= 8, segments grouped by term); divisor[k], grad_scale[k]
+ *            as in the calls above.
  * out[q] = scale[q] * value_q (q < n_terms), out[n_terms] = sum_q percent[q] * out[q]  (_loss.py:199-200).
  * partials: n_terms * dcb_tower_grid() doubles of scratch; ticket: one uint32, zero before the first launch (the kernel
  * resets it).  Values are reduced in a fixed order by the last CTA to finish: deterministic, no extra launch.
@@ -192,7 +195,8 @@ int dcb_clip_grad_finish(const float* acc_parts, int n_split, const void* stu_a,
 /* ---------------------------------------------------------------------------------------------
  * Per-module API on MATERIALISED logits (HardLabel / SoftLabel keep their logits signature).
  * logits: [n, n] with element strides (row_stride, col_stride) so that `logits.T` views work.
- * mode 0 = HardLabel (hard_label.py:10-12), mode 1 = SoftLabel (soft_label.py:11-16).
+ * mode 0 = HardLabel (hard_label.py:10-12), mode 1 = SoftLabel (soft_label.py:11-16),
+ * mode 2 = CLIPCosDiff (clip_cos_diff.py:5-23; rowloss already carries the 1/n and 1/(n(n-1)) means, reduce with scale 1).
  *   saved[i]   = {max_s, Z_s, max_t, Z_t} (float4 per row, for the backward)
  *   rowloss[i] = CE_i (mode 0) or KL_i without the T^2 factor (mode 1), double; reduce with dcb_finalize
  *                (scale 1/n resp. T^2).

@@ -73,6 +73,38 @@ def embed_mse(stu: torch.Tensor, tea: torch.Tensor):
     return F.mse_loss(stu, tea)
 
 
+def out_l1(stu, tea):
+    # loss_component/out_l1.py:9-10
+    return F.l1_loss(stu, tea)
+
+
+def out_cos(stu, tea):
+    # loss_component/out_cos.py:10-11
+    return F.cosine_embedding_loss(stu, tea, torch.ones(len(stu), device=stu.device))
+
+
+def attention_mean_mse(stu: Sequence[torch.Tensor], tea: Sequence[torch.Tensor]):
+    # loss_component/attention_probs_mse.py:10-22 and attention_score_mse.py:10-22
+    acc = 0
+    for k, (s, t) in enumerate(zip(stu, tea)):
+        term = F.mse_loss(_head_mean(s), _head_mean(t))
+        acc = term if k == 0 else acc + term
+    acc /= len(stu)
+    return acc
+
+
+def _neg_elements(x):
+    n = x.shape[0]
+    return x.flatten()[:-1].view(n - 1, n + 1)[:, 1:].flatten()      # clip_cos_diff.py:5-8
+
+
+def cos_diff(stu_logits, tea_logits):
+    # loss_component/clip_cos_diff.py:16-23
+    pos = torch.mean(torch.relu(torch.diagonal(tea_logits) - torch.diagonal(stu_logits)))
+    neg = torch.mean(torch.relu(_neg_elements(stu_logits) - _neg_elements(tea_logits)))
+    return neg + pos
+
+
 def one_tower(names, scale, percent, temperature, stu: Dict, tea: Dict):
     """_loss.py:155-202 for the in-scope names.  `stu`/`tea` are dicts with keys
     last_representation / attention_probs / representations / embedding."""
@@ -84,6 +116,14 @@ def one_tower(names, scale, percent, temperature, stu: Dict, tea: Dict):
             res[n] = hidden_mse(stu["representations"], tea["representations"])
         elif n == "attention_probs_kl":
             res[n] = attention_probs_kl(stu["attention_probs"], tea["attention_probs"])
+        elif n == "attention_probs_mse":
+            res[n] = attention_mean_mse(stu["attention_probs"], tea["attention_probs"])
+        elif n == "attention_score_mse":
+            res[n] = attention_mean_mse(stu["attention_scores"], tea["attention_scores"])
+        elif n == "out_l1":
+            res[n] = out_l1(stu["last_representation"], tea["last_representation"])
+        elif n == "out_cos":
+            res[n] = out_cos(stu["last_representation"], tea["last_representation"])
     loss = 0
     for n, sc in scale.items():
         if n in IMAGE_TEXT_LOSS:
@@ -104,7 +144,7 @@ def two_tower(names, scale, percent, temperature, stu: Dict, tea: Dict):
     for k, v in tres.items():
         res["text_" + k] = v
     s_i2t, s_t2i = clip_logits(stu["visual"]["last_representation"], stu["text"]["last_representation"])
-    if "soft_label" in names:
+    if "soft_label" in names or "cos_diff" in names:
         t_i2t, t_t2i = clip_logits(tea["visual"]["last_representation"], tea["text"]["last_representation"])
     for n in names:
         if n == "hard_label":
@@ -112,6 +152,8 @@ def two_tower(names, scale, percent, temperature, stu: Dict, tea: Dict):
         elif n == "soft_label":
             assert temperature
             res[n] = 0.5 * (soft_label(s_i2t, t_i2t, temperature) + soft_label(s_t2i, t_t2i, temperature))
+        elif n == "cos_diff":
+            res[n] = 0.5 * (cos_diff(s_i2t, t_i2t) + cos_diff(s_t2i, t_t2i))
     loss = 0.5 * (il + tl)
     for n, sc in scale.items():
         if n in IMAGE_TEXT_LOSS:

@@ -5,7 +5,7 @@ TAG=${1:-r01}
 OUT=gpurun_out
 mkdir -p $OUT
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $OUT/smi_$TAG.txt 2>&1
-timeout 600 python -m pytest tests/test_gpu_streaming.py -m gpu -q --timeout 300 > $OUT/pytest_streaming_$TAG.log 2>&1
+timeout 600 python -m pytest tests/test_gpu_streaming.py tests/test_gpu_widened.py -m gpu -q --timeout 300 > $OUT/pytest_streaming_$TAG.log 2>&1
 echo "streaming exit $?" | tee -a $OUT/summary_$TAG.txt
 timeout 300 python -m pytest tests/test_gpu_contrastive.py -m gpu -q --timeout 120 -k "similarity" > $OUT/pytest_similarity_$TAG.log 2>&1
 echo "similarity exit $?" | tee -a $OUT/summary_$TAG.txt

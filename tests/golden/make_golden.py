@@ -22,8 +22,8 @@ sys.dont_write_bytecode = True
 sys.path.insert(0, REF)
 with contextlib.redirect_stdout(io.StringIO()):
     from model._loss import LossCalculator                      # noqa: E402
-    from model.loss_component import (AttentionProbsKL, EmbedMSELoss, HardLabel, HiddenMSE,  # noqa: E402
-                                      SoftLabel)
+    from model.loss_component import (AttentionProbsKL, AttentionProbsMSE, AttentionScoreMSE, CLIPCosDiff,  # noqa: E402
+                                      EmbedMSELoss, HardLabel, HiddenMSE, OutCosLoss, OutL1Loss, SoftLabel)
     from model.component.clip_model import CLIPModel             # noqa: E402
     from model.component.output import (CLIPOutput, ControlOutput, TextTransformerOutput,  # noqa: E402
                                         VisionTransformerOutput)
@@ -158,6 +158,37 @@ clip_case("clip_b40_d64_t4", 40, 64, 4.0)
 clip_case("clip_b130_d72_t1", 130, 72, 1.0)
 
 
+# ---- section 8f widening: out_l1 / out_cos / attention mean MSE / cos_diff ---------------------------------------
+mse_case("out_l1", OutL1Loss(), [bf16(9, 40)], [bf16(9, 40)], as_list=False)
+mse_case("out_l1_with_ties", OutL1Loss(), [bf16(4, 16).round()], [bf16(4, 16).round()], as_list=False)   # exact zeros: sign(0) = 0
+mse_case("out_cos", OutCosLoss(), [bf16(9, 40)], [bf16(9, 40)], as_list=False)
+mse_case("attn_probs_mse", AttentionProbsMSE(), [probs(3, 4, 7) for _ in range(2)], [probs(3, 2, 7) for _ in range(2)])
+mse_case("attn_score_mse", AttentionScoreMSE(), [bf16(2, 3, 6, 6) for _ in range(3)], [bf16(2, 3, 6, 6) for _ in range(2)])
+
+
+def cos_diff_case(name, n):
+    s = (bf16(n, n, scale=0.3)).clamp(-1, 1)
+    t = (s.float() + 0.2 * bf16(n, n).float()).to(torch.bfloat16)
+    mod = CLIPCosDiff()
+    out = {}
+    for dt, tag in ((torch.float32, "f32"), (torch.float64, "f64")):
+        a = s.to(dt).requires_grad_(True)
+        loss = mod(a, t.to(dt))
+        loss.backward()
+        out[f"loss_{tag}"] = loss.detach().numpy()
+        out[f"grad_{tag}"] = a.grad.numpy()
+        b = s.to(dt).requires_grad_(True)
+        loss_t = mod(b.T, t.to(dt).T)
+        loss_t.backward()
+        out[f"loss_T_{tag}"] = loss_t.detach().numpy()
+        out[f"grad_T_{tag}"] = b.grad.numpy()
+    save(name, stu=s.float().numpy(), tea=t.float().numpy(), **out)
+
+
+cos_diff_case("cos_diff_n17", 17)
+cos_diff_case("cos_diff_n64", 64)
+
+
 # ---- a7-a10 LossCalculator end to end --------------------------------------------------------------
 def tower(kind, b, heads, n, w, layers, tea_heads=None):
     cls = VisionTransformerOutput if kind == "image" else TextTransformerOutput
@@ -261,6 +292,17 @@ calc_case("calc_lclip_logits_only",
           "all",
           (tower("image", 36, 3, 6, 24, 1), tower("text", 36, 2, 7, 16, 1)),
           (tower("image", 36, 3, 6, 24, 1), tower("text", 36, 2, 7, 16, 1)))
+
+# the three shipped recipes (config/final_config/{image,text,l_clip}.yaml: loss_name lists)
+calc_case("calc_shipped_image", dict(loss_name=["out_l1", "out_cos"]), "image",
+          tower("image", 6, 3, 6, 24, 2), tower("image", 6, 3, 6, 24, 2))
+calc_case("calc_shipped_lclip", dict(loss_name=["out_l1", "out_cos", "cos_diff"]), "all",
+          (tower("image", 20, 3, 6, 24, 1), tower("text", 20, 2, 7, 16, 1)),
+          (tower("image", 20, 3, 6, 24, 1), tower("text", 20, 2, 7, 16, 1)))
+calc_case("calc_attn_mse_mix",
+          dict(loss_name=["attention_probs_mse", "attention_probs_kl", "hidden_rep_mse", "out_l1"],
+               loss_scale={"attention_probs_mse": 3.0}),
+          "image", tower("image", 3, 4, 6, 24, 2), tower("image", 3, 2, 6, 24, 2))
 
 # ---- host-logic facts (flags, errors) -------------------------------------------------------------
 facts = {}

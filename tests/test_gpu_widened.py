@@ -1,0 +1,139 @@
+"""SURVEY.md section 8f widening on the GPU: the losses of the three shipped recipes (out_l1, out_cos, cos_diff) and the
+attention-map / attention-score MSE siblings, against the reference-generated golden fixtures and the oracle.
+Tolerances as in test_gpu_streaming.py (loss 1e-4, fp32 gradients 1e-3, bf16-stored gradients 4e-3)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden, numbered, rel_l2
+from oracle import closed_form as cf
+
+pytestmark = pytest.mark.gpu
+LOSS_RTOL, GRAD_RTOL, GRAD_BF16_STORAGE_RTOL = 1e-4, 1e-3, 4e-3
+
+
+def dev(x, dtype=torch.bfloat16, grad=False):
+    return torch.tensor(np.asarray(x), device="cuda").to(dtype).requires_grad_(grad)
+
+
+@pytest.mark.parametrize("name,cls", [("out_l1", "OutL1Loss"), ("out_l1_with_ties", "OutL1Loss"), ("out_cos", "OutCosLoss")])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+def test_out_losses_golden(cuda_device, name, cls, dtype):
+    import distillclip_b200.model as m
+    g = golden(name)
+    s, t = dev(g["stu0"], dtype, True), dev(g["tea0"], dtype)
+    loss = getattr(m, cls)()(s, t)
+    loss.backward()
+    assert float(loss.detach()) == pytest.approx(float(g["loss_f64"]), rel=LOSS_RTOL)
+    tol = GRAD_RTOL if dtype == torch.float32 else GRAD_BF16_STORAGE_RTOL
+    assert rel_l2(s.grad.float().cpu().numpy(), g["grad0_f64"]) <= tol
+    if name == "out_l1_with_ties":      # sign(0) = 0 exactly where student == teacher
+        ties = g["stu0"] == g["tea0"]
+        assert ties.any() and float(s.grad.float().cpu().numpy()[ties].__abs__().max()) == 0.0
+
+
+@pytest.mark.parametrize("name,cls", [("attn_probs_mse", "AttentionProbsMSE"), ("attn_score_mse", "AttentionScoreMSE")])
+def test_attention_mean_mse_golden(cuda_device, name, cls):
+    import distillclip_b200.model as m
+    g = golden(name)
+    stu, tea = [dev(x, torch.float32, True) for x in numbered(g, "stu")], [dev(x, torch.float32) for x in numbered(g, "tea")]
+    loss = getattr(m, cls)()(stu, tea)
+    loss.backward()
+    assert float(loss.detach()) == pytest.approx(float(g["loss_f64"]), rel=LOSS_RTOL)
+    for i, s in enumerate(stu):
+        ref = g[f"grad{i}_f64"]
+        if np.all(ref == 0):
+            assert s.grad is None or float(s.grad.abs().max()) == 0.0
+        else:
+            assert rel_l2(s.grad.cpu().numpy(), ref) <= GRAD_RTOL
+
+
+@pytest.mark.parametrize("b,h,n", [(4, 12, 50), (3, 8, 77)])
+def test_attention_mean_mse_random_bf16(cuda_device, b, h, n):
+    from distillclip_b200.model import AttentionProbsMSE
+    gen = torch.Generator().manual_seed(3)
+    stu = [torch.softmax(torch.randn(b, h, n, n, generator=gen), -1).to(torch.bfloat16) for _ in range(2)]
+    tea = [torch.softmax(torch.randn(b, h, n, n, generator=gen), -1).to(torch.bfloat16) for _ in range(2)]
+    ref_loss, ref_grads = cf.attention_mean_mse([s.float().numpy() for s in stu], [t.float().numpy() for t in tea])
+    ds = [s.cuda().requires_grad_(True) for s in stu]
+    loss = AttentionProbsMSE()(ds, [t.cuda() for t in tea])
+    loss.backward()
+    assert float(loss.detach()) == pytest.approx(ref_loss, rel=LOSS_RTOL)
+    for s, r in zip(ds, ref_grads):
+        assert rel_l2(s.grad.float().cpu().numpy(), r) <= GRAD_BF16_STORAGE_RTOL
+
+
+@pytest.mark.parametrize("name", ["cos_diff_n17", "cos_diff_n64"])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_cos_diff_golden(cuda_device, name, dtype):
+    """CLIPCosDiff on materialised logits and on the `.T` view; the off-diagonal index construction (get_neg_element)
+    is exact: gradients are compared entry by entry."""
+    from distillclip_b200.model import CLIPCosDiff
+    g = golden(name)
+    s, t = dev(g["stu"], dtype, True), dev(g["tea"], dtype)      # fixture values are bf16-exact
+    loss = CLIPCosDiff()(s, t)
+    loss.backward()
+    assert float(loss.detach()) == pytest.approx(float(g["loss_f64"]), rel=LOSS_RTOL)
+    assert np.allclose(s.grad.float().cpu().numpy(), g["grad_f64"], rtol=GRAD_BF16_STORAGE_RTOL, atol=0)
+    s.grad = None
+    loss = CLIPCosDiff()(s.T, t.T)
+    loss.backward()
+    assert float(loss.detach()) == pytest.approx(float(g["loss_T_f64"]), rel=LOSS_RTOL)
+    assert np.allclose(s.grad.float().cpu().numpy(), g["grad_T_f64"], rtol=GRAD_BF16_STORAGE_RTOL, atol=0)
+
+
+def _tower(g, prefix, cls, grad):
+    kw = {}
+    for f in ("last_representation", "embedding"):
+        kw[f] = dev(g[f"{prefix}.{f}"], grad=grad)
+    for f in ("attention_probs", "representations"):
+        kw[f] = [dev(x, grad=grad) for x in numbered(g, f"{prefix}.{f}.")]
+    return cls(**kw)
+
+
+def _leaves(t):
+    return [t.last_representation, *t.attention_probs, *t.representations, t.embedding]
+
+
+def _check_calc(g, loss, res, leaves):
+    assert float(loss.detach()) == pytest.approx(float(g["loss_f64"]), rel=LOSS_RTOL)
+    for k, v in res.items():
+        assert float(v.detach()) == pytest.approx(float(g[f"res.{k}_f64"]), rel=LOSS_RTOL), k
+    assert set(res) == {k[4:-4] for k in g if k.startswith("res.") and k.endswith("_f64")}
+    for i, leaf in enumerate(leaves):
+        key = f"grad{i}_f64"
+        if key in g:
+            assert rel_l2(leaf.grad.float().cpu().numpy(), g[key]) <= GRAD_BF16_STORAGE_RTOL, key
+        else:
+            assert leaf.grad is None
+
+
+@pytest.mark.parametrize("name,kwargs", [
+    ("calc_shipped_image", dict(loss_name=["out_l1", "out_cos"])),
+    ("calc_attn_mse_mix", dict(loss_name=["attention_probs_mse", "attention_probs_kl", "hidden_rep_mse", "out_l1"],
+                               loss_scale={"attention_probs_mse": 3.0}))])
+def test_shipped_one_tower_recipes(cuda_device, name, kwargs):
+    """config/final_config/image.yaml and text.yaml ship loss_name = ['out_l1', 'out_cos']."""
+    from distillclip_b200.model import LossCalculator, VisionTransformerOutput
+    g = golden(name)
+    stu, tea = _tower(g, "stu", VisionTransformerOutput, True), _tower(g, "tea", VisionTransformerOutput, False)
+    loss, res = LossCalculator(**kwargs)(stu, tea, "image")
+    loss.backward()
+    _check_calc(g, loss, res, _leaves(stu))
+
+
+def test_shipped_lclip_recipe(cuda_device):
+    """config/final_config/l_clip.yaml ships ['out_l1', 'out_cos', 'cos_diff']; cos_diff reads the caller's logits
+    (CLIPModel.forward, reference clip_model.py:36-44), gradients flow back through them to the embeddings."""
+    from distillclip_b200.model import (CLIPOutput, LossCalculator, TextTransformerOutput, VisionTransformerOutput)
+    g = golden("calc_shipped_lclip")
+    sv, stx = _tower(g, "stu.visual", VisionTransformerOutput, True), _tower(g, "stu.text", TextTransformerOutput, True)
+    tv, ttx = _tower(g, "tea.visual", VisionTransformerOutput, False), _tower(g, "tea.text", TextTransformerOutput, False)
+
+    def clip_out(v, x):
+        a, b = v.last_representation.float(), x.last_representation.float()
+        lg = (a / a.norm(dim=1, keepdim=True)) @ (b / b.norm(dim=1, keepdim=True)).t()
+        return CLIPOutput(visual_output=v, text_output=x, i2t_logits=lg, t2i_logits=lg.T)
+    loss, res = LossCalculator(["out_l1", "out_cos", "cos_diff"])(clip_out(sv, stx), clip_out(tv, ttx), "all")
+    loss.backward()
+    _check_calc(g, loss, res, _leaves(sv) + _leaves(stx))

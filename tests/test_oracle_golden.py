@@ -164,3 +164,60 @@ def test_calculator_port(name, kind):
     for k, v in res.items():
         assert float(v.detach()) == pytest.approx(float(g[f"res.{k}_f32"]), rel=2e-6), k
     assert set(res.keys()) == {k[4:-4] for k in g if k.startswith("res.") and k.endswith("_f32")}
+
+
+# ---- section 8f widening -------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name,fn", [("out_l1", "out_l1"), ("out_l1_with_ties", "out_l1"), ("out_cos", "out_cos")])
+def test_out_losses(name, fn):
+    g = golden(name)
+    loss, grad = getattr(cf, fn)(g["stu0"], g["tea0"])
+    assert abs(loss - g["loss_f64"]) <= 1e-12 * max(abs(g["loss_f64"]), 1e-30)
+    assert np.allclose(grad, g["grad0_f64"], rtol=1e-10, atol=1e-18)
+    t = getattr(tp, fn)(torch.tensor(g["stu0"]), torch.tensor(g["tea0"]))
+    assert t.item() == pytest.approx(float(g["loss_f32"]), rel=1e-6)
+
+
+@pytest.mark.parametrize("name", ["attn_probs_mse", "attn_score_mse"])
+def test_attention_mean_mse(name):
+    g = golden(name)
+    stu, tea = numbered(g, "stu"), numbered(g, "tea")
+    loss, grads = cf.attention_mean_mse(stu, tea)
+    assert abs(loss - g["loss_f64"]) <= 1e-12 * abs(g["loss_f64"])
+    for i, gr in enumerate(grads):
+        assert np.allclose(gr, g[f"grad{i}_f64"], rtol=1e-10, atol=1e-20)
+    t = tp.attention_mean_mse([torch.tensor(x) for x in stu], [torch.tensor(x) for x in tea])
+    assert t.item() == pytest.approx(float(g["loss_f32"]), rel=1e-6)
+
+
+@pytest.mark.parametrize("name", ["cos_diff_n17", "cos_diff_n64"])
+def test_cos_diff(name):
+    g = golden(name)
+    loss, grad = cf.cos_diff(g["stu"], g["tea"])
+    assert loss == pytest.approx(float(g["loss_f64"]), rel=1e-12)
+    assert np.allclose(grad, g["grad_f64"], rtol=1e-12, atol=0)
+    loss_t, grad_t = cf.cos_diff(g["stu"].T, g["tea"].T)
+    assert loss_t == pytest.approx(float(g["loss_T_f64"]), rel=1e-12)
+    assert np.allclose(grad_t.T, g["grad_T_f64"], rtol=1e-12, atol=0)
+    assert tp.cos_diff(torch.tensor(g["stu"]), torch.tensor(g["tea"])).item() == pytest.approx(float(g["loss_f32"]), rel=1e-6)
+
+
+@pytest.mark.parametrize("name,kind,temperature", [("calc_shipped_image", "one", None), ("calc_shipped_lclip", "two", None),
+                                                   ("calc_attn_mse_mix", "one", None)])
+def test_calculator_port_shipped_recipes(name, kind, temperature):
+    """The loss lists of config/final_config/{image,text,l_clip}.yaml through the torch port."""
+    g = golden(name)
+    names = [str(k) for k in g["scale_keys"]]
+    scale = dict(zip(names, g["scale_vals"].tolist()))
+    percent = dict(zip([str(k) for k in g["percent_keys"]], g["percent_vals"].tolist()))
+
+    def to_t(d):
+        return {k: [torch.tensor(x) for x in v] if isinstance(v, list) else torch.tensor(v) for k, v in d.items()}
+    if kind == "one":
+        loss, res = tp.one_tower(names, scale, percent, temperature, to_t(_tower_from(g, "stu")), to_t(_tower_from(g, "tea")))
+    else:
+        stu = {"visual": to_t(_tower_from(g, "stu.visual")), "text": to_t(_tower_from(g, "stu.text"))}
+        tea = {"visual": to_t(_tower_from(g, "tea.visual")), "text": to_t(_tower_from(g, "tea.text"))}
+        loss, res = tp.two_tower(names, scale, percent, temperature, stu, tea)
+    assert float(loss) == pytest.approx(float(g["loss_f32"]), rel=2e-6)
+    for k, v in res.items():
+        assert float(v) == pytest.approx(float(g[f"res.{k}_f32"]), rel=2e-6), k
