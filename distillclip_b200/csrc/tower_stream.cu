@@ -37,7 +37,10 @@ struct TowerParams {
     int n_seg, n_terms;
     long long total_tiles;
     float scale[kTowerMaxTerms], percent[kTowerMaxTerms];
-    double* partials;      // [n_terms][gridDim.x]
+    double* partials;      // [n_terms][partial_stride]
+    int partial_stride;
+    unsigned int ext_mask; // terms whose partials were written by an earlier kernel (attn_tma.cu): ext_count entries each
+    int ext_count;
     unsigned int* ticket;
     float* out;            // [n_terms + 1]
     TowerSeg seg[kTowerMaxSeg];
@@ -57,7 +60,7 @@ __global__ void __launch_bounds__(kStreamThreads, 4) tower_stream_kernel(const _
     auto flush = [&]() {
         const double total = block_sum(cur);
         if (tid == 0) {
-            p.partials[(size_t)cur_term * gridDim.x + blockIdx.x] = total;
+            p.partials[(size_t)cur_term * p.partial_stride + blockIdx.x] = total;
             written |= 1u << cur_term;
         }
         __syncthreads();
@@ -103,7 +106,7 @@ __global__ void __launch_bounds__(kStreamThreads, 4) tower_stream_kernel(const _
     __shared__ bool is_last;
     if (tid == 0)
         for (int q = 0; q < p.n_terms; ++q)
-            if (!(written & (1u << q))) p.partials[(size_t)q * gridDim.x + blockIdx.x] = 0.0;
+            if (!((written | p.ext_mask) & (1u << q))) p.partials[(size_t)q * p.partial_stride + blockIdx.x] = 0.0;
     if (tid == 0) {
         __threadfence();
         const unsigned int ticket = atomicAdd(p.ticket, 1u);
@@ -114,9 +117,10 @@ __global__ void __launch_bounds__(kStreamThreads, 4) tower_stream_kernel(const _
     __threadfence();
     __shared__ double term_sum[kTowerMaxTerms];
     for (int q = 0; q < p.n_terms; ++q) {
-        const volatile double* src = p.partials + (size_t)q * gridDim.x;
+        const volatile double* src = p.partials + (size_t)q * p.partial_stride;
+        const unsigned int cnt = (p.ext_mask & (1u << q)) ? (unsigned int)p.ext_count : gridDim.x;
         double v = 0.0;
-        for (unsigned int i = tid; i < gridDim.x; i += kStreamThreads) v += src[i];     // fixed assignment, fixed tree
+        for (unsigned int i = tid; i < cnt; i += kStreamThreads) v += src[i];     // fixed assignment, fixed tree
         v = block_sum(v);
         if (tid == 0) term_sum[q] = v;
         __syncthreads();
@@ -160,15 +164,20 @@ extern "C" int dcb_tower_fwd_bwd(int n_seg, const int32_t* kind, const int32_t* 
                                  const int64_t* batch, const int32_t* stu_heads, const int32_t* tea_heads,
                                  const int64_t* positions, const int32_t* divisor, const float* grad_scale, int n_terms,
                                  const float* scale, const float* percent, int in_dtype, int grad_dtype,
-                                 double* partials, uint32_t* ticket, float* out, void* stream) {
+                                 double* partials, int partial_stride, uint32_t ext_mask, int ext_count,
+                                 uint32_t* ticket, float* out, void* stream) {
     using namespace dcb;
-    DCB_REQUIRE(n_seg >= 1 && n_seg <= kTowerMaxSeg, "n_seg=%d out of range [1,%d]", n_seg, kTowerMaxSeg);
+    DCB_REQUIRE(n_seg >= 0 && n_seg <= kTowerMaxSeg, "n_seg=%d out of range [0,%d]", n_seg, kTowerMaxSeg);
+    DCB_REQUIRE(partial_stride >= dcb_tower_grid() && ext_count <= partial_stride, "partial_stride too small");
     DCB_REQUIRE(n_terms >= 1 && n_terms <= kTowerMaxTerms, "n_terms=%d out of range [1,%d]", n_terms, kTowerMaxTerms);
     DCB_REQUIRE(partials && ticket && out, "partials / ticket / out must not be NULL");
     TowerParams p{};
     p.n_seg = n_seg;
     p.n_terms = n_terms;
     p.partials = partials;
+    p.partial_stride = partial_stride;
+    p.ext_mask = ext_mask;
+    p.ext_count = ext_count;
     p.ticket = ticket;
     p.out = out;
     for (int q = 0; q < n_terms; ++q) {

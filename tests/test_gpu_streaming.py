@@ -157,6 +157,40 @@ def test_unexpected_upstream_after_fp16_scaling(cuda_device):
     assert rel_l2(s.grad.cpu().numpy(), 0.5 * ref_grads[0]) <= 1e-5
 
 
+@pytest.mark.parametrize("b,hs,ht,n,layers", [(5, 12, 12, 50, 4), (3, 8, 8, 77, 2), (150, 2, 4, 17, 1), (2, 24, 12, 50, 1)])
+@pytest.mark.parametrize("use_tma", [True, False])
+def test_tower_attention_tma_vs_oracle(cuda_device, b, hs, ht, n, layers, use_tma):
+    """LossCalculator tower path with the TMA-staged attention kernel (positions >= 256: N = 50, 77, 17) and with
+    per-thread loads, both against the oracle: unaligned head rows, shifted last chunk, more CTAs than tiles."""
+    from distillclip_b200 import ops
+    from distillclip_b200.model import LossCalculator, VisionTransformerOutput
+    gen = torch.Generator().manual_seed(23)
+    stu = [torch.softmax(torch.randn(b, hs, n, n, generator=gen), -1).to(torch.bfloat16) for _ in range(layers)]
+    tea = [torch.softmax(torch.randn(b, ht, n, n, generator=gen), -1).to(torch.bfloat16) for _ in range(layers)]
+    hid_s = [torch.randn(b, n, 64, generator=gen).to(torch.bfloat16) for _ in range(layers)]
+    hid_t = [torch.randn(b, n, 64, generator=gen).to(torch.bfloat16) for _ in range(layers)]
+    kl, kl_g = cf.attention_probs_kl([x.float().numpy() for x in stu], [x.float().numpy() for x in tea])
+    am, am_g = cf.attention_mean_mse([x.float().numpy() for x in stu], [x.float().numpy() for x in tea])
+    hm, hm_g = cf.hidden_mse([x.float().numpy() for x in hid_s], [x.float().numpy() for x in hid_t])
+    old = ops.USE_ATTN_TMA
+    ops.USE_ATTN_TMA = use_tma
+    try:
+        for names, want, want_g in ((["attention_probs_kl", "hidden_rep_mse"], 0.5 * (kl + hm), kl_g),
+                                    (["attention_probs_mse"], am, am_g)):
+            ds = [x.cuda().requires_grad_(True) for x in stu]
+            dh = [x.cuda().requires_grad_(True) for x in hid_s]
+            out_s = VisionTransformerOutput(attention_probs=ds, representations=dh)
+            out_t = VisionTransformerOutput(attention_probs=[x.cuda() for x in tea], representations=[x.cuda() for x in hid_t])
+            loss, res = LossCalculator(names)(out_s, out_t, "image")
+            loss.backward()
+            assert float(loss.detach()) == pytest.approx(want, rel=LOSS_RTOL)
+            w = 1.0 / len(names)
+            for x, r in zip(ds, want_g):
+                assert rel_l2(x.grad.float().cpu().numpy(), w * r) <= GRAD_BF16_STORAGE_RTOL
+    finally:
+        ops.USE_ATTN_TMA = old
+
+
 def test_upstream_gradient_is_applied(cuda_device):
     """loss * 3 backward: the one-pass gradients are rescaled on the device by the true upstream value."""
     from distillclip_b200.model import HiddenMSE
