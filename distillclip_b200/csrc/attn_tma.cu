@@ -5,15 +5,16 @@
 //
 // Why: a head row of an [B, H, N, N] bf16 map starts every N*N*2 bytes -- 5000 B for N = 50, 11858 B for N = 77 -- so
 // per-thread vector loads are limited to 8 B resp. 2 B.  A whole SAMPLE ([H*N*N] elements) is 16-byte
-// aligned, so the maps are described to TMA as 2-D tensors [B, H*P] and every (head, position chunk) is fetched as a
-// box {256 elements, 1 sample} at the arbitrary element offset h*P + p0: the copy engine does the unaligned gather,
-// the SM only sees shared memory.  Per tile (one sample, `pc` positions): producer warp issues (Hs + Ht) * pc/256
-// TMA loads into a 3-stage ring; 8 compute warps reduce over heads from shared memory (one position pair per thread),
-// write the (head-independent) gradient row once to shared memory, and one elected thread stores it to all Hs head
-// rows of the gradient tensor with TMA.  The last chunk of a sample is shifted back to end at P (overlapping positions
-// are recomputed and rewritten with identical values; their loss contribution is masked).
+// aligned, so the maps are described to TMA as 2-D tensors [B, H*P] and every (head, position chunk) is fetched as
+// boxes {256 elements, 1 sample} starting at the element offset (h*P + p0) rounded DOWN to 8 elements (TMA needs a
+// 16-byte aligned box start: an unaligned one raises an illegal-instruction fault, measured); the residue m_h < 8 is an
+// offset into the shared-memory row, so the SM only ever sees shared memory.  Per tile (one sample, pc - 8 positions):
+// the producer warp issues the loads of all Hs + Ht head rows into a 3-stage ring; 8 compute warps reduce over heads from
+// shared memory (one position pair per thread) and write the head-independent gradient to every student head row with
+// 4-byte (2-byte on odd element offsets) global stores, 128 contiguous bytes per warp instruction.
 //
-// Algorithmic traffic: read s, read t, write ds = 6 B per student element (bf16), all through the copy engine.
+// Algorithmic traffic: read s, read t, write ds = 6 B per student element (bf16); the 2/3 that are reads go through
+// the copy engine in 512-byte requests.
 #include "tc_common.cuh"
 
 namespace dcb {
@@ -26,12 +27,13 @@ constexpr int kMaxLayers = 8;
 }  // namespace atma
 
 struct AttnTmaLayer {
-    CUtensorMap map_s, map_t, map_g;      // [B, Hs*P], [B, Ht*P], [B, Hs*P]
+    CUtensorMap map_s, map_t;             // [B, Hs*P], [B, Ht*P]
+    void* grad;                           // [B, Hs, P] or nullptr
     int batch, hs, ht, positions;
     int chunks;                           // position chunks per sample
     long long tile_begin;
     float inv_hs, inv_ht, val_coef, grad_coef;
-    int term, has_grad;
+    int term;
 };
 struct AttnTmaParams {
     int n_layers, mode;                   // mode 0 = KL, 1 = MSE
@@ -44,14 +46,6 @@ struct AttnTmaParams {
     AttnTmaLayer layer[atma::kMaxLayers];
 };
 
-__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src_smem, int x, int y) {
-    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
-                 ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src_smem), "r"(x), "r"(y) : "memory");
-}
-__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void tma_store_wait_read_prev() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
-__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-
 template <typename T>
 __global__ void __launch_bounds__(atma::kThreads, 1) attn_tma_kernel(const __grid_constant__ AttnTmaParams p) {
     using namespace atma;
@@ -60,12 +54,11 @@ __global__ void __launch_bounds__(atma::kThreads, 1) attn_tma_kernel(const __gri
     const uint32_t smem_base = (smem_u32(smem_raw) + 127u) & ~127u;
     uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
     const int in_stage_bytes = p.max_rows * p.pc * 2;                 // [rows][pc] 16-bit
-    const int out_bytes = p.pc * 2;                                   // one gradient row (same for every head)
     const uint32_t in_ring = smem_base;
-    const uint32_t out_buf = in_ring + kStages * in_stage_bytes;      // 2 buffers
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_gen + kStages * in_stage_bytes + 2 * out_bytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_gen + kStages * in_stage_bytes);
     const uint32_t bar_full = smem_u32(bars), bar_empty = bar_full + 8 * kStages;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int span = p.pc - 8;                                        // positions per tile
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; ++s) {
@@ -87,18 +80,24 @@ __global__ void __launch_bounds__(atma::kThreads, 1) attn_tma_kernel(const __gri
                 const AttnTmaLayer& L = p.layer[k];
                 const long long lt = tile - L.tile_begin;
                 const int b = (int)(lt / L.chunks), c = (int)(lt % L.chunks);
-                int p0 = c * p.pc;
-                if (p0 + p.pc > L.positions) p0 = L.positions - p.pc;          // shifted last chunk
+                const int p0 = c * span;
+                const int len = min(span, L.positions - p0);
                 mbar_wait(bar_empty + 8 * stage, phase ^ 1);
                 const uint32_t dst = in_ring + stage * in_stage_bytes;
                 const uint32_t full = bar_full + 8 * stage;
-                mbar_arrive_expect_tx(full, (L.hs + L.ht) * p.pc * 2);
-                for (int h = 0; h < L.hs; ++h)
-                    for (int x = 0; x < p.pc; x += kBox)
-                        tma_load_2d(dst + (h * p.pc + x) * 2, &L.map_s, full, h * L.positions + p0 + x, b);
-                for (int h = 0; h < L.ht; ++h)
-                    for (int x = 0; x < p.pc; x += kBox)
-                        tma_load_2d(dst + ((L.hs + h) * p.pc + x) * 2, &L.map_t, full, h * L.positions + p0 + x, b);
+                int boxes = 0;
+                for (int h = 0; h < L.hs + L.ht; ++h) {
+                    const int hh = h < L.hs ? h : h - L.hs;
+                    boxes += (((hh * L.positions + p0) & 7) + len + kBox - 1) / kBox;
+                }
+                mbar_arrive_expect_tx(full, boxes * kBox * 2);
+                for (int h = 0; h < L.hs + L.ht; ++h) {
+                    const bool stu = h < L.hs;
+                    const int e0 = (stu ? h : h - L.hs) * L.positions + p0;
+                    const int a0 = e0 & ~7, need = (e0 & 7) + len;
+                    for (int x = 0; x < need; x += kBox)
+                        tma_load_2d(dst + (h * p.pc + x) * 2, stu ? &L.map_s : &L.map_t, full, a0 + x, b);
+                }
                 if (++stage == kStages) { stage = 0; phase ^= 1; }
             }
         }
@@ -107,7 +106,7 @@ __global__ void __launch_bounds__(atma::kThreads, 1) attn_tma_kernel(const __gri
         const int ct = threadIdx.x - 32;
         int stage = 0;
         uint32_t phase = 0;
-        int k = 0, it = 0;
+        int k = 0;
         double cur = 0.0;
         int cur_term = -1;
         unsigned int written = 0;               // thread ct == 0: terms whose partial this CTA has written
@@ -125,7 +124,7 @@ __global__ void __launch_bounds__(atma::kThreads, 1) attn_tma_kernel(const __gri
             asm volatile("bar.sync 1, 256;" ::: "memory");
             cur = 0.0;
         };
-        for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+        for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
             while (k + 1 < p.n_layers && tile >= p.layer[k + 1].tile_begin) ++k;
             const AttnTmaLayer& L = p.layer[k];
             if (L.term != cur_term) {
@@ -134,29 +133,27 @@ __global__ void __launch_bounds__(atma::kThreads, 1) attn_tma_kernel(const __gri
             }
             const long long lt = tile - L.tile_begin;
             const int b = (int)(lt / L.chunks), c = (int)(lt % L.chunks);
-            int p0 = c * p.pc;
-            const int fresh_from = p0;                       // positions below this were counted by the previous chunk
-            if (p0 + p.pc > L.positions) p0 = L.positions - p.pc;
+            const int p0 = c * span;
+            const int len = min(span, L.positions - p0);
             mbar_wait(bar_full + 8 * stage, phase);
-            const uint8_t* in = smem_gen + stage * in_stage_bytes;
-            uint8_t* out = smem_gen + kStages * in_stage_bytes + (it & 1) * out_bytes;
-            // the TMA stores that read this output buffer two tiles ago must have finished reading (<= 1 group pending)
-            if (ct == 0) tma_store_wait_read_prev();
-            asm volatile("bar.sync 1, 256;" ::: "memory");
+            const T* in = reinterpret_cast<const T*>(smem_gen + stage * in_stage_bytes);
+            T* gbase = L.grad ? static_cast<T*>(L.grad) + (size_t)b * L.hs * L.positions + p0 : nullptr;
             float acc = 0.f;
-            for (int x = 2 * ct; x < p.pc; x += 512) {
+            for (int x = 2 * ct; x < len; x += 512) {
+                const bool two = x + 1 < len;
                 float s0 = 0.f, s1 = 0.f, t0 = 0.f, t1 = 0.f;
-                for (int h = 0; h < L.hs; ++h) {
+                for (int h = 0; h < L.hs + L.ht; ++h) {
+                    const bool stu = h < L.hs;
+                    const int m = ((stu ? h : h - L.hs) * L.positions + p0) & 7;
+                    const T* row = in + h * p.pc + m + x;
                     float a, bb;
-                    unpack2<T>(*reinterpret_cast<const uint32_t*>(in + (h * p.pc + x) * 2), a, bb);
-                    s0 += a;
-                    s1 += bb;
-                }
-                for (int h = 0; h < L.ht; ++h) {
-                    float a, bb;
-                    unpack2<T>(*reinterpret_cast<const uint32_t*>(in + ((L.hs + h) * p.pc + x) * 2), a, bb);
-                    t0 += a;
-                    t1 += bb;
+                    if ((m & 1) == 0) {
+                        unpack2<T>(*reinterpret_cast<const uint32_t*>(row), a, bb);
+                    } else {
+                        a = Elem<T>::to_f(row[0]);
+                        bb = Elem<T>::to_f(row[1]);
+                    }
+                    if (stu) { s0 += a; s1 += bb; } else { t0 += a; t1 += bb; }
                 }
                 float g[2];
                 const float sm[2] = {s0 * L.inv_hs, s1 * L.inv_hs}, tm[2] = {t0 * L.inv_ht, t1 * L.inv_ht};
@@ -172,24 +169,25 @@ __global__ void __launch_bounds__(atma::kThreads, 1) attn_tma_kernel(const __gri
                         v = tl - tm[e] * logf(sm[e]);                                       // 0 * -inf -> NaN like the reference
                         g[e] = -L.grad_coef * (tm[e] / sm[e]);
                     }
-                    if (p0 + x + e >= fresh_from) acc += v;
+                    if (e == 0 || two) acc += v;
                 }
-                *reinterpret_cast<uint32_t*>(out + x * 2) = pack2<T>(g[0], g[1]);
+                if (gbase) {
+                    const uint32_t packed = pack2<T>(g[0], g[1]);
+                    for (int h = 0; h < L.hs; ++h) {
+                        T* dstp = gbase + (size_t)h * L.positions + x;
+                        if (two && (((size_t)h * L.positions + p0) & 1) == 0) {
+                            *reinterpret_cast<uint32_t*>(dstp) = packed;
+                        } else {
+                            dstp[0] = Elem<T>::from_f(g[0]);
+                            if (two) dstp[1] = Elem<T>::from_f(g[1]);
+                        }
+                    }
+                }
             }
             cur += (double)acc * (double)L.val_coef;
-            // input stage consumed
             __syncwarp();
-            if (lane == 0) mbar_arrive(bar_empty + 8 * stage);
+            if (lane == 0) mbar_arrive(bar_empty + 8 * stage);      // input stage consumed
             if (++stage == kStages) { stage = 0; phase ^= 1; }
-            // gradient row -> every student head row
-            fence_proxy_async_smem();
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-            if (ct == 0 && L.has_grad) {
-                const uint32_t src = out_buf + (it & 1) * out_bytes;
-                for (int h = 0; h < L.hs; ++h)
-                    for (int x = 0; x < p.pc; x += kBox) tma_store_2d(&L.map_g, src + x * 2, h * L.positions + p0 + x, b);
-                tma_store_commit();
-            }
         }
         if (cur_term >= 0) flush();
         if (ct == 0) {
@@ -199,7 +197,6 @@ __global__ void __launch_bounds__(atma::kThreads, 1) attn_tma_kernel(const __gri
                     p.partials[(size_t)p.layer[l].term * p.partial_stride + blockIdx.x] = 0.0;
                     written |= 1u << p.layer[l].term;
                 }
-            tma_store_wait_all();
         }
     }
 }
@@ -229,10 +226,11 @@ static int encode_flat_map(CUtensorMap* map, const void* base, uint64_t batch, u
     return 0;
 }
 
-// 1 if the TMA-staged kernel can take this layer: 16-bit elements, 16-byte aligned samples, positions >= 256
+// 1 if the TMA-staged kernel can take this layer: 16-bit elements, 16-byte aligned samples, enough positions to fill a box
 extern "C" int dcb_attn_tma_supported(int dtype, int64_t stu_heads, int64_t tea_heads, int64_t positions) {
-    return (dtype == DCB_BF16 || dtype == DCB_F16) && positions >= dcb::atma::kBox && (stu_heads * positions) % 8 == 0 &&
-           (tea_heads * positions) % 8 == 0 && stu_heads + tea_heads <= 64;
+    return (dtype == DCB_BF16 || dtype == DCB_F16) && positions >= 128 && (stu_heads * positions) % 8 == 0 &&
+           (tea_heads * positions) % 8 == 0 && stu_heads + tea_heads <= 64 && stu_heads * positions < (1ll << 31) &&
+           tea_heads * positions < (1ll << 31);
 }
 extern "C" int dcb_attn_tma_grid(void) { return dcb::kNumSMs; }
 
@@ -257,14 +255,16 @@ extern "C" int dcb_attn_tma_fwd_bwd(int n_layers, int mode, const int32_t* term,
     for (int k = 0; k < n_layers; ++k) {
         DCB_REQUIRE(stu[k] && tea[k] && batch[k] >= 1 && divisor[k] >= 1, "layer %d: bad arguments", k);
         DCB_REQUIRE(dcb_attn_tma_supported(dtype, stu_heads[k], tea_heads[k], positions[k]), "layer %d not supported by the TMA path", k);
-        DCB_REQUIRE(((uintptr_t)stu[k] | (uintptr_t)tea[k] | (uintptr_t)(grad_stu ? grad_stu[k] : nullptr)) % 16 == 0, "layer %d: 16-byte alignment", k);
+        DCB_REQUIRE(((uintptr_t)stu[k] | (uintptr_t)tea[k]) % 16 == 0 && (uintptr_t)(grad_stu ? grad_stu[k] : nullptr) % 4 == 0,
+                    "layer %d: inputs must be 16-byte aligned, gradients 4-byte aligned", k);
         DCB_REQUIRE(k == 0 || term[k] >= term[k - 1], "terms must be grouped");
         if (stu_heads[k] + tea_heads[k] > max_rows) max_rows = stu_heads[k] + tea_heads[k];
         if (positions[k] < min_pos) min_pos = positions[k];
     }
-    // positions per tile: as large as shared memory allows (fewer, longer bursts per head row), multiple of 256
+    // shared-memory row length per head (multiple of 256; 8 elements of it are alignment slack): as large as shared
+    // memory allows and the maps need (fewer, longer bursts per head row)
     int pc = 1024;
-    while (pc > atma::kBox && (pc > min_pos || (atma::kStages * max_rows * pc * 2 + 2 * pc * 2) > 200 * 1024)) pc -= atma::kBox;
+    while (pc > atma::kBox && (pc - atma::kBox >= min_pos + 8 || atma::kStages * max_rows * pc * 2 > 200 * 1024)) pc -= atma::kBox;
     p.pc = pc;
     p.max_rows = max_rows;
     long long tiles = 0;
@@ -272,17 +272,12 @@ extern "C" int dcb_attn_tma_fwd_bwd(int n_layers, int mode, const int32_t* term,
         AttnTmaLayer& L = p.layer[k];
         if (encode_flat_map(&L.map_s, stu[k], batch[k], (uint64_t)stu_heads[k] * positions[k])) return 1;
         if (encode_flat_map(&L.map_t, tea[k], batch[k], (uint64_t)tea_heads[k] * positions[k])) return 1;
-        L.has_grad = grad_stu && grad_stu[k];
-        if (L.has_grad) {
-            if (encode_flat_map(&L.map_g, grad_stu[k], batch[k], (uint64_t)stu_heads[k] * positions[k])) return 1;
-        } else {
-            L.map_g = L.map_s;
-        }
+        L.grad = grad_stu ? grad_stu[k] : nullptr;
         L.batch = (int)batch[k];
         L.hs = stu_heads[k];
         L.ht = tea_heads[k];
         L.positions = (int)positions[k];
-        L.chunks = (int)((positions[k] + pc - 1) / pc);
+        L.chunks = (int)((positions[k] + (pc - 8) - 1) / (pc - 8));
         L.tile_begin = tiles;
         tiles += (long long)batch[k] * L.chunks;
         L.inv_hs = 1.0f / (float)stu_heads[k];
@@ -298,7 +293,7 @@ extern "C" int dcb_attn_tma_fwd_bwd(int n_layers, int mode, const int32_t* term,
         }
     }
     p.total_tiles = tiles;
-    const int smem = 128 + atma::kStages * max_rows * pc * 2 + 2 * pc * 2 + 8 * 2 * atma::kStages + 64;
+    const int smem = 128 + atma::kStages * max_rows * pc * 2 + 8 * 2 * atma::kStages + 64;
     const long long grid = dcb_attn_tma_grid();      // fixed: the reduction reads exactly this many partials per term
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     static int max_set_bf = 0, max_set_h = 0;
