@@ -21,7 +21,9 @@ namespace dcb {
 
 namespace atma {
 constexpr int kBox = 256;                 // elements per TMA box (inner extent <= 256)
-constexpr int kThreads = 288;             // warp 0 producer + 8 compute warps
+constexpr int kComputeWarps = 16;
+constexpr int kComputeThreads = 32 * kComputeWarps;
+constexpr int kThreads = 32 + kComputeThreads;   // warp 0 producer + compute warps
 constexpr int kStages = 3;
 constexpr int kMaxLayers = 8;
 }  // namespace atma
@@ -63,7 +65,7 @@ __global__ void __launch_bounds__(atma::kThreads, 1) attn_tma_kernel(const __gri
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; ++s) {
             mbar_init(bar_full + 8 * s, 1);
-            mbar_init(bar_empty + 8 * s, 8);          // one arrive per compute warp
+            mbar_init(bar_empty + 8 * s, kComputeWarps);          // one arrive per compute warp
         }
         fence_barrier_init();
     }
@@ -102,29 +104,32 @@ __global__ void __launch_bounds__(atma::kThreads, 1) attn_tma_kernel(const __gri
             }
         }
     } else {
-        // ---------------------------------------------------------------- compute: 256 threads, position pairs
+        // ---------------------------------------------------------------- compute: position pairs
         const int ct = threadIdx.x - 32;
+        __shared__ int row_off[2][64];          // per tile parity: element offset of each head row inside the stage (h*pc + m_h)
+        __shared__ int row_par[2][64];          // store parity of student row h: 1 if (h*P + p0) is odd
+        int it = 0;
         int stage = 0;
         uint32_t phase = 0;
         int k = 0;
         double cur = 0.0;
         int cur_term = -1;
         unsigned int written = 0;               // thread ct == 0: terms whose partial this CTA has written
-        __shared__ double warp_part[8];
+        __shared__ double warp_part[kComputeWarps];
         auto flush = [&]() {
             double v = warp_sum(cur);
             if (lane == 0) warp_part[warp - 1] = v;
-            asm volatile("bar.sync 1, 256;" ::: "memory");
+            asm volatile("bar.sync 1, %0;" ::"n"(kComputeThreads) : "memory");
             if (ct == 0) {
                 double tot = 0.0;
-                for (int w = 0; w < 8; ++w) tot += warp_part[w];
+                for (int w = 0; w < kComputeWarps; ++w) tot += warp_part[w];
                 p.partials[(size_t)cur_term * p.partial_stride + blockIdx.x] = tot;
                 written |= 1u << cur_term;
             }
-            asm volatile("bar.sync 1, 256;" ::: "memory");
+            asm volatile("bar.sync 1, %0;" ::"n"(kComputeThreads) : "memory");
             cur = 0.0;
         };
-        for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
             while (k + 1 < p.n_layers && tile >= p.layer[k + 1].tile_begin) ++k;
             const AttnTmaLayer& L = p.layer[k];
             if (L.term != cur_term) {
@@ -135,25 +140,47 @@ __global__ void __launch_bounds__(atma::kThreads, 1) attn_tma_kernel(const __gri
             const int b = (int)(lt / L.chunks), c = (int)(lt % L.chunks);
             const int p0 = c * span;
             const int len = min(span, L.positions - p0);
+            const int hs = L.hs, ht = L.ht;
+            int* roff = row_off[it & 1];
+            int* rpar = row_par[it & 1];
+            if (ct < hs + ht) {
+                const int e0 = (ct < hs ? ct : ct - hs) * L.positions + p0;
+                roff[ct] = ct * p.pc + (e0 & 7);
+                rpar[ct] = e0 & 1;
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(kComputeThreads) : "memory");
             mbar_wait(bar_full + 8 * stage, phase);
             const T* in = reinterpret_cast<const T*>(smem_gen + stage * in_stage_bytes);
-            T* gbase = L.grad ? static_cast<T*>(L.grad) + (size_t)b * L.hs * L.positions + p0 : nullptr;
+            T* gbase = L.grad ? static_cast<T*>(L.grad) + (size_t)b * hs * L.positions + p0 : nullptr;
             float acc = 0.f;
-            for (int x = 2 * ct; x < len; x += 512) {
+            for (int x = 2 * ct; x < len; x += 2 * kComputeThreads) {
                 const bool two = x + 1 < len;
                 float s0 = 0.f, s1 = 0.f, t0 = 0.f, t1 = 0.f;
-                for (int h = 0; h < L.hs + L.ht; ++h) {
-                    const bool stu = h < L.hs;
-                    const int m = ((stu ? h : h - L.hs) * L.positions + p0) & 7;
-                    const T* row = in + h * p.pc + m + x;
+#pragma unroll 4
+                for (int h = 0; h < hs; ++h) {
+                    const T* row = in + roff[h] + x;
                     float a, bb;
-                    if ((m & 1) == 0) {
+                    if (rpar[h] == 0) {
                         unpack2<T>(*reinterpret_cast<const uint32_t*>(row), a, bb);
                     } else {
                         a = Elem<T>::to_f(row[0]);
                         bb = Elem<T>::to_f(row[1]);
                     }
-                    if (stu) { s0 += a; s1 += bb; } else { t0 += a; t1 += bb; }
+                    s0 += a;
+                    s1 += bb;
+                }
+#pragma unroll 4
+                for (int h = hs; h < hs + ht; ++h) {
+                    const T* row = in + roff[h] + x;
+                    float a, bb;
+                    if (rpar[h] == 0) {
+                        unpack2<T>(*reinterpret_cast<const uint32_t*>(row), a, bb);
+                    } else {
+                        a = Elem<T>::to_f(row[0]);
+                        bb = Elem<T>::to_f(row[1]);
+                    }
+                    t0 += a;
+                    t1 += bb;
                 }
                 float g[2];
                 const float sm[2] = {s0 * L.inv_hs, s1 * L.inv_hs}, tm[2] = {t0 * L.inv_ht, t1 * L.inv_ht};
@@ -173,9 +200,10 @@ __global__ void __launch_bounds__(atma::kThreads, 1) attn_tma_kernel(const __gri
                 }
                 if (gbase) {
                     const uint32_t packed = pack2<T>(g[0], g[1]);
-                    for (int h = 0; h < L.hs; ++h) {
+#pragma unroll 4
+                    for (int h = 0; h < hs; ++h) {
                         T* dstp = gbase + (size_t)h * L.positions + x;
-                        if (two && (((size_t)h * L.positions + p0) & 1) == 0) {
+                        if (two && rpar[h] == 0) {
                             *reinterpret_cast<uint32_t*>(dstp) = packed;
                         } else {
                             dstp[0] = Elem<T>::from_f(g[0]);

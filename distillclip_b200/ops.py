@@ -140,7 +140,9 @@ def _ticket(dev: torch.device) -> torch.Tensor:
 
 
 #: route eligible attention layers through the TMA-staged kernel (csrc/attn_tma.cu); False = per-thread loads only
-USE_ATTN_TMA = os.environ.get("DCB_ATTN_TMA", "1") != "0"
+#: default OFF: with 1-row boxes of 512 B the copy engine sustains ~1.5 TB/s here against ~4.2 TB/s for the per-thread
+#: loads (scripts/time_tower.py, image stage 123 us vs 44 us); kept as a tested option and a measured negative result
+USE_ATTN_TMA = os.environ.get("DCB_ATTN_TMA", "0") == "1"
 _ATTN_TMA_MAX_LAYERS = 8
 
 
