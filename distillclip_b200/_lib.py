@@ -33,7 +33,8 @@ SIGNATURES = {
     "dcb_row_inv_norm": [C.c_int, _vpp, _vpp, _i64p, C.c_int64, C.c_int, _vp],
     "dcb_transpose_norm_f16": [_vp, _vp, _vp, C.c_int64, C.c_int64, C.c_int64, C.c_int, _vp],
     "dcb_clip_row_stats": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int64, C.c_int64, C.c_int64, C.c_int64,
-                           C.c_int, C.c_float, _vp, _vp, _vp, _vp, _vp, _vp],
+                           C.c_int, C.c_float, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "dcb_clip_col_finish": [_vp, C.c_int64, _vp, C.c_int64, C.c_int64, C.c_float, C.c_int, _vp, _vp, _vp],
     "dcb_clip_losses": [_vp, _vp, C.c_int64, C.c_int64, C.c_int64, C.c_float, C.c_int, _vp, _vp, _vp],
     "dcb_clip_grad_coef": [_vp, C.c_int64, C.c_int64, C.c_float, C.c_int, _vp, _vp, _vp, _vp],
     "dcb_clip_row_grads": [_vp, _vp, _vp, _vp, _vp, C.c_int64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int64,
@@ -94,7 +95,7 @@ def load():
 
 
 # kernels launched per C-ABI call (bench.py reports the sum as "gpu_launches"); dcb_row_inv_norm launches one per matrix
-_LAUNCHES_PER_CALL = {"dcb_clip_row_stats": 2}
+_LAUNCHES_PER_CALL = {"dcb_clip_row_stats": 3}
 LAUNCHES = 0
 
 

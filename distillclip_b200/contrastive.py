@@ -54,16 +54,32 @@ class CudaEngine:
         return outs
 
     def row_stats(self, a_s, b_s, a_t, b_t, a_s_inv, b_s_inv, a_t_inv, b_t_inv, row_offset, temperature,
-                  dump=None):
+                  dump=None, with_cols=False):
+        """One pass over the logit tiles S = a b^T (and T): row statistics [5, rows] + per-row losses [2, rows] of the
+        a-side rows and, with_cols=True, the column sums [4, cols] of the same terms over these rows (this call's
+        contribution to the row statistics of the opposite direction)."""
         rows, dim = a_s.shape
         cols = b_s.shape[0]
         stats = torch.empty(5, rows, dtype=torch.float32, device=a_s.device)
         rowloss = torch.empty(2, rows, dtype=torch.float64, device=a_s.device)
+        col_stats = torch.empty(4, cols, dtype=torch.float32, device=a_s.device) if with_cols else None
         ws = torch.empty(max(1, _lib.load().dcb_clip_workspace_bytes(rows, cols)), dtype=torch.uint8, device=a_s.device)
         _lib.call("dcb_clip_row_stats", _vp(a_s), _vp(b_s), _vp(a_t), _vp(b_t), _vp(a_s_inv), _vp(b_s_inv),
                   _vp(a_t_inv), _vp(b_t_inv), rows, int(row_offset), cols, dim, ops.dtype_code(a_s),
-                  float(temperature or 1.0), _vp(stats), _vp(rowloss), _vp(ws), _vp(dump[0]) if dump else None,
-                  _vp(dump[1]) if dump and a_t is not None else None, ops._stream_ptr())
+                  float(temperature or 1.0), _vp(stats), _vp(rowloss), _vp(col_stats), _vp(ws),
+                  _vp(dump[0]) if dump else None, _vp(dump[1]) if dump and a_t is not None else None, ops._stream_ptr())
+        if not with_cols:
+            _lib.LAUNCHES -= 1          # no column-reduce launch
+            return stats, rowloss
+        return stats, rowloss, col_stats
+
+    def col_finish(self, col_stats, diag_local, row_offset, temperature, has_teacher):
+        """Opposite-direction statistics [5, rows_local] and per-row losses of this rank's rows from complete column sums."""
+        rows = diag_local.shape[0]
+        stats = torch.empty(5, rows, dtype=torch.float32, device=col_stats.device)
+        rowloss = torch.empty(2, rows, dtype=torch.float64, device=col_stats.device)
+        _lib.call("dcb_clip_col_finish", _vp(col_stats), col_stats.shape[1], _vp(diag_local), int(row_offset), rows,
+                  float(temperature or 1.0), int(has_teacher), _vp(stats), _vp(rowloss), ops._stream_ptr())
         return stats, rowloss
 
     def losses(self, rowloss_i2t, rowloss_t2i, global_batch, temperature, has_teacher):
@@ -168,11 +184,14 @@ def contrastive_forward(engine, si, st, ti, tt, temperature, group=None):
 
     def local(x):
         return None if x is None else x[loc]
-    # i2t rows: a = image, b = text ; t2i rows: a = text, b = image
-    stats_i2t, rl_i2t = engine.row_stats(si, st_all, ti, tt_all, local(si_inv_all), st_inv_all, local(ti_inv_all),
-                                         tt_inv_all, offset, temperature)
-    stats_t2i, rl_t2i = engine.row_stats(st, si_all, tt, ti_all, local(st_inv_all), si_inv_all, local(tt_inv_all),
-                                         ti_inv_all, offset, temperature)
+    # ONE pass over the logits of this rank's image rows against all text rows: row sums = i2t statistics of the local
+    # rows, column sums = this rank's share of the t2i statistics of ALL text rows (t2i logits are the transpose)
+    stats_i2t, rl_i2t, col = engine.row_stats(si, st_all, ti, tt_all, local(si_inv_all), st_inv_all, local(ti_inv_all),
+                                              tt_inv_all, offset, temperature, with_cols=True)
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(col, group=group)                 # exchange step 2: complete the column sums
+    stats_t2i, rl_t2i = engine.col_finish(col, stats_i2t[4], offset, temperature, has_teacher)
     sums, out = engine.losses(rl_i2t, rl_t2i, b_global, temperature, has_teacher)
     if world > 1:
         import torch.distributed as dist
@@ -180,7 +199,7 @@ def contrastive_forward(engine, si, st, ti, tt, temperature, group=None):
         out = torch.stack([0.5 * (sums[0] + sums[1]) / b_global, 0.5 * (sums[2] + sums[3])]).to(torch.float32)
     saved = dict(si=si, st=st, ti=ti, tt=tt, si_all=si_all, st_all=st_all, ti_all=ti_all, tt_all=tt_all,
                  si_inv_all=si_inv_all, st_inv_all=st_inv_all, ti_inv_all=ti_inv_all, tt_inv_all=tt_inv_all,
-                 stats_i2t=stats_i2t, stats_t2i=stats_t2i, offset=offset, b_global=b_global, world=world,
+                 stats_i2t=stats_i2t, stats_t2i=stats_t2i, col_stats=col, offset=offset, b_global=b_global, world=world,
                  group=group, temperature=temperature, has_teacher=has_teacher)
     return out, saved
 
@@ -192,11 +211,11 @@ def contrastive_backward(engine, saved, upstream, want_img=True, want_txt=True, 
     b_global, T, has_teacher, offset = s["b_global"], s["temperature"], s["has_teacher"], s["offset"]
     b_local = s["si"].shape[0]
     loc = slice(offset, offset + b_local)
-    # column softmax statistics of a direction = row statistics of the opposite direction, for ALL rows
+    # column softmax statistics of a direction = row statistics of the opposite direction, for ALL rows: the t2i ones
+    # are the (already complete) column sums of the forward pass, the i2t ones are gathered
     stats_i2t_all = _all_gather_cols(s["stats_i2t"], group, world)
-    stats_t2i_all = _all_gather_cols(s["stats_t2i"], group, world)
     coef_i2t_all, gmax_i2t = engine.coef(stats_i2t_all, b_global, T, has_teacher, upstream)
-    coef_t2i_all, gmax_t2i = engine.coef(stats_t2i_all, b_global, T, has_teacher, upstream)
+    coef_t2i_all, gmax_t2i = engine.coef(s["col_stats"], b_global, T, has_teacher, upstream)
     coef_i2t = coef_i2t_all[:, loc].contiguous() if world > 1 else coef_i2t_all
     coef_t2i = coef_t2i_all[:, loc].contiguous() if world > 1 else coef_t2i_all
 

@@ -31,7 +31,8 @@ constexpr int kTileBytes = kBM * kBK * 2;                 // 16 KiB: one [128 x 
 constexpr int kStageBytes = 4 * kTileBytes;               // a_stu, b_stu, a_tea, b_tea
 constexpr int kThreads = 320;                            // 2 control warps + 8 epilogue warps (2 per scheduler)
 constexpr int kTmemCols = 512;
-constexpr int kSmemBytes = 1024 /*align slack*/ + kStages * kStageBytes + 2 * 2 * kBN * 4 + 256;
+constexpr int kColBufBytes = 2 * 4 * 4 * kBN * 4;          // [tile parity][lane quadrant][stat][column] fp32
+constexpr int kSmemBytes = 1024 /*align slack*/ + kStages * kStageBytes + 2 * 2 * kBN * 4 + 256 + kColBufBytes;
 }  // namespace fwd
 
 struct ClipFwdParams {
@@ -41,6 +42,8 @@ struct ClipFwdParams {
     const float* b_inv_tea;
     float* ws;                // [2 * n_split][4][rows] partial sums (x2: the two epilogue warps of a row)
     float* diag;              // [rows] S_ii
+    float* col_part;          // [row_blocks][4][cols] column sums of the same four statistics over each block of 128 rows
+                              // (= the row statistics of the OPPOSITE direction, reduced later), or nullptr
     float* dump_s;            // optional [rows, cols] raw logits (tests only), else nullptr
     float* dump_t;
     int rows, cols, dim;
@@ -55,7 +58,23 @@ __device__ __forceinline__ float ex2(float x) {
     return y;
 }
 
-template <bool kTeacher>
+// Sum over the 32 lanes (= 32 rows) of a[0..15] (= 16 columns): recursive halving, each step exchanges half of the
+// remaining values with the lane `s` away.  Afterwards lane L holds the total of column L >> 1 in a[0].
+__device__ __forceinline__ void column_sums16(float (&a)[16], int lane) {
+#pragma unroll
+    for (int s = 16, n = 8; n >= 1; s >>= 1, n >>= 1) {
+        const bool up = lane & s;
+#pragma unroll
+        for (int i = 0; i < n; ++i) {
+            const float keep = up ? a[i + n] : a[i];
+            const float send = up ? a[i] : a[i + n];
+            a[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+        }
+    }
+    a[0] += __shfl_xor_sync(0xffffffffu, a[0], 1);
+}
+
+template <bool kTeacher, bool kCols>
 __global__ void __launch_bounds__(fwd::kThreads, 1)
 clip_fwd_kernel(const __grid_constant__ CUtensorMap map_a_stu, const __grid_constant__ CUtensorMap map_b_stu,
                 const __grid_constant__ CUtensorMap map_a_tea, const __grid_constant__ CUtensorMap map_b_tea,
@@ -68,6 +87,7 @@ clip_fwd_kernel(const __grid_constant__ CUtensorMap map_a_stu, const __grid_cons
     const uint32_t ring = smem_base;
     float* scale_buf = reinterpret_cast<float*>(smem_gen + kStages * kStageBytes);   // [2 buf][2 stu/tea][128]
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_gen + kStages * kStageBytes + 2 * 2 * kBN * 4);
+    float* col_buf = reinterpret_cast<float*>(smem_gen + kStages * kStageBytes + 2 * 2 * kBN * 4 + 256);   // [2][4][4][128]
     const uint32_t bar_full = smem_u32(bars);                   // [kStages]
     const uint32_t bar_empty = bar_full + 8 * kStages;          // [kStages]
     const uint32_t bar_tfull = bar_empty + 8 * kStages;         // [2]
@@ -184,6 +204,18 @@ clip_fwd_kernel(const __grid_constant__ CUtensorMap map_a_stu, const __grid_cons
             comp = (t - sum) - y;
             sum = t;
         };
+        // column partial sums of the previous tile: [4 quadrants][4 stats][128 columns] -> global, 2 values per thread
+        auto flush_cols = [&](int t_prev) {
+            const float* cb = col_buf + (t_prev & 1) * (4 * 4 * kBN);
+            const int pcol0 = (tile_begin + t_prev) * kBN;
+#pragma unroll
+            for (int o = ep_tid; o < 4 * kBN; o += 256) {
+                const int st = o / kBN, c = o % kBN;
+                if (pcol0 + c < p.cols && (kTeacher || st == 0))
+                    p.col_part[((size_t)rb * 4 + st) * p.cols + pcol0 + c] =
+                        (cb[(0 * 4 + st) * kBN + c] + cb[(1 * 4 + st) * kBN + c]) + (cb[(2 * 4 + st) * kBN + c] + cb[(3 * 4 + st) * kBN + c]);
+            }
+        };
         for (int t = 0; t < n_tiles; ++t) {
             const int as = t & 1;
             const uint32_t aphase = (t >> 1) & 1;
@@ -196,12 +228,15 @@ clip_fwd_kernel(const __grid_constant__ CUtensorMap map_a_stu, const __grid_cons
                 const int c = col0 + ep_tid - kBN;
                 sc[ep_tid] = c < p.cols ? __ldg(p.b_inv_tea + c) : 0.f;
             }
-            asm volatile("bar.sync 1, 256;" ::: "memory");
+            asm volatile("bar.sync 1, 256;" ::: "memory");      // scales staged; every warp is done with tile t-1
+            if (kCols && t > 0) flush_cols(t - 1);
             mbar_wait(bar_tfull + 8 * as, aphase);
             tc_fence_after_sync();
             const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * 256;
+            // masks are only needed where the tile meets the matrix edge, the diagonal, or rows beyond the batch
             const bool edge = (col0 + kBN > p.cols) || (diag_col >= col0 && diag_col < col0 + kBN) ||
-                              (p.dump_s != nullptr);
+                              (row0 + kBM > p.rows) || (p.dump_s != nullptr);
+            float* cb = col_buf + (t & 1) * (4 * 4 * kBN) + q * (4 * kBN);     // this quadrant's [4 stats][128 columns]
 #pragma unroll 1
             for (int ch = 2 * sub; ch < 2 * sub + 2; ++ch) {
                 float sv[32], tv[32];
@@ -215,52 +250,84 @@ clip_fwd_kernel(const __grid_constant__ CUtensorMap map_a_stu, const __grid_cons
                 }
                 const float* scs = sc + ch * 32;
                 const float* sct = sc + kBN + ch * 32;
-                float a0 = 0.f, a1 = 0.f, zs0 = 0.f, zs1 = 0.f, zt0 = 0.f, zt1 = 0.f, w0 = 0.f, w1 = 0.f;
-                if (!edge) {
+                float a_sum = 0.f, zs_sum = 0.f, zt_sum = 0.f, w_sum = 0.f;
 #pragma unroll
-                    for (int c = 0; c < 32; c += 2) {
-                        const float u0 = sv[c] * scs[c], u1 = sv[c + 1] * scs[c + 1];
-                        a0 += ex2(fmaf(u0, k1, n1));
-                        a1 += ex2(fmaf(u1, k1, n1));
-                        if (kTeacher) {
-                            const float v0 = tv[c] * sct[c], v1 = tv[c + 1] * sct[c + 1];
-                            const float et0 = ex2(fmaf(v0, k2t, n1t)), et1 = ex2(fmaf(v1, k2t, n1t));
-                            zs0 += ex2(fmaf(u0, k1t, n1t));
-                            zs1 += ex2(fmaf(u1, k1t, n1t));
-                            zt0 += et0;
-                            zt1 += et1;
-                            w0 = fmaf(et0, fmaf(v0, r_t, -(u0 * r_s)), w0);
-                            w1 = fmaf(et1, fmaf(v1, r_t, -(u1 * r_s)), w1);
+                for (int hc = 0; hc < 2; ++hc) {            // 16 columns at a time (keeps the per-statistic arrays small)
+                    float e[16], f[16];
+                    const int cbase = ch * 32 + hc * 16;
+                    // ---- A = sum exp(S - 1)
+#pragma unroll
+                    for (int c = 0; c < 16; ++c) {
+                        const float u = sv[hc * 16 + c] * scs[hc * 16 + c];
+                        sv[hc * 16 + c] = u;                                  // keep the scaled logit (still * 1/r_s)
+                        e[c] = ex2(fmaf(u, k1, n1));
+                    }
+                    if (edge) {
+#pragma unroll
+                        for (int c = 0; c < 16; ++c) {
+                            const int gc = col0 + cbase + c;
+                            const float s = sv[hc * 16 + c] * r_s;
+                            if (gc == diag_col) { diag = s; have_diag = true; }
+                            if (p.dump_s && row_ok && gc < p.cols) p.dump_s[(size_t)grow * p.cols + gc] = s;
+                            if (!(gc < p.cols && row_ok)) e[c] = 0.f;
                         }
                     }
-                } else {
 #pragma unroll
-                    for (int c = 0; c < 32; ++c) {
-                        const int gc = col0 + ch * 32 + c;
-                        const bool ok = gc < p.cols;
-                        const float u = sv[c] * scs[c];
-                        const float s = u * r_s;
-                        if (gc == diag_col) { diag = s; have_diag = true; }
-                        a0 += ok ? ex2(fmaf(u, k1, n1)) : 0.f;
-                        if (p.dump_s && row_ok && ok) p.dump_s[(size_t)grow * p.cols + gc] = s;
-                        if (kTeacher) {
-                            const float v = tv[c] * sct[c];
-                            const float tt = v * r_t;
-                            const float et = ok ? ex2(fmaf(v, k2t, n1t)) : 0.f;
-                            zs0 += ok ? ex2(fmaf(u, k1t, n1t)) : 0.f;
-                            zt0 += et;
-                            w0 = fmaf(et, tt - s, w0);
-                            if (p.dump_t && row_ok && ok) p.dump_t[(size_t)grow * p.cols + gc] = tt;
+                    for (int c = 0; c < 16; ++c) a_sum += e[c];
+                    if (kCols) {
+                        column_sums16(e, lane);
+                        if (!(lane & 1)) cb[0 * kBN + cbase + (lane >> 1)] = e[0];
+                    }
+                    if (kTeacher) {
+                        // ---- Zs = sum exp((S - 1)/T)
+#pragma unroll
+                        for (int c = 0; c < 16; ++c) e[c] = ex2(fmaf(sv[hc * 16 + c], k1t, n1t));
+                        if (edge) {
+#pragma unroll
+                            for (int c = 0; c < 16; ++c)
+                                if (!(col0 + cbase + c < p.cols && row_ok)) e[c] = 0.f;
+                        }
+#pragma unroll
+                        for (int c = 0; c < 16; ++c) zs_sum += e[c];
+                        if (kCols) {
+                            column_sums16(e, lane);
+                            if (!(lane & 1)) cb[1 * kBN + cbase + (lane >> 1)] = e[0];
+                        }
+                        // ---- Zt = sum exp((Tt - 1)/T),  W = sum exp((Tt - 1)/T) (Tt - S)
+#pragma unroll
+                        for (int c = 0; c < 16; ++c) {
+                            const float v = tv[hc * 16 + c] * sct[hc * 16 + c];
+                            e[c] = ex2(fmaf(v, k2t, n1t));
+                            f[c] = e[c] * fmaf(v, r_t, -(sv[hc * 16 + c] * r_s));
+                            if (p.dump_t && row_ok && col0 + cbase + c < p.cols)
+                                p.dump_t[(size_t)grow * p.cols + col0 + cbase + c] = v * r_t;
+                        }
+                        if (edge) {
+#pragma unroll
+                            for (int c = 0; c < 16; ++c)
+                                if (!(col0 + cbase + c < p.cols && row_ok)) { e[c] = 0.f; f[c] = 0.f; }
+                        }
+#pragma unroll
+                        for (int c = 0; c < 16; ++c) { zt_sum += e[c]; w_sum += f[c]; }
+                        if (kCols) {
+                            column_sums16(e, lane);
+                            if (!(lane & 1)) cb[2 * kBN + cbase + (lane >> 1)] = e[0];
+                            column_sums16(f, lane);
+                            if (!(lane & 1)) cb[3 * kBN + cbase + (lane >> 1)] = f[0];
                         }
                     }
                 }
-                kahan(A, cA, a0 + a1);
+                kahan(A, cA, a_sum);
                 if (kTeacher) {
-                    kahan(Zs, cZs, zs0 + zs1);
-                    kahan(Zt, cZt, zt0 + zt1);
-                    kahan(W, cW, w0 + w1);
+                    kahan(Zs, cZs, zs_sum);
+                    kahan(Zt, cZt, zt_sum);
+                    kahan(W, cW, w_sum);
                 }
             }
+        }
+        if (kCols && n_tiles > 0) {
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            flush_cols(n_tiles - 1);
         }
         if (row_ok) {
             float* w = p.ws + (size_t)(sp * 2 + sub) * 4 * p.rows + grow;
@@ -301,6 +368,38 @@ __global__ void __launch_bounds__(128) clip_combine_kernel(const float* __restri
     rowloss[(size_t)rows + r] = has_teacher ? (double)v[3] / ((double)temperature * (double)v[2]) + log((double)v[1] / (double)v[2]) : 0.0;
 }
 
+// col_stats[k][j] = sum over row blocks of col_part[rb][k][j]  (double accumulation, fixed order)
+__global__ void __launch_bounds__(256) clip_colreduce_kernel(const float* __restrict__ col_part, float* __restrict__ col_stats,
+                                                             int cols, int row_blocks, int n_stats) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int k = blockIdx.y;
+    if (j >= cols) return;
+    double acc = 0.0;
+    if (k < n_stats)
+        for (int rb = 0; rb < row_blocks; ++rb) acc += (double)col_part[((size_t)rb * 4 + k) * cols + j];
+    col_stats[(size_t)k * cols + j] = (float)acc;
+}
+
+// Opposite-direction statistics of this rank's rows from the (all-reduced) column statistics:
+//   stats[k][i] = col_stats[k][row_offset + i] (k < 4), stats[4][i] = S_ii, and the per-row losses as in clip_combine_kernel
+__global__ void __launch_bounds__(128) clip_colfinish_kernel(const float* __restrict__ col_stats, int cols_total,
+                                                             const float* __restrict__ diag, int row_offset, int rows,
+                                                             float temperature, int has_teacher, float* __restrict__ stats,
+                                                             double* __restrict__ rowloss) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    float v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        v[k] = col_stats[(size_t)k * cols_total + row_offset + r];
+        stats[(size_t)k * rows + r] = v[k];
+    }
+    const float dg = diag[r];
+    stats[(size_t)4 * rows + r] = dg;
+    rowloss[r] = 1.0 + log((double)v[0]) - (double)dg;
+    rowloss[(size_t)rows + r] = has_teacher ? (double)v[3] / ((double)temperature * (double)v[2]) + log((double)v[1] / (double)v[2]) : 0.0;
+}
+
 // Column ranges per row block: minimise (waves of 148 CTAs) x (tiles per CTA + fixed per-CTA cost)
 static int clip_fwd_splits(int64_t rows, int64_t cols) {
     const int64_t row_blocks = (rows + fwd::kBM - 1) / fwd::kBM;
@@ -320,14 +419,15 @@ static int clip_fwd_splits(int64_t rows, int64_t cols) {
 
 extern "C" int64_t dcb_clip_workspace_bytes(int64_t rows_local, int64_t cols) {
     if (rows_local < 1 || cols < 1) return 0;
-    return ((int64_t)dcb::clip_fwd_splits(rows_local, cols) * 2 * 4 + 1) * rows_local * (int64_t)sizeof(float);
+    const int64_t row_blocks = (rows_local + dcb::fwd::kBM - 1) / dcb::fwd::kBM;
+    return (((int64_t)dcb::clip_fwd_splits(rows_local, cols) * 2 * 4 + 1) * rows_local + row_blocks * 4 * cols) * (int64_t)sizeof(float);
 }
 
 extern "C" int dcb_clip_row_stats(const void* stu_a, const void* stu_b, const void* tea_a, const void* tea_b,
                                   const float* stu_a_inv, const float* stu_b_inv, const float* tea_a_inv,
                                   const float* tea_b_inv, int64_t rows_local, int64_t row_offset, int64_t cols,
                                   int64_t dim, int dtype, float temperature, float* stats, double* rowloss,
-                                  void* workspace, float* dump_s, float* dump_t, void* stream) {
+                                  float* col_stats, void* workspace, float* dump_s, float* dump_t, void* stream) {
     using namespace dcb;
     DCB_REQUIRE(stu_a && stu_b && stu_a_inv && stu_b_inv && stats && rowloss && workspace, "NULL pointer argument");
     DCB_REQUIRE(dtype == DCB_BF16 || dtype == DCB_F16, "the fused contrastive kernel takes bf16 or fp16 embeddings");
@@ -363,6 +463,7 @@ extern "C" int dcb_clip_row_stats(const void* stu_a, const void* stu_b, const vo
     p.col_tiles = (int)((cols + fwd::kBN - 1) / fwd::kBN);
     p.ws = static_cast<float*>(workspace);
     p.diag = p.ws + (size_t)p.n_split * 2 * 4 * rows_local;
+    p.col_part = col_stats ? p.diag + rows_local : nullptr;
     p.dump_s = dump_s;
     p.dump_t = dump_t;
     p.inv_temp = teacher ? 1.0f / temperature : 1.0f;
@@ -370,18 +471,38 @@ extern "C" int dcb_clip_row_stats(const void* stu_a, const void* stu_b, const vo
     const uint32_t idesc = tc::umma_idesc_f16(fwd::kBM, fwd::kBN, dtype == DCB_BF16 ? 1 : 0);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     dim3 grid((unsigned)(row_blocks * p.n_split));
-    if (teacher) {
-        static const cudaError_t attr_true = cudaFuncSetAttribute(clip_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd::kSmemBytes);
-        DCB_CUDA_OK(attr_true);     // set once per process (not a stream operation; kept out of graph captures)
-        clip_fwd_kernel<true><<<grid, fwd::kThreads, fwd::kSmemBytes, st>>>(ma_s, mb_s, ma_t, mb_t, p, idesc);
-    } else {
-        static const cudaError_t attr_false = cudaFuncSetAttribute(clip_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd::kSmemBytes);
-        DCB_CUDA_OK(attr_false);     // set once per process (not a stream operation; kept out of graph captures)
-        clip_fwd_kernel<false><<<grid, fwd::kThreads, fwd::kSmemBytes, st>>>(ma_s, mb_s, ma_t, mb_t, p, idesc);
+#define DCB_LAUNCH_FWD(TEA, COLS)                                                                                       \
+    {                                                                                                                  \
+        static const cudaError_t attr_ = cudaFuncSetAttribute(clip_fwd_kernel<TEA, COLS>,                              \
+                                                              cudaFuncAttributeMaxDynamicSharedMemorySize, fwd::kSmemBytes); \
+        DCB_CUDA_OK(attr_);     /* set once per process (not a stream operation; kept out of graph captures) */         \
+        clip_fwd_kernel<TEA, COLS><<<grid, fwd::kThreads, fwd::kSmemBytes, st>>>(ma_s, mb_s, ma_t, mb_t, p, idesc);     \
     }
+    if (teacher && col_stats) DCB_LAUNCH_FWD(true, true)
+    else if (teacher) DCB_LAUNCH_FWD(true, false)
+    else if (col_stats) DCB_LAUNCH_FWD(false, true)
+    else DCB_LAUNCH_FWD(false, false)
+#undef DCB_LAUNCH_FWD
     DCB_CUDA_OK(cudaGetLastError());
     clip_combine_kernel<<<(unsigned)((rows_local + 127) / 128), 128, 0, st>>>(p.ws, p.diag, stats, rowloss, (int)rows_local,
                                                                                2 * p.n_split, temperature, teacher ? 1 : 0);
+    DCB_CUDA_OK(cudaGetLastError());
+    if (col_stats) {
+        dim3 g2((unsigned)((cols + 255) / 256), 4);
+        clip_colreduce_kernel<<<g2, 256, 0, st>>>(p.col_part, col_stats, (int)cols, row_blocks, teacher ? 4 : 1);
+        DCB_CUDA_OK(cudaGetLastError());
+    }
+    return 0;
+}
+
+extern "C" int dcb_clip_col_finish(const float* col_stats, int64_t cols_total, const float* diag_local, int64_t row_offset,
+                                   int64_t rows_local, float temperature, int has_teacher, float* stats, double* rowloss,
+                                   void* stream) {
+    using namespace dcb;
+    DCB_REQUIRE(col_stats && diag_local && stats && rowloss && rows_local >= 1 && row_offset >= 0 &&
+                    row_offset + rows_local <= cols_total, "bad arguments");
+    clip_colfinish_kernel<<<(unsigned)((rows_local + 127) / 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+        col_stats, (int)cols_total, diag_local, (int)row_offset, (int)rows_local, temperature, has_teacher, stats, rowloss);
     DCB_CUDA_OK(cudaGetLastError());
     return 0;
 }

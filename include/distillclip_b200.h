@@ -150,13 +150,23 @@ int dcb_transpose_norm_f16(const void* in, const float* inv_norm, void* out, int
  *   stats[3][i] = sum_j exp((T_ij - 1)/T) (T_ij - S_ij)      stats[4][i] = S_ii (global diagonal)
  * tea_* may all be NULL (hard label only; stats[1..3] are then 0).  stats: [5, rows_local] floats.
  * rowloss: [2, rows_local] doubles = {CE_i = 1 + log stats0 - stats4,  KL_i / T^2 = stats3/(T stats2) + log(stats1/stats2)}.
+ * col_stats (optional, [4, cols] floats): the SAME four sums taken down the columns over this call's rows, i.e. this
+ *   call's contribution to the row statistics of the opposite direction (t2i when a = image) -- one pass over the logits
+ *   serves both directions; all-reduce over ranks when sharded, then dcb_clip_col_finish.  NULL = row statistics only.
  * workspace: dcb_clip_workspace_bytes(rows_local, cols) bytes of device scratch.
  * dump_s / dump_t: optional [rows_local, cols] fp32 buffers that receive the logits (tests only; NULL in production). */
 int64_t dcb_clip_workspace_bytes(int64_t rows_local, int64_t cols);
 int dcb_clip_row_stats(const void* stu_a, const void* stu_b, const void* tea_a, const void* tea_b,
                        const float* stu_a_inv, const float* stu_b_inv, const float* tea_a_inv, const float* tea_b_inv,
                        int64_t rows_local, int64_t row_offset, int64_t cols, int64_t dim, int dtype, float temperature,
-                       float* stats, double* rowloss, void* workspace, float* dump_s, float* dump_t, void* stream);
+                       float* stats, double* rowloss, float* col_stats, void* workspace, float* dump_s, float* dump_t,
+                       void* stream);
+
+/* Row statistics / per-row losses of the opposite direction for this rank's rows from the complete column statistics:
+ * stats[k][i] = col_stats[k][row_offset + i] (k < 4), stats[4][i] = diag_local[i] (= stats[4] of dcb_clip_row_stats:
+ * the logit matrix has one diagonal), rowloss as above. */
+int dcb_clip_col_finish(const float* col_stats, int64_t cols_total, const float* diag_local, int64_t row_offset,
+                        int64_t rows_local, float temperature, int has_teacher, float* stats, double* rowloss, void* stream);
 
 /* Loss values of both directions from this rank's per-row losses (the `rowloss` outputs of dcb_clip_row_stats):
  *   sums[0..3] (double) = {sum_i CE_i (i2t), sum_i CE_i (t2i), T^2 sum_i KL_i (i2t), T^2 sum_i KL_i (t2i)}

@@ -14,24 +14,39 @@ class DoubleEngine:
     def _logits(self, a, b, a_inv, b_inv):
         return (a.double() @ b.double().t()) * a_inv[:, None] * b_inv[None, :]
 
-    def row_stats(self, a_s, b_s, a_t, b_t, a_s_inv, b_s_inv, a_t_inv, b_t_inv, row_offset, temperature, dump=None):
+    def row_stats(self, a_s, b_s, a_t, b_t, a_s_inv, b_s_inv, a_t_inv, b_t_inv, row_offset, temperature, dump=None,
+                  with_cols=False):
         S = self._logits(a_s, b_s, a_s_inv, b_s_inv)
-        rows = S.shape[0]
+        rows, cols = S.shape
         idx = torch.arange(rows)
         st = torch.zeros(5, rows, dtype=torch.float64)
-        st[0] = torch.exp(S - 1).sum(1)
+        col = torch.zeros(4, cols, dtype=torch.float64)
+        e1 = torch.exp(S - 1)
+        st[0], col[0] = e1.sum(1), e1.sum(0)
         st[4] = S[idx, row_offset + idx]
         if a_t is not None:
             T = self._logits(a_t, b_t, a_t_inv, b_t_inv)
-            et = torch.exp((T - 1) / temperature)
-            st[1] = torch.exp((S - 1) / temperature).sum(1)
-            st[2] = et.sum(1)
-            st[3] = (et * (T - S)).sum(1)
-        rl = torch.zeros(2, rows, dtype=torch.float64)
+            et, es = torch.exp((T - 1) / temperature), torch.exp((S - 1) / temperature)
+            st[1], col[1] = es.sum(1), es.sum(0)
+            st[2], col[2] = et.sum(1), et.sum(0)
+            st[3], col[3] = (et * (T - S)).sum(1), (et * (T - S)).sum(0)
+        rl = self._rowloss(st, temperature, a_t is not None)
+        return (st, rl, col) if with_cols else (st, rl)
+
+    @staticmethod
+    def _rowloss(st, temperature, has_teacher):
+        rl = torch.zeros(2, st.shape[1], dtype=torch.float64)
         rl[0] = 1 + torch.log(st[0]) - st[4]
-        if a_t is not None:
+        if has_teacher:
             rl[1] = st[3] / (temperature * st[2]) + torch.log(st[1] / st[2])
-        return st, rl
+        return rl
+
+    def col_finish(self, col_stats, diag_local, row_offset, temperature, has_teacher):
+        rows = diag_local.shape[0]
+        st = torch.zeros(5, rows, dtype=torch.float64)
+        st[:4] = col_stats[:, row_offset:row_offset + rows]
+        st[4] = diag_local
+        return st, self._rowloss(st, temperature, has_teacher)
 
     def losses(self, rl_i2t, rl_t2i, global_batch, temperature, has_teacher):
         sums = torch.zeros(4, dtype=torch.float64)

@@ -48,6 +48,14 @@ def test_similarity_tiles_match_matmul(cuda_device, b, d):
     assert np.abs(stats[4].cpu().numpy() - np.diag(s_ref)).max() <= 2e-6
     assert rel_l2(stats[0].cpu().numpy(), np.exp(s_ref - 1).sum(1)) <= 1e-5
     assert rel_l2(stats[2].cpu().numpy(), np.exp((t_ref - 1) / 2.0).sum(1)) <= 1e-5
+    # one pass, both directions: the column sums equal the row statistics of the transposed (t2i) problem
+    st1, _, col = eng.row_stats(si, st, ti, tt, inv[0], inv[1], inv[2], inv[3], 0, 2.0, with_cols=True)
+    st2, _ = eng.row_stats(st, si, tt, ti, inv[1], inv[0], inv[3], inv[2], 0, 2.0)
+    assert torch.equal(st1, stats)
+    for k in range(4):
+        assert rel_l2(col[k].cpu().numpy(), st2[k].double().cpu().numpy()) <= 2e-6, k
+    et = np.exp((t_ref - 1) / 2.0)
+    assert rel_l2(col[3].cpu().numpy(), (et * (t_ref - s_ref)).sum(0)) <= 1e-4
 
 
 @pytest.fixture(params=["pair", "chunk"])
@@ -141,15 +149,19 @@ def test_row_sharded_virtual_ranks(cuda_device, bwd_kernel):
     inv = eng.inv_norms([si, st, ti, tt])
     bl = b // R
     sums = torch.zeros(4, dtype=torch.float64, device="cuda")
-    stats_i, stats_t = [], []
+    stats_i, cols, diags = [], torch.zeros(4, b, device="cuda"), []
     for r in range(R):
         loc = slice(r * bl, (r + 1) * bl)
-        s1, l1 = eng.row_stats(si[loc], st, ti[loc], tt, inv[0][loc], inv[1], inv[2][loc], inv[3], r * bl, T)
-        s2, l2 = eng.row_stats(st[loc], si, tt[loc], ti, inv[1][loc], inv[0], inv[3][loc], inv[2], r * bl, T)
+        s1, l1, col = eng.row_stats(si[loc], st, ti[loc], tt, inv[0][loc], inv[1], inv[2][loc], inv[3], r * bl, T, with_cols=True)
         assert np.abs(s1[4].cpu().numpy() - np.diag(s_ref)[loc]).max() <= 2e-6       # global labels, exact position
-        sums += eng.losses(l1, l2, b, T, True)[0]
-        stats_i.append(s1)
+        cols += col                                                                   # the all-reduce of the real thing
+        stats_i.append((s1, l1))
+    stats_t = []
+    for r in range(R):
+        s2, l2 = eng.col_finish(cols, stats_i[r][0][4].contiguous(), r * bl, T, True)
+        sums += eng.losses(stats_i[r][1], l2, b, T, True)[0]
         stats_t.append(s2)
+    stats_i = [x[0] for x in stats_i]
     assert float(0.5 * (sums[0] + sums[1]) / b) == pytest.approx(ref["hard"], rel=LOSS_RTOL)
     assert float(0.5 * (sums[2] + sums[3])) == pytest.approx(ref["soft"], rel=LOSS_RTOL)
     up = torch.tensor([1.0, 1.0], device="cuda")
