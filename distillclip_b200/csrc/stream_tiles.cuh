@@ -142,71 +142,6 @@ __device__ __forceinline__ float attn_tile(const T* __restrict__ s_base, const T
     return acc;
 }
 
-// Narrow vectors (odd map sizes: N = 77 -> VEC = 1, 2-byte loads) leave too few bytes in flight per thread to cover
-// HBM latency, so a thread then takes several groups, 256 apart (coalescing unchanged), and issues all their loads first.
-template <int VEC> struct AttnGroupsPerThread { static constexpr int value = VEC == 1 ? 4 : (VEC == 2 ? 2 : 1); };
-
-template <typename T, typename G, int VEC, int H, bool MSE, int GRP>
-__device__ __forceinline__ float attn_tile_multi(const T* __restrict__ s_base, const T* __restrict__ t_base, G* __restrict__ g_base,
-                                                 const AttnShape& sh, long long gi0, float gc) {
-    if constexpr (GRP == 1) {
-        return attn_tile<T, G, VEC, H, MSE>(s_base, t_base, g_base, sh, gi0, gc);
-    } else {
-        const long long P = sh.positions;
-        float ssum[GRP][VEC], tsum[GRP][VEC];
-        long long off_s[GRP], off_t[GRP];
-        bool ok[GRP];
-#pragma unroll
-        for (int g = 0; g < GRP; ++g) {
-            const long long gi = gi0 + (long long)g * kStreamThreads;
-            ok[g] = gi < sh.groups;
-            const long long gic = ok[g] ? gi : 0;
-            const long long b = gic / sh.groups_per_b;
-            const long long pos = (gic - b * sh.groups_per_b) * VEC;
-            off_s[g] = (b * sh.hs) * P + pos;
-            off_t[g] = (b * sh.ht) * P + pos;
-        }
-#pragma unroll
-        for (int g = 0; g < GRP; ++g) head_sum<T, VEC, H>(s_base + off_s[g], P, sh.hs, ssum[g]);
-#pragma unroll
-        for (int g = 0; g < GRP; ++g) head_sum<T, VEC, H>(t_base + off_t[g], P, sh.ht, tsum[g]);
-        float acc = 0.f;
-#pragma unroll
-        for (int g = 0; g < GRP; ++g) {
-            float gv[VEC];
-            float a = 0.f;
-#pragma unroll
-            for (int e = 0; e < VEC; ++e) {
-                const float sm = ssum[g][e] * sh.inv_hs;
-                const float tm = tsum[g][e] * sh.inv_ht;
-                if constexpr (MSE) {
-                    const float d = sm - tm;
-                    a = fmaf(d, d, a);
-                    gv[e] = d * gc;
-                } else {
-                    const float tl = (tm == 0.f) ? 0.f : tm * logf(tm);
-                    a += tl - tm * logf(sm);
-                    gv[e] = -gc * (tm / sm);
-                }
-            }
-            if (ok[g]) {
-                acc += a;
-                if (g_base) {
-                    G* __restrict__ gp = g_base + off_s[g];
-                    if constexpr (H > 0) {
-#pragma unroll
-                        for (int h = 0; h < H; ++h) store_vec<G, VEC>(gp + h * P, gv);
-                    } else {
-#pragma unroll 4
-                        for (int h = 0; h < sh.hs; ++h) store_vec<G, VEC>(gp + h * P, gv);
-                    }
-                }
-            }
-        }
-        return acc;
-    }
-}
-
 // ---------------------------------------------------------------------------------------------
 // Cosine rows tile (nn.CosineEmbeddingLoss with target 1, out_cos.py:10-11): one warp per row of [rows, dim].
 //   cos = <s,t> / sqrt((<s,s> + eps)(<t,t> + eps)), eps = 1e-12 (ATen EPSILON);  value = sum_rows (1 - cos)

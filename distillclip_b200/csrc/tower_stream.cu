@@ -93,14 +93,12 @@ __global__ void __launch_bounds__(kStreamThreads, 4) tower_stream_kernel(const _
                                      (int)sg.positions, lt * (kStreamThreads / 32) + (tid >> 5), sg.grad_coef, tid & 31);
         } else {
             AttnShape sh{sg.n, sg.groups_per_b, sg.positions, sg.hs, sg.ht, sg.inv_hs, sg.inv_ht};
-            constexpr int GRP = AttnGroupsPerThread<AVEC>::value;
-            const long long gi0 = lt * (kStreamThreads * GRP) + tid;
             if (sg.kind == 1)
-                acc = attn_tile_multi<T, G, AVEC, AH, false, GRP>(static_cast<const T*>(sg.s), static_cast<const T*>(sg.t),
-                                                                  static_cast<G*>(sg.g), sh, gi0, sg.grad_coef);
+                acc = attn_tile<T, G, AVEC, AH, false>(static_cast<const T*>(sg.s), static_cast<const T*>(sg.t),
+                                                       static_cast<G*>(sg.g), sh, lt * kStreamThreads + tid, sg.grad_coef);
             else
-                acc = attn_tile_multi<T, G, AVEC, AH, true, GRP>(static_cast<const T*>(sg.s), static_cast<const T*>(sg.t),
-                                                                 static_cast<G*>(sg.g), sh, gi0, sg.grad_coef);
+                acc = attn_tile<T, G, AVEC, AH, true>(static_cast<const T*>(sg.s), static_cast<const T*>(sg.t),
+                                                      static_cast<G*>(sg.g), sh, lt * kStreamThreads + tid, sg.grad_coef);
         }
         cur += (double)acc * (double)sg.val_coef;
     }
@@ -251,8 +249,7 @@ extern "C" int dcb_tower_fwd_bwd(int n_seg, const int32_t* kind, const int32_t* 
         } else {
             sg.groups_per_b = sg.positions / avec;
             sg.n *= sg.groups_per_b;
-            const long long per_tile = (long long)kStreamThreads * (avec == 1 ? 4 : (avec == 2 ? 2 : 1));   // AttnGroupsPerThread
-            tiles += (sg.n + per_tile - 1) / per_tile;
+            tiles += (sg.n + kStreamThreads - 1) / kStreamThreads;
         }
     }
     p.total_tiles = tiles;
