@@ -46,6 +46,23 @@ WORKLOADS = {
 L2_BYTES = 126 * 1024 * 1024
 
 
+def ncu_traffic(csv_name, kernel_substr):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` extract (bytes), or None."""
+    import csv
+    path = os.path.join(ROOT, "profiles", csv_name)
+    if not os.path.exists(path):
+        return None
+    try:
+        rows = list(csv.reader(open(path)))
+        hdr, units = rows[0], rows[1]
+        ir, iw, ik = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum"), hdr.index("Kernel Name")
+        scale = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}
+        vals = [float(r[ir]) * scale[units[ir]] + float(r[iw]) * scale[units[iw]] for r in rows[2:] if kernel_substr in r[ik]]
+        return int(sum(vals) / len(vals)) if vals else None
+    except (ValueError, KeyError, IndexError):
+        return None
+
+
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -307,7 +324,11 @@ def bench_tower(cfg, name, args, device, dist, world, pk, with_cpu):
                        "frac": round(nbytes / k_ms / 1e6 / pk["hbm"], 4)}
     dom = "tower_stream_kernel"
     roofline = {"bound": "hbm", "kernel": dom, "achieved": kres[dom]["gbs"], "peak": pk["hbm"], "unit": "GB/s",
-                "frac": kres[dom]["frac"], "traffic": None, "peak_source": pk["source"],
+                "frac": kres[dom]["frac"],
+                "traffic": ncu_traffic("r01_ncu_full_tower_stream.csv", "tower_stream") if name == "image_stage" else None,
+                "traffic_note": "dram bytes read + written inside one isolated launch (ncu --set full, profiles/); part of the "
+                                "gradient writes is still dirty in L2 when the kernel exits",
+                "peak_source": pk["source"],
                 "step_frac": round(algo_bytes / ms / 1e6 / pk["hbm"], 4), "kernels": kres}
 
     # end to end through the module API with HOST (pinned) buffers: H2D of every input + D2H of the loss inside the timer
@@ -360,6 +381,29 @@ def cpu_tower(cfg, stu, tea, budget_s):
             "sample": f"{len(times)} full steps of the same workload (best of), oracle/torch_port.py fp32, {threads} threads"}
 
 
+def cpu_clip(cfg, budget_s):
+    """Oracle torch port of the reference path (normalise, matmul, HardLabel + SoftLabel both directions, autograd) on the
+    host cores; the B x B fp32 logits bound the sample to 4096 rows."""
+    from oracle import torch_port as tp
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    b = min(cfg["batch"], 4096)
+    gen = torch.Generator().manual_seed(2022)
+    si, st, ti, tt = [x.float() for x in make_clip(dict(cfg, batch=b), "cpu", gen, b, 0)]
+    si.requires_grad_(True)
+    st.requires_grad_(True)
+    times, t_end = [], time.perf_counter() + budget_s
+    while len(times) < 3 and (time.perf_counter() < t_end or not times):
+        si.grad = st.grad = None
+        t0 = time.perf_counter()
+        tp.stage_step_cpu(["hard_label", "soft_label"], {"visual": {"last_representation": si}, "text": {"last_representation": st}},
+                          {"visual": {"last_representation": ti}, "text": {"last_representation": tt}},
+                          temperature=cfg["temperature"], two=True, threads=threads)
+        times.append(time.perf_counter() - t0)
+    return {"value": round(b / min(times), 1), "unit": "samples/s", "cores": threads, "kind": "port",
+            "sample": f"{len(times)} fwd+bwd steps on a {b}-row batch (best of), oracle/torch_port.py fp32, {threads} threads"}
+
+
 def bench_clip(cfg, args, device, dist, rank, world, pk, steps, warmup):
     from distillclip_b200 import _lib
     from distillclip_b200.contrastive import clip_contrastive
@@ -385,9 +429,27 @@ def bench_clip(cfg, args, device, dist, rank, world, pk, steps, warmup):
     ms = total_ms / steps
     flops = 12.0 * b * b * d                                     # credited, whole job
     tf = flops / (ms * 1e-3) / 1e12
+    # end to end: pinned host embeddings -> device, fused fwd+bwd through the public call, loss back to the host
+    host = [x.detach().cpu().pin_memory() for x in (si, st, ti, tt)]
+    loss_host = torch.empty((), dtype=torch.float32).pin_memory()
+
+    def e2e_step():
+        a, c_, e, f = [h.to(device, non_blocking=True) for h in host]
+        a.requires_grad_(True)
+        c_.requires_grad_(True)
+        res = clip_contrastive(a, c_, e, f, T, want_hard=True, want_soft=True, group=group)
+        loss = 0.5 * res["hard_label"] + 0.5 * res["soft_label"]
+        loss.backward()
+        loss_host.copy_(loss.detach(), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+    n_e2e = max(3, steps // 4)
+    e2e_ms = Timer(device, flush=False).run(e2e_step, n_e2e, 2, dist, graph=False) / n_e2e
+    e2e = {"value": round(b / (e2e_ms * 1e-3), 1), "unit": "samples/s", "ms_per_step": round(e2e_ms, 4),
+           "h2d_bytes_per_step": sum(h.numel() * 2 for h in host), "d2h_bytes_per_step": 4}
     return {"workload": cfg["desc"], "global_batch": b, "dim": d, "temperature": T, "n_gpus": world,
             "value": round(b / (ms * 1e-3), 1), "unit": "samples/s", "ms_per_step": round(ms, 4), "steps": steps,
             "scaling": "strong", "gpu_launches": launches, "l2_flush": timer.flush_buf is not None, "timing": timer.mode,
+            "e2e": e2e,
             "roofline": {"bound": "tensor", "kernel": "clip_fwd_kernel + clip_bwd_kernel (fused tcgen05, both directions)",
                          "achieved": round(tf, 2), "peak": pk["tf_burst"] * world, "unit": "TFLOP/s",
                          "frac": round(tf / (pk["tf_burst"] * world), 4),
@@ -453,7 +515,9 @@ def run_ours(args):
                 "scaling": "strong", "vs_baseline": None, "dtype": "bf16 in, fp32 accumulate", "data": "synthetic (seed 2022)",
                 "config": {"workload": cfg["desc"], "parallelism": f"rows sharded over {world} rank(s), embedding all-gather",
                            "l2": "flushed before every timed step" if c["l2_flush"] else "inputs larger than L2"},
-                "roofline": c["roofline"], "gpu_launches": c["gpu_launches"], "clocks": sampler.summary()}
+                "roofline": c["roofline"], "e2e": c["e2e"], "gpu_launches": c["gpu_launches"], "clocks": sampler.summary()}
+        if rank == 0 and world == 1 and not args.no_cpu:
+            line["cpu_baseline"] = cpu_clip(cfg, budget_s=20.0)
     if rank == 0:
         print(json.dumps(line), flush=True)
     if dist is not None:
