@@ -1,9 +1,10 @@
 """Mirror of the reference's `model` package for the loss hot path (same import paths below `model`)."""
 from ._loss import IMAGE_TEXT_LOSS, LOSSNAME, LossCalculator
+from .component.clip_model import CLIPModel
 from .component.output import CLIPOutput, ControlOutput, TextTransformerOutput, VisionTransformerOutput
 from .loss_component import (AttentionProbsKL, AttentionProbsMSE, AttentionScoreMSE, CLIPCosDiff, EmbedMSELoss, HardLabel,
                              HiddenMSE, OutCosLoss, OutL1Loss, SoftLabel)
 
-__all__ = ["LossCalculator", "LOSSNAME", "IMAGE_TEXT_LOSS", "CLIPOutput", "ControlOutput",
+__all__ = ["LossCalculator", "LOSSNAME", "IMAGE_TEXT_LOSS", "CLIPModel", "CLIPOutput", "ControlOutput",
            "TextTransformerOutput", "VisionTransformerOutput", "AttentionProbsKL", "AttentionProbsMSE", "AttentionScoreMSE",
            "CLIPCosDiff", "EmbedMSELoss", "HardLabel", "HiddenMSE", "OutCosLoss", "OutL1Loss", "SoftLabel"]
