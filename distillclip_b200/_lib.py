@@ -43,6 +43,8 @@ SIGNATURES = {
                                 C.c_int64, C.c_int64, C.c_int, C.c_float, _vp, _vp, _vp, _vp],
     "dcb_clip_grad_finish": [_vp, C.c_int, _vp, _vp, _vp, _vp, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int64,
                              _vp, _vp, _vp, C.c_int, _vp, C.c_int, _vp],
+    "dcb_row_softmax_stats": [_vp, _vp, C.c_int64, C.c_int64, C.c_int, C.c_float, C.c_int, _vp, _vp, _vp],
+    "dcb_row_softmax_grads": [_vp, _vp, C.c_int64, C.c_int64, C.c_int, C.c_float, C.c_int, _vp, _vp, _vp, C.c_int, _vp],
     "dcb_logits_row_stats": [_vp, C.c_int64, C.c_int64, _vp, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_float,
                              C.c_int, _vp, _vp, _vp],
     "dcb_logits_row_grads": [_vp, C.c_int64, C.c_int64, _vp, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_float,

@@ -3,8 +3,9 @@ from ._loss import IMAGE_TEXT_LOSS, LOSSNAME, LossCalculator
 from .component.clip_model import CLIPModel
 from .component.output import CLIPOutput, ControlOutput, TextTransformerOutput, VisionTransformerOutput
 from .loss_component import (AttentionProbsKL, AttentionProbsMSE, AttentionScoreMSE, CLIPCosDiff, EmbedMSELoss, HardLabel,
-                             HiddenMSE, OutCosLoss, OutL1Loss, SoftLabel)
+                             HiddenMSE, LogitsMSE, OutCELoss, OutCosLoss, OutKLLoss, OutL1Loss, SoftLabel)
 
 __all__ = ["LossCalculator", "LOSSNAME", "IMAGE_TEXT_LOSS", "CLIPModel", "CLIPOutput", "ControlOutput",
            "TextTransformerOutput", "VisionTransformerOutput", "AttentionProbsKL", "AttentionProbsMSE", "AttentionScoreMSE",
-           "CLIPCosDiff", "EmbedMSELoss", "HardLabel", "HiddenMSE", "OutCosLoss", "OutL1Loss", "SoftLabel"]
+           "CLIPCosDiff", "EmbedMSELoss", "HardLabel", "HiddenMSE", "LogitsMSE", "OutCELoss", "OutCosLoss", "OutKLLoss", "OutL1Loss",
+           "SoftLabel"]

@@ -10,7 +10,8 @@ two-tower hard/soft-label terms run as the fused tcgen05 contrastive kernel stra
 
 In scope: hard_label, soft_label, attention_probs_kl, hidden_rep_mse, embedding_mse; widened
 (section 8f) to the losses of the three shipped configs and their siblings: out_l1, out_cos, cos_diff,
-attention_probs_mse, attention_score_mse.  The reference's remaining names are recognised but raise NotImplementedError.
+attention_probs_mse, attention_score_mse, out_kl, out_ce, logits_mse.  The reference's remaining names (last_value_map_kl,
+vit_kd, fine_grain, smd) are recognised but raise NotImplementedError.
 """
 from typing import Dict, List, Union
 
@@ -20,7 +21,7 @@ from torch import nn
 from .. import contrastive, ops
 from .component.output import CLIPOutput, ControlOutput, TextTransformerOutput, VisionTransformerOutput
 from .loss_component import (AttentionProbsKL, AttentionProbsMSE, AttentionScoreMSE, CLIPCosDiff, EmbedMSELoss,
-                             HardLabel, HiddenMSE, OutCosLoss, OutL1Loss, SoftLabel)
+                             HardLabel, HiddenMSE, LogitsMSE, OutCELoss, OutCosLoss, OutKLLoss, OutL1Loss, SoftLabel)
 
 # reference _loss.py:9-12 -- including the missing comma that fuses 'smd' and 'hard_label' 
 LOSSNAME = ['out_l1', 'out_ce', 'out_kl', 'out_cos', 'embedding_mse', 'attention_score_mse',
@@ -29,7 +30,7 @@ LOSSNAME = ['out_l1', 'out_ce', 'out_kl', 'out_cos', 'embedding_mse', 'attention
 IMAGE_TEXT_LOSS = ['hard_label', 'soft_label', 'logits_mse', 'fine_grain', 'cos_diff']
 
 # names the reference accepts (_loss.py:60-94) that are outside this build's hot-path scope
-_REFERENCE_ONLY = ('out_ce', 'out_kl', 'last_value_map_kl', 'vit_kd', 'logits_mse', 'fine_grain', 'smd')
+_REFERENCE_ONLY = ('last_value_map_kl', 'vit_kd', 'fine_grain', 'smd')
 
 # one-tower losses: name -> (kernel family, student field, is a list of layers)
 _TOWER_KERNELS = {
@@ -90,6 +91,7 @@ class LossCalculator(nn.Module):
             'attention_score_mse': AttentionScoreMSE, 'attention_probs_mse': AttentionProbsMSE,
             'hidden_rep_mse': HiddenMSE, 'attention_probs_kl': AttentionProbsKL,
             'hard_label': HardLabel, 'soft_label': lambda: SoftLabel(self.temperature), 'cos_diff': CLIPCosDiff,
+            'out_ce': OutCELoss, 'out_kl': lambda: OutKLLoss(self.temperature), 'logits_mse': LogitsMSE,
         }
         losses = nn.ModuleDict()
         for n in self.loss_name:
@@ -122,6 +124,12 @@ class LossCalculator(nn.Module):
                            tea_out: Union[VisionTransformerOutput, TextTransformerOutput]):
         """reference _loss.py:155-202: raw values per name, `* scale`, `loss += value * percent`."""
         raw_python = {}          # names whose value is a python number (empty teacher list edge case)
+        module_res = {}          # row-softmax losses on the pooled outputs (own small kernels)
+        for name in self.loss:
+            if name == 'out_kl':
+                assert self.temperature, 'You should give the temperature for the kl loss'
+            if name in ('out_ce', 'out_kl'):
+                module_res[name] = self.loss[name](stu_out.last_representation, tea_out.last_representation)
         spec, tensors, order = [], [], []
         for name in self.loss:
             if name not in _TOWER_KERNELS:
@@ -159,6 +167,8 @@ class LossCalculator(nn.Module):
                 cal_res[name] = fused[name]
             elif name in raw_python:
                 cal_res[name] = raw_python[name]
+            elif name in module_res:
+                cal_res[name] = module_res[name]
 
         loss = 0
         pending_fused = fused_total is not None
@@ -197,7 +207,7 @@ class LossCalculator(nn.Module):
                 tea_out.text_output.last_representation if want_soft else None,
                 self.temperature if want_soft else None, want_hard, want_soft, group=self.contrastive_group)
         for loss_name in self.loss_name:
-            if loss_name == 'cos_diff':         # reference _loss.py:143-145, on the caller's materialised logits
+            if loss_name in ('cos_diff', 'logits_mse'):     # reference _loss.py:138-145, on the caller's materialised logits
                 loss = self.loss[loss_name]
                 cal_res[loss_name] = 0.5 * (loss(stu_out.i2t_logits, tea_out.i2t_logits)
                                             + loss(stu_out.t2i_logits, tea_out.t2i_logits))

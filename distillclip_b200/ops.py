@@ -380,3 +380,44 @@ class TowerLossFn(torch.autograd.Function):
             rescale(groups)
         del groups, all_grads, grads, live
         return (None, None, *ret)
+
+
+# ----------------------------------------------------------------------------------------------
+# row-softmax losses on pooled outputs [B, D]: OutKLLoss / OutCELoss
+# ----------------------------------------------------------------------------------------------
+class RowSoftmaxLossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, stu, tea, temperature, mode):
+        rows, cols = stu.shape
+        saved = torch.empty(rows, 4, dtype=torch.float32, device=stu.device)
+        rowloss = torch.empty(rows, dtype=torch.float64, device=stu.device)
+        _lib.call("dcb_row_softmax_stats", C.c_void_p(stu.data_ptr()), C.c_void_p(tea.data_ptr()), rows, cols, dtype_code(stu),
+                  float(temperature or 1.0), mode, C.c_void_p(saved.data_ptr()), C.c_void_p(rowloss.data_ptr()), _stream_ptr())
+        out = finalize([(rowloss, rows)], [float(temperature) ** 2 if mode == 0 else 1.0 / rows], [1.0])
+        ctx.save_for_backward(stu, tea, saved)
+        ctx.meta = (temperature, mode)
+        return out[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        stu, tea, saved = ctx.saved_tensors
+        temperature, mode = ctx.meta
+        up = g.to(torch.float32).reshape(1).contiguous()
+        grad = torch.empty_like(stu)
+        _lib.call("dcb_row_softmax_grads", C.c_void_p(stu.data_ptr()), C.c_void_p(tea.data_ptr()), stu.shape[0], stu.shape[1],
+                  dtype_code(stu), float(temperature or 1.0), mode, C.c_void_p(saved.data_ptr()), C.c_void_p(up.data_ptr()),
+                  C.c_void_p(grad.data_ptr()), _DT[grad.dtype], _stream_ptr())
+        return grad, None, None, None
+
+
+def row_softmax_loss(stu: torch.Tensor, tea: torch.Tensor, temperature, mode: int):
+    """mode 0 = OutKLLoss (out_kl.py:12-16), mode 1 = OutCELoss (out_ce.py:9-13); [B, D] inputs, softmax over dim 1."""
+    _require_cuda(stu, "student output")
+    _require_cuda(tea, "teacher output")
+    dtype_code(stu)
+    if stu.dim() != 2 or stu.shape != tea.shape:
+        raise ValueError(f"expected equal [B, D] tensors, got {tuple(stu.shape)} and {tuple(tea.shape)}")
+    tea = tea.detach()
+    if tea.dtype != stu.dtype:
+        tea = tea.to(stu.dtype)
+    return RowSoftmaxLossFn.apply(stu.contiguous(), tea.contiguous(), temperature, mode)

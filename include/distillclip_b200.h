@@ -238,6 +238,18 @@ int dcb_logits_row_grads(const void* stu_logits, int64_t stu_rs, int64_t stu_cs,
                          int64_t n, int dtype, float temperature, int mode, const float* saved,
                          const float* upstream, void* grad_logits, int grad_dtype, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Row-softmax losses between pooled outputs [rows, cols] (contiguous):
+ *   mode 0 = OutKLLoss (model/loss_component/out_kl.py:12-16): KLDiv(sum)(log_softmax(s/T), softmax(t/T)) * T^2
+ *   mode 1 = OutCELoss (model/loss_component/out_ce.py:9-13):  CrossEntropy(mean)(s, softmax(t))
+ * saved: float4 per row {max_s, Z_s, max_t, Z_t}; rowloss: double per row (reduce with dcb_finalize, scale T^2 resp.
+ * 1/rows); grads: g = up T (p^s - p^t) resp. up (softmax(s) - p^t) / rows; upstream: device float[1].
+ * --------------------------------------------------------------------------------------------- */
+int dcb_row_softmax_stats(const void* stu, const void* tea, int64_t rows, int64_t cols, int dtype, float temperature, int mode,
+                          float* saved, double* rowloss, void* stream);
+int dcb_row_softmax_grads(const void* stu, const void* tea, int64_t rows, int64_t cols, int dtype, float temperature, int mode,
+                          const float* saved, const float* upstream, void* grad, int grad_dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

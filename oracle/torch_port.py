@@ -93,6 +93,22 @@ def attention_mean_mse(stu: Sequence[torch.Tensor], tea: Sequence[torch.Tensor])
     return acc
 
 
+def out_kl(stu, tea, temperature):
+    # loss_component/out_kl.py:12-16
+    return F.kl_div(F.log_softmax(stu / temperature, dim=1), F.softmax(tea / temperature, dim=1),
+                    reduction="sum") * temperature ** 2
+
+
+def out_ce(stu, tea):
+    # loss_component/out_ce.py:9-13
+    return F.cross_entropy(stu, tea.softmax(dim=1))
+
+
+def logits_mse(stu_logits, tea_logits):
+    # loss_component/logits_mse.py:9-10
+    return F.mse_loss(stu_logits, tea_logits)
+
+
 def _neg_elements(x):
     n = x.shape[0]
     return x.flatten()[:-1].view(n - 1, n + 1)[:, 1:].flatten()      # clip_cos_diff.py:5-8
@@ -124,6 +140,11 @@ def one_tower(names, scale, percent, temperature, stu: Dict, tea: Dict):
             res[n] = out_l1(stu["last_representation"], tea["last_representation"])
         elif n == "out_cos":
             res[n] = out_cos(stu["last_representation"], tea["last_representation"])
+        elif n == "out_kl":
+            assert temperature, "You should give the temperature for the kl loss"
+            res[n] = out_kl(stu["last_representation"], tea["last_representation"], temperature)
+        elif n == "out_ce":
+            res[n] = out_ce(stu["last_representation"], tea["last_representation"])
     loss = 0
     for n, sc in scale.items():
         if n in IMAGE_TEXT_LOSS:
@@ -144,7 +165,7 @@ def two_tower(names, scale, percent, temperature, stu: Dict, tea: Dict):
     for k, v in tres.items():
         res["text_" + k] = v
     s_i2t, s_t2i = clip_logits(stu["visual"]["last_representation"], stu["text"]["last_representation"])
-    if "soft_label" in names or "cos_diff" in names:
+    if "soft_label" in names or "cos_diff" in names or "logits_mse" in names:
         t_i2t, t_t2i = clip_logits(tea["visual"]["last_representation"], tea["text"]["last_representation"])
     for n in names:
         if n == "hard_label":
@@ -154,6 +175,8 @@ def two_tower(names, scale, percent, temperature, stu: Dict, tea: Dict):
             res[n] = 0.5 * (soft_label(s_i2t, t_i2t, temperature) + soft_label(s_t2i, t_t2i, temperature))
         elif n == "cos_diff":
             res[n] = 0.5 * (cos_diff(s_i2t, t_i2t) + cos_diff(s_t2i, t_t2i))
+        elif n == "logits_mse":
+            res[n] = 0.5 * (logits_mse(s_i2t, t_i2t) + logits_mse(s_t2i, t_t2i))
     loss = 0.5 * (il + tl)
     for n, sc in scale.items():
         if n in IMAGE_TEXT_LOSS:

@@ -23,7 +23,8 @@ sys.path.insert(0, REF)
 with contextlib.redirect_stdout(io.StringIO()):
     from model._loss import LossCalculator                      # noqa: E402
     from model.loss_component import (AttentionProbsKL, AttentionProbsMSE, AttentionScoreMSE, CLIPCosDiff,  # noqa: E402
-                                      EmbedMSELoss, HardLabel, HiddenMSE, OutCosLoss, OutL1Loss, SoftLabel)
+                                      EmbedMSELoss, HardLabel, HiddenMSE, LogitsMSE, OutCELoss, OutCosLoss, OutKLLoss,
+                                      OutL1Loss, SoftLabel)
     from model.component.clip_model import CLIPModel             # noqa: E402
     from model.component.output import (CLIPOutput, ControlOutput, TextTransformerOutput,  # noqa: E402
                                         VisionTransformerOutput)
@@ -303,6 +304,20 @@ calc_case("calc_attn_mse_mix",
           dict(loss_name=["attention_probs_mse", "attention_probs_kl", "hidden_rep_mse", "out_l1"],
                loss_scale={"attention_probs_mse": 3.0}),
           "image", tower("image", 3, 4, 6, 24, 2), tower("image", 3, 2, 6, 24, 2))
+
+# ---- section 8f widening, second batch: out_kl / out_ce / logits_mse (drawn after every earlier case so those stay put) ---
+mse_case("out_kl_t2", OutKLLoss(2.0), [bf16(9, 40)], [bf16(9, 40)], as_list=False)
+mse_case("out_kl_t05_wide", OutKLLoss(0.5), [bf16(5, 300, scale=2.0)], [bf16(5, 300, scale=2.0)], as_list=False)
+mse_case("out_ce", OutCELoss(), [bf16(9, 40)], [bf16(9, 40)], as_list=False)
+mse_case("out_ce_wide", OutCELoss(), [bf16(5, 300, scale=3.0)], [bf16(5, 300, scale=3.0)], as_list=False)
+mse_case("logits_mse", LogitsMSE(), [bf16(13, 13, scale=0.3)], [bf16(13, 13, scale=0.3)], as_list=False)
+calc_case("calc_out_kl_ce_logits_mse",
+          dict(loss_name=["out_kl", "out_ce", "logits_mse", "hard_label"], temperature=2.0, loss_scale={"out_kl": 0.1}),
+          "all",
+          (tower("image", 20, 3, 6, 24, 1), tower("text", 20, 2, 7, 16, 1)),
+          (tower("image", 20, 3, 6, 24, 1), tower("text", 20, 2, 7, 16, 1)))
+calc_case("calc_out_kl_ce_image", dict(loss_name=["out_ce", "out_kl", "hidden_rep_mse"], temperature=4.0), "image",
+          tower("image", 6, 3, 6, 24, 2), tower("image", 6, 3, 6, 24, 2))
 
 # ---- host-logic facts (flags, errors) -------------------------------------------------------------
 facts = {}

@@ -137,3 +137,63 @@ def test_shipped_lclip_recipe(cuda_device):
     loss, res = LossCalculator(["out_l1", "out_cos", "cos_diff"])(clip_out(sv, stx), clip_out(tv, ttx), "all")
     loss.backward()
     _check_calc(g, loss, res, _leaves(sv) + _leaves(stx))
+
+
+# ---- second batch: out_kl / out_ce / logits_mse ---------------------------------------------------------------------
+@pytest.mark.parametrize("name,make", [("out_kl_t2", lambda m: m.OutKLLoss(2.0)), ("out_kl_t05_wide", lambda m: m.OutKLLoss(0.5)),
+                                       ("out_ce", lambda m: m.OutCELoss()), ("out_ce_wide", lambda m: m.OutCELoss()),
+                                       ("logits_mse", lambda m: m.LogitsMSE())])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+def test_row_softmax_and_logits_mse_golden(cuda_device, name, make, dtype):
+    import distillclip_b200.model as m
+    g = golden(name)
+    s, t = dev(g["stu0"], dtype, True), dev(g["tea0"], dtype)
+    loss = make(m)(s, t)
+    (3.0 * loss).backward()              # a non-unit upstream gradient
+    assert float(loss.detach()) == pytest.approx(float(g["loss_f64"]), rel=LOSS_RTOL)
+    tol = GRAD_RTOL if dtype == torch.float32 else GRAD_BF16_STORAGE_RTOL
+    assert rel_l2(s.grad.float().cpu().numpy() / 3.0, g["grad0_f64"]) <= tol
+
+
+@pytest.mark.parametrize("mode,temperature", [(0, 1.0), (0, 4.0), (1, None)])
+def test_row_softmax_random_bf16_vs_oracle(cuda_device, mode, temperature):
+    """CLIP-sized pooled outputs (B=256, D=512) in bf16 against the f64 closed form on the same bf16-rounded inputs."""
+    from distillclip_b200 import ops
+    gen = torch.Generator().manual_seed(5)
+    s = (torch.randn(256, 512, generator=gen) * 1.5).to(torch.bfloat16)
+    t = (torch.randn(256, 512, generator=gen) * 1.5).to(torch.bfloat16)
+    sd = s.cuda().requires_grad_(True)
+    loss = ops.row_softmax_loss(sd, t.cuda(), temperature, mode)
+    loss.backward()
+    ref, gref = cf.out_kl(s.float().numpy(), t.float().numpy(), temperature) if mode == 0 else \
+        cf.out_ce(s.float().numpy(), t.float().numpy())
+    assert float(loss.detach()) == pytest.approx(float(ref), rel=LOSS_RTOL)
+    assert rel_l2(sd.grad.float().cpu().numpy(), gref) <= GRAD_BF16_STORAGE_RTOL
+
+
+def test_out_kl_ce_one_tower_recipe(cuda_device):
+    from distillclip_b200.model import LossCalculator, VisionTransformerOutput
+    g = golden("calc_out_kl_ce_image")
+    stu, tea = _tower(g, "stu", VisionTransformerOutput, True), _tower(g, "tea", VisionTransformerOutput, False)
+    loss, res = LossCalculator(["out_ce", "out_kl", "hidden_rep_mse"], temperature=4.0)(stu, tea, "image")
+    assert list(res) == ["out_ce", "out_kl", "hidden_rep_mse"]
+    loss.backward()
+    _check_calc(g, loss, res, _leaves(stu))
+
+
+@pytest.mark.parametrize("fused", [True, False])
+def test_out_kl_ce_logits_mse_two_tower_recipe(cuda_device, fused):
+    from distillclip_b200.model import (CLIPOutput, LossCalculator, TextTransformerOutput, VisionTransformerOutput)
+    g = golden("calc_out_kl_ce_logits_mse")
+    sv, stx = _tower(g, "stu.visual", VisionTransformerOutput, True), _tower(g, "stu.text", TextTransformerOutput, True)
+    tv, ttx = _tower(g, "tea.visual", VisionTransformerOutput, False), _tower(g, "tea.text", TextTransformerOutput, False)
+
+    def clip_out(v, x):
+        a, b = v.last_representation.float(), x.last_representation.float()
+        lg = (a / a.norm(dim=1, keepdim=True)) @ (b / b.norm(dim=1, keepdim=True)).t()
+        return CLIPOutput(visual_output=v, text_output=x, i2t_logits=lg, t2i_logits=lg.T)
+    calc = LossCalculator(["out_kl", "out_ce", "logits_mse", "hard_label"], temperature=2.0, loss_scale={"out_kl": 0.1})
+    calc.fused_contrastive = fused
+    loss, res = calc(clip_out(sv, stx), clip_out(tv, ttx), "all")
+    loss.backward()
+    _check_calc(g, loss, res, _leaves(sv) + _leaves(stx))

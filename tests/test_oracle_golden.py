@@ -201,8 +201,22 @@ def test_cos_diff(name):
     assert tp.cos_diff(torch.tensor(g["stu"]), torch.tensor(g["tea"])).item() == pytest.approx(float(g["loss_f32"]), rel=1e-6)
 
 
+@pytest.mark.parametrize("name,fn,temperature", [("out_kl_t2", "out_kl", 2.0), ("out_kl_t05_wide", "out_kl", 0.5),
+                                                 ("out_ce", "out_ce", None), ("out_ce_wide", "out_ce", None),
+                                                 ("logits_mse", "logits_mse", None)])
+def test_row_softmax_and_logits_mse(name, fn, temperature):
+    g = golden(name)
+    args = (temperature,) if temperature else ()
+    loss, grad = getattr(cf, fn)(g["stu0"], g["tea0"], *args)
+    assert loss == pytest.approx(float(g["loss_f64"]), rel=1e-11)
+    assert np.allclose(grad, g["grad0_f64"], rtol=1e-9, atol=1e-16)
+    t = getattr(tp, fn)(torch.tensor(g["stu0"]), torch.tensor(g["tea0"]), *args)
+    assert t.item() == pytest.approx(float(g["loss_f32"]), rel=1e-6)
+
+
 @pytest.mark.parametrize("name,kind,temperature", [("calc_shipped_image", "one", None), ("calc_shipped_lclip", "two", None),
-                                                   ("calc_attn_mse_mix", "one", None)])
+                                                   ("calc_attn_mse_mix", "one", None), ("calc_out_kl_ce_image", "one", 4.0),
+                                                   ("calc_out_kl_ce_logits_mse", "two", 2.0)])
 def test_calculator_port_shipped_recipes(name, kind, temperature):
     """The loss lists of config/final_config/{image,text,l_clip}.yaml through the torch port."""
     g = golden(name)
