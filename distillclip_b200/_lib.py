@@ -40,7 +40,8 @@ SIGNATURES = {
     "dcb_clip_row_grads": [_vp, _vp, _vp, _vp, _vp, C.c_int64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int64,
                            C.c_int64, C.c_int64, C.c_int, C.c_float, _vp, _vp],
     "dcb_clip_row_grads_pair": [_vp, _vp, _vp, _vp, _vp, C.c_int64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int64,
-                                C.c_int64, C.c_int64, C.c_int, C.c_float, _vp, _vp, _vp, _vp],
+                                C.c_int64, C.c_int64, C.c_int, C.c_float, _vp, _vp, C.c_int64, _vp, _vp, _vp],
+    "dcb_clip_col_grads_from_g": [_vp, C.c_int64, _vp, C.c_int64, C.c_int64, C.c_int64, C.c_int64, _vp, _vp],
     "dcb_clip_grad_finish": [_vp, C.c_int, _vp, _vp, _vp, _vp, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int64,
                              _vp, _vp, _vp, C.c_int, _vp, C.c_int, _vp],
     "dcb_row_softmax_stats": [_vp, _vp, C.c_int64, C.c_int64, C.c_int, C.c_float, C.c_int, _vp, _vp, _vp],
@@ -56,6 +57,7 @@ _SPECIAL = {
     "dcb_clip_grad_splits": (C.c_int, [C.c_int64, C.c_int64, C.c_int64]),
     "dcb_clip_pair_splits": (C.c_int, [C.c_int64, C.c_int64, C.c_int64]),
     "dcb_clip_pair_supported": (C.c_int, [C.c_int64]),
+    "dcb_clip_gt_splits": (C.c_int, [C.c_int64, C.c_int64, C.c_int64]),
     "dcb_tower_grid": (C.c_int, []),
     "dcb_attn_tma_grid": (C.c_int, []),
     "dcb_attn_tma_supported": (C.c_int, [C.c_int, C.c_int64, C.c_int64, C.c_int64]),

@@ -41,6 +41,9 @@ class CudaEngine:
     """Thin wrapper over the C ABI (include/distillclip_b200.h)."""
     #: backward kernel choice: CTA-pair kernel for D <= 768 (default) or the single-CTA D-chunked kernel
     use_pair_kernel = os.environ.get("DCB_BWD_KERNEL", "pair") != "chunk"
+    #: one recompute of the logits for BOTH sides' gradients (G tiles stored in fp16, second side = one GEMM); "0" = one
+    #: pair-kernel pass per side (no O(B^2) scratch)
+    single_pass_backward = os.environ.get("DCB_BWD_SINGLE_PASS", "1") != "0"
     #: tests only: [rows, cols] fp32 buffer that receives the logits the pair kernel's epilogue sees
     dump_pair_logits = None
     #: profiling only: int64 [2, 64, 16] buffer for clock64() stamps of the pair kernel's first cluster
@@ -108,8 +111,17 @@ class CudaEngine:
                   ops._stream_ptr())
         return out
 
-    def row_grads(self, a_s, b_s, a_t, b_t, b_s_t, a_s_inv, b_s_inv, a_t_inv, b_t_inv, coef_row, coef_col,
-                  gmax_row, gmax_col, row_offset, global_batch, temperature, upstream, grad_dtype):
+    def single_pass_supported(self, dim: int) -> bool:
+        """Single-recompute backward: the pair kernel stores its fp16 gradient tiles and the other side's gradient is
+        one GEMM over them (csrc/clip_bwd_gt.cu)."""
+        return bool(self.single_pass_backward and self.use_pair_kernel and _lib.load().dcb_clip_pair_supported(dim))
+
+    def alloc_g(self, rows: int, cols: int, device):
+        return torch.empty(rows, (cols + 7) // 8 * 8, dtype=torch.float16, device=device)
+
+    def row_acc(self, a_s, b_s, a_t, b_t, b_s_t, a_s_inv, b_s_inv, a_t_inv, b_t_inv, coef_row, coef_col,
+                gmax_row, gmax_col, temperature, g_out=None):
+        """acc[s, i, :] = 2^k sum_{j in split s} G_ij b_hat_j (fp32 partial buffers); optionally G 2^k -> g_out (fp16)."""
         rows, dim = a_s.shape
         cols = b_s.shape[0]
         lib = _lib.load()
@@ -120,19 +132,43 @@ class CudaEngine:
             _lib.call("dcb_clip_row_grads_pair", _vp(a_s), _vp(b_s), _vp(a_t), _vp(b_t), _vp(b_s_t), b_s_t.shape[1],
                       _vp(a_s_inv), _vp(b_s_inv), _vp(a_t_inv), _vp(b_t_inv), _vp(coef_row), _vp(coef_col),
                       _vp(gmax_row), _vp(gmax_col), rows, cols, dim, ops.dtype_code(a_s), float(temperature or 1.0),
-                      _vp(acc), _vp(self.dump_pair_logits), _vp(self.trace_pair), ops._stream_ptr())
+                      _vp(acc), _vp(g_out), g_out.shape[1] if g_out is not None else 0,
+                      _vp(self.dump_pair_logits), _vp(self.trace_pair), ops._stream_ptr())
         else:
+            if g_out is not None:
+                raise _lib.DistillClipB200Error("the gradient tiles are only stored by the CTA-pair kernel")
             n_split = lib.dcb_clip_grad_splits(rows, cols, dim)
             acc = torch.empty(n_split, rows, dim, dtype=torch.float32, device=a_s.device)
             _lib.call("dcb_clip_row_grads", _vp(a_s), _vp(b_s), _vp(a_t), _vp(b_t), _vp(b_s_t), b_s_t.shape[1],
                       _vp(a_s_inv), _vp(b_s_inv), _vp(a_t_inv), _vp(b_t_inv), _vp(coef_row), _vp(coef_col),
                       _vp(gmax_row), _vp(gmax_col), rows, cols, dim, ops.dtype_code(a_s), float(temperature or 1.0),
                       _vp(acc), ops._stream_ptr())
+        return acc
+
+    def col_acc_from_g(self, g, a_hat_t, rows: int, cols: int, dim: int):
+        """acc[s, j, :] = sum_{i in split s} G[i, j] 2^k a_hat[i, :]  -- tcgen05 GEMM with A = G^T read MN-major."""
+        n_split = _lib.load().dcb_clip_gt_splits(rows, cols, dim)
+        acc = torch.empty(n_split, cols, dim, dtype=torch.float32, device=g.device)
+        _lib.call("dcb_clip_col_grads_from_g", _vp(g), g.shape[1], _vp(a_hat_t), a_hat_t.shape[1], rows, cols, dim,
+                  _vp(acc), ops._stream_ptr())
+        return acc
+
+    def finish_grads(self, acc, a_s, a_s_inv, b_s, b_s_inv, gmax_row, gmax_col, row_offset, global_batch, upstream,
+                     grad_dtype):
+        """2^-k sum_s acc[s] - label term, then the x/||x|| Jacobian (dcb_clip_grad_finish)."""
+        rows, dim = a_s.shape
         grad = torch.empty(rows, dim, dtype=grad_dtype, device=a_s.device)
-        _lib.call("dcb_clip_grad_finish", _vp(acc), n_split, _vp(a_s), _vp(a_s_inv), _vp(b_s), _vp(b_s_inv), rows, cols,
-                  dim, int(row_offset), int(global_batch), _vp(upstream), _vp(gmax_row), _vp(gmax_col),
+        _lib.call("dcb_clip_grad_finish", _vp(acc), acc.shape[0], _vp(a_s), _vp(a_s_inv), _vp(b_s), _vp(b_s_inv), rows,
+                  b_s.shape[0], dim, int(row_offset), int(global_batch), _vp(upstream), _vp(gmax_row), _vp(gmax_col),
                   ops.dtype_code(a_s), _vp(grad), ops._DT[grad_dtype], ops._stream_ptr())
         return grad
+
+    def row_grads(self, a_s, b_s, a_t, b_t, b_s_t, a_s_inv, b_s_inv, a_t_inv, b_t_inv, coef_row, coef_col,
+                  gmax_row, gmax_col, row_offset, global_batch, temperature, upstream, grad_dtype, g_out=None):
+        acc = self.row_acc(a_s, b_s, a_t, b_t, b_s_t, a_s_inv, b_s_inv, a_t_inv, b_t_inv, coef_row, coef_col,
+                           gmax_row, gmax_col, temperature, g_out)
+        return self.finish_grads(acc, a_s, a_s_inv, b_s, b_s_inv, gmax_row, gmax_col, row_offset, global_batch,
+                                 upstream, grad_dtype)
 
 
 # ==============================================================================================
@@ -154,6 +190,21 @@ def _all_gather_rows(x: torch.Tensor, group, world: int) -> torch.Tensor:
     out = torch.empty((world * x.shape[0],) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
     dist.all_gather_into_tensor(out, x.contiguous(), group=group)
     return out
+
+
+def _reduce_scatter_rows(x: torch.Tensor, group, world: int, rank: int) -> torch.Tensor:
+    """[k, world * n, d] partial sums on every rank -> [k, n, d]: this rank's rows summed over ranks."""
+    if world == 1:
+        return x
+    import torch.distributed as dist
+    n = x.shape[1] // world
+    if dist.get_backend(group) == "nccl":
+        out = torch.empty(x.shape[0], n, x.shape[2], dtype=x.dtype, device=x.device)
+        for k in range(x.shape[0]):
+            dist.reduce_scatter_tensor(out[k], x[k], group=group)
+        return out
+    dist.all_reduce(x, group=group)                  # gloo (CPU tests) has no reduce_scatter
+    return x[:, rank * n:(rank + 1) * n].contiguous()
 
 
 def _all_gather_cols(x: torch.Tensor, group, world: int) -> torch.Tensor:
@@ -200,7 +251,7 @@ def contrastive_forward(engine, si, st, ti, tt, temperature, group=None):
     saved = dict(si=si, st=st, ti=ti, tt=tt, si_all=si_all, st_all=st_all, ti_all=ti_all, tt_all=tt_all,
                  si_inv_all=si_inv_all, st_inv_all=st_inv_all, ti_inv_all=ti_inv_all, tt_inv_all=tt_inv_all,
                  stats_i2t=stats_i2t, stats_t2i=stats_t2i, col_stats=col, offset=offset, b_global=b_global, world=world,
-                 group=group, temperature=temperature, has_teacher=has_teacher)
+                 group=group, rank=rank, temperature=temperature, has_teacher=has_teacher)
     return out, saved
 
 
@@ -222,6 +273,21 @@ def contrastive_backward(engine, saved, upstream, want_img=True, want_txt=True, 
     def local(x):
         return None if x is None else x[loc]
     g_img = g_txt = None
+    dim = s["si"].shape[1]
+    if want_img and want_txt and engine.single_pass_supported(dim):
+        # one recompute: the image-side pass also stores G 2^k [local image rows, all text columns]; the text-side
+        # accumulator is G^T a_hat over the LOCAL image rows, summed across ranks (reduce-scatter to the local text rows)
+        g_tiles = engine.alloc_g(b_local, b_global, s["si"].device)
+        g_img = engine.row_grads(s["si"], s["st_all"], s["ti"], s["tt_all"],
+                                 engine.transpose_norm(s["st_all"], s["st_inv_all"]),
+                                 local(s["si_inv_all"]), s["st_inv_all"], local(s["ti_inv_all"]), s["tt_inv_all"],
+                                 coef_i2t, coef_t2i_all, gmax_i2t, gmax_t2i, offset, b_global, T, upstream,
+                                 grad_dtype or s["si"].dtype, g_out=g_tiles)
+        acc = engine.col_acc_from_g(g_tiles, engine.transpose_norm(s["si"], local(s["si_inv_all"])), b_local, b_global, dim)
+        acc = _reduce_scatter_rows(acc, group, world, s["rank"])
+        g_txt = engine.finish_grads(acc, s["st"], local(s["st_inv_all"]), s["si_all"], s["si_inv_all"], gmax_t2i, gmax_i2t,
+                                    offset, b_global, upstream, grad_dtype or s["st"].dtype)
+        return g_img, g_txt
     if want_img:
         g_img = engine.row_grads(s["si"], s["st_all"], s["ti"], s["tt_all"],
                                  engine.transpose_norm(s["st_all"], s["st_inv_all"]),

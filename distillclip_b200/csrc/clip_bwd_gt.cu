@@ -1,0 +1,263 @@
+// Second half of the single-recompute backward of the fused contrastive / logit-KL losses.
+//
+// clip_bwd_pair_kernel (clip_bwd_pair.cu) recomputes the logits once, forms the scaled fp16 gradient tile
+// G_ij 2^k = dL/dS_ij 2^k (both softmax directions already folded in, see clip_bwd.cu), multiplies it into the a-side
+// gradient acc_a = G b_hat, and -- new -- stores the tile to HBM.  This kernel finishes the b side from the stored tiles,
+//        acc_b[j, :] = sum_i G[i, j] a_hat[i, :]                      (autograd through clip_model.py:37-44 for the other tower)
+// as a plain tcgen05 GEMM, so the executed work of the backward equals its algorithmic minimum
+// (recompute 4 B^2 D + two gradient GEMMs 4 B^2 D) instead of recomputing the logits once per direction.
+// 2 B^2 bytes of G scratch are written once and read once: 2 x 2 GiB at B = 32768, ~0.7 ms of HBM time hidden under
+// ~5 ms of tensor work it replaces ~2.9 ms of.
+//
+// Mapping: cluster of 2 CTAs, tcgen05.mma.cta_group::2 with M = 256 (128 j per CTA), N = one chunk of the embedding
+// dimension (<= 384 columns, two instructions of N/2 when N > 256), K = i in chunks of 64.  A = G^T is read straight
+// from the row-major [i, j] scratch as an MN-major operand: a TMA box {64 j, 64 i} with the 128-byte swizzle IS the
+// canonical MN-major SW128 layout ((8,8,m),(8,k)):((1,8,LBO),(64,SBO)) in 16-bit elements, LBO = 8 KiB between the
+// two 64-wide M blocks, SBO = 1 KiB between 8-row K groups; a K = 16 step advances the start address by 2 KiB.
+// B = a_hat^T [D, rows] fp16 (K-major, the same layout the a-side GEMM uses for b_hat^T), each CTA stages half of
+// the N rows.  K can be split over clusters (fp32 partial buffers, summed by clip_grad_finish).
+// Warps: 0 = TMA, 1 = TMEM alloc + MMA issue (leader), 2-5 = epilogue (TMEM -> fp32 partial buffer).
+#include "tc_common.cuh"
+
+namespace dcb {
+
+namespace gt {
+constexpr int kBK = 64, kUmmaK = 16;
+constexpr int kThreads = 192;
+constexpr int kATile = 128 * kBK * 2;                  // 16 KiB: [2 M blocks][64 k][128 B]
+constexpr int kMaxChunk = 384;                         // N columns per cluster
+constexpr int kSmemBudget = 200 * 1024;
+}  // namespace gt
+
+struct ClipGtParams {
+    float* acc;               // [k_split][cols][dim] fp32
+    int rows, cols, dim;      // rows = i (K), cols = j (M)
+    int chunk;                // N columns per cluster (multiple of 32 when > 256, of 16 otherwise)
+    int pieces;               // MMA instructions per K step (1 or 2), each chunk / pieces wide
+    int n_chunks, m_tiles, k_split;
+    int stages, stage_bytes;
+};
+
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);   // start address
+    d |= static_cast<uint64_t>(8192 >> 4) << 16;               // LBO: next 64-element block along M
+    d |= static_cast<uint64_t>(1024 >> 4) << 32;               // SBO: next group of 8 K rows
+    d |= static_cast<uint64_t>(1) << 46;                       // descriptor version (Blackwell)
+    d |= static_cast<uint64_t>(2) << 61;                       // SWIZZLE_128B
+    return d;
+}
+
+__global__ void __launch_bounds__(gt::kThreads, 1)
+clip_gt_gemm_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_constant__ CUtensorMap map_at,
+                    const __grid_constant__ ClipGtParams p, const uint32_t idesc) {
+    using namespace gt;
+    using namespace tc;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+    const uint32_t ring = smem_base;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_gen + p.stages * p.stage_bytes);
+    const uint32_t bar_full = smem_u32(bars);                    // [stages] leader: bytes of both CTAs landed
+    const uint32_t bar_empty = bar_full + 8 * p.stages;          // [stages] each CTA: slot free (multicast commit)
+    const uint32_t bar_accfull = bar_empty + 8 * p.stages;       // each CTA: accumulator final
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * p.stages + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    int unit = blockIdx.x >> 1;
+    const int nc = unit % p.n_chunks;
+    unit /= p.n_chunks;
+    const int mt = unit % p.m_tiles, ks = unit / p.m_tiles;
+    const int total_kc = (p.rows + kBK - 1) / kBK;
+    const int kc_begin = (int)(((long long)ks * total_kc) / p.k_split);
+    const int kc_end = (int)(((long long)(ks + 1) * total_kc) / p.k_split);
+    const int j0 = mt * 256 + (int)rank * 128;                   // first M row (j) of this CTA
+    const int n0 = nc * p.chunk;                                 // first N column (d) of this cluster
+    const int piece_n = p.chunk / p.pieces;                      // N of one MMA
+    const int half_n = piece_n / 2;                              // B rows staged per CTA per piece
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < p.stages; ++s) {
+            mbar_init(bar_full + 8 * s, 1);
+            mbar_init(bar_empty + 8 * s, 1);
+        }
+        mbar_init(bar_accfull, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc_pair(smem_u32(tmem_slot), 512);
+    tc_fence_before_sync();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (elect_one()) {
+            tma_prefetch_desc(&map_g);
+            tma_prefetch_desc(&map_at);
+            const uint32_t bytes_per_cta = kATile + (uint32_t)p.pieces * half_n * kBK * 2;
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int kc = kc_begin; kc < kc_end; ++kc) {
+                mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+                const uint32_t dst = ring + stage * p.stage_bytes;
+                if (leader) mbar_arrive_expect_tx(bar_full + 8 * stage, 2 * bytes_per_cta);
+                const uint32_t full = map_to_cta(bar_full + 8 * stage, 0);
+                tma_load_2d_pair(dst, &map_g, full, j0, kc * kBK);                       // M block 0: j0 .. j0+63
+                tma_load_2d_pair(dst + 64 * kBK * 2, &map_g, full, j0 + 64, kc * kBK);   // M block 1
+                for (int pc = 0; pc < p.pieces; ++pc)
+                    tma_load_2d_pair(dst + kATile + pc * half_n * kBK * 2, &map_at, full, kc * kBK,
+                                     n0 + pc * piece_n + (int)rank * half_n);
+                if (++stage == p.stages) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        if (leader) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int kc = kc_begin; kc < kc_end; ++kc) {
+                mbar_wait(bar_full + 8 * stage, phase);
+                tc_fence_after_sync();
+                const uint32_t src = ring + stage * p.stage_bytes;
+                if (elect_one()) {
+                    const uint64_t da = umma_desc_mn_sw128(src);
+#pragma unroll
+                    for (int k = 0; k < kBK / kUmmaK; ++k) {
+                        const uint32_t accum = (kc > kc_begin || k > 0) ? 1u : 0u;
+                        for (int pc = 0; pc < p.pieces; ++pc) {
+                            const uint64_t db = umma_desc_k_sw128(src + kATile + pc * half_n * kBK * 2);
+                            umma_f16_pair(tmem_base + pc * piece_n, da + (uint64_t)(k * (2048 >> 4)), db + 2 * k, idesc, accum);
+                        }
+                    }
+                    umma_commit_pair(bar_empty + 8 * stage, 3);
+                    if (kc == kc_end - 1) umma_commit_pair(bar_accfull, 3);
+                }
+                __syncwarp();
+                if (++stage == p.stages) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else {
+        // ------------------------------------------------------------ epilogue: TMEM lane = j, columns = d
+        const int q = warp & 3;
+        const int j = j0 + q * 32 + lane;
+        const bool ok = j < p.cols;
+        float* out = p.acc + ((size_t)ks * p.cols + (ok ? j : 0)) * p.dim + n0;
+        if (kc_end > kc_begin) {
+            mbar_wait(bar_accfull, 0);
+            tc_fence_after_sync();
+        }
+        for (int c0 = 0; c0 < p.chunk; c0 += 32) {
+            if (n0 + c0 >= p.dim) break;
+            float v[32];
+            if (kc_end > kc_begin) {
+                tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c0, v);
+                tmem_ld_wait();
+            } else {
+#pragma unroll
+                for (int c = 0; c < 32; ++c) v[c] = 0.f;
+            }
+            if (ok) {
+#pragma unroll
+                for (int c = 0; c < 32; c += 4) {
+                    const int d = n0 + c0 + c;
+                    if (d + 3 < p.dim) {
+                        *reinterpret_cast<float4*>(out + c0 + c) = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
+                    } else {
+                        for (int e = 0; e < 4; ++e)
+                            if (d + e < p.dim) out[c0 + c + e] = v[c + e];
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 1) {
+        __syncwarp();
+        tc_fence_after_sync();
+        tmem_dealloc_pair(tmem_base, 512);
+    }
+}
+
+struct GtPlan {
+    int chunk, pieces, n_chunks, m_tiles, k_split, stages, stage_bytes;
+};
+
+static GtPlan clip_gt_plan(int64_t rows, int64_t cols, int64_t dim) {
+    GtPlan g{};
+    g.n_chunks = (int)((dim + gt::kMaxChunk - 1) / gt::kMaxChunk);
+    const int64_t per = (dim + g.n_chunks - 1) / g.n_chunks;
+    g.chunk = (int)((per + 31) / 32 * 32);                       // multiple of 32: halves stay 8-row swizzle groups
+    g.pieces = g.chunk > 256 ? 2 : 1;
+    g.m_tiles = (int)((cols + 255) / 256);
+    g.stage_bytes = gt::kATile + g.chunk / 2 * gt::kBK * 2;
+    g.stages = gt::kSmemBudget / g.stage_bytes;
+    if (g.stages > 8) g.stages = 8;
+    const int64_t kcs = (rows + gt::kBK - 1) / gt::kBK;
+    const int64_t slots = kNumSMs / 2;
+    int64_t best = 1;
+    double best_cost = 1e30;
+    for (int64_t n = 1; n <= 16 && n <= kcs; ++n) {
+        const int64_t waves = ((int64_t)g.m_tiles * g.n_chunks * n + slots - 1) / slots;
+        const double cost = (double)waves * ((double)((kcs + n - 1) / n) + 12.0) + 0.5 * (double)n;   // ~12 chunks of fill/drain
+        if (cost < best_cost) { best_cost = cost; best = n; }
+    }
+    g.k_split = (int)best;
+    return g;
+}
+
+}  // namespace dcb
+
+extern "C" int dcb_clip_gt_splits(int64_t rows, int64_t cols, int64_t dim) {
+    return dcb::clip_gt_plan(rows, cols, dim).k_split;
+}
+
+extern "C" int dcb_clip_col_grads_from_g(const void* g, int64_t g_pitch_elems, const void* a_hat_t, int64_t at_pitch_elems,
+                                         int64_t rows, int64_t cols, int64_t dim, float* acc_parts, void* stream) {
+    using namespace dcb;
+    DCB_REQUIRE(g && a_hat_t && acc_parts, "NULL pointer argument");
+    DCB_REQUIRE(rows >= 1 && cols >= 1 && dim >= 8 && dim % 8 == 0, "bad shape");
+    DCB_REQUIRE(g_pitch_elems >= cols && g_pitch_elems % 8 == 0, "G pitch must be >= cols and a multiple of 8 elements");
+    DCB_REQUIRE(at_pitch_elems >= rows && at_pitch_elems % 8 == 0, "a_hat^T pitch must be >= rows and a multiple of 8 elements");
+    const GtPlan plan = clip_gt_plan(rows, cols, dim);
+    CUtensorMap map_g, map_at;
+    if (tc::encode_tile_map_16bit(&map_g, g, rows, cols, (uint64_t)g_pitch_elems * 2, 64)) return 1;
+    if (tc::encode_tile_map_16bit(&map_at, a_hat_t, dim, rows, (uint64_t)at_pitch_elems * 2, plan.chunk / plan.pieces / 2)) return 1;
+    ClipGtParams p{};
+    p.acc = acc_parts;
+    p.rows = (int)rows;
+    p.cols = (int)cols;
+    p.dim = (int)dim;
+    p.chunk = plan.chunk;
+    p.pieces = plan.pieces;
+    p.n_chunks = plan.n_chunks;
+    p.m_tiles = plan.m_tiles;
+    p.k_split = plan.k_split;
+    p.stages = plan.stages;
+    p.stage_bytes = plan.stage_bytes;
+    // fp16 x fp16 -> fp32, M = 256 over the pair, A (= G^T) MN-major (bit 15), B K-major
+    const uint32_t idesc = tc::umma_idesc_f16(256, plan.chunk / plan.pieces, 0) | (1u << 15);
+    const int smem = 1024 + plan.stages * plan.stage_bytes + 8 * (2 * plan.stages + 1) + 16;
+    static int max_set = 0;
+    if (smem > max_set) {
+        DCB_CUDA_OK(cudaFuncSetAttribute(clip_gt_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        max_set = smem;
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)(2 * plan.m_tiles * plan.n_chunks * plan.k_split));
+    cfg.blockDim = dim3(gt::kThreads);
+    cfg.dynamicSmemBytes = (size_t)smem;
+    cfg.stream = static_cast<cudaStream_t>(stream);
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    DCB_CUDA_OK(cudaLaunchKernelEx(&cfg, clip_gt_gemm_kernel, map_g, map_at, p, idesc));
+    return 0;
+}

@@ -57,6 +57,8 @@ struct ClipBwdPairParams {
     const float* gmax_row;
     const float* gmax_col;
     float* acc;               // [n_split][rows][dim] fp32
+    __half* g_out;            // optional [rows][g_ld] fp16: the scaled gradient tiles G 2^k for clip_gt_gemm_kernel (else nullptr)
+    long long g_ld;
     float* dump_s;            // tests only: [rows, cols] student logits as seen by the epilogue
     long long* trace;         // profiling only: clock64 timestamps of cluster 0 (see kTraceSlots), else nullptr
     int rows, cols, dim;
@@ -349,6 +351,13 @@ clip_bwd_pair_kernel(const __grid_constant__ CUtensorMap map_a_stu, const __grid
                 packed[c >> 1] = pack2<__half>(g2[0], g2[1]);
             }
             if (tr) DCB_TRACE(t, 12);
+            if (p.g_out && row_ok) {          // 64 contiguous bytes per thread; the b-side gradient GEMM reads them back (clip_bwd_gt.cu)
+                __half* dst = p.g_out + (size_t)grow * p.g_ld + col0 + cbase;
+#pragma unroll
+                for (int c8 = 0; c8 < 4; ++c8)
+                    if (col0 + cbase + 8 * c8 < p.g_ld)
+                        reinterpret_cast<uint4*>(dst)[c8] = make_uint4(packed[4 * c8], packed[4 * c8 + 1], packed[4 * c8 + 2], packed[4 * c8 + 3]);
+            }
             mbar_wait(bar_gempty, (t & 1) ^ 1);
             if (tr) DCB_TRACE(t, 13);
             // columns [cbase, cbase + 32) of row r -> K-major SW128 sub-tile `half`, 16-byte chunks sub*4 .. sub*4+3
@@ -458,8 +467,8 @@ extern "C" int dcb_clip_row_grads_pair(const void* stu_a, const void* stu_b, con
                                        const float* stu_a_inv, const float* stu_b_inv, const float* tea_a_inv,
                                        const float* tea_b_inv, const float* coef_row, const float* coef_col,
                                        const float* gmax_row, const float* gmax_col, int64_t rows_local, int64_t cols,
-                                       int64_t dim, int dtype, float temperature, float* acc_parts, float* dump_s,
-                                       long long* trace, void* stream) {
+                                       int64_t dim, int dtype, float temperature, float* acc_parts, void* g_out,
+                                       int64_t g_pitch_elems, float* dump_s, long long* trace, void* stream) {
     using namespace dcb;
     DCB_REQUIRE(stu_a && stu_b && stu_b_t && stu_a_inv && stu_b_inv && coef_row && coef_col && gmax_row && gmax_col && acc_parts,
                 "NULL pointer argument");
@@ -467,6 +476,8 @@ extern "C" int dcb_clip_row_grads_pair(const void* stu_a, const void* stu_b, con
     DCB_REQUIRE(dcb_clip_pair_supported(dim), "pair kernel supports 8 <= dim <= 768, dim %% 8 == 0 (got %lld)", (long long)dim);
     DCB_REQUIRE(rows_local >= 1 && cols >= 1, "bad shape");
     DCB_REQUIRE(bt_pitch_elems >= cols && bt_pitch_elems % 8 == 0, "bT pitch must be >= cols and a multiple of 8 elements");
+    DCB_REQUIRE(!g_out || (g_pitch_elems >= cols && g_pitch_elems % 8 == 0 && reinterpret_cast<uintptr_t>(g_out) % 16 == 0),
+                "G scratch: pitch must be >= cols and a multiple of 8 elements, base 16-byte aligned");
     const bool teacher = tea_a != nullptr;
     if (teacher) DCB_REQUIRE(tea_b && tea_a_inv && tea_b_inv && temperature > 0.f, "teacher arguments incomplete");
     const int nt = clip_bwd_pair_nt(dim);
@@ -492,6 +503,8 @@ extern "C" int dcb_clip_row_grads_pair(const void* stu_a, const void* stu_b, con
     p.gmax_row = gmax_row;
     p.gmax_col = gmax_col;
     p.acc = acc_parts;
+    p.g_out = static_cast<__half*>(g_out);
+    p.g_ld = g_pitch_elems;
     p.dump_s = dump_s;
     p.trace = trace;
     p.rows = (int)rows_local;

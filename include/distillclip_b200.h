@@ -211,7 +211,18 @@ int dcb_clip_row_grads_pair(const void* stu_a, const void* stu_b, const void* te
                             const float* stu_a_inv, const float* stu_b_inv, const float* tea_a_inv, const float* tea_b_inv,
                             const float* coef_row, const float* coef_col, const float* gmax_row, const float* gmax_col,
                             int64_t rows_local, int64_t cols, int64_t dim, int dtype, float temperature,
-                            float* acc_parts, float* dump_s, long long* trace, void* stream);
+                            float* acc_parts, void* g_out, int64_t g_pitch_elems, float* dump_s, long long* trace,
+                            void* stream);
+
+/* Single-recompute backward: when g_out != NULL the pair kernel also stores its scaled fp16 gradient tiles
+ * G[i, j] 2^k = dL/dS_ij 2^k ([rows_local, g_pitch_elems], pitch >= cols, multiple of 8) and the b-side accumulator
+ *     acc_b[j, :] = sum_i G[i, j] a_hat[i, :]
+ * comes from one tcgen05 GEMM over the stored tiles (A = G^T read as an MN-major operand) instead of a second
+ * recompute of the logits.  a_hat_t: [dim, at_pitch_elems] fp16 from dcb_transpose_norm_f16 of the a side.
+ * acc_parts: dcb_clip_gt_splits(...) buffers of [cols, dim] fp32 for dcb_clip_grad_finish (same 2^k scale). */
+int dcb_clip_gt_splits(int64_t rows, int64_t cols, int64_t dim);
+int dcb_clip_col_grads_from_g(const void* g, int64_t g_pitch_elems, const void* a_hat_t, int64_t at_pitch_elems,
+                              int64_t rows, int64_t cols, int64_t dim, float* acc_parts, void* stream);
 
 /* grad_a[i,:] = r_i (acc_i - a_hat_i (a_hat_i . acc_i)),  acc_i = 2^-k sum_s acc_parts[s][i,:] - (gh/B) b_hat_{row_offset+i}
  * (the -[i==j] label term of the cross entropy, added here in fp32, then the x/||x|| Jacobian of clip_model.py:37-38). */

@@ -69,20 +69,47 @@ class DoubleEngine:
     def transpose_norm(self, b, b_inv):
         return (b.double() * b_inv[:, None]).t().contiguous()
 
-    def row_grads(self, a_s, b_s, a_t, b_t, b_s_t, a_s_inv, b_s_inv, a_t_inv, b_t_inv, coef_row, coef_col,
-                  gmax_row, gmax_col, row_offset, global_batch, temperature, upstream, grad_dtype):
+    single_pass_backward = True
+
+    def single_pass_supported(self, dim):
+        return self.single_pass_backward
+
+    def alloc_g(self, rows, cols, device):
+        return torch.zeros(rows, (cols + 7) // 8 * 8, dtype=torch.float64)
+
+    @staticmethod
+    def _scale(gmax_row, gmax_col):
+        return 2.0 ** (14 - torch.frexp(gmax_row + gmax_col)[1].item())     # the fp16 tile scale of the kernel
+
+    def row_acc(self, a_s, b_s, a_t, b_t, b_s_t, a_s_inv, b_s_inv, a_t_inv, b_t_inv, coef_row, coef_col,
+                gmax_row, gmax_col, temperature, g_out=None):
         S = self._logits(a_s, b_s, a_s_inv, b_s_inv)
         G = torch.exp(S - 1) * (coef_row[0][:, None] + coef_col[0][None, :])
         if a_t is not None:
             T = self._logits(a_t, b_t, a_t_inv, b_t_inv)
             G = G + torch.exp((S - 1) / temperature) * (coef_row[1][:, None] + coef_col[1][None, :])
             G = G - torch.exp((T - 1) / temperature) * (coef_row[2][:, None] + coef_col[2][None, :])
-        scale = 2.0 ** (14 - torch.frexp(gmax_row + gmax_col)[1].item())     # the fp16 tile scale of the kernel
+        scale = self._scale(gmax_row, gmax_col)
         assert float((G.abs() * scale).max()) <= 2.0 ** 14
-        acc = ((G * scale) @ b_s_t.t()) / scale                        # sum_j G_ij b_hat_j
+        if g_out is not None:
+            g_out[:, :G.shape[1]] = G * scale
+        return ((G * scale) @ b_s_t.t())[None]                       # 2^k sum_j G_ij b_hat_j, one split
+
+    def col_acc_from_g(self, g, a_hat_t, rows, cols, dim):
+        return (g[:rows, :cols].t() @ a_hat_t.t()[:rows])[None]      # 2^k sum_i G_ij a_hat_i
+
+    def finish_grads(self, acc, a_s, a_s_inv, b_s, b_s_inv, gmax_row, gmax_col, row_offset, global_batch, upstream,
+                     grad_dtype):
+        acc = acc.sum(0) / self._scale(gmax_row, gmax_col)
         rows = a_s.shape[0]
         gi = row_offset + torch.arange(rows)
         acc = acc - (upstream[0].double() / global_batch) * b_s_inv[gi][:, None] * b_s.double()[gi]
         a_hat = a_s.double() * a_s_inv[:, None]
-        grad = a_s_inv[:, None] * (acc - a_hat * (a_hat * acc).sum(1, keepdim=True))
-        return grad
+        return a_s_inv[:, None] * (acc - a_hat * (a_hat * acc).sum(1, keepdim=True))
+
+    def row_grads(self, a_s, b_s, a_t, b_t, b_s_t, a_s_inv, b_s_inv, a_t_inv, b_t_inv, coef_row, coef_col,
+                  gmax_row, gmax_col, row_offset, global_batch, temperature, upstream, grad_dtype, g_out=None):
+        acc = self.row_acc(a_s, b_s, a_t, b_t, b_s_t, a_s_inv, b_s_inv, a_t_inv, b_t_inv, coef_row, coef_col,
+                           gmax_row, gmax_col, temperature, g_out)
+        return self.finish_grads(acc, a_s, a_s_inv, b_s, b_s_inv, gmax_row, gmax_col, row_offset, global_batch,
+                                 upstream, grad_dtype)

@@ -16,26 +16,28 @@ from distillclip_b200 import contrastive as ct
 CLIP = ["clip_b24_d32_t2", "clip_b40_d64_t4", "clip_b130_d72_t1"]
 
 
-def _run(g, w_hard, w_soft, group=None, rows=slice(None)):
+def _run(g, w_hard, w_soft, group=None, rows=slice(None), single_pass=True):
     T = float(g["temperature"])
     si, st = torch.tensor(g["stu_img"])[rows], torch.tensor(g["stu_txt"])[rows]
     ti, tt = torch.tensor(g["tea_img"])[rows], torch.tensor(g["tea_txt"])[rows]
     eng = DoubleEngine()
+    eng.single_pass_backward = single_pass      # stored gradient tiles + G^T GEMM (+ reduce-scatter) vs one recompute per side
     out, saved = ct.contrastive_forward(eng, si, st, ti, tt, T, group)
     up = torch.tensor([w_hard, w_soft], dtype=torch.float32)
     gi, gt = ct.contrastive_backward(eng, saved, up)
     return out, gi, gt
 
 
+@pytest.mark.parametrize("single_pass", [True, False])
 @pytest.mark.parametrize("name", CLIP)
-def test_decomposition_matches_reference_golden(name):
+def test_decomposition_matches_reference_golden(name, single_pass):
     g = golden(name)
-    out, gi, gt = _run(g, 1.0, 0.0)
+    out, gi, gt = _run(g, 1.0, 0.0, single_pass=single_pass)
     assert float(out[0]) == pytest.approx(float(g["hard_f64"]), rel=1e-10)
     assert float(out[1]) == pytest.approx(float(g["soft_f64"]), rel=1e-9)
     assert rel_l2(gi.numpy(), g["dhard_img_f64"]) <= 1e-9
     assert rel_l2(gt.numpy(), g["dhard_txt_f64"]) <= 1e-9
-    out, gi, gt = _run(g, 0.0, 1.0)
+    out, gi, gt = _run(g, 0.0, 1.0, single_pass=single_pass)
     assert rel_l2(gi.numpy(), g["dsoft_img_f64"]) <= 1e-8
     assert rel_l2(gt.numpy(), g["dsoft_txt_f64"]) <= 1e-8
 
@@ -50,20 +52,20 @@ def test_hard_only_without_teacher():
     assert rel_l2(gi.numpy(), g["dhard_img_f64"]) <= 1e-9
 
 
-def _worker(rank, world, port, name, q):
+def _worker(rank, world, port, name, single_pass, q):
     import torch.distributed as dist
     sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
     dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
     g = golden(name)
     b = g["stu_img"].shape[0] // world
-    out, gi, gt = _run(g, 0.75, 0.5, group=dist.group.WORLD, rows=slice(rank * b, (rank + 1) * b))
+    out, gi, gt = _run(g, 0.75, 0.5, group=dist.group.WORLD, rows=slice(rank * b, (rank + 1) * b), single_pass=single_pass)
     q.put((rank, out.numpy(), gi.numpy(), gt.numpy()))
     dist.barrier()
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("name", ["clip_b24_d32_t2", "clip_b40_d64_t4"])
-def test_row_sharded_world2_gloo(name):
+@pytest.mark.parametrize("name,single_pass", [("clip_b24_d32_t2", True), ("clip_b40_d64_t4", True), ("clip_b40_d64_t4", False)])
+def test_row_sharded_world2_gloo(name, single_pass):
     """Each of 2 ranks holds half the rows; the result must equal the single-process global-batch oracle
     (the oracle of the sharded path is the reference on the concatenated batch)."""
     g = golden(name)
@@ -72,7 +74,7 @@ def test_row_sharded_world2_gloo(name):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = 29500 + os.getpid() % 2000
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, name, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, name, single_pass, q)) for r in range(2)]
     for p in procs:
         p.start()
     res = sorted([q.get(timeout=120) for _ in range(2)], key=lambda x: x[0])

@@ -58,14 +58,39 @@ def test_similarity_tiles_match_matmul(cuda_device, b, d):
     assert rel_l2(col[3].cpu().numpy(), (et * (t_ref - s_ref)).sum(0)) <= 1e-4
 
 
-@pytest.fixture(params=["pair", "chunk"])
+@pytest.fixture(params=["single_pass", "pair", "chunk"])
 def bwd_kernel(request):
-    """Both backward kernels: the CTA-pair kernel (default, D <= 768) and the single-CTA D-chunked kernel."""
+    """The three backward routes: CTA-pair kernel storing its gradient tiles + G^T GEMM for the other side (default,
+    D <= 768), one CTA-pair pass per side, and the single-CTA D-chunked kernel."""
     from distillclip_b200 import contrastive as ct
-    old = ct.CudaEngine.use_pair_kernel
-    ct.CudaEngine.use_pair_kernel = request.param == "pair"
+    old = ct.CudaEngine.use_pair_kernel, ct.CudaEngine.single_pass_backward
+    ct.CudaEngine.use_pair_kernel = request.param != "chunk"
+    ct.CudaEngine.single_pass_backward = request.param == "single_pass"
     yield request.param
-    ct.CudaEngine.use_pair_kernel = old
+    ct.CudaEngine.use_pair_kernel, ct.CudaEngine.single_pass_backward = old
+
+
+@pytest.mark.parametrize("rows,cols,d", [(64, 256, 32), (130, 130, 72), (300, 520, 512), (1030, 700, 768), (257, 64, 8),
+                                         (2048, 1024, 1024)])
+def test_gt_gemm_matches_matmul(cuda_device, rows, cols, d):
+    """clip_gt_gemm_kernel alone: acc[j, :] = sum_i G[i, j] a_hatT[:, i] with G read as an MN-major tcgen05 operand
+    (TMA box {64 j, 64 i}), ragged edges zero-filled, K split over clusters.  fp16 products are exact in fp32, so the
+    only difference to a float64 matmul is fp32 summation order."""
+    from distillclip_b200.contrastive import CudaEngine
+    gen = torch.Generator().manual_seed(rows + cols + d)
+    eng = CudaEngine()
+    g = eng.alloc_g(rows, cols, "cuda")
+    g.fill_(float("nan"))                                        # pitch padding must never be read
+    g[:, :cols] = torch.randn(rows, cols, generator=gen).to(torch.float16).cuda()
+    pitch = (rows + 7) // 8 * 8
+    a_hat_t = torch.full((d, pitch), float("nan"), dtype=torch.float16, device="cuda")
+    a_hat_t[:, :rows] = (torch.randn(d, rows, generator=gen) / 8).to(torch.float16).cuda()
+    acc = eng.col_acc_from_g(g, a_hat_t, rows, cols, d)
+    ref = g[:, :cols].double().t() @ a_hat_t[:, :rows].double().t()
+    got = acc.double().sum(0)
+    assert got.shape == ref.shape
+    assert torch.isfinite(got).all()
+    assert float((got - ref).abs().max()) <= 2e-5 * float(ref.abs().max()) + 1e-6
 
 
 @pytest.mark.parametrize("b,d", [(130, 72), (256, 512), (300, 200), (384, 768)])
