@@ -1,0 +1,74 @@
+"""Row-sharded contrastive path over NCCL on >= 2 GPUs (skipped on a single-GPU box): every rank owns B/R rows of the
+four embedding matrices; losses and gradients must equal the single-process global-batch oracle, for
+both backward routes (stored gradient tiles + reduce-scatter of the G^T GEMM, and one recompute per side)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+from conftest import rel_l2
+from oracle import closed_form as cf
+
+pytestmark = pytest.mark.gpu
+LOSS_RTOL, GRAD_BF16_STORAGE_RTOL = 1e-4, 4e-3
+
+
+def _inputs(b, d, seed):
+    gen = torch.Generator().manual_seed(seed)
+    mk = lambda: torch.randn(b, d, generator=gen).to(torch.bfloat16)
+    si, st = mk(), mk()
+    ti = (si.float() + 0.5 * torch.randn(b, d, generator=gen)).to(torch.bfloat16)
+    tt = (st.float() + 0.5 * torch.randn(b, d, generator=gen)).to(torch.bfloat16)
+    return si, st, ti, tt
+
+
+def _worker(rank, world, port, b, d, T, single_pass, q):
+    import torch.distributed as dist
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world,
+                            device_id=torch.device("cuda", rank))
+    from distillclip_b200 import contrastive as ct
+    ct.CudaEngine.single_pass_backward = single_pass
+    n = b // world
+    rows = slice(rank * n, (rank + 1) * n)
+    si, st, ti, tt = [x[rows].cuda() for x in _inputs(b, d, 11)]
+    si.requires_grad_(True)
+    st.requires_grad_(True)
+    res = ct.clip_contrastive(si, st, ti, tt, T, True, True, group=dist.group.WORLD)
+    (0.6 * res["hard_label"] + 0.4 * res["soft_label"]).backward()
+    torch.cuda.synchronize()
+    q.put((rank, float(res["hard_label"].detach()), float(res["soft_label"].detach()),
+           si.grad.float().cpu().numpy(), st.grad.float().cpu().numpy()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("single_pass", [True, False])
+@pytest.mark.parametrize("b,d,T", [(1024, 256, 2.0), (768, 768, 1.0)])
+def test_nccl_row_sharded_matches_oracle(cuda_device, b, d, T, single_pass):
+    world = min(torch.cuda.device_count(), 4)
+    if world < 2:
+        pytest.skip("needs >= 2 GPUs")
+    if b % world:
+        world = 2
+    si, st, ti, tt = _inputs(b, d, 11)
+    ref = cf.contrastive_from_embeddings(*[x.float().numpy() for x in (si, st, ti, tt)], T, w_hard=0.6, w_soft=0.4)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_worker, args=(r, world, port, b, d, T, single_pass, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=240) for _ in range(world)], key=lambda x: x[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for _, hard, soft, _, _ in res:
+        assert hard == pytest.approx(ref["hard"], rel=LOSS_RTOL)
+        assert soft == pytest.approx(ref["soft"], rel=LOSS_RTOL)
+    assert rel_l2(np.concatenate([r[3] for r in res]), ref["d_img"]) <= GRAD_BF16_STORAGE_RTOL
+    assert rel_l2(np.concatenate([r[4] for r in res]), ref["d_txt"]) <= GRAD_BF16_STORAGE_RTOL
