@@ -419,6 +419,7 @@ static int clip_bwd_pair_splits(int64_t rows, int64_t cols, int64_t dim) {
     const int64_t row_blocks = (rows + 127) / 128;
     const int64_t col_tiles = (cols + clip_bwd_pair_nt(dim) - 1) / clip_bwd_pair_nt(dim);
     const int64_t slots = kNumSMs / 2;                   // clusters resident at once
+    if (const char* e = getenv("DCB_DEBUG_SPLITS")) return atoi(e) > 0 ? atoi(e) : 1;     // profiling experiments only
     int64_t best = 1;
     double best_cost = 1e30;
     for (int64_t n = 1; n <= 32 && n <= col_tiles; ++n) {

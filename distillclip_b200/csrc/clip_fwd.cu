@@ -404,6 +404,7 @@ __global__ void __launch_bounds__(128) clip_colfinish_kernel(const float* __rest
 static int clip_fwd_splits(int64_t rows, int64_t cols) {
     const int64_t row_blocks = (rows + fwd::kBM - 1) / fwd::kBM;
     const int64_t col_tiles = (cols + fwd::kBN - 1) / fwd::kBN;
+    if (const char* e = getenv("DCB_DEBUG_SPLITS")) return atoi(e) > 0 ? atoi(e) : 1;     // profiling experiments only
     int64_t best = 1;
     double best_cost = 1e30;
     for (int64_t n = 1; n <= 64 && n <= col_tiles; ++n) {
