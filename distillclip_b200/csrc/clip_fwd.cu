@@ -5,10 +5,14 @@
 //   HardLabel.forward   CrossEntropy(mean) vs arange(B)                      (reference model/loss_component/hard_label.py:10-12)
 //   SoftLabel.forward   softmax(./T), .log(), KLDiv(sum) * T^2               (reference model/loss_component/soft_label.py:11-16)
 //
-// One CTA owns a block of 128 "a-side" rows and walks a range of 128-wide "b-side" column tiles.  Per tile the
-// raw bf16/fp16 embeddings stream through a TMA -> shared-memory ring (64-wide K chunks, 128 B swizzle) into
-// tcgen05.mma (M=128, N=128, K=16) with the student and the teacher similarity accumulators side by side in
-// TMEM, double-buffered (2 x (128 + 128) = 512 columns) so the MMAs of tile n+1 overlap the epilogue of tile n.
+// A cluster of two CTAs (one TPC) owns 256 "a-side" rows, 128 per CTA, and walks a range of 128-wide "b-side" column
+// tiles.  Per tile the raw bf16/fp16 embeddings stream through a TMA -> shared-memory ring (64-wide K chunks, 128 B
+// swizzle) into tcgen05.mma.cta_group::2 (M=256, N=128, K=16): each CTA stages its own 128 a-rows and only HALF of the
+// b-side tile (64 rows), so a K chunk costs 48 KiB of TMA traffic per SM instead of 64 -- one SM's TMA engine pulls
+// at most ~78 B/clk (scripts/probe/tma_probe.cu) against the 125 B/clk a 128x128 single-CTA tile needs to keep the
+// tensor pipe busy, and the kernel was bound exactly there (r01q).  The leader CTA issues the MMAs; student and teacher
+// similarity accumulators sit side by side in each CTA's TMEM, double-buffered (2 x (128 + 128) = 512 columns), so the
+// MMAs of tile n+1 overlap the epilogue of tile n.
 // The epilogue warps read the accumulators with tcgen05.ld (one row per thread), apply the fp32 inverse norms
 // (logit = acc * r_i * c_j, so normalised embeddings are never rounded to bf16) and accumulate per row
 //   A  = sum_j exp(S_ij - 1)            Zs = sum_j exp((S_ij - 1)/T)
@@ -16,20 +20,25 @@
 // Cosine logits are bounded by 1, so 1 is a valid softmax shift for every row: the sums of different column
 // ranges simply add (no running max, no rescaling), which is what lets a row be split over CTAs and ranks.
 //
-// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2-9 = epilogue.
-// Epilogue warp w reads TMEM lanes 32 (w % 4) .. and the columns [64 sub, 64 sub + 64) of the tile, sub = (w - 2) / 4:
-// two warps per scheduler hide the MUFU / FMA latency (a single warp per scheduler issued every ~3 cycles, ncu r01d).
-// The two column halves of a row are accumulated separately and added by the combine kernel.
+// Warp roles (576 threads): warp 0 = TMA producer, warp 1 = TMEM allocator (+ MMA issuer in the leader), warps 2-17 = epilogue.
+// Epilogue warp w reads TMEM lanes 32 (w % 4) .. and the columns [32 sub, 32 sub + 32) of the tile, sub = (w - 2) / 4,
+// 16 columns at a time: four warps per scheduler hide the MUFU / FMA / shuffle latency (one warp per scheduler issued
+// every ~3 cycles, ncu r01d; two reached 48 % issue utilisation with the epilogue setting the tile time, r01q).
+// The four column quarters of a row are accumulated separately and added by the combine kernel.
 #include "tc_common.cuh"
 
 namespace dcb {
 
 namespace fwd {
 constexpr int kBM = 128, kBN = 128, kBK = 64, kUmmaK = 16;
-constexpr int kStages = 3;
-constexpr int kTileBytes = kBM * kBK * 2;                 // 16 KiB: one [128 x 64] 16-bit operand tile
-constexpr int kStageBytes = 4 * kTileBytes;               // a_stu, b_stu, a_tea, b_tea
-constexpr int kThreads = 320;                            // 2 control warps + 8 epilogue warps (2 per scheduler)
+constexpr int kStages = 4;
+constexpr int kTileBytes = kBM * kBK * 2;                 // 16 KiB: one [128 x 64] 16-bit a-side tile
+constexpr int kBHalfRows = kBN / 2;                       // b rows staged per CTA
+constexpr int kBTileBytes = kBHalfRows * kBK * 2;         // 8 KiB
+constexpr int kStageBytes = 2 * kTileBytes + 2 * kBTileBytes;   // a_stu, a_tea, b_stu half, b_tea half = 48 KiB
+constexpr int kThreads = 576;                            // 2 control warps + 16 epilogue warps (4 per scheduler)
+constexpr int kEpiThreads = kThreads - 64;
+constexpr int kSubs = 4;                                 // column quarters of a tile, one per epilogue warp of a lane quadrant
 constexpr int kTmemCols = 512;
 constexpr int kColBufBytes = 2 * 4 * 4 * kBN * 4;          // [tile parity][lane quadrant][stat][column] fp32
 constexpr int kSmemBytes = 1024 /*align slack*/ + kStages * kStageBytes + 2 * 2 * kBN * 4 + 256 + kColBufBytes;
@@ -40,7 +49,7 @@ struct ClipFwdParams {
     const float* b_inv_stu;   // [cols]
     const float* a_inv_tea;
     const float* b_inv_tea;
-    float* ws;                // [2 * n_split][4][rows] partial sums (x2: the two epilogue warps of a row)
+    float* ws;                // [kSubs * n_split][4][rows] partial sums (x kSubs: the epilogue warps of a row)
     float* diag;              // [rows] S_ii
     float* col_part;          // [row_blocks][4][cols] column sums of the same four statistics over each block of 128 rows
                               // (= the row statistics of the OPPOSITE direction, reduced later), or nullptr
@@ -88,14 +97,17 @@ clip_fwd_kernel(const __grid_constant__ CUtensorMap map_a_stu, const __grid_cons
     float* scale_buf = reinterpret_cast<float*>(smem_gen + kStages * kStageBytes);   // [2 buf][2 stu/tea][128]
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_gen + kStages * kStageBytes + 2 * 2 * kBN * 4);
     float* col_buf = reinterpret_cast<float*>(smem_gen + kStages * kStageBytes + 2 * 2 * kBN * 4 + 256);   // [2][4][4][128]
-    const uint32_t bar_full = smem_u32(bars);                   // [kStages]
-    const uint32_t bar_empty = bar_full + 8 * kStages;          // [kStages]
-    const uint32_t bar_tfull = bar_empty + 8 * kStages;         // [2]
-    const uint32_t bar_tempty = bar_tfull + 16;                 // [2]
+    const uint32_t bar_full = smem_u32(bars);                   // [kStages] leader: TMA bytes of both CTAs
+    const uint32_t bar_empty = bar_full + 8 * kStages;          // [kStages] each CTA: slot free (multicast commit)
+    const uint32_t bar_tfull = bar_empty + 8 * kStages;         // [2] each CTA: accumulators complete (multicast commit)
+    const uint32_t bar_tempty = bar_tfull + 16;                 // [2] leader: 8 epilogue warps of both CTAs drained them
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int rb = blockIdx.x / p.n_split, sp = blockIdx.x % p.n_split;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int cluster_id = blockIdx.x >> 1;
+    const int rb = (cluster_id / p.n_split) * 2 + (int)rank, sp = cluster_id % p.n_split;
     const int tile_begin = (int)(((long long)sp * p.col_tiles) / p.n_split);
     const int tile_end = (int)(((long long)(sp + 1) * p.col_tiles) / p.n_split);
     const int n_tiles = tile_end - tile_begin;
@@ -109,15 +121,17 @@ clip_fwd_kernel(const __grid_constant__ CUtensorMap map_a_stu, const __grid_cons
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(bar_tfull + 8 * s, 1);
-            mbar_init(bar_tempty + 8 * s, 8);     // one arrive per epilogue warp
+            mbar_init(bar_tempty + 8 * s, 32);    // one arrive per epilogue warp of both CTAs
         }
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc(smem_u32(tmem_slot), kTmemCols);
+    if (warp == 1) tmem_alloc_pair(smem_u32(tmem_slot), kTmemCols);
     tc_fence_before_sync();
     __syncthreads();
+    cluster_sync_all();                                          // peer barriers initialised, both TMEM allocations done
     tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
+    const uint32_t l_tempty = map_to_cta(bar_tempty, 0);         // the leader's barriers as seen from this CTA
 
     if (warp == 0) {
         // ---------------------------------------------------------------- TMA producer
@@ -131,27 +145,27 @@ clip_fwd_kernel(const __grid_constant__ CUtensorMap map_a_stu, const __grid_cons
             int stage = 0;
             uint32_t phase = 0;
             for (int t = 0; t < n_tiles; ++t) {
-                const int col0 = (tile_begin + t) * kBN;
+                const int col0 = (tile_begin + t) * kBN + (int)rank * kBHalfRows;       // this CTA's half of the b tile
                 for (int kc = 0; kc < n_kc; ++kc) {
                     mbar_wait(bar_empty + 8 * stage, phase ^ 1);
                     const uint32_t dst = ring + stage * kStageBytes;
-                    const uint32_t full = bar_full + 8 * stage;
-                    mbar_arrive_expect_tx(full, (kTeacher ? 4 : 2) * kTileBytes);
-                    tma_load_2d(dst, &map_a_stu, full, kc * kBK, row0);
-                    tma_load_2d(dst + kTileBytes, &map_b_stu, full, kc * kBK, col0);
+                    if (leader) mbar_arrive_expect_tx(bar_full + 8 * stage, 2 * (kTeacher ? 2 : 1) * (kTileBytes + kBTileBytes));
+                    const uint32_t full = map_to_cta(bar_full + 8 * stage, 0);
+                    tma_load_2d_pair(dst, &map_a_stu, full, kc * kBK, row0);
+                    tma_load_2d_pair(dst + 2 * kTileBytes, &map_b_stu, full, kc * kBK, col0);
                     if (kTeacher) {
-                        tma_load_2d(dst + 2 * kTileBytes, &map_a_tea, full, kc * kBK, row0);
-                        tma_load_2d(dst + 3 * kTileBytes, &map_b_tea, full, kc * kBK, col0);
+                        tma_load_2d_pair(dst + kTileBytes, &map_a_tea, full, kc * kBK, row0);
+                        tma_load_2d_pair(dst + 2 * kTileBytes + kBTileBytes, &map_b_tea, full, kc * kBK, col0);
                     }
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
-        // ---------------------------------------------------------------- MMA issuer: warp-uniform waits, one elected lane issues
+        // ---------------------------------------------------------------- MMA issuer (leader CTA): warp-uniform waits, one elected lane issues
         int stage = 0;
         uint32_t phase = 0;
-        for (int t = 0; t < n_tiles; ++t) {
+        for (int t = 0; leader && t < n_tiles; ++t) {
             const int as = t & 1;                       // accumulator stage
             const uint32_t aphase = (t >> 1) & 1;
             mbar_wait(bar_tempty + 8 * as, aphase ^ 1);
@@ -163,27 +177,28 @@ clip_fwd_kernel(const __grid_constant__ CUtensorMap map_a_stu, const __grid_cons
                 tc_fence_after_sync();
                 const uint32_t src = ring + stage * kStageBytes;
                 if (elect_one()) {
-                    const uint64_t da_s = umma_desc_k_sw128(src), db_s = umma_desc_k_sw128(src + kTileBytes);
-                    const uint64_t da_t = umma_desc_k_sw128(src + 2 * kTileBytes), db_t = umma_desc_k_sw128(src + 3 * kTileBytes);
+                    const uint64_t da_s = umma_desc_k_sw128(src), da_t = umma_desc_k_sw128(src + kTileBytes);
+                    const uint64_t db_s = umma_desc_k_sw128(src + 2 * kTileBytes);
+                    const uint64_t db_t = umma_desc_k_sw128(src + 2 * kTileBytes + kBTileBytes);
 #pragma unroll
                     for (int k = 0; k < kBK / kUmmaK; ++k) {
                         const uint32_t accum = (kc > 0 || k > 0) ? 1u : 0u;
-                        umma_f16(acc_s, da_s + 2 * k, db_s + 2 * k, idesc, accum);     // +32 B per K=16 step
-                        if (kTeacher) umma_f16(acc_t, da_t + 2 * k, db_t + 2 * k, idesc, accum);
+                        umma_f16_pair(acc_s, da_s + 2 * k, db_s + 2 * k, idesc, accum);     // +32 B per K=16 step
+                        if (kTeacher) umma_f16_pair(acc_t, da_t + 2 * k, db_t + 2 * k, idesc, accum);
                     }
-                    umma_commit(bar_empty + 8 * stage);     // frees the smem slot once these MMAs retire
-                    if (kc == n_kc - 1) umma_commit(bar_tfull + 8 * as);     // accumulators of this tile are complete
+                    umma_commit_pair(bar_empty + 8 * stage, 3);     // frees the slot in both CTAs once these MMAs retire
+                    if (kc == n_kc - 1) umma_commit_pair(bar_tfull + 8 * as, 3);     // accumulators of this tile are complete
                 }
                 __syncwarp();
                 if (++stage == kStages) { stage = 0; phase ^= 1; }
             }
         }
     } else {
-        // ---------------------------------------------------------------- epilogue: 4 warps, one row per thread
+        // ---------------------------------------------------------------- epilogue: 16 warps, one row per thread
         const int q = warp & 3;                             // TMEM lane quadrant this warp may read
-        const int sub = (warp - 2) >> 2;                    // column half of the tile handled by this warp
+        const int sub = (warp - 2) >> 2;                    // column quarter of the tile handled by this warp
         const int r = q * 32 + lane;                        // row inside the block
-        const int ep_tid = (warp - 2) * 32 + lane;          // 0..255, used to stage column scales
+        const int ep_tid = (warp - 2) * 32 + lane;          // 0..511, used to stage column scales
         const int grow = row0 + r;                          // local row
         const bool row_ok = grow < p.rows;
         const float LOG2E = 1.4426950408889634f;
@@ -208,8 +223,9 @@ clip_fwd_kernel(const __grid_constant__ CUtensorMap map_a_stu, const __grid_cons
         auto flush_cols = [&](int t_prev) {
             const float* cb = col_buf + (t_prev & 1) * (4 * 4 * kBN);
             const int pcol0 = (tile_begin + t_prev) * kBN;
+            if (row0 >= p.rows) return;                       // second CTA of the last cluster when the row blocks are odd
 #pragma unroll
-            for (int o = ep_tid; o < 4 * kBN; o += 256) {
+            for (int o = ep_tid; o < 4 * kBN; o += kEpiThreads) {
                 const int st = o / kBN, c = o % kBN;
                 if (pcol0 + c < p.cols && (kTeacher || st == 0))
                     p.col_part[((size_t)rb * 4 + st) * p.cols + pcol0 + c] =
@@ -224,49 +240,48 @@ clip_fwd_kernel(const __grid_constant__ CUtensorMap map_a_stu, const __grid_cons
             if (ep_tid < kBN) {
                 const int c = col0 + ep_tid;
                 sc[ep_tid] = c < p.cols ? __ldg(p.b_inv_stu + c) : 0.f;
-            } else if (kTeacher) {
+            } else if (kTeacher && ep_tid < 2 * kBN) {
                 const int c = col0 + ep_tid - kBN;
                 sc[ep_tid] = c < p.cols ? __ldg(p.b_inv_tea + c) : 0.f;
             }
-            asm volatile("bar.sync 1, 256;" ::: "memory");      // scales staged; every warp is done with tile t-1
+            asm volatile("bar.sync 1, 512;" ::: "memory");      // scales staged; every warp is done with tile t-1
             if (kCols && t > 0) flush_cols(t - 1);
             mbar_wait(bar_tfull + 8 * as, aphase);
             tc_fence_after_sync();
             const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * 256;
             // masks are only needed where the tile meets the matrix edge, the diagonal, or rows beyond the batch
             const bool edge = (col0 + kBN > p.cols) || (diag_col >= col0 && diag_col < col0 + kBN) ||
-                              (row0 + kBM > p.rows) || (p.dump_s != nullptr);
+                              (row0 + kBM > p.rows) || (p.dump_s != nullptr) || (p.dump_t != nullptr);
             float* cb = col_buf + (t & 1) * (4 * 4 * kBN) + q * (4 * kBN);     // this quadrant's [4 stats][128 columns]
 #pragma unroll 1
-            for (int ch = 2 * sub; ch < 2 * sub + 2; ++ch) {
-                float sv[32], tv[32];
-                tmem_ld_32x32(lane_addr + ch * 32, sv);
-                if (kTeacher) tmem_ld_32x32(lane_addr + 128 + ch * 32, tv);
+            for (int hc = 0; hc < 2; ++hc) {                // 16 columns at a time (keeps the register footprint under 113)
+                float sv[16], tv[16];
+                const int cbase = sub * 32 + hc * 16;
+                tmem_ld_32x16(lane_addr + cbase, sv);
+                if (kTeacher) tmem_ld_32x16(lane_addr + 128 + cbase, tv);
                 tmem_ld_wait();
-                if (ch == 2 * sub + 1) {                    // last TMEM read of this tile: release the accumulator stage
+                if (hc == 1) {                              // last TMEM read of this tile: release the accumulator stage
                     tc_fence_before_sync();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(bar_tempty + 8 * as);
+                    if (lane == 0) mbar_arrive_cluster(l_tempty + 8 * as);
                 }
-                const float* scs = sc + ch * 32;
-                const float* sct = sc + kBN + ch * 32;
+                const float* scs = sc + cbase;
+                const float* sct = sc + kBN + cbase;
                 float a_sum = 0.f, zs_sum = 0.f, zt_sum = 0.f, w_sum = 0.f;
-#pragma unroll
-                for (int hc = 0; hc < 2; ++hc) {            // 16 columns at a time (keeps the per-statistic arrays small)
+                {
                     float e[16], f[16];
-                    const int cbase = ch * 32 + hc * 16;
                     // ---- A = sum exp(S - 1)
 #pragma unroll
                     for (int c = 0; c < 16; ++c) {
-                        const float u = sv[hc * 16 + c] * scs[hc * 16 + c];
-                        sv[hc * 16 + c] = u;                                  // keep the scaled logit (still * 1/r_s)
+                        const float u = sv[c] * scs[c];
+                        sv[c] = u;                                            // keep the scaled logit (still * 1/r_s)
                         e[c] = ex2(fmaf(u, k1, n1));
                     }
                     if (edge) {
 #pragma unroll
                         for (int c = 0; c < 16; ++c) {
                             const int gc = col0 + cbase + c;
-                            const float s = sv[hc * 16 + c] * r_s;
+                            const float s = sv[c] * r_s;
                             if (gc == diag_col) { diag = s; have_diag = true; }
                             if (p.dump_s && row_ok && gc < p.cols) p.dump_s[(size_t)grow * p.cols + gc] = s;
                             if (!(gc < p.cols && row_ok)) e[c] = 0.f;
@@ -281,7 +296,7 @@ clip_fwd_kernel(const __grid_constant__ CUtensorMap map_a_stu, const __grid_cons
                     if (kTeacher) {
                         // ---- Zs = sum exp((S - 1)/T)
 #pragma unroll
-                        for (int c = 0; c < 16; ++c) e[c] = ex2(fmaf(sv[hc * 16 + c], k1t, n1t));
+                        for (int c = 0; c < 16; ++c) e[c] = ex2(fmaf(sv[c], k1t, n1t));
                         if (edge) {
 #pragma unroll
                             for (int c = 0; c < 16; ++c)
@@ -296,16 +311,17 @@ clip_fwd_kernel(const __grid_constant__ CUtensorMap map_a_stu, const __grid_cons
                         // ---- Zt = sum exp((Tt - 1)/T),  W = sum exp((Tt - 1)/T) (Tt - S)
 #pragma unroll
                         for (int c = 0; c < 16; ++c) {
-                            const float v = tv[hc * 16 + c] * sct[hc * 16 + c];
+                            const float v = tv[c] * sct[c];
                             e[c] = ex2(fmaf(v, k2t, n1t));
-                            f[c] = e[c] * fmaf(v, r_t, -(sv[hc * 16 + c] * r_s));
-                            if (p.dump_t && row_ok && col0 + cbase + c < p.cols)
-                                p.dump_t[(size_t)grow * p.cols + col0 + cbase + c] = v * r_t;
+                            f[c] = e[c] * fmaf(v, r_t, -(sv[c] * r_s));
                         }
                         if (edge) {
 #pragma unroll
-                            for (int c = 0; c < 16; ++c)
+                            for (int c = 0; c < 16; ++c) {
+                                if (p.dump_t && row_ok && col0 + cbase + c < p.cols)
+                                    p.dump_t[(size_t)grow * p.cols + col0 + cbase + c] = tv[c] * sct[c] * r_t;
                                 if (!(col0 + cbase + c < p.cols && row_ok)) { e[c] = 0.f; f[c] = 0.f; }
+                            }
                         }
 #pragma unroll
                         for (int c = 0; c < 16; ++c) { zt_sum += e[c]; w_sum += f[c]; }
@@ -326,11 +342,11 @@ clip_fwd_kernel(const __grid_constant__ CUtensorMap map_a_stu, const __grid_cons
             }
         }
         if (kCols && n_tiles > 0) {
-            asm volatile("bar.sync 1, 256;" ::: "memory");
+            asm volatile("bar.sync 1, 512;" ::: "memory");
             flush_cols(n_tiles - 1);
         }
         if (row_ok) {
-            float* w = p.ws + (size_t)(sp * 2 + sub) * 4 * p.rows + grow;
+            float* w = p.ws + (size_t)(sp * kSubs + sub) * 4 * p.rows + grow;
             w[0] = A;
             w[(size_t)p.rows] = Zs;
             w[(size_t)2 * p.rows] = Zt;
@@ -340,9 +356,11 @@ clip_fwd_kernel(const __grid_constant__ CUtensorMap map_a_stu, const __grid_cons
     }
     tc_fence_before_sync();
     __syncthreads();
+    cluster_sync_all();                  // the peer may still be reading operands this CTA's MMAs depend on / arriving remotely
     if (warp == 1) {
+        __syncwarp();
         tc_fence_after_sync();
-        tc::tmem_dealloc(tmem_base, kTmemCols);
+        tmem_dealloc_pair(tmem_base, kTmemCols);
     }
 }
 
@@ -357,10 +375,10 @@ __global__ void __launch_bounds__(128) clip_combine_kernel(const float* __restri
     float v[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        float acc = 0.f;
-        for (int s = 0; s < n_split; ++s) acc += ws[((size_t)s * 4 + k) * rows + r];
-        v[k] = acc;
-        stats[(size_t)k * rows + r] = acc;
+        double acc = 0.0;
+        for (int s = 0; s < n_split; ++s) acc += (double)ws[((size_t)s * 4 + k) * rows + r];
+        v[k] = (float)acc;
+        stats[(size_t)k * rows + r] = (float)acc;
     }
     const float dg = diag[r];
     stats[(size_t)4 * rows + r] = dg;
@@ -408,7 +426,7 @@ static int clip_fwd_splits(int64_t rows, int64_t cols) {
     int64_t best = 1;
     double best_cost = 1e30;
     for (int64_t n = 1; n <= 64 && n <= col_tiles; ++n) {
-        const int64_t waves = (row_blocks * n + kNumSMs - 1) / kNumSMs;
+        const int64_t waves = ((row_blocks + 1) / 2 * n + kNumSMs / 2 - 1) / (kNumSMs / 2);     // clusters of two row blocks
         const int64_t tiles = (col_tiles + n - 1) / n;
         const double cost = (double)waves * ((double)tiles + 1.0) + 0.01 * (double)n;
         if (cost < best_cost) { best_cost = cost; best = n; }
@@ -421,7 +439,7 @@ static int clip_fwd_splits(int64_t rows, int64_t cols) {
 extern "C" int64_t dcb_clip_workspace_bytes(int64_t rows_local, int64_t cols) {
     if (rows_local < 1 || cols < 1) return 0;
     const int64_t row_blocks = (rows_local + dcb::fwd::kBM - 1) / dcb::fwd::kBM;
-    return (((int64_t)dcb::clip_fwd_splits(rows_local, cols) * 2 * 4 + 1) * rows_local + row_blocks * 4 * cols) * (int64_t)sizeof(float);
+    return (((int64_t)dcb::clip_fwd_splits(rows_local, cols) * dcb::fwd::kSubs * 4 + 1) * rows_local + row_blocks * 4 * cols) * (int64_t)sizeof(float);
 }
 
 extern "C" int dcb_clip_row_stats(const void* stu_a, const void* stu_b, const void* tea_a, const void* tea_b,
@@ -443,10 +461,10 @@ extern "C" int dcb_clip_row_stats(const void* stu_a, const void* stu_b, const vo
     CUtensorMap ma_s, mb_s, ma_t, mb_t;
     const uint64_t pitch = (uint64_t)dim * 2;
     if (tc::encode_tile_map_16bit(&ma_s, stu_a, rows_local, dim, pitch, fwd::kBM)) return 1;
-    if (tc::encode_tile_map_16bit(&mb_s, stu_b, cols, dim, pitch, fwd::kBN)) return 1;
+    if (tc::encode_tile_map_16bit(&mb_s, stu_b, cols, dim, pitch, fwd::kBHalfRows)) return 1;
     if (teacher) {
         if (tc::encode_tile_map_16bit(&ma_t, tea_a, rows_local, dim, pitch, fwd::kBM)) return 1;
-        if (tc::encode_tile_map_16bit(&mb_t, tea_b, cols, dim, pitch, fwd::kBN)) return 1;
+        if (tc::encode_tile_map_16bit(&mb_t, tea_b, cols, dim, pitch, fwd::kBHalfRows)) return 1;
     } else {
         ma_t = ma_s;
         mb_t = mb_s;
@@ -463,21 +481,33 @@ extern "C" int dcb_clip_row_stats(const void* stu_a, const void* stu_b, const vo
     p.n_split = clip_fwd_splits(rows_local, cols);
     p.col_tiles = (int)((cols + fwd::kBN - 1) / fwd::kBN);
     p.ws = static_cast<float*>(workspace);
-    p.diag = p.ws + (size_t)p.n_split * 2 * 4 * rows_local;
+    p.diag = p.ws + (size_t)p.n_split * fwd::kSubs * 4 * rows_local;
     p.col_part = col_stats ? p.diag + rows_local : nullptr;
     p.dump_s = dump_s;
     p.dump_t = dump_t;
     p.inv_temp = teacher ? 1.0f / temperature : 1.0f;
     const int row_blocks = (int)((rows_local + fwd::kBM - 1) / fwd::kBM);
-    const uint32_t idesc = tc::umma_idesc_f16(fwd::kBM, fwd::kBN, dtype == DCB_BF16 ? 1 : 0);
+    const uint32_t idesc = tc::umma_idesc_f16(2 * fwd::kBM, fwd::kBN, dtype == DCB_BF16 ? 1 : 0);     // M = 256 over the CTA pair
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    dim3 grid((unsigned)(row_blocks * p.n_split));
+    dim3 grid((unsigned)(2 * ((row_blocks + 1) / 2) * p.n_split));
 #define DCB_LAUNCH_FWD(TEA, COLS)                                                                                       \
     {                                                                                                                  \
         static const cudaError_t attr_ = cudaFuncSetAttribute(clip_fwd_kernel<TEA, COLS>,                              \
                                                               cudaFuncAttributeMaxDynamicSharedMemorySize, fwd::kSmemBytes); \
         DCB_CUDA_OK(attr_);     /* set once per process (not a stream operation; kept out of graph captures) */         \
-        clip_fwd_kernel<TEA, COLS><<<grid, fwd::kThreads, fwd::kSmemBytes, st>>>(ma_s, mb_s, ma_t, mb_t, p, idesc);     \
+        cudaLaunchConfig_t cfg_{};                                                                                     \
+        cfg_.gridDim = grid;                                                                                           \
+        cfg_.blockDim = dim3(fwd::kThreads);                                                                           \
+        cfg_.dynamicSmemBytes = fwd::kSmemBytes;                                                                       \
+        cfg_.stream = st;                                                                                              \
+        cudaLaunchAttribute attr2_[1];                                                                                 \
+        attr2_[0].id = cudaLaunchAttributeClusterDimension;                                                            \
+        attr2_[0].val.clusterDim.x = 2;                                                                                \
+        attr2_[0].val.clusterDim.y = 1;                                                                                \
+        attr2_[0].val.clusterDim.z = 1;                                                                                \
+        cfg_.attrs = attr2_;                                                                                           \
+        cfg_.numAttrs = 1;                                                                                             \
+        DCB_CUDA_OK(cudaLaunchKernelEx(&cfg_, clip_fwd_kernel<TEA, COLS>, ma_s, mb_s, ma_t, mb_t, p, idesc));           \
     }
     if (teacher && col_stats) DCB_LAUNCH_FWD(true, true)
     else if (teacher) DCB_LAUNCH_FWD(true, false)
@@ -486,7 +516,7 @@ extern "C" int dcb_clip_row_stats(const void* stu_a, const void* stu_b, const vo
 #undef DCB_LAUNCH_FWD
     DCB_CUDA_OK(cudaGetLastError());
     clip_combine_kernel<<<(unsigned)((rows_local + 127) / 128), 128, 0, st>>>(p.ws, p.diag, stats, rowloss, (int)rows_local,
-                                                                               2 * p.n_split, temperature, teacher ? 1 : 0);
+                                                                               fwd::kSubs * p.n_split, temperature, teacher ? 1 : 0);
     DCB_CUDA_OK(cudaGetLastError());
     if (col_stats) {
         dim3 g2((unsigned)((cols + 255) / 256), 4);

@@ -293,7 +293,12 @@ def test_full_size_lclip_properties(cuda_device):
     assert abs(float(out[1])) <= 1e-4 * b and float(gi.abs().max()) <= 1e-6
     out, gi, gt = _fused(si, st, ti, tt, T, 1.0, 1.0, torch.float32)
     out2, gi2, gt2 = _fused(st, si, tt, ti, T, 1.0, 1.0, torch.float32)
-    assert float(out[0]) == pytest.approx(float(out2[0]), rel=1e-6) and float(out[1]) == pytest.approx(float(out2[1]), rel=1e-5)
+    # row sums (Kahan over 16-column pieces) against column sums (butterfly over rows, double across row blocks) of the same
+    # tiles: both within the 1e-4 loss budget of the oracle, a few 1e-5 apart on the KL (a small difference of logs)
+    assert float(out[0]) == pytest.approx(float(out2[0]), rel=1e-6) and float(out[1]) == pytest.approx(float(out2[1]), rel=5e-5)
+    ref = cf.contrastive_from_embeddings(*[x.float().cpu().numpy() for x in (si, st, ti, tt)], T, w_hard=1.0, w_soft=1.0)
+    assert float(out[0]) == pytest.approx(ref["hard"], rel=LOSS_RTOL) and float(out[1]) == pytest.approx(ref["soft"], rel=LOSS_RTOL)
+    assert rel_l2(gi.cpu().numpy(), ref["d_img"]) <= GRAD_RTOL and rel_l2(gt.cpu().numpy(), ref["d_txt"]) <= GRAD_RTOL
     # row sums (per-thread, Kahan) and column sums (warp butterfly + per-row-block reduce) round differently: ~2e-5
     assert rel_l2(gi.cpu().numpy(), gt2.cpu().numpy()) <= 1e-4
     assert 0.0 < float(out[0]) < np.log(b)
