@@ -15,8 +15,12 @@
 // MMAs of tile n+1 overlap the epilogue of tile n.
 // The epilogue warps read the accumulators with tcgen05.ld (one row per thread), apply the fp32 inverse norms
 // (logit = acc * r_i * c_j, so normalised embeddings are never rounded to bf16) and accumulate per row
-//   A  = sum_j exp(S_ij - 1)            Zs = sum_j exp((S_ij - 1)/T)
-//   Zt = sum_j exp((T_ij - 1)/T)        W  = sum_j exp((T_ij - 1)/T) (T_ij - S_ij)        and S_ii.
+//   A  = sum_j exp(S_ij - 1)            Q  = sum_j [es_ij - et_ij + et_ij (T_ij - S_ij)/T]
+//   Zt = sum_j et_ij                    W  = sum_j et_ij (T_ij - S_ij)                    and S_ii,
+// es = exp((S - 1)/T), et = exp((T - 1)/T).  Q is the SECOND-ORDER part of Zs - Zt (Zs = Zt + Q - W/T): the KL of a row,
+//   KL_i / T^2 = W/(T Zt) + log(Zs/Zt) = -m + log1p(m + Q/Zt),  m = -W/(T Zt),
+// is a second-order quantity in (S - T) whose first-order terms cancel; carrying Q instead of Zs keeps fp32 rounding
+// relative to that small quantity rather than to O(1) sums (a nearly converged student at T = 4 lost 1.4e-4 otherwise).
 // Cosine logits are bounded by 1, so 1 is a valid softmax shift for every row: the sums of different column
 // ranges simply add (no running max, no rescaling), which is what lets a row be split over CTAs and ranks.
 //
@@ -208,10 +212,10 @@ clip_fwd_kernel(const __grid_constant__ CUtensorMap map_a_stu, const __grid_cons
         const float n1 = -LOG2E, n1t = -LOG2E * p.inv_temp;
         const int diag_col = p.row_offset + grow;           // global column holding this row's label
         // Row totals with Kahan compensation: sums of each 32-column chunk start from zero (small magnitudes) and are
-        // folded into the running totals with an error term, so Zs/Zt keep ~1e-7 relative accuracy even for B = 32768
-        // (KL_i is a small difference of log Zs and log Zt; plain fp32 accumulation costs ~1e-4 on the loss, measured).
-        float A = 0.f, Zs = 0.f, Zt = 0.f, W = 0.f, diag = 0.f;
-        float cA = 0.f, cZs = 0.f, cZt = 0.f, cW = 0.f;
+        // folded into the running totals with an error term, so Zt, W and Q keep ~1e-7 relative accuracy even for B = 32768
+        // (plain fp32 accumulation costs ~1e-4 on the loss, measured).
+        float A = 0.f, Q = 0.f, Zt = 0.f, W = 0.f, diag = 0.f;
+        float cA = 0.f, cQ = 0.f, cZt = 0.f, cW = 0.f;
         bool have_diag = false;
         auto kahan = [](float& sum, float& comp, float x) {
             const float y = x - comp;
@@ -267,7 +271,7 @@ clip_fwd_kernel(const __grid_constant__ CUtensorMap map_a_stu, const __grid_cons
                 }
                 const float* scs = sc + cbase;
                 const float* sct = sc + kBN + cbase;
-                float a_sum = 0.f, zs_sum = 0.f, zt_sum = 0.f, w_sum = 0.f;
+                float a_sum = 0.f, q_sum = 0.f, zt_sum = 0.f, w_sum = 0.f;
                 {
                     float e[16], f[16];
                     // ---- A = sum exp(S - 1)
@@ -294,40 +298,39 @@ clip_fwd_kernel(const __grid_constant__ CUtensorMap map_a_stu, const __grid_cons
                         if (!(lane & 1)) cb[0 * kBN + cbase + (lane >> 1)] = e[0];
                     }
                     if (kTeacher) {
-                        // ---- Zs = sum exp((S - 1)/T)
+                        // ---- es = exp((S - 1)/T) (kept in e), et = exp((Tt - 1)/T) (overwrites tv), f = et (Tt - S)
+                        if (edge && p.dump_t) {
 #pragma unroll
-                        for (int c = 0; c < 16; ++c) e[c] = ex2(fmaf(sv[c], k1t, n1t));
+                            for (int c = 0; c < 16; ++c)
+                                if (row_ok && col0 + cbase + c < p.cols)
+                                    p.dump_t[(size_t)grow * p.cols + col0 + cbase + c] = tv[c] * sct[c] * r_t;
+                        }
+#pragma unroll
+                        for (int c = 0; c < 16; ++c) {
+                            e[c] = ex2(fmaf(sv[c], k1t, n1t));
+                            const float v = tv[c] * sct[c];
+                            const float et = ex2(fmaf(v, k2t, n1t));
+                            f[c] = et * fmaf(v, r_t, -(sv[c] * r_s));
+                            tv[c] = et;
+                        }
                         if (edge) {
 #pragma unroll
                             for (int c = 0; c < 16; ++c)
-                                if (!(col0 + cbase + c < p.cols && row_ok)) e[c] = 0.f;
+                                if (!(col0 + cbase + c < p.cols && row_ok)) { e[c] = 0.f; tv[c] = 0.f; f[c] = 0.f; }
                         }
+                        // ---- Q = sum (es - et) + f/T,  Zt = sum et,  W = sum f
 #pragma unroll
-                        for (int c = 0; c < 16; ++c) zs_sum += e[c];
+                        for (int c = 0; c < 16; ++c) {
+                            e[c] = fmaf(f[c], p.inv_temp, e[c] - tv[c]);
+                            q_sum += e[c];
+                            zt_sum += tv[c];
+                            w_sum += f[c];
+                        }
                         if (kCols) {
                             column_sums16(e, lane);
                             if (!(lane & 1)) cb[1 * kBN + cbase + (lane >> 1)] = e[0];
-                        }
-                        // ---- Zt = sum exp((Tt - 1)/T),  W = sum exp((Tt - 1)/T) (Tt - S)
-#pragma unroll
-                        for (int c = 0; c < 16; ++c) {
-                            const float v = tv[c] * sct[c];
-                            e[c] = ex2(fmaf(v, k2t, n1t));
-                            f[c] = e[c] * fmaf(v, r_t, -(sv[c] * r_s));
-                        }
-                        if (edge) {
-#pragma unroll
-                            for (int c = 0; c < 16; ++c) {
-                                if (p.dump_t && row_ok && col0 + cbase + c < p.cols)
-                                    p.dump_t[(size_t)grow * p.cols + col0 + cbase + c] = tv[c] * sct[c] * r_t;
-                                if (!(col0 + cbase + c < p.cols && row_ok)) { e[c] = 0.f; f[c] = 0.f; }
-                            }
-                        }
-#pragma unroll
-                        for (int c = 0; c < 16; ++c) { zt_sum += e[c]; w_sum += f[c]; }
-                        if (kCols) {
-                            column_sums16(e, lane);
-                            if (!(lane & 1)) cb[2 * kBN + cbase + (lane >> 1)] = e[0];
+                            column_sums16(tv, lane);
+                            if (!(lane & 1)) cb[2 * kBN + cbase + (lane >> 1)] = tv[0];
                             column_sums16(f, lane);
                             if (!(lane & 1)) cb[3 * kBN + cbase + (lane >> 1)] = f[0];
                         }
@@ -335,7 +338,7 @@ clip_fwd_kernel(const __grid_constant__ CUtensorMap map_a_stu, const __grid_cons
                 }
                 kahan(A, cA, a_sum);
                 if (kTeacher) {
-                    kahan(Zs, cZs, zs_sum);
+                    kahan(Q, cQ, q_sum);
                     kahan(Zt, cZt, zt_sum);
                     kahan(W, cW, w_sum);
                 }
@@ -348,7 +351,7 @@ clip_fwd_kernel(const __grid_constant__ CUtensorMap map_a_stu, const __grid_cons
         if (row_ok) {
             float* w = p.ws + (size_t)(sp * kSubs + sub) * 4 * p.rows + grow;
             w[0] = A;
-            w[(size_t)p.rows] = Zs;
+            w[(size_t)p.rows] = Q;
             w[(size_t)2 * p.rows] = Zt;
             w[(size_t)3 * p.rows] = W;
             if (have_diag) p.diag[grow] = diag;
@@ -364,9 +367,15 @@ clip_fwd_kernel(const __grid_constant__ CUtensorMap map_a_stu, const __grid_cons
     }
 }
 
+// KL_i / T^2 from the row sums (Q, Zt, W): -m + log1p(m + Q/Zt), m = -W/(T Zt)  (see the file header)
+__device__ __forceinline__ double clip_row_kl(double q, double zt, double w, double temperature) {
+    const double m = -w / (temperature * zt);
+    return -m + log1p(m + q / zt);
+}
+
 // stats[k][r] = sum over splits (fixed order -> deterministic), stats[4][r] = S_rr, and the row's loss terms in double
-// (KL_i is a small difference of O(1) terms: W/(T Zt) against log Zs - log Zt):
-//   rowloss[0][r] = CE_r = 1 + log A_r - S_rr       rowloss[1][r] = KL_r / T^2 = W_r/(T Zt_r) + log(Zs_r / Zt_r)
+// (double precision; slot 1 of the statistics is Q, not Zs):
+//   rowloss[0][r] = CE_r = 1 + log A_r - S_rr       rowloss[1][r] = KL_r / T^2 = clip_row_kl(Q_r, Zt_r, W_r)
 __global__ void __launch_bounds__(128) clip_combine_kernel(const float* __restrict__ ws, const float* __restrict__ diag,
                                                            float* __restrict__ stats, double* __restrict__ rowloss,
                                                            int rows, int n_split, float temperature, int has_teacher) {
@@ -383,7 +392,7 @@ __global__ void __launch_bounds__(128) clip_combine_kernel(const float* __restri
     const float dg = diag[r];
     stats[(size_t)4 * rows + r] = dg;
     rowloss[r] = 1.0 + log((double)v[0]) - (double)dg;
-    rowloss[(size_t)rows + r] = has_teacher ? (double)v[3] / ((double)temperature * (double)v[2]) + log((double)v[1] / (double)v[2]) : 0.0;
+    rowloss[(size_t)rows + r] = has_teacher ? clip_row_kl((double)v[1], (double)v[2], (double)v[3], (double)temperature) : 0.0;
 }
 
 // col_stats[k][j] = sum over row blocks of col_part[rb][k][j]  (double accumulation, fixed order)
@@ -415,7 +424,7 @@ __global__ void __launch_bounds__(128) clip_colfinish_kernel(const float* __rest
     const float dg = diag[r];
     stats[(size_t)4 * rows + r] = dg;
     rowloss[r] = 1.0 + log((double)v[0]) - (double)dg;
-    rowloss[(size_t)rows + r] = has_teacher ? (double)v[3] / ((double)temperature * (double)v[2]) + log((double)v[1] / (double)v[2]) : 0.0;
+    rowloss[(size_t)rows + r] = has_teacher ? clip_row_kl((double)v[1], (double)v[2], (double)v[3], (double)temperature) : 0.0;
 }
 
 // Column ranges per row block: minimise (waves of 148 CTAs) x (tiles per CTA + fixed per-CTA cost)

@@ -91,7 +91,9 @@ __global__ void __launch_bounds__(256) clip_coef_kernel(const float* __restrict_
     if (i < rows) {
         const float gh = upstream[0], gs = upstream[1];
         const float a = 0.5f * gh * inv_batch / stats[i];
-        const float b = has_teacher ? 0.5f * gs * temperature / stats[(size_t)rows + i] : 0.f;
+        // stats[1] carries Q, the second-order part of Zs - Zt (clip_fwd.cu): Zs = Zt + Q - W/T
+        const float zs = has_teacher ? stats[(size_t)2 * rows + i] + stats[(size_t)rows + i] - stats[(size_t)3 * rows + i] / temperature : 1.f;
+        const float b = has_teacher ? 0.5f * gs * temperature / zs : 0.f;
         const float c = has_teacher ? 0.5f * gs * temperature / stats[(size_t)2 * rows + i] : 0.f;
         coef[i] = a;
         coef[(size_t)rows + i] = b;

@@ -146,8 +146,11 @@ int dcb_transpose_norm_f16(const void* in, const float* inv_norm, void* out, int
 
 /* dcb_clip_row_stats: ONE fused tcgen05 kernel for one direction.  For each local row i:
  *   stats[0][i] = sum_j exp(S_ij - 1)                 (hard label; S = student cosine logits)
- *   stats[1][i] = sum_j exp((S_ij - 1)/T)             stats[2][i] = sum_j exp((T_ij - 1)/T)
- *   stats[3][i] = sum_j exp((T_ij - 1)/T) (T_ij - S_ij)      stats[4][i] = S_ii (global diagonal)
+ *   stats[1][i] = Q_i = sum_j [es_ij - et_ij + et_ij (T_ij - S_ij)/T],  es = exp((S-1)/T), et = exp((T-1)/T): the
+ *                 second-order part of Zs_i - Zt_i (Zs = Zt + Q - W/T), carried instead of Zs so that the KL of a row,
+ *                 -m + log1p(m + Q/Zt) with m = -W/(T Zt), keeps fp32 rounding relative to its own (small) size
+ *   stats[2][i] = Zt_i = sum_j exp((T_ij - 1)/T)
+ *   stats[3][i] = W_i = sum_j exp((T_ij - 1)/T) (T_ij - S_ij)      stats[4][i] = S_ii (global diagonal)
  * tea_* may all be NULL (hard label only; stats[1..3] are then 0).  stats: [5, rows_local] floats.
  * rowloss: [2, rows_local] doubles = {CE_i = 1 + log stats0 - stats4,  KL_i / T^2 = stats3/(T stats2) + log(stats1/stats2)}.
  * col_stats (optional, [4, cols] floats): the SAME four sums taken down the columns over this call's rows, i.e. this
@@ -176,7 +179,7 @@ int dcb_clip_col_finish(const float* col_stats, int64_t cols_total, const float*
 int dcb_clip_losses(const double* rowloss_i2t, const double* rowloss_t2i, int64_t rows_i2t, int64_t rows_t2i,
                     int64_t global_batch, float temperature, int has_teacher, double* sums, float* out, void* stream);
 
-/* coef[0][i] = gh/(2 B A_i), coef[1][i] = gs T/(2 Zs_i), coef[2][i] = gs T/(2 Zt_i) from stats [5, rows];
+/* coef[0][i] = gh/(2 B A_i), coef[1][i] = gs T/(2 Zs_i) with Zs = Zt + Q - W/T, coef[2][i] = gs T/(2 Zt_i) from stats [5, rows];
  * upstream: device float[2] = {gh = d total / d hard, gs = d total / d soft}.
  * gmax: device float[1], receives max_i (|coef0| + |coef1| + |coef2|) -- the bound that fixes the fp16 scale of G. */
 int dcb_clip_grad_coef(const float* stats, int64_t rows, int64_t global_batch, float temperature, int has_teacher,

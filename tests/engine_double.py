@@ -27,7 +27,8 @@ class DoubleEngine:
         if a_t is not None:
             T = self._logits(a_t, b_t, a_t_inv, b_t_inv)
             et, es = torch.exp((T - 1) / temperature), torch.exp((S - 1) / temperature)
-            st[1], col[1] = es.sum(1), es.sum(0)
+            q = es - et + et * (T - S) / temperature          # second-order part of Zs - Zt, as the kernel carries it
+            st[1], col[1] = q.sum(1), q.sum(0)
             st[2], col[2] = et.sum(1), et.sum(0)
             st[3], col[3] = (et * (T - S)).sum(1), (et * (T - S)).sum(0)
         rl = self._rowloss(st, temperature, a_t is not None)
@@ -38,7 +39,8 @@ class DoubleEngine:
         rl = torch.zeros(2, st.shape[1], dtype=torch.float64)
         rl[0] = 1 + torch.log(st[0]) - st[4]
         if has_teacher:
-            rl[1] = st[3] / (temperature * st[2]) + torch.log(st[1] / st[2])
+            m = -st[3] / (temperature * st[2])
+            rl[1] = -m + torch.log1p(m + st[1] / st[2])
         return rl
 
     def col_finish(self, col_stats, diag_local, row_offset, temperature, has_teacher):
@@ -62,7 +64,7 @@ class DoubleEngine:
         c = torch.zeros(3, stats.shape[1], dtype=torch.float64)
         c[0] = 0.5 * gh / (global_batch * stats[0])
         if has_teacher:
-            c[1] = 0.5 * gs * temperature / stats[1]
+            c[1] = 0.5 * gs * temperature / (stats[2] + stats[1] - stats[3] / temperature)       # Zs = Zt + Q - W/T
             c[2] = 0.5 * gs * temperature / stats[2]
         return c, c.abs().sum(0).max().reshape(1)
 

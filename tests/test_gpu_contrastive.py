@@ -52,10 +52,15 @@ def test_similarity_tiles_match_matmul(cuda_device, b, d):
     st1, _, col = eng.row_stats(si, st, ti, tt, inv[0], inv[1], inv[2], inv[3], 0, 2.0, with_cols=True)
     st2, _ = eng.row_stats(st, si, tt, ti, inv[1], inv[0], inv[3], inv[2], 0, 2.0)
     assert torch.equal(st1, stats)
-    for k in range(4):
+    for k in (0, 2, 3):
         assert rel_l2(col[k].cpu().numpy(), st2[k].double().cpu().numpy()) <= 2e-6, k
-    et = np.exp((t_ref - 1) / 2.0)
+    et, es = np.exp((t_ref - 1) / 2.0), np.exp((s_ref - 1) / 2.0)
     assert rel_l2(col[3].cpu().numpy(), (et * (t_ref - s_ref)).sum(0)) <= 1e-4
+    # slot 1 = Q, the second-order part of Zs - Zt: a sum of per-element differences, accurate relative to ITS size
+    q_ref = es - et + et * (t_ref - s_ref) / 2.0
+    assert rel_l2(stats[1].cpu().numpy(), q_ref.sum(1)) <= 1e-3 and rel_l2(col[1].cpu().numpy(), q_ref.sum(0)) <= 1e-3
+    zs = (stats[2] + stats[1] - stats[3] / 2.0).cpu().numpy()
+    assert rel_l2(zs, es.sum(1)) <= 1e-5
 
 
 @pytest.fixture(params=["single_pass", "pair", "chunk"])
