@@ -450,11 +450,17 @@ def bench_clip(cfg, args, device, dist, rank, world, pk, steps, warmup):
             "value": round(b / (ms * 1e-3), 1), "unit": "samples/s", "ms_per_step": round(ms, 4), "steps": steps,
             "scaling": "strong", "gpu_launches": launches, "l2_flush": timer.flush_buf is not None, "timing": timer.mode,
             "e2e": e2e,
-            "roofline": {"bound": "tensor", "kernel": "clip_fwd_kernel + clip_bwd_kernel (fused tcgen05, both directions)",
+            "roofline": {"bound": "tensor", "kernel": "clip_fwd_kernel + clip_bwd_pair_kernel + clip_gt_gemm_kernel (fused tcgen05)",
                          "achieved": round(tf, 2), "peak": pk["tf_burst"] * world, "unit": "TFLOP/s",
                          "frac": round(tf / (pk["tf_burst"] * world), 4),
                          "frac_of_sustained": round(tf / (pk["tf_sustained"] * world), 4),
-                         "credited_flops": flops, "traffic": None, "peak_source": pk["source"]}}
+                         "credited_flops": flops,
+                         "traffic": (sum(ncu_traffic("r01_ncu_full_clip_sweep.csv", k) or 0 for k in
+                                         ("clip_fwd_kernel", "clip_bwd_pair_kernel", "clip_gt_gemm_kernel")) or None)
+                         if (b, d, world) == (32768, 768, 1) else None,
+                         "traffic_note": "dram bytes of the three tcgen05 kernels of one step (ncu --set full, profiles/), 4.3 GB of "
+                                         "which are the fp16 gradient tiles written once and read once",
+                         "peak_source": pk["source"]}}
 
 
 def run_ours(args):

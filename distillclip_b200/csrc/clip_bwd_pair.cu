@@ -287,6 +287,25 @@ clip_bwd_pair_kernel(const __grid_constant__ CUtensorMap map_a_stu, const __grid
         const float rbeta = (kTeacher && row_ok) ? __ldg(p.coef_row + p.rows + grow) : 0.f;
         const float rg = (kTeacher && row_ok) ? __ldg(p.coef_row + 2 * (size_t)p.rows + grow) : 0.f;
         const float gscale = pair_tile_scale(__ldg(p.gmax_row) + __ldg(p.gmax_col));
+        // column scales / coefficients of a tile: fetched one tile ahead into registers (the ~1000 clk of global-load latency
+        // sat on the per-tile critical path, trace r01q), parked in shared memory at the top of the tile that uses them
+        float pre0 = 0.f, pre1 = 0.f, pre2 = 0.f;
+        auto fetch_scales = [&](int t_next) {
+            pre0 = pre1 = pre2 = 0.f;
+            if (t_next >= n_tiles) return;
+            const int c = ep_tid < NT ? ep_tid : ep_tid - NT;
+            const int gc = (tile_begin + t_next) * NT + c;
+            if (gc >= p.cols) return;
+            if (ep_tid < NT) {
+                pre0 = __ldg(p.b_inv_stu + gc);
+                pre1 = __ldg(p.coef_col + gc);
+            } else if (kTeacher) {
+                pre0 = __ldg(p.b_inv_tea + gc);
+                pre1 = __ldg(p.coef_col + p.cols + gc);
+                pre2 = __ldg(p.coef_col + 2 * (size_t)p.cols + gc);
+            }
+        };
+        fetch_scales(0);
         for (int t = 0; t < n_tiles; ++t) {
             const int as = t % ST;
             const int col0 = (tile_begin + t) * NT;
@@ -294,19 +313,16 @@ clip_bwd_pair_kernel(const __grid_constant__ CUtensorMap map_a_stu, const __grid
             const bool tr = ep_tid == 0;
             if (tr) DCB_TRACE(t, 8);
             if (ep_tid < NT) {
-                const int gc = col0 + ep_tid;
-                const bool ok = gc < p.cols;
-                sc[ep_tid] = ok ? __ldg(p.b_inv_stu + gc) : 0.f;
-                sc[2 * NT + ep_tid] = ok ? __ldg(p.coef_col + gc) : 0.f;
+                sc[ep_tid] = pre0;
+                sc[2 * NT + ep_tid] = pre1;
             } else if (kTeacher) {
                 const int c = ep_tid - NT;
-                const int gc = col0 + c;
-                const bool ok = gc < p.cols;
-                sc[NT + c] = ok ? __ldg(p.b_inv_tea + gc) : 0.f;
-                sc[3 * NT + c] = ok ? __ldg(p.coef_col + p.cols + gc) : 0.f;
-                sc[4 * NT + c] = ok ? __ldg(p.coef_col + 2 * (size_t)p.cols + gc) : 0.f;
+                sc[NT + c] = pre0;
+                sc[3 * NT + c] = pre1;
+                sc[4 * NT + c] = pre2;
             }
             asm volatile("bar.sync 1, 256;" ::: "memory");
+            fetch_scales(t + 1);
             if (tr) DCB_TRACE(t, 9);
             mbar_wait(bar_stfull + 8 * as, (t / ST) & 1);
             if (tr) DCB_TRACE(t, 10);

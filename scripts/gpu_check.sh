@@ -23,7 +23,7 @@ if [ "${NCU:-1}" = "1" ]; then
   timeout 600 $CMD > $OUT/ncu_plain_$TAG.log 2>&1 &&
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches_$TAG.csv $CMD > $OUT/ncu_launches_$TAG.log 2>&1
   echo "ncu launches exit $?" | tee -a $OUT/summary_$TAG.txt
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:"mse_stream|attn_kl|clip_fwd|clip_bwd" -s 10 -c 12 -o $OUT/prof_mse_$TAG -f $CMD > $OUT/ncu_full_$TAG.log 2>&1
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:"tower_stream|mse_stream|attn_kl" -s 6 -c 9 -o $OUT/prof_mse_$TAG -f $CMD > $OUT/ncu_full_$TAG.log 2>&1
   echo "ncu full exit $?" | tee -a $OUT/summary_$TAG.txt
 fi
 for f in $OUT/pytest_*_$TAG.log; do echo "== $f"; tail -n 25 $f; done

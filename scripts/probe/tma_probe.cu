@@ -23,6 +23,10 @@ __device__ __forceinline__ void tma_load(uint32_t dst, const CUtensorMap* m, uin
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                  ::"r"(dst), "l"((uint64_t)m), "r"(bar), "r"(x), "r"(y) : "memory");
 }
+__device__ __forceinline__ void tma_load3(uint32_t dst, const CUtensorMap* m, uint32_t bar, int x, int y, int z) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 ::"r"(dst), "l"((uint64_t)m), "r"(bar), "r"(x), "r"(y), "r"(z) : "memory");
+}
 __device__ __forceinline__ void tma_load_mc(uint32_t dst, const CUtensorMap* m, uint32_t bar, int x, int y, uint16_t mask) {
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
                  ::"r"(dst), "l"((uint64_t)m), "r"(bar), "r"(x), "r"(y), "h"(mask) : "memory");
@@ -32,7 +36,7 @@ __device__ __forceinline__ uint32_t cluster_rank() { uint32_t r; asm volatile("m
 __device__ __forceinline__ void cluster_sync() { asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 
 struct P {
-    int stages, stage_bytes, boxes_per_stage, box_rows, iters, producers, multicast, k_chunks, rows_total;
+    int stages, stage_bytes, boxes_per_stage, box_rows, iters, producers, multicast, k_chunks, rows_total, three_d, hold;
     long long* clocks;
 };
 
@@ -53,7 +57,7 @@ __global__ void __launch_bounds__(192, 1) probe(const __grid_constant__ CUtensor
     }
     __syncthreads();
     if (p.multicast) cluster_sync();
-    const int box_bytes = p.box_rows * 128;
+    const int box_bytes = p.box_rows * 128 * (p.three_d ? 2 : 1);
     const long long t0 = clock64();
     if (warp < p.producers && lane == 0) {
         int stage = 0;
@@ -67,7 +71,8 @@ __global__ void __launch_bounds__(192, 1) probe(const __grid_constant__ CUtensor
                 mbar_expect(full + 8 * stage, per * box_bytes);
                 for (int b = warp * per; b < (warp + 1) * per; ++b) {
                     const int row = (int)(((unsigned)(blockIdx.x * 97 + it * p.boxes_per_stage + b) * (unsigned)p.box_rows) & (unsigned)(p.rows_total - 1));
-                    tma_load(dst + b * box_bytes, &map, full + 8 * stage, kx, row);
+                    if (p.three_d) tma_load3(dst + b * box_bytes, &map, full + 8 * stage, 0, row, (it & 3) * 2);
+                    else tma_load(dst + b * box_bytes, &map, full + 8 * stage, kx, row);
                 }
             } else {
                 // both CTAs receive every box; this CTA issues the boxes with b % 2 == rank
@@ -80,10 +85,16 @@ __global__ void __launch_bounds__(192, 1) probe(const __grid_constant__ CUtensor
             if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
     } else if (warp == 5 && lane == 0) {
+        long long last = 0;
         int stage = 0;
         uint32_t phase = 0;
         for (int it = 0; it < p.iters; ++it) {
             mbar_wait(full + 8 * stage, phase);
+            if (p.hold) {                       // emulate an in-order consumer that needs `hold` clocks per stage
+                const long long until = (it == 0 ? clock64() : last) + p.hold;
+                while (clock64() < until) {}
+                last = until > clock64() - p.hold ? until : clock64();
+            }
             if (!p.multicast) {
                 mbar_arrive(empty + 8 * stage);
             } else {       // the slot is free for refill (by EITHER producer) once both CTAs have consumed it
@@ -113,7 +124,7 @@ int main() {
     CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fp, cudaEnableDefault, &q));
     EncodeFn encode = (EncodeFn)fp;
     CK(cudaFuncSetAttribute(probe, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-    struct Case { const char* name; int stages, boxes, box_rows, producers, multicast, swizzle, ctas; };
+    struct Case { const char* name; int stages, boxes, box_rows, producers, multicast, swizzle, ctas, three_d, hold; };
     const Case cases[] = {
         {"8K boxes x4, 6 stages (as the kernels)", 6, 4, 64, 1, 0, 1, 148},
         {"same, 16 CTAs only", 6, 4, 64, 1, 0, 1, 16},
@@ -131,17 +142,21 @@ int main() {
         {"16K boxes x3 (48K stages), 4 stages", 4, 3, 128, 1, 0, 1, 148},
         {"16K x2 + 8K x2 per stage ~ (48K) modelled as 8K x6, 4 stages", 4, 6, 64, 1, 0, 1, 148},
         {"8K x6 per stage, 4 stages, 2 producers", 4, 6, 64, 2, 0, 1, 148},
+        {"3-D boxes {64,64 rows,2 chunks} = 16K x2, 6 stages", 6, 2, 64, 1, 0, 1, 148, 1, 0},
+        {"8K x4, 6 stages, consumer holds 272 clk/stage", 6, 4, 64, 1, 0, 1, 148, 0, 272},
+        {"16K x2, 6 stages, consumer holds 272 clk/stage", 6, 2, 128, 1, 0, 1, 148, 0, 272},
+        {"8K x4, 6 stages, consumer holds 400 clk/stage", 6, 4, 64, 1, 0, 1, 148, 0, 400},
         {"multicast pair: each CTA issues 2 of 4 boxes", 6, 4, 64, 1, 1, 1, 148},
         {"multicast pair, 16 CTAs only", 6, 4, 64, 1, 1, 1, 16},
         {"multicast pair, 16K boxes", 6, 2, 128, 1, 1, 1, 148},
     };
     for (const Case& c : cases) {
         CUtensorMap map;
-        const cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows_total};
-        const cuuint64_t gstride[1] = {(cuuint64_t)cols * 2};
-        const cuuint32_t box[2] = {64, (cuuint32_t)c.box_rows};
-        const cuuint32_t estr[2] = {1, 1};
-        CUresult r = encode(&map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, buf, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+        const cuuint64_t gdim[3] = {(cuuint64_t)(c.three_d ? 64 : cols), (cuuint64_t)rows_total, (cuuint64_t)(cols / 64)};
+        const cuuint64_t gstride[2] = {(cuuint64_t)cols * 2, 128};
+        const cuuint32_t box[3] = {64, (cuuint32_t)c.box_rows, 2};
+        const cuuint32_t estr[3] = {1, 1, 1};
+        CUresult r = encode(&map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, c.three_d ? 3 : 2, buf, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                             c.swizzle ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { printf("encode failed %d\n", (int)r); return 1; }
@@ -149,7 +164,9 @@ int main() {
         p.stages = c.stages;
         p.boxes_per_stage = c.boxes;
         p.box_rows = c.box_rows;
-        p.stage_bytes = c.boxes * c.box_rows * 128;
+        p.stage_bytes = c.boxes * c.box_rows * 128 * (c.three_d ? 2 : 1);
+        p.three_d = c.three_d;
+        p.hold = c.hold;
         p.iters = 2000;
         p.producers = c.producers;
         p.multicast = c.multicast;
