@@ -41,11 +41,12 @@ def sources():
 
 
 def _digest(paths) -> str:
+    """Content hash of the sources and flags, independent of where the tree lives (the GPU box unpacks it elsewhere)."""
     h = hashlib.sha256()
-    for p in sorted(paths):
+    for p in sorted(paths, key=os.path.basename):
         with open(p, "rb") as f:
-            h.update(p.encode() + b"\0" + f.read())
-    h.update(" ".join(NVCC_FLAGS).encode())
+            h.update(os.path.basename(p).encode() + b"\0" + f.read())
+    h.update(" ".join(x for x in NVCC_FLAGS if ROOT not in x).encode())
     return h.hexdigest()
 
 
@@ -56,9 +57,22 @@ def build(force: bool = False, verbose: bool = False) -> str:
     deps.append(os.path.join(ROOT, "include", "distillclip_b200.h"))
     stamp = os.path.join(OBJ, "stamp.txt")
     digest = _digest(deps)
-    if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read() == digest:
+
+    def fresh():
+        return os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read() == digest
+    if not force and fresh():
         return LIB
     os.makedirs(OBJ, exist_ok=True)
+    # one builder at a time (torchrun starts every rank at once); the others wait on the lock and find the result
+    import fcntl
+    with open(os.path.join(OBJ, "build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        if not force and fresh():
+            return LIB
+        return _build_locked(srcs, stamp, digest, verbose)
+
+
+def _build_locked(srcs, stamp, digest, verbose) -> str:
     exe = nvcc()
 
     def compile_one(src):
@@ -76,10 +90,12 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     with ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
         objs = list(ex.map(compile_one, srcs))
-    cmd = [exe, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC"]
+    tmp = LIB + f".tmp{os.getpid()}"
+    cmd = [exe, "-shared", "-o", tmp, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stderr[-4000:]}")
+    os.replace(tmp, LIB)                    # atomic: a concurrent loader sees the old or the new library, never half of one
     with open(stamp, "w") as f:
         f.write(digest)
     return LIB

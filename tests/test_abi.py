@@ -49,3 +49,22 @@ def test_no_cpu_fallback():
 def _err():
     from distillclip_b200._lib import DistillClipB200Error
     return DistillClipB200Error
+
+
+def test_build_stamp_is_location_independent(tmp_path):
+    """The GPU box unpacks the tree under a different path: the prebuilt .so must be recognised there (a path-dependent
+    stamp made every rank of a torchrun launch rebuild and overwrite the library at the same time)."""
+    import shutil
+    from distillclip_b200 import build as b
+    srcs = b.sources()[:3]
+    copies = []
+    for s in srcs:
+        dst = tmp_path / os.path.basename(s)
+        shutil.copy(s, dst)
+        copies.append(str(dst))
+    assert b._digest(srcs) == b._digest(copies)
+    stamp = os.path.join(b.OBJ, "stamp.txt")
+    if os.path.exists(b.LIB) and os.path.exists(stamp):          # a built tree: build() must be a no-op
+        before = os.path.getmtime(b.LIB)
+        b.build()
+        assert os.path.getmtime(b.LIB) == before
