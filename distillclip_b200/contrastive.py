@@ -223,22 +223,17 @@ def contrastive_forward(engine, si, st, ti, tt, temperature, group=None):
     b_local = si.shape[0]
     b_global = b_local * world
     offset = rank * b_local
-    # exchange step: every rank needs all rows of the opposite modality (student and teacher)
-    si_all, st_all = _all_gather_rows(si, group, world), _all_gather_rows(st, group, world)
-    ti_all = _all_gather_rows(ti, group, world) if has_teacher else None
+    # exchange step: every rank needs all TEXT rows (student and teacher).  The image rows stay local: the t2i direction
+    # comes from column sums / the G^T GEMM over this rank's own image rows (only the two-pass backward gathers them)
+    st_all = _all_gather_rows(st, group, world)
     tt_all = _all_gather_rows(tt, group, world) if has_teacher else None
-    mats = [si_all, st_all] + ([ti_all, tt_all] if has_teacher else [])
-    inv = engine.inv_norms(mats)
-    si_inv_all, st_inv_all = inv[0], inv[1]
-    ti_inv_all, tt_inv_all = (inv[2], inv[3]) if has_teacher else (None, None)
-    loc = slice(offset, offset + b_local)
-
-    def local(x):
-        return None if x is None else x[loc]
+    inv = engine.inv_norms([si, st_all] + ([ti, tt_all] if has_teacher else []))
+    si_inv, st_inv_all = inv[0], inv[1]
+    ti_inv, tt_inv_all = (inv[2], inv[3]) if has_teacher else (None, None)
     # ONE pass over the logits of this rank's image rows against all text rows: row sums = i2t statistics of the local
     # rows, column sums = this rank's share of the t2i statistics of ALL text rows (t2i logits are the transpose)
-    stats_i2t, rl_i2t, col = engine.row_stats(si, st_all, ti, tt_all, local(si_inv_all), st_inv_all, local(ti_inv_all),
-                                              tt_inv_all, offset, temperature, with_cols=True)
+    stats_i2t, rl_i2t, col = engine.row_stats(si, st_all, ti, tt_all, si_inv, st_inv_all, ti_inv, tt_inv_all, offset,
+                                              temperature, with_cols=True)
     if world > 1:
         import torch.distributed as dist
         dist.all_reduce(col, group=group)                 # exchange step 2: complete the column sums
@@ -248,8 +243,8 @@ def contrastive_forward(engine, si, st, ti, tt, temperature, group=None):
         import torch.distributed as dist
         dist.all_reduce(sums, group=group)
         out = torch.stack([0.5 * (sums[0] + sums[1]) / b_global, 0.5 * (sums[2] + sums[3])]).to(torch.float32)
-    saved = dict(si=si, st=st, ti=ti, tt=tt, si_all=si_all, st_all=st_all, ti_all=ti_all, tt_all=tt_all,
-                 si_inv_all=si_inv_all, st_inv_all=st_inv_all, ti_inv_all=ti_inv_all, tt_inv_all=tt_inv_all,
+    saved = dict(si=si, st=st, ti=ti, tt=tt, st_all=st_all, tt_all=tt_all,
+                 si_inv=si_inv, st_inv_all=st_inv_all, ti_inv=ti_inv, tt_inv_all=tt_inv_all,
                  stats_i2t=stats_i2t, stats_t2i=stats_t2i, col_stats=col, offset=offset, b_global=b_global, world=world,
                  group=group, rank=rank, temperature=temperature, has_teacher=has_teacher)
     return out, saved
@@ -276,27 +271,33 @@ def contrastive_backward(engine, saved, upstream, want_img=True, want_txt=True, 
     dim = s["si"].shape[1]
     if want_img and want_txt and engine.single_pass_supported(dim):
         # one recompute: the image-side pass also stores G 2^k [local image rows, all text columns]; the text-side
-        # accumulator is G^T a_hat over the LOCAL image rows, summed across ranks (reduce-scatter to the local text rows)
+        # accumulator is G^T a_hat over the LOCAL image rows, summed across ranks (reduce-scatter to the local text rows);
+        # its label term pairs local text row i with local image row i
         g_tiles = engine.alloc_g(b_local, b_global, s["si"].device)
         g_img = engine.row_grads(s["si"], s["st_all"], s["ti"], s["tt_all"],
                                  engine.transpose_norm(s["st_all"], s["st_inv_all"]),
-                                 local(s["si_inv_all"]), s["st_inv_all"], local(s["ti_inv_all"]), s["tt_inv_all"],
+                                 s["si_inv"], s["st_inv_all"], s["ti_inv"], s["tt_inv_all"],
                                  coef_i2t, coef_t2i_all, gmax_i2t, gmax_t2i, offset, b_global, T, upstream,
                                  grad_dtype or s["si"].dtype, g_out=g_tiles)
-        acc = engine.col_acc_from_g(g_tiles, engine.transpose_norm(s["si"], local(s["si_inv_all"])), b_local, b_global, dim)
+        acc = engine.col_acc_from_g(g_tiles, engine.transpose_norm(s["si"], s["si_inv"]), b_local, b_global, dim)
         acc = _reduce_scatter_rows(acc, group, world, s["rank"])
-        g_txt = engine.finish_grads(acc, s["st"], local(s["st_inv_all"]), s["si_all"], s["si_inv_all"], gmax_t2i, gmax_i2t,
-                                    offset, b_global, upstream, grad_dtype or s["st"].dtype)
+        g_txt = engine.finish_grads(acc, s["st"], local(s["st_inv_all"]), s["si"], s["si_inv"], gmax_t2i, gmax_i2t,
+                                    0, b_global, upstream, grad_dtype or s["st"].dtype)
         return g_img, g_txt
     if want_img:
         g_img = engine.row_grads(s["si"], s["st_all"], s["ti"], s["tt_all"],
                                  engine.transpose_norm(s["st_all"], s["st_inv_all"]),
-                                 local(s["si_inv_all"]), s["st_inv_all"], local(s["ti_inv_all"]), s["tt_inv_all"],
+                                 s["si_inv"], s["st_inv_all"], s["ti_inv"], s["tt_inv_all"],
                                  coef_i2t, coef_t2i_all, gmax_i2t, gmax_t2i, offset, b_global, T, upstream, grad_dtype or s["si"].dtype)
     if want_txt:
-        g_txt = engine.row_grads(s["st"], s["si_all"], s["tt"], s["ti_all"],
-                                 engine.transpose_norm(s["si_all"], s["si_inv_all"]),
-                                 local(s["st_inv_all"]), s["si_inv_all"], local(s["tt_inv_all"]), s["ti_inv_all"],
+        # two-pass route: a second recompute over this rank's text rows against ALL image rows (gathered only here)
+        si_all = _all_gather_rows(s["si"], group, world)
+        ti_all = _all_gather_rows(s["ti"], group, world) if has_teacher else None
+        si_inv_all = _all_gather_rows(s["si_inv"], group, world)
+        ti_inv_all = _all_gather_rows(s["ti_inv"], group, world) if has_teacher else None
+        g_txt = engine.row_grads(s["st"], si_all, s["tt"], ti_all,
+                                 engine.transpose_norm(si_all, si_inv_all),
+                                 local(s["st_inv_all"]), si_inv_all, local(s["tt_inv_all"]), ti_inv_all,
                                  coef_t2i, coef_i2t_all, gmax_t2i, gmax_i2t, offset, b_global, T, upstream, grad_dtype or s["st"].dtype)
     return g_img, g_txt
 
