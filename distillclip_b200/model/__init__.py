@@ -3,9 +3,9 @@ from ._loss import IMAGE_TEXT_LOSS, LOSSNAME, LossCalculator
 from .component.clip_model import CLIPModel
 from .component.output import CLIPOutput, ControlOutput, TextTransformerOutput, VisionTransformerOutput
 from .loss_component import (AttentionProbsKL, AttentionProbsMSE, AttentionScoreMSE, CLIPCosDiff, EmbedMSELoss, HardLabel,
-                             HiddenMSE, LogitsMSE, OutCELoss, OutCosLoss, OutKLLoss, OutL1Loss, SoftLabel)
+                             HiddenMSE, LastValueMapKL, LogitsMSE, OutCELoss, OutCosLoss, OutKLLoss, OutL1Loss, SoftLabel)
 
 __all__ = ["LossCalculator", "LOSSNAME", "IMAGE_TEXT_LOSS", "CLIPModel", "CLIPOutput", "ControlOutput",
            "TextTransformerOutput", "VisionTransformerOutput", "AttentionProbsKL", "AttentionProbsMSE", "AttentionScoreMSE",
-           "CLIPCosDiff", "EmbedMSELoss", "HardLabel", "HiddenMSE", "LogitsMSE", "OutCELoss", "OutCosLoss", "OutKLLoss", "OutL1Loss",
+           "CLIPCosDiff", "EmbedMSELoss", "HardLabel", "HiddenMSE", "LastValueMapKL", "LogitsMSE", "OutCELoss", "OutCosLoss", "OutKLLoss", "OutL1Loss",
            "SoftLabel"]

@@ -10,8 +10,8 @@ two-tower hard/soft-label terms run as the fused tcgen05 contrastive kernel stra
 
 In scope: hard_label, soft_label, attention_probs_kl, hidden_rep_mse, embedding_mse; widened
 (section 8f) to the losses of the three shipped configs and their siblings: out_l1, out_cos, cos_diff,
-attention_probs_mse, attention_score_mse, out_kl, out_ce, logits_mse.  The reference's remaining names (last_value_map_kl,
-vit_kd, fine_grain, smd) are recognised but raise NotImplementedError.
+attention_probs_mse, attention_score_mse, out_kl, out_ce, logits_mse, last_value_map_kl.  The reference's remaining names
+(vit_kd, fine_grain, smd) are recognised but raise NotImplementedError.
 """
 from typing import Dict, List, Union
 
@@ -21,7 +21,7 @@ from torch import nn
 from .. import contrastive, ops
 from .component.output import CLIPOutput, ControlOutput, TextTransformerOutput, VisionTransformerOutput
 from .loss_component import (AttentionProbsKL, AttentionProbsMSE, AttentionScoreMSE, CLIPCosDiff, EmbedMSELoss,
-                             HardLabel, HiddenMSE, LogitsMSE, OutCELoss, OutCosLoss, OutKLLoss, OutL1Loss, SoftLabel)
+                             HardLabel, HiddenMSE, LastValueMapKL, LogitsMSE, OutCELoss, OutCosLoss, OutKLLoss, OutL1Loss, SoftLabel)
 
 # reference _loss.py:9-12 -- including the missing comma that fuses 'smd' and 'hard_label' 
 LOSSNAME = ['out_l1', 'out_ce', 'out_kl', 'out_cos', 'embedding_mse', 'attention_score_mse',
@@ -30,7 +30,7 @@ LOSSNAME = ['out_l1', 'out_ce', 'out_kl', 'out_cos', 'embedding_mse', 'attention
 IMAGE_TEXT_LOSS = ['hard_label', 'soft_label', 'logits_mse', 'fine_grain', 'cos_diff']
 
 # names the reference accepts (_loss.py:60-94) that are outside this build's hot-path scope
-_REFERENCE_ONLY = ('last_value_map_kl', 'vit_kd', 'fine_grain', 'smd')
+_REFERENCE_ONLY = ('vit_kd', 'fine_grain', 'smd')
 
 # one-tower losses: name -> (kernel family, student field, is a list of layers)
 _TOWER_KERNELS = {
@@ -92,6 +92,7 @@ class LossCalculator(nn.Module):
             'hidden_rep_mse': HiddenMSE, 'attention_probs_kl': AttentionProbsKL,
             'hard_label': HardLabel, 'soft_label': lambda: SoftLabel(self.temperature), 'cos_diff': CLIPCosDiff,
             'out_ce': OutCELoss, 'out_kl': lambda: OutKLLoss(self.temperature), 'logits_mse': LogitsMSE,
+            'last_value_map_kl': LastValueMapKL,
         }
         losses = nn.ModuleDict()
         for n in self.loss_name:
@@ -130,6 +131,8 @@ class LossCalculator(nn.Module):
                 assert self.temperature, 'You should give the temperature for the kl loss'
             if name in ('out_ce', 'out_kl'):
                 module_res[name] = self.loss[name](stu_out.last_representation, tea_out.last_representation)
+            elif name == 'last_value_map_kl':
+                module_res[name] = self.loss[name](stu_out.value_map, tea_out.value_map)
         spec, tensors, order = [], [], []
         for name in self.loss:
             if name not in _TOWER_KERNELS:
@@ -181,7 +184,7 @@ class LossCalculator(nn.Module):
                     pending_fused = False
                 continue
             cal_res[loss_name] = cal_res[loss_name] * scale
-            loss += cal_res[loss_name] * self.percent[loss_name]
+            loss = loss + cal_res[loss_name] * self.percent[loss_name]      # not in place: `loss` may be an output view of the tower kernel
         return loss, cal_res
 
     def cal_tow_tower_loss(self, stu_out: CLIPOutput, tea_out: CLIPOutput):

@@ -421,3 +421,41 @@ def row_softmax_loss(stu: torch.Tensor, tea: torch.Tensor, temperature, mode: in
     if tea.dtype != stu.dtype:
         tea = tea.to(stu.dtype)
     return RowSoftmaxLossFn.apply(stu.contiguous(), tea.contiguous(), temperature, mode)
+
+
+# ----------------------------------------------------------------------------------------------
+# LastValueMapKL: KL over the head axis of [B, H, N, N] value-relation maps
+# ----------------------------------------------------------------------------------------------
+class ValueMapKLFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, stu, tea, expected):
+        b, h = stu.shape[0], stu.shape[1]
+        grad = torch.empty_like(stu) if ctx.needs_input_grad[0] else None
+        partials = torch.empty(_lib.MAX_PARTIALS, dtype=torch.float64, device=stu.device)
+        count = C.c_int(0)
+        _lib.call("dcb_value_map_kl_fwd_bwd", C.c_void_p(stu.data_ptr()), C.c_void_p(tea.data_ptr()),
+                  C.c_void_p(grad.data_ptr()) if grad is not None else None, b, h, stu.numel() // (b * h), dtype_code(stu),
+                  dtype_code(stu), float(expected), C.c_void_p(partials.data_ptr()), C.byref(count), _stream_ptr())
+        out = finalize([(partials, count.value)], [1.0], [1.0])
+        ctx.grad, ctx.expected = grad, expected
+        return out[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        grad, ctx.grad = ctx.grad, None
+        if grad is not None:
+            rescale([([grad], _as_upstream(g, grad), ctx.expected)])
+        return grad, None, None
+
+
+def value_map_kl(stu: torch.Tensor, tea: torch.Tensor):
+    """LastValueMapKL (last_value_map_kl.py:10-14): softmax over dim=1 (heads) of both maps, KLDiv(sum)."""
+    _require_cuda(stu, "student value map")
+    _require_cuda(tea, "teacher value map")
+    dtype_code(stu)
+    if stu.dim() < 3 or stu.shape != tea.shape:
+        raise ValueError(f"value maps must be equal [B, H, ...] tensors, got {tuple(stu.shape)} and {tuple(tea.shape)}")
+    tea = tea.detach()
+    if tea.dtype != stu.dtype:
+        tea = tea.to(stu.dtype)
+    return ValueMapKLFn.apply(stu.contiguous(), tea.contiguous(), float(EXPECTED_GRAD_SCALE))

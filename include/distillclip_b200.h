@@ -264,6 +264,15 @@ int dcb_row_softmax_stats(const void* stu, const void* tea, int64_t rows, int64_
 int dcb_row_softmax_grads(const void* stu, const void* tea, int64_t rows, int64_t cols, int dtype, float temperature, int mode,
                           const float* saved, const float* upstream, void* grad, int grad_dtype, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * LastValueMapKL (model/loss_component/last_value_map_kl.py:10-14): KLDiv(sum)(softmax(stu, dim=1).log(), softmax(tea, dim=1))
+ * on [batch, heads, positions] value-relation maps; the softmax runs over the HEAD axis.  One pass, forward value and
+ * student gradient (p^s - p^t) * grad_scale; heads <= 16.  partials: >= DCB_MAX_PARTIALS doubles, reduce with dcb_finalize.
+ * --------------------------------------------------------------------------------------------- */
+int dcb_value_map_kl_fwd_bwd(const void* stu, const void* tea, void* grad_stu, int64_t batch, int64_t heads,
+                             int64_t positions, int in_dtype, int grad_dtype, float grad_scale, double* partials,
+                             int* n_partials, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

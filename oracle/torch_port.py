@@ -104,6 +104,11 @@ def out_ce(stu, tea):
     return F.cross_entropy(stu, tea.softmax(dim=1))
 
 
+def last_value_map_kl(stu, tea):
+    # loss_component/last_value_map_kl.py:10-14
+    return F.kl_div(F.softmax(stu, dim=1).log(), F.softmax(tea, dim=1), reduction="sum")
+
+
 def logits_mse(stu_logits, tea_logits):
     # loss_component/logits_mse.py:9-10
     return F.mse_loss(stu_logits, tea_logits)
@@ -145,6 +150,8 @@ def one_tower(names, scale, percent, temperature, stu: Dict, tea: Dict):
             res[n] = out_kl(stu["last_representation"], tea["last_representation"], temperature)
         elif n == "out_ce":
             res[n] = out_ce(stu["last_representation"], tea["last_representation"])
+        elif n == "last_value_map_kl":
+            res[n] = last_value_map_kl(stu["value_map"], tea["value_map"])
     loss = 0
     for n, sc in scale.items():
         if n in IMAGE_TEXT_LOSS:

@@ -23,7 +23,7 @@ sys.path.insert(0, REF)
 with contextlib.redirect_stdout(io.StringIO()):
     from model._loss import LossCalculator                      # noqa: E402
     from model.loss_component import (AttentionProbsKL, AttentionProbsMSE, AttentionScoreMSE, CLIPCosDiff,  # noqa: E402
-                                      EmbedMSELoss, HardLabel, HiddenMSE, LogitsMSE, OutCELoss, OutCosLoss, OutKLLoss,
+                                      EmbedMSELoss, HardLabel, HiddenMSE, LastValueMapKL, LogitsMSE, OutCELoss, OutCosLoss, OutKLLoss,
                                       OutL1Loss, SoftLabel)
     from model.component.clip_model import CLIPModel             # noqa: E402
     from model.component.output import (CLIPOutput, ControlOutput, TextTransformerOutput,  # noqa: E402
@@ -318,6 +318,11 @@ calc_case("calc_out_kl_ce_logits_mse",
           (tower("image", 20, 3, 6, 24, 1), tower("text", 20, 2, 7, 16, 1)))
 calc_case("calc_out_kl_ce_image", dict(loss_name=["out_ce", "out_kl", "hidden_rep_mse"], temperature=4.0), "image",
           tower("image", 6, 3, 6, 24, 2), tower("image", 6, 3, 6, 24, 2))
+
+# ---- third batch: LastValueMapKL (softmax over the HEAD axis of the value-relation maps, as the encoder emits them) -----
+mse_case("value_map_kl_h3_n7", LastValueMapKL(), [probs(3, 3, 7)], [probs(3, 3, 7)], as_list=False)
+mse_case("value_map_kl_h12_n10", LastValueMapKL(), [probs(2, 12, 10)], [probs(2, 12, 10)], as_list=False)
+mse_case("value_map_kl_scores", LastValueMapKL(), [bf16(2, 8, 5, 5, scale=3.0)], [bf16(2, 8, 5, 5, scale=3.0)], as_list=False)
 
 # ---- host-logic facts (flags, errors) -------------------------------------------------------------
 facts = {}

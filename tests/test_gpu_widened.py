@@ -197,3 +197,53 @@ def test_out_kl_ce_logits_mse_two_tower_recipe(cuda_device, fused):
     loss, res = calc(clip_out(sv, stx), clip_out(tv, ttx), "all")
     loss.backward()
     _check_calc(g, loss, res, _leaves(sv) + _leaves(stx))
+
+
+# ---- third batch: LastValueMapKL -----------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["value_map_kl_h3_n7", "value_map_kl_h12_n10", "value_map_kl_scores"])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+def test_last_value_map_kl_golden(cuda_device, name, dtype):
+    import distillclip_b200.model as m
+    g = golden(name)
+    s, t = dev(g["stu0"], dtype, True), dev(g["tea0"], dtype)
+    loss = m.LastValueMapKL()(s, t)
+    (2.0 * loss).backward()
+    assert float(loss.detach()) == pytest.approx(float(g["loss_f64"]), rel=LOSS_RTOL)
+    tol = GRAD_RTOL if dtype == torch.float32 else GRAD_BF16_STORAGE_RTOL
+    assert rel_l2(s.grad.float().cpu().numpy() / 2.0, g["grad0_f64"]) <= tol
+
+
+def test_last_value_map_kl_full_size(cuda_device):
+    """Image-tower size (B=64, H=12, N=50; odd and even vector paths) against the f64 closed form, plus KL(t, t) = 0."""
+    import distillclip_b200.model as m
+    gen = torch.Generator().manual_seed(3)
+    for n in (50, 7):
+        s = torch.softmax(torch.randn(64, 12, n, n, generator=gen), -1).to(torch.bfloat16)
+        t = torch.softmax(torch.randn(64, 12, n, n, generator=gen), -1).to(torch.bfloat16)
+        sd = s.cuda().requires_grad_(True)
+        loss = m.LastValueMapKL()(sd, t.cuda())
+        loss.backward()
+        ref, gref = cf.last_value_map_kl(s.float().numpy(), t.float().numpy())
+        assert float(loss.detach()) == pytest.approx(float(ref), rel=LOSS_RTOL)
+        assert rel_l2(sd.grad.float().cpu().numpy(), gref) <= GRAD_BF16_STORAGE_RTOL
+        td = t.cuda().requires_grad_(True)
+        zero = m.LastValueMapKL()(td, t.cuda())
+        zero.backward()
+        assert abs(float(zero.detach())) <= 1e-6 * float(ref) and float(td.grad.abs().max()) == 0.0
+
+
+def test_last_value_map_kl_in_loss_calculator(cuda_device):
+    from distillclip_b200.model import LossCalculator, VisionTransformerOutput
+    gen = torch.Generator().manual_seed(4)
+    mk = lambda *sh: torch.randn(*sh, generator=gen).to(torch.bfloat16)
+    stu = VisionTransformerOutput(last_representation=mk(6, 32).cuda().requires_grad_(True), value_map=mk(6, 4, 9, 9).cuda().requires_grad_(True))
+    tea = VisionTransformerOutput(last_representation=mk(6, 32).cuda(), value_map=mk(6, 4, 9, 9).cuda())
+    calc = LossCalculator(["out_l1", "last_value_map_kl"], loss_scale={"last_value_map_kl": 0.5})
+    assert calc.get_control_output().need_value_map
+    loss, res = calc(stu, tea, "image")
+    loss.backward()
+    kl, gkl = cf.last_value_map_kl(stu.value_map.detach().float().cpu().numpy(), tea.value_map.float().cpu().numpy())
+    l1, _ = cf.out_l1(stu.last_representation.detach().float().cpu().numpy(), tea.last_representation.float().cpu().numpy())
+    assert float(res["last_value_map_kl"].detach()) == pytest.approx(0.5 * kl, rel=LOSS_RTOL)
+    assert float(loss.detach()) == pytest.approx(0.5 * (0.5 * kl) + 0.5 * l1, rel=LOSS_RTOL)
+    assert rel_l2(stu.value_map.grad.float().cpu().numpy(), 0.25 * gkl) <= GRAD_BF16_STORAGE_RTOL

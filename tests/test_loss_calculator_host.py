@@ -59,6 +59,6 @@ def test_surface():
 
 
 def test_out_of_scope_names_are_recognised():
-    for n in ("last_value_map_kl", "vit_kd", "fine_grain", "smd"):
+    for n in ("vit_kd", "fine_grain", "smd"):
         with pytest.raises(NotImplementedError):
             make([n], temperature=1.0)

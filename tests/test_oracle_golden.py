@@ -203,7 +203,10 @@ def test_cos_diff(name):
 
 @pytest.mark.parametrize("name,fn,temperature", [("out_kl_t2", "out_kl", 2.0), ("out_kl_t05_wide", "out_kl", 0.5),
                                                  ("out_ce", "out_ce", None), ("out_ce_wide", "out_ce", None),
-                                                 ("logits_mse", "logits_mse", None)])
+                                                 ("logits_mse", "logits_mse", None),
+                                                 ("value_map_kl_h3_n7", "last_value_map_kl", None),
+                                                 ("value_map_kl_h12_n10", "last_value_map_kl", None),
+                                                 ("value_map_kl_scores", "last_value_map_kl", None)])
 def test_row_softmax_and_logits_mse(name, fn, temperature):
     g = golden(name)
     args = (temperature,) if temperature else ()
