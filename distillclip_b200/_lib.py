@@ -34,6 +34,7 @@ SIGNATURES = {
     "dcb_transpose_norm_f16": [_vp, _vp, _vp, C.c_int64, C.c_int64, C.c_int64, C.c_int, _vp],
     "dcb_clip_row_stats": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int64, C.c_int64, C.c_int64, C.c_int64,
                            C.c_int, C.c_float, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "dcb_clip_rank_counts": [_vp, _vp, _vp, _vp, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int, _vp, _vp, _vp, _vp, _vp],
     "dcb_clip_col_finish": [_vp, C.c_int64, _vp, C.c_int64, C.c_int64, C.c_float, C.c_int, _vp, _vp, _vp],
     "dcb_clip_losses": [_vp, _vp, C.c_int64, C.c_int64, C.c_int64, C.c_float, C.c_int, _vp, _vp, _vp],
     "dcb_clip_grad_coef": [_vp, C.c_int64, C.c_int64, C.c_float, C.c_int, _vp, _vp, _vp, _vp],

@@ -76,6 +76,18 @@ class CudaEngine:
             return stats, rowloss
         return stats, rowloss, col_stats
 
+    def rank_counts(self, a, b, a_inv, b_inv, row_offset, ref):
+        """counts[i] = #{j : S_ij > ref[i]} for S = normalised a b^T (exact integers in fp32): the retrieval rank of the
+        label when ref = S_ii of row_stats (validation top-k accuracy, distillclip_b200/metrics.py)."""
+        rows, dim = a.shape
+        cols = b.shape[0]
+        stats = torch.empty(5, rows, dtype=torch.float32, device=a.device)
+        rowloss = torch.empty(2, rows, dtype=torch.float64, device=a.device)
+        ws = torch.empty(max(1, _lib.load().dcb_clip_workspace_bytes(rows, cols)), dtype=torch.uint8, device=a.device)
+        _lib.call("dcb_clip_rank_counts", _vp(a), _vp(b), _vp(a_inv), _vp(b_inv), rows, int(row_offset), cols, dim,
+                  ops.dtype_code(a), _vp(ref), _vp(stats), _vp(rowloss), _vp(ws), ops._stream_ptr())
+        return stats[1]
+
     def col_finish(self, col_stats, diag_local, row_offset, temperature, has_teacher):
         """Opposite-direction statistics [5, rows_local] and per-row losses of this rank's rows from complete column sums."""
         rows = diag_local.shape[0]

@@ -57,6 +57,8 @@ struct ClipFwdParams {
     float* diag;              // [rows] S_ii
     float* col_part;          // [row_blocks][4][cols] column sums of the same four statistics over each block of 128 rows
                               // (= the row statistics of the OPPOSITE direction, reduced later), or nullptr
+    const float* rank_ref;    // optional [rows]: count the logits of row i that are > rank_ref[i] into statistics slot 1 (retrieval
+                              // rank of the label for top-k accuracy; hard-label-only instantiation without column sums)
     float* dump_s;            // optional [rows, cols] raw logits (tests only), else nullptr
     float* dump_t;
     int rows, cols, dim;
@@ -215,6 +217,8 @@ clip_fwd_kernel(const __grid_constant__ CUtensorMap map_a_stu, const __grid_cons
         // folded into the running totals with an error term, so Zt, W and Q keep ~1e-7 relative accuracy even for B = 32768
         // (plain fp32 accumulation costs ~1e-4 on the loss, measured).
         float A = 0.f, Q = 0.f, Zt = 0.f, W = 0.f, diag = 0.f;
+        const float rank_ref = (!kTeacher && !kCols && p.rank_ref && row_ok) ? __ldg(p.rank_ref + grow) : 0.f;
+        int n_greater = 0;
         float cA = 0.f, cQ = 0.f, cZt = 0.f, cW = 0.f;
         bool have_diag = false;
         auto kahan = [](float& sum, float& comp, float x) {
@@ -293,6 +297,13 @@ clip_fwd_kernel(const __grid_constant__ CUtensorMap map_a_stu, const __grid_cons
                     }
 #pragma unroll
                     for (int c = 0; c < 16; ++c) a_sum += e[c];
+                    if constexpr (!kTeacher && !kCols) {
+                        if (p.rank_ref) {                     // same expression as the diagonal extraction: S_ii compares equal to itself
+#pragma unroll
+                            for (int c = 0; c < 16; ++c)
+                                n_greater += (col0 + cbase + c < p.cols && sv[c] * r_s > rank_ref) ? 1 : 0;
+                        }
+                    }
                     if (kCols) {
                         column_sums16(e, lane);
                         if (!(lane & 1)) cb[0 * kBN + cbase + (lane >> 1)] = e[0];
@@ -351,7 +362,7 @@ clip_fwd_kernel(const __grid_constant__ CUtensorMap map_a_stu, const __grid_cons
         if (row_ok) {
             float* w = p.ws + (size_t)(sp * kSubs + sub) * 4 * p.rows + grow;
             w[0] = A;
-            w[(size_t)p.rows] = Q;
+            w[(size_t)p.rows] = (!kTeacher && !kCols && p.rank_ref) ? (float)n_greater : Q;
             w[(size_t)2 * p.rows] = Zt;
             w[(size_t)3 * p.rows] = W;
             if (have_diag) p.diag[grow] = diag;
@@ -451,12 +462,13 @@ extern "C" int64_t dcb_clip_workspace_bytes(int64_t rows_local, int64_t cols) {
     return (((int64_t)dcb::clip_fwd_splits(rows_local, cols) * dcb::fwd::kSubs * 4 + 1) * rows_local + row_blocks * 4 * cols) * (int64_t)sizeof(float);
 }
 
-extern "C" int dcb_clip_row_stats(const void* stu_a, const void* stu_b, const void* tea_a, const void* tea_b,
-                                  const float* stu_a_inv, const float* stu_b_inv, const float* tea_a_inv,
-                                  const float* tea_b_inv, int64_t rows_local, int64_t row_offset, int64_t cols,
-                                  int64_t dim, int dtype, float temperature, float* stats, double* rowloss,
-                                  float* col_stats, void* workspace, float* dump_s, float* dump_t, void* stream) {
-    using namespace dcb;
+namespace dcb {
+static int clip_row_stats_impl(const void* stu_a, const void* stu_b, const void* tea_a, const void* tea_b,
+                               const float* stu_a_inv, const float* stu_b_inv, const float* tea_a_inv,
+                               const float* tea_b_inv, int64_t rows_local, int64_t row_offset, int64_t cols,
+                               int64_t dim, int dtype, float temperature, float* stats, double* rowloss,
+                               float* col_stats, void* workspace, float* dump_s, float* dump_t, const float* rank_ref,
+                               void* stream) {
     DCB_REQUIRE(stu_a && stu_b && stu_a_inv && stu_b_inv && stats && rowloss && workspace, "NULL pointer argument");
     DCB_REQUIRE(dtype == DCB_BF16 || dtype == DCB_F16, "the fused contrastive kernel takes bf16 or fp16 embeddings");
     DCB_REQUIRE(rows_local >= 1 && cols >= 1 && dim >= 8 && dim % 8 == 0, "bad shape rows=%lld cols=%lld dim=%lld (dim %% 8 == 0)",
@@ -494,6 +506,7 @@ extern "C" int dcb_clip_row_stats(const void* stu_a, const void* stu_b, const vo
     p.col_part = col_stats ? p.diag + rows_local : nullptr;
     p.dump_s = dump_s;
     p.dump_t = dump_t;
+    p.rank_ref = rank_ref;
     p.inv_temp = teacher ? 1.0f / temperature : 1.0f;
     const int row_blocks = (int)((rows_local + fwd::kBM - 1) / fwd::kBM);
     const uint32_t idesc = tc::umma_idesc_f16(2 * fwd::kBM, fwd::kBN, dtype == DCB_BF16 ? 1 : 0);     // M = 256 over the CTA pair
@@ -533,6 +546,26 @@ extern "C" int dcb_clip_row_stats(const void* stu_a, const void* stu_b, const vo
         DCB_CUDA_OK(cudaGetLastError());
     }
     return 0;
+}
+}  // namespace dcb
+
+extern "C" int dcb_clip_row_stats(const void* stu_a, const void* stu_b, const void* tea_a, const void* tea_b,
+                                  const float* stu_a_inv, const float* stu_b_inv, const float* tea_a_inv,
+                                  const float* tea_b_inv, int64_t rows_local, int64_t row_offset, int64_t cols,
+                                  int64_t dim, int dtype, float temperature, float* stats, double* rowloss,
+                                  float* col_stats, void* workspace, float* dump_s, float* dump_t, void* stream) {
+    return dcb::clip_row_stats_impl(stu_a, stu_b, tea_a, tea_b, stu_a_inv, stu_b_inv, tea_a_inv, tea_b_inv, rows_local, row_offset,
+                                    cols, dim, dtype, temperature, stats, rowloss, col_stats, workspace, dump_s, dump_t, nullptr,
+                                    stream);
+}
+
+extern "C" int dcb_clip_rank_counts(const void* a, const void* b, const float* a_inv, const float* b_inv, int64_t rows_local,
+                                    int64_t row_offset, int64_t cols, int64_t dim, int dtype, const float* ref, float* stats,
+                                    double* rowloss, void* workspace, void* stream) {
+    using namespace dcb;
+    DCB_REQUIRE(ref, "NULL reference scores");
+    return clip_row_stats_impl(a, b, nullptr, nullptr, a_inv, b_inv, nullptr, nullptr, rows_local, row_offset, cols, dim, dtype,
+                               1.0f, stats, rowloss, nullptr, workspace, nullptr, nullptr, ref, stream);
 }
 
 extern "C" int dcb_clip_col_finish(const float* col_stats, int64_t cols_total, const float* diag_local, int64_t row_offset,

@@ -165,6 +165,14 @@ int dcb_clip_row_stats(const void* stu_a, const void* stu_b, const void* tea_a, 
                        float* stats, double* rowloss, float* col_stats, void* workspace, float* dump_s, float* dump_t,
                        void* stream);
 
+/* Retrieval rank of the label (validation metrics, model/dual_distill_model.py:129-187,220-224: norm_and_logits + top-k
+ * accuracy): same tiles as dcb_clip_row_stats without a teacher, and stats[1][i] = #{j : S_ij > ref[i]} (exact integer in a
+ * float).  With ref = stats[4] (= S_ii) of a previous dcb_clip_row_stats call the label is in the top k iff stats[1][i] < k;
+ * the diagonal itself is produced by the same instructions and never counts as greater than itself. */
+int dcb_clip_rank_counts(const void* a, const void* b, const float* a_inv, const float* b_inv, int64_t rows_local,
+                         int64_t row_offset, int64_t cols, int64_t dim, int dtype, const float* ref, float* stats,
+                         double* rowloss, void* workspace, void* stream);
+
 /* Row statistics / per-row losses of the opposite direction for this rank's rows from the complete column statistics:
  * stats[k][i] = col_stats[k][row_offset + i] (k < 4), stats[4][i] = diag_local[i] (= stats[4] of dcb_clip_row_stats:
  * the logit matrix has one diagonal), rowloss as above. */

@@ -324,6 +324,29 @@ mse_case("value_map_kl_h3_n7", LastValueMapKL(), [probs(3, 3, 7)], [probs(3, 3, 
 mse_case("value_map_kl_h12_n10", LastValueMapKL(), [probs(2, 12, 10)], [probs(2, 12, 10)], as_list=False)
 mse_case("value_map_kl_scores", LastValueMapKL(), [bf16(2, 8, 5, 5, scale=3.0)], [bf16(2, 8, 5, 5, scale=3.0)], as_list=False)
 
+# ---- validation metrics (dual_distill_model.py:204-224, 271-275).  The module itself cannot be imported here (it pulls in
+# pytorch_lightning and torchmetrics, neither is installed): norm_and_logits and log_diag_score are restated line by line,
+# torchmetrics' multiclass top-k accuracy as "label among torch.topk(logits, k)".
+def retrieval_case(name, b, d, noise):
+    img = bf16(b, d)
+    txt = (img.float() + noise * bf16(b, d).float()).to(torch.bfloat16)
+    out = {}
+    for dt, tag in ((torch.float32, "f32"), (torch.float64, "f64")):
+        a, c = img.to(dt), txt.to(dt)
+        a = a / a.norm(dim=1, keepdim=True)
+        c = c / c.norm(dim=1, keepdim=True)
+        logits = a @ c.t()
+        label = torch.arange(b)
+        for k in (1, 3, 5, 10, 20, 50):
+            out[f"acc_top{k}_{tag}"] = (logits.topk(min(k, b), dim=1).indices == label[:, None]).any(1).to(dt).mean().numpy()
+        out[f"softmax_mean_score_{tag}"] = torch.diagonal(torch.softmax(logits, dim=1)).mean().numpy()
+        out[f"mean_score_{tag}"] = torch.diagonal(logits).mean().numpy()
+    save(name, img=img.float().numpy(), txt=txt.float().numpy(), **out)
+
+
+retrieval_case("retrieval_b200_d64", 200, 64, 3.0)
+retrieval_case("retrieval_b77_d40", 77, 40, 1.5)
+
 # ---- host-logic facts (flags, errors) -------------------------------------------------------------
 facts = {}
 with contextlib.redirect_stdout(io.StringIO()):

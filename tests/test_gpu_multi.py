@@ -72,3 +72,40 @@ def test_nccl_row_sharded_matches_oracle(cuda_device, b, d, T, single_pass):
         assert soft == pytest.approx(ref["soft"], rel=LOSS_RTOL)
     assert rel_l2(np.concatenate([r[3] for r in res]), ref["d_img"]) <= GRAD_BF16_STORAGE_RTOL
     assert rel_l2(np.concatenate([r[4] for r in res]), ref["d_txt"]) <= GRAD_BF16_STORAGE_RTOL
+
+
+def _metrics_worker(rank, world, port, q):
+    import torch.distributed as dist
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world,
+                            device_id=torch.device("cuda", rank))
+    from distillclip_b200.metrics import retrieval_metrics
+    si, st, _, _ = _inputs(1024, 256, 5)
+    n = 1024 // world
+    rows = slice(rank * n, (rank + 1) * n)
+    res = retrieval_metrics(si[rows].cuda(), st[rows].cuda(), group=dist.group.WORLD)
+    q.put((rank, {k: float(v) for k, v in res.items()}))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_nccl_retrieval_metrics_match_oracle(cuda_device):
+    world = min(torch.cuda.device_count(), 4)
+    if world < 2:
+        pytest.skip("needs >= 2 GPUs")
+    si, st, _, _ = _inputs(1024, 256, 5)
+    want = cf.retrieval_metrics(si.float().numpy(), st.float().numpy())
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() + 7) % 2000
+    procs = [ctx.Process(target=_metrics_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=240) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for _, got in res:
+        for k, v in want.items():
+            assert got[k] == pytest.approx(v, rel=LOSS_RTOL, abs=1.5 / 1024), k

@@ -247,3 +247,48 @@ def test_last_value_map_kl_in_loss_calculator(cuda_device):
     assert float(res["last_value_map_kl"].detach()) == pytest.approx(0.5 * kl, rel=LOSS_RTOL)
     assert float(loss.detach()) == pytest.approx(0.5 * (0.5 * kl) + 0.5 * l1, rel=LOSS_RTOL)
     assert rel_l2(stu.value_map.grad.float().cpu().numpy(), 0.25 * gkl) <= GRAD_BF16_STORAGE_RTOL
+
+
+# ---- validation metrics from the embeddings ---------------------------------------------------------
+@pytest.mark.parametrize("name", ["retrieval_b200_d64", "retrieval_b77_d40"])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+def test_retrieval_metrics_golden(cuda_device, name, dtype):
+    """norm_and_logits + top-k accuracy + diagonal scores without the B x B logits; fp32 embeddings go through the
+    bf16 hi/lo split.  Accuracies are counts / B: exact unless two logits of a row tie within rounding."""
+    from distillclip_b200.metrics import retrieval_metrics
+    g = golden(name)
+    b = g["img"].shape[0]
+    res = retrieval_metrics(dev(g["img"], dtype), dev(g["txt"], dtype), prefix="stu_")
+    assert set(res) == {f"stu_acc_top{k}" for k in (1, 3, 5, 10, 20, 50)} | {"stu_softmax_mean_score", "stu_mean_score"}
+    for k in (1, 3, 5, 10, 20, 50):
+        assert abs(float(res[f"stu_acc_top{k}"]) - float(g[f"acc_top{k}_f64"])) <= 1.0 / b + 1e-6, k
+    assert float(res["stu_softmax_mean_score"]) == pytest.approx(float(g["softmax_mean_score_f64"]), rel=LOSS_RTOL)
+    assert float(res["stu_mean_score"]) == pytest.approx(float(g["mean_score_f64"]), rel=LOSS_RTOL)
+
+
+def test_retrieval_ranks_exact_and_fp32_split(cuda_device):
+    """Per-row ranks against the f64 oracle at B=1000, D=512: bf16 inputs are exact products on the tensor cores, so ranks
+    may differ only where two logits are within fp32 accumulation error; the fp32 path must resolve differences bf16
+    rounding of the inputs would hide (embeddings that differ only below bf16 precision)."""
+    from distillclip_b200 import contrastive as ct
+    from distillclip_b200.metrics import retrieval_metrics
+    gen = torch.Generator().manual_seed(8)
+    img = torch.randn(1000, 512, generator=gen).to(torch.bfloat16)
+    txt = (img.float() + 4.0 * torch.randn(1000, 512, generator=gen)).to(torch.bfloat16)
+    eng = ct.CudaEngine()
+    a, b = img.cuda(), txt.cuda()
+    inv = eng.inv_norms([a, b])
+    stats, _ = eng.row_stats(a, b, None, None, inv[0], inv[1], None, None, 0, None)
+    ranks = eng.rank_counts(a, b, inv[0], inv[1], 0, stats[4].contiguous()).cpu().numpy()
+    s_ref, _ = cf.clip_logits(img.float().numpy(), txt.float().numpy())
+    ref = (s_ref > np.diag(s_ref)[:, None]).sum(1)
+    assert (ranks != ref).mean() <= 0.01 and np.abs(ranks - ref).max() <= 2
+    # fp32: perturb below bf16 resolution; the oracle on the fp32 values is the reference
+    img32 = img.float() * (1 + 1e-3 * torch.randn(1000, 512, generator=gen))
+    txt32 = txt.float() * (1 + 1e-3 * torch.randn(1000, 512, generator=gen))
+    res = retrieval_metrics(img32.cuda(), txt32.cuda())
+    want = cf.retrieval_metrics(img32.numpy(), txt32.numpy())
+    for k in (1, 5, 50):
+        assert abs(float(res[f"acc_top{k}"]) - want[f"acc_top{k}"]) <= 2e-3, k
+    assert float(res["mean_score"]) == pytest.approx(want["mean_score"], rel=2e-5)
+    assert float(res["softmax_mean_score"]) == pytest.approx(want["softmax_mean_score"], rel=2e-5)

@@ -238,3 +238,13 @@ def test_calculator_port_shipped_recipes(name, kind, temperature):
     assert float(loss) == pytest.approx(float(g["loss_f32"]), rel=2e-6)
     for k, v in res.items():
         assert float(v) == pytest.approx(float(g[f"res.{k}_f32"]), rel=2e-6), k
+
+
+@pytest.mark.parametrize("name", ["retrieval_b200_d64", "retrieval_b77_d40"])
+def test_retrieval_metrics(name):
+    """Validation metrics (dual_distill_model.py:204-224): the oracle's rank formulation (label in the top k iff fewer than
+    k logits of its row are strictly larger) against torch.topk membership."""
+    g = golden(name)
+    res = cf.retrieval_metrics(g["img"], g["txt"])
+    for k, v in res.items():
+        assert v == pytest.approx(float(g[f"{k}_f64"]), rel=1e-12, abs=1e-15), k
