@@ -30,15 +30,16 @@ def _split_fp32(x: torch.Tensor, first_lo: bool):
 
 
 def retrieval_metrics(img: torch.Tensor, txt: torch.Tensor, k_list: Sequence[int] = K_LIST, group=None,
-                      prefix: str = "") -> Dict[str, torch.Tensor]:
+                      prefix: str = "", engine=None) -> Dict[str, torch.Tensor]:
     """-> {f'{prefix}acc_top{k}', f'{prefix}softmax_mean_score', f'{prefix}mean_score'} as 0-dim fp32 CUDA tensors for
     logits = normalise(img) @ normalise(txt).T of the GLOBAL batch (rows of all ranks in rank order)."""
-    ops._require_cuda(img, "image embeddings")
-    ops._require_cuda(txt, "text embeddings")
+    if engine is None:                       # product path: CUDA only; tests pass a CPU engine double for the sharding logic
+        ops._require_cuda(img, "image embeddings")
+        ops._require_cuda(txt, "text embeddings")
+        engine = ct._ENGINE
     if img.dim() != 2 or img.shape != txt.shape:
         raise ValueError(f"expected equal [B, D] embeddings, got {tuple(img.shape)} and {tuple(txt.shape)}")
     img, txt = img.detach(), txt.detach()
-    engine = ct._ENGINE
     rank, world = ct._shard_info(group)
     b_local = img.shape[0]
     if img.dtype == torch.float32:
@@ -46,7 +47,8 @@ def retrieval_metrics(img: torch.Tensor, txt: torch.Tensor, k_list: Sequence[int
         b_inv = (1.0 / txt.norm(dim=1)).contiguous()
         a, b = _split_fp32(img, True), _split_fp32(txt, False)
     else:
-        ops.dtype_code(img)
+        if img.is_cuda:
+            ops.dtype_code(img)
         a, b = img.contiguous(), txt.to(img.dtype).contiguous()
         a_inv, b_inv = engine.inv_norms([a, b])
     if a.shape[1] % 8:

@@ -43,6 +43,9 @@ class DoubleEngine:
             rl[1] = -m + torch.log1p(m + st[1] / st[2])
         return rl
 
+    def rank_counts(self, a, b, a_inv, b_inv, row_offset, ref):
+        return (self._logits(a, b, a_inv, b_inv) > ref[:, None]).sum(1).double()
+
     def col_finish(self, col_stats, diag_local, row_offset, temperature, has_teacher):
         rows = diag_local.shape[0]
         st = torch.zeros(5, rows, dtype=torch.float64)

@@ -88,3 +88,38 @@ def test_row_sharded_world2_gloo(name, single_pass):
     gt = np.concatenate([r[3] for r in res])
     assert rel_l2(gi, ref["d_img"]) <= 1e-8
     assert rel_l2(gt, ref["d_txt"]) <= 1e-8
+
+
+def _metrics_worker(rank, world, port, name, q):
+    import torch.distributed as dist
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    from distillclip_b200.metrics import retrieval_metrics
+    g = golden(name)
+    b = g["img"].shape[0] // world
+    rows = slice(rank * b, (rank + 1) * b)
+    res = retrieval_metrics(torch.tensor(g["img"])[rows].double(), torch.tensor(g["txt"])[rows].double(), group=dist.group.WORLD,
+                            engine=DoubleEngine())
+    q.put((rank, {k: float(v) for k, v in res.items()}))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_retrieval_metrics_sharded_world2_gloo():
+    """Validation metrics with the rows split over 2 ranks (text rows gathered, per-rank sums all-reduced) = the
+    reference-generated values for the whole batch."""
+    name = "retrieval_b200_d64"
+    g = golden(name)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() + 11) % 2000
+    procs = [ctx.Process(target=_metrics_worker, args=(r, 2, port, name, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for _, got in res:
+        for k, v in got.items():
+            assert v == pytest.approx(float(g[f"{k}_f64"]), rel=1e-6, abs=1e-9), k
