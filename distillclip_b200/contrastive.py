@@ -210,6 +210,8 @@ def _reduce_scatter_rows(x: torch.Tensor, group, world: int, rank: int) -> torch
         return x
     import torch.distributed as dist
     n = x.shape[1] // world
+    if x.shape[0] > 1:
+        x = x.sum(0, keepdim=True)               # K-split partials: one collective of [B, D] instead of one per split
     if dist.get_backend(group) == "nccl":
         out = torch.empty(x.shape[0], n, x.shape[2], dtype=x.dtype, device=x.device)
         for k in range(x.shape[0]):
