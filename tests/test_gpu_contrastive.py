@@ -141,7 +141,7 @@ def test_fused_contrastive_golden(cuda_device, bwd_kernel, name):
 
 @pytest.mark.parametrize("b,d,T,dtype", [(256, 512, 2.0, torch.bfloat16), (512, 512, 1.0, torch.bfloat16),
                                          (384, 768, 4.0, torch.bfloat16), (200, 136, 0.5, torch.bfloat16),
-                                         (256, 512, 2.0, torch.float16)])
+                                         (256, 512, 2.0, torch.float16), (256, 1024, 2.0, torch.bfloat16)])
 def test_fused_contrastive_random_vs_oracle(cuda_device, bwd_kernel, b, d, T, dtype):
     si, st, ti, tt = synth(b, d, b + d, dtype)
     ref = cf.contrastive_from_embeddings(*[x.float().numpy() for x in (si, st, ti, tt)], T, w_hard=0.6, w_soft=0.4)
