@@ -150,8 +150,12 @@ clip_bwd_pair_kernel(const __grid_constant__ CUtensorMap map_a_stu, const __grid
     const uint32_t l_full = map_to_cta(bar_full, 0), l_stempty = map_to_cta(bar_stempty, 0);
     const uint32_t l_gfull = map_to_cta(bar_gfull, 0);
 
-    if (warp == 0) {
-        // ---------------------------------------------------------------- operand ring (own halves), MMA issue order
+    if (warp == 0 || warp == 2) {
+        // ---------------------------------------------------------------- operand ring (own halves), MMA issue order.
+        // Two issuing threads (warp 0: student boxes + first K sub-tile of a slice, warp 2: teacher boxes + second sub-tile):
+        // one thread sustains ~50-65 B/clk of 8 KiB boxes, two ~74 (scripts/probe/tma_probe.cu).  Both walk the same
+        // stage/phase sequence; warp 0 alone arms the transaction count.
+        const bool second = warp == 2;
         if (elect_one()) {
             tma_prefetch_desc(&map_a_stu);
             tma_prefetch_desc(&map_b_stu);
@@ -165,11 +169,12 @@ clip_bwd_pair_kernel(const __grid_constant__ CUtensorMap map_a_stu, const __grid
                     for (int kc = 0; kc < n_kc; ++kc) {
                         mbar_wait(bar_empty + 8 * stage, phase ^ 1);
                         const uint32_t dst = ring + stage * C::kStageBytes;
-                        if (leader) mbar_arrive_expect_tx(bar_full + 8 * stage, 2 * kStBytesPerCta);
+                        if (leader && !second) mbar_arrive_expect_tx(bar_full + 8 * stage, 2 * kStBytesPerCta);
                         const uint32_t full = l_full + 8 * stage;
-                        tma_load_2d_pair(dst, &map_a_stu, full, kc * kBK, row0);
-                        tma_load_2d_pair(dst + 2 * kATile, &map_b_stu, full, kc * kBK, col0);
-                        if (kTeacher) {
+                        if (!second) {
+                            tma_load_2d_pair(dst, &map_a_stu, full, kc * kBK, row0);
+                            tma_load_2d_pair(dst + 2 * kATile, &map_b_stu, full, kc * kBK, col0);
+                        } else if (kTeacher) {
                             tma_load_2d_pair(dst + kATile, &map_a_tea, full, kc * kBK, row0);
                             tma_load_2d_pair(dst + 2 * kATile + C::kBTile, &map_b_tea, full, kc * kBK, col0);
                         }
@@ -181,11 +186,12 @@ clip_bwd_pair_kernel(const __grid_constant__ CUtensorMap map_a_stu, const __grid
                     for (int sl = 0; sl < p.slices; ++sl) {
                         mbar_wait(bar_empty + 8 * stage, phase ^ 1);
                         const uint32_t dst = ring + stage * C::kStageBytes;
-                        if (leader) mbar_arrive_expect_tx(bar_full + 8 * stage, 2 * C::kBtSliceBytes);
+                        if (leader && !second) mbar_arrive_expect_tx(bar_full + 8 * stage, 2 * C::kBtSliceBytes);
                         const uint32_t full = l_full + 8 * stage;
-                        for (int ks = 0; ks < kSub; ++ks)
-                            tma_load_2d_pair(dst + ks * (kSliceRows * kBK * 2), &map_bt, full, j0 + ks * kBK,
-                                             sl * 256 + (int)rank * kSliceRows);
+                        static_assert(kSub == 2, "one K sub-tile of a slice per issuing thread");
+                        const int ks = second ? 1 : 0;
+                        tma_load_2d_pair(dst + ks * (kSliceRows * kBK * 2), &map_bt, full, j0 + ks * kBK,
+                                         sl * 256 + (int)rank * kSliceRows);
                         if (++stage == C::kStages) { stage = 0; phase ^= 1; }
                     }
                 }
