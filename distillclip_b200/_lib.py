@@ -43,6 +43,7 @@ SIGNATURES = {
     "dcb_clip_row_grads_pair": [_vp, _vp, _vp, _vp, _vp, C.c_int64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int64,
                                 C.c_int64, C.c_int64, C.c_int, C.c_float, _vp, _vp, C.c_int64, _vp, _vp, _vp],
     "dcb_clip_col_grads_from_g": [_vp, C.c_int64, _vp, C.c_int64, C.c_int64, C.c_int64, C.c_int64, _vp, _vp],
+    "dcb_clip_col_grads_scatter": [_vp, C.c_int64, _vp, C.c_int64, C.c_int64, C.c_int64, C.c_int64, _vp, C.c_int, C.c_int, _vp],
     "dcb_clip_grad_finish": [_vp, C.c_int, _vp, _vp, _vp, _vp, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int64,
                              _vp, _vp, _vp, C.c_int, _vp, C.c_int, _vp],
     "dcb_value_map_kl_fwd_bwd": [_vp, _vp, _vp, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_float, _vp,

@@ -165,6 +165,12 @@ class CudaEngine:
                   _vp(acc), ops._stream_ptr())
         return acc
 
+    def col_acc_scatter(self, g, a_hat_t, rows: int, cols: int, dim: int, dest_ptrs, src_slot: int):
+        """The G^T GEMM with its epilogue storing every output row into the partial buffer of the rank that owns it
+        (peer-mapped pointers `dest_ptrs`, one per rank): the reduce-scatter of the row-sharded backward without a collective."""
+        _lib.call("dcb_clip_col_grads_scatter", _vp(g), g.shape[1], _vp(a_hat_t), a_hat_t.shape[1], rows, cols, dim,
+                  _lib.ptr_array(dest_ptrs), len(dest_ptrs), int(src_slot), ops._stream_ptr())
+
     def finish_grads(self, acc, a_s, a_s_inv, b_s, b_s_inv, gmax_row, gmax_col, row_offset, global_batch, upstream,
                      grad_dtype):
         """2^-k sum_s acc[s] - label term, then the x/||x|| Jacobian (dcb_clip_grad_finish)."""
@@ -219,6 +225,39 @@ def _reduce_scatter_rows(x: torch.Tensor, group, world: int, rank: int) -> torch
         return out
     dist.all_reduce(x, group=group)                  # gloo (CPU tests) has no reduce_scatter
     return x[:, rank * n:(rank + 1) * n].contiguous()
+
+
+class PeerScatter:
+    """Symmetric (peer-mapped) partial buffers for the fused G^T GEMM + reduce-scatter: rank r owns
+    [world * k_split][B/R][D] fp32; every rank's GEMM epilogue stores the rows r owns into slot block `src rank` of r's
+    buffer over NVLink.  Two stream-ordered cross-rank barriers fence a step: before the GEMM (the owner has finished reading
+    the previous step's partials) and after it (all stores have landed).  torch symmetric memory supplies the mapping and the
+    barrier; set DCB_PEER_SCATTER=0 (or `enabled = False`) to use the NCCL reduce-scatter instead."""
+    enabled = os.environ.get("DCB_PEER_SCATTER", "1") != "0"
+    _cache: Dict = {}
+    _broken = False
+
+    @classmethod
+    def get(cls, group, world: int, slots: int, rows: int, dim: int, device):
+        """-> (handle, local buffer [slots, rows, dim], peer pointers) or None when symmetric memory is unavailable."""
+        if not cls.enabled or cls._broken or world > 16:
+            return None
+        import torch.distributed as dist
+        if dist.get_backend(group) != "nccl":
+            return None
+        key = (group.group_name, slots, rows, dim, device.index)
+        if key not in cls._cache:
+            try:
+                import torch.distributed._symmetric_memory as symm
+                buf = symm.empty(slots * rows * dim, dtype=torch.float32, device=device)
+                hdl = symm.rendezvous(buf, group.group_name)
+                cls._cache[key] = (hdl, buf.view(slots, rows, dim), [int(p) for p in hdl.buffer_ptrs])
+            except Exception as exc:          # no P2P mapping on this machine: fall back for the rest of the process
+                cls._broken = True
+                import warnings
+                warnings.warn(f"distillclip_b200: symmetric memory unavailable ({exc}); using the NCCL reduce-scatter")
+                return None
+        return cls._cache[key]
 
 
 def _all_gather_cols(x: torch.Tensor, group, world: int) -> torch.Tensor:
@@ -293,8 +332,20 @@ def contrastive_backward(engine, saved, upstream, want_img=True, want_txt=True, 
                                  s["si_inv"], s["st_inv_all"], s["ti_inv"], s["tt_inv_all"],
                                  coef_i2t, coef_t2i_all, gmax_i2t, gmax_t2i, offset, b_global, T, upstream,
                                  grad_dtype or s["si"].dtype, g_out=g_tiles)
-        acc = engine.col_acc_from_g(g_tiles, engine.transpose_norm(s["si"], s["si_inv"]), b_local, b_global, dim)
-        acc = _reduce_scatter_rows(acc, group, world, s["rank"])
+        a_hat_t = engine.transpose_norm(s["si"], s["si_inv"])
+        peer = None
+        if world > 1 and hasattr(engine, "col_acc_scatter"):
+            k_split = _lib.load().dcb_clip_gt_splits(b_local, b_global, dim)
+            peer = PeerScatter.get(group, world, world * k_split, b_local, dim, s["si"].device)
+        if peer is not None:
+            # GEMM -> reduce-scatter in ONE kernel: the epilogue stores each text row's partial into its owner's buffer
+            hdl, acc, ptrs = peer
+            hdl.barrier(channel=0)              # owners are done with the previous step's partials
+            engine.col_acc_scatter(g_tiles, a_hat_t, b_local, b_global, dim, ptrs, s["rank"])
+            hdl.barrier(channel=1)              # every rank's stores have landed
+        else:
+            acc = engine.col_acc_from_g(g_tiles, a_hat_t, b_local, b_global, dim)
+            acc = _reduce_scatter_rows(acc, group, world, s["rank"])
         g_txt = engine.finish_grads(acc, s["st"], local(s["st_inv_all"]), s["si"], s["si_inv"], gmax_t2i, gmax_i2t,
                                     0, b_global, upstream, grad_dtype or s["st"].dtype)
         return g_img, g_txt

@@ -29,8 +29,16 @@ constexpr int kMaxChunk = 384;                         // N columns per cluster
 constexpr int kSmemBudget = 200 * 1024;
 }  // namespace gt
 
+constexpr int kGtMaxDest = 16;
+
 struct ClipGtParams {
-    float* acc;               // [k_split][cols][dim] fp32
+    float* acc;               // [k_split][cols][dim] fp32 (single destination)
+    // Fused reduce-scatter over peer memory: output row j belongs to rank j / rows_per_dest and is stored straight into THAT
+    // rank's partial buffer dest[rank] (a peer mapping: NVLink stores from the epilogue), slot src_slot * k_split + ks of
+    // [n_dest * k_split][rows_per_dest][dim]; the owner sums the slots in a fixed order (clip_grad_finish).  n_dest == 0: off.
+    float* dest[kGtMaxDest];
+    int n_dest, src_slot;
+    long long rows_per_dest;
     int rows, cols, dim;      // rows = i (K), cols = j (M)
     int chunk;                // N columns per cluster (multiple of 32 when > 256, of 16 otherwise)
     int pieces;               // MMA instructions per K step (1 or 2), each chunk / pieces wide
@@ -143,7 +151,14 @@ clip_gt_gemm_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_cons
         const int q = warp & 3;
         const int j = j0 + q * 32 + lane;
         const bool ok = j < p.cols;
-        float* out = p.acc + ((size_t)ks * p.cols + (ok ? j : 0)) * p.dim + n0;
+        float* out;
+        if (p.n_dest > 0) {
+            const long long jj = ok ? j : 0;
+            const int dst = (int)(jj / p.rows_per_dest);
+            out = p.dest[dst] + (((size_t)p.src_slot * p.k_split + ks) * p.rows_per_dest + (jj - dst * p.rows_per_dest)) * p.dim + n0;
+        } else {
+            out = p.acc + ((size_t)ks * p.cols + (ok ? j : 0)) * p.dim + n0;
+        }
         if (kc_end > kc_begin) {
             mbar_wait(bar_accfull, 0);
             tc_fence_after_sync();
@@ -215,10 +230,11 @@ extern "C" int dcb_clip_gt_splits(int64_t rows, int64_t cols, int64_t dim) {
     return dcb::clip_gt_plan(rows, cols, dim).k_split;
 }
 
-extern "C" int dcb_clip_col_grads_from_g(const void* g, int64_t g_pitch_elems, const void* a_hat_t, int64_t at_pitch_elems,
-                                         int64_t rows, int64_t cols, int64_t dim, float* acc_parts, void* stream) {
-    using namespace dcb;
-    DCB_REQUIRE(g && a_hat_t && acc_parts, "NULL pointer argument");
+namespace dcb {
+static int clip_gt_launch(const void* g, int64_t g_pitch_elems, const void* a_hat_t, int64_t at_pitch_elems, int64_t rows,
+                          int64_t cols, int64_t dim, float* acc_parts, void* const* dest, int n_dest, int src_slot,
+                          void* stream) {
+    DCB_REQUIRE(g && a_hat_t && (acc_parts || n_dest > 0), "NULL pointer argument");
     DCB_REQUIRE(rows >= 1 && cols >= 1 && dim >= 8 && dim % 8 == 0, "bad shape");
     DCB_REQUIRE(g_pitch_elems >= cols && g_pitch_elems % 8 == 0, "G pitch must be >= cols and a multiple of 8 elements");
     DCB_REQUIRE(at_pitch_elems >= rows && at_pitch_elems % 8 == 0, "a_hat^T pitch must be >= rows and a multiple of 8 elements");
@@ -228,6 +244,10 @@ extern "C" int dcb_clip_col_grads_from_g(const void* g, int64_t g_pitch_elems, c
     if (tc::encode_tile_map_16bit(&map_at, a_hat_t, dim, rows, (uint64_t)at_pitch_elems * 2, plan.chunk / plan.pieces / 2)) return 1;
     ClipGtParams p{};
     p.acc = acc_parts;
+    p.n_dest = n_dest;
+    p.src_slot = src_slot;
+    p.rows_per_dest = n_dest > 0 ? cols / n_dest : 0;
+    for (int i = 0; i < n_dest; ++i) p.dest[i] = static_cast<float*>(dest[i]);
     p.rows = (int)rows;
     p.cols = (int)cols;
     p.dim = (int)dim;
@@ -260,4 +280,20 @@ extern "C" int dcb_clip_col_grads_from_g(const void* g, int64_t g_pitch_elems, c
     cfg.numAttrs = 1;
     DCB_CUDA_OK(cudaLaunchKernelEx(&cfg, clip_gt_gemm_kernel, map_g, map_at, p, idesc));
     return 0;
+}
+}  // namespace dcb
+
+extern "C" int dcb_clip_col_grads_from_g(const void* g, int64_t g_pitch_elems, const void* a_hat_t, int64_t at_pitch_elems,
+                                         int64_t rows, int64_t cols, int64_t dim, float* acc_parts, void* stream) {
+    return dcb::clip_gt_launch(g, g_pitch_elems, a_hat_t, at_pitch_elems, rows, cols, dim, acc_parts, nullptr, 0, 0, stream);
+}
+
+extern "C" int dcb_clip_col_grads_scatter(const void* g, int64_t g_pitch_elems, const void* a_hat_t, int64_t at_pitch_elems,
+                                          int64_t rows, int64_t cols, int64_t dim, void* const* dest_parts, int n_dest,
+                                          int src_slot, void* stream) {
+    using namespace dcb;
+    DCB_REQUIRE(dest_parts && n_dest >= 1 && n_dest <= kGtMaxDest && cols % n_dest == 0 && src_slot >= 0 && src_slot < n_dest,
+                "scatter: 1..%d destinations owning equal row ranges, src_slot in range", kGtMaxDest);
+    for (int i = 0; i < n_dest; ++i) DCB_REQUIRE(dest_parts[i], "scatter: NULL destination %d", i);
+    return clip_gt_launch(g, g_pitch_elems, a_hat_t, at_pitch_elems, rows, cols, dim, nullptr, dest_parts, n_dest, src_slot, stream);
 }

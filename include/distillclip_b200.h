@@ -235,6 +235,15 @@ int dcb_clip_gt_splits(int64_t rows, int64_t cols, int64_t dim);
 int dcb_clip_col_grads_from_g(const void* g, int64_t g_pitch_elems, const void* a_hat_t, int64_t at_pitch_elems,
                               int64_t rows, int64_t cols, int64_t dim, float* acc_parts, void* stream);
 
+/* The same GEMM fused with the gradient reduce-scatter of the row-sharded path: output row j belongs to rank
+ * j / (cols / n_dest) and is stored from the epilogue straight into that rank's buffer dest_parts[rank] (peer-mapped device
+ * memory, NVLink stores), slot src_slot * k_split + ks of [n_dest * dcb_clip_gt_splits(...)][cols / n_dest][dim] fp32.  After
+ * a cross-rank barrier the owner reduces its slots in a fixed order with dcb_clip_grad_finish (n_split = n_dest * k_split):
+ * no NCCL reduce-scatter, no atomics, deterministic. */
+int dcb_clip_col_grads_scatter(const void* g, int64_t g_pitch_elems, const void* a_hat_t, int64_t at_pitch_elems,
+                               int64_t rows, int64_t cols, int64_t dim, void* const* dest_parts, int n_dest, int src_slot,
+                               void* stream);
+
 /* grad_a[i,:] = r_i (acc_i - a_hat_i (a_hat_i . acc_i)),  acc_i = 2^-k sum_s acc_parts[s][i,:] - (gh/B) b_hat_{row_offset+i}
  * (the -[i==j] label term of the cross entropy, added here in fp32, then the x/||x|| Jacobian of clip_model.py:37-38). */
 int dcb_clip_grad_finish(const float* acc_parts, int n_split, const void* stu_a, const float* stu_a_inv,
