@@ -147,44 +147,51 @@ clip_gt_gemm_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_cons
             }
         }
     } else {
-        // ------------------------------------------------------------ epilogue: TMEM lane = j, columns = d
+        // ------------------------------------------------------------ epilogue: TMEM lane = j, columns = d.
+        // TMEM -> registers (thread = row) -> shared memory (the operand ring is free once the accumulator is final) ->
+        // global with one ROW per store instruction: 512 contiguous bytes per warp store instead of 32 scattered 16-byte
+        // pieces, which is what makes the stores to a peer's buffer over NVLink efficient (and helps the local ones too).
         const int q = warp & 3;
-        const int j = j0 + q * 32 + lane;
-        const bool ok = j < p.cols;
-        float* out;
-        if (p.n_dest > 0) {
-            const long long jj = ok ? j : 0;
-            const int dst = (int)(jj / p.rows_per_dest);
-            out = p.dest[dst] + (((size_t)p.src_slot * p.k_split + ks) * p.rows_per_dest + (jj - dst * p.rows_per_dest)) * p.dim + n0;
-        } else {
-            out = p.acc + ((size_t)ks * p.cols + (ok ? j : 0)) * p.dim + n0;
-        }
-        if (kc_end > kc_begin) {
+        constexpr int kStageLd = 132;                                   // floats per staged row (128 + 4: conflict-free)
+        float* stage = reinterpret_cast<float*>(smem_gen) + q * (32 * kStageLd);
+        const bool have_acc = kc_end > kc_begin;
+        if (have_acc) {
             mbar_wait(bar_accfull, 0);
             tc_fence_after_sync();
         }
-        for (int c0 = 0; c0 < p.chunk; c0 += 32) {
-            if (n0 + c0 >= p.dim) break;
-            float v[32];
-            if (kc_end > kc_begin) {
-                tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c0, v);
-                tmem_ld_wait();
-            } else {
+        const int rpd = (int)p.rows_per_dest;
+        for (int g0 = 0; g0 < p.chunk; g0 += 128) {
+            if (n0 + g0 >= p.dim) break;
+            const int ccount = p.chunk - g0 < 128 ? p.chunk - g0 : 128;
+            for (int c0 = 0; c0 < ccount; c0 += 32) {
+                float v[32];
+                if (have_acc) {
+                    tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + g0 + c0, v);
+                    tmem_ld_wait();
+                } else {
 #pragma unroll
-                for (int c = 0; c < 32; ++c) v[c] = 0.f;
-            }
-            if (ok) {
-#pragma unroll
-                for (int c = 0; c < 32; c += 4) {
-                    const int d = n0 + c0 + c;
-                    if (d + 3 < p.dim) {
-                        *reinterpret_cast<float4*>(out + c0 + c) = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
-                    } else {
-                        for (int e = 0; e < 4; ++e)
-                            if (d + e < p.dim) out[c0 + c + e] = v[c + e];
-                    }
+                    for (int c = 0; c < 32; ++c) v[c] = 0.f;
                 }
+                float* dst = stage + lane * kStageLd + c0;
+#pragma unroll
+                for (int c = 0; c < 32; c += 4) *reinterpret_cast<float4*>(dst + c) = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
             }
+            __syncwarp();
+            const int d = n0 + g0 + 4 * lane;
+            const bool col_ok = 4 * lane < ccount && d + 3 < p.dim;      // dim % 8 == 0: a float4 is all in or all out
+            for (int r = 0; r < 32; ++r) {
+                const int j = j0 + q * 32 + r;
+                if (j >= p.cols) break;                                     // warp-uniform
+                float* out_row;
+                if (p.n_dest > 0) {
+                    const int dst_rank = j / rpd;
+                    out_row = p.dest[dst_rank] + (((size_t)p.src_slot * p.k_split + ks) * rpd + (j - dst_rank * rpd)) * p.dim;
+                } else {
+                    out_row = p.acc + ((size_t)ks * p.cols + j) * p.dim;
+                }
+                if (col_ok) *reinterpret_cast<float4*>(out_row + d) = *reinterpret_cast<const float4*>(stage + r * kStageLd + 4 * lane);
+            }
+            __syncwarp();
         }
     }
     tc_fence_before_sync();

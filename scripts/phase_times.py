@@ -37,7 +37,7 @@ def timed(name, fn):
 
 
 eng = ct.CudaEngine()
-for m in ("inv_norms", "row_stats", "col_finish", "losses", "coef", "transpose_norm", "row_acc", "col_acc_from_g", "finish_grads"):
+for m in ("inv_norms", "row_stats", "col_finish", "losses", "coef", "transpose_norm", "row_acc", "col_acc_from_g", "col_acc_scatter", "finish_grads"):
     setattr(eng, m, timed(m, getattr(eng, m)))
 ct._all_gather_rows = timed("all_gather_rows", ct._all_gather_rows)
 ct._all_gather_cols = timed("all_gather_cols(stats)", ct._all_gather_cols)
