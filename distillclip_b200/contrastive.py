@@ -230,12 +230,14 @@ def _reduce_scatter_rows(x: torch.Tensor, group, world: int, rank: int) -> torch
 class PeerScatter:
     """Symmetric (peer-mapped) partial buffers for the fused G^T GEMM + reduce-scatter: rank r owns
     [world * k_split][B/R][D] fp32; every rank's GEMM epilogue stores the rows r owns into slot block `src rank` of r's
-    buffer over NVLink.  Two stream-ordered cross-rank barriers fence a step: before the GEMM (the owner has finished reading
-    the previous step's partials) and after it (all stores have landed).  torch symmetric memory supplies the mapping and the
-    barrier; set DCB_PEER_SCATTER=0 (or `enabled = False`) to use the NCCL reduce-scatter instead."""
+    buffer over NVLink.  One stream-ordered cross-rank barrier after the GEMM tells the owner that all stores have landed;
+    the buffers alternate between two copies, so a rank can only overwrite partials its owner read two steps ago -- and the
+    barrier of the step in between already ordered every rank behind that read.  torch symmetric memory supplies the mapping
+    and the barrier; set DCB_PEER_SCATTER=0 (or `enabled = False`) to use the NCCL reduce-scatter instead."""
     enabled = os.environ.get("DCB_PEER_SCATTER", "1") != "0"
     _cache: Dict = {}
     _broken = False
+    _flip: Dict = {}
 
     @classmethod
     def get(cls, group, world: int, slots: int, rows: int, dim: int, device):
@@ -245,7 +247,9 @@ class PeerScatter:
         import torch.distributed as dist
         if dist.get_backend(group) != "nccl":
             return None
-        key = (group.group_name, slots, rows, dim, device.index)
+        base = (group.group_name, slots, rows, dim, device.index)
+        cls._flip[base] = cls._flip.get(base, 0) ^ 1        # alternate per shape
+        key = base + (cls._flip[base],)
         if key not in cls._cache:
             try:
                 import torch.distributed._symmetric_memory as symm
@@ -340,9 +344,8 @@ def contrastive_backward(engine, saved, upstream, want_img=True, want_txt=True, 
         if peer is not None:
             # GEMM -> reduce-scatter in ONE kernel: the epilogue stores each text row's partial into its owner's buffer
             hdl, acc, ptrs = peer
-            hdl.barrier(channel=0)              # owners are done with the previous step's partials
             engine.col_acc_scatter(g_tiles, a_hat_t, b_local, b_global, dim, ptrs, s["rank"])
-            hdl.barrier(channel=1)              # every rank's stores have landed
+            hdl.barrier(channel=0)              # every rank's stores have landed
         else:
             acc = engine.col_acc_from_g(g_tiles, a_hat_t, b_local, b_global, dim)
             acc = _reduce_scatter_rows(acc, group, world, s["rank"])
