@@ -118,6 +118,78 @@ __device__ __forceinline__ float clip_grad_tile_scale(float gmax) {     // must 
 // ---------------------------------------------------------------------------------------------
 constexpr int kFinishMaxPerLane = 24;     // rows up to 768 wide stay in registers (one pass over acc_parts)
 
+// 16-byte version for 16-bit embeddings with dim % 8 == 0, dim <= 1024: lane l owns the 8-element groups l, l + 32, ...
+// (one uint4 of a, one of the label row, two float4 per accumulator split, one 16-byte / two float4 stores per group).
+template <typename T, typename G, int kGroups>
+__global__ void __launch_bounds__(256) clip_grad_finish_vec_kernel(const float* __restrict__ acc_parts, int n_split,
+                                                                   const T* __restrict__ a, const float* __restrict__ a_inv,
+                                                                   const T* __restrict__ b, const float* __restrict__ b_inv,
+                                                                   long long rows, long long cols, int dim, long long row_offset,
+                                                                   float inv_batch, const float* __restrict__ upstream,
+                                                                   const float* __restrict__ gmax_row, const float* __restrict__ gmax_col,
+                                                                   G* __restrict__ grad) {
+    const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const int lane = threadIdx.x & 31;
+    const float r = a_inv[row];
+    const float unscale = 1.0f / clip_grad_tile_scale(gmax_row[0] + gmax_col[0]);
+    const long long gi = row_offset + row;
+    const bool has_label = gi < cols;
+    const float lab = has_label ? upstream[0] * inv_batch * b_inv[gi] : 0.f;
+    const T* __restrict__ ap = a + row * dim;
+    const T* __restrict__ bp = b + (has_label ? gi : 0) * dim;
+    G* __restrict__ gp = grad + row * dim;
+    const size_t split_stride = (size_t)rows * dim;
+    const float* __restrict__ accp = acc_parts + (size_t)row * dim;
+    float v[kGroups][8];
+#pragma unroll
+    for (int g = 0; g < kGroups; ++g)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[g][e] = 0.f;
+    for (int s = 0; s < n_split; ++s) {
+        const float* __restrict__ src = accp + (size_t)s * split_stride;
+#pragma unroll
+        for (int g = 0; g < kGroups; ++g) {
+            const int d = (lane + 32 * g) * 8;
+            if (d < dim) {
+                float lo[4], hi[4];
+                load_vec<float, 4>(src + d, lo);
+                load_vec<float, 4>(src + d + 4, hi);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) { v[g][e] += lo[e]; v[g][4 + e] += hi[e]; }
+            }
+        }
+    }
+    float av[kGroups][8];
+    float dot = 0.f;
+#pragma unroll
+    for (int g = 0; g < kGroups; ++g) {
+        const int d = (lane + 32 * g) * 8;
+        if (d < dim) {
+            float bv[8];
+            load_vec<T, 8>(ap + d, av[g]);
+            load_vec<T, 8>(bp + d, bv);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                av[g][e] *= r;
+                v[g][e] = v[g][e] * unscale - lab * bv[e];
+                dot = fmaf(av[g][e], v[g][e], dot);
+            }
+        }
+    }
+    dot = warp_sum(dot);
+#pragma unroll
+    for (int g = 0; g < kGroups; ++g) {
+        const int d = (lane + 32 * g) * 8;
+        if (d < dim) {
+            float o[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o[e] = r * (v[g][e] - av[g][e] * dot);
+            store_vec<G, 8>(gp + d, o);
+        }
+    }
+}
+
 template <typename T, typename G>
 __global__ void __launch_bounds__(256) clip_grad_finish_kernel(const float* __restrict__ acc_parts, int n_split,
                                                                const T* __restrict__ a, const float* __restrict__ a_inv,
@@ -259,9 +331,27 @@ int dcb_clip_grad_finish(const float* acc_parts, int n_split, const void* stu_a,
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const unsigned grid = (unsigned)((rows + 7) / 8);
     const float inv_b = 1.0f / (float)global_batch;
+    const bool aligned = ((reinterpret_cast<uintptr_t>(acc_parts) | reinterpret_cast<uintptr_t>(stu_a) |
+                           reinterpret_cast<uintptr_t>(stu_b) | reinterpret_cast<uintptr_t>(grad_a)) % 16) == 0;
     return dispatch_in_grad(in_dtype, grad_dtype, [&](auto tt, auto gg) -> int {
         using T = decltype(tt);
         using G = decltype(gg);
+        if constexpr (sizeof(T) == 2) {
+            if (aligned && dim % 8 == 0 && dim <= 1024) {
+                const int groups = (int)((dim / 8 + 31) / 32);
+#define DCB_FINISH_VEC(K)                                                                                                      \
+    clip_grad_finish_vec_kernel<T, G, K><<<grid, 256, 0, st>>>(acc_parts, n_split, static_cast<const T*>(stu_a), stu_a_inv,   \
+                                                              static_cast<const T*>(stu_b), stu_b_inv, rows, cols, (int)dim,  \
+                                                              row_offset, inv_b, upstream, gmax_row, gmax_col, static_cast<G*>(grad_a))
+                if (groups == 1) DCB_FINISH_VEC(1);
+                else if (groups == 2) DCB_FINISH_VEC(2);
+                else if (groups == 3) DCB_FINISH_VEC(3);
+                else DCB_FINISH_VEC(4);
+#undef DCB_FINISH_VEC
+                DCB_CUDA_OK(cudaGetLastError());
+                return 0;
+            }
+        }
         clip_grad_finish_kernel<T, G><<<grid, 256, 0, st>>>(acc_parts, n_split, static_cast<const T*>(stu_a), stu_a_inv,
                                                            static_cast<const T*>(stu_b), stu_b_inv, rows, cols, (int)dim,
                                                            row_offset, inv_b, upstream, gmax_row, gmax_col, static_cast<G*>(grad_a));
