@@ -102,8 +102,8 @@ def load():
     return _lib
 
 
-# kernels launched per C-ABI call (bench.py reports the sum as "gpu_launches"); dcb_row_inv_norm launches one per matrix
-_LAUNCHES_PER_CALL = {"dcb_clip_row_stats": 3}
+# kernels launched per C-ABI call (bench.py reports the sum as "gpu_launches")
+_LAUNCHES_PER_CALL = {"dcb_clip_row_stats": 3, "dcb_clip_rank_counts": 2}
 LAUNCHES = 0
 
 
@@ -111,7 +111,7 @@ def call(name: str, *args) -> None:
     global LAUNCHES
     lib = load()
     rc = getattr(lib, name)(*args)
-    LAUNCHES += int(args[0]) if name == "dcb_row_inv_norm" else _LAUNCHES_PER_CALL.get(name, 1)
+    LAUNCHES += _LAUNCHES_PER_CALL.get(name, 1)
     if rc != 0:
         raise DistillClipB200Error(f"{name} failed: {lib.dcb_last_error().decode(errors='replace')}")
 

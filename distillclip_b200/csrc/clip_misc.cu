@@ -7,20 +7,37 @@ namespace dcb {
 // ---------------------------------------------------------------------------------------------
 // r_i = 1 / ||x_i||_2   (reference model/component/clip_model.py:37-38 divides by x.norm(dim=1))
 // ---------------------------------------------------------------------------------------------
+struct InvNormParams {
+    const void* x[8];
+    float* out[8];
+    long long rows[8];
+};
+
+// one launch for up to 8 matrices (blockIdx.y selects the matrix); 16-byte loads when the rows allow it
 template <typename T>
-__global__ void __launch_bounds__(256) inv_norm_kernel(const T* __restrict__ x, float* __restrict__ out, long long rows,
-                                                       int dim) {
+__global__ void __launch_bounds__(256) inv_norm_kernel(const __grid_constant__ InvNormParams p, int dim, int vec_ok) {
+    const long long rows = p.rows[blockIdx.y];
     const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= rows) return;
     const int lane = threadIdx.x & 31;
-    const T* __restrict__ p = x + row * dim;
+    const T* __restrict__ x = static_cast<const T*>(p.x[blockIdx.y]) + row * dim;
     float acc = 0.f;
-    for (int d = lane; d < dim; d += 32) {
-        const float v = Elem<T>::to_f(p[d]);
-        acc = fmaf(v, v, acc);
+    constexpr int kPer = 16 / (int)sizeof(T);
+    if (vec_ok) {
+        for (int d = lane * kPer; d < dim; d += 32 * kPer) {
+            float v[kPer];
+            load_vec<T, kPer>(x + d, v);
+#pragma unroll
+            for (int e = 0; e < kPer; ++e) acc = fmaf(v[e], v[e], acc);
+        }
+    } else {
+        for (int d = lane; d < dim; d += 32) {
+            const float v = Elem<T>::to_f(x[d]);
+            acc = fmaf(v, v, acc);
+        }
     }
     acc = warp_sum(acc);
-    if (lane == 0) out[row] = 1.0f / sqrtf(acc);
+    if (lane == 0) p.out[blockIdx.y][row] = 1.0f / sqrtf(acc);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -267,15 +284,23 @@ int dcb_row_inv_norm(int n_mats, const void* const* mats, float* const* inv_norm
     using namespace dcb;
     DCB_REQUIRE(n_mats >= 1 && n_mats <= 8 && dim >= 1, "bad arguments");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    InvNormParams p{};
+    long long max_rows = 0;
+    bool vec_ok = (dim * dtype_size(dtype)) % 16 == 0;
     for (int k = 0; k < n_mats; ++k) {
         DCB_REQUIRE(mats[k] && inv_norm[k] && rows[k] >= 1, "matrix %d: bad arguments", k);
-        const unsigned grid = (unsigned)((rows[k] + 7) / 8);
-        switch (dtype) {
-            case DCB_BF16: inv_norm_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(mats[k]), inv_norm[k], rows[k], (int)dim); break;
-            case DCB_F16: inv_norm_kernel<__half><<<grid, 256, 0, st>>>(static_cast<const __half*>(mats[k]), inv_norm[k], rows[k], (int)dim); break;
-            case DCB_F32: inv_norm_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(mats[k]), inv_norm[k], rows[k], (int)dim); break;
-            default: return fail("unknown dtype %d", dtype);
-        }
+        p.x[k] = mats[k];
+        p.out[k] = inv_norm[k];
+        p.rows[k] = rows[k];
+        max_rows = rows[k] > max_rows ? rows[k] : max_rows;
+        vec_ok = vec_ok && reinterpret_cast<uintptr_t>(mats[k]) % 16 == 0;
+    }
+    const dim3 grid((unsigned)((max_rows + 7) / 8), (unsigned)n_mats);
+    switch (dtype) {
+        case DCB_BF16: inv_norm_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(p, (int)dim, vec_ok ? 1 : 0); break;
+        case DCB_F16: inv_norm_kernel<__half><<<grid, 256, 0, st>>>(p, (int)dim, vec_ok ? 1 : 0); break;
+        case DCB_F32: inv_norm_kernel<float><<<grid, 256, 0, st>>>(p, (int)dim, vec_ok ? 1 : 0); break;
+        default: return fail("unknown dtype %d", dtype);
     }
     DCB_CUDA_OK(cudaGetLastError());
     return 0;
