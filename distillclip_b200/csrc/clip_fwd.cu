@@ -387,23 +387,41 @@ __device__ __forceinline__ double clip_row_kl(double q, double zt, double w, dou
 // stats[k][r] = sum over splits (fixed order -> deterministic), stats[4][r] = S_rr, and the row's loss terms in double
 // (double precision; slot 1 of the statistics is Q, not Zs):
 //   rowloss[0][r] = CE_r = 1 + log A_r - S_rr       rowloss[1][r] = KL_r / T^2 = clip_row_kl(Q_r, Zt_r, W_r)
+// Four threads per row (one per statistic, 4 loads in flight each): the kernel is pure latency at B = 4096.
 __global__ void __launch_bounds__(128) clip_combine_kernel(const float* __restrict__ ws, const float* __restrict__ diag,
                                                            float* __restrict__ stats, double* __restrict__ rowloss,
                                                            int rows, int n_split, float temperature, int has_teacher) {
-    const int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= rows) return;
-    float v[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        double acc = 0.0;
-        for (int s = 0; s < n_split; ++s) acc += (double)ws[((size_t)s * 4 + k) * rows + r];
-        v[k] = (float)acc;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = t >> 2, k = t & 3;
+    const bool ok = r < rows;
+    double acc = 0.0;
+    if (ok) {
+        const float* __restrict__ src = ws + (size_t)k * rows + r;
+        const size_t stride = (size_t)4 * rows;
+        int s = 0;
+        for (; s + 4 <= n_split; s += 4) {                      // fixed order, four independent loads at a time
+            const float a0 = src[(size_t)s * stride], a1 = src[(size_t)(s + 1) * stride];
+            const float a2 = src[(size_t)(s + 2) * stride], a3 = src[(size_t)(s + 3) * stride];
+            acc += (double)a0;
+            acc += (double)a1;
+            acc += (double)a2;
+            acc += (double)a3;
+        }
+        for (; s < n_split; ++s) acc += (double)src[(size_t)s * stride];
         stats[(size_t)k * rows + r] = (float)acc;
     }
-    const float dg = diag[r];
-    stats[(size_t)4 * rows + r] = dg;
-    rowloss[r] = 1.0 + log((double)v[0]) - (double)dg;
-    rowloss[(size_t)rows + r] = has_teacher ? clip_row_kl((double)v[1], (double)v[2], (double)v[3], (double)temperature) : 0.0;
+    const float mine = (float)acc;                              // consumers see the fp32 statistics; so does the loss
+    const unsigned quad = threadIdx.x & 28u;
+    const float v0 = __shfl_sync(0xffffffffu, mine, quad), v1 = __shfl_sync(0xffffffffu, mine, quad + 1);
+    const float v2 = __shfl_sync(0xffffffffu, mine, quad + 2), v3 = __shfl_sync(0xffffffffu, mine, quad + 3);
+    if (!ok) return;
+    if (k == 0) {
+        const float dg = diag[r];
+        stats[(size_t)4 * rows + r] = dg;
+        rowloss[r] = 1.0 + log((double)v0) - (double)dg;
+    } else if (k == 1) {
+        rowloss[(size_t)rows + r] = has_teacher ? clip_row_kl((double)v1, (double)v2, (double)v3, (double)temperature) : 0.0;
+    }
 }
 
 // col_stats[k][j] = sum over row blocks of col_part[rb][k][j]  (double accumulation, fixed order)
@@ -537,7 +555,7 @@ static int clip_row_stats_impl(const void* stu_a, const void* stu_b, const void*
     else DCB_LAUNCH_FWD(false, false)
 #undef DCB_LAUNCH_FWD
     DCB_CUDA_OK(cudaGetLastError());
-    clip_combine_kernel<<<(unsigned)((rows_local + 127) / 128), 128, 0, st>>>(p.ws, p.diag, stats, rowloss, (int)rows_local,
+    clip_combine_kernel<<<(unsigned)((rows_local * 4 + 127) / 128), 128, 0, st>>>(p.ws, p.diag, stats, rowloss, (int)rows_local,
                                                                                fwd::kSubs * p.n_split, temperature, teacher ? 1 : 0);
     DCB_CUDA_OK(cudaGetLastError());
     if (col_stats) {

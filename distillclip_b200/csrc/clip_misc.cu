@@ -75,7 +75,17 @@ __global__ void __launch_bounds__(1024) clip_loss_kernel(const double* __restric
         const double* rl = dir == 0 ? rl_i2t : rl_t2i;
         const int rows = dir == 0 ? rows_i2t : rows_t2i;
         double ce = 0.0, kl = 0.0;
-        for (int i = threadIdx.x; i < rows; i += blockDim.x) {
+        int i = threadIdx.x;
+        for (; i + 3 * (int)blockDim.x < rows; i += 4 * blockDim.x) {       // four independent loads in flight (fixed order)
+            const double c0 = rl[i], c1 = rl[i + blockDim.x], c2 = rl[i + 2 * blockDim.x], c3 = rl[i + 3 * blockDim.x];
+            ce += c0; ce += c1; ce += c2; ce += c3;
+            if (has_teacher) {
+                const double* k = rl + (size_t)rows + i;
+                const double k0 = k[0], k1 = k[blockDim.x], k2 = k[2 * blockDim.x], k3 = k[3 * blockDim.x];
+                kl += k0; kl += k1; kl += k2; kl += k3;
+            }
+        }
+        for (; i < rows; i += blockDim.x) {
             ce += rl[i];
             if (has_teacher) kl += rl[(size_t)rows + i];
         }
