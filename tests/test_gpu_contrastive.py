@@ -152,6 +152,19 @@ def test_fused_contrastive_random_vs_oracle(cuda_device, bwd_kernel, b, d, T, dt
     assert rel_l2(gt.cpu().numpy(), ref["d_txt"]) <= GRAD_RTOL
 
 
+@pytest.mark.parametrize("T", [0.05, 0.3, 16.0])
+def test_fused_contrastive_temperature_range(cuda_device, T):
+    """Sharp (T = 0.05: exp((S-1)/T) spans 17 decades, just above MIN_FUSED_TEMPERATURE) and flat (T = 16: the row KL is a
+    ~1e-6 second-order quantity) softmaxes against the f64 oracle."""
+    si, st, ti, tt = synth(256, 128, 77)
+    ref = cf.contrastive_from_embeddings(*[x.float().numpy() for x in (si, st, ti, tt)], T, w_hard=0.5, w_soft=0.5)
+    out, gi, gt = _fused(si.cuda(), st.cuda(), ti.cuda(), tt.cuda(), T, 0.5, 0.5, torch.float32)
+    assert float(out[0]) == pytest.approx(ref["hard"], rel=LOSS_RTOL)
+    assert float(out[1]) == pytest.approx(ref["soft"], rel=LOSS_RTOL)
+    assert rel_l2(gi.cpu().numpy(), ref["d_img"]) <= GRAD_RTOL
+    assert rel_l2(gt.cpu().numpy(), ref["d_txt"]) <= GRAD_RTOL
+
+
 def test_hard_label_only_autograd(cuda_device, bwd_kernel):
     from distillclip_b200.contrastive import clip_contrastive
     si, st, _, _ = synth(320, 256, 9)
