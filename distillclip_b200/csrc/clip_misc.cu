@@ -61,6 +61,35 @@ __global__ void __launch_bounds__(256) transpose_norm_f16_kernel(const T* __rest
     }
 }
 
+// 64 x 64 tiles, two elements per access (dim even): a warp reads / writes 128 contiguous bytes per instruction
+template <typename T>
+__global__ void __launch_bounds__(256) transpose_norm_f16_x2_kernel(const T* __restrict__ in, const float* __restrict__ inv_norm,
+                                                                    __half* __restrict__ out, int rows, int dim, long long pitch) {
+    __shared__ float tile[64][65];
+    const int j0 = blockIdx.x * 64, d0 = blockIdx.y * 64;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;      // 32 x 8
+    for (int k = ty; k < 64; k += 8) {
+        const int j = j0 + k, d = d0 + 2 * tx;
+        float v[2] = {0.f, 0.f};
+        if (j < rows && d < dim) {                               // dim even: d + 1 < dim as well
+            load_vec<T, 2>(in + (long long)j * dim + d, v);
+            const float r = inv_norm[j];
+            v[0] *= r;
+            v[1] *= r;
+        }
+        tile[k][2 * tx] = v[0];
+        tile[k][2 * tx + 1] = v[1];
+    }
+    __syncthreads();
+    for (int k = ty; k < 64; k += 8) {
+        const int d = d0 + k, j = j0 + 2 * tx;
+        if (d < dim && j < pitch) {                              // pitch even: j + 1 < pitch as well; columns >= rows are zero
+            const float o[2] = {j < rows ? tile[2 * tx][k] : 0.f, j + 1 < rows ? tile[2 * tx + 1][k] : 0.f};
+            store_vec<__half, 2>(out + (long long)d * pitch + j, o);
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Loss values of both directions from the per-row losses written by the forward kernel's combine step
 // (rowloss[0][i] = CE_i = 1 + log A_i - S_ii, rowloss[1][i] = KL_i / T^2 = W_i/(T Zt_i) + log(Zs_i/Zt_i), double):
@@ -320,9 +349,19 @@ int dcb_transpose_norm_f16(const void* in, const float* inv_norm, void* out, int
                            int64_t out_pitch_elems, int dtype, void* stream) {
     using namespace dcb;
     DCB_REQUIRE(in && inv_norm && out && rows >= 1 && dim >= 1 && out_pitch_elems >= rows, "bad arguments");
-    dim3 grid((unsigned)((out_pitch_elems + 31) / 32), (unsigned)((dim + 31) / 32));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     __half* o = static_cast<__half*>(out);
+    if (dim % 2 == 0 && out_pitch_elems % 2 == 0 && reinterpret_cast<uintptr_t>(in) % 4 == 0 && reinterpret_cast<uintptr_t>(out) % 4 == 0) {
+        dim3 grid2((unsigned)((out_pitch_elems + 63) / 64), (unsigned)((dim + 63) / 64));
+        switch (dtype) {
+            case DCB_BF16: transpose_norm_f16_x2_kernel<__nv_bfloat16><<<grid2, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(in), inv_norm, o, (int)rows, (int)dim, out_pitch_elems); break;
+            case DCB_F16: transpose_norm_f16_x2_kernel<__half><<<grid2, 256, 0, st>>>(static_cast<const __half*>(in), inv_norm, o, (int)rows, (int)dim, out_pitch_elems); break;
+            default: return fail("transpose: bf16 or fp16 input only");
+        }
+        DCB_CUDA_OK(cudaGetLastError());
+        return 0;
+    }
+    dim3 grid((unsigned)((out_pitch_elems + 31) / 32), (unsigned)((dim + 31) / 32));
     switch (dtype) {
         case DCB_BF16: transpose_norm_f16_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(in), inv_norm, o, (int)rows, (int)dim, out_pitch_elems); break;
         case DCB_F16: transpose_norm_f16_kernel<__half><<<grid, 256, 0, st>>>(static_cast<const __half*>(in), inv_norm, o, (int)rows, (int)dim, out_pitch_elems); break;
