@@ -4,19 +4,28 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME] [--no-extras]
 
 A "step" is one fwd+bwd pass of the loss stack over one batch of synthetic input (seed 2022).
-Primary workload (default): BASELINE configs[1], the image-encoder stage -- attention-map KL + hidden MSE over L=4
-layer pairs, batch 256, 50 tokens, 12 heads, width 768, bf16.  It does not shard (per-sample sums, no exchange step),
-so with --gpus N every rank runs an independent replica ("scaling": "weak").  The path that does shard -- the fused
-InfoNCE + logit-KL kernels, rows split over ranks with an embedding all-gather -- is timed in the same run and reported
-under "contrastive" (BASELINE configs[3] and [4]), so every line carries both rooflines.
+
+Headline workload (default, every N): BASELINE configs[4], the scale sweep -- fused InfoNCE + teacher/student logit KL,
+global batch 32768, dim 768, bf16, logits never materialised.  It is the path that shards: with
+--gpus N every rank owns B/N rows of the four embedding matrices, the text rows are exchanged over NVLink and each rank
+computes its row slice of the global logits and the gradients of its own rows -- "scaling": "strong" (fixed global batch).
+The streaming stages (configs[1] image stage, configs[2] text stage: attention-map KL + hidden / embedding MSE) have no
+exchange step; they run as independent replicas and are reported under "stages" with their own HBM rooflines, and the
+L-CLIP stage (configs[3], B=4096, D=512) under "lclip".
+
+Every workload carries a "parity" block measured in this run, before timing: losses against the float64 oracle (1e-4),
+fp32 gradients of sampled rows (1e-3), and the bf16 gradients the public API hands back (storage rounding, 4e-3); at
+N > 1 for both backward routes (peer-memory scatter fused into the G^T GEMM, and the NCCL reduce-scatter).
 
 Timing: CUDA events on the launching stream per step, summed over exactly K steps after W warm-ups, barrier +
 synchronize on both sides, max over ranks.  Inputs larger than L2 are simply re-read; for working sets below 126 MB
-the L2 is flushed (256 MiB memset) before every timed step, outside the event pair.
+the L2 is flushed by READING a 256 MiB buffer before every timed step, outside the event pair.
 """
 from __future__ import annotations
 
 import argparse
+import contextlib
+import io
 import json
 import os
 import statistics
@@ -44,6 +53,8 @@ WORKLOADS = {
                   desc="BASELINE configs[4]: InfoNCE + logit KL, B=32768, D=768, bf16, logits never materialised, rows sharded over ranks"),
 }
 L2_BYTES = 126 * 1024 * 1024
+LOSS_RTOL, GRAD_RTOL, GRAD_STORAGE_RTOL = 1e-4, 1e-3, 4e-3
+PROFILE_ROUND = "r02"
 
 
 def ncu_traffic(csv_name, kernel_substr):
@@ -61,6 +72,14 @@ def ncu_traffic(csv_name, kernel_substr):
         return int(sum(vals) / len(vals)) if vals else None
     except (ValueError, KeyError, IndexError):
         return None
+
+
+def first_traffic(names, kernel_substr):
+    for n in names:
+        v = ncu_traffic(n, kernel_substr)
+        if v is not None:
+            return v
+    return None
 
 
 def peaks():
@@ -148,20 +167,36 @@ def tower_elements(cfg):
     return {k: el[k] for k in cfg["names"]}
 
 
-def make_clip(cfg, device, gen, rows, offset):
-    """Rank-local rows [offset, offset+rows) of one global seeded batch (every rank draws the same global tensors)."""
+def make_clip_global(cfg, device, gen):
+    """The four GLOBAL seeded embedding matrices (every rank draws the same tensors; the oracle runs on these)."""
     b, d = cfg["batch"], cfg["dim"]
     ti = torch.randn(b, d, device=device, generator=gen)
     tt = ti * 0.6 + 0.8 * torch.randn(b, d, device=device, generator=gen)
     si = ti + 0.5 * torch.randn(b, d, device=device, generator=gen)
     st = tt + 0.5 * torch.randn(b, d, device=device, generator=gen)
+    return [x.to(torch.bfloat16).contiguous() for x in (si, st, ti, tt)]
+
+
+def make_clip(cfg, device, gen, rows, offset):
+    """Rank-local rows [offset, offset+rows) of the global seeded batch."""
     loc = slice(offset, offset + rows)
-    return [x[loc].to(torch.bfloat16).contiguous() for x in (si, st, ti, tt)]
+    return [x[loc].contiguous() for x in make_clip_global(cfg, device, gen)]
 
 
 # ------------------------------------------------------------------------------------------------
 # timing helpers
 # ------------------------------------------------------------------------------------------------
+class L2Flush:
+    """Evicts the L2 by READING a 256 MiB buffer (a write would leave 126 MB of dirty lines for the timed kernel to evict)."""
+
+    def __init__(self, device):
+        self.buf = torch.zeros(64 * 1024 * 1024, dtype=torch.int32, device=device)
+        self.sink = torch.zeros((), dtype=torch.int64, device=device)
+
+    def __call__(self):
+        torch.sum(self.buf, out=self.sink)
+
+
 class Timer:
     """Times exactly `steps` executions of `fn` with one CUDA-event pair per step (summed), after `warmup` untimed
     executions, barrier + synchronize on both sides, max over ranks.  With graph=True the step is captured once into
@@ -170,7 +205,7 @@ class Timer:
     step runs eagerly and `mode` says so."""
 
     def __init__(self, device, flush: bool):
-        self.flush_buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=device) if flush else None
+        self.flush = L2Flush(device) if flush else None
         self.mode = "eager"
 
     def _capture(self, fn):
@@ -203,8 +238,8 @@ class Timer:
         torch.cuda.synchronize()
         pairs = []
         for _ in range(steps):
-            if self.flush_buf is not None:
-                self.flush_buf.zero_()
+            if self.flush is not None:
+                self.flush()
             s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             s.record()
             run_step()
@@ -222,11 +257,11 @@ class Timer:
         return total_ms
 
 
-def time_kernel(fn, iters, device):
+def time_kernel(fn, iters, device, flush=None):
     """Average duration of the launch(es) in `fn`, measured on the launching stream with one event pair per launch.
-    `fn` is captured into a CUDA graph and replays alternate with a 256 MiB L2 flush, all enqueued ahead of the GPU,
-    so each pair brackets exactly one cold-L2 execution and no host time."""
-    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=device)
+    `fn` is captured into a CUDA graph and replays alternate with an L2 flush (a 256 MiB read), all enqueued ahead of the
+    GPU, so each pair brackets exactly one cold-L2 execution and no host time."""
+    flush = flush or L2Flush(device)
     fn()
     torch.cuda.synchronize()
     g = torch.cuda.CUDAGraph()
@@ -234,7 +269,7 @@ def time_kernel(fn, iters, device):
         fn()
     pairs = []
     for _ in range(iters + 2):
-        flush.zero_()
+        flush()
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
         g.replay()
@@ -245,17 +280,70 @@ def time_kernel(fn, iters, device):
     return sum(times) / len(times)
 
 
+def _rel(a, b):
+    a, b = a.double(), b.double()
+    den = float(b.norm())
+    return float((a - b).norm()) / den if den > 0 else float((a - b).norm())
+
+
+def _max_over_ranks(vals, dist):
+    if dist is None:
+        return vals
+    t = torch.tensor(vals, dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return [float(x) for x in t.tolist()]
+
+
 # ------------------------------------------------------------------------------------------------
-# our arm
+# streaming stages (image / text): parity, step, dominant kernel, e2e
 # ------------------------------------------------------------------------------------------------
-def bench_tower(cfg, name, args, device, dist, world, pk, with_cpu):
+def parity_tower(cfg, stu, tea, device):
+    """Our CUDA path against the reference's op sequence in float64 (oracle/torch_port.py on CUDA fp64 + autograd)."""
+    from oracle import torch_port as tp
+    from distillclip_b200 import ops
+    from distillclip_b200.model import LossCalculator, TextTransformerOutput, VisionTransformerOutput
+    names = cfg["names"]
+    s64 = {k: ([x.double().requires_grad_(True) for x in v] if isinstance(v, list) else v.double().requires_grad_(True)) for k, v in stu.items()}
+    t64 = {k: ([x.double() for x in v] if isinstance(v, list) else v.double()) for k, v in tea.items()}
+    percent = {n: 1 / len(names) for n in names}
+    ref_loss, ref_res = tp.one_tower(names, {n: 1 for n in names}, percent, None, s64, t64)
+    ref_loss.backward()
+    ref_grads = {k: ([x.grad for x in v] if isinstance(v, list) else [v.grad]) for k, v in s64.items()}
+    cls = VisionTransformerOutput if cfg["model_type"] == "image" else TextTransformerOutput
+    leaves = {k: ([x.clone().requires_grad_(True) for x in v] if isinstance(v, list) else v.clone().requires_grad_(True)) for k, v in stu.items()}
+    with contextlib.redirect_stdout(io.StringIO()):
+        calc = LossCalculator(names)
+    loss, res = calc(cls(**leaves), cls(**tea), cfg["model_type"])
+    loss.backward()
+    loss_err = {"total": abs(float(loss) - float(ref_loss)) / abs(float(ref_loss))}
+    for k in names:
+        loss_err[k] = abs(float(res[k]) - float(ref_res[k])) / abs(float(ref_res[k]))
+    g_api = max(_rel(g.grad, w) for k, v in leaves.items() for g, w in zip(v if isinstance(v, list) else [v], ref_grads[k]))
+    fields = {"hidden_rep_mse": (ops.KIND_MSE, "representations"), "attention_probs_kl": (ops.KIND_ATTN_KL, "attention_probs"),
+              "embedding_mse": (ops.KIND_MSE, "embedding")}
+    entries = []
+    for nm in names:
+        kind, field = fields[nm]
+        sv, tv = stu[field], tea[field]
+        sv, tv = (sv if isinstance(sv, list) else [sv]), (tv if isinstance(tv, list) else [tv])
+        entries.append((kind, len(sv), sv, tv, [True] * len(sv), percent[nm]))
+    _, grads32, _ = ops.launch_tower(entries, [1.0] * len(names), [percent[n] for n in names], grad_dtype=torch.float32)
+    g32 = max(_rel(g, w) for nm, gl in zip(names, grads32) for g, w in zip(gl, ref_grads[fields[nm][1]]))
+    torch.cuda.synchronize()
+    ok = max(loss_err.values()) <= LOSS_RTOL and g32 <= GRAD_RTOL and g_api <= GRAD_STORAGE_RTOL
+    return {"ok": bool(ok), "loss_rel_err": {k: float(f"{v:.3e}") for k, v in loss_err.items()},
+            "grad_rel_l2_fp32_out": float(f"{g32:.3e}"), "grad_rel_l2_api_bf16": float(f"{g_api:.3e}"),
+            "tol": {"loss": LOSS_RTOL, "grad_fp32": GRAD_RTOL, "grad_bf16_storage": GRAD_STORAGE_RTOL},
+            "checker": "oracle/torch_port.py (the reference's op sequence) in float64 on the same inputs, full size"}
+
+
+def bench_tower(cfg, name, args, device, dist, world, pk):
     from distillclip_b200 import _lib, ops
     from distillclip_b200.model import LossCalculator, TextTransformerOutput, VisionTransformerOutput
     gen = torch.Generator(device=device).manual_seed(2022)
     stu, tea = make_tower(cfg, device, gen), make_tower(cfg, device, gen)
+    parity = parity_tower(cfg, stu, tea, device)
     cls = VisionTransformerOutput if cfg["model_type"] == "image" else TextTransformerOutput
-    import contextlib
-    import io
     with contextlib.redirect_stdout(io.StringIO()):
         calc = LossCalculator(cfg["names"]).to(device)
 
@@ -318,14 +406,16 @@ def bench_tower(cfg, name, args, device, dist, world, pk, with_cpu):
     kernels["attn_kl_kernel"] = (lambda: ops.launch_attn_kl(s_a, t_a, len(s_a), 1.0, [True] * len(s_a), out=(p_a, g_a)),
                                  6 * elements["attention_probs_kl"])
     kres = {}
+    flush = L2Flush(device)
     for kname, (fn, nbytes) in kernels.items():
-        k_ms = time_kernel(fn, 20, device)
+        k_ms = time_kernel(fn, 20, device, flush)
         kres[kname] = {"ms": round(k_ms, 5), "algorithmic_bytes": nbytes, "gbs": round(nbytes / k_ms / 1e6, 1),
                        "frac": round(nbytes / k_ms / 1e6 / pk["hbm"], 4)}
     dom = "tower_stream_kernel"
     roofline = {"bound": "hbm", "kernel": dom, "achieved": kres[dom]["gbs"], "peak": pk["hbm"], "unit": "GB/s",
                 "frac": kres[dom]["frac"],
-                "traffic": ncu_traffic("r01_ncu_full_tower_stream.csv", "tower_stream") if name == "image_stage" else None,
+                "traffic": first_traffic([f"{PROFILE_ROUND}_ncu_full_tower_{name}.csv", "r01_ncu_full_tower_stream.csv" if name == "image_stage" else ""],
+                                         "tower_stream"),
                 "traffic_note": "dram bytes read + written inside one isolated launch (ncu --set full, profiles/); part of the "
                                 "gradient writes is still dirty in L2 when the kernel exits",
                 "peak_source": pk["source"],
@@ -348,25 +438,26 @@ def bench_tower(cfg, name, args, device, dist, world, pk, with_cpu):
         loss.backward()
         loss_host.copy_(loss.detach(), non_blocking=True)
         torch.cuda.current_stream().synchronize()
-    e2e_ms = Timer(device, flush=False).run(e2e_step, max(3, args.steps // 4), 2, dist, graph=False) / max(3, args.steps // 4)
+    n_e2e = max(3, args.steps // 4)
+    e2e_ms = Timer(device, flush=False).run(e2e_step, n_e2e, 2, dist, graph=False) / n_e2e
     e2e = {"value": round(world * cfg["batch"] / (e2e_ms * 1e-3), 1), "unit": "samples/s", "ms_per_step": round(e2e_ms, 4),
            "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4}
-
-    cpu = cpu_tower(cfg, stu, tea, budget_s=20.0) if with_cpu else None
-    return dict(value=value, ms=ms, launches=launches, roofline=roofline, e2e=e2e, cpu=cpu,
-                flush=timer.flush_buf is not None, algo_bytes=algo_bytes, mode=timer.mode)
+    return dict(value=value, ms=ms, launches=launches, roofline=roofline, e2e=e2e, parity=parity,
+                flush=timer.flush is not None, algo_bytes=algo_bytes, mode=timer.mode)
 
 
-def cpu_tower(cfg, stu, tea, budget_s):
+def cpu_tower(cfg, budget_s):
     """The oracle's torch port of the reference path on the host cores, fp32 copies, bounded time."""
     from oracle import torch_port as tp
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
     names = cfg["names"]
+    gen = torch.Generator().manual_seed(2022)
+    stu, tea = make_tower(cfg, "cpu", gen), make_tower(cfg, "cpu", gen)
 
     def to_cpu(d, grad):
-        return {k: ([x.float().cpu().requires_grad_(grad) for x in v] if isinstance(v, list)
-                    else v.float().cpu().requires_grad_(grad)) for k, v in d.items()}
+        return {k: ([x.float().requires_grad_(grad) for x in v] if isinstance(v, list)
+                    else v.float().requires_grad_(grad)) for k, v in d.items()}
     s, t = to_cpu(stu, True), to_cpu(tea, False)
     times, t_end = [], time.perf_counter() + budget_s
     while len(times) < 5 and (time.perf_counter() < t_end or not times):
@@ -404,16 +495,109 @@ def cpu_clip(cfg, budget_s):
             "sample": f"{len(times)} fwd+bwd steps on a {b}-row batch (best of), oracle/torch_port.py fp32, {threads} threads"}
 
 
-def bench_clip(cfg, args, device, dist, rank, world, pk, steps, warmup):
+# ------------------------------------------------------------------------------------------------
+# contrastive path (sweep / lclip): parity, step, per-kernel rooflines, e2e
+# ------------------------------------------------------------------------------------------------
+def parity_clip(cfg, glob, rank, world, dist, group, device):
+    """Losses of the GLOBAL batch and gradients of sampled local rows against the chunked float64 oracle
+    (oracle/chunked_fp64.py, literal formulas of the reference, run here on the GPU in torch float64 on the full global
+    batch), for every backward route available at this world size, plus the bf16 gradients of the public call."""
+    from oracle import chunked_fp64 as ck
+    from distillclip_b200 import contrastive as ct
+    b, T = cfg["batch"], cfg["temperature"]
+    rows = b // world
+    off = rank * rows
+    w_hard, w_soft = 0.5, 0.5
+    gen = torch.Generator().manual_seed(100 + rank)
+    n_samp = min(rows, 256)
+    loc_i = sorted(torch.randperm(rows, generator=gen)[:n_samp].tolist())
+    loc_t = sorted(torch.randperm(rows, generator=gen)[:n_samp].tolist())
+    ref = ck.contrastive_chunked(*glob, temperature=T, weights={"hard": w_hard, "soft": w_soft},
+                                 sample_img=[off + i for i in loc_i], sample_txt=[off + i for i in loc_t], chunk=2048)
+    si, st, ti, tt = [x[off:off + rows].contiguous() for x in glob]
+    eng = ct.CudaEngine()
+    up = torch.tensor([w_hard, w_soft], dtype=torch.float32, device=device)
+    routes = {}
+    route_list = [("fused", None)] if world == 1 else [("peer_scatter", True), ("nccl_reduce_scatter", False)]
+    old = ct.PeerScatter.enabled
+    for rname, peer in route_list:
+        if peer is not None:
+            ct.PeerScatter.enabled = peer
+        out, saved = ct.contrastive_forward(eng, si, st, ti, tt, T, group)
+        gi, gt = ct.contrastive_backward(eng, saved, up, grad_dtype=torch.float32)
+        torch.cuda.synchronize()
+        errs = [abs(float(out[0]) - ref["hard"]) / abs(ref["hard"]), abs(float(out[1]) - ref["soft"]) / abs(ref["soft"]),
+                _rel(gi[loc_i], ref["d_img"]), _rel(gt[loc_t], ref["d_txt"])]
+        errs = _max_over_ranks(errs, dist)
+        routes[rname] = {"hard_rel_err": float(f"{errs[0]:.3e}"), "soft_rel_err": float(f"{errs[1]:.3e}"),
+                         "grad_img_rel_l2": float(f"{errs[2]:.3e}"), "grad_txt_rel_l2": float(f"{errs[3]:.3e}"),
+                         "ok": bool(max(errs[:2]) <= LOSS_RTOL and max(errs[2:]) <= GRAD_RTOL)}
+        if peer and world > 1 and not ct.PeerScatter._cache:
+            routes[rname]["note"] = "symmetric memory unavailable: this route fell back to the NCCL reduce-scatter"
+    ct.PeerScatter.enabled = old
+    # the public call (bf16 gradients as autograd returns them)
+    a, c_ = si.clone().requires_grad_(True), st.clone().requires_grad_(True)
+    res = ct.clip_contrastive(a, c_, ti, tt, T, want_hard=True, want_soft=True, group=group)
+    (w_hard * res["hard_label"] + w_soft * res["soft_label"]).backward()
+    torch.cuda.synchronize()
+    api = _max_over_ranks([_rel(a.grad[loc_i], ref["d_img"]), _rel(c_.grad[loc_t], ref["d_txt"])], dist)
+    ok = all(r["ok"] for r in routes.values()) and max(api) <= GRAD_STORAGE_RTOL
+    return {"ok": bool(ok), "routes": routes, "grad_rel_l2_api_bf16": float(f"{max(api):.3e}"),
+            "sampled_rows_per_side_per_rank": n_samp, "oracle": {"hard": ref["hard"], "soft": ref["soft"]},
+            "tol": {"loss": LOSS_RTOL, "grad_fp32": GRAD_RTOL, "grad_bf16_storage": GRAD_STORAGE_RTOL},
+            "checker": "oracle/chunked_fp64.py: literal reference formulas in float64 on the full global batch (max over ranks)"}
+
+
+def clip_kernel_times(cfg, glob, rank, world, device, pk):
+    """The three tcgen05 kernels of one step at this rank's shapes, each timed alone (cold L2, CUDA events on the launching
+    stream) through the raw C-ABI calls; flops = executed = credited (12 B^2 D / R per rank in total)."""
+    from distillclip_b200 import contrastive as ct
+    b, d, T = cfg["batch"], cfg["dim"], cfg["temperature"]
+    rows = b // world
+    off = rank * rows
+    si, st, ti, tt = glob
+    eng = ct.CudaEngine()
+    inv = eng.inv_norms([si, st, ti, tt])
+    loc = slice(off, off + rows)
+    a_s, a_t, a_si, a_ti = si[loc].contiguous(), ti[loc].contiguous(), inv[0][loc].contiguous(), inv[2][loc].contiguous()
+    stats, rl, col = eng.row_stats(a_s, st, a_t, tt, a_si, inv[1], a_ti, inv[3], off, T, with_cols=True)
+    st2, _ = eng.col_finish(col, stats[4].contiguous(), off, T, True)
+    up = torch.tensor([0.5, 0.5], dtype=torch.float32, device=device)
+    coef_r, gm_r = eng.coef(stats, b, T, True, up)
+    coef_c, gm_c = eng.coef(col, b, T, True, up)
+    bt = eng.transpose_norm(st, inv[1])
+    at = eng.transpose_norm(a_s, a_si)
+    out = {}
+    flush = L2Flush(device)
+    kernels = {"clip_fwd_kernel": (lambda: eng.row_stats(a_s, st, a_t, tt, a_si, inv[1], a_ti, inv[3], off, T, with_cols=True), 4.0)}
+    if eng.single_pass_supported(d):
+        g = eng.alloc_g(rows, b, device)
+        kernels["clip_bwd_pair_kernel"] = (lambda: eng.row_acc(a_s, st, a_t, tt, bt, a_si, inv[1], a_ti, inv[3], coef_r, coef_c,
+                                                               gm_r, gm_c, T, g_out=g), 6.0)
+        kernels["clip_gt_gemm_kernel"] = (lambda: eng.col_acc_from_g(g, at, rows, b, d), 2.0)
+    for kname, (fn, fl) in kernels.items():
+        ms = time_kernel(fn, 10, device, flush)
+        flops = fl * rows * b * d
+        tf = flops / (ms * 1e-3) / 1e12
+        out[kname] = {"ms": round(ms, 5), "flops": flops, "tflops": round(tf, 1), "frac": round(tf / pk["tf_burst"], 4),
+                      "frac_of_sustained": round(tf / pk["tf_sustained"], 4)}
+    return out
+
+
+def bench_clip(cfg, name, args, device, dist, rank, world, pk, steps, warmup):
     from distillclip_b200 import _lib
     from distillclip_b200.contrastive import clip_contrastive
     b, d, T = cfg["batch"], cfg["dim"], cfg["temperature"]
     rows = b // world
     gen = torch.Generator(device=device).manual_seed(2022)
-    si, st, ti, tt = make_clip(cfg, device, gen, rows, rank * rows)
+    glob = make_clip_global(cfg, device, gen)
+    group = dist.group.WORLD if (dist is not None and world > 1) else None
+    parity = parity_clip(cfg, glob, rank, world, dist, group, device)
+    kres = clip_kernel_times(cfg, glob, rank, world, device, pk)
+    si, st, ti, tt = [x[rank * rows:(rank + 1) * rows].contiguous() for x in glob]
+    del glob
     si.requires_grad_(True)
     st.requires_grad_(True)
-    group = dist.group.WORLD if (dist is not None and world > 1) else None
 
     def step():
         si.grad = None
@@ -425,7 +609,7 @@ def bench_clip(cfg, args, device, dist, rank, world, pk, steps, warmup):
     _lib.LAUNCHES = 0
     step()
     launches = _lib.LAUNCHES * steps
-    total_ms = timer.run(step, steps, warmup, dist, graph=True)      # NCCL collectives are graph-capturable; falls back to eager
+    total_ms = timer.run(step, steps, warmup, dist, graph=True)      # the collectives are graph-capturable; falls back to eager
     ms = total_ms / steps
     flops = 12.0 * b * b * d                                     # credited, whole job
     tf = flops / (ms * 1e-3) / 1e12
@@ -445,22 +629,22 @@ def bench_clip(cfg, args, device, dist, rank, world, pk, steps, warmup):
     n_e2e = max(3, steps // 4)
     e2e_ms = Timer(device, flush=False).run(e2e_step, n_e2e, 2, dist, graph=False) / n_e2e
     e2e = {"value": round(b / (e2e_ms * 1e-3), 1), "unit": "samples/s", "ms_per_step": round(e2e_ms, 4),
-           "h2d_bytes_per_step": sum(h.numel() * 2 for h in host), "d2h_bytes_per_step": 4}
+           "h2d_bytes_per_step": sum(h.numel() * 2 for h in host) * world, "d2h_bytes_per_step": 4 * world}
+    dom = max(kres, key=lambda k: kres[k]["ms"])
+    traffic = first_traffic([f"{PROFILE_ROUND}_ncu_full_clip_{name}.csv", f"r01_ncu_full_clip_{name}.csv"], dom) if world == 1 else None
+    roofline = {"bound": "tensor", "kernel": dom, "achieved": kres[dom]["tflops"], "peak": pk["tf_burst"], "unit": "TFLOP/s",
+                "frac": kres[dom]["frac"], "frac_of_sustained": kres[dom]["frac_of_sustained"],
+                "traffic": traffic,
+                "traffic_note": "dram bytes of one launch of the dominant kernel (ncu --set full, profiles/): it writes the fp16 gradient "
+                                "tiles G (2 B_local B bytes) for the G^T GEMM in addition to re-reading the embeddings from L2/HBM",
+                "peak_source": pk["source"], "kernels": kres,
+                "step": {"credited_flops": flops, "tflops_all_gpus": round(tf, 2), "peak_all_gpus": pk["tf_burst"] * world,
+                         "frac": round(tf / (pk["tf_burst"] * world), 4),
+                         "frac_of_sustained": round(tf / (pk["tf_sustained"] * world), 4)}}
     return {"workload": cfg["desc"], "global_batch": b, "dim": d, "temperature": T, "n_gpus": world,
             "value": round(b / (ms * 1e-3), 1), "unit": "samples/s", "ms_per_step": round(ms, 4), "steps": steps,
-            "scaling": "strong", "gpu_launches": launches, "l2_flush": timer.flush_buf is not None, "timing": timer.mode,
-            "e2e": e2e,
-            "roofline": {"bound": "tensor", "kernel": "clip_fwd_kernel + clip_bwd_pair_kernel + clip_gt_gemm_kernel (fused tcgen05)",
-                         "achieved": round(tf, 2), "peak": pk["tf_burst"] * world, "unit": "TFLOP/s",
-                         "frac": round(tf / (pk["tf_burst"] * world), 4),
-                         "frac_of_sustained": round(tf / (pk["tf_sustained"] * world), 4),
-                         "credited_flops": flops,
-                         "traffic": (sum(ncu_traffic("r01_ncu_full_clip_sweep.csv", k) or 0 for k in
-                                         ("clip_fwd_kernel", "clip_bwd_pair_kernel", "clip_gt_gemm_kernel")) or None)
-                         if (b, d, world) == (32768, 768, 1) else None,
-                         "traffic_note": "dram bytes of the three tcgen05 kernels of one step (ncu --set full, profiles/), 4.3 GB of "
-                                         "which are the fp16 gradient tiles written once and read once",
-                         "peak_source": pk["source"]}}
+            "scaling": "strong", "gpu_launches": launches, "l2_flush": timer.flush is not None, "timing": timer.mode,
+            "e2e": e2e, "roofline": roofline, "parity": parity}
 
 
 def run_ours(args):
@@ -481,49 +665,50 @@ def run_ours(args):
     pk = peaks()
     name = args.workload
     cfg = WORKLOADS[name]
-    line = {}
     sampler = ClockSampler(torch.cuda.current_device())
     sampler.__enter__()                                           # nvidia-smi -lms 100 for the whole measurement phase
-    if cfg["kind"] == "tower":
-        r = bench_tower(cfg, name, args, device, dist, world, pk, with_cpu=False)
-        line = {"metric": "distill-loss fwd+bwd samples/sec", "value": round(r["value"], 1), "unit": "samples/s",
-                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(r["ms"], 5),
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16 in, fp32 accumulate",
-                "data": "synthetic (seed 2022)",
-                "config": {"workload": cfg["desc"], "parallelism": f"{world} independent replica(s); this path has no exchange step",
-                           "l2": "flushed before every timed step" if r["flush"] else "inputs (student+teacher) larger than the 126 MB L2",
-                           "algorithmic_bytes_per_step": r["algo_bytes"], "timing": r["mode"]},
-                "roofline": r["roofline"], "e2e": r["e2e"], "gpu_launches": r["launches"]}
-        extras = []
+    base = {"metric": "distill-loss fwd+bwd samples/sec", "unit": "samples/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "higher_is_better": True, "vs_baseline": None, "dtype": "bf16 in, fp32 accumulate",
+            "data": "synthetic (seed 2022)"}
+    if cfg["kind"] == "clip":
+        if cfg["batch"] % (128 * world):
+            raise SystemExit(f"bench.py: global batch {cfg['batch']} must be a multiple of 128 x {world} ranks")
+        c = bench_clip(cfg, name, args, device, dist, rank, world, pk, args.steps, args.warmup)
+        line = dict(base, value=c["value"], ms_per_step=c["ms_per_step"], scaling="strong",
+                    config={"workload": cfg["desc"], "global_batch": cfg["batch"], "dim": cfg["dim"], "temperature": cfg["temperature"],
+                            "parallelism": f"rows sharded over {world} rank(s); text rows exchanged over NVLink, gradient reduce-scatter "
+                                           f"fused into the G^T GEMM (peer memory)" if world > 1 else "1 GPU",
+                            "l2": "flushed (by reading) before every timed step" if c["l2_flush"] else "inputs larger than the 126 MB L2",
+                            "timing": c["timing"]},
+                    roofline=c["roofline"], e2e=c["e2e"], gpu_launches=c["gpu_launches"], parity=c["parity"])
         if not args.no_extras:
-            for cname in ("lclip", "sweep"):
-                ccfg = WORKLOADS[cname]
-                if ccfg["batch"] % (128 * world):
-                    continue
-                steps = max(3, min(args.steps, 20 if cname == "lclip" else 5))
-                extras.append(bench_clip(ccfg, args, device, dist, rank, world, pk, steps, 3))
-            if world == 1:
-                t = bench_tower(WORKLOADS["text_stage"], "text_stage", args, device, dist, world, pk, with_cpu=False)
-                line["text_stage"] = {"workload": WORKLOADS["text_stage"]["desc"], "value": round(t["value"], 1),
-                                      "unit": "samples/s", "ms_per_step": round(t["ms"], 5), "roofline": t["roofline"],
-                                      "e2e": t["e2e"], "gpu_launches": t["launches"], "timing": t["mode"]}
-        line["contrastive"] = extras
-        sampler.__exit__(None, None, None)
-        line["clocks"] = sampler.summary()
-        if rank == 0 and world == 1 and not args.no_cpu:             # CPU leg after the GPU clocks have been sampled
-            gen = torch.Generator(device=device).manual_seed(2022)
-            line["cpu_baseline"] = cpu_tower(cfg, make_tower(cfg, device, gen), make_tower(cfg, device, gen), budget_s=20.0)
+            stages = {}
+            stage_names = ("image_stage", "text_stage") if world == 1 else ("image_stage",)
+            for sname in stage_names:
+                scfg = WORKLOADS[sname]
+                sub = argparse.Namespace(steps=max(3, min(args.steps, 20)), warmup=max(3, args.warmup))
+                t = bench_tower(scfg, sname, sub, device, dist, world, pk)
+                stages[sname] = {"workload": scfg["desc"], "value": round(t["value"], 1), "unit": "samples/s",
+                                 "ms_per_step": round(t["ms"], 5), "scaling": "weak",
+                                 "parallelism": f"{world} independent replica(s); this path has no exchange step",
+                                 "roofline": t["roofline"], "e2e": t["e2e"], "gpu_launches": t["launches"],
+                                 "timing": t["mode"], "parity": t["parity"]}
+            line["stages"] = stages
+            other = "lclip" if name == "sweep" else "sweep"
+            ocfg = WORKLOADS[other]
+            if ocfg["batch"] % (128 * world) == 0:
+                line[other] = bench_clip(ocfg, other, args, device, dist, rank, world, pk, max(3, min(args.steps, 20)), 3)
     else:
-        c = bench_clip(cfg, args, device, dist, rank, world, pk, args.steps, args.warmup)
-        sampler.__exit__(None, None, None)
-        line = {"metric": "distill-loss fwd+bwd samples/sec", "value": c["value"], "unit": "samples/s", "n_gpus": world,
-                "steps": args.steps, "warmup": args.warmup, "ms_per_step": c["ms_per_step"], "higher_is_better": True,
-                "scaling": "strong", "vs_baseline": None, "dtype": "bf16 in, fp32 accumulate", "data": "synthetic (seed 2022)",
-                "config": {"workload": cfg["desc"], "parallelism": f"rows sharded over {world} rank(s), embedding all-gather",
-                           "l2": "flushed before every timed step" if c["l2_flush"] else "inputs larger than L2"},
-                "roofline": c["roofline"], "e2e": c["e2e"], "gpu_launches": c["gpu_launches"], "clocks": sampler.summary()}
-        if rank == 0 and world == 1 and not args.no_cpu:
-            line["cpu_baseline"] = cpu_clip(cfg, budget_s=20.0)
+        r = bench_tower(cfg, name, args, device, dist, world, pk)
+        line = dict(base, value=round(r["value"], 1), ms_per_step=round(r["ms"], 5), scaling="weak",
+                    config={"workload": cfg["desc"], "parallelism": f"{world} independent replica(s); this path has no exchange step",
+                            "l2": "flushed (by reading) before every timed step" if r["flush"] else "inputs (student+teacher) larger than the 126 MB L2",
+                            "algorithmic_bytes_per_step": r["algo_bytes"], "timing": r["mode"]},
+                    roofline=r["roofline"], e2e=r["e2e"], gpu_launches=r["launches"], parity=r["parity"])
+    sampler.__exit__(None, None, None)
+    line["clocks"] = sampler.summary()
+    if rank == 0 and world == 1 and not args.no_cpu:                 # CPU leg after the GPU clocks have been sampled
+        line["cpu_baseline"] = cpu_clip(cfg, budget_s=20.0) if cfg["kind"] == "clip" else cpu_tower(cfg, budget_s=20.0)
     if rank == 0:
         print(json.dumps(line), flush=True)
     if dist is not None:
@@ -571,8 +756,11 @@ def run_reference(args):
             stu = {"visual": {"last_representation": si}, "text": {"last_representation": st}}
             tea = {"visual": {"last_representation": ti}, "text": {"last_representation": tt}}
             tp.stage_step_cpu(names, stu, tea, temperature=cfg["temperature"], two=True, threads=threads)
-        batch, sample = b, f"each step = full fwd+bwd on a {b}-row sub-batch (B x B fp32 logits do not fit the time budget at B={cfg['batch']})"
-    steps, warmup = max(1, min(args.steps, 5)), max(1, min(args.warmup, 1))
+        batch = b
+        sample = (f"each step = full fwd+bwd (normalise, matmul, HardLabel + SoftLabel both directions, autograd) on a {b}-row "
+                  f"sub-batch of the same seeded data: the reference materialises B x B fp32 logits (4.3 GB per matrix at "
+                  f"B={cfg['batch']}), and its cost per sample grows with B, so this sample FAVOURS the reference")
+    steps, warmup = max(1, args.steps), max(0, args.warmup)       # honoured as given (the sample keeps the run to ~a minute)
     for _ in range(warmup):
         step()
     t0 = time.perf_counter()
@@ -580,10 +768,13 @@ def run_reference(args):
         step()
     ms = (time.perf_counter() - t0) / steps * 1e3
     value = round(batch / (ms * 1e-3), 1)
+    config = {"workload": cfg["desc"]}
+    if cfg["kind"] == "clip":
+        config.update(global_batch=cfg["batch"], dim=cfg["dim"], temperature=cfg["temperature"])
     line = {"impl": "reference", "metric": "distill-loss fwd+bwd samples/sec", "value": value, "unit": "samples/s",
             "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": steps, "warmup": warmup, "ms_per_step": round(ms, 3),
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32 (bf16 inputs upcast)",
-            "data": "synthetic (seed 2022)", "config": {"workload": cfg["desc"]},
+            "higher_is_better": True, "scaling": "strong" if cfg["kind"] == "clip" else "weak", "vs_baseline": None,
+            "dtype": "fp32 (bf16 inputs upcast)", "data": "synthetic (seed 2022)", "config": config,
             "cpu_baseline": {"value": value, "unit": "samples/s", "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -592,11 +783,11 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
-    ap.add_argument("--workload", choices=sorted(WORKLOADS), default="image_stage")
-    ap.add_argument("--no-extras", action="store_true", help="skip the contrastive / text-stage sub-benchmarks")
+    ap.add_argument("--workload", choices=sorted(WORKLOADS), default="sweep")
+    ap.add_argument("--no-extras", action="store_true", help="skip the streaming-stage / L-CLIP sub-benchmarks")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

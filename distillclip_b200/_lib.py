@@ -27,8 +27,6 @@ SIGNATURES = {
     "dcb_finalize": [C.c_int, _vpp, _i32p, _f32p, _f32p, _vp, _vp],
     "dcb_tower_fwd_bwd": [C.c_int, _i32p, _i32p, _vpp, _vpp, _vpp, _i64p, _i64p, _i32p, _i32p, _i64p, _i32p, _f32p,
                           C.c_int, _f32p, _f32p, C.c_int, C.c_int, _vp, C.c_int, C.c_uint32, C.c_int, _vp, _vp, _vp],
-    "dcb_attn_tma_fwd_bwd": [C.c_int, C.c_int, _i32p, _vpp, _vpp, _vpp, _i64p, _i32p, _i32p, _i64p, _i32p, _f32p, C.c_int,
-                             _vp, C.c_int, _vp],
     "dcb_rescale_grads": [C.c_int, _vpp, _i64p, C.c_int, _vpp, _f32p, _vp],
     "dcb_row_inv_norm": [C.c_int, _vpp, _vpp, _i64p, C.c_int64, C.c_int, _vp],
     "dcb_transpose_norm_f16": [_vp, _vp, _vp, C.c_int64, C.c_int64, C.c_int64, C.c_int, _vp],
@@ -63,8 +61,6 @@ _SPECIAL = {
     "dcb_clip_pair_supported": (C.c_int, [C.c_int64]),
     "dcb_clip_gt_splits": (C.c_int, [C.c_int64, C.c_int64, C.c_int64]),
     "dcb_tower_grid": (C.c_int, []),
-    "dcb_attn_tma_grid": (C.c_int, []),
-    "dcb_attn_tma_supported": (C.c_int, [C.c_int, C.c_int64, C.c_int64, C.c_int64]),
     "dcb_version": (C.c_int, []),
     "dcb_compiled_arch": (C.c_int, []),
     "dcb_last_error": (C.c_char_p, []),

@@ -46,7 +46,7 @@ def _digest(paths) -> str:
     for p in sorted(paths, key=os.path.basename):
         with open(p, "rb") as f:
             h.update(os.path.basename(p).encode() + b"\0" + f.read())
-    h.update(" ".join(x for x in NVCC_FLAGS if ROOT not in x).encode())
+    h.update(" ".join(x for x in NVCC_FLAGS if ROOT not in x).encode() + b" cudart=shared")
     return h.hexdigest()
 
 
@@ -91,7 +91,11 @@ def _build_locked(srcs, stamp, digest, verbose) -> str:
     with ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
         objs = list(ex.map(compile_one, srcs))
     tmp = LIB + f".tmp{os.getpid()}"
-    cmd = [exe, "-shared", "-o", tmp, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC"]
+    # shared cudart: the process already holds torch's libcudart.so.12 (same SONAME); the rpath covers a bare ctypes load.
+    # A static cudart would drag every runtime entry point's name into the shipped .so.
+    cuda_lib = os.path.join(os.path.dirname(os.path.dirname(exe)), "lib64")
+    cmd = [exe, "-shared", "--cudart", "shared", "-o", tmp, *objs, "-gencode", "arch=compute_100a,code=sm_100a",
+           "-Xcompiler", "-fPIC", "-Xlinker", f"-rpath={cuda_lib}"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stderr[-4000:]}")

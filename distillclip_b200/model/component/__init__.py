@@ -1,4 +1,4 @@
-from .clip_model import CLIPModel
+from .clip_model import LazyLogitsCLIP
 from .output import CLIPOutput, ControlOutput, TextTransformerOutput, VisionTransformerOutput
 
-__all__ = ["CLIPModel", "CLIPOutput", "ControlOutput", "TextTransformerOutput", "VisionTransformerOutput"]
+__all__ = ["LazyLogitsCLIP", "CLIPOutput", "ControlOutput", "TextTransformerOutput", "VisionTransformerOutput"]

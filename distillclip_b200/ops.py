@@ -139,18 +139,25 @@ def _ticket(dev: torch.device) -> torch.Tensor:
     return t
 
 
-#: route eligible attention layers through the TMA-staged kernel (csrc/attn_tma.cu); False = per-thread loads only
-#: default OFF: with 1-row boxes of 512 B the copy engine sustains ~1.5 TB/s here against ~4.2 TB/s for the per-thread
-#: loads (scripts/time_tower.py, image stage 123 us vs 44 us); kept as a tested option and a measured negative result
-USE_ATTN_TMA = os.environ.get("DCB_ATTN_TMA", "0") == "1"
-_ATTN_TMA_MAX_LAYERS = 8
+def _seg_shape(kind, s, t):
+    if kind in (KIND_MSE, KIND_L1):
+        if s.shape != t.shape:
+            raise ValueError(f"{kind}: student {tuple(s.shape)} and teacher {tuple(t.shape)} shapes differ")
+        return 1, 1, 1, 1
+    if kind == KIND_COS:
+        if s.shape != t.shape or s.dim() != 2:
+            raise ValueError(f"cosine loss takes equal [B, D] tensors: student {tuple(s.shape)}, teacher {tuple(t.shape)}")
+        return s.shape[0], 1, 1, s.shape[1]
+    if s.dim() < 3 or t.dim() != s.dim() or s.shape[0] != t.shape[0] or s.shape[2:] != t.shape[2:]:
+        raise ValueError(f"attention maps must be [B, H, ...] with equal B and map size: "
+                         f"student {tuple(s.shape)} vs teacher {tuple(t.shape)}")
+    return s.shape[0], s.shape[1], t.shape[1], s.numel() // (s.shape[0] * s.shape[1])
 
 
 def launch_tower(entries, scale: Sequence[float], percent: Sequence[float], grad_dtype: Optional[torch.dtype] = None,
                  out=None):
-    """All streaming losses of one tower: attention-map layers that qualify go through the TMA-staged kernel
-    (csrc/attn_tma.cu), everything else plus the deterministic reduction and weighting through the tower kernel
-    (csrc/tower_stream.cu) -- one or two launches per tower.
+    """All streaming losses of one tower -- every layer of every term, the deterministic reduction and the weighting --
+    in ONE launch of the tower kernel (csrc/tower_stream.cu).
     entries: [(kind, divisor, stu list, tea list, need_grad list, grad_scale)], one per loss term.
     -> (out[n_terms + 1] = scaled term values + weighted total, grads per entry, partials).  `out=(out, grads, partials)`
     reuses buffers (kernel-only timing)."""
@@ -160,50 +167,19 @@ def launch_tower(entries, scale: Sequence[float], percent: Sequence[float], grad
     gd = _DT[grad_dtype] if grad_dtype is not None else in_dt
     n_terms = len(entries)
     stride = lib.dcb_tower_grid()
-    seg = dict(kinds=[], terms=[], stu=[], tea=[], grad=[], numel=[], batch=[], hs=[], ht=[], pos=[], div=[], gsc=[])
-    tma = {0: dict(seg, **{k: [] for k in seg}), 1: dict(seg, **{k: [] for k in seg})}       # per mode
+    d = dict(kinds=[], terms=[], stu=[], tea=[], grad=[], numel=[], batch=[], hs=[], ht=[], pos=[], div=[], gsc=[])
     all_grads = [] if out is None else out[1]
-    ext_mask = 0
     for ti, (kind, divisor, stu, tea, need, pre) in enumerate(entries):
         grads = [] if out is None else all_grads[ti]
-        via_tma = []
         for li, (s, t, ng) in enumerate(zip(stu, tea, need)):
-            if kind in (KIND_MSE, KIND_L1):
-                if s.shape != t.shape:
-                    raise ValueError(f"{kind}: student {tuple(s.shape)} and teacher {tuple(t.shape)} shapes differ")
-                shape = (1, 1, 1, 1)
-            elif kind == KIND_COS:
-                if s.shape != t.shape or s.dim() != 2:
-                    raise ValueError(f"cosine loss takes equal [B, D] tensors: student {tuple(s.shape)}, teacher {tuple(t.shape)}")
-                shape = (s.shape[0], 1, 1, s.shape[1])
-            else:
-                if s.dim() < 3 or t.dim() != s.dim() or s.shape[0] != t.shape[0] or s.shape[2:] != t.shape[2:]:
-                    raise ValueError(f"attention maps must be [B, H, ...] with equal B and map size: "
-                                     f"student {tuple(s.shape)} vs teacher {tuple(t.shape)}")
-                shape = (s.shape[0], s.shape[1], t.shape[1], s.numel() // (s.shape[0] * s.shape[1]))
+            b_, hs_, ht_, pos_ = _seg_shape(kind, s, t)
             if out is None:
                 grads.append(torch.empty_like(s, dtype=grad_dtype or s.dtype) if ng else None)
-            via_tma.append(bool(USE_ATTN_TMA and kind in (KIND_ATTN_KL, KIND_ATTN_MSE) and gd == in_dt
-                                and lib.dcb_attn_tma_supported(in_dt, shape[1], shape[2], shape[3])))
-        # a term goes through the TMA kernel only as a whole (its partials are reduced with a different count)
-        use_tma = bool(via_tma) and all(via_tma)
-        dst = tma[0 if kind == KIND_ATTN_KL else 1] if use_tma else seg
-        if use_tma and len(dst["kinds"]) + len(stu) > _ATTN_TMA_MAX_LAYERS:
-            use_tma, dst = False, seg
-        if use_tma:
-            ext_mask |= 1 << ti
-        for li, (s, t) in enumerate(zip(stu, tea)):
             g = grads[li]
-            if kind in (KIND_MSE, KIND_L1):
-                b_, hs_, ht_, pos_ = 1, 1, 1, 1
-            elif kind == KIND_COS:
-                b_, hs_, ht_, pos_ = s.shape[0], 1, 1, s.shape[1]
-            else:
-                b_, hs_, ht_, pos_ = s.shape[0], s.shape[1], t.shape[1], s.numel() // (s.shape[0] * s.shape[1])
-            dst["kinds"].append(_KIND_CODE[kind]), dst["terms"].append(ti)
-            dst["stu"].append(s.data_ptr()), dst["tea"].append(t.data_ptr()), dst["grad"].append(g.data_ptr() if g is not None else 0)
-            dst["numel"].append(s.numel()), dst["batch"].append(b_), dst["hs"].append(hs_), dst["ht"].append(ht_)
-            dst["pos"].append(pos_), dst["div"].append(int(divisor)), dst["gsc"].append(float(pre))
+            d["kinds"].append(_KIND_CODE[kind]), d["terms"].append(ti)
+            d["stu"].append(s.data_ptr()), d["tea"].append(t.data_ptr()), d["grad"].append(g.data_ptr() if g is not None else 0)
+            d["numel"].append(s.numel()), d["batch"].append(b_), d["hs"].append(hs_), d["ht"].append(ht_)
+            d["pos"].append(pos_), d["div"].append(int(divisor)), d["gsc"].append(float(pre))
         if out is None:
             all_grads.append(grads)
     if out is None:
@@ -211,21 +187,13 @@ def launch_tower(entries, scale: Sequence[float], percent: Sequence[float], grad
         partials = torch.empty(n_terms * stride, dtype=torch.float64, device=dev)
     else:
         res, partials = out[0], out[2]
-    for mode in (0, 1):
-        d = tma[mode]
-        if d["kinds"]:
-            _lib.call("dcb_attn_tma_fwd_bwd", len(d["kinds"]), mode, _lib.i32_array(d["terms"]), _lib.ptr_array(d["stu"]),
-                      _lib.ptr_array(d["tea"]), _lib.ptr_array(d["grad"]), _lib.i64_array(d["batch"]), _lib.i32_array(d["hs"]),
-                      _lib.i32_array(d["ht"]), _lib.i64_array(d["pos"]), _lib.i32_array(d["div"]), _lib.f32_array(d["gsc"]),
-                      in_dt, C.c_void_p(partials.data_ptr()), stride, _stream_ptr())
-    d = seg
     n = len(d["kinds"])
     pad = (lambda v: v if v else [0])
     _lib.call("dcb_tower_fwd_bwd", n, _lib.i32_array(pad(d["kinds"])), _lib.i32_array(pad(d["terms"])), _lib.ptr_array(pad(d["stu"])),
               _lib.ptr_array(pad(d["tea"])), _lib.ptr_array(pad(d["grad"])), _lib.i64_array(pad(d["numel"])), _lib.i64_array(pad(d["batch"])),
               _lib.i32_array(pad(d["hs"])), _lib.i32_array(pad(d["ht"])), _lib.i64_array(pad(d["pos"])), _lib.i32_array(pad(d["div"])),
               _lib.f32_array(pad(d["gsc"])), n_terms, _lib.f32_array(scale), _lib.f32_array(percent), in_dt, gd,
-              C.c_void_p(partials.data_ptr()), stride, ext_mask, lib.dcb_attn_tma_grid(),
+              C.c_void_p(partials.data_ptr()), stride, 0, 0,
               C.c_void_p(_ticket(dev).data_ptr()), C.c_void_p(res.data_ptr()), _stream_ptr())
     return res, all_grads, partials
 

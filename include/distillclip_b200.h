@@ -74,8 +74,8 @@ int dcb_attn_kl_fwd_bwd(int n_layers, const void* const* stu, const void* const*
  * out[q] = scale[q] * value_q (q < n_terms), out[n_terms] = sum_q percent[q] * out[q]  (_loss.py:199-200).
  * partials: n_terms rows of partial_stride (>= dcb_tower_grid()) doubles of scratch; ticket: one uint32, zero before the
  * first launch (the kernel resets it).  Values are reduced in a fixed order by the last CTA to finish: deterministic,
- * no extra launch.  Terms in ext_mask were already reduced to ext_count partials per row by dcb_attn_tma_fwd_bwd on the
- * same stream (n_seg may then be 0: this call only finishes the weighting).
+ * no extra launch.  Terms in ext_mask were already reduced to ext_count partials per row by another kernel on the same
+ * stream (n_seg may then be 0: this call only finishes the weighting); pass 0 / 0 otherwise.
  * --------------------------------------------------------------------------------------------- */
 int dcb_tower_grid(void);
 int dcb_tower_fwd_bwd(int n_seg, const int32_t* kind, const int32_t* term, const void* const* stu,
@@ -85,21 +85,6 @@ int dcb_tower_fwd_bwd(int n_seg, const int32_t* kind, const int32_t* term, const
                       const float* scale, const float* percent, int in_dtype, int grad_dtype,
                       double* partials, int partial_stride, uint32_t ext_mask, int ext_count,
                       uint32_t* ticket, float* out, void* stream);
-
-/* ---------------------------------------------------------------------------------------------
- * Attention-map KL (mode 0, attention_probs_kl.py:10-22) or MSE of the head means (mode 1, attention_probs_mse.py /
- * attention_score_mse.py) with TMA-staged tiles: every (head, position chunk) is fetched by the copy engine at its
- * arbitrary element offset, so maps whose head rows are not 16-byte aligned (N = 50, 77) stream at full width.
- * Layers must satisfy dcb_attn_tma_supported (bf16/fp16, positions >= 256, 16-byte aligned samples); gradients are
- * written in the input dtype.  Fills partials[term[l]][0 .. dcb_attn_tma_grid()) (row stride partial_stride doubles);
- * finish with dcb_tower_fwd_bwd(ext_mask, ext_count = dcb_attn_tma_grid()).
- * --------------------------------------------------------------------------------------------- */
-int dcb_attn_tma_supported(int dtype, int64_t stu_heads, int64_t tea_heads, int64_t positions);
-int dcb_attn_tma_grid(void);
-int dcb_attn_tma_fwd_bwd(int n_layers, int mode, const int32_t* term, const void* const* stu, const void* const* tea,
-                         void* const* grad_stu, const int64_t* batch, const int32_t* stu_heads, const int32_t* tea_heads,
-                         const int64_t* positions, const int32_t* divisor, const float* grad_scale, int dtype,
-                         double* partials, int partial_stride, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Deterministic reduction + weighting (model/_loss.py:195-200 and :148-152).

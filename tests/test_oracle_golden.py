@@ -248,3 +248,33 @@ def test_retrieval_metrics(name):
     res = cf.retrieval_metrics(g["img"], g["txt"])
     for k, v in res.items():
         assert v == pytest.approx(float(g[f"{k}_f64"]), rel=1e-12, abs=1e-15), k
+
+
+@pytest.mark.parametrize("name", CLIP)
+@pytest.mark.parametrize("chunk", [7, 64])
+def test_chunked_fp64_oracle_matches_golden_and_closed_form(name, chunk):
+    """oracle/chunked_fp64.py (the full-size checker: literal formulas, row chunks, two passes) against the reference-made
+    fixtures and the dense float64 oracle, including the cos_diff / logits_mse terms and sampled-row gradients."""
+    from oracle import chunked_fp64 as ck
+    g = golden(name)
+    T = float(g["temperature"])
+    emb = [torch.tensor(g[k]).to(torch.bfloat16).float() for k in ("stu_img", "stu_txt", "tea_img", "tea_txt")]
+    b = emb[0].shape[0]
+    rows_i, rows_t = list(range(0, b, 3)), list(range(1, b, 4))
+    w = {"hard": 0.7, "soft": 0.3, "cos_diff": 0.4, "logits_mse": 1.5}
+    out = ck.contrastive_chunked(*emb, temperature=T, weights=w, sample_img=rows_i, sample_txt=rows_t, chunk=chunk)
+    assert out["hard"] == pytest.approx(float(g["hard_f64"]), rel=1e-10)
+    assert out["soft"] == pytest.approx(float(g["soft_f64"]), rel=1e-9)
+    np_emb = [x.numpy() for x in emb]
+    ref = cf.contrastive_from_embeddings(*np_emb, T, w_hard=w["hard"], w_soft=w["soft"])
+    s, _ = cf.clip_logits(np_emb[0], np_emb[1])
+    t, _ = cf.clip_logits(np_emb[2], np_emb[3])
+    cd, g_cd = cf.cos_diff(s, t)
+    cd2, g_cd2 = cf.cos_diff(s.T, t.T)
+    lm, g_lm = cf.logits_mse(s, t)
+    assert out["cos_diff"] == pytest.approx(0.5 * (cd + cd2), rel=1e-12)
+    assert out["logits_mse"] == pytest.approx(lm, rel=1e-12)
+    dl = ref["d_logits"] + w["cos_diff"] * 0.5 * (g_cd + g_cd2.T) + w["logits_mse"] * g_lm
+    d_img, d_txt = cf.clip_logits_backward(np_emb[0], np_emb[1], dl)
+    assert rel_l2(out["d_img"].numpy(), d_img[rows_i]) <= 1e-10
+    assert rel_l2(out["d_txt"].numpy(), d_txt[rows_t]) <= 1e-10
