@@ -191,10 +191,10 @@ class L2Flush:
 
     def __init__(self, device):
         self.buf = torch.zeros(64 * 1024 * 1024, dtype=torch.int32, device=device)
-        self.sink = torch.zeros((), dtype=torch.int64, device=device)
+        self.sink = None
 
     def __call__(self):
-        torch.sum(self.buf, out=self.sink)
+        self.sink = self.buf.sum()
 
 
 class Timer:
@@ -501,9 +501,10 @@ def cpu_clip(cfg, budget_s):
 def parity_clip(cfg, glob, rank, world, dist, group, device):
     """Losses of the GLOBAL batch and gradients of sampled local rows against the chunked float64 oracle
     (oracle/chunked_fp64.py, literal formulas of the reference, run here on the GPU in torch float64 on the full global
-    batch), for every backward route available at this world size, plus the bf16 gradients of the public call."""
+    batch), for every exchange route available at this world size, plus the bf16 gradients of the public call."""
     from oracle import chunked_fp64 as ck
     from distillclip_b200 import contrastive as ct
+    from distillclip_b200 import pipeline as pl
     b, T = cfg["batch"], cfg["temperature"]
     rows = b // world
     off = rank * rows
@@ -515,66 +516,88 @@ def parity_clip(cfg, glob, rank, world, dist, group, device):
     ref = ck.contrastive_chunked(*glob, temperature=T, weights={"hard": w_hard, "soft": w_soft},
                                  sample_img=[off + i for i in loc_i], sample_txt=[off + i for i in loc_t], chunk=2048)
     si, st, ti, tt = [x[off:off + rows].contiguous() for x in glob]
-    eng = ct.CudaEngine()
-    up = torch.tensor([w_hard, w_soft], dtype=torch.float32, device=device)
+    eng = ct._ENGINE
+    one = torch.ones((), dtype=torch.float32, device=device)
     routes = {}
-    route_list = [("fused", None)] if world == 1 else [("peer_scatter", True), ("nccl_reduce_scatter", False)]
-    old = ct.PeerScatter.enabled
-    for rname, peer in route_list:
-        if peer is not None:
-            ct.PeerScatter.enabled = peer
-        out, saved = ct.contrastive_forward(eng, si, st, ti, tt, T, group)
-        gi, gt = ct.contrastive_backward(eng, saved, up, grad_dtype=torch.float32)
+    # (name, symmetric-memory exchange, peer-memory scatter fused into the G^T GEMM)
+    route_list = [("single_gpu", True, True)] if world == 1 else [("peer_memory", True, True), ("peer_memory+nccl_reduce_scatter", True, False),
+                                                                   ("nccl_collectives", False, False)]
+    old = pl.SymmExchange.enabled, pl.SymmExchange.scatter_enabled
+    for rname, symm, scatter in route_list:
+        pl.SymmExchange.enabled, pl.SymmExchange.scatter_enabled = symm, scatter
+        xc = pl.exchange_for(group)
+        out, saved = pl.pipeline_forward(eng, xc, si, st, ti, tt, T, (w_hard, w_soft, 1.0, 1.0))
+        gi, gt = pl.pipeline_backward(eng, saved, (one, None, None), grad_dtype=torch.float32)
         torch.cuda.synchronize()
         errs = [abs(float(out[0]) - ref["hard"]) / abs(ref["hard"]), abs(float(out[1]) - ref["soft"]) / abs(ref["soft"]),
                 _rel(gi[loc_i], ref["d_img"]), _rel(gt[loc_t], ref["d_txt"])]
         errs = _max_over_ranks(errs, dist)
         routes[rname] = {"hard_rel_err": float(f"{errs[0]:.3e}"), "soft_rel_err": float(f"{errs[1]:.3e}"),
                          "grad_img_rel_l2": float(f"{errs[2]:.3e}"), "grad_txt_rel_l2": float(f"{errs[3]:.3e}"),
+                         "exchange": type(xc).__name__,
                          "ok": bool(max(errs[:2]) <= LOSS_RTOL and max(errs[2:]) <= GRAD_RTOL)}
-        if peer and world > 1 and not ct.PeerScatter._cache:
-            routes[rname]["note"] = "symmetric memory unavailable: this route fell back to the NCCL reduce-scatter"
-    ct.PeerScatter.enabled = old
+    pl.SymmExchange.enabled, pl.SymmExchange.scatter_enabled = old
     # the public call (bf16 gradients as autograd returns them)
     a, c_ = si.clone().requires_grad_(True), st.clone().requires_grad_(True)
-    res = ct.clip_contrastive(a, c_, ti, tt, T, want_hard=True, want_soft=True, group=group)
-    (w_hard * res["hard_label"] + w_soft * res["soft_label"]).backward()
+    res = ct.clip_contrastive(a, c_, ti, tt, T, want_hard=True, want_soft=True, group=group, percent=(w_hard, w_soft))
+    res["total"].backward()
     torch.cuda.synchronize()
-    api = _max_over_ranks([_rel(a.grad[loc_i], ref["d_img"]), _rel(c_.grad[loc_t], ref["d_txt"])], dist)
-    ok = all(r["ok"] for r in routes.values()) and max(api) <= GRAD_STORAGE_RTOL
-    return {"ok": bool(ok), "routes": routes, "grad_rel_l2_api_bf16": float(f"{max(api):.3e}"),
+    api = _max_over_ranks([_rel(a.grad[loc_i], ref["d_img"]), _rel(c_.grad[loc_t], ref["d_txt"]),
+                           abs(float(res["total"]) - (w_hard * ref["hard"] + w_soft * ref["soft"])) / abs(w_hard * ref["hard"] + w_soft * ref["soft"])], dist)
+    ok = all(r["ok"] for r in routes.values()) and max(api[:2]) <= GRAD_STORAGE_RTOL and api[2] <= LOSS_RTOL
+    return {"ok": bool(ok), "routes": routes, "grad_rel_l2_api_bf16": float(f"{max(api[:2]):.3e}"),
+            "total_rel_err_api": float(f"{api[2]:.3e}"),
             "sampled_rows_per_side_per_rank": n_samp, "oracle": {"hard": ref["hard"], "soft": ref["soft"]},
             "tol": {"loss": LOSS_RTOL, "grad_fp32": GRAD_RTOL, "grad_bf16_storage": GRAD_STORAGE_RTOL},
             "checker": "oracle/chunked_fp64.py: literal reference formulas in float64 on the full global batch (max over ranks)"}
 
 
 def clip_kernel_times(cfg, glob, rank, world, device, pk):
-    """The three tcgen05 kernels of one step at this rank's shapes, each timed alone (cold L2, CUDA events on the launching
-    stream) through the raw C-ABI calls; flops = executed = credited (12 B^2 D / R per rank in total)."""
+    """The three tcgen05 kernels of one step at this rank's shapes (local rows x ALL columns), each timed alone (cold L2,
+    CUDA events on the launching stream) through the raw C-ABI calls; flops = executed = credited (12 B^2 D / R
+    per rank in total)."""
     from distillclip_b200 import contrastive as ct
+    from distillclip_b200 import pipeline as pl
     b, d, T = cfg["batch"], cfg["dim"], cfg["temperature"]
     rows = b // world
     off = rank * rows
+    eng = ct._ENGINE
     si, st, ti, tt = glob
-    eng = ct.CudaEngine()
-    inv = eng.inv_norms([si, st, ti, tt])
-    loc = slice(off, off + rows)
-    a_s, a_t, a_si, a_ti = si[loc].contiguous(), ti[loc].contiguous(), inv[0][loc].contiguous(), inv[2][loc].contiguous()
-    stats, rl, col = eng.row_stats(a_s, st, a_t, tt, a_si, inv[1], a_ti, inv[3], off, T, with_cols=True)
-    st2, _ = eng.col_finish(col, stats[4].contiguous(), off, T, True)
-    up = torch.tensor([0.5, 0.5], dtype=torch.float32, device=device)
-    coef_r, gm_r = eng.coef(stats, b, T, True, up)
-    coef_c, gm_c = eng.coef(col, b, T, True, up)
-    bt = eng.transpose_norm(st, inv[1])
-    at = eng.transpose_norm(a_s, a_si)
+    a_s, a_t = si[off:off + rows].contiguous(), ti[off:off + rows].contiguous()
+    # one-rank pipeline over (local image rows) x (all text rows) prepares every operand the kernels take
+    xc = pl.LocalExchange()
+    inv = [torch.empty(x.shape[0], dtype=torch.float32, device=device) for x in (a_s, st, a_t, tt)]
+    at = torch.empty(d, (rows + 7) // 8 * 8, dtype=torch.float16, device=device)
+    bt = torch.empty(1, d, b, dtype=torch.float16, device=device)
+    eng.prep([st, tt], [inv[1], inv[3]], [None, None], [bt[0], None])
+    eng.prep([a_s, a_t], [inv[0], inv[2]], [None, None], [at, None])
+    parts = eng.fwd_parts(rows, b)
+    ws = torch.empty(parts, 4, rows, dtype=torch.float32, device=device)
+    diag = torch.empty(rows, dtype=torch.float32, device=device)
+    col_part = torch.empty((rows + 127) // 128, 4, b, dtype=torch.float32, device=device)
+    fwd = lambda: eng.fwd_chunk(a_s, st, a_t, tt, inv[0], inv[1], inv[2], inv[3], off, T, ws, diag, col_part, b)
+    fwd()
+    stats = torch.empty(5, rows, dtype=torch.float32, device=device)
+    coef_row = torch.empty(3, rows, dtype=torch.float32, device=device)
+    slots = torch.empty(1, pl.slot_floats(b, rows), dtype=torch.float32, device=device)
+    eng.post1(ws, diag, col_part, T, True, b, stats, coef_row, [slots[0]])
+    # column coefficients of all B columns: a full one-rank forward on the global batch would give the exact ones; for timing
+    # the column sums of this rank's rows are representative (same magnitudes)
+    fake = torch.empty(1, pl.slot_floats(b, b), dtype=torch.float32, device=device)
+    fake.zero_()
+    fake[0, :4 * b] = slots[0, :4 * b] * world
+    fake[0, 4 * b:5 * b] = 0.5
+    _, coef_col, bounds, _ = eng.post2(fake, b, b, T, True, (0.5, 0.5, 1.0, 1.0))
+    bounds[:3] = bounds[3:]
+    one = torch.ones((), dtype=torch.float32, device=device)
+    up = (one, None, None, 0.5, 0.5, 1.0, 1.0)
     out = {}
     flush = L2Flush(device)
-    kernels = {"clip_fwd_kernel": (lambda: eng.row_stats(a_s, st, a_t, tt, a_si, inv[1], a_ti, inv[3], off, T, with_cols=True), 4.0)}
-    if eng.single_pass_supported(d):
-        g = eng.alloc_g(rows, b, device)
-        kernels["clip_bwd_pair_kernel"] = (lambda: eng.row_acc(a_s, st, a_t, tt, bt, a_si, inv[1], a_ti, inv[3], coef_r, coef_c,
-                                                               gm_r, gm_c, T, g_out=g), 6.0)
-        kernels["clip_gt_gemm_kernel"] = (lambda: eng.col_acc_from_g(g, at, rows, b, d), 2.0)
+    g = eng.alloc_g(rows, b, device)
+    kernels = {"clip_fwd_kernel": (fwd, 4.0),
+               "clip_bwd_pair_kernel": (lambda: eng.pair_bwd(a_s, st, a_t, tt, bt, inv[0], inv[1], inv[2], inv[3], coef_row, coef_col,
+                                                             bounds, up, T, g), 6.0),
+               "clip_gt_gemm_kernel": (lambda: eng.col_acc_from_g(g, at, rows, b, d), 2.0)}
     for kname, (fn, fl) in kernels.items():
         ms = time_kernel(fn, 10, device, flush)
         flops = fl * rows * b * d
@@ -602,8 +625,8 @@ def bench_clip(cfg, name, args, device, dist, rank, world, pk, steps, warmup):
     def step():
         si.grad = None
         st.grad = None
-        res = clip_contrastive(si, st, ti, tt, T, want_hard=True, want_soft=True, group=group)
-        (0.5 * res["hard_label"] + 0.5 * res["soft_label"]).backward()
+        res = clip_contrastive(si, st, ti, tt, T, want_hard=True, want_soft=True, group=group, percent=(0.5, 0.5))
+        res["total"].backward()
     timer = Timer(device, flush=4 * b * d * 2 < L2_BYTES)
     step()
     _lib.LAUNCHES = 0
@@ -621,8 +644,8 @@ def bench_clip(cfg, name, args, device, dist, rank, world, pk, steps, warmup):
         a, c_, e, f = [h.to(device, non_blocking=True) for h in host]
         a.requires_grad_(True)
         c_.requires_grad_(True)
-        res = clip_contrastive(a, c_, e, f, T, want_hard=True, want_soft=True, group=group)
-        loss = 0.5 * res["hard_label"] + 0.5 * res["soft_label"]
+        res = clip_contrastive(a, c_, e, f, T, want_hard=True, want_soft=True, group=group, percent=(0.5, 0.5))
+        loss = res["total"]
         loss.backward()
         loss_host.copy_(loss.detach(), non_blocking=True)
         torch.cuda.current_stream().synchronize()

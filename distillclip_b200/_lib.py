@@ -44,6 +44,21 @@ SIGNATURES = {
     "dcb_clip_col_grads_scatter": [_vp, C.c_int64, _vp, C.c_int64, C.c_int64, C.c_int64, C.c_int64, _vp, C.c_int, C.c_int, _vp],
     "dcb_clip_grad_finish": [_vp, C.c_int, _vp, _vp, _vp, _vp, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int64,
                              _vp, _vp, _vp, C.c_int, _vp, C.c_int, _vp],
+    "dcb_memcpy_async": [_vp, _vp, C.c_int64, _vp],
+    "dcb_clip_prep": [C.c_int, _vpp, _vpp, _vpp, _vpp, _i64p, C.c_int64, C.c_int64, C.c_int, _vp],
+    "dcb_clip_fwd_chunk": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int,
+                           C.c_float, _vp, _vp, _vp, C.c_int64, _vp],
+    "dcb_clip_post1": [_vp, C.c_int, _vp, _vp, C.c_int, C.c_int64, C.c_int64, C.c_float, C.c_int, C.c_int64, _vp, _vp, _vpp,
+                       C.c_int, _vp, _vp],
+    "dcb_clip_post2": [_vp, C.c_int, C.c_int64, C.c_int64, C.c_float, C.c_int, C.c_int64, C.c_float, C.c_float, C.c_float,
+                       C.c_float, _vp, _vp, _vp, _vp, _vp, _vp],
+    "dcb_clip_pair_bwd": [_vp, _vp, _vp, _vp, _vp, C.c_int64, C.c_int64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                          C.c_float, C.c_float, C.c_float, C.c_float, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_float,
+                          _vp, _vp, C.c_int64, _vp],
+    "dcb_clip_finish2": [_vp, C.c_int, C.c_int64, _vp, _vp, _vp, C.c_int64, _vp, _vp, C.c_int64, C.c_int64,
+                         _vp, C.c_int, C.c_int64, _vp, _vp, _vp, C.c_int64, _vp, _vp, C.c_int64, C.c_int64,
+                         C.c_int64, C.c_int64, _vp, _vp, _vp, C.c_float, C.c_float, C.c_float, C.c_float, _vp, C.c_int, C.c_int,
+                         _vp],
     "dcb_value_map_kl_fwd_bwd": [_vp, _vp, _vp, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_float, _vp,
                                  C.POINTER(C.c_int), _vp],
     "dcb_row_softmax_stats": [_vp, _vp, C.c_int64, C.c_int64, C.c_int, C.c_float, C.c_int, _vp, _vp, _vp],
@@ -60,6 +75,9 @@ _SPECIAL = {
     "dcb_clip_pair_splits": (C.c_int, [C.c_int64, C.c_int64, C.c_int64]),
     "dcb_clip_pair_supported": (C.c_int, [C.c_int64]),
     "dcb_clip_gt_splits": (C.c_int, [C.c_int64, C.c_int64, C.c_int64]),
+    "dcb_clip_fwd_chunk_parts": (C.c_int, [C.c_int64, C.c_int64]),
+    "dcb_clip_slot_floats": (C.c_int64, [C.c_int64, C.c_int64]),
+    "dcb_clip_post_scratch_bytes": (C.c_int64, [C.c_int64, C.c_int64]),
     "dcb_tower_grid": (C.c_int, []),
     "dcb_version": (C.c_int, []),
     "dcb_compiled_arch": (C.c_int, []),
@@ -99,7 +117,7 @@ def load():
 
 
 # kernels launched per C-ABI call (bench.py reports the sum as "gpu_launches")
-_LAUNCHES_PER_CALL = {"dcb_clip_row_stats": 3, "dcb_clip_rank_counts": 2}
+_LAUNCHES_PER_CALL = {"dcb_clip_row_stats": 3, "dcb_clip_rank_counts": 2, "dcb_memcpy_async": 0}
 LAUNCHES = 0
 
 

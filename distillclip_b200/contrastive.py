@@ -169,7 +169,8 @@ class CudaEngine:
         """The G^T GEMM with its epilogue storing every output row into the partial buffer of the rank that owns it
         (peer-mapped pointers `dest_ptrs`, one per rank): the reduce-scatter of the row-sharded backward without a collective."""
         _lib.call("dcb_clip_col_grads_scatter", _vp(g), g.shape[1], _vp(a_hat_t), a_hat_t.shape[1], rows, cols, dim,
-                  _lib.ptr_array(dest_ptrs), len(dest_ptrs), int(src_slot), ops._stream_ptr())
+                  _lib.ptr_array([d if isinstance(d, int) else d.data_ptr() for d in dest_ptrs]), len(dest_ptrs), int(src_slot),
+                  ops._stream_ptr())
 
     def finish_grads(self, acc, a_s, a_s_inv, b_s, b_s_inv, gmax_row, gmax_col, row_offset, global_batch, upstream,
                      grad_dtype):
@@ -187,6 +188,96 @@ class CudaEngine:
                            gmax_row, gmax_col, temperature, g_out)
         return self.finish_grads(acc, a_s, a_s_inv, b_s, b_s_inv, gmax_row, gmax_col, row_offset, global_batch,
                                  upstream, grad_dtype)
+
+    # ------------------------------------------------------------------------------------------
+    # pipeline flavour (distillclip_b200/pipeline.py): fused small kernels, unit coefficients, exchange-friendly outputs
+    # ------------------------------------------------------------------------------------------
+    slot_dtype = stat_dtype = torch.float32
+    tr_dtype = torch.float16
+    _scratch: Dict = {}
+
+    def gt_splits(self, rows, cols, dim):
+        return _lib.load().dcb_clip_gt_splits(rows, cols, dim)
+
+    def fwd_parts(self, rows, cols_chunk):
+        return _lib.load().dcb_clip_fwd_chunk_parts(rows, cols_chunk)
+
+    @classmethod
+    def _post_scratch(cls, rows, cols, dev, which):
+        """Zero-initialised ticket + block partials of the post kernels (they reset the ticket): one per device, stream, kernel."""
+        need = _lib.load().dcb_clip_post_scratch_bytes(rows, cols)
+        key = (dev.index, torch.cuda.current_stream(dev).cuda_stream, which)
+        buf = cls._scratch.get(key)
+        if buf is None or buf.numel() < need:
+            buf = cls._scratch[key] = torch.zeros(max(need, 4096), dtype=torch.uint8, device=dev)
+        return buf
+
+    def prep(self, mats, invs, copies, trs):
+        rows, dim = mats[0].shape
+        _lib.call("dcb_clip_prep", len(mats), _lib.ptr_array([m.data_ptr() for m in mats]),
+                  _lib.ptr_array([o.data_ptr() for o in invs]),
+                  _lib.ptr_array([c.data_ptr() if c is not None else 0 for c in copies]),
+                  _lib.ptr_array([t.data_ptr() if t is not None else 0 for t in trs]),
+                  _lib.i64_array([t.stride(0) if t is not None else 0 for t in trs]), rows, dim, ops.dtype_code(mats[0]),
+                  ops._stream_ptr())
+
+    def fwd_chunk(self, a_s, b_s, a_t, b_t, a_s_inv, b_s_inv, a_t_inv, b_t_inv, label_col0, temperature, ws_chunk, diag,
+                  col_part_chunk, col_part_ld):
+        _lib.call("dcb_clip_fwd_chunk", _vp(a_s), _vp(b_s), _vp(a_t), _vp(b_t), _vp(a_s_inv), _vp(b_s_inv), _vp(a_t_inv),
+                  _vp(b_t_inv), a_s.shape[0], int(label_col0), b_s.shape[0], a_s.shape[1], ops.dtype_code(a_s),
+                  float(temperature or 1.0), _vp(ws_chunk), _vp(diag), _vp(col_part_chunk), int(col_part_ld), ops._stream_ptr())
+
+    def post1(self, ws, diag, col_part, temperature, has_teacher, global_batch, stats, coef_row, dests):
+        rows, cols = diag.shape[0], col_part.shape[2]
+        _lib.call("dcb_clip_post1", _vp(ws), ws.shape[0], _vp(diag), _vp(col_part), col_part.shape[0], rows, cols,
+                  float(temperature or 1.0), int(has_teacher), int(global_batch), _vp(stats), _vp(coef_row),
+                  _lib.ptr_array([d.data_ptr() for d in dests]), len(dests), _vp(self._post_scratch(rows, cols, diag.device, 1)),
+                  ops._stream_ptr())
+
+    def post2(self, slots, rows_per_src, cols, temperature, has_teacher, weights):
+        dev = slots.device
+        col_stats = torch.empty(4, cols, dtype=torch.float32, device=dev)
+        coef_col = torch.empty(3, cols, dtype=torch.float32, device=dev)
+        bounds = torch.empty(6, dtype=torch.float32, device=dev)
+        out = torch.empty(5, dtype=torch.float32, device=dev)
+        p_h, p_s, s_h, s_s = [float(w) for w in weights]
+        _lib.call("dcb_clip_post2", _vp(slots), slots.shape[0], int(rows_per_src), int(cols), float(temperature or 1.0),
+                  int(has_teacher), int(cols), p_h, p_s, s_h, s_s, _vp(col_stats), _vp(coef_col), _vp(bounds), _vp(out),
+                  _vp(self._post_scratch(rows_per_src, cols, dev, 2)), ops._stream_ptr())
+        return col_stats, coef_col, bounds, out
+
+    def pair_bwd(self, a_s, b_s, a_t, b_t, bt_all, a_s_inv, b_s_inv, a_t_inv, b_t_inv, coef_row, coef_col, bounds, up,
+                 temperature, g_out):
+        rows, dim = a_s.shape
+        cols = b_s.shape[0]
+        n_split = _lib.load().dcb_clip_pair_splits(rows, cols, dim)
+        acc = torch.empty(n_split, rows, dim, dtype=torch.float32, device=a_s.device)
+        g_t, g_h, g_s, w_h, w_s, s_h, s_s = up
+        _lib.call("dcb_clip_pair_bwd", _vp(a_s), _vp(b_s), _vp(a_t), _vp(b_t), _vp(bt_all), bt_all.stride(1), cols // bt_all.shape[0],
+                  _vp(a_s_inv), _vp(b_s_inv), _vp(a_t_inv), _vp(b_t_inv), _vp(coef_row), _vp(coef_col), _vp(bounds),
+                  _vp(g_t), _vp(g_h), _vp(g_s), float(w_h), float(w_s), float(s_h), float(s_s), rows, cols, dim,
+                  ops.dtype_code(a_s), float(temperature or 1.0), _vp(acc), _vp(g_out), g_out.shape[1] if g_out is not None else 0,
+                  ops._stream_ptr())
+        return acc
+
+    def finish2(self, side_a, side_b, global_batch, up, bounds, grad_dtype):
+        """side = dict(acc [n_split, rows, D], x [rows, D], x_inv, y (label rows of the other tower), y_inv, label_offset) or None."""
+        g_t, g_h, g_s, w_h, w_s, s_h, s_s = up
+        args, grads, ref = [], [], side_a or side_b
+        dim = ref["x"].shape[1]
+        for sd in (side_a, side_b):
+            if sd is None:
+                args += [None, 0, 0, None, None, None, 0, None, None, 0, 0]
+                grads.append(None)
+                continue
+            x, acc = sd["x"], sd["acc"]
+            g = torch.empty(x.shape, dtype=grad_dtype, device=x.device)
+            grads.append(g)
+            args += [_vp(acc), acc.shape[0], acc.stride(0), _vp(x), _vp(sd["x_inv"]), _vp(g), x.shape[0], _vp(sd["y"]),
+                     _vp(sd["y_inv"]), sd["y"].shape[0], int(sd["label_offset"])]
+        _lib.call("dcb_clip_finish2", *args, dim, int(global_batch), _vp(g_t), _vp(g_h), _vp(g_s), float(w_h), float(w_s),
+                  float(s_h), float(s_s), _vp(bounds), ops.dtype_code(ref["x"]), ops._DT[grad_dtype], ops._stream_ptr())
+        return grads[0], grads[1]
 
 
 # ==============================================================================================
@@ -397,12 +488,49 @@ class ClipContrastiveFn(torch.autograd.Function):
         return g_img, g_txt, None, None, None, None
 
 
-def fused_supported(stu_img: torch.Tensor, stu_txt: torch.Tensor, temperature=None) -> bool:
-    """The tcgen05 path takes bf16/fp16 [B, D] embeddings with D % 8 == 0 and T >= MIN_FUSED_TEMPERATURE."""
-    ok = (stu_img.is_cuda and stu_img.dim() == 2 and stu_img.shape == stu_txt.shape and stu_img.dtype in _HALF
+def _as_scalar(g: Optional[torch.Tensor]):
+    if g is None:
+        return None
+    if g.dtype != torch.float32 or not g.is_contiguous():
+        g = g.to(torch.float32).contiguous()
+    return g
+
+
+class ClipPipelineFn(torch.autograd.Function):
+    """(stu_img, stu_txt, tea_img, tea_txt) -> (hard * s_hard, soft * s_soft, p_hard * hard * s_hard + p_soft * soft * s_soft):
+    0.5*(i2t + t2i) of CrossEntropy(mean) and of T^2 KL(sum) with the scale / percent weighting of reference
+    _loss.py:130-137,231-234, for the global batch of the exchange `xc` (distillclip_b200/pipeline.py)."""
+
+    @staticmethod
+    def forward(ctx, si, st, ti, tt, temperature, xc, weights):
+        from . import pipeline
+        out, saved = pipeline.pipeline_forward(_ENGINE, xc, si, st, ti, tt, temperature, weights)
+        ctx.set_materialize_grads(False)
+        if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
+            ctx.saved = saved
+        else:
+            xc.release(saved["set"])                   # nothing will come back for these buffers
+        return out[2], out[3], out[4]
+
+    @staticmethod
+    def backward(ctx, g_hard, g_soft, g_total):
+        from . import pipeline
+        ups = (_as_scalar(g_total), _as_scalar(g_hard), _as_scalar(g_soft))
+        g_img, g_txt = pipeline.pipeline_backward(_ENGINE, ctx.saved, ups, ctx.needs_input_grad[0], ctx.needs_input_grad[1])
+        return g_img, g_txt, None, None, None, None, None
+
+
+def fused_supported(stu_img: torch.Tensor, stu_txt: torch.Tensor, temperature=None, tea_img=None, tea_txt=None) -> bool:
+    """The tcgen05 path takes bf16/fp16 [B, D] embeddings with D % 8 == 0, T >= MIN_FUSED_TEMPERATURE and (for the soft
+    label) teacher embeddings of the student's shape."""
+    ok = (stu_img is not None and stu_txt is not None and stu_img.is_cuda and stu_img.dim() == 2
+          and stu_img.shape == stu_txt.shape and stu_img.dtype in _HALF
           and stu_txt.dtype == stu_img.dtype and stu_img.shape[1] % 8 == 0)
     if temperature is not None:
         ok = ok and float(temperature) >= MIN_FUSED_TEMPERATURE
+    for t in (tea_img, tea_txt):
+        if t is not None:
+            ok = ok and t.is_cuda and t.shape == stu_img.shape
     return bool(ok)
 
 
@@ -412,13 +540,18 @@ def _prep(x: Optional[torch.Tensor], dtype, what: str):
     ops._require_cuda(x, what)
     if x.dtype != dtype:
         x = x.to(dtype)
-    return x if x.is_contiguous() else x.contiguous()
+    if not x.is_contiguous() or x.data_ptr() % 16:
+        x = x.contiguous() if not x.is_contiguous() else x.clone()
+    return x
 
 
 def clip_contrastive(stu_img, stu_txt, tea_img=None, tea_txt=None, temperature=None, want_hard=True,
-                     want_soft=False, group=None) -> Dict[str, torch.Tensor]:
-    """Fused hard-label / soft-label losses from embeddings.  Returns {'hard_label': ..., 'soft_label': ...}
-    (only the requested keys); values are 0-dim fp32 tensors on the autograd graph of the student embeddings."""
+                     want_soft=False, group=None, percent=None, scale=None) -> Dict[str, torch.Tensor]:
+    """Fused hard-label / soft-label losses from embeddings.  Returns {'hard_label': ..., 'soft_label': ...} (only the
+    requested keys; multiplied by `scale = (s_hard, s_soft)` when given) and, with `percent = (p_hard, p_soft)`, also
+    'total' = p_hard * hard_label + p_soft * soft_label computed on the device.  Values are 0-dim fp32 tensors on the
+    autograd graph of the student embeddings.  With a process group the batch is the GLOBAL batch (rows of all ranks)."""
+    from . import pipeline
     if not fused_supported(stu_img, stu_txt, temperature if want_soft else None):
         raise _lib.DistillClipB200Error(
             "fused contrastive path needs CUDA bf16/fp16 [B, D] embeddings with D % 8 == 0 and "
@@ -433,13 +566,30 @@ def clip_contrastive(stu_img, stu_txt, tea_img=None, tea_txt=None, temperature=N
         if ti.shape != si.shape or tt.shape != st.shape:
             raise ValueError("teacher and student embeddings must have the same [B, D] shape on the fused path "
                              f"(student {tuple(si.shape)}, teacher {tuple(ti.shape)})")
-    hard, soft = ClipContrastiveFn.apply(si, st, ti, tt, float(temperature) if want_soft else None, group)
+    s_h, s_s = (float(scale[0]), float(scale[1])) if scale is not None else (1.0, 1.0)
+    p_h, p_s = (float(percent[0]), float(percent[1])) if percent is not None else (0.0, 0.0)
+    T = float(temperature) if want_soft else None
+    xc = pipeline.exchange_for(group)
+    if xc.world > 1:
+        pipeline.check_equal_batches(group, si.shape[0], si.device)
     res = {}
+    if USE_PIPELINE and pipeline.pipeline_supported(_ENGINE, xc, si.shape[0], si.shape[1]):
+        hard, soft, total = ClipPipelineFn.apply(si, st, ti, tt, T, xc, (p_h, p_s, s_h, s_s))
+    else:
+        hard, soft = ClipContrastiveFn.apply(si, st, ti, tt, T, group)
+        hard, soft = hard * s_h, soft * s_s
+        total = hard * p_h + soft * p_s
     if want_hard:
         res["hard_label"] = hard
     if want_soft:
         res["soft_label"] = soft
+    if percent is not None:
+        res["total"] = total
     return res
+
+
+#: False (or DCB_PIPELINE=0): the round-1 flow (one launch per quantity, NCCL collectives) for every shape
+USE_PIPELINE = os.environ.get("DCB_PIPELINE", "1") != "0"
 
 
 # ==============================================================================================

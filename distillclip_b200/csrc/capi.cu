@@ -91,6 +91,16 @@ int dcb_version(void) { return 100; }
 int dcb_compiled_arch(void) { return 100; }
 const char* dcb_last_error(void) { return dcb::error_buffer(); }
 
+// One stream-ordered device-to-device copy (local or peer-mapped addresses: unified addressing resolves the route; peer
+// pulls over NVLink run on the copy engines and leave the SMs to the tensor kernels).
+int dcb_memcpy_async(void* dst, const void* src, int64_t bytes, void* stream) {
+    using namespace dcb;
+    DCB_REQUIRE(dst && src && bytes >= 0, "bad arguments");
+    if (bytes == 0) return 0;
+    DCB_CUDA_OK(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDefault, static_cast<cudaStream_t>(stream)));
+    return 0;
+}
+
 int dcb_finalize(int n_terms, const double* const* partials, const int32_t* counts, const float* scale,
                  const float* percent, float* out, void* stream) {
     using namespace dcb;

@@ -15,6 +15,7 @@
 // (w - 4) / 4-th 32-column chunk of its rows, so every scheduler has two epilogue warps to hide MUFU / FMA latency
 // (one warp per scheduler issued only every ~4 cycles, ncu r01d).
 #include "tc_common.cuh"
+#include "clip_shared.cuh"
 
 namespace dcb {
 
@@ -54,8 +55,12 @@ struct ClipBwdPairParams {
     const float* b_inv_tea;
     const float* coef_row;
     const float* coef_col;
-    const float* gmax_row;
-    const float* gmax_col;
+    const float* gmax_row;    // legacy mode (bounds == nullptr): coefficients already carry the upstream gradients,
+    const float* gmax_col;    //   gmax_row[0] + gmax_col[0] bounds |G|
+    const float* bounds;      // pipeline mode: coef_row / coef_col are UNIT coefficients, multiplied here by the upstream
+    ClipUpstream up;          //   gradients read from the device; bounds[6] fixes the fp16 scale (clip_shared.cuh)
+    int bt_block_cols;        // b_hatT is stored as row blocks [n_blocks][dim][bt_block_cols] (one block per source rank);
+    int bt_block_rows;        //   bt_block_rows = rows of one block (= dim).  One block: bt_block_cols >= cols
     float* acc;               // [n_split][rows][dim] fp32
     __half* g_out;            // optional [rows][g_ld] fp16: the scaled gradient tiles G 2^k for clip_gt_gemm_kernel (else nullptr)
     long long g_ld;
@@ -182,7 +187,10 @@ clip_bwd_pair_kernel(const __grid_constant__ CUtensorMap map_a_stu, const __grid
                     }
                 }
                 if (tt > 0) {                                          // b_hatT slices for the gradient GEMM of tile tt-1
-                    const int j0 = (tile_begin + tt - 1) * NT;
+                    const int jg = (tile_begin + tt - 1) * NT;
+                    const int blk = jg / p.bt_block_cols;                  // tiles never straddle a block (host checks)
+                    const int j0 = jg - blk * p.bt_block_cols;
+                    const int y0 = blk * p.bt_block_rows;
                     for (int sl = 0; sl < p.slices; ++sl) {
                         mbar_wait(bar_empty + 8 * stage, phase ^ 1);
                         const uint32_t dst = ring + stage * C::kStageBytes;
@@ -191,7 +199,7 @@ clip_bwd_pair_kernel(const __grid_constant__ CUtensorMap map_a_stu, const __grid
                         static_assert(kSub == 2, "one K sub-tile of a slice per issuing thread");
                         const int ks = second ? 1 : 0;
                         tma_load_2d_pair(dst + ks * (kSliceRows * kBK * 2), &map_bt, full, j0 + ks * kBK,
-                                         sl * 256 + (int)rank * kSliceRows);
+                                         y0 + sl * 256 + (int)rank * kSliceRows);
                         if (++stage == C::kStages) { stage = 0; phase ^= 1; }
                     }
                 }
@@ -289,10 +297,17 @@ clip_bwd_pair_kernel(const __grid_constant__ CUtensorMap map_a_stu, const __grid
         const float r_t = (kTeacher && row_ok) ? __ldg(p.a_inv_tea + grow) : 0.f;
         const float k1 = r_s * LOG2E, k1t = r_s * LOG2E * p.inv_temp, k2t = r_t * LOG2E * p.inv_temp;
         const float n1 = -LOG2E, n1t = -LOG2E * p.inv_temp;
-        const float ra = row_ok ? __ldg(p.coef_row + grow) : 0.f;
-        const float rbeta = (kTeacher && row_ok) ? __ldg(p.coef_row + p.rows + grow) : 0.f;
-        const float rg = (kTeacher && row_ok) ? __ldg(p.coef_row + 2 * (size_t)p.rows + grow) : 0.f;
-        const float gscale = pair_tile_scale(__ldg(p.gmax_row) + __ldg(p.gmax_col));
+        float up_h = 1.f, up_s = 1.f, gbound;
+        if (p.bounds) {
+            clip_load_upstream(p.up, up_h, up_s);
+            gbound = clip_grad_bound(p.bounds, up_h, up_s);
+        } else {
+            gbound = __ldg(p.gmax_row) + __ldg(p.gmax_col);
+        }
+        const float ra = row_ok ? up_h * __ldg(p.coef_row + grow) : 0.f;
+        const float rbeta = (kTeacher && row_ok) ? up_s * __ldg(p.coef_row + p.rows + grow) : 0.f;
+        const float rg = (kTeacher && row_ok) ? up_s * __ldg(p.coef_row + 2 * (size_t)p.rows + grow) : 0.f;
+        const float gscale = pair_tile_scale(gbound);
         // column scales / coefficients of a tile: fetched one tile ahead into registers (the ~1000 clk of global-load latency
         // sat on the per-tile critical path, trace r01q), parked in shared memory at the top of the tile that uses them
         float pre0 = 0.f, pre1 = 0.f, pre2 = 0.f;
@@ -304,11 +319,11 @@ clip_bwd_pair_kernel(const __grid_constant__ CUtensorMap map_a_stu, const __grid
             if (gc >= p.cols) return;
             if (ep_tid < NT) {
                 pre0 = __ldg(p.b_inv_stu + gc);
-                pre1 = __ldg(p.coef_col + gc);
+                pre1 = up_h * __ldg(p.coef_col + gc);
             } else if (kTeacher) {
                 pre0 = __ldg(p.b_inv_tea + gc);
-                pre1 = __ldg(p.coef_col + p.cols + gc);
-                pre2 = __ldg(p.coef_col + 2 * (size_t)p.cols + gc);
+                pre1 = up_s * __ldg(p.coef_col + p.cols + gc);
+                pre2 = up_s * __ldg(p.coef_col + 2 * (size_t)p.cols + gc);
             }
         };
         fetch_scales(0);
@@ -485,20 +500,24 @@ extern "C" int dcb_clip_pair_splits(int64_t rows_local, int64_t cols, int64_t di
     return dcb::clip_bwd_pair_splits(rows_local, cols, dim);
 }
 
-extern "C" int dcb_clip_row_grads_pair(const void* stu_a, const void* stu_b, const void* tea_a, const void* tea_b,
-                                       const void* stu_b_t, int64_t bt_pitch_elems,
-                                       const float* stu_a_inv, const float* stu_b_inv, const float* tea_a_inv,
-                                       const float* tea_b_inv, const float* coef_row, const float* coef_col,
-                                       const float* gmax_row, const float* gmax_col, int64_t rows_local, int64_t cols,
-                                       int64_t dim, int dtype, float temperature, float* acc_parts, void* g_out,
-                                       int64_t g_pitch_elems, float* dump_s, long long* trace, void* stream) {
-    using namespace dcb;
-    DCB_REQUIRE(stu_a && stu_b && stu_b_t && stu_a_inv && stu_b_inv && coef_row && coef_col && gmax_row && gmax_col && acc_parts,
-                "NULL pointer argument");
+namespace dcb {
+static int clip_pair_launch(const void* stu_a, const void* stu_b, const void* tea_a, const void* tea_b,
+                            const void* stu_b_t, int64_t bt_pitch_elems, int64_t bt_block_cols,
+                            const float* stu_a_inv, const float* stu_b_inv, const float* tea_a_inv,
+                            const float* tea_b_inv, const float* coef_row, const float* coef_col,
+                            const float* gmax_row, const float* gmax_col, const float* bounds, const ClipUpstream& up,
+                            int64_t rows_local, int64_t cols,
+                            int64_t dim, int dtype, float temperature, float* acc_parts, void* g_out,
+                            int64_t g_pitch_elems, float* dump_s, long long* trace, void* stream) {
+    DCB_REQUIRE(stu_a && stu_b && stu_b_t && stu_a_inv && stu_b_inv && coef_row && coef_col && acc_parts &&
+                    (bounds || (gmax_row && gmax_col)), "NULL pointer argument");
+    if (bt_block_cols <= 0 || bt_block_cols >= cols) bt_block_cols = cols;
+    DCB_REQUIRE(bt_block_cols == cols || (bt_block_cols % 128 == 0 && cols % bt_block_cols == 0),
+                "b_hatT blocks must hold a multiple of 128 columns and divide the column count");
     DCB_REQUIRE(dtype == DCB_BF16 || dtype == DCB_F16, "the fused contrastive kernel takes bf16 or fp16 embeddings");
     DCB_REQUIRE(dcb_clip_pair_supported(dim), "pair kernel supports 8 <= dim <= 768, dim %% 8 == 0 (got %lld)", (long long)dim);
     DCB_REQUIRE(rows_local >= 1 && cols >= 1, "bad shape");
-    DCB_REQUIRE(bt_pitch_elems >= cols && bt_pitch_elems % 8 == 0, "bT pitch must be >= cols and a multiple of 8 elements");
+    DCB_REQUIRE(bt_pitch_elems >= bt_block_cols && bt_pitch_elems % 8 == 0, "bT pitch must be >= the block width and a multiple of 8 elements");
     DCB_REQUIRE(!g_out || (g_pitch_elems >= cols && g_pitch_elems % 8 == 0 && reinterpret_cast<uintptr_t>(g_out) % 16 == 0),
                 "G scratch: pitch must be >= cols and a multiple of 8 elements, base 16-byte aligned");
     const bool teacher = tea_a != nullptr;
@@ -515,7 +534,8 @@ extern "C" int dcb_clip_row_grads_pair(const void* stu_a, const void* stu_b, con
         ma_t = ma_s;
         mb_t = mb_s;
     }
-    if (tc::encode_tile_map_16bit(&mbt, stu_b_t, dim, cols, (uint64_t)bt_pitch_elems * 2, bwdp::kSliceRows)) return 1;
+    const int64_t n_blocks = cols / bt_block_cols;
+    if (tc::encode_tile_map_16bit(&mbt, stu_b_t, dim * n_blocks, bt_block_cols, (uint64_t)bt_pitch_elems * 2, bwdp::kSliceRows)) return 1;
     ClipBwdPairParams p{};
     p.a_inv_stu = stu_a_inv;
     p.b_inv_stu = stu_b_inv;
@@ -525,6 +545,10 @@ extern "C" int dcb_clip_row_grads_pair(const void* stu_a, const void* stu_b, con
     p.coef_col = coef_col;
     p.gmax_row = gmax_row;
     p.gmax_col = gmax_col;
+    p.bounds = bounds;
+    p.up = up;
+    p.bt_block_cols = (int)bt_block_cols;
+    p.bt_block_rows = (int)dim;
     p.acc = acc_parts;
     p.g_out = static_cast<__half*>(g_out);
     p.g_ld = g_pitch_elems;
@@ -550,4 +574,34 @@ extern "C" int dcb_clip_row_grads_pair(const void* stu_a, const void* stu_b, con
     const int smem = bwdp::Cfg<128, 1>::smem_bytes();   // D <= 768: 128 + 384 TMEM columns, S/T single buffered
     return teacher ? launch_pair<true, 128, 1>(grid, smem, st, ma_s, mb_s, ma_t, mb_t, mbt, p, idesc_st, idesc_grad)
                    : launch_pair<false, 128, 1>(grid, smem, st, ma_s, mb_s, ma_t, mb_t, mbt, p, idesc_st, idesc_grad);
+}
+}  // namespace dcb
+
+extern "C" int dcb_clip_row_grads_pair(const void* stu_a, const void* stu_b, const void* tea_a, const void* tea_b,
+                                       const void* stu_b_t, int64_t bt_pitch_elems,
+                                       const float* stu_a_inv, const float* stu_b_inv, const float* tea_a_inv,
+                                       const float* tea_b_inv, const float* coef_row, const float* coef_col,
+                                       const float* gmax_row, const float* gmax_col, int64_t rows_local, int64_t cols,
+                                       int64_t dim, int dtype, float temperature, float* acc_parts, void* g_out,
+                                       int64_t g_pitch_elems, float* dump_s, long long* trace, void* stream) {
+    return dcb::clip_pair_launch(stu_a, stu_b, tea_a, tea_b, stu_b_t, bt_pitch_elems, 0, stu_a_inv, stu_b_inv, tea_a_inv, tea_b_inv,
+                                 coef_row, coef_col, gmax_row, gmax_col, nullptr, dcb::ClipUpstream{}, rows_local, cols, dim, dtype,
+                                 temperature, acc_parts, g_out, g_pitch_elems, dump_s, trace, stream);
+}
+
+// Pipeline flavour: UNIT coefficients (dcb_clip_post1 / dcb_clip_post2) times the upstream gradients read from the device, the
+// fp16 scale from bounds[6], and b_hatT stored as one [dim, bt_block_cols] block per source rank (bt_block_cols = B / R).
+extern "C" int dcb_clip_pair_bwd(const void* stu_a, const void* stu_b, const void* tea_a, const void* tea_b,
+                                 const void* stu_b_t, int64_t bt_pitch_elems, int64_t bt_block_cols,
+                                 const float* stu_a_inv, const float* stu_b_inv, const float* tea_a_inv,
+                                 const float* tea_b_inv, const float* coef_row, const float* coef_col, const float* bounds,
+                                 const float* g_total, const float* g_hard, const float* g_soft, float w_hard, float w_soft,
+                                 float s_hard, float s_soft, int64_t rows_local, int64_t cols, int64_t dim, int dtype,
+                                 float temperature, float* acc_parts, void* g_out, int64_t g_pitch_elems, void* stream) {
+    using namespace dcb;
+    DCB_REQUIRE(bounds, "NULL bounds");
+    return clip_pair_launch(stu_a, stu_b, tea_a, tea_b, stu_b_t, bt_pitch_elems, bt_block_cols, stu_a_inv, stu_b_inv, tea_a_inv,
+                            tea_b_inv, coef_row, coef_col, nullptr, nullptr, bounds,
+                            ClipUpstream{g_total, g_hard, g_soft, w_hard, w_soft, s_hard, s_soft}, rows_local, cols, dim, dtype,
+                            temperature, acc_parts, g_out, g_pitch_elems, nullptr, nullptr, stream);
 }

@@ -62,7 +62,9 @@ struct ClipFwdParams {
     float* dump_s;            // optional [rows, cols] raw logits (tests only), else nullptr
     float* dump_t;
     int rows, cols, dim;
-    int row_offset;           // global index of local row 0 (labels = arange(B): the diagonal is global)
+    int row_offset;           // column (relative to b-side row 0 of THIS launch) holding the label of local row 0: labels are
+                              // arange(B) over the global batch, so this is (global row offset) - (first column of the chunk)
+    int col_part_ld;          // columns per statistic row of col_part (= cols unless the launch covers a chunk of the columns)
     int n_split, col_tiles;
     float inv_temp;           // 1/T
 };
@@ -236,7 +238,7 @@ clip_fwd_kernel(const __grid_constant__ CUtensorMap map_a_stu, const __grid_cons
             for (int o = ep_tid; o < 4 * kBN; o += kEpiThreads) {
                 const int st = o / kBN, c = o % kBN;
                 if (pcol0 + c < p.cols && (kTeacher || st == 0))
-                    p.col_part[((size_t)rb * 4 + st) * p.cols + pcol0 + c] =
+                    p.col_part[((size_t)rb * 4 + st) * p.col_part_ld + pcol0 + c] =
                         (cb[(0 * 4 + st) * kBN + c] + cb[(1 * 4 + st) * kBN + c]) + (cb[(2 * 4 + st) * kBN + c] + cb[(3 * 4 + st) * kBN + c]);
             }
         };
@@ -290,7 +292,7 @@ clip_fwd_kernel(const __grid_constant__ CUtensorMap map_a_stu, const __grid_cons
                         for (int c = 0; c < 16; ++c) {
                             const int gc = col0 + cbase + c;
                             const float s = sv[c] * r_s;
-                            if (gc == diag_col) { diag = s; have_diag = true; }
+                            if (gc == diag_col && gc < p.cols) { diag = s; have_diag = true; }
                             if (p.dump_s && row_ok && gc < p.cols) p.dump_s[(size_t)grow * p.cols + gc] = s;
                             if (!(gc < p.cols && row_ok)) e[c] = 0.f;
                         }
@@ -486,12 +488,15 @@ static int clip_row_stats_impl(const void* stu_a, const void* stu_b, const void*
                                const float* tea_b_inv, int64_t rows_local, int64_t row_offset, int64_t cols,
                                int64_t dim, int dtype, float temperature, float* stats, double* rowloss,
                                float* col_stats, void* workspace, float* dump_s, float* dump_t, const float* rank_ref,
-                               void* stream) {
-    DCB_REQUIRE(stu_a && stu_b && stu_a_inv && stu_b_inv && stats && rowloss && workspace, "NULL pointer argument");
+                               void* stream, float* chunk_ws = nullptr, float* chunk_diag = nullptr, float* chunk_col_part = nullptr,
+                               int64_t chunk_col_part_ld = 0) {
+    const bool chunk_mode = chunk_ws != nullptr;     // tiles only: partial sums into caller-owned buffers, no combine / colreduce
+    DCB_REQUIRE(stu_a && stu_b && stu_a_inv && stu_b_inv && (chunk_mode || (stats && rowloss && workspace)), "NULL pointer argument");
     DCB_REQUIRE(dtype == DCB_BF16 || dtype == DCB_F16, "the fused contrastive kernel takes bf16 or fp16 embeddings");
     DCB_REQUIRE(rows_local >= 1 && cols >= 1 && dim >= 8 && dim % 8 == 0, "bad shape rows=%lld cols=%lld dim=%lld (dim %% 8 == 0)",
                 (long long)rows_local, (long long)cols, (long long)dim);
     DCB_REQUIRE(rows_local < (1ll << 30) && cols < (1ll << 30), "batch too large");
+    DCB_REQUIRE(row_offset > -(1ll << 30) && row_offset < (1ll << 30), "row offset out of range");
     const bool teacher = tea_a != nullptr;
     if (teacher) {
         DCB_REQUIRE(tea_b && tea_a_inv && tea_b_inv, "teacher pointers must be all set or all NULL");
@@ -519,9 +524,18 @@ static int clip_row_stats_impl(const void* stu_a, const void* stu_b, const void*
     p.row_offset = (int)row_offset;
     p.n_split = clip_fwd_splits(rows_local, cols);
     p.col_tiles = (int)((cols + fwd::kBN - 1) / fwd::kBN);
-    p.ws = static_cast<float*>(workspace);
-    p.diag = p.ws + (size_t)p.n_split * fwd::kSubs * 4 * rows_local;
-    p.col_part = col_stats ? p.diag + rows_local : nullptr;
+    if (chunk_mode) {
+        p.ws = chunk_ws;
+        p.diag = chunk_diag;
+        p.col_part = chunk_col_part;
+        p.col_part_ld = (int)chunk_col_part_ld;
+        col_stats = chunk_col_part;                 // selects the column-sum instantiation below
+    } else {
+        p.ws = static_cast<float*>(workspace);
+        p.diag = p.ws + (size_t)p.n_split * fwd::kSubs * 4 * rows_local;
+        p.col_part = col_stats ? p.diag + rows_local : nullptr;
+        p.col_part_ld = (int)cols;
+    }
     p.dump_s = dump_s;
     p.dump_t = dump_t;
     p.rank_ref = rank_ref;
@@ -555,6 +569,7 @@ static int clip_row_stats_impl(const void* stu_a, const void* stu_b, const void*
     else DCB_LAUNCH_FWD(false, false)
 #undef DCB_LAUNCH_FWD
     DCB_CUDA_OK(cudaGetLastError());
+    if (chunk_mode) return 0;
     clip_combine_kernel<<<(unsigned)((rows_local * 4 + 127) / 128), 128, 0, st>>>(p.ws, p.diag, stats, rowloss, (int)rows_local,
                                                                                fwd::kSubs * p.n_split, temperature, teacher ? 1 : 0);
     DCB_CUDA_OK(cudaGetLastError());
@@ -575,6 +590,25 @@ extern "C" int dcb_clip_row_stats(const void* stu_a, const void* stu_b, const vo
     return dcb::clip_row_stats_impl(stu_a, stu_b, tea_a, tea_b, stu_a_inv, stu_b_inv, tea_a_inv, tea_b_inv, rows_local, row_offset,
                                     cols, dim, dtype, temperature, stats, rowloss, col_stats, workspace, dump_s, dump_t, nullptr,
                                     stream);
+}
+
+// Tiles only, for a chunk of the columns (the b-side rows of one source rank): partial row sums of the chunk into
+// ws_chunk[parts][4][rows] (parts = dcb_clip_fwd_chunk_parts), S_ii into diag[rows] where the label falls inside the chunk,
+// column sums of the chunk into col_part_chunk[row_blocks][4][col_part_ld] (pointer already advanced to the chunk's first
+// column).  label_col0 = (global index of local row 0) - (global index of the chunk's first column).  dcb_clip_post1 reduces.
+extern "C" int dcb_clip_fwd_chunk_parts(int64_t rows_local, int64_t cols_chunk) {
+    return dcb::clip_fwd_splits(rows_local, cols_chunk) * dcb::fwd::kSubs;
+}
+extern "C" int dcb_clip_fwd_chunk(const void* stu_a, const void* stu_b, const void* tea_a, const void* tea_b,
+                                  const float* stu_a_inv, const float* stu_b_inv, const float* tea_a_inv,
+                                  const float* tea_b_inv, int64_t rows_local, int64_t label_col0, int64_t cols_chunk,
+                                  int64_t dim, int dtype, float temperature, float* ws_chunk, float* diag,
+                                  float* col_part_chunk, int64_t col_part_ld, void* stream) {
+    using namespace dcb;
+    DCB_REQUIRE(ws_chunk && diag && col_part_chunk && col_part_ld >= cols_chunk, "NULL / bad chunk buffers");
+    return clip_row_stats_impl(stu_a, stu_b, tea_a, tea_b, stu_a_inv, stu_b_inv, tea_a_inv, tea_b_inv, rows_local, label_col0,
+                               cols_chunk, dim, dtype, temperature, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
+                               stream, ws_chunk, diag, col_part_chunk, col_part_ld);
 }
 
 extern "C" int dcb_clip_rank_counts(const void* a, const void* b, const float* a_inv, const float* b_inv, int64_t rows_local,

@@ -19,6 +19,7 @@ import torch
 from torch import nn
 
 from .. import contrastive, ops
+from .._lib import DistillClipB200Error
 from .component.output import CLIPOutput, ControlOutput, TextTransformerOutput, VisionTransformerOutput
 from .loss_component import (AttentionProbsKL, AttentionProbsMSE, AttentionScoreMSE, CLIPCosDiff, EmbedMSELoss,
                              HardLabel, HiddenMSE, LastValueMapKL, LogitsMSE, OutCELoss, OutCosLoss, OutKLLoss, OutL1Loss, SoftLabel)
@@ -200,20 +201,35 @@ class LossCalculator(nn.Module):
         want_hard, want_soft = 'hard_label' in self.loss, 'soft_label' in self.loss
         if want_soft:
             assert self.temperature
+        stu_img, stu_txt = stu_out.visual_output.last_representation, stu_out.text_output.last_representation
+        tea_img = tea_out.visual_output.last_representation if want_soft else None
+        tea_txt = tea_out.text_output.last_representation if want_soft else None
         fused = {}
         if (want_hard or want_soft) and self.fused_contrastive and contrastive.fused_supported(
-                stu_out.visual_output.last_representation, stu_out.text_output.last_representation,
-                self.temperature if want_soft else None):
-            fused = contrastive.clip_contrastive(
-                stu_out.visual_output.last_representation, stu_out.text_output.last_representation,
-                tea_out.visual_output.last_representation if want_soft else None,
-                tea_out.text_output.last_representation if want_soft else None,
-                self.temperature if want_soft else None, want_hard, want_soft, group=self.contrastive_group)
+                stu_img, stu_txt, self.temperature if want_soft else None, tea_img, tea_txt):
+            # scale / percent of reference _loss.py:231-234 applied on the device; a name missing from loss_scale (after
+            # set_scale with a partial dict) is neither scaled nor added, exactly like the reference's loop over loss_scale
+            def weight(name):
+                if name not in self.loss or name not in self.loss_scale:
+                    return 1.0, 0.0
+                return float(self.loss_scale[name]), float(self.percent[name])
+            (s_h, p_h), (s_s, p_s) = weight('hard_label'), weight('soft_label')
+            fused = contrastive.clip_contrastive(stu_img, stu_txt, tea_img, tea_txt, self.temperature if want_soft else None,
+                                                 want_hard, want_soft, group=self.contrastive_group,
+                                                 percent=(p_h, p_s), scale=(s_h, s_s))
+
+        def logits_of(out, who):
+            if out.i2t_logits is None or out.t2i_logits is None:
+                raise DistillClipB200Error(
+                    f"{who} CLIPOutput carries no logits (LazyLogitsCLIP?) but '{loss_name}' cannot run on the fused path here: "
+                    "it needs CUDA bf16/fp16 [B, D] embeddings with D % 8 == 0, a teacher of the same shape and "
+                    f"temperature >= {contrastive.MIN_FUSED_TEMPERATURE}; materialise the logits or fix the inputs")
+            return out.i2t_logits, out.t2i_logits
         for loss_name in self.loss_name:
             if loss_name in ('cos_diff', 'logits_mse'):     # reference _loss.py:138-145, on the caller's materialised logits
                 loss = self.loss[loss_name]
-                cal_res[loss_name] = 0.5 * (loss(stu_out.i2t_logits, tea_out.i2t_logits)
-                                            + loss(stu_out.t2i_logits, tea_out.t2i_logits))
+                (s_i2t, s_t2i), (t_i2t, t_t2i) = logits_of(stu_out, 'student'), logits_of(tea_out, 'teacher')
+                cal_res[loss_name] = 0.5 * (loss(s_i2t, t_i2t) + loss(s_t2i, t_t2i))
                 continue
             if loss_name not in ('hard_label', 'soft_label'):
                 continue
@@ -221,17 +237,25 @@ class LossCalculator(nn.Module):
                 cal_res[loss_name] = fused[loss_name]
             elif loss_name == 'hard_label':
                 loss = self.loss[loss_name]
-                cal_res[loss_name] = 0.5 * (loss(stu_out.i2t_logits) + loss(stu_out.t2i_logits))
+                s_i2t, s_t2i = logits_of(stu_out, 'student')
+                cal_res[loss_name] = 0.5 * (loss(s_i2t) + loss(s_t2i))
             else:
                 loss = self.loss[loss_name]
-                cal_res[loss_name] = 0.5 * (loss(stu_out.i2t_logits, tea_out.i2t_logits)
-                                            + loss(stu_out.t2i_logits, tea_out.t2i_logits))
+                (s_i2t, s_t2i), (t_i2t, t_t2i) = logits_of(stu_out, 'student'), logits_of(tea_out, 'teacher')
+                cal_res[loss_name] = 0.5 * (loss(s_i2t, t_i2t) + loss(s_t2i, t_t2i))
 
         loss = 0.5 * (image_loss + text_loss)
+        fused_pending = 'total' in fused
         for (loss_name, scale) in self.loss_scale.items():
-            if loss_name in IMAGE_TEXT_LOSS:
-                cal_res[loss_name] = cal_res[loss_name] * scale
-                loss += cal_res[loss_name] * self.percent[loss_name]
+            if loss_name not in IMAGE_TEXT_LOSS:
+                continue
+            if loss_name in fused:                          # already scaled; their weighted sum was formed on the device
+                if fused_pending:
+                    loss = loss + fused['total']
+                    fused_pending = False
+                continue
+            cal_res[loss_name] = cal_res[loss_name] * scale
+            loss += cal_res[loss_name] * self.percent[loss_name]
         return loss, cal_res
 
     def forward(self, stu_out: Union[CLIPOutput, VisionTransformerOutput, TextTransformerOutput],

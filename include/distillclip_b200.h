@@ -237,6 +237,75 @@ int dcb_clip_grad_finish(const float* acc_parts, int n_split, const void* stu_a,
                          const float* gmax_col, int in_dtype, void* grad_a, int grad_dtype, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Fused contrastive PIPELINE (distillclip_b200/pipeline.py): the same tcgen05 kernels driven by four small fused kernels,
+ * 7 launches per fwd+bwd on one GPU, and on N GPUs three peer-memory exchanges with one barrier each instead of collectives.
+ * Replaces, for the GLOBAL batch: clip_model.py:36-44 (normalise + matmul), hard_label.py:10-12, soft_label.py:11-16, the
+ * 0.5 (i2t + t2i) sums and the scale / percent weighting of _loss.py:130-137,231-234, and autograd through all of it.
+ * --------------------------------------------------------------------------------------------- */
+/* stream-ordered device-to-device copy (peer-mapped source: a copy-engine pull over NVLink) */
+int dcb_memcpy_async(void* dst, const void* src, int64_t bytes, void* stream);
+
+/* prep: for up to 4 matrices [rows, dim] (bf16/fp16, 16-byte aligned): inv_norm[k][i] = 1/||x_i|| (clip_model.py:37-38);
+ * copy_out[k] (optional) = the raw rows (this rank's slice of the buffer peers pull from); tr_out[k] (optional) = fp16
+ * [dim, tr_pitch_elems[k]] = (x * inv_norm).T, the K-major operand of the gradient GEMMs. */
+int dcb_clip_prep(int n_mats, const void* const* mats, float* const* inv_norm, void* const* copy_out, void* const* tr_out,
+                  const int64_t* tr_pitch_elems, int64_t rows, int64_t dim, int dtype, void* stream);
+
+/* Similarity tiles of the local rows against ONE chunk of the columns (the text rows of one source rank): partial row sums
+ * into ws_chunk[dcb_clip_fwd_chunk_parts(...)][4][rows], S_ii into diag[rows] where the label column
+ * (label_col0 + i, relative to the chunk) falls inside the chunk, column sums into
+ * col_part_chunk[ceil(rows/128)][4][col_part_ld] (pointer advanced to the chunk's first column). */
+int dcb_clip_fwd_chunk_parts(int64_t rows_local, int64_t cols_chunk);
+int dcb_clip_fwd_chunk(const void* stu_a, const void* stu_b, const void* tea_a, const void* tea_b,
+                       const float* stu_a_inv, const float* stu_b_inv, const float* tea_a_inv, const float* tea_b_inv,
+                       int64_t rows_local, int64_t label_col0, int64_t cols_chunk, int64_t dim, int dtype, float temperature,
+                       float* ws_chunk, float* diag, float* col_part_chunk, int64_t col_part_ld, void* stream);
+
+/* Statistics slot exchanged between ranks, in floats: [4][cols] column sums | [rows_per_rank] S_ii | 2 doubles
+ * {sum CE_i2t, sum KL_i2t / T^2} | 4 floats {max of the three unit coefficients, 0}. */
+int64_t dcb_clip_slot_floats(int64_t cols, int64_t rows_per_rank);
+int64_t dcb_clip_post_scratch_bytes(int64_t rows, int64_t cols);   /* zero-initialised once; the kernels reset their ticket */
+
+/* post1: row statistics stats[5][rows] of the local rows (fixed-order sum of the n_part partial sets), UNIT gradient
+ * coefficients coef_row[3][rows] = {1/(2 B A_i), T/(2 Zs_i), T/(2 Zt_i)} (no upstream gradient in them), and this rank's slot
+ * (column sums over its rows, S_ii, i2t loss sums, maxima) stored into dest_slots[0..n_dest): this rank's slot inside every
+ * rank's slot buffer (peer-mapped addresses: NVLink stores; n_dest = 1 with a local buffer when a collective follows). */
+int dcb_clip_post1(const float* ws, int n_part, const float* diag, const float* col_part, int row_blocks, int64_t rows,
+                   int64_t cols, float temperature, int has_teacher, int64_t global_batch, float* stats, float* coef_row,
+                   void* const* dest_slots, int n_dest, void* scratch, void* stream);
+
+/* post2 (after the cross-rank barrier): slots[n_src][dcb_clip_slot_floats] summed in source order -> col_stats[4][cols],
+ * coef_col[3][cols] (unit coefficients of the t2i direction), bounds[6] = maxima over all rows / all columns (they fix the
+ * fp16 scale of the gradient tiles), out[5] = {hard, soft, hard * s_hard, soft * s_soft, p_hard * out[2] + p_soft * out[3]}
+ * with hard = 0.5 (CE_i2t + CE_t2i) (mean), soft = 0.5 T^2 (KL_i2t + KL_t2i) (sum) of the GLOBAL batch (_loss.py:130-137,231-234). */
+int dcb_clip_post2(const float* slots, int n_src, int64_t rows_per_src, int64_t cols, float temperature, int has_teacher,
+                   int64_t global_batch, float p_hard, float p_soft, float s_hard, float s_soft, float* col_stats,
+                   float* coef_col, float* bounds, float* out, void* scratch, void* stream);
+
+/* Backward, first kernel: as dcb_clip_row_grads_pair, but with UNIT coefficients multiplied on the device by
+ *   up_hard = *g_total * w_hard + *g_hard * s_hard,  up_soft = *g_total * w_soft + *g_soft * s_soft
+ * (0-dim fp32 device scalars from autograd, NULL = no gradient for that output; w = percent * scale), the fp16 tile scale
+ * from bounds[6], and stu_b_t stored as one [dim, bt_block_cols] block per source rank ([cols / bt_block_cols][dim][pitch]). */
+int dcb_clip_pair_bwd(const void* stu_a, const void* stu_b, const void* tea_a, const void* tea_b,
+                      const void* stu_b_t, int64_t bt_pitch_elems, int64_t bt_block_cols,
+                      const float* stu_a_inv, const float* stu_b_inv, const float* tea_a_inv, const float* tea_b_inv,
+                      const float* coef_row, const float* coef_col, const float* bounds,
+                      const float* g_total, const float* g_hard, const float* g_soft, float w_hard, float w_soft,
+                      float s_hard, float s_soft, int64_t rows_local, int64_t cols, int64_t dim, int dtype,
+                      float temperature, float* acc_parts, void* g_out, int64_t g_pitch_elems, void* stream);
+
+/* Backward, last kernel, both towers in one launch (side a = image rows from the pair kernel's accumulators, side b = text
+ * rows from the G^T GEMM's): grad[i,:] = r_i (acc_i - x_hat_i (x_hat_i . acc_i)), acc_i = 2^-k sum_s acc[s][i,:] - (up_hard / B)
+ * y_hat_{label_offset + i}.  A side with grad == NULL is skipped. */
+int dcb_clip_finish2(const float* acc_a, int n_split_a, int64_t split_stride_a, const void* a, const float* a_inv, void* grad_a,
+                     int64_t rows_a, const void* a_label, const float* a_label_inv, int64_t a_label_rows, int64_t a_label_offset,
+                     const float* acc_b, int n_split_b, int64_t split_stride_b, const void* b, const float* b_inv, void* grad_b,
+                     int64_t rows_b, const void* b_label, const float* b_label_inv, int64_t b_label_rows, int64_t b_label_offset,
+                     int64_t dim, int64_t global_batch, const float* g_total, const float* g_hard, const float* g_soft,
+                     float w_hard, float w_soft, float s_hard, float s_soft, const float* bounds, int in_dtype, int grad_dtype,
+                     void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Per-module API on MATERIALISED logits (HardLabel / SoftLabel keep their logits signature).
  * logits: [n, n] with element strides (row_stride, col_stride) so that `logits.T` views work.
  * mode 0 = HardLabel (hard_label.py:10-12), mode 1 = SoftLabel (soft_label.py:11-16),

@@ -118,3 +118,128 @@ class DoubleEngine:
                            gmax_row, gmax_col, temperature, g_out)
         return self.finish_grads(acc, a_s, a_s_inv, b_s, b_s_inv, gmax_row, gmax_col, row_offset, global_batch,
                                  upstream, grad_dtype)
+
+    # ------------------------------------------------------------------------------------------
+    # pipeline flavour (distillclip_b200/pipeline.py): same stage boundaries and slot layout as the CUDA kernels
+    # ------------------------------------------------------------------------------------------
+    slot_dtype = stat_dtype = tr_dtype = torch.float64
+
+    def gt_splits(self, rows, cols, dim):
+        return 1
+
+    def fwd_parts(self, rows, cols_chunk):
+        return 1
+
+    def prep(self, mats, invs, copies, trs):
+        for m, inv, c, t in zip(mats, invs, copies, trs):
+            r = 1.0 / m.double().norm(dim=1)
+            inv.copy_(r)
+            if c is not None:
+                c.copy_(m)
+            if t is not None:
+                t.zero_()
+                t[:, :m.shape[0]] = (m.double() * r[:, None]).t()
+
+    def fwd_chunk(self, a_s, b_s, a_t, b_t, a_s_inv, b_s_inv, a_t_inv, b_t_inv, label_col0, temperature, ws_chunk, diag,
+                  col_part_chunk, col_part_ld):
+        S = self._logits(a_s, b_s, a_s_inv, b_s_inv)
+        rows, cols = S.shape
+        ws_chunk.zero_()
+        col_part_chunk.zero_()
+        e1 = torch.exp(S - 1)
+        ws_chunk[0, 0], col_part_chunk[0, 0] = e1.sum(1), e1.sum(0)
+        lab = label_col0 + torch.arange(rows)
+        hit = (lab >= 0) & (lab < cols)
+        diag[hit] = S[torch.arange(rows)[hit], lab[hit]]
+        if a_t is not None:
+            T = self._logits(a_t, b_t, a_t_inv, b_t_inv)
+            et, es = torch.exp((T - 1) / temperature), torch.exp((S - 1) / temperature)
+            q = es - et + et * (T - S) / temperature
+            ws_chunk[0, 1], col_part_chunk[0, 1] = q.sum(1), q.sum(0)
+            ws_chunk[0, 2], col_part_chunk[0, 2] = et.sum(1), et.sum(0)
+            ws_chunk[0, 3], col_part_chunk[0, 3] = (et * (T - S)).sum(1), (et * (T - S)).sum(0)
+
+    @staticmethod
+    def _unit_coefs(st, global_batch, temperature, has_teacher):
+        c = torch.zeros(3, st.shape[1], dtype=torch.float64)
+        c[0] = 0.5 / (global_batch * st[0])
+        if has_teacher:
+            c[1] = 0.5 * temperature / (st[2] + st[1] - st[3] / temperature)
+            c[2] = 0.5 * temperature / st[2]
+        return c
+
+    def post1(self, ws, diag, col_part, temperature, has_teacher, global_batch, stats, coef_row, dests):
+        from distillclip_b200.pipeline import slot_floats, slot_tail
+        rows, cols = diag.shape[0], col_part.shape[2]
+        stats[:4] = ws.sum(0)
+        stats[4] = diag
+        rl = self._rowloss(stats, temperature, has_teacher)
+        coef_row.copy_(self._unit_coefs(stats, global_batch, temperature, has_teacher))
+        slot = torch.zeros(slot_floats(cols, rows), dtype=torch.float64)
+        slot[:4 * cols] = col_part.sum(0).reshape(-1)
+        slot[4 * cols:4 * cols + rows] = diag
+        tail = slot_tail(cols, rows)
+        slot[tail], slot[tail + 1] = rl[0].sum(), rl[1].sum()
+        slot[tail + 4:tail + 7] = coef_row.max(1).values
+        for d in dests:
+            d.copy_(slot)
+
+    def post2(self, slots, rows_per_src, cols, temperature, has_teacher, weights):
+        from distillclip_b200.pipeline import slot_tail
+        n_src = slots.shape[0]
+        tail = slot_tail(cols, rows_per_src)
+        st = torch.zeros(5, cols, dtype=torch.float64)
+        st[:4] = slots[:, :4 * cols].reshape(n_src, 4, cols).sum(0)
+        st[4] = slots[:, 4 * cols:4 * cols + rows_per_src].reshape(-1)
+        rl = self._rowloss(st, temperature, has_teacher)
+        coef_col = self._unit_coefs(st, cols, temperature, has_teacher)
+        hard = 0.5 * (slots[:, tail].sum() + rl[0].sum()) / cols
+        soft = 0.5 * (temperature or 1.0) ** 2 * (slots[:, tail + 1].sum() + rl[1].sum())
+        p_h, p_s, s_h, s_s = weights
+        out = torch.stack([hard, soft, hard * s_h, soft * s_s, hard * s_h * p_h + soft * s_s * p_s])
+        bounds = torch.cat([slots[:, tail + 4:tail + 7].max(0).values, coef_col.max(1).values])
+        return st[:4].clone(), coef_col, bounds, out
+
+    @staticmethod
+    def _ups(up):
+        g_t, g_h, g_s, w_h, w_s, s_h, s_s = up
+        f = lambda g: 0.0 if g is None else float(g)
+        return f(g_t) * w_h + f(g_h) * s_h, f(g_t) * w_s + f(g_s) * s_s
+
+    @staticmethod
+    def _scale2(bounds, up_h, up_s):
+        gmax = abs(up_h) * (bounds[0] + bounds[3]) + abs(up_s) * (bounds[1] + bounds[2] + bounds[4] + bounds[5])
+        return 2.0 ** (14 - torch.frexp(gmax)[1].item()) if float(gmax) > 0 else 1.0
+
+    def pair_bwd(self, a_s, b_s, a_t, b_t, bt_all, a_s_inv, b_s_inv, a_t_inv, b_t_inv, coef_row, coef_col, bounds, up,
+                 temperature, g_out):
+        up_h, up_s = self._ups(up)
+        S = self._logits(a_s, b_s, a_s_inv, b_s_inv)
+        G = torch.exp(S - 1) * up_h * (coef_row[0][:, None] + coef_col[0][None, :])
+        if a_t is not None:
+            T = self._logits(a_t, b_t, a_t_inv, b_t_inv)
+            G = G + torch.exp((S - 1) / temperature) * up_s * (coef_row[1][:, None] + coef_col[1][None, :])
+            G = G - torch.exp((T - 1) / temperature) * up_s * (coef_row[2][:, None] + coef_col[2][None, :])
+        scale = self._scale2(bounds, up_h, up_s)
+        assert float((G.abs() * scale).max()) <= 2.0 ** 14
+        if g_out is not None:
+            g_out[:, :G.shape[1]] = G * scale
+        n = b_s.shape[0] // bt_all.shape[0]
+        b_hat_t = torch.cat([bt_all[r][:, :n] for r in range(bt_all.shape[0])], dim=1)        # [D, B]
+        return ((G * scale) @ b_hat_t.t())[None]
+
+    def finish2(self, side_a, side_b, global_batch, up, bounds, grad_dtype):
+        up_h, up_s = self._ups(up)
+        scale = self._scale2(bounds, up_h, up_s)
+        out = []
+        for sd in (side_a, side_b):
+            if sd is None:
+                out.append(None)
+                continue
+            x, x_inv = sd["x"].double(), sd["x_inv"]
+            acc = sd["acc"].sum(0) / scale
+            gi = sd["label_offset"] + torch.arange(x.shape[0])
+            acc = acc - (up_h / global_batch) * sd["y_inv"][gi][:, None] * sd["y"].double()[gi]
+            x_hat = x * x_inv[:, None]
+            out.append(x_inv[:, None] * (acc - x_hat * (x_hat * acc).sum(1, keepdim=True)))
+        return out[0], out[1]

@@ -123,3 +123,139 @@ def test_retrieval_metrics_sharded_world2_gloo():
     for _, got in res:
         for k, v in got.items():
             assert v == pytest.approx(float(g[f"{k}_f64"]), rel=1e-6, abs=1e-9), k
+
+
+# ----------------------------------------------------------------------------------------------
+# the pipeline flow (distillclip_b200/pipeline.py): stage boundaries, slot layout, exchanges, buffer-set bookkeeping
+# ----------------------------------------------------------------------------------------------
+def _run_pipeline(g, weights, ups, group=None, rows=slice(None), hard_only=False):
+    from distillclip_b200 import pipeline as pl
+    T = float(g["temperature"])
+    si, st = torch.tensor(g["stu_img"])[rows].double(), torch.tensor(g["stu_txt"])[rows].double()
+    ti, tt = (None, None) if hard_only else (torch.tensor(g["tea_img"])[rows].double(), torch.tensor(g["tea_txt"])[rows].double())
+    eng = DoubleEngine()
+    xc = pl.LocalExchange() if group is None else pl.CollectiveExchange(group)
+    out, saved = pl.pipeline_forward(eng, xc, si, st, ti, tt, None if hard_only else T, weights)
+    gi, gt = pl.pipeline_backward(eng, saved, ups)
+    return out, gi, gt, xc, saved
+
+
+@pytest.mark.parametrize("name", CLIP)
+def test_pipeline_decomposition_matches_reference_golden(name):
+    g = golden(name)
+    one = torch.tensor(1.0)
+    out, gi, gt, _, _ = _run_pipeline(g, (1.0, 0.0, 1.0, 1.0), (one, None, None))
+    assert float(out[0]) == pytest.approx(float(g["hard_f64"]), rel=1e-10)
+    assert float(out[1]) == pytest.approx(float(g["soft_f64"]), rel=1e-9)
+    assert rel_l2(gi.numpy(), g["dhard_img_f64"]) <= 1e-9
+    assert rel_l2(gt.numpy(), g["dhard_txt_f64"]) <= 1e-9
+    out, gi, gt, _, _ = _run_pipeline(g, (0.0, 1.0, 1.0, 1.0), (one, None, None))
+    assert rel_l2(gi.numpy(), g["dsoft_img_f64"]) <= 1e-8
+    assert rel_l2(gt.numpy(), g["dsoft_txt_f64"]) <= 1e-8
+
+
+def test_pipeline_weighting_and_upstream_routes():
+    """out = {hard, soft, hard s_h, soft s_s, p_h hard s_h + p_s soft s_s} (reference _loss.py:231-234); gradients for an
+    upstream on `total` plus one on the scaled soft term = the oracle with the combined weights."""
+    g = golden(CLIP[1])
+    T = float(g["temperature"])
+    p_h, p_s, s_h, s_s = 0.3, 0.7, 2.0, 0.25
+    g_total, g_soft = torch.tensor(1.5), torch.tensor(-0.5)
+    out, gi, gt, _, _ = _run_pipeline(g, (p_h, p_s, s_h, s_s), (g_total, None, g_soft))
+    hard, soft = float(g["hard_f64"]), float(g["soft_f64"])
+    assert out.numpy() == pytest.approx([hard, soft, hard * s_h, soft * s_s, p_h * hard * s_h + p_s * soft * s_s], rel=1e-9)
+    ref = cf.contrastive_from_embeddings(g["stu_img"], g["stu_txt"], g["tea_img"], g["tea_txt"], T,
+                                         w_hard=1.5 * p_h * s_h, w_soft=1.5 * p_s * s_s - 0.5 * s_s)
+    assert rel_l2(gi.numpy(), ref["d_img"]) <= 1e-8 and rel_l2(gt.numpy(), ref["d_txt"]) <= 1e-8
+
+
+def test_pipeline_hard_only_and_buffer_sets():
+    from distillclip_b200 import pipeline as pl
+    g = golden(CLIP[0])
+    out, gi, gt, xc, saved = _run_pipeline(g, (1.0, 0.0, 1.0, 1.0), (torch.tensor(1.0), None, None), hard_only=True)
+    assert float(out[0]) == pytest.approx(float(g["hard_f64"]), rel=1e-10) and float(out[1]) == 0.0
+    assert rel_l2(gi.numpy(), g["dhard_img_f64"]) <= 1e-9
+    with pytest.raises(RuntimeError, match="already ran"):                 # buffers were released by the first backward
+        pl.pipeline_backward(DoubleEngine(), saved, (torch.tensor(1.0), None, None))
+    # more than MAX_SETS forwards in flight: the oldest is recycled and its backward refuses to run on overwritten buffers
+    eng, xc = DoubleEngine(), pl.LocalExchange()
+    si, st = torch.tensor(g["stu_img"]).double(), torch.tensor(g["stu_txt"]).double()
+    fw = [pl.pipeline_forward(eng, xc, si, st, None, None, None)[1] for _ in range(pl.MAX_SETS + 1)]
+    with pytest.raises(RuntimeError, match="recycled"):
+        pl.pipeline_backward(eng, fw[0], (torch.tensor(1.0), None, None))
+    gi2, _ = pl.pipeline_backward(eng, fw[-1], (torch.tensor(1.0), None, None))
+    assert rel_l2(gi2.numpy(), g["dhard_img_f64"]) <= 1e-9
+
+
+def _pipeline_worker(rank, world, port, name, q):
+    import torch.distributed as dist
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    from distillclip_b200 import pipeline as pl
+    g = golden(name)
+    b = g["stu_img"].shape[0] // world
+    pl.check_equal_batches(dist.group.WORLD, b, torch.device("cpu"))
+    res = []
+    for step in range(3):                          # three steps: buffer sets are reused, results must not change
+        out, gi, gt, _, _ = _run_pipeline(g, (0.75, 0.5, 1.0, 1.0), (torch.tensor(1.0), None, None), group=dist.group.WORLD,
+                                          rows=slice(rank * b, (rank + 1) * b))
+        res.append((out.numpy(), gi.numpy(), gt.numpy()))
+    q.put((rank, res))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("name,world", [("clip_b24_d32_t2", 2), ("clip_b40_d64_t4", 2), ("clip_b24_d32_t2", 3)])
+def test_pipeline_row_sharded_gloo(name, world):
+    """The pipeline's three exchanges (text rows, statistics slots, text-gradient partial sums) under gloo with the
+    collective-based exchange: every rank obtains the global losses; gradients concatenate to the oracle's."""
+    g = golden(name)
+    T = float(g["temperature"])
+    ref = cf.contrastive_from_embeddings(g["stu_img"], g["stu_txt"], g["tea_img"], g["tea_txt"], T, w_hard=0.75, w_soft=0.5)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() + 31 * world) % 2000
+    procs = [ctx.Process(target=_pipeline_worker, args=(r, world, port, name, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in range(world)], key=lambda x: x[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for step in range(3):
+        for rank, steps in res:
+            out = steps[step][0]
+            assert float(out[0]) == pytest.approx(ref["hard"], rel=1e-10)
+            assert float(out[1]) == pytest.approx(ref["soft"], rel=1e-9)
+            assert float(out[4]) == pytest.approx(0.75 * ref["hard"] + 0.5 * ref["soft"], rel=1e-9)
+        assert rel_l2(np.concatenate([r[1][step][1] for r in res]), ref["d_img"]) <= 1e-8
+        assert rel_l2(np.concatenate([r[1][step][2] for r in res]), ref["d_txt"]) <= 1e-8
+
+
+def test_unequal_batches_are_rejected_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() + 77) % 2000
+    procs = [ctx.Process(target=_unequal_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+    assert all("same per-rank batch" in r for r in res)
+
+
+def _unequal_worker(rank, world, port, q):
+    import torch.distributed as dist
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    from distillclip_b200 import pipeline as pl
+    try:
+        pl._CHECKED_BATCH.clear()
+        # both ranks see a NEW (group, batch) pair, so both reach the check
+        pl.check_equal_batches(dist.group.WORLD, 8 + rank, torch.device("cpu"))
+        q.put("no error")
+    except ValueError as e:
+        q.put(str(e))
+    dist.barrier()
+    dist.destroy_process_group()

@@ -25,58 +25,72 @@ def _inputs(b, d, seed):
     return si, st, ti, tt
 
 
-def _worker(rank, world, port, b, d, T, single_pass, q, peer=True):
+def _worker(rank, world, port, b, d, T, route, q):
     import torch.distributed as dist
     sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world,
                             device_id=torch.device("cuda", rank))
-    from distillclip_b200 import contrastive as ct
-    ct.CudaEngine.single_pass_backward = single_pass
-    ct.PeerScatter.enabled = peer
+    from distillclip_b200 import contrastive as ct, pipeline as pl
+    pl.SymmExchange.enabled = route in ("peer_memory", "reduce_scatter")
+    pl.SymmExchange.scatter_enabled = route == "peer_memory"
+    ct.USE_PIPELINE = route != "legacy"
+    if route == "legacy_two_pass":
+        ct.USE_PIPELINE, ct.CudaEngine.single_pass_backward = False, False
     n = b // world
     rows = slice(rank * n, (rank + 1) * n)
-    si, st, ti, tt = [x[rows].cuda() for x in _inputs(b, d, 11)]
-    si.requires_grad_(True)
-    st.requires_grad_(True)
-    res = ct.clip_contrastive(si, st, ti, tt, T, True, True, group=dist.group.WORLD)
-    (0.6 * res["hard_label"] + 0.4 * res["soft_label"]).backward()
-    torch.cuda.synchronize()
-    q.put((rank, float(res["hard_label"].detach()), float(res["soft_label"].detach()),
-           si.grad.float().cpu().numpy(), st.grad.float().cpu().numpy(), bool(ct.PeerScatter._cache)))
+    emb = [x[rows].cuda() for x in _inputs(b, d, 11)]
+    out = []
+    for step in range(3):                       # three steps: the exchange buffers are reused
+        si, st, ti, tt = [x.clone() for x in emb]
+        si.requires_grad_(True)
+        st.requires_grad_(True)
+        res = ct.clip_contrastive(si, st, ti, tt, T, True, True, group=dist.group.WORLD, percent=(0.6, 0.4))
+        res["total"].backward()
+        torch.cuda.synchronize()
+        out.append((float(res["hard_label"].detach()), float(res["soft_label"].detach()), float(res["total"].detach()),
+                    si.grad.float().cpu().numpy(), st.grad.float().cpu().numpy()))
+    xc = pl.exchange_for(dist.group.WORLD)
+    q.put((rank, out, type(xc).__name__, getattr(xc, "fallback", None) is not None))
     dist.barrier()
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("single_pass,peer", [(True, True), (True, False), (False, False)])
+@pytest.mark.parametrize("route", ["peer_memory", "reduce_scatter", "collectives", "legacy", "legacy_two_pass"])
 @pytest.mark.parametrize("b,d,T", [(1024, 256, 2.0), (768, 768, 1.0)])
-def test_nccl_row_sharded_matches_oracle(cuda_device, b, d, T, single_pass, peer):
-    """peer=True: the G^T GEMM stores its rows into the owners' symmetric buffers (fused reduce-scatter); peer=False: NCCL
-    reduce-scatter; single_pass=False: one recompute per side, no gradient exchange."""
+def test_nccl_row_sharded_matches_oracle(cuda_device, b, d, T, route):
+    """peer_memory: symmetric-memory exchanges, the G^T GEMM stores its rows into the owners' buffers; reduce_scatter: same
+    forward, NCCL reduce-scatter of the text gradients; collectives: NCCL all-gathers for everything; legacy*: the round-1
+    flow (one launch per quantity, NCCL collectives; two_pass = one recompute per side, no gradient exchange)."""
     world = min(torch.cuda.device_count(), 4)
     if world < 2:
         pytest.skip("needs >= 2 GPUs")
-    if b % world:
-        world = 2
+    while b % (128 * world):
+        world -= 1
+    if world < 2:
+        pytest.skip("batch does not split into 128-row blocks")
     si, st, ti, tt = _inputs(b, d, 11)
     ref = cf.contrastive_from_embeddings(*[x.float().numpy() for x in (si, st, ti, tt)], T, w_hard=0.6, w_soft=0.4)
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = 29500 + os.getpid() % 2000
-    procs = [ctx.Process(target=_worker, args=(r, world, port, b, d, T, single_pass, q, peer)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, b, d, T, route, q)) for r in range(world)]
     for p in procs:
         p.start()
     res = sorted([q.get(timeout=240) for _ in range(world)], key=lambda x: x[0])
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    if peer and not all(r[5] for r in res):
-        pytest.skip("torch symmetric memory is not available on this machine: the peer-scatter route fell back to NCCL")
-    for _, hard, soft, _, _, _ in res:
-        assert hard == pytest.approx(ref["hard"], rel=LOSS_RTOL)
-        assert soft == pytest.approx(ref["soft"], rel=LOSS_RTOL)
-    assert rel_l2(np.concatenate([r[3] for r in res]), ref["d_img"]) <= GRAD_BF16_STORAGE_RTOL
-    assert rel_l2(np.concatenate([r[4] for r in res]), ref["d_txt"]) <= GRAD_BF16_STORAGE_RTOL
+    if route in ("peer_memory", "reduce_scatter") and any(r[3] or r[2] != "SymmExchange" for r in res):
+        pytest.skip("torch symmetric memory is not available on this machine: the exchange fell back to NCCL collectives")
+    for step in range(3):
+        for _, out, _, _ in res:
+            hard, soft, total = out[step][:3]
+            assert hard == pytest.approx(ref["hard"], rel=LOSS_RTOL)
+            assert soft == pytest.approx(ref["soft"], rel=LOSS_RTOL)
+            assert total == pytest.approx(0.6 * ref["hard"] + 0.4 * ref["soft"], rel=LOSS_RTOL)
+        assert rel_l2(np.concatenate([r[1][step][3] for r in res]), ref["d_img"]) <= GRAD_BF16_STORAGE_RTOL
+        assert rel_l2(np.concatenate([r[1][step][4] for r in res]), ref["d_txt"]) <= GRAD_BF16_STORAGE_RTOL
 
 
 def _metrics_worker(rank, world, port, q):
