@@ -61,7 +61,7 @@ def ncu_traffic(csv_name, kernel_substr):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` extract (bytes), or None."""
     import csv
     path = os.path.join(ROOT, "profiles", csv_name)
-    if not os.path.exists(path):
+    if not csv_name or not os.path.isfile(path):
         return None
     try:
         rows = list(csv.reader(open(path)))

@@ -26,7 +26,8 @@ SIGNATURES = {
                             C.c_float, _vp, C.POINTER(C.c_int), _vp],
     "dcb_finalize": [C.c_int, _vpp, _i32p, _f32p, _f32p, _vp, _vp],
     "dcb_tower_fwd_bwd": [C.c_int, _i32p, _i32p, _vpp, _vpp, _vpp, _i64p, _i64p, _i32p, _i32p, _i64p, _i32p, _f32p,
-                          C.c_int, _f32p, _f32p, C.c_int, C.c_int, _vp, C.c_int, C.c_uint32, C.c_int, _vp, _vp, _vp],
+                          C.c_int, _f32p, _f32p, C.c_int, C.c_int, _vp, C.c_int, C.c_uint32, C.c_int, _vp, _vp, _vp, _vpp,
+                          _f32p, _f32p, _vp],
     "dcb_rescale_grads": [C.c_int, _vpp, _i64p, C.c_int, _vpp, _f32p, _vp],
     "dcb_row_inv_norm": [C.c_int, _vpp, _vpp, _i64p, C.c_int64, C.c_int, _vp],
     "dcb_transpose_norm_f16": [_vp, _vp, _vp, C.c_int64, C.c_int64, C.c_int64, C.c_int, _vp],
@@ -60,7 +61,7 @@ SIGNATURES = {
                          C.c_int64, C.c_int64, _vp, _vp, _vp, C.c_float, C.c_float, C.c_float, C.c_float, _vp, C.c_int, C.c_int,
                          _vp],
     "dcb_value_map_kl_fwd_bwd": [_vp, _vp, _vp, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_float, _vp,
-                                 C.POINTER(C.c_int), _vp],
+                                 C.POINTER(C.c_int), _vp, _vp, C.c_float, _vp],
     "dcb_row_softmax_stats": [_vp, _vp, C.c_int64, C.c_int64, C.c_int, C.c_float, C.c_int, _vp, _vp, _vp],
     "dcb_row_softmax_grads": [_vp, _vp, C.c_int64, C.c_int64, C.c_int, C.c_float, C.c_int, _vp, _vp, _vp, C.c_int, _vp],
     "dcb_logits_row_stats": [_vp, C.c_int64, C.c_int64, _vp, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_float,

@@ -28,6 +28,14 @@ int encode_tile_map_16bit(CUtensorMap* map, const void* base, uint64_t rows, uin
                           uint32_t box_rows) {
     EncodeFn encode = resolve_encode();
     if (!encode) return fail("cuTensorMapEncodeTiled is not available from the CUDA driver");
+    // cuTensorMapEncodeTiled is a DRIVER call: it needs a current context on the calling thread.  Runtime calls bind the
+    // primary context lazily, driver calls do not -- and autograd runs backward on its own worker thread, where this may be
+    // the first CUDA call (CUresult 201 otherwise).  Once per thread.
+    static thread_local bool ctx_bound = false;
+    if (!ctx_bound) {
+        DCB_CUDA_OK(cudaFree(nullptr));
+        ctx_bound = true;
+    }
     if (reinterpret_cast<uintptr_t>(base) % 16 != 0) return fail("TMA: matrix base must be 16-byte aligned");
     if (row_pitch_bytes % 16 != 0) return fail("TMA: row pitch (%llu bytes) must be a multiple of 16", (unsigned long long)row_pitch_bytes);
     if (box_rows == 0 || box_rows > 256) return fail("TMA: box_rows=%u out of range", box_rows);

@@ -32,6 +32,10 @@ struct TowerSeg {
     float inv_hs, inv_ht;
     float val_coef;
     float grad_coef;
+    // regrad mode (backward): recompute this segment's gradients with the TRUE upstream gradient unless it equals what the
+    // forward pass assumed: skip iff *up == expected * fwd_mult, else coefficient = grad_coef * (*up * up_mult)
+    const float* up;
+    float up_mult, expected;
 };
 struct TowerParams {
     int n_seg, n_terms;
@@ -43,6 +47,9 @@ struct TowerParams {
     int ext_count;
     unsigned int* ticket;
     float* out;            // [n_terms + 1]
+    const float* fwd_mult; // optional device scalar multiplied into every gradient written by the forward pass (the AMP
+                           // GradScaler's scale tensor: gradients are rounded once, at the scaled magnitude)
+    int regrad;            // 1 = gradients only (see TowerSeg::up): no values, no partials, no ticket
     TowerSeg seg[kTowerMaxSeg];
 };
 
@@ -52,6 +59,26 @@ __global__ void __launch_bounds__(kStreamThreads, 4) tower_stream_kernel(const _
     constexpr long long kMseTile = (long long)kStreamThreads * kMseUnroll * MVEC;
     constexpr long long kMseTileScalar = (long long)kStreamThreads * kMseUnroll;
     const int tid = threadIdx.x;
+    __shared__ float seg_gc[kTowerMaxSeg];
+    __shared__ unsigned char seg_skip[kTowerMaxSeg];
+    __shared__ int any_work;
+    if (tid == 0) any_work = 0;
+    __syncthreads();
+    if (tid < p.n_seg) {
+        const float fm = p.fwd_mult ? __ldg(p.fwd_mult) : 1.f;
+        float gc = p.seg[tid].grad_coef * fm;
+        bool skip = false;
+        if (p.regrad) {
+            const float up = __ldg(p.seg[tid].up);
+            skip = up == p.seg[tid].expected * fm || p.seg[tid].g == nullptr;
+            gc = p.seg[tid].grad_coef * (up * p.seg[tid].up_mult);
+        }
+        seg_gc[tid] = gc;
+        seg_skip[tid] = skip ? 1 : 0;
+        if (!skip) atomicOr(&any_work, 1);
+    }
+    __syncthreads();
+    if (p.regrad && !any_work) return;             // the common case in backward: nothing to do, no HBM traffic
     // Tiles are ordered by segment and segments by term, so a CTA meets the terms in non-decreasing order: one running
     // accumulator, flushed (block reduce -> partials[term][cta]) whenever the term changes.
     double cur = 0.0;
@@ -70,7 +97,9 @@ __global__ void __launch_bounds__(kStreamThreads, 4) tower_stream_kernel(const _
     for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         while (k + 1 < p.n_seg && tile >= p.seg[k + 1].tile_begin) ++k;
         const TowerSeg& sg = p.seg[k];
-        if (sg.term != cur_term) {                     // block-uniform
+        if (p.regrad && seg_skip[k]) continue;
+        const float gcoef = seg_gc[k];
+        if (!p.regrad && sg.term != cur_term) {        // block-uniform
             if (cur_term >= 0) flush();
             cur_term = sg.term;
         }
@@ -83,25 +112,26 @@ __global__ void __launch_bounds__(kStreamThreads, 4) tower_stream_kernel(const _
             const T* tp = static_cast<const T*>(sg.t) + base;
             G* gp = g ? g + base : nullptr;
             if (sg.kind == 0)
-                acc = sg.aligned ? mse_tile<T, G, MVEC, false>(sp, tp, gp, sg.n - base, sg.grad_coef, tid)
-                                 : mse_tile<T, G, 1, false>(sp, tp, gp, sg.n - base, sg.grad_coef, tid);
+                acc = sg.aligned ? mse_tile<T, G, MVEC, false>(sp, tp, gp, sg.n - base, gcoef, tid)
+                                 : mse_tile<T, G, 1, false>(sp, tp, gp, sg.n - base, gcoef, tid);
             else
-                acc = sg.aligned ? mse_tile<T, G, MVEC, true>(sp, tp, gp, sg.n - base, sg.grad_coef, tid)
-                                 : mse_tile<T, G, 1, true>(sp, tp, gp, sg.n - base, sg.grad_coef, tid);
+                acc = sg.aligned ? mse_tile<T, G, MVEC, true>(sp, tp, gp, sg.n - base, gcoef, tid)
+                                 : mse_tile<T, G, 1, true>(sp, tp, gp, sg.n - base, gcoef, tid);
         } else if (sg.kind == 3) {
             acc = cos_row_tile<T, G>(static_cast<const T*>(sg.s), static_cast<const T*>(sg.t), static_cast<G*>(sg.g), sg.n,
-                                     (int)sg.positions, lt * (kStreamThreads / 32) + (tid >> 5), sg.grad_coef, tid & 31);
+                                     (int)sg.positions, lt * (kStreamThreads / 32) + (tid >> 5), gcoef, tid & 31);
         } else {
             AttnShape sh{sg.n, sg.groups_per_b, sg.positions, sg.hs, sg.ht, sg.inv_hs, sg.inv_ht};
             if (sg.kind == 1)
                 acc = attn_tile<T, G, AVEC, AH, false>(static_cast<const T*>(sg.s), static_cast<const T*>(sg.t),
-                                                       static_cast<G*>(sg.g), sh, lt * kStreamThreads + tid, sg.grad_coef);
+                                                       static_cast<G*>(sg.g), sh, lt * kStreamThreads + tid, gcoef);
             else
                 acc = attn_tile<T, G, AVEC, AH, true>(static_cast<const T*>(sg.s), static_cast<const T*>(sg.t),
-                                                      static_cast<G*>(sg.g), sh, lt * kStreamThreads + tid, sg.grad_coef);
+                                                      static_cast<G*>(sg.g), sh, lt * kStreamThreads + tid, gcoef);
         }
         cur += (double)acc * (double)sg.val_coef;
     }
+    if (p.regrad) return;
     if (cur_term >= 0) flush();
     __shared__ bool is_last;
     if (tid == 0)
@@ -165,12 +195,18 @@ extern "C" int dcb_tower_fwd_bwd(int n_seg, const int32_t* kind, const int32_t* 
                                  const int64_t* positions, const int32_t* divisor, const float* grad_scale, int n_terms,
                                  const float* scale, const float* percent, int in_dtype, int grad_dtype,
                                  double* partials, int partial_stride, uint32_t ext_mask, int ext_count,
-                                 uint32_t* ticket, float* out, void* stream) {
+                                 uint32_t* ticket, float* out, const float* fwd_mult, const float* const* upstream,
+                                 const float* up_mult, const float* expected, void* stream) {
     using namespace dcb;
+    const bool regrad = upstream != nullptr;
     DCB_REQUIRE(n_seg >= 0 && n_seg <= kTowerMaxSeg, "n_seg=%d out of range [0,%d]", n_seg, kTowerMaxSeg);
-    DCB_REQUIRE(partial_stride >= dcb_tower_grid() && ext_count <= partial_stride, "partial_stride too small");
     DCB_REQUIRE(n_terms >= 1 && n_terms <= kTowerMaxTerms, "n_terms=%d out of range [1,%d]", n_terms, kTowerMaxTerms);
-    DCB_REQUIRE(partials && ticket && out, "partials / ticket / out must not be NULL");
+    if (regrad) {
+        DCB_REQUIRE(up_mult && expected, "regrad mode needs up_mult and expected per segment");
+    } else {
+        DCB_REQUIRE(partial_stride >= dcb_tower_grid() && ext_count <= partial_stride, "partial_stride too small");
+        DCB_REQUIRE(partials && ticket && out, "partials / ticket / out must not be NULL");
+    }
     TowerParams p{};
     p.n_seg = n_seg;
     p.n_terms = n_terms;
@@ -180,6 +216,8 @@ extern "C" int dcb_tower_fwd_bwd(int n_seg, const int32_t* kind, const int32_t* 
     p.ext_count = ext_count;
     p.ticket = ticket;
     p.out = out;
+    p.fwd_mult = fwd_mult;
+    p.regrad = regrad ? 1 : 0;
     for (int q = 0; q < n_terms; ++q) {
         p.scale[q] = scale ? scale[q] : 1.f;
         p.percent[q] = percent ? percent[q] : 0.f;
@@ -195,6 +233,12 @@ extern "C" int dcb_tower_fwd_bwd(int n_seg, const int32_t* kind, const int32_t* 
         sg.g = grad_stu ? grad_stu[k] : nullptr;
         sg.kind = kind[k];
         sg.term = term[k];
+        if (regrad) {
+            DCB_REQUIRE(upstream[k] || !sg.g, "segment %d: regrad needs the upstream gradient pointer", k);
+            sg.up = upstream[k];
+            sg.up_mult = up_mult[k];
+            sg.expected = expected[k];
+        }
         if (kind[k] == 0 || kind[k] == 2) {
             DCB_REQUIRE(numel[k] >= 1, "segment %d: numel must be >= 1", k);
             sg.n = numel[k];

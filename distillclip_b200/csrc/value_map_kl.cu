@@ -19,7 +19,18 @@ template <typename T, typename G, int VEC>
 __global__ void __launch_bounds__(kVmThreads) value_map_kl_kernel(const T* __restrict__ s_base, const T* __restrict__ t_base,
                                                                   G* __restrict__ g_base, long long groups, long long groups_per_b,
                                                                   long long positions, int heads, float grad_scale,
-                                                                  double* __restrict__ partials) {
+                                                                  double* __restrict__ partials, const float* __restrict__ fwd_mult,
+                                                                  const float* __restrict__ upstream, float expected) {
+    // forward: gradients carry grad_scale * (*fwd_mult); regrad (upstream != nullptr, partials == nullptr): recompute them
+    // with the true upstream gradient unless it is what the forward pass assumed
+    const float fm = fwd_mult ? __ldg(fwd_mult) : 1.f;
+    if (upstream) {
+        const float up = __ldg(upstream);
+        if (up == expected * fm) return;
+        grad_scale *= up;
+    } else {
+        grad_scale *= fm;
+    }
     double acc = 0.0;
     for (long long gi = (long long)blockIdx.x * kVmThreads + threadIdx.x; gi < groups; gi += (long long)gridDim.x * kVmThreads) {
         const long long b = gi / groups_per_b;
@@ -64,6 +75,7 @@ __global__ void __launch_bounds__(kVmThreads) value_map_kl_kernel(const T* __res
                 if (h < heads) store_vec<G, VEC>(g_base + off + h * positions, sv[h]);
         }
     }
+    if (partials == nullptr) return;
     acc = block_sum(acc);
     if (threadIdx.x == 0) partials[blockIdx.x] = acc;
 }
@@ -72,9 +84,10 @@ __global__ void __launch_bounds__(kVmThreads) value_map_kl_kernel(const T* __res
 
 extern "C" int dcb_value_map_kl_fwd_bwd(const void* stu, const void* tea, void* grad_stu, int64_t batch, int64_t heads,
                                         int64_t positions, int in_dtype, int grad_dtype, float grad_scale, double* partials,
-                                        int* n_partials, void* stream) {
+                                        int* n_partials, const float* fwd_mult, const float* upstream, float expected,
+                                        void* stream) {
     using namespace dcb;
-    DCB_REQUIRE(stu && tea && partials && n_partials, "NULL pointer argument");
+    DCB_REQUIRE(stu && tea && ((partials && n_partials) || (upstream && grad_stu)), "NULL pointer argument");
     DCB_REQUIRE(batch >= 1 && positions >= 1, "bad shape");
     DCB_REQUIRE(heads >= 1 && heads <= kVmMaxHeads, "value-map KL supports 1..%d heads (got %lld)", kVmMaxHeads, (long long)heads);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -90,9 +103,9 @@ extern "C" int dcb_value_map_kl_fwd_bwd(const void* stu, const void* tea, void* 
             if (grid > DCB_MAX_PARTIALS) grid = DCB_MAX_PARTIALS;
             value_map_kl_kernel<T, G, VEC><<<(unsigned)grid, kVmThreads, 0, st>>>(
                 static_cast<const T*>(stu), static_cast<const T*>(tea), static_cast<G*>(grad_stu), groups, groups_per_b, positions,
-                (int)heads, grad_scale, partials);
+                (int)heads, grad_scale, upstream ? nullptr : partials, fwd_mult, upstream, expected);
             DCB_CUDA_OK(cudaGetLastError());
-            *n_partials = (int)grid;
+            if (n_partials) *n_partials = (int)grid;
             return 0;
         };
         // widest vector whose byte width divides every head's start offset (positions * sizeof(T)) and the base pointers

@@ -48,12 +48,17 @@ _TOWER_KERNELS = {
 class LossCalculator(nn.Module):
     #: use the fused embeddings->loss kernel for hard/soft label in two-tower mode (else the logits modules)
     fused_contrastive = True
-    #: upstream gradient assumed by the one-pass streaming kernels (set to GradScaler.get_scale() under fp16 AMP);
-    #: None = use distillclip_b200.ops.EXPECTED_GRAD_SCALE
+    #: upstream gradient assumed by the one-pass streaming kernels; None = distillclip_b200.ops.EXPECTED_GRAD_SCALE (1.0).
+    #: A different upstream value is always honoured exactly (backward recomputes the gradients with the true value, one
+    #: more pass); under fp16 AMP set `grad_scaler` instead so that the extra pass never happens.
     expected_grad_scale = None
+    #: a torch.amp.GradScaler: its device-side scale tensor is read by the forward kernels, so the one-pass gradients are
+    #: written -- and rounded to fp16 exactly once -- at the magnitude `scaler.scale(loss).backward()` will ask for
+    grad_scaler = None
     #: torch.distributed process group for GLOBAL-batch contrastive losses (embeddings all-gathered, each rank
     #: computes its row slice; SURVEY.md F5: the reference itself is local-batch, so the default is None)
     contrastive_group = None
+    _warned_fp16 = False
 
     def __init__(self, loss_name: List, loss_scale: dict = None,
                  temperature=None, percent=None, smd_tau: float = 0.04, vit_kd_para: Dict = None):
@@ -121,10 +126,18 @@ class LossCalculator(nn.Module):
         return need_para
 
     # ------------------------------------------------------------------------------------------
+    def _assumed_upstream(self):
+        """-> (host float, optional device scalar): the upstream gradient of the TOTAL loss the one-pass kernels assume."""
+        expected = float(self.expected_grad_scale if self.expected_grad_scale is not None else ops.EXPECTED_GRAD_SCALE)
+        return expected, ops.grad_scaler_mult(self.grad_scaler)
+
     def cal_one_tower_loss(self,
                            stu_out: Union[VisionTransformerOutput, TextTransformerOutput],
-                           tea_out: Union[VisionTransformerOutput, TextTransformerOutput]):
-        """reference _loss.py:155-202: raw values per name, `* scale`, `loss += value * percent`."""
+                           tea_out: Union[VisionTransformerOutput, TextTransformerOutput], tower_weight: float = 1.0):
+        """reference _loss.py:155-202: raw values per name, `* scale`, `loss += value * percent`.  `tower_weight`: the factor
+        the caller applies to this tower's total (0.5 in two-tower mode), folded into the assumed upstream gradient."""
+        expected, fwd_mult = self._assumed_upstream()
+        expected *= float(tower_weight)
         raw_python = {}          # names whose value is a python number (empty teacher list edge case)
         module_res = {}          # row-softmax losses on the pooled outputs (own small kernels)
         for name in self.loss:
@@ -133,7 +146,9 @@ class LossCalculator(nn.Module):
             if name in ('out_ce', 'out_kl'):
                 module_res[name] = self.loss[name](stu_out.last_representation, tea_out.last_representation)
             elif name == 'last_value_map_kl':
-                module_res[name] = self.loss[name](stu_out.value_map, tea_out.value_map)
+                w = float(self.loss_scale.get(name, 1)) * float(self.percent.get(name, 0))
+                module_res[name] = ops.value_map_kl(stu_out.value_map, tea_out.value_map, expected=w * expected if w else None,
+                                                    fwd_mult=fwd_mult if w else None)
         spec, tensors, order = [], [], []
         for name in self.loss:
             if name not in _TOWER_KERNELS:
@@ -152,20 +167,28 @@ class LossCalculator(nn.Module):
             order.append(name)
             spec.append((kind, divisor, len(s), name))
             tensors.append((s, t))
+        if fwd_mult is None and expected == float(tower_weight) and not self._warned_fp16 and any(
+                x.dtype == torch.float16 and x.requires_grad for s, _ in tensors for x in s):
+            self._warned_fp16 = True
+            import warnings
+            warnings.warn("distillclip_b200: fp16 student tensors with an assumed upstream gradient of 1.0 -- under a GradScaler "
+                          "the gradients are recomputed in backward at the true loss scale (exact, one extra pass over the "
+                          "inputs); set LossCalculator.grad_scaler = scaler to write them once")
 
         weights_ok = all(n in self.loss_scale and n in self.percent for n in order)
         cal_res = {}
+        fused_total, fused = None, {}
         if order and weights_ok:
             full_spec = [(kind, div, n, float(self.loss_scale[name]), float(self.percent[name]))
                          for kind, div, n, name in spec]
             flat = [x for s, t in tensors for x in (*s, *t)]
-            expected = float(self.expected_grad_scale if self.expected_grad_scale is not None else ops.EXPECTED_GRAD_SCALE)
-            outs = ops.TowerLossFn.apply(full_spec, expected, *flat)
+            outs = ops.TowerLossFn.apply(full_spec, expected, fwd_mult, *flat)
             fused_total, fused = outs[0], dict(zip(order, outs[1:]))
         else:
-            fused_total, fused = None, {}
+            # after set_scale / set_percent with a partial dict: raw values from one single-term launch each; the loop below
+            # scales and adds only what the reference's loop over loss_scale would
             for (kind, div, n, name), (s, t) in zip(spec, tensors):
-                cal_res[name] = ops.StreamLossFn.apply(kind, div, n, float(ops.EXPECTED_GRAD_SCALE), *s, *t)
+                cal_res[name] = ops.TowerLossFn.apply([(kind, div, n, 1.0, 1.0)], float(ops.EXPECTED_GRAD_SCALE), None, *s, *t)[0]
         for name in self.loss:                      # dict order of the reference: order of self.loss
             if name in fused:
                 cal_res[name] = fused[name]
@@ -191,8 +214,9 @@ class LossCalculator(nn.Module):
     def cal_tow_tower_loss(self, stu_out: CLIPOutput, tea_out: CLIPOutput):
         """reference _loss.py:118-153."""
         cal_res = {}
-        image_loss, image_loss_dict = self.cal_one_tower_loss(stu_out.visual_output, tea_out.visual_output)
-        text_loss, text_loss_dict = self.cal_one_tower_loss(stu_out.text_output, tea_out.text_output)
+        # each tower's total enters the loss as 0.5 * total (reference _loss.py:148): tell the one-pass kernels
+        image_loss, image_loss_dict = self.cal_one_tower_loss(stu_out.visual_output, tea_out.visual_output, tower_weight=0.5)
+        text_loss, text_loss_dict = self.cal_one_tower_loss(stu_out.text_output, tea_out.text_output, tower_weight=0.5)
         for k, v in image_loss_dict.items():
             cal_res['image_' + k] = v
         for k, v in text_loss_dict.items():

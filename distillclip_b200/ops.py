@@ -155,19 +155,22 @@ def _seg_shape(kind, s, t):
 
 
 def launch_tower(entries, scale: Sequence[float], percent: Sequence[float], grad_dtype: Optional[torch.dtype] = None,
-                 out=None):
+                 out=None, fwd_mult: Optional[torch.Tensor] = None, regrad=None):
     """All streaming losses of one tower -- every layer of every term, the deterministic reduction and the weighting --
     in ONE launch of the tower kernel (csrc/tower_stream.cu).
     entries: [(kind, divisor, stu list, tea list, need_grad list, grad_scale)], one per loss term.
     -> (out[n_terms + 1] = scaled term values + weighted total, grads per entry, partials).  `out=(out, grads, partials)`
-    reuses buffers (kernel-only timing)."""
+    reuses buffers (kernel-only timing).  fwd_mult: optional device scalar multiplied into every gradient (AMP loss scale).
+    regrad = [(upstream 0-dim fp32 device tensor, up_mult, expected)] per entry: gradients only, into out[1], recomputed
+    with the true upstream gradient unless it equals what the forward assumed (see include/distillclip_b200.h)."""
     lib = _lib.load()
     dev = entries[0][2][0].device
     in_dt = dtype_code(entries[0][2][0])
     gd = _DT[grad_dtype] if grad_dtype is not None else in_dt
     n_terms = len(entries)
     stride = lib.dcb_tower_grid()
-    d = dict(kinds=[], terms=[], stu=[], tea=[], grad=[], numel=[], batch=[], hs=[], ht=[], pos=[], div=[], gsc=[])
+    d = dict(kinds=[], terms=[], stu=[], tea=[], grad=[], numel=[], batch=[], hs=[], ht=[], pos=[], div=[], gsc=[],
+             up=[], upm=[], exp=[])
     all_grads = [] if out is None else out[1]
     for ti, (kind, divisor, stu, tea, need, pre) in enumerate(entries):
         grads = [] if out is None else all_grads[ti]
@@ -180,21 +183,31 @@ def launch_tower(entries, scale: Sequence[float], percent: Sequence[float], grad
             d["stu"].append(s.data_ptr()), d["tea"].append(t.data_ptr()), d["grad"].append(g.data_ptr() if g is not None else 0)
             d["numel"].append(s.numel()), d["batch"].append(b_), d["hs"].append(hs_), d["ht"].append(ht_)
             d["pos"].append(pos_), d["div"].append(int(divisor)), d["gsc"].append(float(pre))
+            if regrad is not None:
+                up, upm, exp = regrad[ti]
+                d["up"].append(up.data_ptr()), d["upm"].append(float(upm)), d["exp"].append(float(exp))
         if out is None:
             all_grads.append(grads)
-    if out is None:
-        res = torch.empty(n_terms + 1, dtype=torch.float32, device=dev)
-        partials = torch.empty(n_terms * stride, dtype=torch.float64, device=dev)
-    else:
-        res, partials = out[0], out[2]
+    res = partials = None
+    if regrad is None:
+        if out is None:
+            res = torch.empty(n_terms + 1, dtype=torch.float32, device=dev)
+            partials = torch.empty(n_terms * stride, dtype=torch.float64, device=dev)
+        else:
+            res, partials = out[0], out[2]
     n = len(d["kinds"])
     pad = (lambda v: v if v else [0])
     _lib.call("dcb_tower_fwd_bwd", n, _lib.i32_array(pad(d["kinds"])), _lib.i32_array(pad(d["terms"])), _lib.ptr_array(pad(d["stu"])),
               _lib.ptr_array(pad(d["tea"])), _lib.ptr_array(pad(d["grad"])), _lib.i64_array(pad(d["numel"])), _lib.i64_array(pad(d["batch"])),
               _lib.i32_array(pad(d["hs"])), _lib.i32_array(pad(d["ht"])), _lib.i64_array(pad(d["pos"])), _lib.i32_array(pad(d["div"])),
               _lib.f32_array(pad(d["gsc"])), n_terms, _lib.f32_array(scale), _lib.f32_array(percent), in_dt, gd,
-              C.c_void_p(partials.data_ptr()), stride, 0, 0,
-              C.c_void_p(_ticket(dev).data_ptr()), C.c_void_p(res.data_ptr()), _stream_ptr())
+              C.c_void_p(partials.data_ptr()) if partials is not None else None, stride, 0, 0,
+              C.c_void_p(_ticket(dev).data_ptr()) if regrad is None else None,
+              C.c_void_p(res.data_ptr()) if res is not None else None,
+              C.c_void_p(fwd_mult.data_ptr()) if fwd_mult is not None else None,
+              _lib.ptr_array(pad(d["up"])) if regrad is not None else None,
+              _lib.f32_array(pad(d["upm"])) if regrad is not None else None,
+              _lib.f32_array(pad(d["exp"])) if regrad is not None else None, _stream_ptr())
     return res, all_grads, partials
 
 
@@ -232,122 +245,134 @@ def _as_upstream(g: Optional[torch.Tensor], like: torch.Tensor) -> torch.Tensor:
 
 
 # ----------------------------------------------------------------------------------------------
-# autograd: one loss family (used by the per-module classes)
+# autograd
 # ----------------------------------------------------------------------------------------------
 #: Upstream gradient the one-pass kernels assume when they write the student gradients during the forward pass.
-#: 1.0 is right for plain `loss.backward()`.  Under fp16 AMP set it (or `LossCalculator.expected_grad_scale`) to
-#: `GradScaler.get_scale()`: a different upstream value is still honoured exactly (device-side rescale in backward),
-#: but fp16-stored gradients were then already rounded at the unscaled magnitude.
+#: 1.0 is right for plain `loss.backward()`.  A different upstream value is ALWAYS honoured exactly: backward compares on
+#: the device and, on a mismatch, recomputes the gradients from the inputs with the true value (one more pass over the
+#: inputs, a single rounding at the true magnitude -- fp16 AMP is safe without any configuration).  To avoid that extra
+#: pass under a GradScaler, hand the scaler to `LossCalculator.grad_scaler` (its device scale tensor is read by the
+#: forward kernel) or set this / `LossCalculator.expected_grad_scale` to `scaler.get_scale()`.
 EXPECTED_GRAD_SCALE = 1.0
 
 KIND_MSE, KIND_ATTN_KL, KIND_L1, KIND_COS, KIND_ATTN_MSE = "mse", "attn_kl", "l1", "cos", "attn_mse"
-_LAUNCH = {KIND_MSE: launch_mse, KIND_ATTN_KL: launch_attn_kl}        # per-family kernels (the others are tower-only)
+_LAUNCH = {KIND_MSE: launch_mse, KIND_ATTN_KL: launch_attn_kl}        # per-family kernels (raw launches, kernel timing)
 _KIND_CODE = {KIND_MSE: 0, KIND_ATTN_KL: 1, KIND_L1: 2, KIND_COS: 3, KIND_ATTN_MSE: 4}
+_NAN = float("nan")
 
 
-class StreamLossFn(torch.autograd.Function):
-    """loss = kernel(stu_0..n-1, tea_0..n-1); gradients for the students come out of the same pass."""
+def grad_scaler_mult(scaler) -> Optional[torch.Tensor]:
+    """Device scalar holding a torch.amp.GradScaler's current scale (None when there is none / it is disabled)."""
+    if scaler is None or not getattr(scaler, "is_enabled", lambda: True)():
+        return None
+    t = getattr(scaler, "_scale", None)
+    if t is None and hasattr(scaler, "_lazy_init_scale_growth_tracker"):
+        scaler._lazy_init_scale_growth_tracker(torch.device("cuda", torch.cuda.current_device()))
+        t = getattr(scaler, "_scale", None)
+    if t is None:
+        return None
+    return t if t.dtype == torch.float32 else t.float()
+
+
+class TowerLossFn(torch.autograd.Function):
+    """spec: list of (kind, divisor, n_layers, scale, percent); tensors: for each entry stu_0.., tea_0..
+    Returns (total, res_0, ..., res_{k-1}) with res_k = raw_k * scale_k and total = sum res_k * percent_k
+    (reference model/_loss.py:195-200).  `expected` = upstream gradient of `total` assumed in the forward pass (times the
+    device scalar `fwd_mult` when given).  Terms may differ in dtype (fp16 AMP: softmax outputs are fp32, linear outputs
+    fp16): one launch per dtype."""
 
     @staticmethod
-    def forward(ctx, kind: str, divisor: int, n: int, expected: float, *tensors):
-        stu, tea = list(tensors[:n]), list(tensors[n:])
-        need = [bool(ng) for ng in ctx.needs_input_grad[4:4 + n]]
-        partials, count, grads = _LAUNCH[kind](stu, tea, divisor, expected, need)
-        out = finalize([(partials, count)], [1.0], [1.0])
-        ctx.grads = grads
-        ctx.n = n
-        ctx.expected = expected
-        return out[0]
+    def forward(ctx, spec, expected, fwd_mult, *tensors):
+        ctx.set_materialize_grads(False)
+        entries, layout = [], []
+        off = 0
+        for kind, divisor, n, scale, percent in spec:
+            stu, tea = list(tensors[off:off + n]), list(tensors[off + n:off + 2 * n])
+            need = [bool(x) for x in ctx.needs_input_grad[3 + off:3 + off + n]]
+            w = float(np.float32(percent) * np.float32(scale))
+            pre = w * expected if w != 0.0 else 1.0
+            entries.append((kind, divisor, stu, tea, need, pre))
+            layout.append((off, n, w, pre))
+            off += 2 * n
+        # one launch per dtype (terms keep their order inside a group)
+        groups = {}
+        for i, e in enumerate(entries):
+            groups.setdefault(e[2][0].dtype, []).append(i)
+        for idx in groups.values():
+            if len(idx) > _lib.TOWER_MAX_TERMS or sum(len(entries[i][2]) for i in idx) > _lib.TOWER_MAX_SEG:
+                raise _lib.DistillClipB200Error("one tower launch takes <= 8 loss terms and <= 40 layer pairs per dtype")
+        outs = [None] * len(spec)
+        all_grads = [None] * len(spec)
+        total = None
+        for idx in groups.values():
+            res, grads, _ = launch_tower([entries[i] for i in idx], [spec[i][3] for i in idx], [spec[i][4] for i in idx],
+                                         fwd_mult=fwd_mult)
+            for j, i in enumerate(idx):
+                outs[i], all_grads[i] = res[j], grads[j]
+            total = res[len(idx)] if total is None else total + res[len(idx)]
+        ctx.all_grads, ctx.layout, ctx.spec, ctx.n_in, ctx.groups = all_grads, layout, spec, len(tensors), list(groups.values())
+        ctx.expected, ctx.fwd_mult = expected, fwd_mult
+        ctx.save_for_backward(*tensors)
+        return (total, *outs)
 
     @staticmethod
-    def backward(ctx, g):
-        # hand the gradient buffers over without keeping a reference: autograd's AccumulateGrad then adopts them
-        # as `.grad` instead of cloning (a clone would re-read and re-write every gradient byte)
-        grads, ctx.grads = ctx.grads, None
-        if any(x is not None for x in grads):
-            rescale([(grads, _as_upstream(g, next(x for x in grads if x is not None)), ctx.expected)])
-        return (None, None, None, None, *grads, *([None] * ctx.n))
+    def backward(ctx, g_total, *g_res):
+        tensors = ctx.saved_tensors
+        ret: List[Optional[torch.Tensor]] = [None] * ctx.n_in
+        # First backward: the forward-time buffers are checked on the device and handed over WITHOUT keeping a reference, so
+        # AccumulateGrad adopts them as `.grad` (no clone, no extra HBM pass).  Any later backward of the same graph
+        # (retain_graph=True) recomputes into fresh buffers: the adopted ones belong to the caller now.
+        first = ctx.all_grads is not None
+        all_grads, ctx.all_grads = ctx.all_grads, None
+        dev = tensors[0].device
+        zero = None
+        for idx in ctx.groups:
+            entries, regrad, bufs = [], [], []
+            for i in idx:
+                kind, divisor, n, scale, percent = ctx.spec[i]
+                off, _, w, pre = ctx.layout[i]
+                stu, tea = list(tensors[off:off + n]), list(tensors[off + n:off + 2 * n])
+                need = [bool(x) for x in ctx.needs_input_grad[3 + off:3 + off + n]]
+                if first:
+                    grads = all_grads[i]
+                else:
+                    grads = [torch.empty_like(s) if ng else None for s, ng in zip(stu, need)]
+                if not any(need):
+                    continue
+                if g_res[i] is None and g_total is not None and pre == w * ctx.expected:
+                    # common path, no torch kernels: true multiplier = g_total * w, assumed = expected (* fwd_mult) * w
+                    regrad.append((_as_upstream(g_total, stu[0]), w, ctx.expected if first else _NAN))
+                else:
+                    if g_total is None and g_res[i] is None:
+                        if zero is None:
+                            zero = torch.zeros((), dtype=torch.float32, device=dev)
+                        up = zero
+                    else:
+                        up = _as_upstream(g_total, stu[0]) * w if g_total is not None else None
+                        if g_res[i] is not None:
+                            r = _as_upstream(g_res[i], stu[0]) * float(scale)
+                            up = r if up is None else up + r
+                    regrad.append((up.contiguous(), 1.0, _NAN))          # NaN never compares equal: always recompute
+                entries.append((kind, divisor, stu, tea, need, 1.0))
+                bufs.append(grads)
+                ret[off:off + n] = grads
+            if entries:
+                launch_tower(entries, [1.0] * len(entries), [1.0] * len(entries), out=(None, bufs, None),
+                             fwd_mult=ctx.fwd_mult, regrad=regrad)
+        del all_grads
+        return (None, None, None, *ret)
 
 
 def stream_loss(kind: str, stu: Sequence[torch.Tensor], tea: Sequence[torch.Tensor]):
-    """Reference list semantics: zip-truncation, divisor len(stu), ZeroDivisionError on empty (F8)."""
+    """Reference list semantics: zip-truncation, divisor len(stu), ZeroDivisionError on empty (F8).  One term through the
+    tower kernel (value + gradients in one pass, backward-time check / recompute as for a whole tower)."""
     divisor = len(stu)
     if divisor == 0:
         raise ZeroDivisionError("division by zero")
     s, t = _prep_pair(stu, tea)
     if not s:
         return 0.0          # reference: `res_loss = 0; res_loss /= len(stu)` -> python float
-    if kind not in _LAUNCH:
-        return TowerLossFn.apply([(kind, divisor, len(s), 1.0, 1.0)], float(EXPECTED_GRAD_SCALE), *s, *t)[0]
-    return StreamLossFn.apply(kind, divisor, len(s), float(EXPECTED_GRAD_SCALE), *s, *t)
-
-
-# ----------------------------------------------------------------------------------------------
-# autograd: a whole tower (LossCalculator.cal_one_tower_loss) -> one finalize, one rescale
-# ----------------------------------------------------------------------------------------------
-class TowerLossFn(torch.autograd.Function):
-    """spec: list of (kind, divisor, n_layers, scale, percent); tensors: for each entry stu_0.., tea_0..
-    Returns (total, res_0, ..., res_{k-1}) with res_k = raw_k * scale_k and total = sum res_k * percent_k
-    (reference model/_loss.py:195-200).  `expected` = upstream gradient of `total` assumed in the forward pass."""
-
-    @staticmethod
-    def forward(ctx, spec, expected, *tensors):
-        ctx.set_materialize_grads(False)
-        entries, all_grads, pres, layout = [], [], [], []
-        off = 0
-        for kind, divisor, n, scale, percent in spec:
-            stu, tea = list(tensors[off:off + n]), list(tensors[off + n:off + 2 * n])
-            need = [bool(x) for x in ctx.needs_input_grad[2 + off:2 + off + n]]
-            w = float(np.float32(percent) * np.float32(scale))
-            pre = w * expected if w != 0.0 else 1.0
-            entries.append((kind, divisor, stu, tea, need, pre))
-            pres.append((pre, w))
-            layout.append((off, n))
-            off += 2 * n
-        scales, percents = [sp[3] for sp in spec], [sp[4] for sp in spec]
-        n_seg = sum(len(e[2]) for e in entries)
-        dtypes = {t.dtype for e in entries for t in e[2]}
-        tower_only = any(e[0] not in _LAUNCH for e in entries)
-        if tower_only and not (len(spec) <= _lib.TOWER_MAX_TERMS and n_seg <= _lib.TOWER_MAX_SEG and len(dtypes) == 1):
-            raise _lib.DistillClipB200Error("these losses need one dtype per tower, <= 8 terms and <= 40 layer pairs")
-        if len(spec) <= _lib.TOWER_MAX_TERMS and n_seg <= _lib.TOWER_MAX_SEG and len(dtypes) == 1:
-            out, all_grads, _ = launch_tower(entries, scales, percents)       # ONE launch incl. the weighting
-        else:
-            terms = []
-            for kind, divisor, stu, tea, need, pre in entries:
-                partials, count, grads = _LAUNCH[kind](stu, tea, divisor, pre, need)
-                terms.append((partials, count))
-                all_grads.append(grads)
-            out = finalize(terms, scales, percents)
-        ctx.all_grads, ctx.pres, ctx.layout, ctx.spec, ctx.n_in = all_grads, pres, layout, spec, len(tensors)
-        ctx.expected = expected
-        k = len(spec)
-        return (out[k], *out[:k].unbind(0))
-
-    @staticmethod
-    def backward(ctx, g_total, *g_res):
-        ret: List[Optional[torch.Tensor]] = [None] * ctx.n_in
-        groups = []
-        # drop ctx's references so AccumulateGrad can adopt the buffers as `.grad` (no clone, no extra HBM pass)
-        all_grads, ctx.all_grads = ctx.all_grads, None
-        grads = live = None
-        for i, (grads, (pre, w), (off, n)) in enumerate(zip(all_grads, ctx.pres, ctx.layout)):
-            live = [x for x in grads if x is not None]
-            if not live:
-                continue
-            scale = float(ctx.spec[i][3])
-            if g_res[i] is None and pre == w * ctx.expected and g_total is not None:
-                groups.append((grads, _as_upstream(g_total, live[0]), ctx.expected))   # common path: no torch kernels
-            else:
-                up = _as_upstream(g_total, live[0]) * w
-                if g_res[i] is not None:
-                    up = up + _as_upstream(g_res[i], live[0]) * scale
-                groups.append((grads, up.contiguous(), pre))
-            ret[off:off + n] = grads
-        if groups:
-            rescale(groups)
-        del groups, all_grads, grads, live
-        return (None, None, *ret)
+    return TowerLossFn.apply([(kind, divisor, len(s), 1.0, 1.0)], float(EXPECTED_GRAD_SCALE), None, *s, *t)[0]
 
 
 # ----------------------------------------------------------------------------------------------
@@ -396,27 +421,41 @@ def row_softmax_loss(stu: torch.Tensor, tea: torch.Tensor, temperature, mode: in
 # ----------------------------------------------------------------------------------------------
 class ValueMapKLFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, stu, tea, expected):
-        b, h = stu.shape[0], stu.shape[1]
+    def forward(ctx, stu, tea, expected, fwd_mult):
         grad = torch.empty_like(stu) if ctx.needs_input_grad[0] else None
-        partials = torch.empty(_lib.MAX_PARTIALS, dtype=torch.float64, device=stu.device)
-        count = C.c_int(0)
-        _lib.call("dcb_value_map_kl_fwd_bwd", C.c_void_p(stu.data_ptr()), C.c_void_p(tea.data_ptr()),
-                  C.c_void_p(grad.data_ptr()) if grad is not None else None, b, h, stu.numel() // (b * h), dtype_code(stu),
-                  dtype_code(stu), float(expected), C.c_void_p(partials.data_ptr()), C.byref(count), _stream_ptr())
-        out = finalize([(partials, count.value)], [1.0], [1.0])
-        ctx.grad, ctx.expected = grad, expected
-        return out[0]
+        out = ValueMapKLFn._launch(stu, tea, grad, float(expected), fwd_mult, None, 0.0)
+        ctx.grad, ctx.expected, ctx.fwd_mult = grad, expected, fwd_mult
+        ctx.save_for_backward(stu, tea)
+        return out
+
+    @staticmethod
+    def _launch(stu, tea, grad, grad_scale, fwd_mult, upstream, expected):
+        b, h = stu.shape[0], stu.shape[1]
+        vp = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
+        if upstream is None:
+            partials = torch.empty(_lib.MAX_PARTIALS, dtype=torch.float64, device=stu.device)
+            count = C.c_int(0)
+            _lib.call("dcb_value_map_kl_fwd_bwd", vp(stu), vp(tea), vp(grad), b, h, stu.numel() // (b * h), dtype_code(stu),
+                      dtype_code(stu), grad_scale, vp(partials), C.byref(count), vp(fwd_mult), None, 0.0, _stream_ptr())
+            return finalize([(partials, count.value)], [1.0], [1.0])[0]
+        _lib.call("dcb_value_map_kl_fwd_bwd", vp(stu), vp(tea), vp(grad), b, h, stu.numel() // (b * h), dtype_code(stu),
+                  dtype_code(stu), grad_scale, None, None, vp(fwd_mult), vp(upstream), float(expected), _stream_ptr())
+        return None
 
     @staticmethod
     def backward(ctx, g):
-        grad, ctx.grad = ctx.grad, None
-        if grad is not None:
-            rescale([([grad], _as_upstream(g, grad), ctx.expected)])
-        return grad, None, None
+        stu, tea = ctx.saved_tensors
+        if not ctx.needs_input_grad[0] or g is None:
+            return None, None, None, None
+        first = ctx.grad is not None
+        grad, ctx.grad = ctx.grad, None                     # hand over (AccumulateGrad adopts it); later backwards recompute
+        if not first:
+            grad = torch.empty_like(stu)
+        ValueMapKLFn._launch(stu, tea, grad, 1.0, ctx.fwd_mult, _as_upstream(g, stu), ctx.expected if first else _NAN)
+        return grad, None, None, None
 
 
-def value_map_kl(stu: torch.Tensor, tea: torch.Tensor):
+def value_map_kl(stu: torch.Tensor, tea: torch.Tensor, expected=None, fwd_mult=None):
     """LastValueMapKL (last_value_map_kl.py:10-14): softmax over dim=1 (heads) of both maps, KLDiv(sum)."""
     _require_cuda(stu, "student value map")
     _require_cuda(tea, "teacher value map")
@@ -426,4 +465,4 @@ def value_map_kl(stu: torch.Tensor, tea: torch.Tensor):
     tea = tea.detach()
     if tea.dtype != stu.dtype:
         tea = tea.to(stu.dtype)
-    return ValueMapKLFn.apply(stu.contiguous(), tea.contiguous(), float(EXPECTED_GRAD_SCALE))
+    return ValueMapKLFn.apply(stu.contiguous(), tea.contiguous(), float(EXPECTED_GRAD_SCALE if expected is None else expected), fwd_mult)

@@ -84,7 +84,8 @@ int dcb_tower_fwd_bwd(int n_seg, const int32_t* kind, const int32_t* term, const
                       const int64_t* positions, const int32_t* divisor, const float* grad_scale, int n_terms,
                       const float* scale, const float* percent, int in_dtype, int grad_dtype,
                       double* partials, int partial_stride, uint32_t ext_mask, int ext_count,
-                      uint32_t* ticket, float* out, void* stream);
+                      uint32_t* ticket, float* out, const float* fwd_mult, const float* const* upstream,
+                      const float* up_mult, const float* expected, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Deterministic reduction + weighting (model/_loss.py:195-200 and :148-152).
@@ -338,11 +339,13 @@ int dcb_row_softmax_grads(const void* stu, const void* tea, int64_t rows, int64_
 /* ---------------------------------------------------------------------------------------------
  * LastValueMapKL (model/loss_component/last_value_map_kl.py:10-14): KLDiv(sum)(softmax(stu, dim=1).log(), softmax(tea, dim=1))
  * on [batch, heads, positions] value-relation maps; the softmax runs over the HEAD axis.  One pass, forward value and
- * student gradient (p^s - p^t) * grad_scale; heads <= 16.  partials: >= DCB_MAX_PARTIALS doubles, reduce with dcb_finalize.
+ * student gradient (p^s - p^t) * grad_scale * (*fwd_mult); heads <= 16.  partials: >= DCB_MAX_PARTIALS doubles, reduce with
+ * dcb_finalize.  fwd_mult (optional device scalar): the AMP GradScaler's scale.  Regrad mode (upstream != NULL, partials
+ * NULL): gradients only, coefficient grad_scale * (*upstream), skipped entirely when *upstream == expected * (*fwd_mult).
  * --------------------------------------------------------------------------------------------- */
 int dcb_value_map_kl_fwd_bwd(const void* stu, const void* tea, void* grad_stu, int64_t batch, int64_t heads,
                              int64_t positions, int in_dtype, int grad_dtype, float grad_scale, double* partials,
-                             int* n_partials, void* stream);
+                             int* n_partials, const float* fwd_mult, const float* upstream, float expected, void* stream);
 
 #ifdef __cplusplus
 }
