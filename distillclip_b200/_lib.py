@@ -46,6 +46,7 @@ SIGNATURES = {
     "dcb_clip_grad_finish": [_vp, C.c_int, _vp, _vp, _vp, _vp, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int64,
                              _vp, _vp, _vp, C.c_int, _vp, C.c_int, _vp],
     "dcb_memcpy_async": [_vp, _vp, C.c_int64, _vp],
+    "dcb_peer_gather": [C.c_int, _vpp, _vpp, _i64p, _vp],
     "dcb_clip_prep": [C.c_int, _vpp, _vpp, _vpp, _vpp, _i64p, C.c_int64, C.c_int64, C.c_int, _vp],
     "dcb_clip_fwd_chunk": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int,
                            C.c_float, _vp, _vp, _vp, C.c_int64, _vp],

@@ -123,6 +123,12 @@ class LocalExchange:
     def wait_chunk(self, s, src):
         pass
 
+    def wait_all(self, s):
+        pass
+
+    def tile_streams(self):
+        return None
+
     def slot_targets(self, s):
         return [s.slots[0]]
 
@@ -190,6 +196,7 @@ class CollectiveExchange(LocalExchange):
         b_local, dim, dtype, has_teacher, k_split, _, aux = key
         s.contrib = torch.empty(slot_floats(self.world * b_local, b_local), dtype=aux[0], device=device)
         s.b_local = b_local
+        s.single_chunk = True                     # everything arrives at once: one tile launch over all columns
         return s
 
     def start_gather(self, s):
@@ -214,6 +221,7 @@ class CollectiveExchange(LocalExchange):
 class SymmExchange(LocalExchange):
     """NCCL group + torch symmetric memory: every buffer of a set lives in one peer-mapped arena; transfers are copy-engine
     pulls on a side stream, statistics and text gradients are stored straight into the owners' arenas by the kernels."""
+    chunked = True           # per-source-rank tile launches (unless a set is flagged single_chunk)
     _instances: Dict = {}
     _collective: Dict = {}
     _broken = False
@@ -276,36 +284,74 @@ class SymmExchange(LocalExchange):
     def _impl(self, s):
         return self.fallback if (self.fallback is not None and not hasattr(s, "hdl")) else None
 
+    #: text-side bytes per peer below which the exchange is ONE gather kernel on the main stream followed by ONE tile launch
+    #: (latency-bound regime); above it: copy-engine pulls on a side stream, one tile launch per source rank as it lands
+    small_bytes = int(os.environ.get("DCB_SMALL_EXCHANGE_BYTES", str(4 << 20)))
+
+    def _pieces(self, s, src):
+        n = s.b_local
+        out = []
+        for name in ("st_all", "tt_all", "st_inv_all", "tt_inv_all", "bt_all"):
+            buf = getattr(s, name)
+            if buf is None:
+                continue
+            piece = buf[src] if name == "bt_all" else buf[src * n:(src + 1) * n]
+            rel = piece.data_ptr() - s.arena.data_ptr()
+            out.append((name, piece.data_ptr(), s.peer_base[src] + rel, piece.numel() * piece.element_size()))
+        return out
+
     def start_gather(self, s):
         if self._impl(s):
             return self._impl(s).start_gather(s)
         from . import _lib
+        r = self.rank
+        per_peer = sum(nb for _, _, _, nb in self._pieces(s, r))
+        s.single_chunk = per_peer <= self.small_bytes
+        if s.single_chunk:
+            # latency regime: barrier + one gather kernel (P2P loads) on the main stream
+            s.hdl.barrier(channel=1)
+            cps = [c for k in range(1, self.world) for c in self._pieces(s, (r + k) % self.world)]
+            for i in range(0, len(cps), 64):
+                part = cps[i:i + 64]
+                _lib.call("dcb_peer_gather", len(part), _lib.ptr_array([c[1] for c in part]), _lib.ptr_array([c[2] for c in part]),
+                          _lib.i64_array([c[3] for c in part]), torch.cuda.current_stream().cuda_stream)
+            return
         main = torch.cuda.current_stream()
         ready = torch.cuda.Event()
         ready.record(main)
-        n, r = s.b_local, self.rank
         with torch.cuda.stream(self.comm):
             self.comm.wait_event(ready)
             s.hdl.barrier(channel=1)                          # every rank has published its slice (and left its previous step)
             stream = torch.cuda.current_stream().cuda_stream
+            late = []
             for k in range(1, self.world):
                 src = (r + k) % self.world
-                for name in ("st_all", "tt_all", "st_inv_all", "tt_inv_all", "bt_all"):
-                    buf = getattr(s, name)
-                    if buf is None:
+                for name, dst, peer, nb in self._pieces(s, src):
+                    if name == "bt_all":
+                        late.append((dst, peer, nb))           # only the backward reads it: after every forward operand
                         continue
-                    off = s.regions[name][0]
-                    piece = buf[src] if name == "bt_all" else buf[src * n:(src + 1) * n]
-                    rel = piece.data_ptr() - s.arena.data_ptr()
-                    _lib.call("dcb_memcpy_async", piece.data_ptr(), s.peer_base[src] + rel, piece.numel() * piece.element_size(), stream)
-                    assert rel >= off
+                    _lib.call("dcb_memcpy_async", dst, peer, nb, stream)
                 s.events[src].record(self.comm)
+            for dst, peer, nb in late:
+                _lib.call("dcb_memcpy_async", dst, peer, nb, stream)
+            s.events[r].record(self.comm)                     # own index: "everything has arrived"
 
     def wait_chunk(self, s, src):
-        if self._impl(s):
+        if self._impl(s) or getattr(s, "single_chunk", False):
             return
         if src != self.rank:
             torch.cuda.current_stream().wait_event(s.events[src])
+
+    def wait_all(self, s):
+        if self._impl(s) or getattr(s, "single_chunk", False):
+            return
+        torch.cuda.current_stream().wait_event(s.events[self.rank])
+
+    def tile_streams(self):
+        """Two side streams for the per-source tile launches (independent outputs: consecutive chunks overlap their tails)."""
+        if not hasattr(self, "_tile_streams"):
+            self._tile_streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+        return self._tile_streams
 
     def slot_targets(self, s):
         if self._impl(s):
@@ -409,17 +455,42 @@ def forward_tiles(engine, v):
     si, ti, has_teacher, b, temperature = v["si"], v["ti"], v["has_teacher"], v["b_global"], v["temperature"]
     b_local, dev, f32 = si.shape[0], si.device, engine.stat_dtype
     row_blocks = (b_local + 127) // 128
-    parts = engine.fwd_parts(b_local, b_local)
-    ws = torch.empty(world * parts, 4, b_local, dtype=f32, device=dev)
+    single = world == 1 or getattr(s, "single_chunk", False) or not getattr(xc, "chunked", False)
+    n_chunks = 1 if single else world
+    cols_chunk = b if n_chunks == 1 else b_local
+    parts = engine.fwd_parts(b_local, cols_chunk)
+    ws = torch.empty(n_chunks * parts, 4, b_local, dtype=f32, device=dev)
     diag = torch.empty(b_local, dtype=f32, device=dev)
     col_part = torch.empty(row_blocks, 4, b, dtype=f32, device=dev)
-    for k in range(world):
-        src = (rank + k) % world
-        xc.wait_chunk(s, src)
-        c = slice(src * b_local, (src + 1) * b_local)
-        engine.fwd_chunk(si, s.st_all[c], ti, s.tt_all[c] if has_teacher else None, v["si_inv"], s.st_inv_all[c], v["ti_inv"],
-                         s.tt_inv_all[c] if has_teacher else None, (rank - src) * b_local, temperature,
-                         ws[k * parts:(k + 1) * parts], diag, col_part[:, :, c], b)
+    if n_chunks == 1:
+        for src in range(world):
+            xc.wait_chunk(s, src)
+        engine.fwd_chunk(si, s.st_all, ti, s.tt_all, v["si_inv"], s.st_inv_all, v["ti_inv"], s.tt_inv_all,
+                         rank * b_local, temperature, ws, diag, col_part, b)
+    else:
+        # one launch per source rank, own block first, then the peers' blocks in arrival order.  The launches write disjoint
+        # outputs, so they alternate between two side streams: the tail of one chunk overlaps the head of the next
+        main = torch.cuda.current_stream()
+        streams = xc.tile_streams()
+        fork = torch.cuda.Event()
+        fork.record(main)
+        for k in range(world):
+            src = (rank + k) % world
+            c = slice(src * b_local, (src + 1) * b_local)
+            st_ = streams[k % 2] if streams else main
+            with torch.cuda.stream(st_):
+                if k < 2 and streams:
+                    st_.wait_event(fork)
+                xc.wait_chunk(s, src)
+                engine.fwd_chunk(si, s.st_all[c], ti, s.tt_all[c] if has_teacher else None, v["si_inv"], s.st_inv_all[c], v["ti_inv"],
+                                 s.tt_inv_all[c] if has_teacher else None, (rank - src) * b_local, temperature,
+                                 ws[k * parts:(k + 1) * parts], diag, col_part[:, :, c], b)
+        if streams:
+            for st_ in streams:
+                join = torch.cuda.Event()
+                join.record(st_)
+                main.wait_event(join)
+        xc.wait_all(s)
     v["stats_i2t"] = torch.empty(5, b_local, dtype=f32, device=dev)
     v["coef_row"] = torch.empty(3, b_local, dtype=f32, device=dev)
     engine.post1(ws, diag, col_part, temperature, has_teacher, b, v["stats_i2t"], v["coef_row"], xc.slot_targets(s))

@@ -245,6 +245,9 @@ int dcb_clip_grad_finish(const float* acc_parts, int n_split, const void* stu_a,
  * --------------------------------------------------------------------------------------------- */
 /* stream-ordered device-to-device copy (peer-mapped source: a copy-engine pull over NVLink) */
 int dcb_memcpy_async(void* dst, const void* src, int64_t bytes, void* stream);
+/* up to 64 (dst, src, bytes) copies in ONE kernel launch (16-byte aligned; peer-mapped sources = loads over NVLink): the
+ * latency-optimised exchange for small global batches */
+int dcb_peer_gather(int n_copies, void* const* dst, const void* const* src, const int64_t* bytes, void* stream);
 
 /* prep: for up to 4 matrices [rows, dim] (bf16/fp16, 16-byte aligned): inv_norm[k][i] = 1/||x_i|| (clip_model.py:37-38);
  * copy_out[k] (optional) = the raw rows (this rank's slice of the buffer peers pull from); tr_out[k] (optional) = fp16

@@ -98,8 +98,10 @@ class VirtualExchange:
     statistics slots and text-gradient partial buffers, the 'peers' are reached through ordinary tensors.  The caller runs
     each pipeline stage for all ranks before the next stage (that is what the barriers of the real exchange enforce)."""
 
-    def __init__(self, world, rank, shared):
-        self.world, self.rank, self.shared = world, rank, shared
+    chunked = True             # one tile launch per source rank, as the symmetric-memory exchange does
+
+    def __init__(self, world, rank, shared, chunked=True):
+        self.world, self.rank, self.shared, self.chunked = world, rank, shared, chunked
 
     def acquire(self, b_local, dim, dtype, has_teacher, k_split, device, aux):
         from distillclip_b200 import pipeline as pl
@@ -125,6 +127,12 @@ class VirtualExchange:
     def wait_chunk(self, s, src):
         pass
 
+    def wait_all(self, s):
+        pass
+
+    def tile_streams(self):
+        return None
+
     def slot_targets(self, s):
         return [self.shared["slots"][d][self.rank] for d in range(self.world)]
 
@@ -141,9 +149,10 @@ class VirtualExchange:
         pass
 
 
+@pytest.mark.parametrize("chunked", [True, False])
 @pytest.mark.parametrize("R,b,d,T,teacher", [(4, 512, 256, 2.0, True), (2, 768, 768, 1.0, True), (8, 1024, 64, 2.0, True),
                                              (3, 384, 512, 2.0, False)])
-def test_pipeline_virtual_ranks(cuda_device, R, b, d, T, teacher):
+def test_pipeline_virtual_ranks(cuda_device, R, b, d, T, teacher, chunked):
     """Every kernel's multi-rank path on one GPU; the result must equal the single-process global-batch oracle
     and the one-rank pipeline on the same data."""
     from distillclip_b200 import contrastive as ct, pipeline as pl
@@ -157,7 +166,7 @@ def test_pipeline_virtual_ranks(cuda_device, R, b, d, T, teacher):
                                          T if teacher else None, w_hard=w[0], w_soft=w[1])
     n = b // R
     shared = {}
-    xcs = [VirtualExchange(R, r, shared) for r in range(R)]
+    xcs = [VirtualExchange(R, r, shared, chunked) for r in range(R)]
     loc = [slice(r * n, (r + 1) * n) for r in range(R)]
     vs = [pl.forward_prep(eng, xcs[r], si[loc[r]].contiguous(), st[loc[r]].contiguous(), ti[loc[r]].contiguous() if teacher else None,
                           tt[loc[r]].contiguous() if teacher else None, T if teacher else None, w) for r in range(R)]
