@@ -49,18 +49,16 @@ SIGNATURES = {
     "dcb_peer_gather": [C.c_int, _vpp, _vpp, _i64p, _vp],
     "dcb_clip_prep": [C.c_int, _vpp, _vpp, _vpp, _vpp, _i64p, C.c_int64, C.c_int64, C.c_int, _vp],
     "dcb_clip_fwd_chunk": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int,
-                           C.c_float, _vp, _vp, _vp, C.c_int64, _vp],
+                           C.c_float, _vp, _vp, _vp, C.c_int64, _vp, _vp, _vp],
     "dcb_clip_post1": [_vp, C.c_int, _vp, _vp, C.c_int, C.c_int64, C.c_int64, C.c_float, C.c_int, C.c_int64, _vp, _vp, _vpp,
-                       C.c_int, _vp, _vp],
-    "dcb_clip_post2": [_vp, C.c_int, C.c_int64, C.c_int64, C.c_float, C.c_int, C.c_int64, C.c_float, C.c_float, C.c_float,
-                       C.c_float, _vp, _vp, _vp, _vp, _vp, _vp],
-    "dcb_clip_pair_bwd": [_vp, _vp, _vp, _vp, _vp, C.c_int64, C.c_int64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
-                          C.c_float, C.c_float, C.c_float, C.c_float, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_float,
+                       C.c_int, _vp, _vp, _vp, _vp],
+    "dcb_clip_post2": [_vp, C.c_int, C.c_int64, C.c_int64, C.c_float, C.c_int, C.c_int64, _f32p, _vp, _vp, _vp, _vp, _vp, _vp],
+    "dcb_clip_pair_bwd": [_vp, _vp, _vp, _vp, _vp, C.c_int64, C.c_int64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vpp, _f32p,
+                          C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_float,
                           _vp, _vp, C.c_int64, _vp],
     "dcb_clip_finish2": [_vp, C.c_int, C.c_int64, _vp, _vp, _vp, C.c_int64, _vp, _vp, C.c_int64, C.c_int64,
                          _vp, C.c_int, C.c_int64, _vp, _vp, _vp, C.c_int64, _vp, _vp, C.c_int64, C.c_int64,
-                         C.c_int64, C.c_int64, _vp, _vp, _vp, C.c_float, C.c_float, C.c_float, C.c_float, _vp, C.c_int, C.c_int,
-                         _vp],
+                         C.c_int64, C.c_int64, _vpp, _f32p, _vp, _vp, C.c_int, C.c_int, _vp],
     "dcb_value_map_kl_fwd_bwd": [_vp, _vp, _vp, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_float, _vp,
                                  C.POINTER(C.c_int), _vp, _vp, C.c_float, _vp],
     "dcb_row_softmax_stats": [_vp, _vp, C.c_int64, C.c_int64, C.c_int, C.c_float, C.c_int, _vp, _vp, _vp],

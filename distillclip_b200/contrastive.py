@@ -222,47 +222,52 @@ class CudaEngine:
                   ops._stream_ptr())
 
     def fwd_chunk(self, a_s, b_s, a_t, b_t, a_s_inv, b_s_inv, a_t_inv, b_t_inv, label_col0, temperature, ws_chunk, diag,
-                  col_part_chunk, col_part_ld):
+                  col_part_chunk, col_part_ld, ws_extra=None, diag_t=None):
         _lib.call("dcb_clip_fwd_chunk", _vp(a_s), _vp(b_s), _vp(a_t), _vp(b_t), _vp(a_s_inv), _vp(b_s_inv), _vp(a_t_inv),
                   _vp(b_t_inv), a_s.shape[0], int(label_col0), b_s.shape[0], a_s.shape[1], ops.dtype_code(a_s),
-                  float(temperature or 1.0), _vp(ws_chunk), _vp(diag), _vp(col_part_chunk), int(col_part_ld), ops._stream_ptr())
+                  float(temperature or 1.0), _vp(ws_chunk), _vp(diag), _vp(col_part_chunk), int(col_part_ld), _vp(ws_extra),
+                  _vp(diag_t), ops._stream_ptr())
 
-    def post1(self, ws, diag, col_part, temperature, has_teacher, global_batch, stats, coef_row, dests):
+    def post1(self, ws, diag, col_part, temperature, has_teacher, global_batch, stats, coef_row, dests, ws_extra=None, diag_t=None):
         rows, cols = diag.shape[0], col_part.shape[2]
         _lib.call("dcb_clip_post1", _vp(ws), ws.shape[0], _vp(diag), _vp(col_part), col_part.shape[0], rows, cols,
                   float(temperature or 1.0), int(has_teacher), int(global_batch), _vp(stats), _vp(coef_row),
-                  _lib.ptr_array([d.data_ptr() for d in dests]), len(dests), _vp(self._post_scratch(rows, cols, diag.device, 1)),
-                  ops._stream_ptr())
+                  _lib.ptr_array([d.data_ptr() for d in dests]), len(dests), _vp(ws_extra), _vp(diag_t),
+                  _vp(self._post_scratch(rows, cols, diag.device, 1)), ops._stream_ptr())
 
     def post2(self, slots, rows_per_src, cols, temperature, has_teacher, weights):
         dev = slots.device
         col_stats = torch.empty(4, cols, dtype=torch.float32, device=dev)
         coef_col = torch.empty(3, cols, dtype=torch.float32, device=dev)
         bounds = torch.empty(6, dtype=torch.float32, device=dev)
-        out = torch.empty(5, dtype=torch.float32, device=dev)
-        p_h, p_s, s_h, s_s = [float(w) for w in weights]
+        out = torch.empty(9, dtype=torch.float32, device=dev)
         _lib.call("dcb_clip_post2", _vp(slots), slots.shape[0], int(rows_per_src), int(cols), float(temperature or 1.0),
-                  int(has_teacher), int(cols), p_h, p_s, s_h, s_s, _vp(col_stats), _vp(coef_col), _vp(bounds), _vp(out),
+                  int(has_teacher), int(cols), _lib.f32_array(weights), _vp(col_stats), _vp(coef_col), _vp(bounds), _vp(out),
                   _vp(self._post_scratch(rows_per_src, cols, dev, 2)), ops._stream_ptr())
         return col_stats, coef_col, bounds, out
 
+    @staticmethod
+    def _up_args(up):
+        """up = (g5 tensors-or-None, w8 floats) -> ctypes arrays"""
+        g5, w8 = up
+        return _lib.ptr_array([g.data_ptr() if g is not None else 0 for g in g5]), _lib.f32_array(w8)
+
     def pair_bwd(self, a_s, b_s, a_t, b_t, bt_all, a_s_inv, b_s_inv, a_t_inv, b_t_inv, coef_row, coef_col, bounds, up,
-                 temperature, g_out):
+                 temperature, g_out, extra=False, row_offset=0):
         rows, dim = a_s.shape
         cols = b_s.shape[0]
         n_split = _lib.load().dcb_clip_pair_splits(rows, cols, dim)
         acc = torch.empty(n_split, rows, dim, dtype=torch.float32, device=a_s.device)
-        g_t, g_h, g_s, w_h, w_s, s_h, s_s = up
+        g5, w8 = self._up_args(up)
         _lib.call("dcb_clip_pair_bwd", _vp(a_s), _vp(b_s), _vp(a_t), _vp(b_t), _vp(bt_all), bt_all.stride(1), cols // bt_all.shape[0],
                   _vp(a_s_inv), _vp(b_s_inv), _vp(a_t_inv), _vp(b_t_inv), _vp(coef_row), _vp(coef_col), _vp(bounds),
-                  _vp(g_t), _vp(g_h), _vp(g_s), float(w_h), float(w_s), float(s_h), float(s_s), rows, cols, dim,
+                  g5, w8, int(bool(extra)), int(row_offset), cols, rows, cols, dim,
                   ops.dtype_code(a_s), float(temperature or 1.0), _vp(acc), _vp(g_out), g_out.shape[1] if g_out is not None else 0,
                   ops._stream_ptr())
         return acc
 
-    def finish2(self, side_a, side_b, global_batch, up, bounds, grad_dtype):
+    def finish2(self, side_a, side_b, global_batch, up, bounds, grad_dtype, cos_flag=None):
         """side = dict(acc [n_split, rows, D], x [rows, D], x_inv, y (label rows of the other tower), y_inv, label_offset) or None."""
-        g_t, g_h, g_s, w_h, w_s, s_h, s_s = up
         args, grads, ref = [], [], side_a or side_b
         dim = ref["x"].shape[1]
         for sd in (side_a, side_b):
@@ -275,8 +280,9 @@ class CudaEngine:
             grads.append(g)
             args += [_vp(acc), acc.shape[0], acc.stride(0), _vp(x), _vp(sd["x_inv"]), _vp(g), x.shape[0], _vp(sd["y"]),
                      _vp(sd["y_inv"]), sd["y"].shape[0], int(sd["label_offset"])]
-        _lib.call("dcb_clip_finish2", *args, dim, int(global_batch), _vp(g_t), _vp(g_h), _vp(g_s), float(w_h), float(w_s),
-                  float(s_h), float(s_s), _vp(bounds), ops.dtype_code(ref["x"]), ops._DT[grad_dtype], ops._stream_ptr())
+        g5, w8 = self._up_args(up)
+        _lib.call("dcb_clip_finish2", *args, dim, int(global_batch), g5, w8, _vp(cos_flag), _vp(bounds),
+                  ops.dtype_code(ref["x"]), ops._DT[grad_dtype], ops._stream_ptr())
         return grads[0], grads[1]
 
 
@@ -497,27 +503,28 @@ def _as_scalar(g: Optional[torch.Tensor]):
 
 
 class ClipPipelineFn(torch.autograd.Function):
-    """(stu_img, stu_txt, tea_img, tea_txt) -> (hard * s_hard, soft * s_soft, p_hard * hard * s_hard + p_soft * soft * s_soft):
-    0.5*(i2t + t2i) of CrossEntropy(mean) and of T^2 KL(sum) with the scale / percent weighting of reference
-    _loss.py:130-137,231-234, for the global batch of the exchange `xc` (distillclip_b200/pipeline.py)."""
+    """(stu_img, stu_txt, tea_img, tea_txt) -> (hard s_hard, soft s_soft, cos_diff s_cos, logits_mse s_mse, total): the four
+    logit losses of reference _loss.py:130-145 -- 0.5*(i2t + t2i) of CrossEntropy(mean), T^2 KL(sum), CLIPCosDiff and
+    LogitsMSE -- with the scale / percent weighting of _loss.py:231-234 (total = sum percent * scaled value), for the global
+    batch of the exchange `xc` (distillclip_b200/pipeline.py)."""
 
     @staticmethod
-    def forward(ctx, si, st, ti, tt, temperature, xc, weights):
+    def forward(ctx, si, st, ti, tt, temperature, xc, weights, extra):
         from . import pipeline
-        out, saved = pipeline.pipeline_forward(_ENGINE, xc, si, st, ti, tt, temperature, weights)
+        out, saved = pipeline.pipeline_forward(_ENGINE, xc, si, st, ti, tt, temperature, weights, extra)
         ctx.set_materialize_grads(False)
         if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
             ctx.saved = saved
         else:
             xc.release(saved["set"])                   # nothing will come back for these buffers
-        return out[2], out[3], out[4]
+        return out[2], out[3], out[7], out[8], out[4]
 
     @staticmethod
-    def backward(ctx, g_hard, g_soft, g_total):
+    def backward(ctx, g_hard, g_soft, g_cos, g_mse, g_total):
         from . import pipeline
-        ups = (_as_scalar(g_total), _as_scalar(g_hard), _as_scalar(g_soft))
+        ups = tuple(_as_scalar(g) for g in (g_total, g_hard, g_soft, g_cos, g_mse))
         g_img, g_txt = pipeline.pipeline_backward(_ENGINE, ctx.saved, ups, ctx.needs_input_grad[0], ctx.needs_input_grad[1])
-        return g_img, g_txt, None, None, None, None, None
+        return g_img, g_txt, None, None, None, None, None, None
 
 
 def fused_supported(stu_img: torch.Tensor, stu_txt: torch.Tensor, temperature=None, tea_img=None, tea_txt=None) -> bool:
@@ -546,12 +553,16 @@ def _prep(x: Optional[torch.Tensor], dtype, what: str):
 
 
 def clip_contrastive(stu_img, stu_txt, tea_img=None, tea_txt=None, temperature=None, want_hard=True,
-                     want_soft=False, group=None, percent=None, scale=None) -> Dict[str, torch.Tensor]:
-    """Fused hard-label / soft-label losses from embeddings.  Returns {'hard_label': ..., 'soft_label': ...} (only the
-    requested keys; multiplied by `scale = (s_hard, s_soft)` when given) and, with `percent = (p_hard, p_soft)`, also
-    'total' = p_hard * hard_label + p_soft * soft_label computed on the device.  Values are 0-dim fp32 tensors on the
-    autograd graph of the student embeddings.  With a process group the batch is the GLOBAL batch (rows of all ranks)."""
+                     want_soft=False, group=None, percent=None, scale=None, want_cos_diff=False,
+                     want_logits_mse=False) -> Dict[str, torch.Tensor]:
+    """Fused logit losses from embeddings.  Returns {'hard_label', 'soft_label', 'cos_diff', 'logits_mse'} (only the requested
+    keys; multiplied by `scale` when given) and, with `percent`, also 'total' = sum percent * scaled value computed on the
+    device.  `percent` / `scale`: 2-tuples (hard, soft) or 4-tuples (hard, soft, cos_diff, logits_mse).  Values are 0-dim fp32
+    tensors on the autograd graph of the student embeddings.  With a process group the batch is the GLOBAL batch (rows of
+    all ranks).  cos_diff / logits_mse (reference clip_cos_diff.py:5-23, logits_mse.py:9-10) need the teacher embeddings."""
     from . import pipeline
+    extra = bool(want_cos_diff or want_logits_mse)
+    need_teacher = bool(want_soft or extra)
     if not fused_supported(stu_img, stu_txt, temperature if want_soft else None):
         raise _lib.DistillClipB200Error(
             "fused contrastive path needs CUDA bf16/fp16 [B, D] embeddings with D % 8 == 0 and "
@@ -559,33 +570,52 @@ def clip_contrastive(stu_img, stu_txt, tea_img=None, tea_txt=None, temperature=N
     dt = stu_img.dtype
     si, st = _prep(stu_img, dt, "student image embedding"), _prep(stu_txt, dt, "student text embedding")
     ti = tt = None
-    if want_soft:
+    if need_teacher:
         if tea_img is None or tea_txt is None:
-            raise ValueError("soft_label needs the teacher embeddings")
+            raise ValueError("soft_label / cos_diff / logits_mse need the teacher embeddings")
         ti, tt = _prep(tea_img.detach(), dt, "teacher image embedding"), _prep(tea_txt.detach(), dt, "teacher text embedding")
         if ti.shape != si.shape or tt.shape != st.shape:
             raise ValueError("teacher and student embeddings must have the same [B, D] shape on the fused path "
                              f"(student {tuple(si.shape)}, teacher {tuple(ti.shape)})")
-    s_h, s_s = (float(scale[0]), float(scale[1])) if scale is not None else (1.0, 1.0)
-    p_h, p_s = (float(percent[0]), float(percent[1])) if percent is not None else (0.0, 0.0)
-    T = float(temperature) if want_soft else None
+    sc = [float(x) for x in scale] if scale is not None else [1.0, 1.0]
+    pc = [float(x) for x in percent] if percent is not None else [0.0, 0.0]
+    sc, pc = sc + [1.0] * (4 - len(sc)), pc + [0.0] * (4 - len(pc))
+    # the soft-label statistics need a temperature; when only cos_diff / logits_mse use the teacher any valid one will do
+    T = float(temperature) if (want_soft or (need_teacher and temperature)) else (1.0 if need_teacher else None)
     xc = pipeline.exchange_for(group)
     if xc.world > 1:
         pipeline.check_equal_batches(group, si.shape[0], si.device)
     res = {}
     if USE_PIPELINE and pipeline.pipeline_supported(_ENGINE, xc, si.shape[0], si.shape[1]):
-        hard, soft, total = ClipPipelineFn.apply(si, st, ti, tt, T, xc, (p_h, p_s, s_h, s_s))
+        weights = (pc[0], pc[1], sc[0], sc[1], pc[2], pc[3], sc[2], sc[3])
+        hard, soft, cosd, lmse, total = ClipPipelineFn.apply(si, st, ti, tt, T, xc, weights, extra)
     else:
+        if extra:
+            raise _lib.DistillClipB200Error("cos_diff / logits_mse from embeddings need the pipeline path (D <= 768, D % 8 == 0, "
+                                            "per-rank batch a multiple of 128 when sharded); use the logits modules otherwise")
         hard, soft = ClipContrastiveFn.apply(si, st, ti, tt, T, group)
-        hard, soft = hard * s_h, soft * s_s
-        total = hard * p_h + soft * p_s
+        hard, soft = hard * sc[0], soft * sc[1]
+        total = hard * pc[0] + soft * pc[1]
+        cosd = lmse = None
     if want_hard:
         res["hard_label"] = hard
     if want_soft:
         res["soft_label"] = soft
+    if want_cos_diff:
+        res["cos_diff"] = cosd
+    if want_logits_mse:
+        res["logits_mse"] = lmse
     if percent is not None:
         res["total"] = total
     return res
+
+
+def extras_supported(stu_img, group=None) -> bool:
+    """cos_diff / logits_mse from embeddings ride on the pipeline kernels only."""
+    from . import pipeline
+    if not USE_PIPELINE or stu_img is None or stu_img.dim() != 2:
+        return False
+    return pipeline.pipeline_supported(_ENGINE, pipeline.exchange_for(group), stu_img.shape[0], stu_img.shape[1])
 
 
 #: False (or DCB_PIPELINE=0): the round-1 flow (one launch per quantity, NCCL collectives) for every shape

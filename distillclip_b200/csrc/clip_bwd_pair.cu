@@ -59,6 +59,9 @@ struct ClipBwdPairParams {
     const float* gmax_col;    //   gmax_row[0] + gmax_col[0] bounds |G|
     const float* bounds;      // pipeline mode: coef_row / coef_col are UNIT coefficients, multiplied here by the upstream
     ClipUpstream up;          //   gradients read from the device; bounds[6] fixes the fp16 scale (clip_shared.cuh)
+    int extra;                // 1: add d(CLIPCosDiff)/dS and d(LogitsMSE)/dS to the tiles (kExtra instantiation)
+    int diag0;                //    global column index of local row 0 (the diagonal carries no off-diagonal cos_diff term)
+    float inv_batch, inv_pairs;   // 1/B, 1/(B (B - 1))
     int bt_block_cols;        // b_hatT is stored as row blocks [n_blocks][dim][bt_block_cols] (one block per source rank);
     int bt_block_rows;        //   bt_block_rows = rows of one block (= dim).  One block: bt_block_cols >= cols
     float* acc;               // [n_split][rows][dim] fp32
@@ -93,7 +96,7 @@ __device__ __forceinline__ float ex2p(float x) {
     return y;
 }
 
-template <bool kTeacher, int NT, int ST>
+template <bool kTeacher, int NT, int ST, bool kExtra = false>
 __global__ void __launch_bounds__(bwdp::kThreads, 1)
 clip_bwd_pair_kernel(const __grid_constant__ CUtensorMap map_a_stu, const __grid_constant__ CUtensorMap map_b_stu,
                      const __grid_constant__ CUtensorMap map_a_tea, const __grid_constant__ CUtensorMap map_b_tea,
@@ -298,9 +301,17 @@ clip_bwd_pair_kernel(const __grid_constant__ CUtensorMap map_a_stu, const __grid
         const float k1 = r_s * LOG2E, k1t = r_s * LOG2E * p.inv_temp, k2t = r_t * LOG2E * p.inv_temp;
         const float n1 = -LOG2E, n1t = -LOG2E * p.inv_temp;
         float up_h = 1.f, up_s = 1.f, gbound;
+        float xc1 = 0.f, xc2 = 0.f;                       // kExtra: up_cos / (B (B - 1)) and 2 up_mse / B^2
         if (p.bounds) {
             clip_load_upstream(p.up, up_h, up_s);
             gbound = clip_grad_bound(p.bounds, up_h, up_s);
+            if constexpr (kExtra) {
+                float up_c, up_m;
+                clip_load_upstream_extra(p.up, up_c, up_m);
+                gbound += clip_extra_bound(up_c, up_m, p.inv_batch, p.inv_pairs);
+                xc1 = up_c * p.inv_pairs;
+                xc2 = 2.f * up_m * p.inv_batch * p.inv_batch;
+            }
         } else {
             gbound = __ldg(p.gmax_row) + __ldg(p.gmax_col);
         }
@@ -382,6 +393,12 @@ clip_bwd_pair_kernel(const __grid_constant__ CUtensorMap map_a_stu, const __grid
                         const float v = tv[c + e] * s_ct[c + e];
                         g = fmaf(ex2p(fmaf(u, k1t, n1t)), rbeta + s_b[c + e], g);
                         g = fmaf(-ex2p(fmaf(v, k2t, n1t)), rg + s_g[c + e], g);
+                        if constexpr (kExtra) {
+                            const float d = fmaf(u, r_s, -(v * r_t));                  // S_ij - T_ij
+                            const bool off_diag = col0 + cbase + c + e != p.diag0 + grow;
+                            g = fmaf(xc2, d, g);                                       // logits_mse.py:9-10
+                            g += (d > 0.f && off_diag) ? xc1 : 0.f;                    // clip_cos_diff.py:21-23 (relu'(0) = 0)
+                        }
                     }
                     g2[e] = g * gscale;
                 }
@@ -468,13 +485,13 @@ static int clip_bwd_pair_splits(int64_t rows, int64_t cols, int64_t dim) {
     return (int)best;
 }
 
-template <bool kTeacher, int NT, int ST>
+template <bool kTeacher, int NT, int ST, bool kExtra = false>
 static int launch_pair(dim3 grid, int smem, cudaStream_t st, const CUtensorMap& ma_s, const CUtensorMap& mb_s,
                        const CUtensorMap& ma_t, const CUtensorMap& mb_t, const CUtensorMap& mbt,
                        const ClipBwdPairParams& p, uint32_t idesc_st, uint32_t idesc_grad) {
     static int max_set = 0;
     if (smem > max_set) {
-        DCB_CUDA_OK(cudaFuncSetAttribute(clip_bwd_pair_kernel<kTeacher, NT, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        DCB_CUDA_OK(cudaFuncSetAttribute(clip_bwd_pair_kernel<kTeacher, NT, ST, kExtra>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         max_set = smem;
     }
     cudaLaunchConfig_t cfg{};
@@ -489,7 +506,7 @@ static int launch_pair(dim3 grid, int smem, cudaStream_t st, const CUtensorMap& 
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    DCB_CUDA_OK(cudaLaunchKernelEx(&cfg, clip_bwd_pair_kernel<kTeacher, NT, ST>, ma_s, mb_s, ma_t, mb_t, mbt, p, idesc_st, idesc_grad));
+    DCB_CUDA_OK(cudaLaunchKernelEx(&cfg, clip_bwd_pair_kernel<kTeacher, NT, ST, kExtra>, ma_s, mb_s, ma_t, mb_t, mbt, p, idesc_st, idesc_grad));
     return 0;
 }
 
@@ -506,7 +523,7 @@ static int clip_pair_launch(const void* stu_a, const void* stu_b, const void* te
                             const float* stu_a_inv, const float* stu_b_inv, const float* tea_a_inv,
                             const float* tea_b_inv, const float* coef_row, const float* coef_col,
                             const float* gmax_row, const float* gmax_col, const float* bounds, const ClipUpstream& up,
-                            int64_t rows_local, int64_t cols,
+                            int extra, int64_t row_offset, int64_t global_batch, int64_t rows_local, int64_t cols,
                             int64_t dim, int dtype, float temperature, float* acc_parts, void* g_out,
                             int64_t g_pitch_elems, float* dump_s, long long* trace, void* stream) {
     DCB_REQUIRE(stu_a && stu_b && stu_b_t && stu_a_inv && stu_b_inv && coef_row && coef_col && acc_parts &&
@@ -549,6 +566,13 @@ static int clip_pair_launch(const void* stu_a, const void* stu_b, const void* te
     p.up = up;
     p.bt_block_cols = (int)bt_block_cols;
     p.bt_block_rows = (int)dim;
+    p.extra = extra;
+    p.diag0 = (int)row_offset;
+    if (extra) {
+        DCB_REQUIRE(teacher && bounds && global_batch >= 1, "the cos_diff / logits_mse terms need the teacher and the pipeline mode");
+        p.inv_batch = 1.0f / (float)global_batch;
+        p.inv_pairs = global_batch > 1 ? (float)(1.0 / ((double)global_batch * (double)(global_batch - 1))) : 0.f;
+    }
     p.acc = acc_parts;
     p.g_out = static_cast<__half*>(g_out);
     p.g_ld = g_pitch_elems;
@@ -566,6 +590,10 @@ static int clip_pair_launch(const void* stu_a, const void* stu_b, const void* te
     const uint32_t idesc_grad = tc::umma_idesc_f16(128, 256, 0);          // fp16 G x fp16 b_hatT, 256-row slices
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     dim3 grid((unsigned)(2 * row_blocks * p.n_split));
+    if (extra) {
+        if (dim <= 512) return launch_pair<true, 128, 2, true>(grid, bwdp::Cfg<128, 2>::smem_bytes(), st, ma_s, mb_s, ma_t, mb_t, mbt, p, idesc_st, idesc_grad);
+        return launch_pair<true, 128, 1, true>(grid, bwdp::Cfg<128, 1>::smem_bytes(), st, ma_s, mb_s, ma_t, mb_t, mbt, p, idesc_st, idesc_grad);
+    }
     if (dim <= 512) {       // S/T double buffered: 2 x 128 + D/2 <= 512 TMEM columns
         const int smem = bwdp::Cfg<128, 2>::smem_bytes();
         return teacher ? launch_pair<true, 128, 2>(grid, smem, st, ma_s, mb_s, ma_t, mb_t, mbt, p, idesc_st, idesc_grad)
@@ -585,7 +613,7 @@ extern "C" int dcb_clip_row_grads_pair(const void* stu_a, const void* stu_b, con
                                        int64_t dim, int dtype, float temperature, float* acc_parts, void* g_out,
                                        int64_t g_pitch_elems, float* dump_s, long long* trace, void* stream) {
     return dcb::clip_pair_launch(stu_a, stu_b, tea_a, tea_b, stu_b_t, bt_pitch_elems, 0, stu_a_inv, stu_b_inv, tea_a_inv, tea_b_inv,
-                                 coef_row, coef_col, gmax_row, gmax_col, nullptr, dcb::ClipUpstream{}, rows_local, cols, dim, dtype,
+                                 coef_row, coef_col, gmax_row, gmax_col, nullptr, dcb::ClipUpstream{}, 0, 0, 0, rows_local, cols, dim, dtype,
                                  temperature, acc_parts, g_out, g_pitch_elems, dump_s, trace, stream);
 }
 
@@ -595,13 +623,13 @@ extern "C" int dcb_clip_pair_bwd(const void* stu_a, const void* stu_b, const voi
                                  const void* stu_b_t, int64_t bt_pitch_elems, int64_t bt_block_cols,
                                  const float* stu_a_inv, const float* stu_b_inv, const float* tea_a_inv,
                                  const float* tea_b_inv, const float* coef_row, const float* coef_col, const float* bounds,
-                                 const float* g_total, const float* g_hard, const float* g_soft, float w_hard, float w_soft,
-                                 float s_hard, float s_soft, int64_t rows_local, int64_t cols, int64_t dim, int dtype,
+                                 const float* const* g5, const float* w8, int extra, int64_t row_offset, int64_t global_batch,
+                                 int64_t rows_local, int64_t cols, int64_t dim, int dtype,
                                  float temperature, float* acc_parts, void* g_out, int64_t g_pitch_elems, void* stream) {
     using namespace dcb;
-    DCB_REQUIRE(bounds, "NULL bounds");
+    DCB_REQUIRE(bounds && g5 && w8, "NULL bounds / upstream description");
     return clip_pair_launch(stu_a, stu_b, tea_a, tea_b, stu_b_t, bt_pitch_elems, bt_block_cols, stu_a_inv, stu_b_inv, tea_a_inv,
-                            tea_b_inv, coef_row, coef_col, nullptr, nullptr, bounds,
-                            ClipUpstream{g_total, g_hard, g_soft, w_hard, w_soft, s_hard, s_soft}, rows_local, cols, dim, dtype,
-                            temperature, acc_parts, g_out, g_pitch_elems, nullptr, nullptr, stream);
+                            tea_b_inv, coef_row, coef_col, nullptr, nullptr, bounds, clip_upstream_from(g5, w8), extra, row_offset,
+                            global_batch, rows_local, cols, dim, dtype, temperature, acc_parts, g_out, g_pitch_elems, nullptr, nullptr,
+                            stream);
 }

@@ -61,6 +61,9 @@ struct ClipFwdParams {
                               // rank of the label for top-k accuracy; hard-label-only instantiation without column sums)
     float* dump_s;            // optional [rows, cols] raw logits (tests only), else nullptr
     float* dump_t;
+    float* ws_extra;          // kExtra: [kSubs * n_split][2][rows] partial sums of relu(S - T) and (S - T)^2 over the row
+                              // (CLIPCosDiff clip_cos_diff.py:16-23 and LogitsMSE logits_mse.py:9-10 from the same tiles)
+    float* diag_t;            // kExtra: [rows] teacher logit T_ii
     int rows, cols, dim;
     int row_offset;           // column (relative to b-side row 0 of THIS launch) holding the label of local row 0: labels are
                               // arange(B) over the global batch, so this is (global row offset) - (first column of the chunk)
@@ -91,7 +94,7 @@ __device__ __forceinline__ void column_sums16(float (&a)[16], int lane) {
     a[0] += __shfl_xor_sync(0xffffffffu, a[0], 1);
 }
 
-template <bool kTeacher, bool kCols>
+template <bool kTeacher, bool kCols, bool kExtra = false>
 __global__ void __launch_bounds__(fwd::kThreads, 1)
 clip_fwd_kernel(const __grid_constant__ CUtensorMap map_a_stu, const __grid_constant__ CUtensorMap map_b_stu,
                 const __grid_constant__ CUtensorMap map_a_tea, const __grid_constant__ CUtensorMap map_b_tea,
@@ -222,6 +225,7 @@ clip_fwd_kernel(const __grid_constant__ CUtensorMap map_a_stu, const __grid_cons
         const float rank_ref = (!kTeacher && !kCols && p.rank_ref && row_ok) ? __ldg(p.rank_ref + grow) : 0.f;
         int n_greater = 0;
         float cA = 0.f, cQ = 0.f, cZt = 0.f, cW = 0.f;
+        float XR = 0.f, XM = 0.f, cXR = 0.f, cXM = 0.f, diag_tv = 0.f;     // kExtra: relu(S - T) and (S - T)^2 row sums, T_ii
         bool have_diag = false;
         auto kahan = [](float& sum, float& comp, float x) {
             const float y = x - comp;
@@ -277,7 +281,7 @@ clip_fwd_kernel(const __grid_constant__ CUtensorMap map_a_stu, const __grid_cons
                 }
                 const float* scs = sc + cbase;
                 const float* sct = sc + kBN + cbase;
-                float a_sum = 0.f, q_sum = 0.f, zt_sum = 0.f, w_sum = 0.f;
+                float a_sum = 0.f, q_sum = 0.f, zt_sum = 0.f, w_sum = 0.f, xr_sum = 0.f, xm_sum = 0.f;
                 {
                     float e[16], f[16];
                     // ---- A = sum exp(S - 1)
@@ -323,8 +327,16 @@ clip_fwd_kernel(const __grid_constant__ CUtensorMap map_a_stu, const __grid_cons
                             e[c] = ex2(fmaf(sv[c], k1t, n1t));
                             const float v = tv[c] * sct[c];
                             const float et = ex2(fmaf(v, k2t, n1t));
-                            f[c] = et * fmaf(v, r_t, -(sv[c] * r_s));
+                            const float d = fmaf(v, r_t, -(sv[c] * r_s));               // T_ij - S_ij
+                            f[c] = et * d;
                             tv[c] = et;
+                            if constexpr (kExtra) {
+                                const int gc = col0 + cbase + c;
+                                const bool ok = !edge || (gc < p.cols && row_ok);
+                                if (edge && gc == diag_col && gc < p.cols) diag_tv = v * r_t;
+                                xr_sum += ok ? fmaxf(-d, 0.f) : 0.f;
+                                xm_sum = ok ? fmaf(d, d, xm_sum) : xm_sum;
+                            }
                         }
                         if (edge) {
 #pragma unroll
@@ -354,6 +366,10 @@ clip_fwd_kernel(const __grid_constant__ CUtensorMap map_a_stu, const __grid_cons
                     kahan(Q, cQ, q_sum);
                     kahan(Zt, cZt, zt_sum);
                     kahan(W, cW, w_sum);
+                    if constexpr (kExtra) {
+                        kahan(XR, cXR, xr_sum);
+                        kahan(XM, cXM, xm_sum);
+                    }
                 }
             }
         }
@@ -368,6 +384,12 @@ clip_fwd_kernel(const __grid_constant__ CUtensorMap map_a_stu, const __grid_cons
             w[(size_t)2 * p.rows] = Zt;
             w[(size_t)3 * p.rows] = W;
             if (have_diag) p.diag[grow] = diag;
+            if constexpr (kExtra) {
+                float* x = p.ws_extra + (size_t)(sp * kSubs + sub) * 2 * p.rows + grow;
+                x[0] = XR;
+                x[(size_t)p.rows] = XM;
+                if (have_diag) p.diag_t[grow] = diag_tv;
+            }
         }
     }
     tc_fence_before_sync();
@@ -489,7 +511,7 @@ static int clip_row_stats_impl(const void* stu_a, const void* stu_b, const void*
                                int64_t dim, int dtype, float temperature, float* stats, double* rowloss,
                                float* col_stats, void* workspace, float* dump_s, float* dump_t, const float* rank_ref,
                                void* stream, float* chunk_ws = nullptr, float* chunk_diag = nullptr, float* chunk_col_part = nullptr,
-                               int64_t chunk_col_part_ld = 0) {
+                               int64_t chunk_col_part_ld = 0, float* chunk_ws_extra = nullptr, float* chunk_diag_t = nullptr) {
     const bool chunk_mode = chunk_ws != nullptr;     // tiles only: partial sums into caller-owned buffers, no combine / colreduce
     DCB_REQUIRE(stu_a && stu_b && stu_a_inv && stu_b_inv && (chunk_mode || (stats && rowloss && workspace)), "NULL pointer argument");
     DCB_REQUIRE(dtype == DCB_BF16 || dtype == DCB_F16, "the fused contrastive kernel takes bf16 or fp16 embeddings");
@@ -529,6 +551,9 @@ static int clip_row_stats_impl(const void* stu_a, const void* stu_b, const void*
         p.diag = chunk_diag;
         p.col_part = chunk_col_part;
         p.col_part_ld = (int)chunk_col_part_ld;
+        p.ws_extra = chunk_ws_extra;
+        p.diag_t = chunk_diag_t;
+        DCB_REQUIRE(!chunk_ws_extra || (teacher && chunk_diag_t), "the cos_diff / logits_mse sums need the teacher and a T_ii buffer");
         col_stats = chunk_col_part;                 // selects the column-sum instantiation below
     } else {
         p.ws = static_cast<float*>(workspace);
@@ -544,9 +569,9 @@ static int clip_row_stats_impl(const void* stu_a, const void* stu_b, const void*
     const uint32_t idesc = tc::umma_idesc_f16(2 * fwd::kBM, fwd::kBN, dtype == DCB_BF16 ? 1 : 0);     // M = 256 over the CTA pair
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     dim3 grid((unsigned)(2 * ((row_blocks + 1) / 2) * p.n_split));
-#define DCB_LAUNCH_FWD(TEA, COLS)                                                                                       \
+#define DCB_LAUNCH_FWD(TEA, COLS, ...)                                                                                       \
     {                                                                                                                  \
-        static const cudaError_t attr_ = cudaFuncSetAttribute(clip_fwd_kernel<TEA, COLS>,                              \
+        static const cudaError_t attr_ = cudaFuncSetAttribute(clip_fwd_kernel<TEA, COLS __VA_ARGS__>,                              \
                                                               cudaFuncAttributeMaxDynamicSharedMemorySize, fwd::kSmemBytes); \
         DCB_CUDA_OK(attr_);     /* set once per process (not a stream operation; kept out of graph captures) */         \
         cudaLaunchConfig_t cfg_{};                                                                                     \
@@ -561,9 +586,10 @@ static int clip_row_stats_impl(const void* stu_a, const void* stu_b, const void*
         attr2_[0].val.clusterDim.z = 1;                                                                                \
         cfg_.attrs = attr2_;                                                                                           \
         cfg_.numAttrs = 1;                                                                                             \
-        DCB_CUDA_OK(cudaLaunchKernelEx(&cfg_, clip_fwd_kernel<TEA, COLS>, ma_s, mb_s, ma_t, mb_t, p, idesc));           \
+        DCB_CUDA_OK(cudaLaunchKernelEx(&cfg_, clip_fwd_kernel<TEA, COLS __VA_ARGS__>, ma_s, mb_s, ma_t, mb_t, p, idesc));           \
     }
-    if (teacher && col_stats) DCB_LAUNCH_FWD(true, true)
+    if (teacher && col_stats && p.ws_extra) DCB_LAUNCH_FWD(true, true, , true)
+    else if (teacher && col_stats) DCB_LAUNCH_FWD(true, true)
     else if (teacher) DCB_LAUNCH_FWD(true, false)
     else if (col_stats) DCB_LAUNCH_FWD(false, true)
     else DCB_LAUNCH_FWD(false, false)
@@ -596,6 +622,8 @@ extern "C" int dcb_clip_row_stats(const void* stu_a, const void* stu_b, const vo
 // ws_chunk[parts][4][rows] (parts = dcb_clip_fwd_chunk_parts), S_ii into diag[rows] where the label falls inside the chunk,
 // column sums of the chunk into col_part_chunk[row_blocks][4][col_part_ld] (pointer already advanced to the chunk's first
 // column).  label_col0 = (global index of local row 0) - (global index of the chunk's first column).  dcb_clip_post1 reduces.
+// ws_extra_chunk (optional, [parts][2][rows]) + diag_t[rows]: also the row sums of relu(S - T) and (S - T)^2 and T_ii, for
+// CLIPCosDiff / LogitsMSE from the same tiles.
 extern "C" int dcb_clip_fwd_chunk_parts(int64_t rows_local, int64_t cols_chunk) {
     return dcb::clip_fwd_splits(rows_local, cols_chunk) * dcb::fwd::kSubs;
 }
@@ -603,12 +631,13 @@ extern "C" int dcb_clip_fwd_chunk(const void* stu_a, const void* stu_b, const vo
                                   const float* stu_a_inv, const float* stu_b_inv, const float* tea_a_inv,
                                   const float* tea_b_inv, int64_t rows_local, int64_t label_col0, int64_t cols_chunk,
                                   int64_t dim, int dtype, float temperature, float* ws_chunk, float* diag,
-                                  float* col_part_chunk, int64_t col_part_ld, void* stream) {
+                                  float* col_part_chunk, int64_t col_part_ld, float* ws_extra_chunk, float* diag_t,
+                                  void* stream) {
     using namespace dcb;
     DCB_REQUIRE(ws_chunk && diag && col_part_chunk && col_part_ld >= cols_chunk, "NULL / bad chunk buffers");
     return clip_row_stats_impl(stu_a, stu_b, tea_a, tea_b, stu_a_inv, stu_b_inv, tea_a_inv, tea_b_inv, rows_local, label_col0,
                                cols_chunk, dim, dtype, temperature, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
-                               stream, ws_chunk, diag, col_part_chunk, col_part_ld);
+                               stream, ws_chunk, diag, col_part_chunk, col_part_ld, ws_extra_chunk, diag_t);
 }
 
 extern "C" int dcb_clip_rank_counts(const void* a, const void* b, const float* a_inv, const float* b_inv, int64_t rows_local,

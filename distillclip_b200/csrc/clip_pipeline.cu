@@ -94,13 +94,14 @@ __global__ void __launch_bounds__(256) clip_prep_kernel(const __grid_constant__ 
 
 // ---------------------------------------------------------------------------------------------
 // statistics slot exchanged between ranks (floats): [4][cols] column sums | [rows_per_rank] S_ii of the source's rows |
-// (8-byte aligned) 2 doubles {sum CE_i2t, sum KL_i2t / T^2 over the source's rows} | 4 floats {max x, max y, max z, 0}
+// (8-byte aligned) 5 doubles {sum CE_i2t, sum KL_i2t / T^2, sum relu(T_ii - S_ii), sum_{i != j} relu(S_ij - T_ij),
+// sum (S_ij - T_ij)^2 over the source's rows} | 4 floats {max x, max y, max z, 0} | 2 floats padding
 // ---------------------------------------------------------------------------------------------
 __host__ __device__ inline long long clip_slot_tail(long long cols, long long rows_per_rank) {
     return (4 * cols + rows_per_rank + 3) / 4 * 4;
 }
 __host__ __device__ inline long long clip_slot_floats_(long long cols, long long rows_per_rank) {
-    return clip_slot_tail(cols, rows_per_rank) + 8;
+    return clip_slot_tail(cols, rows_per_rank) + 16;
 }
 
 constexpr int kMaxRanks = 16;
@@ -109,10 +110,12 @@ struct ClipPost1Params {
     const float* ws;          // [n_part][4][rows]
     const float* diag;        // [rows]
     const float* col_part;    // [row_blocks][4][cols]
+    const float* ws_extra;    // optional [n_part][2][rows]: relu(S - T) and (S - T)^2 row sums (cos_diff / logits_mse)
+    const float* diag_t;      // optional [rows] T_ii
     float* stats;             // [5][rows]
-    float* coef_row;          // [3][rows] unit coefficients
+    float* coef_row;          // [4][rows] unit coefficients x, y, z and the flag [T_ii > S_ii] of the cos_diff label term
     float* dest[kMaxRanks];   // this source's slot in every destination rank's buffer
-    double* block_part;       // [grid][2]
+    double* block_part;       // [grid][5]
     float* block_max;         // [grid][4]
     unsigned int* ticket;
     int n_dest, rows, cols, n_part, row_blocks, n_stats;
@@ -165,7 +168,7 @@ __global__ void __launch_bounds__(256) clip_post1_kernel(const __grid_constant__
     const unsigned quad = tid & 28u;
     const float v0 = __shfl_sync(0xffffffffu, mine, quad), v1 = __shfl_sync(0xffffffffu, mine, quad + 1);
     const float v2 = __shfl_sync(0xffffffffu, mine, quad + 2), v3 = __shfl_sync(0xffffffffu, mine, quad + 3);
-    double ce = 0.0, kl = 0.0;
+    double ce = 0.0, kl = 0.0, pos = 0.0, neg = 0.0, mse = 0.0;
     float mx = 0.f, my = 0.f, mz = 0.f;
     if (ok && k == 0) {
         const float dg = p.diag[r];
@@ -174,7 +177,26 @@ __global__ void __launch_bounds__(256) clip_post1_kernel(const __grid_constant__
         mx = 0.5f * p.inv_batch / v0;
         p.coef_row[r] = mx;
         for (int d = 0; d < p.n_dest; ++d) p.dest[d][4 * (size_t)p.cols + r] = dg;
-    } else if (ok && k == 1) {
+    } else if (ok && (k == 2 || k == 3)) {
+        // cos_diff / logits_mse: threads 2 and 3 of the row sum the relu(S - T) resp. (S - T)^2 partial sets (fixed order)
+        float flag = 0.f;
+        if (p.ws_extra) {
+            const float* __restrict__ src = p.ws_extra + (size_t)(k - 2) * p.rows + r;
+            const size_t stride = (size_t)2 * p.rows;
+            double a = 0.0;
+            for (int s = 0; s < p.n_part; ++s) a += (double)src[(size_t)s * stride];
+            if (k == 2) {
+                const float ds = p.diag[r], dt = p.diag_t[r];
+                pos = (double)fmaxf(dt - ds, 0.f);                           // clip_cos_diff.py:17-18
+                neg = a - (double)fmaxf(ds - dt, 0.f);                       // get_neg_element drops exactly the diagonal (:5-8)
+                flag = dt > ds ? 1.f : 0.f;
+            } else {
+                mse = a;
+            }
+        }
+        if (k == 2) p.coef_row[(size_t)3 * p.rows + r] = flag;
+    }
+    if (ok && k == 1) {
         if (p.has_teacher) {
             kl = clip_row_kl_d((double)v1, (double)v2, (double)v3, (double)p.temperature);
             const float zs = v2 + v1 - v3 / p.temperature;          // Zs = Zt + Q - W/T (slot 1 carries Q, clip_fwd.cu)
@@ -208,16 +230,18 @@ __global__ void __launch_bounds__(256) clip_post1_kernel(const __grid_constant__
         }
     }
     // ---- block partial sums -> last block -> tail of every slot
-    ce = block_sum(ce);
-    __syncthreads();
-    kl = block_sum(kl);
-    __syncthreads();
+    double sums[5] = {ce, kl, pos, neg, mse};
+#pragma unroll
+    for (int q = 0; q < 5; ++q) {
+        sums[q] = block_sum(sums[q]);
+        __syncthreads();
+    }
     mx = block_max_f(mx, smax);
     my = block_max_f(my, smax);
     mz = block_max_f(mz, smax);
     if (tid == 0) {
-        p.block_part[2 * blockIdx.x] = ce;
-        p.block_part[2 * blockIdx.x + 1] = kl;
+#pragma unroll
+        for (int q = 0; q < 5; ++q) p.block_part[5 * blockIdx.x + q] = sums[q];
         p.block_max[4 * blockIdx.x] = mx;
         p.block_max[4 * blockIdx.x + 1] = my;
         p.block_max[4 * blockIdx.x + 2] = mz;
@@ -229,28 +253,29 @@ __global__ void __launch_bounds__(256) clip_post1_kernel(const __grid_constant__
     __threadfence();
     const volatile double* bp = p.block_part;
     const volatile float* bm = p.block_max;
-    double c2 = 0.0, k2 = 0.0;
+    double t2[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
     float x2 = 0.f, y2 = 0.f, z2 = 0.f;
     for (unsigned i = tid; i < gridDim.x; i += 256) {          // fixed assignment, fixed tree
-        c2 += bp[2 * i];
-        k2 += bp[2 * i + 1];
+#pragma unroll
+        for (int q = 0; q < 5; ++q) t2[q] += bp[5 * i + q];
         x2 = fmaxf(x2, bm[4 * i]);
         y2 = fmaxf(y2, bm[4 * i + 1]);
         z2 = fmaxf(z2, bm[4 * i + 2]);
     }
-    c2 = block_sum(c2);
-    __syncthreads();
-    k2 = block_sum(k2);
-    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 5; ++q) {
+        t2[q] = block_sum(t2[q]);
+        __syncthreads();
+    }
     x2 = block_max_f(x2, smax);
     y2 = block_max_f(y2, smax);
     z2 = block_max_f(z2, smax);
     if (tid == 0) {
         for (int d = 0; d < p.n_dest; ++d) {
             double* td = reinterpret_cast<double*>(p.dest[d] + p.tail_off);
-            td[0] = c2;
-            td[1] = k2;
-            float* tm = p.dest[d] + p.tail_off + 4;
+#pragma unroll
+            for (int q = 0; q < 5; ++q) td[q] = t2[q];
+            float* tm = p.dest[d] + p.tail_off + 10;
             tm[0] = x2;
             tm[1] = y2;
             tm[2] = z2;
@@ -266,14 +291,15 @@ struct ClipPost2Params {
     float* col_stats;         // [4][cols]
     float* coef_col;          // [3][cols]
     float* bounds;            // [6]
-    float* out;               // [5] = hard, soft, hard * s_hard, soft * s_soft, p_hard * out[2] + p_soft * out[3]
+    float* out;               // [9] = hard, soft, hard s_hard, soft s_soft, total, cos_diff, logits_mse, cos s_cos, mse s_mse;
+                              // total = p_hard out[2] + p_soft out[3] + p_cos out[7] + p_mse out[8]
     double* block_part;
     float* block_max;
     unsigned int* ticket;
     int n_src, rows_per_src, cols;
     float temperature, inv_batch;
     int has_teacher;
-    float p_hard, p_soft, s_hard, s_soft;
+    float p_hard, p_soft, s_hard, s_soft, p_cos, p_mse, s_cos, s_mse;
 };
 
 __global__ void __launch_bounds__(256) clip_post2_kernel(const __grid_constant__ ClipPost2Params p) {
@@ -344,13 +370,16 @@ __global__ void __launch_bounds__(256) clip_post2_kernel(const __grid_constant__
     y2 = block_max_f(y2, smax);
     z2 = block_max_f(z2, smax);
     if (tid == 0) {
-        double ce_rows = 0.0, kl_rows = 0.0;
+        double ce_rows = 0.0, kl_rows = 0.0, pos = 0.0, neg = 0.0, mse = 0.0;
         float rx = 0.f, ry = 0.f, rz = 0.f;
         for (int s = 0; s < p.n_src; ++s) {                    // the i2t sums of every rank's rows, fixed order
             const double* td = reinterpret_cast<const double*>(p.slots + (size_t)s * p.slot_floats + p.tail_off);
             ce_rows += td[0];
             kl_rows += td[1];
-            const float* tm = p.slots + (size_t)s * p.slot_floats + p.tail_off + 4;
+            pos += td[2];
+            neg += td[3];
+            mse += td[4];
+            const float* tm = p.slots + (size_t)s * p.slot_floats + p.tail_off + 10;
             rx = fmaxf(rx, tm[0]);
             ry = fmaxf(ry, tm[1]);
             rz = fmaxf(rz, tm[2]);
@@ -362,7 +391,15 @@ __global__ void __launch_bounds__(256) clip_post2_kernel(const __grid_constant__
         p.out[1] = soft;
         p.out[2] = hard * p.s_hard;                                                  // _loss.py:233
         p.out[3] = soft * p.s_soft;
-        p.out[4] = p.out[2] * p.p_hard + p.out[3] * p.p_soft;                        // _loss.py:234
+        // CLIPCosDiff and LogitsMSE are invariant under transposition: 0.5 (loss(i2t) + loss(t2i)) = loss(i2t) (_loss.py:138-145)
+        const double nb = (double)p.cols;
+        const float cosd = (float)(pos / nb + (p.cols > 1 ? neg / (nb * (nb - 1.0)) : 0.0));   // clip_cos_diff.py:16-23
+        const float lmse = (float)(mse / (nb * nb));                                            // logits_mse.py:9-10
+        p.out[5] = cosd;
+        p.out[6] = lmse;
+        p.out[7] = cosd * p.s_cos;
+        p.out[8] = lmse * p.s_mse;
+        p.out[4] = p.out[2] * p.p_hard + p.out[3] * p.p_soft + p.out[7] * p.p_cos + p.out[8] * p.p_mse;   // _loss.py:234
         p.bounds[0] = rx;
         p.bounds[1] = ry;
         p.bounds[2] = rz;
@@ -387,13 +424,15 @@ struct ClipFinishSide {
     void* grad;               // [rows][dim]
     long long rows, label_rows, label_offset, split_stride;
     int n_split;
+    const float* cos_flag;    // optional [rows]: [T_ii > S_ii], the diagonal term of CLIPCosDiff (same pairing as the label)
 };
 struct ClipFinishParams {
     ClipFinishSide side[2];
     ClipUpstream up;
     const float* bounds;
     int dim;
-    float inv_batch;
+    float inv_batch, inv_pairs;
+    int extra;                // cos_diff / logits_mse terms are part of the gradient tiles
 };
 
 template <typename T, typename G, int kGroups>
@@ -404,11 +443,23 @@ __global__ void __launch_bounds__(256) clip_finish2_kernel(const __grid_constant
     const int lane = threadIdx.x & 31;
     float up_h, up_s;
     clip_load_upstream(p.up, up_h, up_s);
-    const float unscale = 1.0f / clip_tile_scale(clip_grad_bound(p.bounds, up_h, up_s));
+    float gbound = clip_grad_bound(p.bounds, up_h, up_s);
+    if (p.extra) {
+        float up_c, up_m;
+        clip_load_upstream_extra(p.up, up_c, up_m);
+        gbound += clip_extra_bound(up_c, up_m, p.inv_batch, p.inv_pairs);
+    }
+    const float unscale = 1.0f / clip_tile_scale(gbound);
     const float r = sd.x_inv[row];
     const long long gi = sd.label_offset + row;
     const bool has_label = gi < sd.label_rows;
-    const float lab = has_label ? up_h * p.inv_batch * sd.y_inv[gi] : 0.f;
+    float lab_w = up_h;
+    if (sd.cos_flag) {
+        float up_c, up_m;
+        clip_load_upstream_extra(p.up, up_c, up_m);
+        lab_w += up_c * sd.cos_flag[row];             // d/dS_ii of relu(T_ii - S_ii) / B = -[T_ii > S_ii] / B, like the -1/B of the label
+    }
+    const float lab = has_label ? lab_w * p.inv_batch * sd.y_inv[gi] : 0.f;
     const int dim = p.dim;
     const T* __restrict__ xp = static_cast<const T*>(sd.x) + row * dim;
     const T* __restrict__ yp = static_cast<const T*>(sd.y) + (has_label ? gi : 0) * dim;
@@ -500,7 +551,7 @@ int dcb_clip_prep(int n_mats, const void* const* mats, float* const* inv_norm, v
 
 int dcb_clip_post1(const float* ws, int n_part, const float* diag, const float* col_part, int row_blocks, int64_t rows,
                    int64_t cols, float temperature, int has_teacher, int64_t global_batch, float* stats, float* coef_row,
-                   void* const* dest_slots, int n_dest, void* scratch, void* stream) {
+                   void* const* dest_slots, int n_dest, const float* ws_extra, const float* diag_t, void* scratch, void* stream) {
     using namespace dcb;
     DCB_REQUIRE(ws && diag && col_part && stats && coef_row && dest_slots && scratch, "NULL pointer argument");
     DCB_REQUIRE(n_dest >= 1 && n_dest <= kMaxRanks && rows >= 1 && cols >= 1 && n_part >= 1 && row_blocks >= 1, "bad arguments");
@@ -508,6 +559,9 @@ int dcb_clip_post1(const float* ws, int n_part, const float* diag, const float* 
     p.ws = ws;
     p.diag = diag;
     p.col_part = col_part;
+    p.ws_extra = ws_extra;
+    p.diag_t = diag_t;
+    DCB_REQUIRE(!ws_extra || diag_t, "the cos_diff sums need T_ii");
     p.stats = stats;
     p.coef_row = coef_row;
     for (int d = 0; d < n_dest; ++d) {
@@ -526,10 +580,10 @@ int dcb_clip_post1(const float* ws, int n_part, const float* diag, const float* 
     p.has_teacher = has_teacher;
     const long long work = 4 * rows > cols ? 4 * rows : cols;
     const unsigned grid = (unsigned)((work + 255) / 256);
-    // scratch: [ticket (16 B)] [grid x 2 doubles] [grid x 4 floats]
+    // scratch: [ticket (16 B)] [grid x 5 doubles] [grid x 4 floats]
     p.ticket = static_cast<unsigned int*>(scratch);
     p.block_part = reinterpret_cast<double*>(static_cast<char*>(scratch) + 16);
-    p.block_max = reinterpret_cast<float*>(static_cast<char*>(scratch) + 16 + (size_t)grid * 16);
+    p.block_max = reinterpret_cast<float*>(static_cast<char*>(scratch) + 16 + (size_t)grid * 40);
     clip_post1_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
     DCB_CUDA_OK(cudaGetLastError());
     return 0;
@@ -537,11 +591,11 @@ int dcb_clip_post1(const float* ws, int n_part, const float* diag, const float* 
 
 int64_t dcb_clip_post_scratch_bytes(int64_t rows, int64_t cols) {
     const long long work = 4 * rows > cols ? 4 * rows : cols;
-    return 16 + ((work + 255) / 256) * 32;
+    return 16 + ((work + 255) / 256) * 56;
 }
 
 int dcb_clip_post2(const float* slots, int n_src, int64_t rows_per_src, int64_t cols, float temperature, int has_teacher,
-                   int64_t global_batch, float p_hard, float p_soft, float s_hard, float s_soft, float* col_stats,
+                   int64_t global_batch, const float* weights8, float* col_stats,
                    float* coef_col, float* bounds, float* out, void* scratch, void* stream) {
     using namespace dcb;
     DCB_REQUIRE(slots && col_stats && coef_col && bounds && out && scratch, "NULL pointer argument");
@@ -560,10 +614,15 @@ int dcb_clip_post2(const float* slots, int n_src, int64_t rows_per_src, int64_t 
     p.temperature = temperature;
     p.inv_batch = 1.0f / (float)global_batch;
     p.has_teacher = has_teacher;
-    p.p_hard = p_hard;
-    p.p_soft = p_soft;
-    p.s_hard = s_hard;
-    p.s_soft = s_soft;
+    DCB_REQUIRE(weights8, "NULL weights");       // host array {p_hard, p_soft, s_hard, s_soft, p_cos, p_mse, s_cos, s_mse}
+    p.p_hard = weights8[0];
+    p.p_soft = weights8[1];
+    p.s_hard = weights8[2];
+    p.s_soft = weights8[3];
+    p.p_cos = weights8[4];
+    p.p_mse = weights8[5];
+    p.s_cos = weights8[6];
+    p.s_mse = weights8[7];
     const unsigned grid = (unsigned)((cols + 255) / 256);
     p.ticket = static_cast<unsigned int*>(scratch);
     p.block_part = reinterpret_cast<double*>(static_cast<char*>(scratch) + 16);
@@ -577,15 +636,15 @@ int dcb_clip_finish2(const float* acc_a, int n_split_a, int64_t split_stride_a, 
                      int64_t rows_a, const void* a_label, const float* a_label_inv, int64_t a_label_rows, int64_t a_label_offset,
                      const float* acc_b, int n_split_b, int64_t split_stride_b, const void* b, const float* b_inv, void* grad_b,
                      int64_t rows_b, const void* b_label, const float* b_label_inv, int64_t b_label_rows, int64_t b_label_offset,
-                     int64_t dim, int64_t global_batch, const float* g_total, const float* g_hard, const float* g_soft,
-                     float w_hard, float w_soft, float s_hard, float s_soft, const float* bounds, int in_dtype, int grad_dtype,
-                     void* stream) {
+                     int64_t dim, int64_t global_batch, const float* const* g5, const float* w8, const float* cos_flag,
+                     const float* bounds, int in_dtype, int grad_dtype, void* stream) {
     using namespace dcb;
     DCB_REQUIRE(bounds && dim >= 8 && dim % 8 == 0 && dim <= 1024 && global_batch >= 1, "bad arguments (dim %% 8 == 0, dim <= 1024)");
     DCB_REQUIRE(in_dtype == DCB_BF16 || in_dtype == DCB_F16, "bf16 or fp16 embeddings only");
     ClipFinishParams p{};
-    p.side[0] = ClipFinishSide{acc_a, a, a_inv, a_label, a_label_inv, grad_a, rows_a, a_label_rows, a_label_offset, split_stride_a, n_split_a};
-    p.side[1] = ClipFinishSide{acc_b, b, b_inv, b_label, b_label_inv, grad_b, rows_b, b_label_rows, b_label_offset, split_stride_b, n_split_b};
+    DCB_REQUIRE(g5 && w8, "NULL upstream description");
+    p.side[0] = ClipFinishSide{acc_a, a, a_inv, a_label, a_label_inv, grad_a, rows_a, a_label_rows, a_label_offset, split_stride_a, n_split_a, cos_flag};
+    p.side[1] = ClipFinishSide{acc_b, b, b_inv, b_label, b_label_inv, grad_b, rows_b, b_label_rows, b_label_offset, split_stride_b, n_split_b, cos_flag};
     long long max_rows = 0;
     for (int s = 0; s < 2; ++s) {
         const ClipFinishSide& sd = p.side[s];
@@ -596,10 +655,12 @@ int dcb_clip_finish2(const float* acc_a, int n_split_a, int64_t split_stride_a, 
         max_rows = sd.rows > max_rows ? sd.rows : max_rows;
     }
     DCB_REQUIRE(max_rows >= 1, "nothing to do");
-    p.up = ClipUpstream{g_total, g_hard, g_soft, w_hard, w_soft, s_hard, s_soft};
+    p.up = clip_upstream_from(g5, w8);
     p.bounds = bounds;
     p.dim = (int)dim;
     p.inv_batch = 1.0f / (float)global_batch;
+    p.inv_pairs = global_batch > 1 ? (float)(1.0 / ((double)global_batch * (double)(global_batch - 1))) : 0.f;
+    p.extra = cos_flag != nullptr;
     const dim3 grid((unsigned)((max_rows + 7) / 8), 2);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int groups = (int)((dim / 8 + 31) / 32);

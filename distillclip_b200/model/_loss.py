@@ -223,24 +223,32 @@ class LossCalculator(nn.Module):
             cal_res['text_' + k] = v
 
         want_hard, want_soft = 'hard_label' in self.loss, 'soft_label' in self.loss
+        want_cos, want_mse = 'cos_diff' in self.loss, 'logits_mse' in self.loss
         if want_soft:
             assert self.temperature
         stu_img, stu_txt = stu_out.visual_output.last_representation, stu_out.text_output.last_representation
-        tea_img = tea_out.visual_output.last_representation if want_soft else None
-        tea_txt = tea_out.text_output.last_representation if want_soft else None
+        need_tea = want_soft or want_cos or want_mse
+        tea_img = tea_out.visual_output.last_representation if need_tea else None
+        tea_txt = tea_out.text_output.last_representation if need_tea else None
         fused = {}
-        if (want_hard or want_soft) and self.fused_contrastive and contrastive.fused_supported(
+        if (want_hard or want_soft or want_cos or want_mse) and self.fused_contrastive and contrastive.fused_supported(
                 stu_img, stu_txt, self.temperature if want_soft else None, tea_img, tea_txt):
+            # cos_diff / logits_mse ride on the pipeline kernels only; otherwise they stay on the caller's logits
+            extras = (want_cos or want_mse) and contrastive.extras_supported(stu_img, self.contrastive_group)
+            f_cos, f_mse = want_cos and extras, want_mse and extras
             # scale / percent of reference _loss.py:231-234 applied on the device; a name missing from loss_scale (after
             # set_scale with a partial dict) is neither scaled nor added, exactly like the reference's loop over loss_scale
-            def weight(name):
-                if name not in self.loss or name not in self.loss_scale:
+            def weight(name, on):
+                if not on or name not in self.loss_scale:
                     return 1.0, 0.0
                 return float(self.loss_scale[name]), float(self.percent[name])
-            (s_h, p_h), (s_s, p_s) = weight('hard_label'), weight('soft_label')
-            fused = contrastive.clip_contrastive(stu_img, stu_txt, tea_img, tea_txt, self.temperature if want_soft else None,
-                                                 want_hard, want_soft, group=self.contrastive_group,
-                                                 percent=(p_h, p_s), scale=(s_h, s_s))
+            ws = [weight('hard_label', want_hard), weight('soft_label', want_soft), weight('cos_diff', f_cos), weight('logits_mse', f_mse)]
+            if want_hard or want_soft or f_cos or f_mse:
+                fused = contrastive.clip_contrastive(stu_img, stu_txt, tea_img if (want_soft or f_cos or f_mse) else None,
+                                                     tea_txt if (want_soft or f_cos or f_mse) else None,
+                                                     self.temperature if want_soft else None, want_hard, want_soft,
+                                                     group=self.contrastive_group, percent=[w[1] for w in ws],
+                                                     scale=[w[0] for w in ws], want_cos_diff=f_cos, want_logits_mse=f_mse)
 
         def logits_of(out, who):
             if out.i2t_logits is None or out.t2i_logits is None:
@@ -250,6 +258,9 @@ class LossCalculator(nn.Module):
                     f"temperature >= {contrastive.MIN_FUSED_TEMPERATURE}; materialise the logits or fix the inputs")
             return out.i2t_logits, out.t2i_logits
         for loss_name in self.loss_name:
+            if loss_name in ('cos_diff', 'logits_mse') and loss_name in fused:
+                cal_res[loss_name] = fused[loss_name]
+                continue
             if loss_name in ('cos_diff', 'logits_mse'):     # reference _loss.py:138-145, on the caller's materialised logits
                 loss = self.loss[loss_name]
                 (s_i2t, s_t2i), (t_i2t, t_t2i) = logits_of(stu_out, 'student'), logits_of(tea_out, 'teacher')

@@ -41,8 +41,9 @@ def slot_tail(cols: int, rows_per_rank: int) -> int:
 
 
 def slot_floats(cols: int, rows_per_rank: int) -> int:
-    """Statistics slot (floats): [4][cols] column sums | [rows_per_rank] S_ii | 2 doubles (i2t loss sums) | 4 floats (maxima)."""
-    return slot_tail(cols, rows_per_rank) + 8
+    """Statistics slot (floats): [4][cols] column sums | [rows_per_rank] S_ii | 5 doubles (i2t CE / KL sums, cos_diff positive and
+    negative sums, logits_mse sum) | 4 floats (maxima) | 2 floats padding."""
+    return slot_tail(cols, rows_per_rank) + 16
 
 
 class PeerRef:
@@ -419,7 +420,17 @@ def pipeline_supported(engine, xc, b_local: int, dim: int) -> bool:
     return xc.world == 1 or b_local % 128 == 0          # logit tiles must not straddle two ranks' b_hatT blocks
 
 
-def forward_prep(engine, xc, si, st, ti, tt, temperature, weights=(1.0, 1.0, 1.0, 1.0)):
+def _weights8(weights):
+    """(p_hard, p_soft, s_hard, s_soft[, p_cos, p_mse, s_cos, s_mse]) -> 8-tuple of floats."""
+    w = [float(x) for x in weights]
+    if len(w) == 4:
+        w += [0.0, 0.0, 1.0, 1.0]
+    if len(w) != 8:
+        raise ValueError("weights: (p_hard, p_soft, s_hard, s_soft) or that plus (p_cos, p_mse, s_cos, s_mse)")
+    return tuple(w)
+
+
+def forward_prep(engine, xc, si, st, ti, tt, temperature, weights=(1.0, 1.0, 1.0, 1.0), extra=False):
     """Stage 1: acquire the exchange buffers, prep kernel (inverse norms, this rank's slice of the text buffers, fp16
     transposes), start pulling the peers' slices.  -> state dict."""
     world, rank = xc.world, xc.rank
@@ -444,7 +455,8 @@ def forward_prep(engine, xc, si, st, ti, tt, temperature, weights=(1.0, 1.0, 1.0
     engine.prep(mats, invs, copies, trs)
     xc.start_gather(s)
     return dict(si=si, st=st, ti=ti, tt=tt, si_inv=si_inv, ti_inv=ti_inv, at=at, set=s, xc=xc, b_global=b,
-                temperature=temperature, has_teacher=has_teacher, weights=tuple(float(w) for w in weights), k_split=k_split)
+                temperature=temperature, has_teacher=has_teacher, weights=_weights8(weights), k_split=k_split,
+                extra=bool(extra and has_teacher))
 
 
 def forward_tiles(engine, v):
@@ -462,11 +474,14 @@ def forward_tiles(engine, v):
     ws = torch.empty(n_chunks * parts, 4, b_local, dtype=f32, device=dev)
     diag = torch.empty(b_local, dtype=f32, device=dev)
     col_part = torch.empty(row_blocks, 4, b, dtype=f32, device=dev)
+    extra = v["extra"]                          # cos_diff / logits_mse sums from the same tiles
+    wx = torch.empty(n_chunks * parts, 2, b_local, dtype=f32, device=dev) if extra else None
+    diag_t = torch.empty(b_local, dtype=f32, device=dev) if extra else None
     if n_chunks == 1:
         for src in range(world):
             xc.wait_chunk(s, src)
         engine.fwd_chunk(si, s.st_all, ti, s.tt_all, v["si_inv"], s.st_inv_all, v["ti_inv"], s.tt_inv_all,
-                         rank * b_local, temperature, ws, diag, col_part, b)
+                         rank * b_local, temperature, ws, diag, col_part, b, wx, diag_t)
     else:
         # one launch per source rank, own block first, then the peers' blocks in arrival order.  The launches write disjoint
         # outputs, so they alternate between two side streams: the tail of one chunk overlaps the head of the next
@@ -484,7 +499,8 @@ def forward_tiles(engine, v):
                 xc.wait_chunk(s, src)
                 engine.fwd_chunk(si, s.st_all[c], ti, s.tt_all[c] if has_teacher else None, v["si_inv"], s.st_inv_all[c], v["ti_inv"],
                                  s.tt_inv_all[c] if has_teacher else None, (rank - src) * b_local, temperature,
-                                 ws[k * parts:(k + 1) * parts], diag, col_part[:, :, c], b)
+                                 ws[k * parts:(k + 1) * parts], diag, col_part[:, :, c], b,
+                                 wx[k * parts:(k + 1) * parts] if extra else None, diag_t)
         if streams:
             for st_ in streams:
                 join = torch.cuda.Event()
@@ -492,8 +508,8 @@ def forward_tiles(engine, v):
                 main.wait_event(join)
         xc.wait_all(s)
     v["stats_i2t"] = torch.empty(5, b_local, dtype=f32, device=dev)
-    v["coef_row"] = torch.empty(3, b_local, dtype=f32, device=dev)
-    engine.post1(ws, diag, col_part, temperature, has_teacher, b, v["stats_i2t"], v["coef_row"], xc.slot_targets(s))
+    v["coef_row"] = torch.empty(4, b_local, dtype=f32, device=dev)
+    engine.post1(ws, diag, col_part, temperature, has_teacher, b, v["stats_i2t"], v["coef_row"], xc.slot_targets(s), wx, diag_t)
 
 
 def forward_finish(engine, v):
@@ -505,10 +521,12 @@ def forward_finish(engine, v):
     return out
 
 
-def pipeline_forward(engine, xc, si, st, ti, tt, temperature, weights=(1.0, 1.0, 1.0, 1.0)):
+def pipeline_forward(engine, xc, si, st, ti, tt, temperature, weights=(1.0, 1.0, 1.0, 1.0), extra=False):
     """si/st/ti/tt: this rank's rows [B_local, D] (ti/tt None = hard label only).  weights = (percent_hard, percent_soft,
-    scale_hard, scale_soft).  -> (out[5] = {hard, soft, hard * s_hard, soft * s_soft, weighted sum}, saved state)."""
-    v = forward_prep(engine, xc, si, st, ti, tt, temperature, weights)
+    scale_hard, scale_soft[, percent_cos, percent_mse, scale_cos, scale_mse]); extra=True also evaluates CLIPCosDiff and
+    LogitsMSE on the same tiles.  -> (out[9] = {hard, soft, hard s_hard, soft s_soft, weighted sum, cos_diff, logits_mse,
+    cos_diff s_cos, logits_mse s_mse}, saved state)."""
+    v = forward_prep(engine, xc, si, st, ti, tt, temperature, weights, extra)
     forward_tiles(engine, v)
     return forward_finish(engine, v), v
 
@@ -523,8 +541,11 @@ def _check_live(v):
 
 
 def _upstream(v, ups):
-    p_h, p_s, s_h, s_s = v["weights"]
-    return (ups[0], ups[1], ups[2], p_h * s_h, p_s * s_s, s_h, s_s)
+    """-> (g5, w8): g5 = (g_total, g_hard, g_soft, g_cos, g_mse) device scalars or None; w8 = (w_hard, w_soft, s_hard, s_soft,
+    w_cos, w_mse, s_cos, s_mse) with w = percent * scale (see csrc/clip_shared.cuh)."""
+    p_h, p_s, s_h, s_s, p_c, p_m, s_c, s_m = v["weights"]
+    g5 = tuple(ups) + (None,) * (5 - len(ups))
+    return (g5, (p_h * s_h, p_s * s_s, s_h, s_s, p_c * s_c, p_m * s_m, s_c, s_m))
 
 
 def backward_gemms(engine, v, ups, want_txt=True):
@@ -537,7 +558,8 @@ def backward_gemms(engine, v, ups, want_txt=True):
     b = v["b_global"]
     g = engine.alloc_g(b_local, b, si.device)
     v["acc_a"] = engine.pair_bwd(si, s.st_all, v["ti"], s.tt_all, s.bt_all, v["si_inv"], s.st_inv_all, v["ti_inv"], s.tt_inv_all,
-                                 v["coef_row"], v["coef_col"], v["bounds"], _upstream(v, ups), v["temperature"], g)
+                                 v["coef_row"], v["coef_col"], v["bounds"], _upstream(v, ups), v["temperature"], g,
+                                 extra=v["extra"], row_offset=xc.rank * b_local)
     v["acc_b"], v["scattered"] = None, False
     if want_txt:
         targets = xc.gt_targets(s) if xc.world > 1 else None
@@ -563,7 +585,7 @@ def backward_finish(engine, v, ups, want_img=True, want_txt=True, grad_dtype=Non
     g_img, g_txt = engine.finish2(
         dict(acc=v["acc_a"], x=si, x_inv=v["si_inv"], y=s.st_all, y_inv=s.st_inv_all, label_offset=xc.rank * b_local) if want_img else None,
         dict(acc=acc_b, x=st, x_inv=s.st_inv_all[loc], y=si, y_inv=v["si_inv"], label_offset=0) if want_txt else None,
-        v["b_global"], _upstream(v, ups), v["bounds"], grad_dtype or si.dtype)
+        v["b_global"], _upstream(v, ups), v["bounds"], grad_dtype or si.dtype, cos_flag=v["coef_row"][3] if v["extra"] else None)
     xc.release(s)
     v["released"] = True
     v["acc_a"] = v["acc_b"] = None

@@ -263,51 +263,63 @@ int dcb_clip_fwd_chunk_parts(int64_t rows_local, int64_t cols_chunk);
 int dcb_clip_fwd_chunk(const void* stu_a, const void* stu_b, const void* tea_a, const void* tea_b,
                        const float* stu_a_inv, const float* stu_b_inv, const float* tea_a_inv, const float* tea_b_inv,
                        int64_t rows_local, int64_t label_col0, int64_t cols_chunk, int64_t dim, int dtype, float temperature,
-                       float* ws_chunk, float* diag, float* col_part_chunk, int64_t col_part_ld, void* stream);
+                       float* ws_chunk, float* diag, float* col_part_chunk, int64_t col_part_ld, float* ws_extra_chunk,
+                       float* diag_t, void* stream);
+/* ws_extra_chunk (optional, [parts][2][rows]) and diag_t[rows]: ALSO the row sums of relu(S_ij - T_ij) and (S_ij - T_ij)^2 and
+ * the teacher diagonal T_ii -- CLIPCosDiff (clip_cos_diff.py:5-23) and LogitsMSE (logits_mse.py:9-10) from the same tiles, so the
+ * shipped stage-3 recipe (config/final_config/l_clip.yaml:30) never materialises the B x B logits either. */
 
 /* Statistics slot exchanged between ranks, in floats: [4][cols] column sums | [rows_per_rank] S_ii | 2 doubles
- * {sum CE_i2t, sum KL_i2t / T^2} | 4 floats {max of the three unit coefficients, 0}. */
+ * {sum CE_i2t, sum KL_i2t / T^2, sum relu(T_ii - S_ii), sum_{i != j} relu(S_ij - T_ij), sum (S_ij - T_ij)^2} | 4 floats {max of
+ * the three unit coefficients, 0} | 2 floats padding. */
 int64_t dcb_clip_slot_floats(int64_t cols, int64_t rows_per_rank);
 int64_t dcb_clip_post_scratch_bytes(int64_t rows, int64_t cols);   /* zero-initialised once; the kernels reset their ticket */
 
 /* post1: row statistics stats[5][rows] of the local rows (fixed-order sum of the n_part partial sets), UNIT gradient
- * coefficients coef_row[3][rows] = {1/(2 B A_i), T/(2 Zs_i), T/(2 Zt_i)} (no upstream gradient in them), and this rank's slot
+ * coefficients coef_row[4][rows] = {1/(2 B A_i), T/(2 Zs_i), T/(2 Zt_i), [T_ii > S_ii]} (no upstream gradient in them; the
+ * fourth row is the diagonal flag of CLIPCosDiff, 0 without ws_extra / diag_t), and this rank's slot
  * (column sums over its rows, S_ii, i2t loss sums, maxima) stored into dest_slots[0..n_dest): this rank's slot inside every
  * rank's slot buffer (peer-mapped addresses: NVLink stores; n_dest = 1 with a local buffer when a collective follows). */
 int dcb_clip_post1(const float* ws, int n_part, const float* diag, const float* col_part, int row_blocks, int64_t rows,
                    int64_t cols, float temperature, int has_teacher, int64_t global_batch, float* stats, float* coef_row,
-                   void* const* dest_slots, int n_dest, void* scratch, void* stream);
+                   void* const* dest_slots, int n_dest, const float* ws_extra, const float* diag_t, void* scratch, void* stream);
 
 /* post2 (after the cross-rank barrier): slots[n_src][dcb_clip_slot_floats] summed in source order -> col_stats[4][cols],
  * coef_col[3][cols] (unit coefficients of the t2i direction), bounds[6] = maxima over all rows / all columns (they fix the
- * fp16 scale of the gradient tiles), out[5] = {hard, soft, hard * s_hard, soft * s_soft, p_hard * out[2] + p_soft * out[3]}
- * with hard = 0.5 (CE_i2t + CE_t2i) (mean), soft = 0.5 T^2 (KL_i2t + KL_t2i) (sum) of the GLOBAL batch (_loss.py:130-137,231-234). */
+ * fp16 scale of the gradient tiles), out[9] = {hard, soft, hard s_hard, soft s_soft, total, cos_diff, logits_mse, cos_diff s_cos,
+ * logits_mse s_mse}, total = p_hard out[2] + p_soft out[3] + p_cos out[7] + p_mse out[8], with hard = 0.5 (CE_i2t + CE_t2i) (mean),
+ * soft = 0.5 T^2 (KL_i2t + KL_t2i) (sum), cos_diff = mean relu(T_ii - S_ii) + mean_{i != j} relu(S_ij - T_ij), logits_mse =
+ * mean (S - T)^2 of the GLOBAL batch (_loss.py:130-145,231-234).  weights8 (host) = {p_hard, p_soft, s_hard, s_soft, p_cos,
+ * p_mse, s_cos, s_mse}. */
 int dcb_clip_post2(const float* slots, int n_src, int64_t rows_per_src, int64_t cols, float temperature, int has_teacher,
-                   int64_t global_batch, float p_hard, float p_soft, float s_hard, float s_soft, float* col_stats,
+                   int64_t global_batch, const float* weights8, float* col_stats,
                    float* coef_col, float* bounds, float* out, void* scratch, void* stream);
 
 /* Backward, first kernel: as dcb_clip_row_grads_pair, but with UNIT coefficients multiplied on the device by
  *   up_hard = *g_total * w_hard + *g_hard * s_hard,  up_soft = *g_total * w_soft + *g_soft * s_soft
- * (0-dim fp32 device scalars from autograd, NULL = no gradient for that output; w = percent * scale), the fp16 tile scale
- * from bounds[6], and stu_b_t stored as one [dim, bt_block_cols] block per source rank ([cols / bt_block_cols][dim][pitch]). */
+ * (g5 = {g_total, g_hard, g_soft, g_cos, g_mse}: 0-dim fp32 device scalars from autograd, NULL = no gradient for that output;
+ * w8 (host) = {w_hard, w_soft, s_hard, s_soft, w_cos, w_mse, s_cos, s_mse}, w = percent * scale), the fp16 tile scale from
+ * bounds[6], and stu_b_t stored as one [dim, bt_block_cols] block per source rank ([cols / bt_block_cols][dim][pitch]).
+ * extra = 1 adds d(CLIPCosDiff)/dS_ij = up_cos [S_ij > T_ij] / (B (B - 1)) (i != j; row_offset = global index of local row 0)
+ * and d(LogitsMSE)/dS_ij = 2 up_mse (S_ij - T_ij) / B^2 to the tiles. */
 int dcb_clip_pair_bwd(const void* stu_a, const void* stu_b, const void* tea_a, const void* tea_b,
                       const void* stu_b_t, int64_t bt_pitch_elems, int64_t bt_block_cols,
                       const float* stu_a_inv, const float* stu_b_inv, const float* tea_a_inv, const float* tea_b_inv,
                       const float* coef_row, const float* coef_col, const float* bounds,
-                      const float* g_total, const float* g_hard, const float* g_soft, float w_hard, float w_soft,
-                      float s_hard, float s_soft, int64_t rows_local, int64_t cols, int64_t dim, int dtype,
+                      const float* const* g5, const float* w8, int extra, int64_t row_offset, int64_t global_batch,
+                      int64_t rows_local, int64_t cols, int64_t dim, int dtype,
                       float temperature, float* acc_parts, void* g_out, int64_t g_pitch_elems, void* stream);
 
 /* Backward, last kernel, both towers in one launch (side a = image rows from the pair kernel's accumulators, side b = text
  * rows from the G^T GEMM's): grad[i,:] = r_i (acc_i - x_hat_i (x_hat_i . acc_i)), acc_i = 2^-k sum_s acc[s][i,:] - (up_hard / B)
- * y_hat_{label_offset + i}.  A side with grad == NULL is skipped. */
+ * y_hat_{label_offset + i}.  A side with grad == NULL is skipped.  cos_flag (optional, [rows] = coef_row row 3): the diagonal
+ * term of CLIPCosDiff, -up_cos [T_ii > S_ii] / B, joins the label term (and the tiles carried the extra terms). */
 int dcb_clip_finish2(const float* acc_a, int n_split_a, int64_t split_stride_a, const void* a, const float* a_inv, void* grad_a,
                      int64_t rows_a, const void* a_label, const float* a_label_inv, int64_t a_label_rows, int64_t a_label_offset,
                      const float* acc_b, int n_split_b, int64_t split_stride_b, const void* b, const float* b_inv, void* grad_b,
                      int64_t rows_b, const void* b_label, const float* b_label_inv, int64_t b_label_rows, int64_t b_label_offset,
-                     int64_t dim, int64_t global_batch, const float* g_total, const float* g_hard, const float* g_soft,
-                     float w_hard, float w_soft, float s_hard, float s_soft, const float* bounds, int in_dtype, int grad_dtype,
-                     void* stream);
+                     int64_t dim, int64_t global_batch, const float* const* g5, const float* w8, const float* cos_flag,
+                     const float* bounds, int in_dtype, int grad_dtype, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Per-module API on MATERIALISED logits (HardLabel / SoftLabel keep their logits signature).

@@ -141,7 +141,7 @@ class DoubleEngine:
                 t[:, :m.shape[0]] = (m.double() * r[:, None]).t()
 
     def fwd_chunk(self, a_s, b_s, a_t, b_t, a_s_inv, b_s_inv, a_t_inv, b_t_inv, label_col0, temperature, ws_chunk, diag,
-                  col_part_chunk, col_part_ld):
+                  col_part_chunk, col_part_ld, ws_extra=None, diag_t=None):
         S = self._logits(a_s, b_s, a_s_inv, b_s_inv)
         rows, cols = S.shape
         ws_chunk.zero_()
@@ -158,6 +158,10 @@ class DoubleEngine:
             ws_chunk[0, 1], col_part_chunk[0, 1] = q.sum(1), q.sum(0)
             ws_chunk[0, 2], col_part_chunk[0, 2] = et.sum(1), et.sum(0)
             ws_chunk[0, 3], col_part_chunk[0, 3] = (et * (T - S)).sum(1), (et * (T - S)).sum(0)
+            if ws_extra is not None:
+                ws_extra.zero_()
+                ws_extra[0, 0], ws_extra[0, 1] = torch.relu(S - T).sum(1), ((S - T) ** 2).sum(1)
+                diag_t[hit] = T[torch.arange(rows)[hit], lab[hit]]
 
     @staticmethod
     def _unit_coefs(st, global_batch, temperature, has_teacher):
@@ -168,19 +172,26 @@ class DoubleEngine:
             c[2] = 0.5 * temperature / st[2]
         return c
 
-    def post1(self, ws, diag, col_part, temperature, has_teacher, global_batch, stats, coef_row, dests):
+    def post1(self, ws, diag, col_part, temperature, has_teacher, global_batch, stats, coef_row, dests, ws_extra=None, diag_t=None):
         from distillclip_b200.pipeline import slot_floats, slot_tail
         rows, cols = diag.shape[0], col_part.shape[2]
         stats[:4] = ws.sum(0)
         stats[4] = diag
         rl = self._rowloss(stats, temperature, has_teacher)
-        coef_row.copy_(self._unit_coefs(stats, global_batch, temperature, has_teacher))
+        coef_row.zero_()
+        coef_row[:3] = self._unit_coefs(stats, global_batch, temperature, has_teacher)
         slot = torch.zeros(slot_floats(cols, rows), dtype=torch.float64)
         slot[:4 * cols] = col_part.sum(0).reshape(-1)
         slot[4 * cols:4 * cols + rows] = diag
         tail = slot_tail(cols, rows)
         slot[tail], slot[tail + 1] = rl[0].sum(), rl[1].sum()
-        slot[tail + 4:tail + 7] = coef_row.max(1).values
+        if ws_extra is not None:
+            x = ws_extra.sum(0)
+            slot[tail + 2] = torch.relu(diag_t - diag).sum()
+            slot[tail + 3] = x[0].sum() - torch.relu(diag - diag_t).sum()
+            slot[tail + 4] = x[1].sum()
+            coef_row[3] = (diag_t > diag).double()
+        slot[tail + 10:tail + 13] = coef_row[:3].max(1).values
         for d in dests:
             d.copy_(slot)
 
@@ -195,32 +206,48 @@ class DoubleEngine:
         coef_col = self._unit_coefs(st, cols, temperature, has_teacher)
         hard = 0.5 * (slots[:, tail].sum() + rl[0].sum()) / cols
         soft = 0.5 * (temperature or 1.0) ** 2 * (slots[:, tail + 1].sum() + rl[1].sum())
-        p_h, p_s, s_h, s_s = weights
-        out = torch.stack([hard, soft, hard * s_h, soft * s_s, hard * s_h * p_h + soft * s_s * p_s])
-        bounds = torch.cat([slots[:, tail + 4:tail + 7].max(0).values, coef_col.max(1).values])
+        cosd = slots[:, tail + 2].sum() / cols + (slots[:, tail + 3].sum() / (cols * (cols - 1.0)) if cols > 1 else 0.0)
+        lmse = slots[:, tail + 4].sum() / (float(cols) * cols)
+        p_h, p_s, s_h, s_s, p_c, p_m, s_c, s_m = weights
+        out = torch.stack([hard, soft, hard * s_h, soft * s_s,
+                           hard * s_h * p_h + soft * s_s * p_s + cosd * s_c * p_c + lmse * s_m * p_m,
+                           cosd, lmse, cosd * s_c, lmse * s_m])
+        bounds = torch.cat([slots[:, tail + 10:tail + 13].max(0).values, coef_col.max(1).values])
         return st[:4].clone(), coef_col, bounds, out
 
     @staticmethod
     def _ups(up):
-        g_t, g_h, g_s, w_h, w_s, s_h, s_s = up
+        g5, w8 = up
         f = lambda g: 0.0 if g is None else float(g)
-        return f(g_t) * w_h + f(g_h) * s_h, f(g_t) * w_s + f(g_s) * s_s
+        gt = f(g5[0])
+        return (gt * w8[0] + f(g5[1]) * w8[2], gt * w8[1] + f(g5[2]) * w8[3], gt * w8[4] + f(g5[3]) * w8[6], gt * w8[5] + f(g5[4]) * w8[7])
 
     @staticmethod
-    def _scale2(bounds, up_h, up_s):
+    def _scale2(bounds, ups, batch, extra):
+        up_h, up_s, up_c, up_m = ups
         gmax = abs(up_h) * (bounds[0] + bounds[3]) + abs(up_s) * (bounds[1] + bounds[2] + bounds[4] + bounds[5])
+        if extra:
+            gmax = gmax + abs(up_c) / (batch * (batch - 1.0)) + abs(up_m) * 4.0 / (batch * batch)
+        gmax = torch.as_tensor(gmax, dtype=torch.float64)
         return 2.0 ** (14 - torch.frexp(gmax)[1].item()) if float(gmax) > 0 else 1.0
 
     def pair_bwd(self, a_s, b_s, a_t, b_t, bt_all, a_s_inv, b_s_inv, a_t_inv, b_t_inv, coef_row, coef_col, bounds, up,
-                 temperature, g_out):
-        up_h, up_s = self._ups(up)
+                 temperature, g_out, extra=False, row_offset=0):
+        ups = self._ups(up)
+        up_h, up_s, up_c, up_m = ups
         S = self._logits(a_s, b_s, a_s_inv, b_s_inv)
+        batch = S.shape[1]
         G = torch.exp(S - 1) * up_h * (coef_row[0][:, None] + coef_col[0][None, :])
         if a_t is not None:
             T = self._logits(a_t, b_t, a_t_inv, b_t_inv)
             G = G + torch.exp((S - 1) / temperature) * up_s * (coef_row[1][:, None] + coef_col[1][None, :])
             G = G - torch.exp((T - 1) / temperature) * up_s * (coef_row[2][:, None] + coef_col[2][None, :])
-        scale = self._scale2(bounds, up_h, up_s)
+            if extra:
+                off = torch.ones_like(S, dtype=torch.bool)
+                idx = torch.arange(S.shape[0])
+                off[idx, row_offset + idx] = False
+                G = G + up_c / (batch * (batch - 1.0)) * ((S > T) & off).double() + 2.0 * up_m / (batch * batch) * (S - T)
+        scale = self._scale2(bounds, ups, batch, extra)
         assert float((G.abs() * scale).max()) <= 2.0 ** 14
         if g_out is not None:
             g_out[:, :G.shape[1]] = G * scale
@@ -228,9 +255,10 @@ class DoubleEngine:
         b_hat_t = torch.cat([bt_all[r][:, :n] for r in range(bt_all.shape[0])], dim=1)        # [D, B]
         return ((G * scale) @ b_hat_t.t())[None]
 
-    def finish2(self, side_a, side_b, global_batch, up, bounds, grad_dtype):
-        up_h, up_s = self._ups(up)
-        scale = self._scale2(bounds, up_h, up_s)
+    def finish2(self, side_a, side_b, global_batch, up, bounds, grad_dtype, cos_flag=None):
+        ups = self._ups(up)
+        up_h, up_s, up_c, up_m = ups
+        scale = self._scale2(bounds, ups, global_batch, cos_flag is not None)
         out = []
         for sd in (side_a, side_b):
             if sd is None:
@@ -239,7 +267,9 @@ class DoubleEngine:
             x, x_inv = sd["x"].double(), sd["x_inv"]
             acc = sd["acc"].sum(0) / scale
             gi = sd["label_offset"] + torch.arange(x.shape[0])
-            acc = acc - (up_h / global_batch) * sd["y_inv"][gi][:, None] * sd["y"].double()[gi]
+            lab = up_h + (up_c * cos_flag if cos_flag is not None else 0.0)
+            acc = acc - (lab / global_batch)[:, None] * sd["y_inv"][gi][:, None] * sd["y"].double()[gi] if cos_flag is not None else \
+                acc - (up_h / global_batch) * sd["y_inv"][gi][:, None] * sd["y"].double()[gi]
             x_hat = x * x_inv[:, None]
             out.append(x_inv[:, None] * (acc - x_hat * (x_hat * acc).sum(1, keepdim=True)))
         return out[0], out[1]

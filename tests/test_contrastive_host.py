@@ -128,16 +128,40 @@ def test_retrieval_metrics_sharded_world2_gloo():
 # ----------------------------------------------------------------------------------------------
 # the pipeline flow (distillclip_b200/pipeline.py): stage boundaries, slot layout, exchanges, buffer-set bookkeeping
 # ----------------------------------------------------------------------------------------------
-def _run_pipeline(g, weights, ups, group=None, rows=slice(None), hard_only=False):
+def _run_pipeline(g, weights, ups, group=None, rows=slice(None), hard_only=False, extra=False):
     from distillclip_b200 import pipeline as pl
     T = float(g["temperature"])
     si, st = torch.tensor(g["stu_img"])[rows].double(), torch.tensor(g["stu_txt"])[rows].double()
     ti, tt = (None, None) if hard_only else (torch.tensor(g["tea_img"])[rows].double(), torch.tensor(g["tea_txt"])[rows].double())
     eng = DoubleEngine()
     xc = pl.LocalExchange() if group is None else pl.CollectiveExchange(group)
-    out, saved = pl.pipeline_forward(eng, xc, si, st, ti, tt, None if hard_only else T, weights)
+    out, saved = pl.pipeline_forward(eng, xc, si, st, ti, tt, None if hard_only else T, weights, extra)
     gi, gt = pl.pipeline_backward(eng, saved, ups)
     return out, gi, gt, xc, saved
+
+
+@pytest.mark.parametrize("name", CLIP)
+def test_pipeline_cos_diff_and_logits_mse_from_embeddings(name):
+    """CLIPCosDiff (clip_cos_diff.py:5-23) and LogitsMSE (logits_mse.py:9-10) from the same tiles: values = the reference on
+    materialised logits (0.5 (i2t + t2i), _loss.py:138-145); gradients incl. the diagonal term and exact off-diagonal set."""
+    g = golden(name)
+    T = float(g["temperature"])
+    s, _ = cf.clip_logits(g["stu_img"], g["stu_txt"])
+    t, _ = cf.clip_logits(g["tea_img"], g["tea_txt"])
+    cd, g_cd = cf.cos_diff(s, t)
+    cd2, g_cd2 = cf.cos_diff(s.T, t.T)
+    lm, g_lm = cf.logits_mse(s, t)
+    w = (0.2, 0.1, 1.0, 1.0, 0.4, 0.3, 2.0, 0.5)        # p_hard, p_soft, s_hard, s_soft, p_cos, p_mse, s_cos, s_mse
+    out, gi, gt, _, _ = _run_pipeline(g, w, (torch.tensor(1.0), None, None, torch.tensor(0.25), None), extra=True)
+    assert float(out[5]) == pytest.approx(0.5 * (cd + cd2), rel=1e-10) and float(out[6]) == pytest.approx(lm, rel=1e-10)
+    assert float(out[7]) == pytest.approx(2.0 * 0.5 * (cd + cd2), rel=1e-10)
+    hard, soft = float(g["hard_f64"]), float(g["soft_f64"])
+    assert float(out[4]) == pytest.approx(0.2 * hard + 0.1 * soft + 0.4 * 2.0 * 0.5 * (cd + cd2) + 0.3 * 0.5 * lm, rel=1e-9)
+    ref = cf.contrastive_from_embeddings(g["stu_img"], g["stu_txt"], g["tea_img"], g["tea_txt"], T, w_hard=0.2, w_soft=0.1)
+    w_cos = 0.4 * 2.0 + 0.25 * 2.0                          # g_total * p * s + g_cos * s
+    dl = ref["d_logits"] + w_cos * 0.5 * (g_cd + g_cd2.T) + 0.3 * 0.5 * g_lm
+    d_img, d_txt = cf.clip_logits_backward(g["stu_img"], g["stu_txt"], dl)
+    assert rel_l2(gi.numpy(), d_img) <= 1e-8 and rel_l2(gt.numpy(), d_txt) <= 1e-8
 
 
 @pytest.mark.parametrize("name", CLIP)
@@ -163,7 +187,7 @@ def test_pipeline_weighting_and_upstream_routes():
     g_total, g_soft = torch.tensor(1.5), torch.tensor(-0.5)
     out, gi, gt, _, _ = _run_pipeline(g, (p_h, p_s, s_h, s_s), (g_total, None, g_soft))
     hard, soft = float(g["hard_f64"]), float(g["soft_f64"])
-    assert out.numpy() == pytest.approx([hard, soft, hard * s_h, soft * s_s, p_h * hard * s_h + p_s * soft * s_s], rel=1e-9)
+    assert out[:5].numpy() == pytest.approx([hard, soft, hard * s_h, soft * s_s, p_h * hard * s_h + p_s * soft * s_s], rel=1e-9)
     ref = cf.contrastive_from_embeddings(g["stu_img"], g["stu_txt"], g["tea_img"], g["tea_txt"], T,
                                          w_hard=1.5 * p_h * s_h, w_soft=1.5 * p_s * s_s - 0.5 * s_s)
     assert rel_l2(gi.numpy(), ref["d_img"]) <= 1e-8 and rel_l2(gt.numpy(), ref["d_txt"]) <= 1e-8
@@ -197,8 +221,8 @@ def _pipeline_worker(rank, world, port, name, q):
     pl.check_equal_batches(dist.group.WORLD, b, torch.device("cpu"))
     res = []
     for step in range(3):                          # three steps: buffer sets are reused, results must not change
-        out, gi, gt, _, _ = _run_pipeline(g, (0.75, 0.5, 1.0, 1.0), (torch.tensor(1.0), None, None), group=dist.group.WORLD,
-                                          rows=slice(rank * b, (rank + 1) * b))
+        out, gi, gt, _, _ = _run_pipeline(g, (0.75, 0.5, 1.0, 1.0, 0.25, 0.5, 1.0, 1.0), (torch.tensor(1.0), None, None),
+                                          group=dist.group.WORLD, rows=slice(rank * b, (rank + 1) * b), extra=True)
         res.append((out.numpy(), gi.numpy(), gt.numpy()))
     q.put((rank, res))
     dist.barrier()
@@ -212,6 +236,13 @@ def test_pipeline_row_sharded_gloo(name, world):
     g = golden(name)
     T = float(g["temperature"])
     ref = cf.contrastive_from_embeddings(g["stu_img"], g["stu_txt"], g["tea_img"], g["tea_txt"], T, w_hard=0.75, w_soft=0.5)
+    s_l, _ = cf.clip_logits(g["stu_img"], g["stu_txt"])
+    t_l, _ = cf.clip_logits(g["tea_img"], g["tea_txt"])
+    cd, g_cd = cf.cos_diff(s_l, t_l)
+    lm, g_lm = cf.logits_mse(s_l, t_l)
+    _, g_cd2 = cf.cos_diff(s_l.T, t_l.T)
+    d_img, d_txt = cf.clip_logits_backward(g["stu_img"], g["stu_txt"], ref["d_logits"] + 0.25 * 0.5 * (g_cd + g_cd2.T) + 0.5 * g_lm)
+    ref = dict(ref, d_img=d_img, d_txt=d_txt, cos=cd, mse=lm)
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = 29500 + (os.getpid() + 31 * world) % 2000
@@ -227,7 +258,8 @@ def test_pipeline_row_sharded_gloo(name, world):
             out = steps[step][0]
             assert float(out[0]) == pytest.approx(ref["hard"], rel=1e-10)
             assert float(out[1]) == pytest.approx(ref["soft"], rel=1e-9)
-            assert float(out[4]) == pytest.approx(0.75 * ref["hard"] + 0.5 * ref["soft"], rel=1e-9)
+            assert float(out[4]) == pytest.approx(0.75 * ref["hard"] + 0.5 * ref["soft"] + 0.25 * ref["cos"] + 0.5 * ref["mse"], rel=1e-9)
+            assert float(out[5]) == pytest.approx(ref["cos"], rel=1e-10) and float(out[6]) == pytest.approx(ref["mse"], rel=1e-10)
         assert rel_l2(np.concatenate([r[1][step][1] for r in res]), ref["d_img"]) <= 1e-8
         assert rel_l2(np.concatenate([r[1][step][2] for r in res]), ref["d_txt"]) <= 1e-8
 

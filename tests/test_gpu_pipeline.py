@@ -93,6 +93,56 @@ def test_public_call_weighting_and_upstream_routes(cuda_device):
     assert all(v == vals[0] for v in vals) and vals[0] == pytest.approx(ref0["soft"], rel=LOSS_RTOL)
 
 
+def _extras_oracle(si, st, ti, tt, T, w):
+    """values and gradients of p_h hard + p_s soft + p_c s_c cos_diff + p_m s_m logits_mse from the float64 closed forms."""
+    f = lambda x: x.float().cpu().numpy()
+    s, _ = cf.clip_logits(f(si), f(st))
+    t, _ = cf.clip_logits(f(ti), f(tt))
+    cd, g_cd = cf.cos_diff(s, t)
+    cd2, g_cd2 = cf.cos_diff(s.T, t.T)
+    lm, g_lm = cf.logits_mse(s, t)
+    p_h, p_s, s_h, s_s, p_c, p_m, s_c, s_m = w
+    ref = cf.contrastive_from_embeddings(f(si), f(st), f(ti), f(tt), T, w_hard=p_h * s_h, w_soft=p_s * s_s)
+    dl = ref["d_logits"] + p_c * s_c * 0.5 * (g_cd + g_cd2.T) + p_m * s_m * 0.5 * (g_lm + g_lm.T.T)
+    d_img, d_txt = cf.clip_logits_backward(f(si), f(st), dl)
+    return dict(hard=ref["hard"], soft=ref["soft"], cos=0.5 * (cd + cd2), mse=lm, d_img=d_img, d_txt=d_txt)
+
+
+@pytest.mark.parametrize("b,d,T", [(256, 512, 2.0), (384, 768, 4.0), (130, 72, 1.0), (520, 64, 2.0)])
+def test_pipeline_cos_diff_logits_mse_vs_oracle(cuda_device, b, d, T):
+    """CLIPCosDiff (reference clip_cos_diff.py:5-23: exact off-diagonal set, diagonal term) and LogitsMSE (logits_mse.py:9-10)
+    from the embeddings inside the fused kernels, alone and mixed with hard / soft label."""
+    from distillclip_b200 import contrastive as ct, pipeline as pl
+    si, st, ti, tt = [x.cuda() for x in synth(b, d, b + d)]
+    for w in ((0.0, 0.0, 1.0, 1.0, 1.0, 0.0, 1.0, 1.0), (0.0, 0.0, 1.0, 1.0, 0.0, 1.0, 1.0, 1.0), (0.3, 0.2, 1.0, 2.0, 0.4, 0.1, 0.5, 3.0)):
+        ref = _extras_oracle(si, st, ti, tt, T, w)
+        out, saved = pl.pipeline_forward(ct._ENGINE, pl.LocalExchange(), si, st, ti, tt, T, w, extra=True)
+        gi, gt = pl.pipeline_backward(ct._ENGINE, saved, (_one(), None, None, None, None), grad_dtype=torch.float32)
+        assert float(out[5]) == pytest.approx(ref["cos"], rel=LOSS_RTOL)
+        assert float(out[6]) == pytest.approx(ref["mse"], rel=LOSS_RTOL)
+        want = w[0] * w[2] * ref["hard"] + w[1] * w[3] * ref["soft"] + w[4] * w[6] * ref["cos"] + w[5] * w[7] * ref["mse"]
+        assert float(out[4]) == pytest.approx(want, rel=LOSS_RTOL)
+        # the indicator [S_ij > T_ij] can flip where |S - T| is at rounding level: budget 2e-3 for the pure cos_diff gradient
+        tol = 2e-3 if w[4] else GRAD_RTOL
+        assert rel_l2(gi.cpu().numpy(), ref["d_img"]) <= tol
+        assert rel_l2(gt.cpu().numpy(), ref["d_txt"]) <= tol
+
+
+def test_public_call_cos_diff_only(cuda_device):
+    """The shipped stage-3 loss list has cos_diff and no hard / soft label: clip_contrastive(want_cos_diff=True) alone."""
+    from distillclip_b200.contrastive import clip_contrastive
+    si, st, ti, tt = [x.cuda() for x in synth(256, 128, 3)]
+    a, c = si.clone().requires_grad_(True), st.clone().requires_grad_(True)
+    res = clip_contrastive(a, c, ti, tt, None, want_hard=False, want_soft=False, want_cos_diff=True, want_logits_mse=True)
+    assert set(res) == {"cos_diff", "logits_mse"}
+    (res["cos_diff"] + 2.0 * res["logits_mse"]).backward()
+    ref = _extras_oracle(si, st, ti, tt, 1.0, (0.0, 0.0, 1.0, 1.0, 1.0, 2.0, 1.0, 1.0))
+    assert float(res["cos_diff"]) == pytest.approx(ref["cos"], rel=LOSS_RTOL)
+    assert float(res["logits_mse"]) == pytest.approx(ref["mse"], rel=LOSS_RTOL)
+    assert rel_l2(a.grad.float().cpu().numpy(), ref["d_img"]) <= GRAD_BF16_STORAGE_RTOL
+    assert rel_l2(c.grad.float().cpu().numpy(), ref["d_txt"]) <= GRAD_BF16_STORAGE_RTOL
+
+
 class VirtualExchange:
     """R ranks inside one process (TEST INFRASTRUCTURE): the text-side buffers are shared, every virtual rank owns its
     statistics slots and text-gradient partial buffers, the 'peers' are reached through ordinary tensors.  The caller runs
@@ -160,16 +210,17 @@ def test_pipeline_virtual_ranks(cuda_device, R, b, d, T, teacher, chunked):
     si, st, ti, tt = [x.cuda() for x in synth(b, d, 21 + R)]
     if not teacher:
         ti = tt = None
-    w = (0.75, 0.5 if teacher else 0.0, 1.0, 1.0)
-    ref = cf.contrastive_from_embeddings(si.float().cpu().numpy(), st.float().cpu().numpy(),
-                                         ti.float().cpu().numpy() if teacher else None, tt.float().cpu().numpy() if teacher else None,
-                                         T if teacher else None, w_hard=w[0], w_soft=w[1])
+    w = (0.75, 0.5, 1.0, 1.0, 0.3, 0.2, 1.0, 1.0) if teacher else (0.75, 0.0, 1.0, 1.0)
+    if teacher:
+        ref = _extras_oracle(si, st, ti, tt, T, w)
+    else:
+        ref = cf.contrastive_from_embeddings(si.float().cpu().numpy(), st.float().cpu().numpy(), w_hard=w[0])
     n = b // R
     shared = {}
     xcs = [VirtualExchange(R, r, shared, chunked) for r in range(R)]
     loc = [slice(r * n, (r + 1) * n) for r in range(R)]
     vs = [pl.forward_prep(eng, xcs[r], si[loc[r]].contiguous(), st[loc[r]].contiguous(), ti[loc[r]].contiguous() if teacher else None,
-                          tt[loc[r]].contiguous() if teacher else None, T if teacher else None, w) for r in range(R)]
+                          tt[loc[r]].contiguous() if teacher else None, T if teacher else None, w, teacher) for r in range(R)]
     for r in range(R):
         pl.forward_tiles(eng, vs[r])
     outs = [pl.forward_finish(eng, vs[r]) for r in range(R)]
@@ -179,6 +230,8 @@ def test_pipeline_virtual_ranks(cuda_device, R, b, d, T, teacher, chunked):
     assert float(outs[0][0]) == pytest.approx(ref["hard"], rel=LOSS_RTOL)
     if teacher:
         assert float(outs[0][1]) == pytest.approx(ref["soft"], rel=LOSS_RTOL)
+        assert float(outs[0][5]) == pytest.approx(ref["cos"], rel=LOSS_RTOL)
+        assert float(outs[0][6]) == pytest.approx(ref["mse"], rel=LOSS_RTOL)
     ups = (_one(), None, None)
     for r in range(R):
         pl.backward_gemms(eng, vs[r], ups)

@@ -122,19 +122,25 @@ def test_shipped_one_tower_recipes(cuda_device, name, kwargs):
     _check_calc(g, loss, res, _leaves(stu))
 
 
-def test_shipped_lclip_recipe(cuda_device):
-    """config/final_config/l_clip.yaml ships ['out_l1', 'out_cos', 'cos_diff']; cos_diff reads the caller's logits
-    (CLIPModel.forward, reference clip_model.py:36-44), gradients flow back through them to the embeddings."""
+@pytest.mark.parametrize("route", ["lazy_logits", "fused_with_logits_present", "logits_modules"])
+def test_shipped_lclip_recipe(cuda_device, route):
+    """config/final_config/l_clip.yaml ships ['out_l1', 'out_cos', 'cos_diff'].  lazy_logits: the CLIPOutput carries NO logits
+    (LazyLogitsCLIP) and cos_diff comes from the embeddings inside the fused tcgen05 kernels (no B x B matrix
+    anywhere); logits_modules: CLIPCosDiff on the caller's logits (CLIPModel.forward, reference clip_model.py:36-44)."""
     from distillclip_b200.model import (CLIPOutput, LossCalculator, TextTransformerOutput, VisionTransformerOutput)
     g = golden("calc_shipped_lclip")
     sv, stx = _tower(g, "stu.visual", VisionTransformerOutput, True), _tower(g, "stu.text", TextTransformerOutput, True)
     tv, ttx = _tower(g, "tea.visual", VisionTransformerOutput, False), _tower(g, "tea.text", TextTransformerOutput, False)
 
     def clip_out(v, x):
+        if route == "lazy_logits":
+            return CLIPOutput(visual_output=v, text_output=x)
         a, b = v.last_representation.float(), x.last_representation.float()
         lg = (a / a.norm(dim=1, keepdim=True)) @ (b / b.norm(dim=1, keepdim=True)).t()
         return CLIPOutput(visual_output=v, text_output=x, i2t_logits=lg, t2i_logits=lg.T)
-    loss, res = LossCalculator(["out_l1", "out_cos", "cos_diff"])(clip_out(sv, stx), clip_out(tv, ttx), "all")
+    calc = LossCalculator(["out_l1", "out_cos", "cos_diff"])
+    calc.fused_contrastive = route != "logits_modules"
+    loss, res = calc(clip_out(sv, stx), clip_out(tv, ttx), "all")
     loss.backward()
     _check_calc(g, loss, res, _leaves(sv) + _leaves(stx))
 
@@ -181,7 +187,7 @@ def test_out_kl_ce_one_tower_recipe(cuda_device):
     _check_calc(g, loss, res, _leaves(stu))
 
 
-@pytest.mark.parametrize("fused", [True, False])
+@pytest.mark.parametrize("fused", [True, False, "lazy"])
 def test_out_kl_ce_logits_mse_two_tower_recipe(cuda_device, fused):
     from distillclip_b200.model import (CLIPOutput, LossCalculator, TextTransformerOutput, VisionTransformerOutput)
     g = golden("calc_out_kl_ce_logits_mse")
@@ -189,11 +195,13 @@ def test_out_kl_ce_logits_mse_two_tower_recipe(cuda_device, fused):
     tv, ttx = _tower(g, "tea.visual", VisionTransformerOutput, False), _tower(g, "tea.text", TextTransformerOutput, False)
 
     def clip_out(v, x):
+        if fused == "lazy":                  # no logits at all: logits_mse and hard_label both from the embeddings
+            return CLIPOutput(visual_output=v, text_output=x)
         a, b = v.last_representation.float(), x.last_representation.float()
         lg = (a / a.norm(dim=1, keepdim=True)) @ (b / b.norm(dim=1, keepdim=True)).t()
         return CLIPOutput(visual_output=v, text_output=x, i2t_logits=lg, t2i_logits=lg.T)
     calc = LossCalculator(["out_kl", "out_ce", "logits_mse", "hard_label"], temperature=2.0, loss_scale={"out_kl": 0.1})
-    calc.fused_contrastive = fused
+    calc.fused_contrastive = bool(fused)
     loss, res = calc(clip_out(sv, stx), clip_out(tv, ttx), "all")
     loss.backward()
     _check_calc(g, loss, res, _leaves(sv) + _leaves(stx))
