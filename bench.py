@@ -578,7 +578,7 @@ def clip_kernel_times(cfg, glob, rank, world, device, pk):
     fwd = lambda: eng.fwd_chunk(a_s, st, a_t, tt, inv[0], inv[1], inv[2], inv[3], off, T, ws, diag, col_part, b)
     fwd()
     stats = torch.empty(5, rows, dtype=torch.float32, device=device)
-    coef_row = torch.empty(3, rows, dtype=torch.float32, device=device)
+    coef_row = torch.empty(4, rows, dtype=torch.float32, device=device)
     slots = torch.empty(1, pl.slot_floats(b, rows), dtype=torch.float32, device=device)
     eng.post1(ws, diag, col_part, T, True, b, stats, coef_row, [slots[0]])
     # column coefficients of all B columns: a full one-rank forward on the global batch would give the exact ones; for timing
@@ -587,10 +587,10 @@ def clip_kernel_times(cfg, glob, rank, world, device, pk):
     fake.zero_()
     fake[0, :4 * b] = slots[0, :4 * b] * world
     fake[0, 4 * b:5 * b] = 0.5
-    _, coef_col, bounds, _ = eng.post2(fake, b, b, T, True, (0.5, 0.5, 1.0, 1.0))
+    _, coef_col, bounds, _ = eng.post2(fake, b, b, T, True, (0.5, 0.5, 1.0, 1.0, 0.0, 0.0, 1.0, 1.0))
     bounds[:3] = bounds[3:]
     one = torch.ones((), dtype=torch.float32, device=device)
-    up = (one, None, None, 0.5, 0.5, 1.0, 1.0)
+    up = ((one, None, None, None, None), (0.5, 0.5, 1.0, 1.0, 0.0, 0.0, 1.0, 1.0))
     out = {}
     flush = L2Flush(device)
     g = eng.alloc_g(rows, b, device)

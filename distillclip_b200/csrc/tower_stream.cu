@@ -25,6 +25,7 @@ struct TowerSeg {
     long long tile_begin;
     long long positions;   // ATTN
     long long groups_per_b;
+    long long total_s, total_t;   // ATTN, aligned mode: elements of the student / teacher tensor
     int kind;              // 0 = MSE, 1 = attention KL, 2 = L1, 3 = cosine rows, 4 = attention (head-mean) MSE
     int term;
     int hs, ht;
@@ -53,8 +54,12 @@ struct TowerParams {
     TowerSeg seg[kTowerMaxSeg];
 };
 
-template <typename T, typename G, int AVEC, int AH>
-__global__ void __launch_bounds__(kStreamThreads, 4) tower_stream_kernel(const __grid_constant__ TowerParams p) {
+// GPT = attention groups per thread (stream_tiles.cuh: attn_tile_multi): 2 keeps twice the loads in flight (image stage
+// attention tiles 0.76 -> 0.86 of HBM, scripts/attn_gpt_probe.py) at ~90 registers, hence 2 resident CTAs instead of 4.
+// AVEC = 0: attention tiles on aligned 16-byte accesses with in-register realignment (attn_tile_aligned), for 16-bit maps
+// whose head rows are off the 16-byte grid.
+template <typename T, typename G, int AVEC, int AH, int GPT>
+__global__ void __launch_bounds__(kStreamThreads, (AVEC == 0 || GPT > 1) ? 2 : 4) tower_stream_kernel(const __grid_constant__ TowerParams p) {
     constexpr int MVEC = Elem<T>::kPer16B;
     constexpr long long kMseTile = (long long)kStreamThreads * kMseUnroll * MVEC;
     constexpr long long kMseTileScalar = (long long)kStreamThreads * kMseUnroll;
@@ -122,12 +127,34 @@ __global__ void __launch_bounds__(kStreamThreads, 4) tower_stream_kernel(const _
                                      (int)sg.positions, lt * (kStreamThreads / 32) + (tid >> 5), gcoef, tid & 31);
         } else {
             AttnShape sh{sg.n, sg.groups_per_b, sg.positions, sg.hs, sg.ht, sg.inv_hs, sg.inv_ht};
-            if (sg.kind == 1)
-                acc = attn_tile<T, G, AVEC, AH, false>(static_cast<const T*>(sg.s), static_cast<const T*>(sg.t),
-                                                       static_cast<G*>(sg.g), sh, lt * kStreamThreads + tid, gcoef);
-            else
-                acc = attn_tile<T, G, AVEC, AH, true>(static_cast<const T*>(sg.s), static_cast<const T*>(sg.t),
-                                                      static_cast<G*>(sg.g), sh, lt * kStreamThreads + tid, gcoef);
+            if constexpr (AVEC == 0) {
+                __shared__ uint4 xchg[kStreamThreads];
+                acc = 0.f;
+                if constexpr (sizeof(T) == 2 && sizeof(G) == 2) {
+                    AttnShape8 sh8{sg.n, sg.groups_per_b, sg.positions, sg.total_s, sg.total_t, sg.hs, sg.ht, sg.inv_hs, sg.inv_ht};
+                    if (sg.kind == 1)
+                        acc = attn_tile_aligned<T, G, AH, false>(static_cast<const T*>(sg.s), static_cast<const T*>(sg.t),
+                                                                 static_cast<G*>(sg.g), sh8, lt * kStreamThreads + tid, gcoef, xchg, tid);
+                    else
+                        acc = attn_tile_aligned<T, G, AH, true>(static_cast<const T*>(sg.s), static_cast<const T*>(sg.t),
+                                                                static_cast<G*>(sg.g), sh8, lt * kStreamThreads + tid, gcoef, xchg, tid);
+                }
+            } else if constexpr (GPT > 1 && AH > 0) {
+                const long long g0 = lt * (kStreamThreads * GPT) + tid;
+                if (sg.kind == 1)
+                    acc = attn_tile_multi<T, G, AVEC, AH, false, GPT>(static_cast<const T*>(sg.s), static_cast<const T*>(sg.t),
+                                                                      static_cast<G*>(sg.g), sh, g0, kStreamThreads, gcoef);
+                else
+                    acc = attn_tile_multi<T, G, AVEC, AH, true, GPT>(static_cast<const T*>(sg.s), static_cast<const T*>(sg.t),
+                                                                     static_cast<G*>(sg.g), sh, g0, kStreamThreads, gcoef);
+            } else {
+                if (sg.kind == 1)
+                    acc = attn_tile<T, G, AVEC, AH, false>(static_cast<const T*>(sg.s), static_cast<const T*>(sg.t),
+                                                           static_cast<G*>(sg.g), sh, lt * kStreamThreads + tid, gcoef);
+                else
+                    acc = attn_tile<T, G, AVEC, AH, true>(static_cast<const T*>(sg.s), static_cast<const T*>(sg.t),
+                                                          static_cast<G*>(sg.g), sh, lt * kStreamThreads + tid, gcoef);
+            }
         }
         cur += (double)acc * (double)sg.val_coef;
     }
@@ -168,19 +195,39 @@ __global__ void __launch_bounds__(kStreamThreads, 4) tower_stream_kernel(const _
     }
 }
 
+// attention groups per thread for this launch (0 = no attention segment with a compile-time head count)
+static int tower_gpt(int avec, int common_h) {
+    if (!(common_h == 12 || common_h == 8) || avec > 4) return 1;
+    // measured (scripts/attn_gpt_probe.py): 2 groups per thread lift the stand-alone attention kernel (image stage 0.76 -> 0.86
+    // of HBM) but not the tower launch, where the MSE tiles prefer 4 resident CTAs (image 0.89 either way, text 0.72 -> 0.68)
+    if (const char* e = getenv("DCB_ATTN_GPT")) return atoi(e) == 2 ? 2 : 1;
+    return 1;
+}
+
 template <typename T, typename G, int AVEC>
 static int launch_tower_h(const TowerParams& p, int common_h, unsigned grid, cudaStream_t st) {
     bool done = false;
-    if constexpr (AVEC <= 4) {          // head loops fully unrolled for the two head counts of the BASELINE configs
+    if constexpr (AVEC == 0) {
+        if (common_h == 12) tower_stream_kernel<T, G, 0, 12, 1><<<grid, kStreamThreads, 0, st>>>(p);
+        else if (common_h == 8) tower_stream_kernel<T, G, 0, 8, 1><<<grid, kStreamThreads, 0, st>>>(p);
+        else tower_stream_kernel<T, G, 0, 0, 1><<<grid, kStreamThreads, 0, st>>>(p);
+        DCB_CUDA_OK(cudaGetLastError());
+        return 0;
+    } else if constexpr (AVEC <= 4) {          // head loops fully unrolled for the two head counts of the BASELINE configs
+        const int gpt = tower_gpt(AVEC, common_h);
         if (common_h == 12) {
-            tower_stream_kernel<T, G, AVEC, 12><<<grid, kStreamThreads, 0, st>>>(p);
+            if (gpt == 2) tower_stream_kernel<T, G, AVEC, 12, 2><<<grid, kStreamThreads, 0, st>>>(p);
+            else tower_stream_kernel<T, G, AVEC, 12, 1><<<grid, kStreamThreads, 0, st>>>(p);
             done = true;
         } else if (common_h == 8) {
-            tower_stream_kernel<T, G, AVEC, 8><<<grid, kStreamThreads, 0, st>>>(p);
+            if (gpt == 2) tower_stream_kernel<T, G, AVEC, 8, 2><<<grid, kStreamThreads, 0, st>>>(p);
+            else tower_stream_kernel<T, G, AVEC, 8, 1><<<grid, kStreamThreads, 0, st>>>(p);
             done = true;
         }
     }
-    if (!done) tower_stream_kernel<T, G, AVEC, 0><<<grid, kStreamThreads, 0, st>>>(p);
+    if constexpr (AVEC > 0) {
+        if (!done) tower_stream_kernel<T, G, AVEC, 0, 1><<<grid, kStreamThreads, 0, st>>>(p);
+    }
     DCB_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -279,6 +326,14 @@ extern "C" int dcb_tower_fwd_bwd(int n_seg, const int32_t* kind, const int32_t* 
             return fail("segment %d: unknown kind %d", k, kind[k]);
         }
     }
+    // head rows off the 16-byte grid (avec < 8 for 16-bit maps): aligned vectors + realignment when every pointer allows it
+    // (default OFF -- a measured negative result: the realignment network costs more issue slots than the narrow loads cost
+    // memory efficiency; DCB_ATTN_ALIGNED=1 selects it, tests keep it bit-identical to the default path)
+    bool aligned_mode = common_h != -1 && isz == 2 && gsz == 2 && avec < 8 && getenv("DCB_ATTN_ALIGNED") && !getenv("DCB_ATTN_NO_ALIGNED");
+    for (int k = 0; k < n_seg && aligned_mode; ++k)
+        if (p.seg[k].kind == 1 || p.seg[k].kind == 4)
+            aligned_mode = p.seg[k].g && (((uintptr_t)p.seg[k].s | (uintptr_t)p.seg[k].t | (uintptr_t)p.seg[k].g) % 16 == 0);
+    const int gpt = aligned_mode ? 1 : tower_gpt(avec, common_h);
     long long tiles = 0;
     const long long mse_tile_vec = (long long)kStreamThreads * kMseUnroll * (16 / isz);
     const long long mse_tile_scalar = (long long)kStreamThreads * kMseUnroll;
@@ -291,19 +346,25 @@ extern "C" int dcb_tower_fwd_bwd(int n_seg, const int32_t* kind, const int32_t* 
         } else if (sg.kind == 3) {
             tiles += (sg.n + kStreamThreads / 32 - 1) / (kStreamThreads / 32);       // one warp per row
         } else {
-            sg.groups_per_b = sg.positions / avec;
+            sg.total_s = sg.n * sg.hs * sg.positions;                 // sg.n holds the batch here
+            sg.total_t = sg.n * sg.ht * sg.positions;
+            sg.groups_per_b = aligned_mode ? (sg.positions + 7) / 8 : sg.positions / avec;
             sg.n *= sg.groups_per_b;
-            tiles += (sg.n + kStreamThreads - 1) / kStreamThreads;
+            tiles += (sg.n + kStreamThreads * gpt - 1) / (kStreamThreads * gpt);
         }
     }
     p.total_tiles = tiles;
-    long long grid = tiles < (long long)dcb_tower_grid() ? tiles : (long long)dcb_tower_grid();
+    const long long max_grid = (long long)kNumSMs * ((aligned_mode || gpt > 1) ? 2 : 4);     // one persistent CTA per resident slot
+    long long grid = tiles < max_grid ? tiles : max_grid;
     if (grid < 1) grid = 1;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     return dispatch_in_grad(in_dtype, grad_dtype, [&](auto tt, auto gg) -> int {
         using T = decltype(tt);
         using G = decltype(gg);
         constexpr int kMax = Elem<T>::kPer16B;
+        if constexpr (sizeof(T) == 2 && sizeof(G) == 2) {
+            if (aligned_mode) return launch_tower_h<T, G, 0>(p, common_h, (unsigned)grid, st);
+        }
         if (avec >= kMax) return launch_tower_h<T, G, kMax>(p, common_h, (unsigned)grid, st);
         if (avec == 4) {
             if constexpr (kMax > 4) return launch_tower_h<T, G, 4>(p, common_h, (unsigned)grid, st);

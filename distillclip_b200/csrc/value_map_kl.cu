@@ -33,7 +33,7 @@ __global__ void __launch_bounds__(kVmThreads) value_map_kl_kernel(const T* __res
     }
     double acc = 0.0;
     for (long long gi = (long long)blockIdx.x * kVmThreads + threadIdx.x; gi < groups; gi += (long long)gridDim.x * kVmThreads) {
-        const long long b = gi / groups_per_b;
+        const long long b = ((unsigned long long)(gi | groups_per_b) >> 32) == 0 ? (long long)((unsigned)gi / (unsigned)groups_per_b) : gi / groups_per_b;
         const long long pos = (gi - b * groups_per_b) * VEC;
         const long long off = b * heads * positions + pos;
         float sv[kVmMaxHeads][VEC], tv[kVmMaxHeads][VEC];

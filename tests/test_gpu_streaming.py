@@ -260,3 +260,41 @@ def test_full_size_image_stage_properties(cuda_device):
     assert abs(float(kl)) <= 1e-3                              # KL(t || t) = 0 up to fp32 log rounding over 2.56M terms
     for x in a:
         assert torch.equal(x.grad[:, 0], x.grad[:, 5]) and torch.equal(x.grad[:, 0], x.grad[:, 11])
+
+
+@pytest.mark.parametrize("b,hs,ht,n", [(3, 8, 8, 77), (5, 12, 12, 50), (150, 2, 4, 17), (2, 24, 12, 50), (7, 8, 8, 3), (1, 1, 1, 5),
+                                       (33, 12, 12, 7), (2, 8, 8, 129)])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_attention_aligned_vectors_match_per_thread_path(cuda_device, b, hs, ht, n, dtype, monkeypatch):
+    """16-bit maps whose head rows are off the 16-byte grid go through aligned vector loads / stores with in-register
+    realignment (stream_tiles.cuh: attn_tile_aligned): bit-identical to the per-thread-load path (same summation order) and
+    equal to the oracle, for row ends that are not multiples of 8, tiny maps, tensors that end inside a vector, mismatched
+    and unrolled head counts, both in the stand-alone kernel and in the tower kernel (KL and head-mean MSE)."""
+    from distillclip_b200 import ops
+    gen = torch.Generator().manual_seed(b + n)
+    stu = [torch.softmax(torch.randn(b, hs, n, n, generator=gen), -1).to(dtype).cuda() for _ in range(2)]
+    tea = [torch.softmax(torch.randn(b, ht, n, n, generator=gen), -1).to(dtype).cuda() for _ in range(2)]
+    ref, ref_g = cf.attention_probs_kl([x.float().cpu().numpy() for x in stu], [x.float().cpu().numpy() for x in tea])
+
+    def run_all():
+        part, cnt, grads = ops.launch_attn_kl(stu, tea, 2, 1.0, [True, True])
+        val = ops.finalize([(part, cnt)], [1.0], [1.0])[0]
+        out = {}
+        for kind in (ops.KIND_ATTN_KL, ops.KIND_ATTN_MSE):
+            res, tg, _ = ops.launch_tower([(kind, 2, stu, tea, [True, True], 1.0)], [1.0], [1.0])
+            out[kind] = (res.clone(), [g.clone() for g in tg[0]])
+        torch.cuda.synchronize()
+        return val.clone(), [g.clone() for g in grads], out
+    monkeypatch.setenv("DCB_ATTN_ALIGNED", "1")           # the aligned path is opt-in (measured slower, profiles/README.md)
+    val_a, g_a, tower_a = run_all()
+    monkeypatch.delenv("DCB_ATTN_ALIGNED")
+    val_p, g_p, tower_p = run_all()
+    assert float(val_a) == pytest.approx(ref, rel=LOSS_RTOL) and float(val_a) == pytest.approx(float(val_p), rel=1e-6)
+    for x, y, r in zip(g_a, g_p, ref_g):
+        assert torch.equal(x, y)
+        assert rel_l2(x.float().cpu().numpy(), r) <= GRAD_BF16_STORAGE_RTOL
+    for kind in tower_a:
+        assert float(tower_a[kind][0][0]) == pytest.approx(float(tower_p[kind][0][0]), rel=1e-6)
+        for x, y in zip(tower_a[kind][1], tower_p[kind][1]):
+            assert torch.equal(x, y)
+    assert float(tower_a[ops.KIND_ATTN_KL][0][0]) == pytest.approx(ref, rel=LOSS_RTOL)
