@@ -75,6 +75,7 @@ _SPECIAL = {
     "dcb_clip_pair_splits": (C.c_int, [C.c_int64, C.c_int64, C.c_int64]),
     "dcb_clip_pair_supported": (C.c_int, [C.c_int64]),
     "dcb_clip_gt_splits": (C.c_int, [C.c_int64, C.c_int64, C.c_int64]),
+    "dcb_clip_gt_splits_scatter": (C.c_int, [C.c_int64, C.c_int64, C.c_int64]),
     "dcb_clip_fwd_chunk_parts": (C.c_int, [C.c_int64, C.c_int64]),
     "dcb_clip_slot_floats": (C.c_int64, [C.c_int64, C.c_int64]),
     "dcb_clip_post_scratch_bytes": (C.c_int64, [C.c_int64, C.c_int64]),

@@ -196,8 +196,9 @@ class CudaEngine:
     tr_dtype = torch.float16
     _scratch: Dict = {}
 
-    def gt_splits(self, rows, cols, dim):
-        return _lib.load().dcb_clip_gt_splits(rows, cols, dim)
+    def gt_splits(self, rows, cols, dim, scatter=False):
+        lib = _lib.load()
+        return lib.dcb_clip_gt_splits_scatter(rows, cols, dim) if scatter else lib.dcb_clip_gt_splits(rows, cols, dim)
 
     def fwd_parts(self, rows, cols_chunk):
         return _lib.load().dcb_clip_fwd_chunk_parts(rows, cols_chunk)

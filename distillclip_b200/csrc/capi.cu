@@ -99,7 +99,18 @@ __global__ void __launch_bounds__(256) peer_gather_kernel(const __grid_constant_
     const uint4* __restrict__ src = static_cast<const uint4*>(p.src[k]);
     uint4* __restrict__ dst = static_cast<uint4*>(p.dst[k]);
     const long long n = p.vecs[k];
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + 3 * stride < n; i += 4 * stride) {                 // four NVLink round trips in flight per thread
+        uint4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                         : "=r"(v[u].x), "=r"(v[u].y), "=r"(v[u].z), "=r"(v[u].w) : "l"(src + i + u * stride));
+#pragma unroll
+        for (int u = 0; u < 4; ++u) dst[i + u * stride] = v[u];
+    }
+    for (; i < n; i += stride) {
         uint4 v;
         asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(src + i));
         dst[i] = v;
@@ -125,7 +136,7 @@ int dcb_peer_gather(int n_copies, void* const* dst, const void* const* src, cons
         max_vecs = p.vecs[k] > max_vecs ? p.vecs[k] : max_vecs;
     }
     long long bx = (max_vecs + 255) / 256;
-    const long long cap = (2LL * kNumSMs + n_copies - 1) / n_copies;      // ~2 CTAs per SM in total
+    const long long cap = (4LL * kNumSMs + n_copies - 1) / n_copies;      // ~4 CTAs per SM in total
     if (bx > cap) bx = cap;
     if (bx < 1) bx = 1;
     peer_gather_kernel<<<dim3((unsigned)bx, (unsigned)n_copies), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);

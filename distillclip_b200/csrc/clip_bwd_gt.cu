@@ -208,7 +208,9 @@ struct GtPlan {
     int chunk, pieces, n_chunks, m_tiles, k_split, stages, stage_bytes;
 };
 
-static GtPlan clip_gt_plan(int64_t rows, int64_t cols, int64_t dim) {
+// scatter: the partial buffers live in the owners' memory (NVLink stores) -- every extra K split is another [cols, dim] fp32
+// image over the links and another slot for the finish kernel to sum, which costs far more than the wave it balances
+static GtPlan clip_gt_plan(int64_t rows, int64_t cols, int64_t dim, bool scatter = false) {
     GtPlan g{};
     g.n_chunks = (int)((dim + gt::kMaxChunk - 1) / gt::kMaxChunk);
     const int64_t per = (dim + g.n_chunks - 1) / g.n_chunks;
@@ -224,7 +226,10 @@ static GtPlan clip_gt_plan(int64_t rows, int64_t cols, int64_t dim) {
     double best_cost = 1e30;
     for (int64_t n = 1; n <= 16 && n <= kcs; ++n) {
         const int64_t waves = ((int64_t)g.m_tiles * g.n_chunks * n + slots - 1) / slots;
-        const double cost = (double)waves * ((double)((kcs + n - 1) / n) + 12.0) + 0.5 * (double)n;   // ~12 chunks of fill/drain
+        // unit = one 64-deep K step of a 256 x chunk tile pair (~0.4 us); writing + re-reading one fp32 image of the result
+        // costs ~cols * dim * 8 B / 6 TB/s locally, ~cols * dim * 4 B / 0.6 TB/s over NVLink
+        const double image_us = (double)cols * (double)dim * (scatter ? 4.0 / 0.6e6 : 8.0 / 6.0e6);
+        const double cost = (double)waves * ((double)((kcs + n - 1) / n) + 12.0) + (double)n * image_us / 0.4;   // ~12 chunks of fill/drain
         if (cost < best_cost) { best_cost = cost; best = n; }
     }
     g.k_split = (int)best;
@@ -236,6 +241,9 @@ static GtPlan clip_gt_plan(int64_t rows, int64_t cols, int64_t dim) {
 extern "C" int dcb_clip_gt_splits(int64_t rows, int64_t cols, int64_t dim) {
     return dcb::clip_gt_plan(rows, cols, dim).k_split;
 }
+extern "C" int dcb_clip_gt_splits_scatter(int64_t rows, int64_t cols, int64_t dim) {
+    return dcb::clip_gt_plan(rows, cols, dim, true).k_split;
+}
 
 namespace dcb {
 static int clip_gt_launch(const void* g, int64_t g_pitch_elems, const void* a_hat_t, int64_t at_pitch_elems, int64_t rows,
@@ -245,7 +253,7 @@ static int clip_gt_launch(const void* g, int64_t g_pitch_elems, const void* a_ha
     DCB_REQUIRE(rows >= 1 && cols >= 1 && dim >= 8 && dim % 8 == 0, "bad shape");
     DCB_REQUIRE(g_pitch_elems >= cols && g_pitch_elems % 8 == 0, "G pitch must be >= cols and a multiple of 8 elements");
     DCB_REQUIRE(at_pitch_elems >= rows && at_pitch_elems % 8 == 0, "a_hat^T pitch must be >= rows and a multiple of 8 elements");
-    const GtPlan plan = clip_gt_plan(rows, cols, dim);
+    const GtPlan plan = clip_gt_plan(rows, cols, dim, n_dest > 0);
     CUtensorMap map_g, map_at;
     if (tc::encode_tile_map_16bit(&map_g, g, rows, cols, (uint64_t)g_pitch_elems * 2, 64)) return 1;
     if (tc::encode_tile_map_16bit(&map_at, a_hat_t, dim, rows, (uint64_t)at_pitch_elems * 2, plan.chunk / plan.pieces / 2)) return 1;

@@ -309,13 +309,23 @@ class SymmExchange(LocalExchange):
         per_peer = sum(nb for _, _, _, nb in self._pieces(s, r))
         s.single_chunk = per_peer <= self.small_bytes
         if s.single_chunk:
-            # latency regime: barrier + one gather kernel (P2P loads) on the main stream
+            # latency regime: barrier + one gather kernel (P2P loads over NVLink) on the main stream for what the forward needs;
+            # the b_hat^T blocks (backward only) are gathered by a second launch on the side stream, behind the tile kernel
+            def gather(cps, stream):
+                for i in range(0, len(cps), 64):
+                    part = cps[i:i + 64]
+                    _lib.call("dcb_peer_gather", len(part), _lib.ptr_array([c[1] for c in part]), _lib.ptr_array([c[2] for c in part]),
+                              _lib.i64_array([c[3] for c in part]), stream)
             s.hdl.barrier(channel=1)
+            main = torch.cuda.current_stream()
+            published = torch.cuda.Event()
+            published.record(main)
             cps = [c for k in range(1, self.world) for c in self._pieces(s, (r + k) % self.world)]
-            for i in range(0, len(cps), 64):
-                part = cps[i:i + 64]
-                _lib.call("dcb_peer_gather", len(part), _lib.ptr_array([c[1] for c in part]), _lib.ptr_array([c[2] for c in part]),
-                          _lib.i64_array([c[3] for c in part]), torch.cuda.current_stream().cuda_stream)
+            gather([c for c in cps if c[0] != "bt_all"], main.cuda_stream)
+            with torch.cuda.stream(self.comm):
+                self.comm.wait_event(published)
+                gather([c for c in cps if c[0] == "bt_all"], self.comm.cuda_stream)
+                s.events[r].record(self.comm)
             return
         main = torch.cuda.current_stream()
         ready = torch.cuda.Event()
@@ -344,7 +354,7 @@ class SymmExchange(LocalExchange):
             torch.cuda.current_stream().wait_event(s.events[src])
 
     def wait_all(self, s):
-        if self._impl(s) or getattr(s, "single_chunk", False):
+        if self._impl(s):
             return
         torch.cuda.current_stream().wait_event(s.events[self.rank])
 
@@ -438,7 +448,7 @@ def forward_prep(engine, xc, si, st, ti, tt, temperature, weights=(1.0, 1.0, 1.0
     b_local, dim = si.shape
     b = b_local * world
     dev = si.device
-    k_split = engine.gt_splits(b_local, b, dim)
+    k_split = engine.gt_splits(b_local, b, dim, scatter=world > 1)      # sizes the peer-scatter partial buffers
     s = xc.acquire(b_local, dim, si.dtype, has_teacher, k_split, dev, (engine.stat_dtype, engine.tr_dtype))
     loc = slice(rank * b_local, (rank + 1) * b_local)
     pitch = (b_local + 7) // 8 * 8
@@ -506,7 +516,7 @@ def forward_tiles(engine, v):
                 join = torch.cuda.Event()
                 join.record(st_)
                 main.wait_event(join)
-        xc.wait_all(s)
+    xc.wait_all(s)
     v["stats_i2t"] = torch.empty(5, b_local, dtype=f32, device=dev)
     v["coef_row"] = torch.empty(4, b_local, dtype=f32, device=dev)
     engine.post1(ws, diag, col_part, temperature, has_teacher, b, v["stats_i2t"], v["coef_row"], xc.slot_targets(s), wx, diag_t)

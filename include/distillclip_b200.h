@@ -218,6 +218,7 @@ int dcb_clip_row_grads_pair(const void* stu_a, const void* stu_b, const void* te
  * recompute of the logits.  a_hat_t: [dim, at_pitch_elems] fp16 from dcb_transpose_norm_f16 of the a side.
  * acc_parts: dcb_clip_gt_splits(...) buffers of [cols, dim] fp32 for dcb_clip_grad_finish (same 2^k scale). */
 int dcb_clip_gt_splits(int64_t rows, int64_t cols, int64_t dim);
+int dcb_clip_gt_splits_scatter(int64_t rows, int64_t cols, int64_t dim);   /* K splits dcb_clip_col_grads_scatter uses */
 int dcb_clip_col_grads_from_g(const void* g, int64_t g_pitch_elems, const void* a_hat_t, int64_t at_pitch_elems,
                               int64_t rows, int64_t cols, int64_t dim, float* acc_parts, void* stream);
 

@@ -1,5 +1,6 @@
-"""Per-phase device times of the row-sharded contrastive step (CUDA events around every engine call and collective).
-torchrun --nproc-per-node N scripts/phase_times.py [B D]   (rank 0 prints; eager, so launch gaps are included in 'step')"""
+"""Per-phase device times of the row-sharded contrastive pipeline (CUDA events around every engine call and exchange step).
+torchrun --nproc-per-node N scripts/phase_times.py [B D]   (rank 0 prints; eager, ranks aligned by a barrier before each step,
+so launch gaps are included in 'step'; chunked mode runs its tile launches on the main stream here so that they can be timed)"""
 import collections
 import os
 import sys
@@ -9,7 +10,7 @@ import torch
 import torch.distributed as dist
 
 import bench
-from distillclip_b200 import contrastive as ct
+from distillclip_b200 import contrastive as ct, pipeline as pl
 
 b, d = (int(sys.argv[1]), int(sys.argv[2])) if len(sys.argv) > 2 else (32768, 768)
 rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
@@ -36,39 +37,42 @@ def timed(name, fn):
     return wrapper
 
 
-eng = ct.CudaEngine()
-for m in ("inv_norms", "row_stats", "col_finish", "losses", "coef", "transpose_norm", "row_acc", "col_acc_from_g", "col_acc_scatter", "finish_grads"):
+eng = ct._ENGINE
+xc = pl.exchange_for(group)
+for m in ("prep", "fwd_chunk", "post1", "post2", "pair_bwd", "col_acc_from_g", "col_acc_scatter", "finish2"):
     setattr(eng, m, timed(m, getattr(eng, m)))
-ct._all_gather_rows = timed("all_gather_rows", ct._all_gather_rows)
-ct._all_gather_cols = timed("all_gather_cols(stats)", ct._all_gather_cols)
-ct._reduce_scatter_rows = timed("reduce_scatter(grad)", ct._reduce_scatter_rows)
-if world > 1:
-    dist.all_reduce = timed("all_reduce(col/sums)", dist.all_reduce)
-up = torch.tensor([0.5, 0.5], device="cuda")
-steps = []
-for it in range(6):
-    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    if world > 1:
+for m in ("start_gather", "exchange_slots", "after_scatter", "wait_all"):
+    if hasattr(xc, m):
+        setattr(xc, m, timed("xc." + m, getattr(xc, m)))
+xc.tile_streams = lambda: None                      # tiles on the main stream: their events then bracket the waits as well
+one = torch.ones((), device="cuda")
+for it in range(25):
+    if group is not None:
         dist.barrier()
     torch.cuda.synchronize()
-    s0.record()
-    out, saved = ct.contrastive_forward(eng, si, st, ti, tt, 2.0, group)
-    ct.contrastive_backward(eng, saved, up)
-    s1.record()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    out, saved = pl.pipeline_forward(eng, xc, si, st, ti, tt, 2.0, (0.5, 0.5, 1.0, 1.0))
+    em = torch.cuda.Event(enable_timing=True)
+    em.record()
+    pl.pipeline_backward(eng, saved, (one, None, None))
+    e1.record()
     torch.cuda.synchronize()
-    if it >= 2:
-        steps.append(s0.elapsed_time(s1))
-        for name, e0, e1 in pending:
-            records[name].append(e0.elapsed_time(e1))
+    if it >= 5:
+        records["step"].append(e0.elapsed_time(e1))
+        records["forward"].append(e0.elapsed_time(em))
+        records["backward"].append(em.elapsed_time(e1))
+        agg = collections.defaultdict(float)
+        for name, a, c in pending:
+            agg[name] += a.elapsed_time(c)
+        for k, v in agg.items():
+            records[k].append(v)
     pending.clear()
 if rank == 0:
-    k = len(steps)
-    print(f"world {world}  B={b} D={d}: step {sum(steps) / k:.3f} ms (eager)")
-    tot = 0.0
-    for name, v in records.items():
-        per_step = sum(v) / k
-        tot += per_step
-        print(f"  {name:26s} {per_step:7.3f} ms  ({len(v) // k} calls)")
-    print(f"  {'sum of phases':26s} {tot:7.3f} ms")
-if world > 1:
+    print(f"B={b} D={d} world={world} exchange={type(xc).__name__} single_chunk={getattr(saved['set'], 'single_chunk', None)}")
+    for k, v in records.items():
+        v = sorted(v)
+        print(f"  {k:22s} median {v[len(v)//2]*1e3:9.1f} us   min {v[0]*1e3:9.1f} us")
+if group is not None:
+    dist.barrier()
     dist.destroy_process_group()

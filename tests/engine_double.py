@@ -124,7 +124,7 @@ class DoubleEngine:
     # ------------------------------------------------------------------------------------------
     slot_dtype = stat_dtype = tr_dtype = torch.float64
 
-    def gt_splits(self, rows, cols, dim):
+    def gt_splits(self, rows, cols, dim, scatter=False):
         return 1
 
     def fwd_parts(self, rows, cols_chunk):
