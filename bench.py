@@ -55,6 +55,9 @@ WORKLOADS = {
 L2_BYTES = 126 * 1024 * 1024
 LOSS_RTOL, GRAD_RTOL, GRAD_STORAGE_RTOL = 1e-4, 1e-3, 4e-3
 PROFILE_ROUND = "r02"
+# tolerances (BASELINE.json north_star): losses 1e-4; gradients 1e-3 -- asserted on the kernels' fp32 gradient output AND on the
+# bf16 gradients of the public API against the float64 reference rounded to bf16 (what the reference itself hands a bf16 leaf);
+# the distance of a bf16-stored gradient to the UNROUNDED float64 one is storage rounding (~1.7e-3), bounded at 4e-3
 
 
 def ncu_traffic(csv_name, kernel_substr):
@@ -319,6 +322,7 @@ def parity_tower(cfg, stu, tea, device):
     for k in names:
         loss_err[k] = abs(float(res[k]) - float(ref_res[k])) / abs(float(ref_res[k]))
     g_api = max(_rel(g.grad, w) for k, v in leaves.items() for g, w in zip(v if isinstance(v, list) else [v], ref_grads[k]))
+    g_api_r = max(_rel(g.grad, w.to(torch.bfloat16)) for k, v in leaves.items() for g, w in zip(v if isinstance(v, list) else [v], ref_grads[k]))
     fields = {"hidden_rep_mse": (ops.KIND_MSE, "representations"), "attention_probs_kl": (ops.KIND_ATTN_KL, "attention_probs"),
               "embedding_mse": (ops.KIND_MSE, "embedding")}
     entries = []
@@ -330,9 +334,10 @@ def parity_tower(cfg, stu, tea, device):
     _, grads32, _ = ops.launch_tower(entries, [1.0] * len(names), [percent[n] for n in names], grad_dtype=torch.float32)
     g32 = max(_rel(g, w) for nm, gl in zip(names, grads32) for g, w in zip(gl, ref_grads[fields[nm][1]]))
     torch.cuda.synchronize()
-    ok = max(loss_err.values()) <= LOSS_RTOL and g32 <= GRAD_RTOL and g_api <= GRAD_STORAGE_RTOL
+    ok = max(loss_err.values()) <= LOSS_RTOL and g32 <= GRAD_RTOL and g_api <= GRAD_STORAGE_RTOL and g_api_r <= GRAD_RTOL
     return {"ok": bool(ok), "loss_rel_err": {k: float(f"{v:.3e}") for k, v in loss_err.items()},
-            "grad_rel_l2_fp32_out": float(f"{g32:.3e}"), "grad_rel_l2_api_bf16": float(f"{g_api:.3e}"),
+            "grad_rel_l2_fp32_out": float(f"{g32:.3e}"), "grad_rel_l2_api_vs_bf16_rounded_reference": float(f"{g_api_r:.3e}"),
+            "grad_rel_l2_api_bf16": float(f"{g_api:.3e}"),
             "tol": {"loss": LOSS_RTOL, "grad_fp32": GRAD_RTOL, "grad_bf16_storage": GRAD_STORAGE_RTOL},
             "checker": "oracle/torch_port.py (the reference's op sequence) in float64 on the same inputs, full size"}
 
@@ -542,10 +547,16 @@ def parity_clip(cfg, glob, rank, world, dist, group, device):
     res = ct.clip_contrastive(a, c_, ti, tt, T, want_hard=True, want_soft=True, group=group, percent=(w_hard, w_soft))
     res["total"].backward()
     torch.cuda.synchronize()
+    want = w_hard * ref["hard"] + w_soft * ref["soft"]
+    # autograd hands bf16 leaves bf16 gradients -- in the reference too (the cast back from its fp32 copies rounds them): the
+    # API-level comparison is therefore against the float64 gradient ROUNDED TO bf16, at the 1e-3 tolerance; the distance to the
+    # unrounded float64 gradient (pure storage rounding, ~1.7e-3) is reported next to it
     api = _max_over_ranks([_rel(a.grad[loc_i], ref["d_img"]), _rel(c_.grad[loc_t], ref["d_txt"]),
-                           abs(float(res["total"]) - (w_hard * ref["hard"] + w_soft * ref["soft"])) / abs(w_hard * ref["hard"] + w_soft * ref["soft"])], dist)
-    ok = all(r["ok"] for r in routes.values()) and max(api[:2]) <= GRAD_STORAGE_RTOL and api[2] <= LOSS_RTOL
-    return {"ok": bool(ok), "routes": routes, "grad_rel_l2_api_bf16": float(f"{max(api[:2]):.3e}"),
+                           abs(float(res["total"].detach()) - want) / abs(want),
+                           _rel(a.grad[loc_i], ref["d_img"].to(torch.bfloat16)), _rel(c_.grad[loc_t], ref["d_txt"].to(torch.bfloat16))], dist)
+    ok = all(r["ok"] for r in routes.values()) and max(api[:2]) <= GRAD_STORAGE_RTOL and api[2] <= LOSS_RTOL and max(api[3:]) <= GRAD_RTOL
+    return {"ok": bool(ok), "routes": routes, "grad_rel_l2_api_vs_bf16_rounded_reference": float(f"{max(api[3:]):.3e}"),
+            "grad_rel_l2_api_bf16": float(f"{max(api[:2]):.3e}"),
             "total_rel_err_api": float(f"{api[2]:.3e}"),
             "sampled_rows_per_side_per_rank": n_samp, "oracle": {"hard": ref["hard"], "soft": ref["soft"]},
             "tol": {"loss": LOSS_RTOL, "grad_fp32": GRAD_RTOL, "grad_bf16_storage": GRAD_STORAGE_RTOL},
