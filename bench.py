@@ -626,8 +626,11 @@ def bench_clip(cfg, name, args, device, dist, rank, world, pk, steps, warmup):
     gen = torch.Generator(device=device).manual_seed(2022)
     glob = make_clip_global(cfg, device, gen)
     group = dist.group.WORLD if (dist is not None and world > 1) else None
-    parity = parity_clip(cfg, glob, rank, world, dist, group, device)
-    kres = clip_kernel_times(cfg, glob, rank, world, device, pk)
+    if args.no_parity:
+        parity, kres = None, {"not_measured": {"ms": 0.0, "tflops": 0.0, "frac": 0.0, "frac_of_sustained": 0.0}}
+    else:
+        parity = parity_clip(cfg, glob, rank, world, dist, group, device)
+        kres = clip_kernel_times(cfg, glob, rank, world, device, pk)
     si, st, ti, tt = [x[rank * rows:(rank + 1) * rows].contiguous() for x in glob]
     del glob
     si.requires_grad_(True)
@@ -823,6 +826,8 @@ def main():
     ap.add_argument("--workload", choices=sorted(WORKLOADS), default="sweep")
     ap.add_argument("--no-extras", action="store_true", help="skip the streaming-stage / L-CLIP sub-benchmarks")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-parity", action="store_true",
+                    help="profiling runs only: skip the in-run parity check and the per-kernel timings (their launches would fill an ncu launch list)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

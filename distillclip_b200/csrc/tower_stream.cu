@@ -48,7 +48,6 @@ struct TowerParams {
     int ext_count;
     unsigned int* ticket;
     float* out;            // [n_terms + 1]
-    int l2_prefetch;       // attention tiles with narrow loads: bulk-prefetch the CTA's next tile into L2
     const float* fwd_mult; // optional device scalar multiplied into every gradient written by the forward pass (the AMP
                            // GradScaler's scale tensor: gradients are rounded once, at the scaled magnitude)
     int regrad;            // 1 = gradients only (see TowerSeg::up): no values, no partials, no ticket
@@ -104,34 +103,6 @@ __global__ void __launch_bounds__(kStreamThreads, (AVEC == 0 || GPT > 1) ? 2 : 4
         while (k + 1 < p.n_seg && tile >= p.seg[k + 1].tile_begin) ++k;
         const TowerSeg& sg = p.seg[k];
         if (p.regrad && seg_skip[k]) continue;
-        if constexpr (AVEC > 0 && AVEC < 8) {
-            // Narrow attention loads (head rows off the 16-byte grid) keep too few bytes in flight per thread to cover the HBM
-            // latency (ncu r02: 5.7 warps per issue waiting on loads).  Pull this CTA's NEXT attention tile into L2 with one bulk
-            // prefetch per head row (thread h < hs + ht), so its loads find an L2 hit: the bytes in flight live in L2, not in registers.
-            if (p.l2_prefetch) {
-                const long long nt = tile + gridDim.x;
-                int kn = k;
-                while (kn + 1 < p.n_seg && nt >= p.seg[kn + 1].tile_begin) ++kn;
-                const TowerSeg& sn = p.seg[kn];
-                if (nt < p.total_tiles && (sn.kind == 1 || sn.kind == 4) && tid < sn.hs + sn.ht) {
-                    const long long g0 = (nt - sn.tile_begin) * (kStreamThreads * GPT);
-                    const long long b = div_groups(g0, sn.groups_per_b);
-                    const long long pos = (g0 - b * sn.groups_per_b) * AVEC;
-                    const bool stu = tid < sn.hs;
-                    const int h = stu ? tid : tid - sn.hs;
-                    const long long e0 = (b * (stu ? sn.hs : sn.ht) + h) * sn.positions + pos;
-                    long long n_el = (long long)kStreamThreads * GPT * AVEC;
-                    if (n_el > sn.positions - pos) n_el = sn.positions - pos;
-                    const char* base = static_cast<const char*>(stu ? sn.s : sn.t);
-                    const long long lo = (e0 * (long long)sizeof(T)) & ~15ll;
-                    long long hi = ((e0 + n_el) * (long long)sizeof(T) + 15) & ~15ll;
-                    const long long end = (stu ? sn.total_s : sn.total_t) * (long long)sizeof(T) & ~15ll;
-                    if (hi > end) hi = end;
-                    if (hi > lo)
-                        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(base + lo), "r"((unsigned)(hi - lo)) : "memory");
-                }
-            }
-        }
         const float gcoef = seg_gc[k];
         if (!p.regrad && sg.term != cur_term) {        // block-uniform
             if (cur_term >= 0) flush();
@@ -294,7 +265,6 @@ extern "C" int dcb_tower_fwd_bwd(int n_seg, const int32_t* kind, const int32_t* 
     p.out = out;
     p.fwd_mult = fwd_mult;
     p.regrad = regrad ? 1 : 0;
-    p.l2_prefetch = getenv("DCB_ATTN_NO_PREFETCH") ? 0 : 1;
     for (int q = 0; q < n_terms; ++q) {
         p.scale[q] = scale ? scale[q] : 1.f;
         p.percent[q] = percent ? percent[q] : 0.f;

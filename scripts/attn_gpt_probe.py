@@ -14,8 +14,7 @@ for name in ("image_stage", "text_stage"):
     els = bench.tower_elements(cfg)
     el = els["attention_probs_kl"]
     s_a, t_a = stu["attention_probs"], tea["attention_probs"]
-    for label, env in (("gpt=1 no prefetch", {"DCB_ATTN_GPT": "1", "DCB_ATTN_NO_PREFETCH": "1"}), ("gpt=1 +L2 prefetch", {"DCB_ATTN_GPT": "1"}),
-                       ("gpt=2 no prefetch", {"DCB_ATTN_GPT": "2", "DCB_ATTN_NO_PREFETCH": "1"}), ("gpt=2 +L2 prefetch", {"DCB_ATTN_GPT": "2"}),
+    for label, env in (("per-thread gpt=1", {"DCB_ATTN_GPT": "1"}), ("per-thread gpt=2", {"DCB_ATTN_GPT": "2"}),
                        ("aligned 16 B", {"DCB_ATTN_ALIGNED": "1"})):
         for k in ("DCB_ATTN_NO_ALIGNED", "DCB_ATTN_GPT", "DCB_ATTN_ALIGNED", "DCB_ATTN_NO_PREFETCH"):
             os.environ.pop(k, None)

@@ -8,7 +8,7 @@ timeout 900 python bench.py --steps 20 --warmup 5 > $OUT/${TAG}_bench_n1.json 2>
 echo "bench exit $?"
 timeout 600 python bench.py --impl reference --steps 20 --warmup 5 > $OUT/${TAG}_bench_ref_n1.json 2> $OUT/${TAG}_bench_ref_n1.err
 echo "reference exit $?"
-CMD="python bench.py --steps 2 --warmup 3 --no-extras --no-cpu"
+CMD="python bench.py --steps 2 --warmup 3 --no-extras --no-cpu --no-parity"
 timeout 600 $CMD > $OUT/${TAG}_plain.log 2>&1 &&
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $OUT/${TAG}_launches_sweep.csv $CMD > $OUT/${TAG}_ncu_launches.log 2>&1
 echo "launch list exit $?"
