@@ -377,6 +377,91 @@ __device__ __forceinline__ float attn_tile_aligned(const T* __restrict__ s_base,
 }
 
 // ---------------------------------------------------------------------------------------------
+// STAGED attention tile (16- and 32-bit maps whose head rows are off the 16-byte grid): the bytes in flight live in shared
+// memory, not in registers.  One tile = W consecutive positions of one sample, all student and teacher heads.  Every head
+// row's byte range is rounded out to 16-byte chunks and fetched with cp.async (16 B per copy, any row alignment), one commit
+// group per tile, the NEXT tile of the CTA in flight while the current one is computed (2 buffers).  Threads then read their
+// positions from shared memory with element-sized loads (a row's start offset inside its first chunk is row_off).
+// Why: with per-thread 2-byte loads a thread holds 2 useful bytes per register in flight; 4 CTAs x 256 threads x 16 loads keep
+// ~48 KB per SM outstanding, below what the HBM latency needs (ncu r02: DRAM traffic = algorithmic, 60 % issue slots, 5.7
+// warps per issue stalled on loads).  Two staged tiles per CTA keep 2 x 17 KB x 4 CTAs = 136 KB per SM in flight.
+// ---------------------------------------------------------------------------------------------
+struct AttnStaged {
+    long long positions;     // P
+    long long tiles_per_b;   // ceil(P / W)
+    long long total_s, total_t;   // elements of the student / teacher tensor
+    int W, row_bytes;        // positions per tile; staged bytes per head row = W * sizeof(T) + 32
+    int hs, ht;
+    float inv_hs, inv_ht;
+};
+
+__device__ __forceinline__ unsigned smem_addr_u32(const void* p) { return static_cast<unsigned>(__cvta_generic_to_shared(p)); }
+
+// all threads of the CTA; ends with a commit_group (possibly empty)
+template <typename T>
+__device__ __forceinline__ void attn_stage_issue(const T* __restrict__ s_base, const T* __restrict__ t_base, const AttnStaged& a,
+                                                 long long tile, unsigned char* buf, short* row_off, int tid) {
+    constexpr long long ES = sizeof(T);
+    const long long b = div_groups(tile, a.tiles_per_b);
+    const long long p0 = (tile - b * a.tiles_per_b) * a.W;
+    const int rows = a.hs + a.ht;
+    const int cpr = a.row_bytes >> 4;
+    for (int c = tid; c < rows * cpr; c += kStreamThreads) {
+        const int row = c / cpr, j = c - row * cpr;
+        const bool stu = row < a.hs;
+        const long long e0 = (b * (stu ? a.hs : a.ht) + (stu ? row : row - a.hs)) * a.positions + p0;
+        const long long first = (e0 * ES) & ~15ll;
+        const long long src = first + 16ll * j;
+        const long long end = (stu ? a.total_s : a.total_t) * ES;
+        if (j == 0) row_off[row] = (short)(e0 * ES - first);
+        const long long left = end - src;
+        if (left > 0) {
+            const char* base = reinterpret_cast<const char*>(stu ? s_base : t_base);
+            const unsigned dst = smem_addr_u32(buf + (size_t)row * a.row_bytes + 16 * j);
+            const unsigned n = left >= 16 ? 16u : (unsigned)left;          // the tensor's last chunk: zero-fill past its end
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(base + src), "r"(n) : "memory");
+        }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
+template <typename T, typename G, int H, bool MSE>
+__device__ __forceinline__ float attn_stage_compute(const unsigned char* buf, const short* row_off, G* __restrict__ g_base,
+                                                    const AttnStaged& a, long long tile, float gc, int tid) {
+    const long long b = div_groups(tile, a.tiles_per_b);
+    const long long p0 = (tile - b * a.tiles_per_b) * a.W;
+    const int hs = H > 0 ? H : a.hs, ht = H > 0 ? H : a.ht;
+    float acc = 0.f;
+    for (int q = tid; q < a.W; q += kStreamThreads) {
+        if (p0 + q >= a.positions) break;
+        float ss = 0.f, ts = 0.f;
+        const unsigned char* col = buf + (size_t)q * sizeof(T);
+#pragma unroll 4
+        for (int h = 0; h < hs; ++h) ss += Elem<T>::to_f(*reinterpret_cast<const T*>(col + (size_t)h * a.row_bytes + row_off[h]));
+#pragma unroll 4
+        for (int h = 0; h < ht; ++h) ts += Elem<T>::to_f(*reinterpret_cast<const T*>(col + (size_t)(hs + h) * a.row_bytes + row_off[hs + h]));
+        const float sm = ss * a.inv_hs, tm = ts * a.inv_ht;
+        float g;
+        if constexpr (MSE) {
+            const float d = sm - tm;
+            acc = fmaf(d, d, acc);
+            g = d * gc;
+        } else {
+            const float ratio = tm / sm;
+            acc += kl_term(tm, sm, ratio);
+            g = -gc * ratio;
+        }
+        if (g_base) {
+            G* __restrict__ gp = g_base + (b * hs) * a.positions + p0 + q;
+            const G gval = Elem<G>::from_f(g);
+#pragma unroll 4
+            for (int h = 0; h < hs; ++h) gp[(long long)h * a.positions] = gval;
+        }
+    }
+    return acc;
+}
+
+// ---------------------------------------------------------------------------------------------
 // Cosine rows tile (nn.CosineEmbeddingLoss with target 1, out_cos.py:10-11): one warp per row of [rows, dim].
 //   cos = <s,t> / sqrt((<s,s> + eps)(<t,t> + eps)), eps = 1e-12 (ATen EPSILON);  value = sum_rows (1 - cos)
 //   d value / d s = -( t / sqrt(..) - cos * s / (<s,s> + eps) )      (times gc)

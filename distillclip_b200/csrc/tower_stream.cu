@@ -50,6 +50,8 @@ struct TowerParams {
     float* out;            // [n_terms + 1]
     const float* fwd_mult; // optional device scalar multiplied into every gradient written by the forward pass (the AMP
                            // GradScaler's scale tensor: gradients are rounded once, at the scaled magnitude)
+    int stage_max_rows;    // staged attention tiles: max hs + ht over the attention segments
+    int stage_w, stage_row_bytes;   // staged attention tiles (AVEC == -1): positions per tile, staged bytes per head row
     int regrad;            // 1 = gradients only (see TowerSeg::up): no values, no partials, no ticket
     TowerSeg seg[kTowerMaxSeg];
 };
@@ -57,7 +59,10 @@ struct TowerParams {
 // GPT = attention groups per thread (stream_tiles.cuh: attn_tile_multi): 2 keeps twice the loads in flight (image stage
 // attention tiles 0.76 -> 0.86 of HBM, scripts/attn_gpt_probe.py) at ~90 registers, hence 2 resident CTAs instead of 4.
 // AVEC = 0: attention tiles on aligned 16-byte accesses with in-register realignment (attn_tile_aligned), for 16-bit maps
-// whose head rows are off the 16-byte grid.
+// whose head rows are off the 16-byte grid.  AVEC = -1: STAGED attention tiles (cp.async into shared memory, next tile in
+// flight while the current one is computed; stream_tiles.cuh).
+extern __shared__ __align__(16) unsigned char tower_dyn_smem[];
+
 template <typename T, typename G, int AVEC, int AH, int GPT>
 __global__ void __launch_bounds__(kStreamThreads, (AVEC == 0 || GPT > 1) ? 2 : 4) tower_stream_kernel(const __grid_constant__ TowerParams p) {
     constexpr int MVEC = Elem<T>::kPer16B;
@@ -99,6 +104,9 @@ __global__ void __launch_bounds__(kStreamThreads, (AVEC == 0 || GPT > 1) ? 2 : 4
         cur = 0.0;
     };
     int k = 0;
+    [[maybe_unused]] int stage_buf = 0;                 // staged mode: buffer holding the current attention tile
+    [[maybe_unused]] bool stage_ready = false;          //   ... whose copies are already in flight
+    [[maybe_unused]] __shared__ short stage_row_off[2][64];
     for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         while (k + 1 < p.n_seg && tile >= p.seg[k + 1].tile_begin) ++k;
         const TowerSeg& sg = p.seg[k];
@@ -127,7 +135,39 @@ __global__ void __launch_bounds__(kStreamThreads, (AVEC == 0 || GPT > 1) ? 2 : 4
                                      (int)sg.positions, lt * (kStreamThreads / 32) + (tid >> 5), gcoef, tid & 31);
         } else {
             AttnShape sh{sg.n, sg.groups_per_b, sg.positions, sg.hs, sg.ht, sg.inv_hs, sg.inv_ht};
-            if constexpr (AVEC == 0) {
+            if constexpr (AVEC == -1) {
+                const size_t buf_bytes = (size_t)(p.stage_max_rows) * p.stage_row_bytes;
+                auto staged = [&](const TowerSeg& q) {
+                    return AttnStaged{q.positions, q.groups_per_b, q.total_s, q.total_t, p.stage_w, p.stage_row_bytes, q.hs, q.ht, q.inv_hs, q.inv_ht};
+                };
+                const AttnStaged cur_a = staged(sg);
+                if (!stage_ready)
+                    attn_stage_issue<T>(static_cast<const T*>(sg.s), static_cast<const T*>(sg.t), cur_a, lt,
+                                        tower_dyn_smem + stage_buf * buf_bytes, stage_row_off[stage_buf], tid);
+                // the CTA's next tile: start its copies now if it is an attention tile too
+                const long long nt = tile + gridDim.x;
+                int kn = k;
+                while (kn + 1 < p.n_seg && nt >= p.seg[kn + 1].tile_begin) ++kn;
+                const TowerSeg& sn = p.seg[kn];
+                const bool next_staged = nt < p.total_tiles && (sn.kind == 1 || sn.kind == 4) && !(p.regrad && seg_skip[kn]);
+                if (next_staged) {
+                    attn_stage_issue<T>(static_cast<const T*>(sn.s), static_cast<const T*>(sn.t), staged(sn), nt - sn.tile_begin,
+                                        tower_dyn_smem + (stage_buf ^ 1) * buf_bytes, stage_row_off[stage_buf ^ 1], tid);
+                    asm volatile("cp.async.wait_group 1;" ::: "memory");
+                } else {
+                    asm volatile("cp.async.wait_group 0;" ::: "memory");
+                }
+                __syncthreads();
+                if (sg.kind == 1)
+                    acc = attn_stage_compute<T, G, AH, false>(tower_dyn_smem + stage_buf * buf_bytes, stage_row_off[stage_buf],
+                                                              static_cast<G*>(sg.g), cur_a, lt, gcoef, tid);
+                else
+                    acc = attn_stage_compute<T, G, AH, true>(tower_dyn_smem + stage_buf * buf_bytes, stage_row_off[stage_buf],
+                                                             static_cast<G*>(sg.g), cur_a, lt, gcoef, tid);
+                __syncthreads();                         // everyone is done with this buffer before it is refilled
+                stage_ready = next_staged;
+                stage_buf ^= 1;
+            } else if constexpr (AVEC == 0) {
                 __shared__ uint4 xchg[kStreamThreads];
                 acc = 0.f;
                 if constexpr (sizeof(T) == 2 && sizeof(G) == 2) {
@@ -204,10 +244,26 @@ static int tower_gpt(int avec, int common_h) {
     return 1;
 }
 
+template <typename T, typename G, int AH>
+static int launch_tower_staged(const TowerParams& p, unsigned grid, size_t smem, cudaStream_t st) {
+    static size_t max_set = 0;
+    if (smem > 48 * 1024 && smem > max_set) {
+        DCB_CUDA_OK(cudaFuncSetAttribute(tower_stream_kernel<T, G, -1, AH, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        max_set = smem;
+    }
+    tower_stream_kernel<T, G, -1, AH, 1><<<grid, kStreamThreads, smem, st>>>(p);
+    DCB_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
 template <typename T, typename G, int AVEC>
-static int launch_tower_h(const TowerParams& p, int common_h, unsigned grid, cudaStream_t st) {
+static int launch_tower_h(const TowerParams& p, int common_h, unsigned grid, cudaStream_t st, size_t smem = 0) {
     bool done = false;
-    if constexpr (AVEC == 0) {
+    if constexpr (AVEC == -1) {
+        if (common_h == 12) return launch_tower_staged<T, G, 12>(p, grid, smem, st);
+        if (common_h == 8) return launch_tower_staged<T, G, 8>(p, grid, smem, st);
+        return launch_tower_staged<T, G, 0>(p, grid, smem, st);
+    } else if constexpr (AVEC == 0) {
         if (common_h == 12) tower_stream_kernel<T, G, 0, 12, 1><<<grid, kStreamThreads, 0, st>>>(p);
         else if (common_h == 8) tower_stream_kernel<T, G, 0, 8, 1><<<grid, kStreamThreads, 0, st>>>(p);
         else tower_stream_kernel<T, G, 0, 0, 1><<<grid, kStreamThreads, 0, st>>>(p);
@@ -333,7 +389,30 @@ extern "C" int dcb_tower_fwd_bwd(int n_seg, const int32_t* kind, const int32_t* 
     for (int k = 0; k < n_seg && aligned_mode; ++k)
         if (p.seg[k].kind == 1 || p.seg[k].kind == 4)
             aligned_mode = p.seg[k].g && (((uintptr_t)p.seg[k].s | (uintptr_t)p.seg[k].t | (uintptr_t)p.seg[k].g) % 16 == 0);
-    const int gpt = aligned_mode ? 1 : tower_gpt(avec, common_h);
+    // STAGED mode: head rows off the 16-byte grid (per-thread vectors narrower than 16 bytes) -> cp.async staging through shared
+    // memory with the next tile in flight (stream_tiles.cuh).  Needs 16-byte aligned map bases and <= 64 head rows per tile.
+    // (default OFF -- the second measured negative result on these tiles: bit-identical but slower, text stage 0.58 vs 0.72 of HBM,
+    // image stage 0.58 vs 0.90: without the load stalls the tile is issue-bound, and the staging adds copies, syncs and index
+    // arithmetic on top; DCB_ATTN_STAGED=1 selects it, tests keep it bit-identical to the default path)
+    bool staged_mode = common_h != -1 && !aligned_mode && avec * isz < 16 && getenv("DCB_ATTN_STAGED") && !getenv("DCB_ATTN_NO_STAGED");
+    int max_rows = 0;
+    for (int k = 0; k < n_seg && staged_mode; ++k)
+        if (p.seg[k].kind == 1 || p.seg[k].kind == 4) {
+            staged_mode = (((uintptr_t)p.seg[k].s | (uintptr_t)p.seg[k].t) % 16 == 0) && p.seg[k].hs + p.seg[k].ht <= 64;
+            max_rows = p.seg[k].hs + p.seg[k].ht > max_rows ? p.seg[k].hs + p.seg[k].ht : max_rows;
+        }
+    size_t stage_smem = 0;
+    if (staged_mode) {
+        int w = 512;
+        if (const char* e = getenv("DCB_ATTN_STAGE_W")) w = atoi(e) >= 256 ? atoi(e) / 256 * 256 : 256;     // profiling only
+        while (w > 256 && 2 * (size_t)max_rows * (w * isz + 32) > 56 * 1024) w -= 256;
+        p.stage_w = w;
+        p.stage_row_bytes = w * isz + 32;
+        p.stage_max_rows = max_rows;
+        stage_smem = 2 * (size_t)max_rows * p.stage_row_bytes;
+        staged_mode = stage_smem <= 100 * 1024;
+    }
+    const int gpt = (aligned_mode || staged_mode) ? 1 : tower_gpt(avec, common_h);
     long long tiles = 0;
     const long long mse_tile_vec = (long long)kStreamThreads * kMseUnroll * (16 / isz);
     const long long mse_tile_scalar = (long long)kStreamThreads * kMseUnroll;
@@ -348,6 +427,12 @@ extern "C" int dcb_tower_fwd_bwd(int n_seg, const int32_t* kind, const int32_t* 
         } else {
             sg.total_s = sg.n * sg.hs * sg.positions;                 // sg.n holds the batch here
             sg.total_t = sg.n * sg.ht * sg.positions;
+            if (staged_mode) {                                        // one tile = stage_w positions of one sample
+                sg.groups_per_b = (sg.positions + p.stage_w - 1) / p.stage_w;
+                sg.n *= sg.groups_per_b;
+                tiles += sg.n;
+                continue;
+            }
             sg.groups_per_b = aligned_mode ? (sg.positions + 7) / 8 : sg.positions / avec;
             sg.n *= sg.groups_per_b;
             tiles += (sg.n + kStreamThreads * gpt - 1) / (kStreamThreads * gpt);
@@ -362,6 +447,7 @@ extern "C" int dcb_tower_fwd_bwd(int n_seg, const int32_t* kind, const int32_t* 
         using T = decltype(tt);
         using G = decltype(gg);
         constexpr int kMax = Elem<T>::kPer16B;
+        if (staged_mode) return launch_tower_h<T, G, -1>(p, common_h, (unsigned)grid, st, stage_smem);
         if constexpr (sizeof(T) == 2 && sizeof(G) == 2) {
             if (aligned_mode) return launch_tower_h<T, G, 0>(p, common_h, (unsigned)grid, st);
         }

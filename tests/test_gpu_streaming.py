@@ -288,7 +288,14 @@ def test_attention_aligned_vectors_match_per_thread_path(cuda_device, b, hs, ht,
     monkeypatch.setenv("DCB_ATTN_ALIGNED", "1")           # the aligned path is opt-in (measured slower, profiles/README.md)
     val_a, g_a, tower_a = run_all()
     monkeypatch.delenv("DCB_ATTN_ALIGNED")
-    val_p, g_p, tower_p = run_all()
+    val_p, g_p, tower_p = run_all()                       # default: per-thread loads (the reference point for bit-identity)
+    monkeypatch.setenv("DCB_ATTN_STAGED", "1")            # cp.async-staged tiles in the tower kernel (opt-in, measured slower)
+    _, _, tower_s = run_all()
+    monkeypatch.delenv("DCB_ATTN_STAGED")
+    for kind in tower_s:
+        assert float(tower_s[kind][0][0]) == pytest.approx(float(tower_p[kind][0][0]), rel=1e-6)
+        for x, y in zip(tower_s[kind][1], tower_p[kind][1]):
+            assert torch.equal(x, y)
     assert float(val_a) == pytest.approx(ref, rel=LOSS_RTOL) and float(val_a) == pytest.approx(float(val_p), rel=1e-6)
     for x, y, r in zip(g_a, g_p, ref_g):
         assert torch.equal(x, y)
