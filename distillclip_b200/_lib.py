@@ -28,7 +28,6 @@ SIGNATURES = {
     "dcb_tower_fwd_bwd": [C.c_int, _i32p, _i32p, _vpp, _vpp, _vpp, _i64p, _i64p, _i32p, _i32p, _i64p, _i32p, _f32p,
                           C.c_int, _f32p, _f32p, C.c_int, C.c_int, _vp, C.c_int, C.c_uint32, C.c_int, _vp, _vp, _vp, _vpp,
                           _f32p, _f32p, _vp],
-    "dcb_rescale_grads": [C.c_int, _vpp, _i64p, C.c_int, _vpp, _f32p, _vp],
     "dcb_row_inv_norm": [C.c_int, _vpp, _vpp, _i64p, C.c_int64, C.c_int, _vp],
     "dcb_transpose_norm_f16": [_vp, _vp, _vp, C.c_int64, C.c_int64, C.c_int64, C.c_int, _vp],
     "dcb_clip_row_stats": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int64, C.c_int64, C.c_int64, C.c_int64,

@@ -1,5 +1,5 @@
-// C-ABI glue that is not tied to one loss family: error buffer, version, deterministic finalize,
-// and the backward-time gradient rescale.
+// C-ABI glue that is not tied to one loss family: error buffer, version, deterministic finalize, and the device-to-device
+// copies of the sharded exchange.
 #include "common.cuh"
 
 namespace dcb {
@@ -53,34 +53,6 @@ __global__ void __launch_bounds__(32 * DCB_MAX_TERMS) finalize_kernel(const __gr
         }
         out[p.n_terms] = total;
     }
-}
-
-// ---------------------------------------------------------------------------------------------
-// rescale: grads[k] *= (*upstream[k]) / expected[k], skipped entirely when equal.
-// ---------------------------------------------------------------------------------------------
-struct RescaleSeg {
-    void* g;
-    long long n;
-    const float* upstream;
-    float expected;
-};
-struct RescaleParams {
-    int n_seg;
-    RescaleSeg seg[2 * DCB_MAX_LAYERS];
-};
-
-template <typename G>
-__global__ void __launch_bounds__(256) rescale_kernel(const __grid_constant__ RescaleParams p) {
-    const int k = blockIdx.y;
-    if (k >= p.n_seg) return;
-    const float up = __ldg(p.seg[k].upstream);
-    const float expected = p.seg[k].expected;
-    if (up == expected) return;                       // common case: nothing to do, no HBM traffic
-    const float f = up / expected;
-    G* __restrict__ g = static_cast<G*>(p.seg[k].g);
-    const long long n = p.seg[k].n;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-        g[i] = Elem<G>::from_f(Elem<G>::to_f(g[i]) * f);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -173,29 +145,6 @@ int dcb_finalize(int n_terms, const double* const* partials, const int32_t* coun
         p.percent[k] = percent ? percent[k] : 0.f;
     }
     finalize_kernel<<<1, 32 * DCB_MAX_TERMS, 0, static_cast<cudaStream_t>(stream)>>>(p, out);
-    DCB_CUDA_OK(cudaGetLastError());
-    return 0;
-}
-
-int dcb_rescale_grads(int n_seg, void* const* grads, const int64_t* numel, int dtype,
-                      const float* const* upstream, const float* expected, void* stream) {
-    using namespace dcb;
-    DCB_REQUIRE(n_seg >= 1 && n_seg <= 2 * DCB_MAX_LAYERS, "n_seg=%d out of range", n_seg);
-    RescaleParams p{};
-    p.n_seg = n_seg;
-    for (int k = 0; k < n_seg; ++k) {
-        DCB_REQUIRE(grads[k] && upstream[k], "segment %d: NULL pointer", k);
-        DCB_REQUIRE(expected[k] != 0.f, "segment %d: expected upstream gradient must be non-zero", k);
-        p.seg[k] = RescaleSeg{grads[k], (long long)numel[k], upstream[k], expected[k]};
-    }
-    dim3 grid(kNumSMs * 2, n_seg);
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    switch (dtype) {
-        case DCB_BF16: rescale_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(p); break;
-        case DCB_F16: rescale_kernel<__half><<<grid, 256, 0, st>>>(p); break;
-        case DCB_F32: rescale_kernel<float><<<grid, 256, 0, st>>>(p); break;
-        default: return fail("unknown dtype %d", dtype);
-    }
     DCB_CUDA_OK(cudaGetLastError());
     return 0;
 }

@@ -63,8 +63,13 @@ struct TowerParams {
 // flight while the current one is computed; stream_tiles.cuh).
 extern __shared__ __align__(16) unsigned char tower_dyn_smem[];
 
+// resident CTAs per SM the register budget is compiled for: per-thread loads in flight = 2 heads' worth x AVEC x GPT
+constexpr int tower_min_blocks(int avec, int gpt) {
+    return avec == 0 ? 2 : (gpt == 1 ? 4 : (avec * gpt <= 2 ? 4 : (avec * gpt <= 4 ? 3 : 2)));
+}
+
 template <typename T, typename G, int AVEC, int AH, int GPT>
-__global__ void __launch_bounds__(kStreamThreads, (AVEC == 0 || GPT > 1) ? 2 : 4) tower_stream_kernel(const __grid_constant__ TowerParams p) {
+__global__ void __launch_bounds__(kStreamThreads, tower_min_blocks(AVEC, GPT)) tower_stream_kernel(const __grid_constant__ TowerParams p) {
     constexpr int MVEC = Elem<T>::kPer16B;
     constexpr long long kMseTile = (long long)kStreamThreads * kMseUnroll * MVEC;
     constexpr long long kMseTileScalar = (long long)kStreamThreads * kMseUnroll;
@@ -238,9 +243,10 @@ __global__ void __launch_bounds__(kStreamThreads, (AVEC == 0 || GPT > 1) ? 2 : 4
 // attention groups per thread for this launch (0 = no attention segment with a compile-time head count)
 static int tower_gpt(int avec, int common_h) {
     if (!(common_h == 12 || common_h == 8) || avec > 4) return 1;
-    // measured (scripts/attn_gpt_probe.py): 2 groups per thread lift the stand-alone attention kernel (image stage 0.76 -> 0.86
-    // of HBM) but not the tower launch, where the MSE tiles prefer 4 resident CTAs (image 0.89 either way, text 0.72 -> 0.68)
-    if (const char* e = getenv("DCB_ATTN_GPT")) return atoi(e) == 2 ? 2 : 1;
+    // measured (scripts/attn_gpt_probe.py, round 2): with 2-byte loads (N = 77) 2 groups per thread at 4 resident CTAs lift the text
+    // tower 0.72 -> 0.77 of HBM (4 groups: 0.73); with 8-byte loads (N = 50) the tower is 0.89-0.92 either way -> 1 group
+    if (const char* e = getenv("DCB_ATTN_GPT")) return (atoi(e) == 2 || (atoi(e) == 4 && avec == 1)) ? atoi(e) : 1;
+    if (avec == 1) return 2;
     return 1;
 }
 
@@ -271,15 +277,24 @@ static int launch_tower_h(const TowerParams& p, int common_h, unsigned grid, cud
         return 0;
     } else if constexpr (AVEC <= 4) {          // head loops fully unrolled for the two head counts of the BASELINE configs
         const int gpt = tower_gpt(AVEC, common_h);
-        if (common_h == 12) {
-            if (gpt == 2) tower_stream_kernel<T, G, AVEC, 12, 2><<<grid, kStreamThreads, 0, st>>>(p);
-            else tower_stream_kernel<T, G, AVEC, 12, 1><<<grid, kStreamThreads, 0, st>>>(p);
-            done = true;
-        } else if (common_h == 8) {
-            if (gpt == 2) tower_stream_kernel<T, G, AVEC, 8, 2><<<grid, kStreamThreads, 0, st>>>(p);
-            else tower_stream_kernel<T, G, AVEC, 8, 1><<<grid, kStreamThreads, 0, st>>>(p);
-            done = true;
+#define DCB_TOWER_CASE(HH)                                                                                      \
+        if (common_h == HH) {                                                                                      \
+            bool g4 = false;                                                                                       \
+            if constexpr (AVEC == 1) {                                                                             \
+                if (gpt == 4) {                                                                                    \
+                    tower_stream_kernel<T, G, AVEC, HH, 4><<<grid, kStreamThreads, 0, st>>>(p);                    \
+                    g4 = true;                                                                                     \
+                }                                                                                                  \
+            }                                                                                                      \
+            if (!g4) {                                                                                             \
+                if (gpt == 2) tower_stream_kernel<T, G, AVEC, HH, 2><<<grid, kStreamThreads, 0, st>>>(p);          \
+                else tower_stream_kernel<T, G, AVEC, HH, 1><<<grid, kStreamThreads, 0, st>>>(p);                   \
+            }                                                                                                      \
+            done = true;                                                                                           \
         }
+        DCB_TOWER_CASE(12)
+        DCB_TOWER_CASE(8)
+#undef DCB_TOWER_CASE
     }
     if constexpr (AVEC > 0) {
         if (!done) tower_stream_kernel<T, G, AVEC, 0, 1><<<grid, kStreamThreads, 0, st>>>(p);
@@ -439,7 +454,7 @@ extern "C" int dcb_tower_fwd_bwd(int n_seg, const int32_t* kind, const int32_t* 
         }
     }
     p.total_tiles = tiles;
-    const long long max_grid = (long long)kNumSMs * ((aligned_mode || gpt > 1) ? 2 : 4);     // one persistent CTA per resident slot
+    const long long max_grid = (long long)kNumSMs * (staged_mode ? 4 : tower_min_blocks(aligned_mode ? 0 : avec, gpt));     // one persistent CTA per resident slot
     long long grid = tiles < max_grid ? tiles : max_grid;
     if (grid < 1) grid = 1;
     cudaStream_t st = static_cast<cudaStream_t>(stream);

@@ -1,9 +1,11 @@
 """Host side of the streaming losses: launches through the C ABI + custom autograd.
 
 The one-pass kernels write the student gradients during the forward pass, pre-multiplied by the
-upstream gradient the caller expects (`percent * scale` when called from LossCalculator, else 1).
-`backward` only has to check that expectation on the device (`dcb_rescale_grads`, which exits without
-touching HBM when it holds), so fwd+bwd costs read s + read t + write ds and nothing more.
+upstream gradient the caller is assumed to send (`percent * scale` when called from LossCalculator, else 1;
+times a GradScaler's device-side scale when one is registered).  `backward` launches the same kernel in
+"regrad" mode: it compares the real upstream scalar on the device and exits without touching HBM when
+the assumption held -- fwd+bwd then costs read s + read t + write ds and nothing more -- and otherwise
+recomputes the gradients from the inputs with the true value (one rounding, at the true magnitude).
 """
 from __future__ import annotations
 
@@ -218,22 +220,6 @@ def finalize(terms: Sequence[Tuple[torch.Tensor, int]], scale: Sequence[float], 
               _lib.i32_array([c for _, c in terms]), _lib.f32_array(scale), _lib.f32_array(percent),
               C.c_void_p(out.data_ptr()), _stream_ptr())
     return out
-
-
-def rescale(groups: Sequence[Tuple[Sequence[Optional[torch.Tensor]], torch.Tensor, float]]):
-    """groups: (grads, upstream 0-dim fp32 device tensor, expected value). In-place, early-exit when equal."""
-    by_dtype = {}
-    for grads, up, expected in groups:
-        for g in grads:
-            if g is not None:
-                by_dtype.setdefault(g.dtype, []).append((g, up, expected))
-    for dt, segs in by_dtype.items():
-        for i in range(0, len(segs), 2 * _lib.MAX_LAYERS):
-            part = segs[i:i + 2 * _lib.MAX_LAYERS]
-            _lib.call("dcb_rescale_grads", len(part), _lib.ptr_array([g.data_ptr() for g, _, _ in part]),
-                      _lib.i64_array([g.numel() for g, _, _ in part]), _DT[dt],
-                      _lib.ptr_array([u.data_ptr() for _, u, _ in part]), _lib.f32_array([e for _, _, e in part]),
-                      _stream_ptr())
 
 
 def _as_upstream(g: Optional[torch.Tensor], like: torch.Tensor) -> torch.Tensor:

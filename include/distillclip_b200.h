@@ -97,15 +97,6 @@ int dcb_finalize(int n_terms, const double* const* partials, const int32_t* coun
                  const float* percent, float* out, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
- * Backward helper: the one-pass kernels above write gradients pre-multiplied by the upstream
- * gradient the caller EXPECTS (grad_scale).  At backward time the true upstream scalar lives on
- * the device; this kernel multiplies segment k in place by (*upstream[k] / expected[k]) and exits
- * immediately when they are equal (the common case), so no host sync and no extra HBM pass.
- * --------------------------------------------------------------------------------------------- */
-int dcb_rescale_grads(int n_seg, void* const* grads, const int64_t* numel, int dtype,
-                      const float* const* upstream, const float* expected, void* stream);
-
-/* ---------------------------------------------------------------------------------------------
  * Fused global-batch contrastive (InfoNCE) + teacher/student logit KL from EMBEDDINGS.
  * Replaces, without ever writing the B x B logits:
  *   CLIPModel.forward's normalise + `image_feature @ text_feature.t()` (model/component/clip_model.py:36-44),

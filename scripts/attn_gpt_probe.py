@@ -14,7 +14,7 @@ for name in ("image_stage", "text_stage"):
     els = bench.tower_elements(cfg)
     el = els["attention_probs_kl"]
     s_a, t_a = stu["attention_probs"], tea["attention_probs"]
-    for label, env in (("per-thread gpt=1", {"DCB_ATTN_GPT": "1"}), ("per-thread gpt=2", {"DCB_ATTN_GPT": "2"}),
+    for label, env in (("per-thread gpt=1", {"DCB_ATTN_GPT": "1"}), ("per-thread gpt=2", {"DCB_ATTN_GPT": "2"}), ("per-thread gpt=4", {"DCB_ATTN_GPT": "4"}),
                        ("aligned 16 B", {"DCB_ATTN_ALIGNED": "1"}), ("staged W=512", {"DCB_ATTN_STAGED": "1"}),
                        ("staged W=256", {"DCB_ATTN_STAGED": "1", "DCB_ATTN_STAGE_W": "256"})):
         for k in ("DCB_ATTN_NO_ALIGNED", "DCB_ATTN_GPT", "DCB_ATTN_ALIGNED", "DCB_ATTN_STAGED", "DCB_ATTN_STAGE_W"):

@@ -13,8 +13,8 @@ entries = [(ops.KIND_ATTN_KL, 4, stu["attention_probs"], tea["attention_probs"],
 if "embedding" in stu:
     entries.append((ops.KIND_MSE, 1, [stu["embedding"]], [tea["embedding"]], [True], 1.0))
 w = [1.0] * len(entries)
-for env in ({"DCB_ATTN_GPT": "1"}, {"DCB_ATTN_ALIGNED": "1"}):
-    for k in ("DCB_ATTN_NO_ALIGNED", "DCB_ATTN_GPT", "DCB_ATTN_ALIGNED"):
+for env in ({"DCB_ATTN_GPT": "1"}, {"DCB_ATTN_STAGED": "1"}):
+    for k in ("DCB_ATTN_NO_ALIGNED", "DCB_ATTN_GPT", "DCB_ATTN_ALIGNED", "DCB_ATTN_STAGED"):
         os.environ.pop(k, None)
     os.environ.update(env)
     bufs = ops.launch_tower(entries, w, w)
