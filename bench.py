@@ -605,10 +605,15 @@ def clip_kernel_times(cfg, glob, rank, world, device, pk):
     out = {}
     flush = L2Flush(device)
     g = eng.alloc_g(rows, b, device)
-    kernels = {"clip_fwd_kernel": (fwd, 4.0),
-               "clip_bwd_pair_kernel": (lambda: eng.pair_bwd(a_s, st, a_t, tt, bt, inv[0], inv[1], inv[2], inv[3], coef_row, coef_col,
-                                                             bounds, up, T, g), 6.0),
-               "clip_gt_gemm_kernel": (lambda: eng.col_acc_from_g(g, at, rows, b, d), 2.0)}
+    kernels = {"clip_fwd_kernel": (fwd, 4.0)}
+    if eng.use_split(rows, b):       # split backward: recompute -> G tiles, then one GEMM per tower over the stored tiles
+        kernels["clip_g_tiles_kernel"] = (lambda: eng.g_tiles(a_s, st, a_t, tt, inv[0], inv[1], inv[2], inv[3], coef_row, coef_col,
+                                                              bounds, up, T, g), 4.0)
+        kernels["clip_gt_gemm_kernel<A=G>"] = (lambda: eng.row_acc_from_g(g, bt, rows, b, d), 2.0)
+    else:
+        kernels["clip_bwd_pair_kernel"] = (lambda: eng.pair_bwd(a_s, st, a_t, tt, bt, inv[0], inv[1], inv[2], inv[3], coef_row, coef_col,
+                                                                bounds, up, T, g), 6.0)
+    kernels["clip_gt_gemm_kernel"] = (lambda: eng.col_acc_from_g(g, at, rows, b, d), 2.0)
     for kname, (fn, fl) in kernels.items():
         ms = time_kernel(fn, 10, device, flush)
         flops = fl * rows * b * d
@@ -668,12 +673,12 @@ def bench_clip(cfg, name, args, device, dist, rank, world, pk, steps, warmup):
     e2e = {"value": round(b / (e2e_ms * 1e-3), 1), "unit": "samples/s", "ms_per_step": round(e2e_ms, 4),
            "h2d_bytes_per_step": sum(h.numel() * 2 for h in host) * world, "d2h_bytes_per_step": 4 * world}
     dom = max(kres, key=lambda k: kres[k]["ms"])
-    traffic = first_traffic([f"{PROFILE_ROUND}_ncu_full_clip_{name}.csv", f"r01_ncu_full_clip_{name}.csv"], dom) if world == 1 else None
+    traffic = first_traffic([f"{PROFILE_ROUND}_ncu_full_clip_{name}.csv", f"r01_ncu_full_clip_{name}.csv"], dom.split("<")[0]) if world == 1 else None
     roofline = {"bound": "tensor", "kernel": dom, "achieved": kres[dom]["tflops"], "peak": pk["tf_burst"], "unit": "TFLOP/s",
                 "frac": kres[dom]["frac"], "frac_of_sustained": kres[dom]["frac_of_sustained"],
                 "traffic": traffic,
-                "traffic_note": "dram bytes of one launch of the dominant kernel (ncu --set full, profiles/): it writes the fp16 gradient "
-                                "tiles G (2 B_local B bytes) for the G^T GEMM in addition to re-reading the embeddings from L2/HBM",
+                "traffic_note": "dram bytes of one launch of the dominant kernel (ncu --set full, profiles/); the backward writes the fp16 "
+                                "gradient tiles G (2 B_local B bytes) once and the two gradient GEMMs read them back",
                 "peak_source": pk["source"], "kernels": kres,
                 "step": {"credited_flops": flops, "tflops_all_gpus": round(tf, 2), "peak_all_gpus": pk["tf_burst"] * world,
                          "frac": round(tf / (pk["tf_burst"] * world), 4),

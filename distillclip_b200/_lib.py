@@ -55,6 +55,9 @@ SIGNATURES = {
     "dcb_clip_pair_bwd": [_vp, _vp, _vp, _vp, _vp, C.c_int64, C.c_int64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vpp, _f32p,
                           C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_float,
                           _vp, _vp, C.c_int64, _vp],
+    "dcb_clip_g_tiles": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vpp, _f32p, C.c_int, C.c_int64, C.c_int64,
+                         C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_float, _vp, C.c_int64, _vp],
+    "dcb_clip_row_grads_from_g": [_vp, C.c_int64, _vp, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int64, _vp, _vp],
     "dcb_clip_finish2": [_vp, C.c_int, C.c_int64, _vp, _vp, _vp, C.c_int64, _vp, _vp, C.c_int64, C.c_int64,
                          _vp, C.c_int, C.c_int64, _vp, _vp, _vp, C.c_int64, _vp, _vp, C.c_int64, C.c_int64,
                          C.c_int64, C.c_int64, _vpp, _f32p, _vp, _vp, C.c_int, C.c_int, _vp],
@@ -74,6 +77,7 @@ _SPECIAL = {
     "dcb_clip_pair_splits": (C.c_int, [C.c_int64, C.c_int64, C.c_int64]),
     "dcb_clip_pair_supported": (C.c_int, [C.c_int64]),
     "dcb_clip_gt_splits": (C.c_int, [C.c_int64, C.c_int64, C.c_int64]),
+    "dcb_clip_rg_splits": (C.c_int, [C.c_int64, C.c_int64, C.c_int64]),
     "dcb_clip_gt_splits_scatter": (C.c_int, [C.c_int64, C.c_int64, C.c_int64]),
     "dcb_clip_fwd_chunk_parts": (C.c_int, [C.c_int64, C.c_int64]),
     "dcb_clip_slot_floats": (C.c_int64, [C.c_int64, C.c_int64]),

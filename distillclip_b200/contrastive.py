@@ -267,6 +267,34 @@ class CudaEngine:
                   ops._stream_ptr())
         return acc
 
+    #: split backward (csrc/clip_bwd_g.cu): recompute -> fp16 G tiles, then one tcgen05 GEMM per tower over the stored tiles,
+    #: instead of the pair kernel that fuses the image-side GEMM into the recompute.  "auto": when the local block of the
+    #: logit matrix has at least `split_min_tiles` 128 x 128 tiles (below that the extra launch costs more than it saves)
+    split_backward = os.environ.get("DCB_BWD_SPLIT", "auto")
+    split_min_tiles = int(os.environ.get("DCB_BWD_SPLIT_MIN_TILES", "4096"))
+
+    def use_split(self, rows: int, cols: int) -> bool:
+        if self.split_backward in ("0", "1"):
+            return self.split_backward == "1"
+        return ((rows + 127) // 128) * ((cols + 127) // 128) >= self.split_min_tiles
+
+    def g_tiles(self, a_s, b_s, a_t, b_t, a_s_inv, b_s_inv, a_t_inv, b_t_inv, coef_row, coef_col, bounds, up, temperature,
+                g_out, extra=False, row_offset=0):
+        rows, dim = a_s.shape
+        cols = b_s.shape[0]
+        g5, w8 = self._up_args(up)
+        _lib.call("dcb_clip_g_tiles", _vp(a_s), _vp(b_s), _vp(a_t), _vp(b_t), _vp(a_s_inv), _vp(b_s_inv), _vp(a_t_inv), _vp(b_t_inv),
+                  _vp(coef_row), _vp(coef_col), _vp(bounds), g5, w8, int(bool(extra)), int(row_offset), cols, rows, cols, dim,
+                  ops.dtype_code(a_s), float(temperature or 1.0), _vp(g_out), g_out.shape[1], ops._stream_ptr())
+
+    def row_acc_from_g(self, g, bt_all, rows: int, cols: int, dim: int):
+        """acc[s, i, :] = sum_{j in split s} G[i, j] 2^k b_hat[j, :]  -- tcgen05 GEMM with A = G read K-major."""
+        n_split = _lib.load().dcb_clip_rg_splits(rows, cols, dim)
+        acc = torch.empty(n_split, rows, dim, dtype=torch.float32, device=g.device)
+        _lib.call("dcb_clip_row_grads_from_g", _vp(g), g.shape[1], _vp(bt_all), bt_all.stride(1), cols // bt_all.shape[0],
+                  rows, cols, dim, _vp(acc), ops._stream_ptr())
+        return acc
+
     def finish2(self, side_a, side_b, global_batch, up, bounds, grad_dtype, cos_flag=None):
         """side = dict(acc [n_split, rows, D], x [rows, D], x_inv, y (label rows of the other tower), y_inv, label_offset) or None."""
         args, grads, ref = [], [], side_a or side_b

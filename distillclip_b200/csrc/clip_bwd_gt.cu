@@ -17,6 +17,12 @@
 // B = a_hat^T [D, rows] fp16 (K-major, the same layout the a-side GEMM uses for b_hat^T), each CTA stages half of
 // the N rows.  K can be split over clusters (fp32 partial buffers, summed by clip_grad_finish).
 // Warps: 0 = TMA, 1 = TMEM alloc + MMA issue (leader), 2-5 = epilogue (TMEM -> fp32 partial buffer).
+//
+// kAK = true instantiation (split backward, clip_bwd_g.cu): the OTHER tower's gradient from the same stored tiles,
+//        acc_a[i, :] = sum_j G[i, j] b_hat[j, :]
+// -- M = i, K = j, so A = G is an ordinary K-major operand (one TMA box {64 j, 128 i} per CTA and K chunk) and B = b_hat^T
+// [D, cols] fp16 K-major, stored as one [D, cols / R] block per source rank (`b_block_cols`).  Same ring, MMA shape, K split
+// and epilogue; in the code below "rows" is always the K extent and "cols" the M extent of the launch.
 #include "tc_common.cuh"
 
 namespace dcb {
@@ -44,6 +50,8 @@ struct ClipGtParams {
     int pieces;               // MMA instructions per K step (1 or 2), each chunk / pieces wide
     int n_chunks, m_tiles, k_split;
     int stages, stage_bytes;
+    int b_block_cols;         // kAK: B is stored as row blocks [n_blocks][b_block_rows][b_block_cols] over K (0 = one block)
+    int b_block_rows;
 };
 
 __device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr) {
@@ -56,6 +64,7 @@ __device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr) {
     return d;
 }
 
+template <bool kAK>
 __global__ void __launch_bounds__(gt::kThreads, 1)
 clip_gt_gemm_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_constant__ CUtensorMap map_at,
                     const __grid_constant__ ClipGtParams p, const uint32_t idesc) {
@@ -113,11 +122,20 @@ clip_gt_gemm_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_cons
                 const uint32_t dst = ring + stage * p.stage_bytes;
                 if (leader) mbar_arrive_expect_tx(bar_full + 8 * stage, 2 * bytes_per_cta);
                 const uint32_t full = map_to_cta(bar_full + 8 * stage, 0);
-                tma_load_2d_pair(dst, &map_g, full, j0, kc * kBK);                       // M block 0: j0 .. j0+63
-                tma_load_2d_pair(dst + 64 * kBK * 2, &map_g, full, j0 + 64, kc * kBK);   // M block 1
+                int bx = kc * kBK, by = n0 + (int)rank * half_n;
+                if constexpr (kAK) {
+                    tma_load_2d_pair(dst, &map_g, full, kc * kBK, j0);                       // K-major: 128 M rows x 64 k
+                    if (p.b_block_cols > 0) {                                                // K chunks never straddle a block
+                        const int blk = bx / p.b_block_cols;
+                        bx -= blk * p.b_block_cols;
+                        by += blk * p.b_block_rows;
+                    }
+                } else {
+                    tma_load_2d_pair(dst, &map_g, full, j0, kc * kBK);                       // M block 0: j0 .. j0+63
+                    tma_load_2d_pair(dst + 64 * kBK * 2, &map_g, full, j0 + 64, kc * kBK);   // M block 1
+                }
                 for (int pc = 0; pc < p.pieces; ++pc)
-                    tma_load_2d_pair(dst + kATile + pc * half_n * kBK * 2, &map_at, full, kc * kBK,
-                                     n0 + pc * piece_n + (int)rank * half_n);
+                    tma_load_2d_pair(dst + kATile + pc * half_n * kBK * 2, &map_at, full, bx, by + pc * piece_n);
                 if (++stage == p.stages) { stage = 0; phase ^= 1; }
             }
         }
@@ -130,13 +148,14 @@ clip_gt_gemm_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_cons
                 tc_fence_after_sync();
                 const uint32_t src = ring + stage * p.stage_bytes;
                 if (elect_one()) {
-                    const uint64_t da = umma_desc_mn_sw128(src);
+                    const uint64_t da = kAK ? umma_desc_k_sw128(src) : umma_desc_mn_sw128(src);
+                    constexpr uint64_t kAStep = kAK ? 2 : (2048 >> 4);       // start-address step of A per K = 16
 #pragma unroll
                     for (int k = 0; k < kBK / kUmmaK; ++k) {
                         const uint32_t accum = (kc > kc_begin || k > 0) ? 1u : 0u;
                         for (int pc = 0; pc < p.pieces; ++pc) {
                             const uint64_t db = umma_desc_k_sw128(src + kATile + pc * half_n * kBK * 2);
-                            umma_f16_pair(tmem_base + pc * piece_n, da + (uint64_t)(k * (2048 >> 4)), db + 2 * k, idesc, accum);
+                            umma_f16_pair(tmem_base + pc * piece_n, da + (uint64_t)k * kAStep, db + 2 * k, idesc, accum);
                         }
                     }
                     umma_commit_pair(bar_empty + 8 * stage, 3);
@@ -246,18 +265,30 @@ extern "C" int dcb_clip_gt_splits_scatter(int64_t rows, int64_t cols, int64_t di
 }
 
 namespace dcb {
+// rows = K extent, cols = M extent.  a_kmajor = false: G is [rows][cols] (A = G^T MN-major), B = a_hat^T [dim][rows].
+// a_kmajor = true: G is [cols][rows] (A = G K-major), B = b_hat^T in blocks of b_block_cols K columns ([dim * n_blocks][b_block_cols]).
 static int clip_gt_launch(const void* g, int64_t g_pitch_elems, const void* a_hat_t, int64_t at_pitch_elems, int64_t rows,
                           int64_t cols, int64_t dim, float* acc_parts, void* const* dest, int n_dest, int src_slot,
-                          void* stream) {
+                          void* stream, bool a_kmajor = false, int64_t b_block_cols = 0) {
     DCB_REQUIRE(g && a_hat_t && (acc_parts || n_dest > 0), "NULL pointer argument");
     DCB_REQUIRE(rows >= 1 && cols >= 1 && dim >= 8 && dim % 8 == 0, "bad shape");
-    DCB_REQUIRE(g_pitch_elems >= cols && g_pitch_elems % 8 == 0, "G pitch must be >= cols and a multiple of 8 elements");
-    DCB_REQUIRE(at_pitch_elems >= rows && at_pitch_elems % 8 == 0, "a_hat^T pitch must be >= rows and a multiple of 8 elements");
+    DCB_REQUIRE(g_pitch_elems >= (a_kmajor ? rows : cols) && g_pitch_elems % 8 == 0, "G pitch must be >= its column count and a multiple of 8 elements");
+    if (b_block_cols <= 0 || b_block_cols >= rows) b_block_cols = rows;
+    DCB_REQUIRE(b_block_cols == rows || (a_kmajor && b_block_cols % 64 == 0 && rows % b_block_cols == 0),
+                "B blocks must hold a multiple of 64 K columns and divide the K extent");
+    DCB_REQUIRE(at_pitch_elems >= b_block_cols && at_pitch_elems % 8 == 0, "B^T pitch must be >= its column count and a multiple of 8 elements");
     const GtPlan plan = clip_gt_plan(rows, cols, dim, n_dest > 0);
     CUtensorMap map_g, map_at;
-    if (tc::encode_tile_map_16bit(&map_g, g, rows, cols, (uint64_t)g_pitch_elems * 2, 64)) return 1;
-    if (tc::encode_tile_map_16bit(&map_at, a_hat_t, dim, rows, (uint64_t)at_pitch_elems * 2, plan.chunk / plan.pieces / 2)) return 1;
+    if (a_kmajor) {
+        if (tc::encode_tile_map_16bit(&map_g, g, cols, rows, (uint64_t)g_pitch_elems * 2, 128)) return 1;
+    } else {
+        if (tc::encode_tile_map_16bit(&map_g, g, rows, cols, (uint64_t)g_pitch_elems * 2, 64)) return 1;
+    }
+    const int64_t n_blocks = rows / b_block_cols;
+    if (tc::encode_tile_map_16bit(&map_at, a_hat_t, dim * n_blocks, b_block_cols, (uint64_t)at_pitch_elems * 2, plan.chunk / plan.pieces / 2)) return 1;
     ClipGtParams p{};
+    p.b_block_cols = n_blocks > 1 ? (int)b_block_cols : 0;
+    p.b_block_rows = (int)dim;
     p.acc = acc_parts;
     p.n_dest = n_dest;
     p.src_slot = src_slot;
@@ -274,12 +305,13 @@ static int clip_gt_launch(const void* g, int64_t g_pitch_elems, const void* a_ha
     p.stages = plan.stages;
     p.stage_bytes = plan.stage_bytes;
     // fp16 x fp16 -> fp32, M = 256 over the pair, A (= G^T) MN-major (bit 15), B K-major
-    const uint32_t idesc = tc::umma_idesc_f16(256, plan.chunk / plan.pieces, 0) | (1u << 15);
+    const uint32_t idesc = tc::umma_idesc_f16(256, plan.chunk / plan.pieces, 0) | (a_kmajor ? 0u : (1u << 15));
     const int smem = 1024 + plan.stages * plan.stage_bytes + 8 * (2 * plan.stages + 1) + 16;
-    static int max_set = 0;
-    if (smem > max_set) {
-        DCB_CUDA_OK(cudaFuncSetAttribute(clip_gt_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        max_set = smem;
+    static int max_set[2] = {0, 0};
+    if (smem > max_set[a_kmajor]) {
+        if (a_kmajor) DCB_CUDA_OK(cudaFuncSetAttribute(clip_gt_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        else DCB_CUDA_OK(cudaFuncSetAttribute(clip_gt_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        max_set[a_kmajor] = smem;
     }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)(2 * plan.m_tiles * plan.n_chunks * plan.k_split));
@@ -293,10 +325,24 @@ static int clip_gt_launch(const void* g, int64_t g_pitch_elems, const void* a_ha
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    DCB_CUDA_OK(cudaLaunchKernelEx(&cfg, clip_gt_gemm_kernel, map_g, map_at, p, idesc));
+    if (a_kmajor) DCB_CUDA_OK(cudaLaunchKernelEx(&cfg, clip_gt_gemm_kernel<true>, map_g, map_at, p, idesc));
+    else DCB_CUDA_OK(cudaLaunchKernelEx(&cfg, clip_gt_gemm_kernel<false>, map_g, map_at, p, idesc));
     return 0;
 }
 }  // namespace dcb
+
+// Split backward, a side: acc_parts[s][i, :] = sum_{j in K split s} G[i, j] 2^k b_hat[j, :] from the tiles dcb_clip_g_tiles stored.
+// b_hat_t: fp16 [n_blocks][dim][bt_pitch_elems] with bt_block_cols valid columns per block (one block per source rank; 0 = one
+// block of `cols` columns).  acc_parts: dcb_clip_rg_splits(...) buffers of [rows_local, dim] fp32 (same 2^k scale).
+extern "C" int dcb_clip_rg_splits(int64_t rows_local, int64_t cols, int64_t dim) {
+    return dcb::clip_gt_plan(cols, rows_local, dim).k_split;
+}
+extern "C" int dcb_clip_row_grads_from_g(const void* g, int64_t g_pitch_elems, const void* b_hat_t, int64_t bt_pitch_elems,
+                                         int64_t bt_block_cols, int64_t rows_local, int64_t cols, int64_t dim, float* acc_parts,
+                                         void* stream) {
+    return dcb::clip_gt_launch(g, g_pitch_elems, b_hat_t, bt_pitch_elems, cols, rows_local, dim, acc_parts, nullptr, 0, 0, stream,
+                               true, bt_block_cols);
+}
 
 extern "C" int dcb_clip_col_grads_from_g(const void* g, int64_t g_pitch_elems, const void* a_hat_t, int64_t at_pitch_elems,
                                          int64_t rows, int64_t cols, int64_t dim, float* acc_parts, void* stream) {

@@ -567,9 +567,16 @@ def backward_gemms(engine, v, ups, want_txt=True):
     b_local, dim = si.shape
     b = v["b_global"]
     g = engine.alloc_g(b_local, b, si.device)
-    v["acc_a"] = engine.pair_bwd(si, s.st_all, v["ti"], s.tt_all, s.bt_all, v["si_inv"], s.st_inv_all, v["ti_inv"], s.tt_inv_all,
-                                 v["coef_row"], v["coef_col"], v["bounds"], _upstream(v, ups), v["temperature"], g,
-                                 extra=v["extra"], row_offset=xc.rank * b_local)
+    if getattr(engine, "use_split", None) and engine.use_split(b_local, b):
+        # split flow: recompute -> fp16 G tiles; both towers' gradients are GEMMs over the stored tiles
+        engine.g_tiles(si, s.st_all, v["ti"], s.tt_all, v["si_inv"], s.st_inv_all, v["ti_inv"], s.tt_inv_all, v["coef_row"],
+                       v["coef_col"], v["bounds"], _upstream(v, ups), v["temperature"], g, extra=v["extra"],
+                       row_offset=xc.rank * b_local)
+        v["acc_a"] = engine.row_acc_from_g(g, s.bt_all, b_local, b, dim)
+    else:
+        v["acc_a"] = engine.pair_bwd(si, s.st_all, v["ti"], s.tt_all, s.bt_all, v["si_inv"], s.st_inv_all, v["ti_inv"], s.tt_inv_all,
+                                     v["coef_row"], v["coef_col"], v["bounds"], _upstream(v, ups), v["temperature"], g,
+                                     extra=v["extra"], row_offset=xc.rank * b_local)
     v["acc_b"], v["scattered"] = None, False
     if want_txt:
         targets = xc.gt_targets(s) if xc.world > 1 else None

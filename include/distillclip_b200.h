@@ -302,6 +302,24 @@ int dcb_clip_pair_bwd(const void* stu_a, const void* stu_b, const void* tea_a, c
                       int64_t rows_local, int64_t cols, int64_t dim, int dtype,
                       float temperature, float* acc_parts, void* g_out, int64_t g_pitch_elems, void* stream);
 
+/* SPLIT backward (default for large batches): the logits are recomputed once by a kernel of the forward's shape (256 rows
+ * per CTA pair, double-buffered S/T accumulators) that only STORES the scaled fp16 gradient tiles G 2^k (arguments as
+ * dcb_clip_pair_bwd, without accumulators); both towers' gradients are then tcgen05 GEMMs over the stored tiles:
+ * dcb_clip_row_grads_from_g (acc_a = G b_hat, A = G K-major; b_hat_t in blocks of bt_block_cols columns per source rank) and
+ * dcb_clip_col_grads_from_g / _scatter (acc_b = G^T a_hat).  acc_parts: dcb_clip_rg_splits(...) buffers of [rows_local, dim].
+ * Replaces autograd through clip_model.py:36-44 + hard_label.py:10-12 + soft_label.py:11-16 (+ clip_cos_diff.py:16-23,
+ * logits_mse.py:9-10 with extra = 1), like the pair kernel it is an alternative to. */
+int dcb_clip_g_tiles(const void* stu_a, const void* stu_b, const void* tea_a, const void* tea_b,
+                     const float* stu_a_inv, const float* stu_b_inv, const float* tea_a_inv, const float* tea_b_inv,
+                     const float* coef_row, const float* coef_col, const float* bounds,
+                     const float* const* g5, const float* w8, int extra, int64_t row_offset, int64_t global_batch,
+                     int64_t rows_local, int64_t cols, int64_t dim, int dtype, float temperature, void* g_out,
+                     int64_t g_pitch_elems, void* stream);
+int dcb_clip_rg_splits(int64_t rows_local, int64_t cols, int64_t dim);
+int dcb_clip_row_grads_from_g(const void* g, int64_t g_pitch_elems, const void* b_hat_t, int64_t bt_pitch_elems,
+                              int64_t bt_block_cols, int64_t rows_local, int64_t cols, int64_t dim, float* acc_parts,
+                              void* stream);
+
 /* Backward, last kernel, both towers in one launch (side a = image rows from the pair kernel's accumulators, side b = text
  * rows from the G^T GEMM's): grad[i,:] = r_i (acc_i - x_hat_i (x_hat_i . acc_i)), acc_i = 2^-k sum_s acc[s][i,:] - (up_hard / B)
  * y_hat_{label_offset + i}.  A side with grad == NULL is skipped.  cos_flag (optional, [rows] = coef_row row 3): the diagonal

@@ -12,6 +12,6 @@ CMD="python bench.py --steps 2 --warmup 3 --no-extras --no-cpu --no-parity"
 timeout 600 $CMD > $OUT/${TAG}_plain.log 2>&1 &&
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $OUT/${TAG}_launches_sweep.csv $CMD > $OUT/${TAG}_ncu_launches.log 2>&1
 echo "launch list exit $?"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:"clip_fwd_kernel|clip_bwd_pair_kernel|clip_gt_gemm_kernel|clip_post|clip_prep|clip_finish2" -c 8 -o $OUT/${TAG}_prof_sweep -f $CMD > $OUT/${TAG}_ncu_full.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"clip_fwd_kernel|clip_bwd_pair_kernel|clip_g_tiles_kernel|clip_gt_gemm_kernel|clip_post|clip_prep|clip_finish2" -c 8 -o $OUT/${TAG}_prof_sweep -f $CMD > $OUT/${TAG}_ncu_full.log 2>&1
 echo "ncu full exit $?"
 tail -c 600 $OUT/${TAG}_bench_n1.err

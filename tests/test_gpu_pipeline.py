@@ -13,6 +13,18 @@ pytestmark = pytest.mark.gpu
 LOSS_RTOL, GRAD_RTOL, GRAD_BF16_STORAGE_RTOL = 1e-4, 1e-3, 4e-3
 
 
+@pytest.fixture(params=["pair", "split"], autouse=True)
+def backward_flow(request):
+    """Every test of this module runs with both backward flows: the fused pair kernel (recompute + image-side GEMM) and the
+    split flow (recompute -> fp16 G tiles, one GEMM per tower over the stored tiles; the default above 4096 tiles)."""
+    from distillclip_b200 import contrastive as ct
+    eng = type(ct._ENGINE)
+    old = eng.split_backward
+    eng.split_backward = "1" if request.param == "split" else "0"
+    yield request.param
+    eng.split_backward = old
+
+
 def synth(b, d, seed, dtype=torch.bfloat16):
     gen = torch.Generator().manual_seed(seed)
     ti = torch.randn(b, d, generator=gen)
