@@ -2,8 +2,9 @@
 in seven launches on one GPU and with three cross-rank barriers (no collective) on N GPUs.
 
     forward   prep -> [similarity tiles per source rank, as the peers' text rows arrive] -> post1 -> (barrier) -> post2
-    backward  pair kernel (recompute once, image-side gradient, fp16 G tiles) -> G^T GEMM scattering every text row's partial
-              sums into its owner's buffer -> (barrier) -> finish (both towers)
+    backward  recompute once -> fp16 G tiles (split flow; small batches: the pair kernel, which also does the image-side GEMM)
+              -> G^T GEMM scattering every text row's partial sums into its owner's buffer -> (barrier, behind the image-side
+              GEMM over the same tiles) -> finish (both towers)
 
 Replaces `CLIPModel.forward`'s normalise + matmul (reference model/component/clip_model.py:36-44), `HardLabel`
 (model/loss_component/hard_label.py:10-12), `SoftLabel` (soft_label.py:11-16), the 0.5 (i2t + t2i) sums and the scale /
@@ -382,8 +383,24 @@ class SymmExchange(LocalExchange):
         off = s.regions["gt_parts"][0]
         return [s.gt_parts if d == self.rank else PeerRef(s.peer_base[d] + off) for d in range(self.world)]
 
+    def begin_after_scatter(self, s):
+        """Start the barrier that follows the scattering GEMM on the side stream; `after_scatter` then only waits for it."""
+        main = torch.cuda.current_stream()
+        issued = torch.cuda.Event()
+        issued.record(main)
+        with torch.cuda.stream(self.comm):
+            self.comm.wait_event(issued)
+            s.hdl.barrier(channel=0)
+            s.scatter_done = torch.cuda.Event()
+            s.scatter_done.record(self.comm)
+
     def after_scatter(self, s):
-        s.hdl.barrier(channel=0)
+        done = getattr(s, "scatter_done", None)
+        if done is not None:
+            torch.cuda.current_stream().wait_event(done)
+            s.scatter_done = None
+        else:
+            s.hdl.barrier(channel=0)
 
     def reduce_scatter(self, acc, s):
         return _reduce_scatter(self.group, self.rank, acc, s.b_local)
@@ -567,24 +584,33 @@ def backward_gemms(engine, v, ups, want_txt=True):
     b_local, dim = si.shape
     b = v["b_global"]
     g = engine.alloc_g(b_local, b, si.device)
+    v["acc_b"], v["scattered"] = None, False
+
+    def text_side():
+        if not want_txt:
+            return
+        targets = xc.gt_targets(s) if xc.world > 1 else None
+        if targets is not None:
+            engine.col_acc_scatter(g, v["at"], b_local, b, dim, targets, xc.rank)
+            v["scattered"] = True
+            if hasattr(xc, "begin_after_scatter"):
+                xc.begin_after_scatter(s)         # the cross-rank barrier runs on the side stream, behind whatever follows here
+        else:
+            v["acc_b"] = engine.col_acc_from_g(g, v["at"], b_local, b, dim)
+
     if getattr(engine, "use_split", None) and engine.use_split(b_local, b):
-        # split flow: recompute -> fp16 G tiles; both towers' gradients are GEMMs over the stored tiles
+        # split flow: recompute -> fp16 G tiles; both towers' gradients are GEMMs over the stored tiles.  The text-side GEMM goes
+        # first: its NVLink stores and the barrier that follows them overlap the (local) image-side GEMM
         engine.g_tiles(si, s.st_all, v["ti"], s.tt_all, v["si_inv"], s.st_inv_all, v["ti_inv"], s.tt_inv_all, v["coef_row"],
                        v["coef_col"], v["bounds"], _upstream(v, ups), v["temperature"], g, extra=v["extra"],
                        row_offset=xc.rank * b_local)
+        text_side()
         v["acc_a"] = engine.row_acc_from_g(g, s.bt_all, b_local, b, dim)
     else:
         v["acc_a"] = engine.pair_bwd(si, s.st_all, v["ti"], s.tt_all, s.bt_all, v["si_inv"], s.st_inv_all, v["ti_inv"], s.tt_inv_all,
                                      v["coef_row"], v["coef_col"], v["bounds"], _upstream(v, ups), v["temperature"], g,
                                      extra=v["extra"], row_offset=xc.rank * b_local)
-    v["acc_b"], v["scattered"] = None, False
-    if want_txt:
-        targets = xc.gt_targets(s) if xc.world > 1 else None
-        if targets is not None:
-            engine.col_acc_scatter(g, v["at"], b_local, b, dim, targets, xc.rank)
-            v["scattered"] = True
-        else:
-            v["acc_b"] = engine.col_acc_from_g(g, v["at"], b_local, b, dim)
+        text_side()
 
 
 def backward_finish(engine, v, ups, want_img=True, want_txt=True, grad_dtype=None):
