@@ -29,6 +29,8 @@
 // 16 columns at a time: four warps per scheduler hide the MUFU / FMA / shuffle latency (one warp per scheduler issued
 // every ~3 cycles, ncu r01d; two reached 48 % issue utilisation with the epilogue setting the tile time, r01q).
 // The four column quarters of a row are accumulated separately and added by the combine kernel.
+#include <type_traits>
+
 #include "tc_common.cuh"
 
 namespace dcb {
@@ -76,22 +78,6 @@ __device__ __forceinline__ float ex2(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
-}
-
-// Sum over the 32 lanes (= 32 rows) of a[0..15] (= 16 columns): recursive halving, each step exchanges half of the
-// remaining values with the lane `s` away.  Afterwards lane L holds the total of column L >> 1 in a[0].
-__device__ __forceinline__ void column_sums16(float (&a)[16], int lane) {
-#pragma unroll
-    for (int s = 16, n = 8; n >= 1; s >>= 1, n >>= 1) {
-        const bool up = lane & s;
-#pragma unroll
-        for (int i = 0; i < n; ++i) {
-            const float keep = up ? a[i + n] : a[i];
-            const float send = up ? a[i] : a[i + n];
-            a[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
-        }
-    }
-    a[0] += __shfl_xor_sync(0xffffffffu, a[0], 1);
 }
 
 template <bool kTeacher, bool kCols, bool kExtra = false>
@@ -205,32 +191,45 @@ clip_fwd_kernel(const __grid_constant__ CUtensorMap map_a_stu, const __grid_cons
             }
         }
     } else {
-        // ---------------------------------------------------------------- epilogue: 16 warps, one row per thread
+        // ---------------------------------------------------------------- epilogue: 16 warps; warp (q, sub) owns TMEM lanes
+        // 32 q .. 32 q + 31 (rows) and columns [32 sub, 32 sub + 32) of the tile.  The accumulators are read with the 16x256b
+        // shape (the mma fragment layout, scripts/probe/tmem_layout_probe.cu): thread t = 4 g + m of the warp holds the FOUR rows
+        // 16 h + 8 rr + g (h, rr in {0, 1}) and the column pairs 8 rep + 2 m + {0, 1} -- so the column sums (the statistics of the
+        // opposite direction) are three in-thread additions plus a recursive halving over 8 lane groups, and the row sums a
+        // halving over 4 lanes once per tile, instead of a 32-lane butterfly per statistic and 16 columns (which was half of
+        // this kernel's instructions: 45 -> 25 per logit pair).
         const int q = warp & 3;                             // TMEM lane quadrant this warp may read
         const int sub = (warp - 2) >> 2;                    // column quarter of the tile handled by this warp
-        const int r = q * 32 + lane;                        // row inside the block
+        const int g = lane >> 2, m = lane & 3;
         const int ep_tid = (warp - 2) * 32 + lane;          // 0..511, used to stage column scales
-        const int grow = row0 + r;                          // local row
-        const bool row_ok = grow < p.rows;
+        constexpr int NR = kTeacher ? (kExtra ? 6 : 4) : 2; // row sums carried per row: A, Q (or the rank count), Zt, W, relu(S-T), (S-T)^2
+        constexpr int NC = kTeacher ? 4 : 1;                // column sums
         const float LOG2E = 1.4426950408889634f;
-        const float r_s = row_ok ? __ldg(p.a_inv_stu + grow) : 0.f;
-        const float r_t = (kTeacher && row_ok) ? __ldg(p.a_inv_tea + grow) : 0.f;
-        const float k1 = r_s * LOG2E, k1t = r_s * LOG2E * p.inv_temp, k2t = r_t * LOG2E * p.inv_temp;
-        const float n1 = -LOG2E, n1t = -LOG2E * p.inv_temp;
-        const int diag_col = p.row_offset + grow;           // global column holding this row's label
-        // Row totals with Kahan compensation: sums of each 32-column chunk start from zero (small magnitudes) and are
-        // folded into the running totals with an error term, so Zt, W and Q keep ~1e-7 relative accuracy even for B = 32768
-        // (plain fp32 accumulation costs ~1e-4 on the loss, measured).
-        float A = 0.f, Q = 0.f, Zt = 0.f, W = 0.f, diag = 0.f;
-        const float rank_ref = (!kTeacher && !kCols && p.rank_ref && row_ok) ? __ldg(p.rank_ref + grow) : 0.f;
-        int n_greater = 0;
-        float cA = 0.f, cQ = 0.f, cZt = 0.f, cW = 0.f;
-        float XR = 0.f, XM = 0.f, cXR = 0.f, cXM = 0.f, diag_tv = 0.f;     // kExtra: relu(S - T) and (S - T)^2 row sums, T_ii
-        bool have_diag = false;
-        auto kahan = [](float& sum, float& comp, float x) {
-            const float y = x - comp;
+        const float k1 = LOG2E, n1 = -LOG2E, k1t = LOG2E * p.inv_temp, n1t = -LOG2E * p.inv_temp;
+        const bool ranking = !kTeacher && !kCols && p.rank_ref != nullptr;
+        // the four rows this thread computes on (index 2 h + rr)
+        float r_s[4], r_t[4], rank_ref[4];
+        bool rok[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int grow_i = row0 + q * 32 + 16 * (i >> 1) + 8 * (i & 1) + g;
+            rok[i] = grow_i < p.rows;
+            r_s[i] = rok[i] ? __ldg(p.a_inv_stu + grow_i) : 0.f;
+            r_t[i] = (kTeacher && rok[i]) ? __ldg(p.a_inv_tea + grow_i) : 0.f;
+            rank_ref[i] = (ranking && rok[i]) ? __ldg(p.rank_ref + grow_i) : 0.f;
+        }
+        // the one row this thread OWNS the totals of (after the per-tile halving over the 4 lanes of a group): index m
+        const int grow = row0 + q * 32 + 16 * (m >> 1) + 8 * (m & 1) + g;
+        const bool row_ok = grow < p.rows;
+        // Row totals with Kahan compensation: the sums of each tile quarter start from zero (small magnitudes) and are folded
+        // into the running totals with an error term, so Zt, W and Q keep ~1e-7 relative accuracy even for B = 32768
+        float tot[NR], comp[NR];
+#pragma unroll
+        for (int k = 0; k < NR; ++k) tot[k] = comp[k] = 0.f;
+        auto kahan = [](float& sum, float& c, float x) {
+            const float y = x - c;
             const float t = sum + y;
-            comp = (t - sum) - y;
+            c = (t - sum) - y;
             sum = t;
         };
         // column partial sums of the previous tile: [4 quadrants][4 stats][128 columns] -> global, 2 values per thread
@@ -263,113 +262,141 @@ clip_fwd_kernel(const __grid_constant__ CUtensorMap map_a_stu, const __grid_cons
             mbar_wait(bar_tfull + 8 * as, aphase);
             tc_fence_after_sync();
             const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * 256;
-            // masks are only needed where the tile meets the matrix edge, the diagonal, or rows beyond the batch
-            const bool edge = (col0 + kBN > p.cols) || (diag_col >= col0 && diag_col < col0 + kBN) ||
+            // masks are only needed where the tile meets the matrix edge, the diagonal, or rows beyond the batch (CTA-uniform)
+            const int dlo = p.row_offset + row0;                // label columns of this CTA's rows: [dlo, dlo + 128)
+            const bool edge = (col0 + kBN > p.cols) || (dlo < col0 + kBN && dlo + kBM > col0) ||
                               (row0 + kBM > p.rows) || (p.dump_s != nullptr) || (p.dump_t != nullptr);
             float* cb = col_buf + (t & 1) * (4 * 4 * kBN) + q * (4 * kBN);     // this quadrant's [4 stats][128 columns]
-#pragma unroll 1
-            for (int hc = 0; hc < 2; ++hc) {                // 16 columns at a time (keeps the register footprint under 113)
-                float sv[16], tv[16];
-                const int cbase = sub * 32 + hc * 16;
-                tmem_ld_32x16(lane_addr + cbase, sv);
-                if (kTeacher) tmem_ld_32x16(lane_addr + 128 + cbase, tv);
-                tmem_ld_wait();
-                if (hc == 1) {                              // last TMEM read of this tile: release the accumulator stage
-                    tc_fence_before_sync();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive_cluster(l_tempty + 8 * as);
-                }
-                const float* scs = sc + cbase;
-                const float* sct = sc + kBN + cbase;
-                float a_sum = 0.f, q_sum = 0.f, zt_sum = 0.f, w_sum = 0.f, xr_sum = 0.f, xm_sum = 0.f;
+            float rowp[4][NR];                              // this tile quarter's sums of the four rows
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int k = 0; k < NR; ++k) rowp[i][k] = 0.f;
+            // 8 columns at a time: this thread's column pair is cbase + 2 m + {0, 1}.  Two instantiations of the body: the masked one
+            // only for tiles on the matrix edge / the diagonal (a per-element `if (edge)` gets if-converted into predicated
+            // address arithmetic for every element)
+            auto piece = [&](int pc, auto edge_tag) {
+                constexpr bool kEdge = decltype(edge_tag)::value;
+                const int cbase = sub * 32 + pc * 8;
+                float cs[2], ct[2];
                 {
-                    float e[16], f[16];
-                    // ---- A = sum exp(S - 1)
-#pragma unroll
-                    for (int c = 0; c < 16; ++c) {
-                        const float u = sv[c] * scs[c];
-                        sv[c] = u;                                            // keep the scaled logit (still * 1/r_s)
-                        e[c] = ex2(fmaf(u, k1, n1));
-                    }
-                    if (edge) {
-#pragma unroll
-                        for (int c = 0; c < 16; ++c) {
-                            const int gc = col0 + cbase + c;
-                            const float s = sv[c] * r_s;
-                            if (gc == diag_col && gc < p.cols) { diag = s; have_diag = true; }
-                            if (p.dump_s && row_ok && gc < p.cols) p.dump_s[(size_t)grow * p.cols + gc] = s;
-                            if (!(gc < p.cols && row_ok)) e[c] = 0.f;
-                        }
-                    }
-#pragma unroll
-                    for (int c = 0; c < 16; ++c) a_sum += e[c];
-                    if constexpr (!kTeacher && !kCols) {
-                        if (p.rank_ref) {                     // same expression as the diagonal extraction: S_ii compares equal to itself
-#pragma unroll
-                            for (int c = 0; c < 16; ++c)
-                                n_greater += (col0 + cbase + c < p.cols && sv[c] * r_s > rank_ref) ? 1 : 0;
-                        }
-                    }
-                    if (kCols) {
-                        column_sums16(e, lane);
-                        if (!(lane & 1)) cb[0 * kBN + cbase + (lane >> 1)] = e[0];
-                    }
+                    const float2 a = *reinterpret_cast<const float2*>(sc + cbase + 2 * m);
+                    cs[0] = a.x;
+                    cs[1] = a.y;
                     if (kTeacher) {
-                        // ---- es = exp((S - 1)/T) (kept in e), et = exp((Tt - 1)/T) (overwrites tv), f = et (Tt - S)
-                        if (edge && p.dump_t) {
+                        const float2 b = *reinterpret_cast<const float2*>(sc + kBN + cbase + 2 * m);
+                        ct[0] = b.x;
+                        ct[1] = b.y;
+                    }
+                }
+                float colacc[NC][2];                        // sums over this thread's four rows, per statistic and column
 #pragma unroll
-                            for (int c = 0; c < 16; ++c)
-                                if (row_ok && col0 + cbase + c < p.cols)
-                                    p.dump_t[(size_t)grow * p.cols + col0 + cbase + c] = tv[c] * sct[c] * r_t;
-                        }
+                for (int k = 0; k < NC; ++k) colacc[k][0] = colacc[k][1] = 0.f;
 #pragma unroll
-                        for (int c = 0; c < 16; ++c) {
-                            e[c] = ex2(fmaf(sv[c], k1t, n1t));
-                            const float v = tv[c] * sct[c];
-                            const float et = ex2(fmaf(v, k2t, n1t));
-                            const float d = fmaf(v, r_t, -(sv[c] * r_s));               // T_ij - S_ij
-                            f[c] = et * d;
-                            tv[c] = et;
-                            if constexpr (kExtra) {
-                                const int gc = col0 + cbase + c;
-                                const bool ok = !edge || (gc < p.cols && row_ok);
-                                if (edge && gc == diag_col && gc < p.cols) diag_tv = v * r_t;
-                                xr_sum += ok ? fmaxf(-d, 0.f) : 0.f;
-                                xm_sum = ok ? fmaf(d, d, xm_sum) : xm_sum;
+                for (int h = 0; h < 2; ++h) {
+                    float sv[4], tv[4];                      // register 2 rr + e
+                    const uint32_t a = lane_addr + (static_cast<uint32_t>(16 * h) << 16) + cbase;
+                    tmem_ld_16x256b_x1(a, sv);
+                    if (kTeacher) tmem_ld_16x256b_x1(a + 128, tv);
+                    tmem_ld_wait();
+                    if (pc == 3 && h == 1) {                 // last TMEM read of this tile: release the accumulator stage
+                        tc_fence_before_sync();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive_cluster(l_tempty + 8 * as);
+                    }
+#pragma unroll
+                    for (int rr = 0; rr < 2; ++rr) {
+                        const int ri = 2 * h + rr;
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            const float s = sv[2 * rr + e] * cs[e] * r_s[ri];      // S_ij
+                            float e1 = ex2(fmaf(s, k1, n1));                        // exp(S - 1)
+                            float et = 0.f, f = 0.f, qv = 0.f, xr = 0.f, xm = 0.f, cnt = 0.f;
+                            float tl = 0.f;
+                            if (kTeacher) {
+                                tl = tv[2 * rr + e] * ct[e] * r_t[ri];              // T_ij
+                                const float es = ex2(fmaf(s, k1t, n1t));
+                                et = ex2(fmaf(tl, k1t, n1t));
+                                const float d = tl - s;
+                                f = et * d;
+                                qv = fmaf(f, p.inv_temp, es - et);
+                                if constexpr (kExtra) {
+                                    xr = fmaxf(-d, 0.f);
+                                    xm = d * d;
+                                }
+                            } else if (ranking) {
+                                cnt = s > rank_ref[ri] ? 1.f : 0.f;       // same expression as the diagonal: S_ii compares equal to itself
+                            }
+                            if constexpr (kEdge) {
+                                const int gc = col0 + cbase + 2 * m + e;
+                                const int grow_i = row0 + q * 32 + 16 * h + 8 * rr + g;
+                                const bool ok = gc < p.cols && rok[ri];
+                                if (ok && gc == p.row_offset + grow_i) {
+                                    p.diag[grow_i] = s;
+                                    if constexpr (kExtra) p.diag_t[grow_i] = tl;
+                                }
+                                if (ok && p.dump_s) p.dump_s[(size_t)grow_i * p.cols + gc] = s;
+                                if (kTeacher && ok && p.dump_t) p.dump_t[(size_t)grow_i * p.cols + gc] = tl;
+                                if (!ok) e1 = et = f = qv = xr = xm = cnt = 0.f;
+                            }
+                            rowp[ri][0] += e1;
+                            colacc[0][e] += e1;
+                            if (kTeacher) {
+                                rowp[ri][1] += qv;
+                                rowp[ri][2] += et;
+                                rowp[ri][3] += f;
+                                if constexpr (kExtra) {
+                                    rowp[ri][4] += xr;
+                                    rowp[ri][5] += xm;
+                                }
+                                if constexpr (NC == 4) {
+                                    colacc[1][e] += qv;
+                                    colacc[2][e] += et;
+                                    colacc[3][e] += f;
+                                }
+                            } else {
+                                rowp[ri][1] += cnt;
                             }
                         }
-                        if (edge) {
-#pragma unroll
-                            for (int c = 0; c < 16; ++c)
-                                if (!(col0 + cbase + c < p.cols && row_ok)) { e[c] = 0.f; tv[c] = 0.f; f[c] = 0.f; }
-                        }
-                        // ---- Q = sum (es - et) + f/T,  Zt = sum et,  W = sum f
-#pragma unroll
-                        for (int c = 0; c < 16; ++c) {
-                            e[c] = fmaf(f[c], p.inv_temp, e[c] - tv[c]);
-                            q_sum += e[c];
-                            zt_sum += tv[c];
-                            w_sum += f[c];
-                        }
-                        if (kCols) {
-                            column_sums16(e, lane);
-                            if (!(lane & 1)) cb[1 * kBN + cbase + (lane >> 1)] = e[0];
-                            column_sums16(tv, lane);
-                            if (!(lane & 1)) cb[2 * kBN + cbase + (lane >> 1)] = tv[0];
-                            column_sums16(f, lane);
-                            if (!(lane & 1)) cb[3 * kBN + cbase + (lane >> 1)] = f[0];
-                        }
                     }
                 }
-                kahan(A, cA, a_sum);
-                if (kTeacher) {
-                    kahan(Q, cQ, q_sum);
-                    kahan(Zt, cZt, zt_sum);
-                    kahan(W, cW, w_sum);
-                    if constexpr (kExtra) {
-                        kahan(XR, cXR, xr_sum);
-                        kahan(XM, cXM, xm_sum);
+                if (kCols) {
+                    // sum over the 8 lane groups g (lane bits 4, 3, 2): one halving step, then two plain exchanges.  Afterwards
+                    // lane holds the total of column cbase + 2 m + (lane >> 4 & 1).
+                    const bool up16 = lane & 16;
+#pragma unroll
+                    for (int k = 0; k < NC; ++k) {
+                        const float keep = up16 ? colacc[k][1] : colacc[k][0];
+                        const float send = up16 ? colacc[k][0] : colacc[k][1];
+                        float w = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+                        w += __shfl_xor_sync(0xffffffffu, w, 8);
+                        w += __shfl_xor_sync(0xffffffffu, w, 4);
+                        if (!(lane & 12)) cb[k * kBN + cbase + 2 * m + ((lane >> 4) & 1)] = w;
                     }
+                }
+            };
+            if (edge) {
+#pragma unroll 1
+                for (int pc = 0; pc < 4; ++pc) piece(pc, std::true_type{});
+            } else {
+#pragma unroll 1
+                for (int pc = 0; pc < 4; ++pc) piece(pc, std::false_type{});
+            }
+            // row sums of this tile quarter: halving over the 4 lanes of a group (lane bits 0, 1); lane m ends with row index m
+            {
+                const bool up1 = lane & 1, up2 = lane & 2;
+#pragma unroll
+                for (int k = 0; k < NR; ++k) {
+                    float v[2];
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const float keep = up1 ? rowp[2 * h + 1][k] : rowp[2 * h][k];
+                        const float send = up1 ? rowp[2 * h][k] : rowp[2 * h + 1][k];
+                        v[h] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+                    }
+                    const float keep = up2 ? v[1] : v[0];
+                    const float send = up2 ? v[0] : v[1];
+                    kahan(tot[k], comp[k], keep + __shfl_xor_sync(0xffffffffu, send, 2));
                 }
             }
         }
@@ -379,16 +406,14 @@ clip_fwd_kernel(const __grid_constant__ CUtensorMap map_a_stu, const __grid_cons
         }
         if (row_ok) {
             float* w = p.ws + (size_t)(sp * kSubs + sub) * 4 * p.rows + grow;
-            w[0] = A;
-            w[(size_t)p.rows] = (!kTeacher && !kCols && p.rank_ref) ? (float)n_greater : Q;
-            w[(size_t)2 * p.rows] = Zt;
-            w[(size_t)3 * p.rows] = W;
-            if (have_diag) p.diag[grow] = diag;
+            w[0] = tot[0];
+            w[(size_t)p.rows] = tot[1];                      // Q, or the rank count of the ranking instantiation
+            w[(size_t)2 * p.rows] = kTeacher ? tot[kTeacher ? 2 : 0] : 0.f;
+            w[(size_t)3 * p.rows] = kTeacher ? tot[kTeacher ? 3 : 0] : 0.f;
             if constexpr (kExtra) {
                 float* x = p.ws_extra + (size_t)(sp * kSubs + sub) * 2 * p.rows + grow;
-                x[0] = XR;
-                x[(size_t)p.rows] = XM;
-                if (have_diag) p.diag_t[grow] = diag_tv;
+                x[0] = tot[4];
+                x[(size_t)p.rows] = tot[5];
             }
         }
     }

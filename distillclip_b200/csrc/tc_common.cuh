@@ -145,6 +145,24 @@ __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, float (&v)[16]) {
         : "r"(taddr)
         : "memory");
 }
+// 16 lanes x 16 consecutive fp32 columns in the mma fragment layout: thread t = 4 g + m receives, in register 4 rep + 2 rr + e,
+// lane (base lane + 8 rr + g), column 8 rep + 2 m + e  (verified on B200: scripts/probe/tmem_layout_probe.cu)
+__device__ __forceinline__ void tmem_ld_16x256b_x2(uint32_t taddr, float (&v)[8]) {
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.16x256b.x2.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+        : "r"(taddr)
+        : "memory");
+}
+// 16 lanes x 8 columns: register 2 rr + e <-> lane (base lane + 8 rr + g), column 2 m + e
+__device__ __forceinline__ void tmem_ld_16x256b_x1(uint32_t taddr, float (&v)[4]) {
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile("tcgen05.ld.sync.aligned.16x256b.x1.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+                 : "r"(taddr)
+                 : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ------------------------------------------------------------------------------------------
