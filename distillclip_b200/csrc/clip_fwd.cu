@@ -205,7 +205,9 @@ clip_fwd_kernel(const __grid_constant__ CUtensorMap map_a_stu, const __grid_cons
         constexpr int NR = kTeacher ? (kExtra ? 6 : 4) : 2; // row sums carried per row: A, Q (or the rank count), Zt, W, relu(S-T), (S-T)^2
         constexpr int NC = kTeacher ? 4 : 1;                // column sums
         const float LOG2E = 1.4426950408889634f;
-        const float k1 = LOG2E, n1 = -LOG2E, k1t = LOG2E * p.inv_temp, n1t = -LOG2E * p.inv_temp;
+        const float k1 = LOG2E, n1 = -LOG2E;
+        const float2 k1t2 = make_float2(LOG2E * p.inv_temp, LOG2E * p.inv_temp), n1t2 = make_float2(-LOG2E * p.inv_temp, -LOG2E * p.inv_temp);
+        const float2 neg2 = make_float2(-1.f, -1.f), invt2 = make_float2(p.inv_temp, p.inv_temp);
         const bool ranking = !kTeacher && !kCols && p.rank_ref != nullptr;
         // the four rows this thread computes on (index 2 h + rr)
         float r_s[4], r_t[4], rank_ref[4];
@@ -278,20 +280,11 @@ clip_fwd_kernel(const __grid_constant__ CUtensorMap map_a_stu, const __grid_cons
             auto piece = [&](int pc, auto edge_tag) {
                 constexpr bool kEdge = decltype(edge_tag)::value;
                 const int cbase = sub * 32 + pc * 8;
-                float cs[2], ct[2];
-                {
-                    const float2 a = *reinterpret_cast<const float2*>(sc + cbase + 2 * m);
-                    cs[0] = a.x;
-                    cs[1] = a.y;
-                    if (kTeacher) {
-                        const float2 b = *reinterpret_cast<const float2*>(sc + kBN + cbase + 2 * m);
-                        ct[0] = b.x;
-                        ct[1] = b.y;
-                    }
-                }
-                float colacc[NC][2];                        // sums over this thread's four rows, per statistic and column
+                const float2 cs2 = *reinterpret_cast<const float2*>(sc + cbase + 2 * m);
+                const float2 ct2 = kTeacher ? *reinterpret_cast<const float2*>(sc + kBN + cbase + 2 * m) : make_float2(0.f, 0.f);
+                float2 colacc[NC];                          // sums over this thread's four rows, per statistic and column
 #pragma unroll
-                for (int k = 0; k < NC; ++k) colacc[k][0] = colacc[k][1] = 0.f;
+                for (int k = 0; k < NC; ++k) colacc[k] = make_float2(0.f, 0.f);
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     float sv[4], tv[4];                      // register 2 rr + e
@@ -306,57 +299,65 @@ clip_fwd_kernel(const __grid_constant__ CUtensorMap map_a_stu, const __grid_cons
                     }
 #pragma unroll
                     for (int rr = 0; rr < 2; ++rr) {
+                        // the two columns of a row go through packed fp32x2 arithmetic (FMUL2 / FFMA2 / FADD2: half the issue slots)
                         const int ri = 2 * h + rr;
-#pragma unroll
-                        for (int e = 0; e < 2; ++e) {
-                            const float s = sv[2 * rr + e] * cs[e] * r_s[ri];      // S_ij
-                            float e1 = ex2(fmaf(s, k1, n1));                        // exp(S - 1)
-                            float et = 0.f, f = 0.f, qv = 0.f, xr = 0.f, xm = 0.f, cnt = 0.f;
-                            float tl = 0.f;
-                            if (kTeacher) {
-                                tl = tv[2 * rr + e] * ct[e] * r_t[ri];              // T_ij
-                                const float es = ex2(fmaf(s, k1t, n1t));
-                                et = ex2(fmaf(tl, k1t, n1t));
-                                const float d = tl - s;
-                                f = et * d;
-                                qv = fmaf(f, p.inv_temp, es - et);
-                                if constexpr (kExtra) {
-                                    xr = fmaxf(-d, 0.f);
-                                    xm = d * d;
-                                }
-                            } else if (ranking) {
-                                cnt = s > rank_ref[ri] ? 1.f : 0.f;       // same expression as the diagonal: S_ii compares equal to itself
+                        const float2 u2 = __fmul2_rn(make_float2(sv[2 * rr], sv[2 * rr + 1]), cs2);
+                        const float2 s2 = make_float2(u2.x * r_s[ri], u2.y * r_s[ri]);                  // S_ij
+                        float2 e1 = make_float2(ex2(fmaf(s2.x, k1, n1)), ex2(fmaf(s2.y, k1, n1)));      // exp(S - 1)
+                        float2 et = make_float2(0.f, 0.f), f = et, qv = et, xr = et, xm = et, cnt = et, tl2 = et;
+                        if (kTeacher) {
+                            const float2 v2 = __fmul2_rn(make_float2(tv[2 * rr], tv[2 * rr + 1]), ct2);
+                            tl2 = make_float2(v2.x * r_t[ri], v2.y * r_t[ri]);                          // T_ij
+                            const float2 as2 = __ffma2_rn(s2, k1t2, n1t2), at2 = __ffma2_rn(tl2, k1t2, n1t2);
+                            const float2 es = make_float2(ex2(as2.x), ex2(as2.y));
+                            et = make_float2(ex2(at2.x), ex2(at2.y));
+                            const float2 d = __ffma2_rn(s2, neg2, tl2);                                 // T - S
+                            f = __fmul2_rn(et, d);
+                            qv = __ffma2_rn(f, invt2, __ffma2_rn(et, neg2, es));                        // es - et + f / T
+                            if constexpr (kExtra) {
+                                xr = make_float2(fmaxf(-d.x, 0.f), fmaxf(-d.y, 0.f));
+                                xm = __fmul2_rn(d, d);
                             }
-                            if constexpr (kEdge) {
+                        } else if (ranking) {
+                            // same expression as the diagonal: S_ii compares equal to itself
+                            cnt = make_float2(s2.x > rank_ref[ri] ? 1.f : 0.f, s2.y > rank_ref[ri] ? 1.f : 0.f);
+                        }
+                        if constexpr (kEdge) {
+                            const int grow_i = row0 + q * 32 + 16 * h + 8 * rr + g;
+#pragma unroll
+                            for (int e = 0; e < 2; ++e) {
                                 const int gc = col0 + cbase + 2 * m + e;
-                                const int grow_i = row0 + q * 32 + 16 * h + 8 * rr + g;
                                 const bool ok = gc < p.cols && rok[ri];
+                                const float s = e ? s2.y : s2.x, tl = e ? tl2.y : tl2.x;
                                 if (ok && gc == p.row_offset + grow_i) {
                                     p.diag[grow_i] = s;
                                     if constexpr (kExtra) p.diag_t[grow_i] = tl;
                                 }
                                 if (ok && p.dump_s) p.dump_s[(size_t)grow_i * p.cols + gc] = s;
                                 if (kTeacher && ok && p.dump_t) p.dump_t[(size_t)grow_i * p.cols + gc] = tl;
-                                if (!ok) e1 = et = f = qv = xr = xm = cnt = 0.f;
-                            }
-                            rowp[ri][0] += e1;
-                            colacc[0][e] += e1;
-                            if (kTeacher) {
-                                rowp[ri][1] += qv;
-                                rowp[ri][2] += et;
-                                rowp[ri][3] += f;
-                                if constexpr (kExtra) {
-                                    rowp[ri][4] += xr;
-                                    rowp[ri][5] += xm;
+                                if (!ok) {
+                                    if (e) e1.y = et.y = f.y = qv.y = xr.y = xm.y = cnt.y = 0.f;
+                                    else e1.x = et.x = f.x = qv.x = xr.x = xm.x = cnt.x = 0.f;
                                 }
-                                if constexpr (NC == 4) {
-                                    colacc[1][e] += qv;
-                                    colacc[2][e] += et;
-                                    colacc[3][e] += f;
-                                }
-                            } else {
-                                rowp[ri][1] += cnt;
                             }
+                        }
+                        rowp[ri][0] += e1.x + e1.y;
+                        colacc[0] = __fadd2_rn(colacc[0], e1);
+                        if (kTeacher) {
+                            rowp[ri][1] += qv.x + qv.y;
+                            rowp[ri][2] += et.x + et.y;
+                            rowp[ri][3] += f.x + f.y;
+                            if constexpr (kExtra) {
+                                rowp[ri][4] += xr.x + xr.y;
+                                rowp[ri][5] += xm.x + xm.y;
+                            }
+                            if constexpr (NC == 4) {
+                                colacc[1] = __fadd2_rn(colacc[1], qv);
+                                colacc[2] = __fadd2_rn(colacc[2], et);
+                                colacc[3] = __fadd2_rn(colacc[3], f);
+                            }
+                        } else {
+                            rowp[ri][1] += cnt.x + cnt.y;
                         }
                     }
                 }
@@ -366,8 +367,8 @@ clip_fwd_kernel(const __grid_constant__ CUtensorMap map_a_stu, const __grid_cons
                     const bool up16 = lane & 16;
 #pragma unroll
                     for (int k = 0; k < NC; ++k) {
-                        const float keep = up16 ? colacc[k][1] : colacc[k][0];
-                        const float send = up16 ? colacc[k][0] : colacc[k][1];
+                        const float keep = up16 ? colacc[k].y : colacc[k].x;
+                        const float send = up16 ? colacc[k].x : colacc[k].y;
                         float w = keep + __shfl_xor_sync(0xffffffffu, send, 16);
                         w += __shfl_xor_sync(0xffffffffu, w, 8);
                         w += __shfl_xor_sync(0xffffffffu, w, 4);

@@ -37,6 +37,8 @@ __device__ __forceinline__ void cluster_sync() { asm volatile("barrier.cluster.a
 
 struct P {
     int stages, stage_bytes, boxes_per_stage, box_rows, iters, producers, multicast, k_chunks, rows_total, three_d, hold;
+    int lsu_bytes;            // extra bytes per stage fetched by a cp.async (LDGSTS) warp next to the TMA boxes (0 = off)
+    const uint8_t* src;
     long long* clocks;
 };
 
@@ -45,13 +47,15 @@ __global__ void __launch_bounds__(192, 1) probe(const __grid_constant__ CUtensor
     extern __shared__ uint8_t raw[];
     const uint32_t base = (smem_u32(raw) + 1023u) & ~1023u;
     uint64_t* bars = reinterpret_cast<uint64_t*>(raw + (base - smem_u32(raw)) + p.stages * p.stage_bytes);
-    const uint32_t full = smem_u32(bars), empty = full + 8 * p.stages;
+    const uint32_t full = smem_u32(bars), empty = full + 8 * p.stages, lfull = empty + 8 * p.stages;
+    const int tma_bytes = p.stage_bytes - p.lsu_bytes;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = p.multicast ? cluster_rank() : 0;
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.stages; ++s) {
             mbar_init(full + 8 * s, p.producers);
             mbar_init(empty + 8 * s, p.multicast ? 2 : 1);
+            mbar_init(lfull + 8 * s, 32);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -84,12 +88,32 @@ __global__ void __launch_bounds__(192, 1) probe(const __grid_constant__ CUtensor
             }
             if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
+    } else if (warp == 4 && p.lsu_bytes > 0) {
+        // second ingest path: one warp, 16 bytes per lane per cp.async, 128-byte rows (8 lanes per row), completion through
+        // cp.async.mbarrier.arrive.noinc on a barrier of its own
+        int stage = 0;
+        uint32_t phase = 0;
+        const int rows = p.lsu_bytes / 128;
+        for (int it = 0; it < p.iters; ++it) {
+            mbar_wait(empty + 8 * stage, phase ^ 1);
+            const uint32_t dst = base + stage * p.stage_bytes + tma_bytes;
+            const unsigned row0 = ((unsigned)(blockIdx.x * 131 + it) * (unsigned)rows) & (unsigned)(p.rows_total - 1);
+            const int kx = ((it + 3) & 7) * 128;
+            for (int r = lane >> 3; r < rows; r += 4) {
+                const uint8_t* g = p.src + (size_t)(row0 + r) * 1536 + kx + (lane & 7) * 16;
+                const uint32_t d = dst + r * 128 + (((lane & 7) ^ (r & 7)) << 4);
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(g) : "memory");
+            }
+            asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(lfull + 8 * stage) : "memory");
+            if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
     } else if (warp == 5 && lane == 0) {
         long long last = 0;
         int stage = 0;
         uint32_t phase = 0;
         for (int it = 0; it < p.iters; ++it) {
             mbar_wait(full + 8 * stage, phase);
+            if (p.lsu_bytes > 0) mbar_wait(lfull + 8 * stage, phase);
             if (p.hold) {                       // emulate an in-order consumer that needs `hold` clocks per stage
                 const long long until = (it == 0 ? clock64() : last) + p.hold;
                 while (clock64() < until) {}
@@ -124,7 +148,7 @@ int main() {
     CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fp, cudaEnableDefault, &q));
     EncodeFn encode = (EncodeFn)fp;
     CK(cudaFuncSetAttribute(probe, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-    struct Case { const char* name; int stages, boxes, box_rows, producers, multicast, swizzle, ctas, three_d, hold; };
+    struct Case { const char* name; int stages, boxes, box_rows, producers, multicast, swizzle, ctas, three_d, hold, lsu; };
     const Case cases[] = {
         {"8K boxes x4, 6 stages (as the kernels)", 6, 4, 64, 1, 0, 1, 148},
         {"same, 16 CTAs only", 6, 4, 64, 1, 0, 1, 16},
@@ -146,6 +170,10 @@ int main() {
         {"8K x4, 6 stages, consumer holds 272 clk/stage", 6, 4, 64, 1, 0, 1, 148, 0, 272},
         {"16K x2, 6 stages, consumer holds 272 clk/stage", 6, 2, 128, 1, 0, 1, 148, 0, 272},
         {"8K x4, 6 stages, consumer holds 400 clk/stage", 6, 4, 64, 1, 0, 1, 148, 0, 400},
+        {"16K x2 by TMA + 16K by a cp.async warp (48K stages), 4 stages", 4, 2, 128, 1, 0, 1, 148, 0, 0, 16384},
+        {"16K x2 by TMA + 8K by a cp.async warp (40K stages), 4 stages", 4, 2, 128, 1, 0, 1, 148, 0, 0, 8192},
+        {"16K x2 by TMA alone (32K stages), 4 stages", 4, 2, 128, 1, 0, 1, 148, 0, 0, 0},
+        {"16K x1 by TMA + 16K by a cp.async warp (32K stages), 6 stages", 6, 1, 128, 1, 0, 1, 148, 0, 0, 16384},
         {"multicast pair: each CTA issues 2 of 4 boxes", 6, 4, 64, 1, 1, 1, 148},
         {"multicast pair, 16 CTAs only", 6, 4, 64, 1, 1, 1, 16},
         {"multicast pair, 16K boxes", 6, 2, 128, 1, 1, 1, 148},
@@ -164,7 +192,9 @@ int main() {
         p.stages = c.stages;
         p.boxes_per_stage = c.boxes;
         p.box_rows = c.box_rows;
-        p.stage_bytes = c.boxes * c.box_rows * 128 * (c.three_d ? 2 : 1);
+        p.stage_bytes = c.boxes * c.box_rows * 128 * (c.three_d ? 2 : 1) + c.lsu;
+        p.lsu_bytes = c.lsu;
+        p.src = static_cast<const uint8_t*>(buf);
         p.three_d = c.three_d;
         p.hold = c.hold;
         p.iters = 2000;
@@ -173,7 +203,7 @@ int main() {
         p.k_chunks = cols / 64;
         p.rows_total = rows_total;
         p.clocks = clocks;
-        const int smem = 1024 + p.stages * p.stage_bytes + 16 * p.stages + 64;
+        const int smem = 1024 + p.stages * p.stage_bytes + 24 * p.stages + 64;
         cudaLaunchConfig_t cfg{};
         cfg.gridDim = dim3(c.ctas);
         cfg.blockDim = dim3(192);
