@@ -269,9 +269,10 @@ class CudaEngine:
 
     #: split backward (csrc/clip_bwd_g.cu): recompute -> fp16 G tiles, then one tcgen05 GEMM per tower over the stored tiles,
     #: instead of the pair kernel that fuses the image-side GEMM into the recompute.  "auto": when the local block of the
-    #: logit matrix has at least `split_min_tiles` 128 x 128 tiles (below that the extra launch costs more than it saves)
+    #: logit matrix has at least `split_min_tiles` 128 x 128 tiles (measured: 4 % faster at 4096 x 4096 x 512 already; below that the
+    #: fused kernel saves a launch)
     split_backward = os.environ.get("DCB_BWD_SPLIT", "auto")
-    split_min_tiles = int(os.environ.get("DCB_BWD_SPLIT_MIN_TILES", "4096"))
+    split_min_tiles = int(os.environ.get("DCB_BWD_SPLIT_MIN_TILES", "1024"))
 
     def use_split(self, rows: int, cols: int) -> bool:
         if self.split_backward in ("0", "1"):

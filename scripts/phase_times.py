@@ -39,7 +39,7 @@ def timed(name, fn):
 
 eng = ct._ENGINE
 xc = pl.exchange_for(group)
-for m in ("prep", "fwd_chunk", "post1", "post2", "pair_bwd", "col_acc_from_g", "col_acc_scatter", "finish2"):
+for m in ("prep", "fwd_chunk", "post1", "post2", "pair_bwd", "g_tiles", "row_acc_from_g", "col_acc_from_g", "col_acc_scatter", "finish2"):
     setattr(eng, m, timed(m, getattr(eng, m)))
 for m in ("start_gather", "exchange_slots", "after_scatter", "wait_all"):
     if hasattr(xc, m):
