@@ -14,4 +14,6 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --c
 echo "launch list exit $?"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:"clip_fwd_kernel|clip_bwd_pair_kernel|clip_g_tiles_kernel|clip_gt_gemm_kernel|clip_post|clip_prep|clip_finish2" -c 8 -o $OUT/${TAG}_prof_sweep -f $CMD > $OUT/${TAG}_ncu_full.log 2>&1
 echo "ncu full exit $?"
+# the reports are large (gpurun brings back at most 64 MiB): extract the counters here and keep only the CSV
+python scripts/ncu_extract.py $OUT/${TAG}_prof_sweep.ncu-rep $OUT/${TAG}_ncu_full_clip_sweep.csv && rm -f $OUT/${TAG}_prof_sweep.ncu-rep
 tail -c 600 $OUT/${TAG}_bench_n1.err

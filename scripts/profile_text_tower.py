@@ -1,4 +1,5 @@
-"""Text-stage tower launch for ncu: 2 launches with per-thread loads (1 group per thread), then 2 with aligned vectors."""
+"""Tower launch for ncu (text stage by default): 2 launches with the default tile (2 position groups per thread for 2-byte
+loads), 2 with one group per thread, 2 with aligned 16-byte vectors."""
 import os
 import sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -13,7 +14,7 @@ entries = [(ops.KIND_ATTN_KL, 4, stu["attention_probs"], tea["attention_probs"],
 if "embedding" in stu:
     entries.append((ops.KIND_MSE, 1, [stu["embedding"]], [tea["embedding"]], [True], 1.0))
 w = [1.0] * len(entries)
-for env in ({"DCB_ATTN_GPT": "1"}, {"DCB_ATTN_STAGED": "1"}):
+for env in ({}, {"DCB_ATTN_GPT": "1"}, {"DCB_ATTN_ALIGNED": "1"}):
     for k in ("DCB_ATTN_NO_ALIGNED", "DCB_ATTN_GPT", "DCB_ATTN_ALIGNED", "DCB_ATTN_STAGED"):
         os.environ.pop(k, None)
     os.environ.update(env)
