@@ -196,6 +196,9 @@ class CudaEngine:
     tr_dtype = torch.float16
     _scratch: Dict = {}
 
+    def rg_splits(self, rows, cols, dim):
+        return _lib.load().dcb_clip_rg_splits(rows, cols, dim)
+
     def gt_splits(self, rows, cols, dim, scatter=False):
         lib = _lib.load()
         return lib.dcb_clip_gt_splits_scatter(rows, cols, dim) if scatter else lib.dcb_clip_gt_splits(rows, cols, dim)
@@ -288,10 +291,12 @@ class CudaEngine:
                   _vp(coef_row), _vp(coef_col), _vp(bounds), g5, w8, int(bool(extra)), int(row_offset), cols, rows, cols, dim,
                   ops.dtype_code(a_s), float(temperature or 1.0), _vp(g_out), g_out.shape[1], ops._stream_ptr())
 
-    def row_acc_from_g(self, g, bt_all, rows: int, cols: int, dim: int):
-        """acc[s, i, :] = sum_{j in split s} G[i, j] 2^k b_hat[j, :]  -- tcgen05 GEMM with A = G read K-major."""
+    def row_acc_from_g(self, g, bt_all, rows: int, cols: int, dim: int, out=None):
+        """acc[s, i, :] = sum_{j in split s} G[i, j] 2^k b_hat[j, :]  -- tcgen05 GEMM with A = G read K-major.  `out`: the
+        accumulator allocated by the caller (on the stream that will consume it) when this launch goes to a side stream."""
         n_split = _lib.load().dcb_clip_rg_splits(rows, cols, dim)
-        acc = torch.empty(n_split, rows, dim, dtype=torch.float32, device=g.device)
+        acc = out if out is not None else torch.empty(n_split, rows, dim, dtype=torch.float32, device=g.device)
+        assert acc.shape == (n_split, rows, dim)
         _lib.call("dcb_clip_row_grads_from_g", _vp(g), g.shape[1], _vp(bt_all), bt_all.stride(1), cols // bt_all.shape[0],
                   rows, cols, dim, _vp(acc), ops._stream_ptr())
         return acc

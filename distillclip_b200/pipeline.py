@@ -575,6 +575,22 @@ def _upstream(v, ups):
     return (g5, (p_h * s_h, p_s * s_s, s_h, s_s, p_c * s_c, p_m * s_m, s_c, s_m))
 
 
+_SIDE: Dict = {}
+GEMM_OVERLAP = os.environ.get("DCB_GEMM_OVERLAP", "1") != "0"
+
+
+def _gemm_side_streams(xc, x):
+    """-> [side stream] for the second gradient GEMM of the split backward, or None (CPU engine double, DCB_GEMM_OVERLAP=0)."""
+    if not GEMM_OVERLAP or not x.is_cuda:
+        return None
+    if xc.world > 1:
+        return xc.tile_streams()
+    key = x.device.index
+    if key not in _SIDE:
+        _SIDE[key] = [torch.cuda.Stream(device=x.device)]
+    return _SIDE[key]
+
+
 def backward_gemms(engine, v, ups, want_txt=True):
     """Backward stage 1: pair kernel (recompute once; image-side accumulators; fp16 gradient tiles) and the G^T GEMM, whose
     epilogue scatters every text row's partial sums into its owner's buffer when peer memory is available."""
@@ -604,8 +620,25 @@ def backward_gemms(engine, v, ups, want_txt=True):
         engine.g_tiles(si, s.st_all, v["ti"], s.tt_all, v["si_inv"], s.st_inv_all, v["ti_inv"], s.tt_inv_all, v["coef_row"],
                        v["coef_col"], v["bounds"], _upstream(v, ups), v["temperature"], g, extra=v["extra"],
                        row_offset=xc.rank * b_local)
-        text_side()
-        v["acc_a"] = engine.row_acc_from_g(g, s.bt_all, b_local, b, dim)
+        streams = _gemm_side_streams(xc, si) if want_txt else None
+        if streams:
+            # the two GEMMs are independent: the image-side one runs beside the text-side one on a side stream and fills the SMs
+            # its partial last wave leaves idle -- and, sharded, its store phases (the scattering GEMM is bound by its NVLink
+            # stores at small K = B / R rows per rank): 4.78 -> 4.53 ms per step on 2 GPUs
+            main = torch.cuda.current_stream()
+            v["acc_a"] = torch.empty(engine.rg_splits(b_local, b, dim), b_local, dim, dtype=engine.stat_dtype, device=si.device)
+            fork = torch.cuda.Event()
+            fork.record(main)
+            text_side()
+            with torch.cuda.stream(streams[0]):
+                streams[0].wait_event(fork)
+                engine.row_acc_from_g(g, s.bt_all, b_local, b, dim, out=v["acc_a"])
+                v["side_done"] = torch.cuda.Event()
+                v["side_done"].record(streams[0])
+            v["g_scratch"] = g                # read on the side stream: keep it until the streams have joined (backward_finish)
+        else:
+            text_side()
+            v["acc_a"] = engine.row_acc_from_g(g, s.bt_all, b_local, b, dim)
     else:
         v["acc_a"] = engine.pair_bwd(si, s.st_all, v["ti"], s.tt_all, s.bt_all, v["si_inv"], s.st_inv_all, v["ti_inv"], s.tt_inv_all,
                                      v["coef_row"], v["coef_col"], v["bounds"], _upstream(v, ups), v["temperature"], g,
@@ -620,6 +653,8 @@ def backward_finish(engine, v, ups, want_img=True, want_txt=True, grad_dtype=Non
     b_local = si.shape[0]
     loc = slice(xc.rank * b_local, (xc.rank + 1) * b_local)
     acc_b = v["acc_b"]
+    if v.get("side_done") is not None:
+        torch.cuda.current_stream().wait_event(v.pop("side_done"))
     if v["scattered"]:
         xc.after_scatter(s)
         acc_b = s.gt_parts
@@ -632,6 +667,7 @@ def backward_finish(engine, v, ups, want_img=True, want_txt=True, grad_dtype=Non
     xc.release(s)
     v["released"] = True
     v["acc_a"] = v["acc_b"] = None
+    v.pop("g_scratch", None)
     return g_img, g_txt
 
 
