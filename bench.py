@@ -659,7 +659,7 @@ def bench_clip(cfg, name, args, device, dist, rank, world, pk, steps, warmup):
     host = [x.detach().cpu().pin_memory() for x in (si, st, ti, tt)]
     loss_host = torch.empty((), dtype=torch.float32).pin_memory()
 
-    def e2e_step():
+    def e2e_serial():
         a, c_, e, f = [h.to(device, non_blocking=True) for h in host]
         a.requires_grad_(True)
         c_.requires_grad_(True)
@@ -668,10 +668,48 @@ def bench_clip(cfg, name, args, device, dist, rank, world, pk, steps, warmup):
         loss.backward()
         loss_host.copy_(loss.detach(), non_blocking=True)
         torch.cuda.current_stream().synchronize()
-    n_e2e = max(3, steps // 4)
-    e2e_ms = Timer(device, flush=False).run(e2e_step, n_e2e, 2, dist, graph=False) / n_e2e
+
+    # the same loop the way an input pipeline feeds a training step: the pinned inputs of step i+1 are copied on a side stream
+    # while step i computes (two device buffer sets, prefetch depth 1).  Every step's copies and its loss read-back are inside
+    # the timed region; a step waits for ITS copies before it starts.
+    copy_stream = torch.cuda.Stream()
+    dev_bufs = [[torch.empty(h.shape, dtype=h.dtype, device=device) for h in host] for _ in range(2)]
+    ready = [torch.cuda.Event() for _ in range(2)]
+    state = {"i": 0}
+
+    def prefetch(slot):
+        with torch.cuda.stream(copy_stream):
+            for h, dbuf in zip(host, dev_bufs[slot]):
+                dbuf.copy_(h, non_blocking=True)
+            ready[slot].record(copy_stream)
+
+    def e2e_step():
+        slot = state["i"] & 1
+        state["i"] += 1
+        main = torch.cuda.current_stream()
+        copy_stream.wait_stream(main)            # the step that last used the other buffer set has been enqueued before this point
+        prefetch(slot ^ 1)
+        main.wait_event(ready[slot])
+        a, c_, e, f = dev_bufs[slot]
+        a = a.detach().requires_grad_(True)
+        c_ = c_.detach().requires_grad_(True)
+        res = clip_contrastive(a, c_, e, f, T, want_hard=True, want_soft=True, group=group, percent=(0.5, 0.5))
+        loss = res["total"]
+        loss.backward()
+        loss_host.copy_(loss.detach(), non_blocking=True)
+        main.synchronize()
+    n_serial = max(3, steps // 4)
+    serial_ms = Timer(device, flush=False).run(e2e_serial, n_serial, 2, dist, graph=False) / n_serial
+    torch.cuda.synchronize()
+    prefetch(0)
+    n_e2e = steps                                # as many steps as the device-timed loop: same sustained-clock regime
+    e2e_ms = Timer(device, flush=False).run(e2e_step, n_e2e, 3, dist, graph=False) / n_e2e
+    torch.cuda.synchronize()
     e2e = {"value": round(b / (e2e_ms * 1e-3), 1), "unit": "samples/s", "ms_per_step": round(e2e_ms, 4),
-           "h2d_bytes_per_step": sum(h.numel() * 2 for h in host) * world, "d2h_bytes_per_step": 4 * world}
+           "h2d_bytes_per_step": sum(h.numel() * 2 for h in host) * world, "d2h_bytes_per_step": 4 * world,
+           "pipelining": "inputs of step i+1 copied from pinned memory on a side stream while step i computes (prefetch depth 1); "
+                         "every step's H2D copies and loss read-back are inside the timed region",
+           "serial_ms_per_step": round(serial_ms, 4)}
     dom = max(kres, key=lambda k: kres[k]["ms"])
     traffic = first_traffic([f"{PROFILE_ROUND}_ncu_full_clip_{name}.csv", f"r01_ncu_full_clip_{name}.csv"], dom.split("<")[0]) if world == 1 else None
     roofline = {"bound": "tensor", "kernel": dom, "achieved": kres[dom]["tflops"], "peak": pk["tf_burst"], "unit": "TFLOP/s",
