@@ -231,6 +231,31 @@ class DoubleEngine:
         gmax = torch.as_tensor(gmax, dtype=torch.float64)
         return 2.0 ** (14 - torch.frexp(gmax)[1].item()) if float(gmax) > 0 else 1.0
 
+    #: True: pipeline.backward_gemms takes the split flow (g_tiles -> text-side GEMM -> image-side GEMM) with this double too
+    split = False
+
+    def use_split(self, rows, cols):
+        return self.split
+
+    def rg_splits(self, rows, cols, dim):
+        return 1
+
+    def g_tiles(self, a_s, b_s, a_t, b_t, a_s_inv, b_s_inv, a_t_inv, b_t_inv, coef_row, coef_col, bounds, up, temperature,
+                g_out, extra=False, row_offset=0):
+        """The recompute kernel of the split backward: only the scaled gradient tiles."""
+        dummy_bt = torch.zeros(1, a_s.shape[1], b_s.shape[0], dtype=torch.float64)
+        self.pair_bwd(a_s, b_s, a_t, b_t, dummy_bt, a_s_inv, b_s_inv, a_t_inv, b_t_inv, coef_row, coef_col, bounds, up,
+                      temperature, g_out, extra=extra, row_offset=row_offset)
+
+    def row_acc_from_g(self, g, bt_all, rows, cols, dim, out=None):
+        n = cols // bt_all.shape[0]
+        b_hat_t = torch.cat([bt_all[r][:, :n] for r in range(bt_all.shape[0])], dim=1)        # [D, B]
+        acc = (g[:rows, :cols].double() @ b_hat_t.t())[None]                                      # 2^k sum_j G_ij b_hat_j
+        if out is not None:
+            out.copy_(acc)
+            return out
+        return acc
+
     def pair_bwd(self, a_s, b_s, a_t, b_t, bt_all, a_s_inv, b_s_inv, a_t_inv, b_t_inv, coef_row, coef_col, bounds, up,
                  temperature, g_out, extra=False, row_offset=0):
         ups = self._ups(up)

@@ -128,6 +128,15 @@ def test_retrieval_metrics_sharded_world2_gloo():
 # ----------------------------------------------------------------------------------------------
 # the pipeline flow (distillclip_b200/pipeline.py): stage boundaries, slot layout, exchanges, buffer-set bookkeeping
 # ----------------------------------------------------------------------------------------------
+@pytest.fixture(params=["pair", "split"])
+def flow(request):
+    """Both backward flows of pipeline.backward_gemms: the fused pair kernel, and the split flow (gradient tiles first, then the
+    text-side GEMM, then the image-side GEMM) -- with the float64 engine double."""
+    DoubleEngine.split = request.param == "split"
+    yield request.param
+    DoubleEngine.split = False
+
+
 def _run_pipeline(g, weights, ups, group=None, rows=slice(None), hard_only=False, extra=False):
     from distillclip_b200 import pipeline as pl
     T = float(g["temperature"])
@@ -141,7 +150,7 @@ def _run_pipeline(g, weights, ups, group=None, rows=slice(None), hard_only=False
 
 
 @pytest.mark.parametrize("name", CLIP)
-def test_pipeline_cos_diff_and_logits_mse_from_embeddings(name):
+def test_pipeline_cos_diff_and_logits_mse_from_embeddings(name, flow):
     """CLIPCosDiff (clip_cos_diff.py:5-23) and LogitsMSE (logits_mse.py:9-10) from the same tiles: values = the reference on
     materialised logits (0.5 (i2t + t2i), _loss.py:138-145); gradients incl. the diagonal term and exact off-diagonal set."""
     g = golden(name)
@@ -165,7 +174,7 @@ def test_pipeline_cos_diff_and_logits_mse_from_embeddings(name):
 
 
 @pytest.mark.parametrize("name", CLIP)
-def test_pipeline_decomposition_matches_reference_golden(name):
+def test_pipeline_decomposition_matches_reference_golden(name, flow):
     g = golden(name)
     one = torch.tensor(1.0)
     out, gi, gt, _, _ = _run_pipeline(g, (1.0, 0.0, 1.0, 1.0), (one, None, None))
@@ -178,7 +187,7 @@ def test_pipeline_decomposition_matches_reference_golden(name):
     assert rel_l2(gt.numpy(), g["dsoft_txt_f64"]) <= 1e-8
 
 
-def test_pipeline_weighting_and_upstream_routes():
+def test_pipeline_weighting_and_upstream_routes(flow):
     """out = {hard, soft, hard s_h, soft s_s, p_h hard s_h + p_s soft s_s} (reference _loss.py:231-234); gradients for an
     upstream on `total` plus one on the scaled soft term = the oracle with the combined weights."""
     g = golden(CLIP[1])
@@ -193,7 +202,7 @@ def test_pipeline_weighting_and_upstream_routes():
     assert rel_l2(gi.numpy(), ref["d_img"]) <= 1e-8 and rel_l2(gt.numpy(), ref["d_txt"]) <= 1e-8
 
 
-def test_pipeline_hard_only_and_buffer_sets():
+def test_pipeline_hard_only_and_buffer_sets(flow):
     from distillclip_b200 import pipeline as pl
     g = golden(CLIP[0])
     out, gi, gt, xc, saved = _run_pipeline(g, (1.0, 0.0, 1.0, 1.0), (torch.tensor(1.0), None, None), hard_only=True)
@@ -211,9 +220,10 @@ def test_pipeline_hard_only_and_buffer_sets():
     assert rel_l2(gi2.numpy(), g["dhard_img_f64"]) <= 1e-9
 
 
-def _pipeline_worker(rank, world, port, name, q):
+def _pipeline_worker(rank, world, port, name, q, split=False):
     import torch.distributed as dist
     sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    DoubleEngine.split = split
     dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
     from distillclip_b200 import pipeline as pl
     g = golden(name)
@@ -229,8 +239,8 @@ def _pipeline_worker(rank, world, port, name, q):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("name,world", [("clip_b24_d32_t2", 2), ("clip_b40_d64_t4", 2), ("clip_b24_d32_t2", 3)])
-def test_pipeline_row_sharded_gloo(name, world):
+@pytest.mark.parametrize("name,world,split", [("clip_b24_d32_t2", 2, False), ("clip_b40_d64_t4", 2, True), ("clip_b24_d32_t2", 3, True)])
+def test_pipeline_row_sharded_gloo(name, world, split):
     """The pipeline's three exchanges (text rows, statistics slots, text-gradient partial sums) under gloo with the
     collective-based exchange: every rank obtains the global losses; gradients concatenate to the oracle's."""
     g = golden(name)
@@ -246,7 +256,7 @@ def test_pipeline_row_sharded_gloo(name, world):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = 29500 + (os.getpid() + 31 * world) % 2000
-    procs = [ctx.Process(target=_pipeline_worker, args=(r, world, port, name, q)) for r in range(world)]
+    procs = [ctx.Process(target=_pipeline_worker, args=(r, world, port, name, q, split)) for r in range(world)]
     for p in procs:
         p.start()
     res = sorted([q.get(timeout=120) for _ in range(world)], key=lambda x: x[0])
