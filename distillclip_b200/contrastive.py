@@ -277,6 +277,11 @@ class CudaEngine:
     split_backward = os.environ.get("DCB_BWD_SPLIT", "auto")
     split_min_tiles = int(os.environ.get("DCB_BWD_SPLIT_MIN_TILES", "1024"))
 
+    def split_supported(self, dim: int) -> bool:
+        """The split flow has no TMEM-resident gradient accumulator, so it also covers 768 < D <= 1024 (the finish kernel's row
+        registers end there); it shares the stored-tiles switch with the pair flow."""
+        return bool(self.single_pass_backward and self.use_pair_kernel and dim % 8 == 0 and 8 <= dim <= 1024)
+
     def use_split(self, rows: int, cols: int) -> bool:
         if self.split_backward in ("0", "1"):
             return self.split_backward == "1"
@@ -626,7 +631,7 @@ def clip_contrastive(stu_img, stu_txt, tea_img=None, tea_txt=None, temperature=N
         hard, soft, cosd, lmse, total = ClipPipelineFn.apply(si, st, ti, tt, T, xc, weights, extra)
     else:
         if extra:
-            raise _lib.DistillClipB200Error("cos_diff / logits_mse from embeddings need the pipeline path (D <= 768, D % 8 == 0, "
+            raise _lib.DistillClipB200Error("cos_diff / logits_mse from embeddings need the pipeline path (D <= 1024, D % 8 == 0, "
                                             "per-rank batch a multiple of 128 when sharded); use the logits modules otherwise")
         hard, soft = ClipContrastiveFn.apply(si, st, ti, tt, T, group)
         hard, soft = hard * sc[0], soft * sc[1]

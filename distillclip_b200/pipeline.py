@@ -442,7 +442,9 @@ def check_equal_batches(group, b_local: int, device) -> None:
 # forward / backward
 # ==============================================================================================
 def pipeline_supported(engine, xc, b_local: int, dim: int) -> bool:
-    if not engine.single_pass_supported(dim):
+    """D <= 768: either backward flow; 768 < D <= 1024: the split flow only (the fused pair kernel keeps the whole [rows, D]
+    gradient accumulator in TMEM, which ends at D = 768)."""
+    if not (engine.single_pass_supported(dim) or (getattr(engine, "split_supported", None) and engine.split_supported(dim))):
         return False
     return xc.world == 1 or b_local % 128 == 0          # logit tiles must not straddle two ranks' b_hatT blocks
 
@@ -614,7 +616,7 @@ def backward_gemms(engine, v, ups, want_txt=True):
         else:
             v["acc_b"] = engine.col_acc_from_g(g, v["at"], b_local, b, dim)
 
-    if getattr(engine, "use_split", None) and engine.use_split(b_local, b):
+    if getattr(engine, "use_split", None) and (engine.use_split(b_local, b) or not engine.single_pass_supported(dim)):
         # split flow: recompute -> fp16 G tiles; both towers' gradients are GEMMs over the stored tiles.  The text-side GEMM goes
         # first: its NVLink stores and the barrier that follows them overlap the (local) image-side GEMM
         engine.g_tiles(si, s.st_all, v["ti"], s.tt_all, v["si_inv"], s.st_inv_all, v["ti_inv"], s.tt_inv_all, v["coef_row"],

@@ -40,7 +40,8 @@ def _one(v=1.0):
 
 @pytest.mark.parametrize("b,d,T,dtype", [(256, 512, 2.0, torch.bfloat16), (384, 768, 4.0, torch.bfloat16),
                                          (200, 136, 0.5, torch.bfloat16), (130, 72, 1.0, torch.bfloat16),
-                                         (256, 512, 2.0, torch.float16), (1000, 64, 2.0, torch.bfloat16)])
+                                         (256, 512, 2.0, torch.float16), (1000, 64, 2.0, torch.bfloat16),
+                                         (384, 1024, 2.0, torch.bfloat16), (200, 896, 1.0, torch.bfloat16)])
 def test_pipeline_single_gpu_vs_oracle(cuda_device, b, d, T, dtype):
     from distillclip_b200 import contrastive as ct, pipeline as pl
     si, st, ti, tt = synth(b, d, b + d, dtype)
@@ -212,7 +213,7 @@ class VirtualExchange:
 
 
 @pytest.mark.parametrize("chunked", [True, False])
-@pytest.mark.parametrize("R,b,d,T,teacher", [(4, 512, 256, 2.0, True), (2, 768, 768, 1.0, True), (8, 1024, 64, 2.0, True),
+@pytest.mark.parametrize("R,b,d,T,teacher", [(4, 512, 256, 2.0, True), (2, 768, 768, 1.0, True), (8, 1024, 64, 2.0, True), (2, 512, 1024, 2.0, True),
                                              (3, 384, 512, 2.0, False)])
 def test_pipeline_virtual_ranks(cuda_device, R, b, d, T, teacher, chunked):
     """Every kernel's multi-rank path on one GPU; the result must equal the single-process global-batch oracle
