@@ -272,10 +272,10 @@ class CudaEngine:
 
     #: split backward (csrc/clip_bwd_g.cu): recompute -> fp16 G tiles, then one tcgen05 GEMM per tower over the stored tiles,
     #: instead of the pair kernel that fuses the image-side GEMM into the recompute.  "auto": when the local block of the
-    #: logit matrix has at least `split_min_tiles` 128 x 128 tiles (measured: 4 % faster at 4096 x 4096 x 512 already; below that the
-    #: fused kernel saves a launch)
+    #: logit matrix has at least `split_min_tiles` 128 x 128 tiles (measured at D = 512: 4096 x 4096 4 % faster, 2048 x 4096 8 %, 1024 x 4096 4 %;
+    #: below that the fused kernel saves a launch)
     split_backward = os.environ.get("DCB_BWD_SPLIT", "auto")
-    split_min_tiles = int(os.environ.get("DCB_BWD_SPLIT_MIN_TILES", "1024"))
+    split_min_tiles = int(os.environ.get("DCB_BWD_SPLIT_MIN_TILES", "256"))
 
     def split_supported(self, dim: int) -> bool:
         """The split flow has no TMEM-resident gradient accumulator, so it also covers 768 < D <= 1024 (the finish kernel's row
