@@ -213,32 +213,26 @@ __global__ void __launch_bounds__(256) clip_post1_kernel(const __grid_constant__
         p.coef_row[(size_t)p.rows + r] = my;
         p.coef_row[(size_t)2 * p.rows + r] = mz;
     }
-    // ---- columns: this rank's share of the column sums, to every rank's slot.  The four statistics' loads of four row blocks
-    // are issued together (16 in flight per thread: one statistic at a time left the kernel at 1.4 TB/s, ncu r02); every sum
-    // still runs over the row blocks in order, in double (same bits as before)
+    // ---- columns: this rank's share of the column sums, to every rank's slot
     if (t < p.cols) {
-        double a[4] = {0.0, 0.0, 0.0, 0.0};
-        const float* __restrict__ src = p.col_part + t;
-        const size_t stride = (size_t)4 * p.cols;
-        int rb = 0;
-        for (; rb + 4 <= p.row_blocks; rb += 4) {
-            float v[4][4];
-#pragma unroll
-            for (int kk = 0; kk < 4; ++kk)
-#pragma unroll
-                for (int u = 0; u < 4; ++u) v[kk][u] = kk < p.n_stats ? src[(size_t)(rb + u) * stride + (size_t)kk * p.cols] : 0.f;
-#pragma unroll
-            for (int kk = 0; kk < 4; ++kk)
-#pragma unroll
-                for (int u = 0; u < 4; ++u) a[kk] += (double)v[kk][u];
-        }
-        for (; rb < p.row_blocks; ++rb)
-#pragma unroll
-            for (int kk = 0; kk < 4; ++kk)
-                if (kk < p.n_stats) a[kk] += (double)src[(size_t)rb * stride + (size_t)kk * p.cols];
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) {
-            const float f = (float)a[kk];
+            double a = 0.0;
+            if (kk < p.n_stats) {
+                const float* __restrict__ src = p.col_part + (size_t)kk * p.cols + t;
+                const size_t stride = (size_t)4 * p.cols;
+                int rb = 0;
+                for (; rb + 4 <= p.row_blocks; rb += 4) {
+                    const float a0 = src[(size_t)rb * stride], a1 = src[(size_t)(rb + 1) * stride];
+                    const float a2 = src[(size_t)(rb + 2) * stride], a3 = src[(size_t)(rb + 3) * stride];
+                    a += (double)a0;
+                    a += (double)a1;
+                    a += (double)a2;
+                    a += (double)a3;
+                }
+                for (; rb < p.row_blocks; ++rb) a += (double)src[(size_t)rb * stride];
+            }
+            const float f = (float)a;
             for (int d = 0; d < p.n_dest; ++d) p.dest[d][(size_t)kk * p.cols + t] = f;
         }
     }
